@@ -1,0 +1,193 @@
+// Generic bit-field decode/encode kernels and their C entry points.
+// sm_100a only.  Streaming, HBM-bound: no tensor cores by design.
+#include <string>
+#include <vector>
+#include "bb_runtime.cuh"
+#include "bb_bitfield_plan.h"
+
+namespace bb {
+
+constexpr int kBlock = 256;
+constexpr int kCtasPerSm = 8;       // 2048 resident threads per SM
+
+// The decode table lives in shared memory (see DecodeLut): built once per
+// CTA from the per-code levels in the kernel parameters; the grid is sized to
+// the machine and strides over the items, so the build cost is amortised.
+template <int BPS, int CODEC, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
+    using Lut = DecodeLut<BPS>;
+    __shared__ __align__(16) float lut[CODEC == CODEC_LEVELS ? Lut::kFloats : 2];
+    if (CODEC == CODEC_LEVELS) {
+        for (int i = threadIdx.x; i < Lut::kFloats; i += kBlock)
+            lut[i] = Lut::value(lv.v, i);
+        __syncthreads();
+    }
+    const uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < p.nitems;
+         item += stride) {
+        if (MODE == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(p, lut, item);
+        else if (MODE == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(p, lut, item);
+        else if (MODE == MODE_RUN) dec_run<BPS, CODEC>(p, lut, item);
+        else dec_scalar<BPS, CODEC>(p, lut, item);
+        if (item + stride < item) break;       // 32-bit wrap guard
+    }
+}
+
+template <typename T, int BPS, int QUANT, int MODE>
+__global__ void __launch_bounds__(kBlock)
+k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
+    const uint32_t stride = gridDim.x * kBlock;
+    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < p.nitems;
+         item += stride) {
+        if (MODE == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(p, c, item);
+        else if (MODE == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(p, c, item);
+        else if (MODE == MODE_RUN) enc_word<T, BPS, QUANT, true>(p, c, item);
+        else enc_word<T, BPS, QUANT, false>(p, c, item);
+        if (item + stride < item) break;
+    }
+}
+
+template <int BPS, int CODEC>
+static int launch_decode(const std::vector<DecLaunch> &launches,
+                         const float *levels_host, cudaStream_t stream) {
+    LevelTable<BPS> lv;
+    for (int i = 0; i < (1 << BPS); ++i)
+        lv.v[i] = (CODEC == CODEC_LEVELS && levels_host) ? levels_host[i] : 0.f;
+    for (const DecLaunch &l : launches) {
+        unsigned grid = stream_grid(l.g.nitems, kBlock, kCtasPerSm);
+        switch (l.mode) {
+        case MODE_ROWGROUP4:
+            k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP4>
+                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+            break;
+        case MODE_ROWGROUP2:
+            k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP2>
+                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+            break;
+        case MODE_RUN:
+            k_decode_bitfield<BPS, CODEC, MODE_RUN>
+                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+            break;
+        default:
+            k_decode_bitfield<BPS, CODEC, MODE_SCALAR>
+                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+        }
+        BB_CHECK_LAUNCH("bb_decode_bitfield launch");
+    }
+    return BB_OK;
+}
+
+template <typename T, int BPS, int QUANT>
+static int launch_encode(const std::vector<EncLaunch> &launches,
+                         cudaStream_t stream) {
+    static const QuantConsts<T> consts = make_quant_consts<T>();
+    for (const EncLaunch &l : launches) {
+        unsigned grid = stream_grid(l.g.nitems, kBlock, kCtasPerSm);
+        switch (l.mode) {
+        case MODE_ROWGROUP4:
+            k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP4>
+                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+            break;
+        case MODE_ROWGROUP2:
+            k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP2>
+                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+            break;
+        case MODE_RUN:
+            k_encode_bitfield<T, BPS, QUANT, MODE_RUN>
+                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+            break;
+        default:
+            k_encode_bitfield<T, BPS, QUANT, MODE_SCALAR>
+                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+        }
+        BB_CHECK_LAUNCH("bb_encode_bitfield launch");
+    }
+    return BB_OK;
+}
+
+template <typename T>
+static int dispatch_encode(int bps, int quantiser,
+                           const std::vector<EncLaunch> &l, cudaStream_t s) {
+    if (quantiser == BB_QUANT_OFFSET_BINARY) {
+        switch (bps) {
+        case 1: return launch_encode<T, 1, QUANT_OFFSET>(l, s);
+        case 2: return launch_encode<T, 2, QUANT_OFFSET>(l, s);
+        case 4: return launch_encode<T, 4, QUANT_OFFSET>(l, s);
+        case 8: return launch_encode<T, 8, QUANT_OFFSET>(l, s);
+        }
+    } else if (quantiser == BB_QUANT_MARK5B) {
+        switch (bps) {
+        case 1: return launch_encode<T, 1, QUANT_MARK5B>(l, s);
+        case 2: return launch_encode<T, 2, QUANT_MARK5B>(l, s);
+        }
+    } else if (quantiser == BB_QUANT_SINT) {
+        switch (bps) {
+        case 4: return launch_encode<T, 4, QUANT_SINT>(l, s);
+        case 8: return launch_encode<T, 8, QUANT_SINT>(l, s);
+        }
+    }
+    return set_error(BB_ERR_UNSUPPORTED,
+                     "cannot encode data with %d bits (quantiser %d)", bps,
+                     quantiser);
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_decode_bitfield(
+    const void *src, const int64_t *unit_offset, int64_t nset, int32_t nthread,
+    int64_t payload_nbytes, int32_t bps, int32_t nelem, int32_t complex_data,
+    int32_t codec, const float *levels_host, float fill_value,
+    int64_t sample_start, int64_t nsample, float *out, void *stream) {
+    if (!src || !unit_offset || !out)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(out, 16) || !aligned(src, 4))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "out must be 16-byte and src 4-byte aligned");
+    if (codec == BB_CODEC_LEVELS && !levels_host)
+        return set_error(BB_ERR_ARGUMENT, "levels_host required");
+    std::vector<DecLaunch> launches;
+    std::string err;
+    if (!plan_decode(src, unit_offset, nset, nthread, payload_nbytes, bps,
+                     nelem, complex_data, fill_value, sample_start, nsample,
+                     out, launches, err))
+        return set_error(BB_ERR_ARGUMENT, "%s", err.c_str());
+    cudaStream_t s = as_stream(stream);
+    if (codec == BB_CODEC_LEVELS) {
+        switch (bps) {
+        case 1: return launch_decode<1, CODEC_LEVELS>(launches, levels_host, s);
+        case 2: return launch_decode<2, CODEC_LEVELS>(launches, levels_host, s);
+        case 4: return launch_decode<4, CODEC_LEVELS>(launches, levels_host, s);
+        case 8: return launch_decode<8, CODEC_LEVELS>(launches, levels_host, s);
+        }
+    } else if (codec == BB_CODEC_SINT) {
+        switch (bps) {
+        case 4: return launch_decode<4, CODEC_SINT>(launches, nullptr, s);
+        case 8: return launch_decode<8, CODEC_SINT>(launches, nullptr, s);
+        }
+    }
+    return set_error(BB_ERR_UNSUPPORTED, "no decoder for bps=%d codec=%d", bps,
+                     codec);
+}
+
+extern "C" int bb_encode_bitfield(
+    const void *in, int32_t in_dtype, void *dst, const int64_t *unit_offset,
+    int64_t nset, int32_t nthread, int64_t payload_nbytes, int32_t bps,
+    int32_t nelem, int32_t quantiser, void *stream) {
+    if (!in || !dst || !unit_offset)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(in, 16) || !aligned(dst, 4))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "in must be 16-byte and dst 4-byte aligned");
+    std::vector<EncLaunch> launches;
+    std::string err;
+    if (!plan_encode(in, dst, unit_offset, nset, nthread, payload_nbytes, bps,
+                     nelem, launches, err))
+        return set_error(BB_ERR_ARGUMENT, "%s", err.c_str());
+    cudaStream_t s = as_stream(stream);
+    if (in_dtype == BB_F32) return dispatch_encode<float>(bps, quantiser, launches, s);
+    if (in_dtype == BB_F64) return dispatch_encode<double>(bps, quantiser, launches, s);
+    return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+}

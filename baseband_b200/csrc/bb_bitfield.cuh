@@ -1,0 +1,348 @@
+// Generic LSB-first bit-field codec: per-thread bodies.
+//
+// Logical layout (see include/baseband_b200.h, bb_decode_bitfield):
+//   unit (set, slot): nword 32-bit words = codes of BPS bits, LSB first, in
+//                     order [time][E]   (E = nelem)
+//   out:              [row][slot][E] float32, row = set*spf + t - sample_start
+//
+// Three work decompositions, chosen by the launcher:
+//   ROWGROUP<G>  E*G == 4, nthread % G == 0.  A thread takes word k of G
+//                neighbouring slots and writes, for each time in that word, one
+//                float4 covering the G slots.  Lanes are ordered (group
+//                fastest, then word) so every warp store covers whole rows.
+//                This is the VDIF multi-thread single-channel path (C1, C2).
+//   RUN          nthread == 1, or E a power of two >= 4.  Output-centric: a
+//                thread owns one float4 of the output (4 consecutive codes of
+//                one unit), so a warp store is 512 contiguous bytes.
+//   SCALAR       anything else: one output element per thread.
+#pragma once
+#include "bb_common.cuh"
+#include "bb_quant.cuh"
+
+namespace bb {
+
+enum { CODEC_LEVELS = 0, CODEC_SINT = 1 };
+
+template <int BPS>
+struct LevelTable { float v[1 << BPS]; };
+
+// Decode look-up table as the kernels use it (shared memory on the device).
+// For 1 and 2 bit the table is indexed by TWO adjacent codes and yields both
+// values at once: 2 bit -> 16 entries x 8 B = 128 B, one entry per pair of
+// banks, so a warp-wide LDS.64 never has a bank conflict; 1 bit -> 4 entries.
+// 4 and 8 bit are indexed by one code (16 entries: conflict free).
+template <int BPS>
+struct DecodeLut {
+    static constexpr int kPair = BPS <= 2;
+    static constexpr int kEntries = kPair ? (1 << (2 * BPS)) : (1 << BPS);
+    static constexpr int kFloats = kPair ? 2 * kEntries : kEntries;
+    // entry i of the table built from per-code levels
+    static BB_HD float value(const float *levels, int i) {
+        if (kPair) {
+            int entry = i >> 1, which = i & 1;
+            int code = which ? (entry >> BPS) : (entry & ((1 << BPS) - 1));
+            return levels[code];
+        }
+        return levels[i];
+    }
+};
+
+// ------------------------------------------------------------------ decode
+struct DecGeom {
+    const uint8_t *src;
+    const long long *unit_offset;   // [nset * nthread] for this launch
+    float *out;                     // row 0 of the whole call
+    long long row_base;             // row of (set 0, t 0) of this launch
+    long long nsample;              // valid rows are [0, nsample)
+    uint32_t nset, nthread, nelem, nword;
+    uint32_t tpw;                   // times per word (ROWGROUP)
+    uint32_t spf;                   // samples (times) per unit
+    uint32_t nitems;
+    uint32_t ngroup;                // nthread / G
+    int32_t log2_nelem;             // RUN with nthread > 1
+    uint32_t complex_fill;
+    float fill;
+    FastDiv div_nword, div_ngroup, div_rowlen, div_spf, div_nelem, div_unitlen;
+};
+
+template <int BPS>
+BB_HD float sint_code(uint32_t w, uint32_t pos) {
+    return (float)((int32_t)(w << (32 - BPS - pos)) >> (32 - BPS));
+}
+
+// Values of codes 2j and 2j+1 of word w.
+template <int BPS, int CODEC>
+BB_HD F2 decode_pair(uint32_t w, uint32_t j, const float *lut) {
+    F2 r;
+    if (CODEC == CODEC_SINT) {
+        r.x = sint_code<BPS>(w, 2 * j * BPS);
+        r.y = sint_code<BPS>(w, (2 * j + 1) * BPS);
+    } else if (BPS <= 2) {
+        uint32_t idx = (w >> (2 * BPS * j)) & ((1u << (2 * BPS)) - 1u);
+        r = reinterpret_cast<const F2 *>(lut)[idx];
+    } else {
+        r.x = lut[(w >> (2 * j * BPS)) & ((1u << BPS) - 1u)];
+        r.y = lut[(w >> ((2 * j + 1) * BPS)) & ((1u << BPS) - 1u)];
+    }
+    return r;
+}
+
+template <int BPS, int CODEC>
+BB_HD float decode_one(uint32_t w, uint32_t c, const float *lut) {
+    F2 r = decode_pair<BPS, CODEC>(w, c >> 1, lut);
+    return (c & 1u) ? r.y : r.x;
+}
+
+BB_HD uint32_t load_u32(const uint8_t *p) {
+    return *reinterpret_cast<const uint32_t *>(p);
+}
+
+// ROWGROUP: item = lw * ngroup + g, lw = word index over the launch's sets.
+template <int BPS, int CODEC, int G>
+BB_HD void dec_rowgroup(const DecGeom &p, const float *lut, uint32_t item) {
+    constexpr int E = 4 / G;
+    constexpr int CPW = 32 / BPS;          // codes per word
+    constexpr int TPW = CPW / E;           // times per word
+    uint32_t lw, g;
+    p.div_ngroup.divmod(item, lw, g);
+    uint32_t set, k;
+    p.div_nword.divmod(lw, set, k);
+    const long long row0 = p.row_base + (long long)lw * TPW;
+    if (row0 + TPW <= 0 || row0 >= p.nsample) return;
+    uint32_t w[G];
+    bool all_ok = true;
+    long long off[G];
+    const long long *uo = p.unit_offset + (size_t)set * p.nthread + g * G;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        off[j] = uo[j];
+        all_ok = all_ok && off[j] >= 0;
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j)
+        w[j] = off[j] >= 0 ? load_u32(p.src + off[j] + 4ull * k) : 0u;
+    const size_t rowlen = (size_t)p.nthread * E;
+    float *dst = p.out + row0 * (long long)rowlen + g * 4;
+    if (all_ok && row0 >= 0 && row0 + TPW <= p.nsample) {
+        // Fast path: whole word inside the requested rows, every slot valid.
+        if (E == 1) {
+#pragma unroll
+            for (int m = 0; m < TPW / 2; ++m) {
+                F2 a = decode_pair<BPS, CODEC>(w[0], m, lut);
+                F2 b = decode_pair<BPS, CODEC>(w[1 % G], m, lut);
+                F2 c = decode_pair<BPS, CODEC>(w[2 % G], m, lut);
+                F2 d = decode_pair<BPS, CODEC>(w[3 % G], m, lut);
+                *reinterpret_cast<F4 *>(dst) = F4{a.x, b.x, c.x, d.x};
+                dst += rowlen;
+                *reinterpret_cast<F4 *>(dst) = F4{a.y, b.y, c.y, d.y};
+                dst += rowlen;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TPW; ++i) {
+                F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
+                F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
+                *reinterpret_cast<F4 *>(dst) = F4{a.x, a.y, b.x, b.y};
+                dst += rowlen;
+            }
+        }
+        return;
+    }
+    // Edge path: partial word at either end of the read, or invalid frames.
+    const float fill_im = p.complex_fill ? 0.f : p.fill;
+#pragma unroll 1
+    for (int i = 0; i < TPW; ++i, dst += rowlen) {
+        if (row0 + i < 0 || row0 + i >= p.nsample) continue;
+        F4 v;
+        if (E == 1) {
+            v.x = off[0] >= 0 ? decode_one<BPS, CODEC>(w[0], i, lut) : p.fill;
+            v.y = off[1 % G] >= 0 ? decode_one<BPS, CODEC>(w[1 % G], i, lut) : p.fill;
+            v.z = off[2 % G] >= 0 ? decode_one<BPS, CODEC>(w[2 % G], i, lut) : p.fill;
+            v.w = off[3 % G] >= 0 ? decode_one<BPS, CODEC>(w[3 % G], i, lut) : p.fill;
+        } else {
+            F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
+            F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
+            v.x = off[0] >= 0 ? a.x : p.fill;
+            v.y = off[0] >= 0 ? a.y : fill_im;
+            v.z = off[1 % G] >= 0 ? b.x : p.fill;
+            v.w = off[1 % G] >= 0 ? b.y : fill_im;
+        }
+        *reinterpret_cast<F4 *>(dst) = v;
+    }
+}
+
+// RUN: item = float4 index within the launch's block of rows.
+template <int BPS, int CODEC>
+BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
+    constexpr int CPW = 32 / BPS;
+    const uint32_t n = item * 4u;              // element index in the launch
+    const uint32_t rowlen = p.nthread * p.nelem;
+    long long gidx = p.row_base * (long long)rowlen + n;
+    if (gidx < 0 || gidx >= p.nsample * (long long)rowlen) return;
+    uint32_t set, pcode, slot;
+    if (p.nthread == 1) {
+        p.div_unitlen.divmod(n, set, pcode);     // unitlen = spf * nelem
+        slot = 0;
+    } else {
+        uint32_t row, rem, t;
+        p.div_rowlen.divmod(n, row, rem);
+        slot = rem >> p.log2_nelem;
+        uint32_t e = rem & (p.nelem - 1u);
+        p.div_spf.divmod(row, set, t);
+        pcode = (t << p.log2_nelem) + e;
+    }
+    long long off = p.unit_offset[(size_t)set * p.nthread + slot];
+    F4 v;
+    if (off >= 0) {
+        uint32_t w = load_u32(p.src + off + 4ull * (pcode / CPW));
+        uint32_t j = (pcode % CPW) >> 1;       // pair index, even
+        F2 a = decode_pair<BPS, CODEC>(w, j, lut);
+        F2 b = decode_pair<BPS, CODEC>(w, j + 1, lut);
+        v = F4{a.x, a.y, b.x, b.y};
+    } else {
+        const float fill_im = p.complex_fill ? 0.f : p.fill;
+        v = F4{p.fill, fill_im, p.fill, fill_im};
+    }
+    *reinterpret_cast<F4 *>(p.out + gidx) = v;
+}
+
+// SCALAR: item = element index within the launch's block of rows.
+template <int BPS, int CODEC>
+BB_HD void dec_scalar(const DecGeom &p, const float *lut, uint32_t item) {
+    constexpr int CPW = 32 / BPS;
+    const uint32_t rowlen = p.nthread * p.nelem;
+    long long gidx = p.row_base * (long long)rowlen + item;
+    if (gidx < 0 || gidx >= p.nsample * (long long)rowlen) return;
+    uint32_t row, rem, slot, e, set, t;
+    p.div_rowlen.divmod(item, row, rem);
+    p.div_nelem.divmod(rem, slot, e);
+    p.div_spf.divmod(row, set, t);
+    uint32_t pcode = t * p.nelem + e;
+    long long off = p.unit_offset[(size_t)set * p.nthread + slot];
+    float v;
+    if (off >= 0) {
+        uint32_t w = load_u32(p.src + off + 4ull * (pcode / CPW));
+        v = decode_one<BPS, CODEC>(w, pcode % CPW, lut);
+    } else {
+        v = (p.complex_fill && (e & 1u)) ? 0.f : p.fill;
+    }
+    p.out[gidx] = v;
+}
+
+// ------------------------------------------------------------------ encode
+struct EncGeom {
+    const void *in;                 // [nset*spf][nthread][nelem] T (whole call)
+    unsigned long long in_elem_offset;   // first element of this launch
+    uint8_t *dst;
+    const long long *unit_offset;
+    uint32_t nset, nthread, nelem, nword, spf, nitems, ngroup;
+    int32_t log2_nelem;
+    FastDiv div_nword, div_ngroup, div_nthread;
+};
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    float x, y, z, w;
+    static BB_HD Vec4 load(const float *p) {
+        F4 v = *reinterpret_cast<const F4 *>(p);
+        return {v.x, v.y, v.z, v.w};
+    }
+};
+template <> struct Vec4<double> {
+    double x, y, z, w;
+    static BB_HD Vec4 load(const double *p) {
+        D2 a = *reinterpret_cast<const D2 *>(p);
+        D2 b = *reinterpret_cast<const D2 *>(p + 2);
+        return {a.x, a.y, b.x, b.y};
+    }
+};
+
+BB_HD void store_u32(uint8_t *p, uint32_t v) {
+    *reinterpret_cast<uint32_t *>(p) = v;
+}
+
+template <typename T, int BPS, int QUANT, int G>
+BB_HD void enc_rowgroup(const EncGeom &p, const QuantConsts<T> &c,
+                        uint32_t item) {
+    constexpr int E = 4 / G;
+    constexpr int CPW = 32 / BPS;
+    constexpr int TPW = CPW / E;
+    uint32_t lw, g;
+    p.div_ngroup.divmod(item, lw, g);
+    uint32_t set, k;
+    p.div_nword.divmod(lw, set, k);
+    const size_t rowlen = (size_t)p.nthread * E;
+    const T *src = reinterpret_cast<const T *>(p.in) + p.in_elem_offset
+        + (size_t)lw * TPW * rowlen + g * 4;
+    uint32_t w[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) w[j] = 0u;
+#pragma unroll
+    for (int i = 0; i < TPW; ++i) {
+        Vec4<T> v = Vec4<T>::load(src + (size_t)i * rowlen);
+        uint32_t q0 = quantise<T, BPS, QUANT>(v.x, c);
+        uint32_t q1 = quantise<T, BPS, QUANT>(v.y, c);
+        uint32_t q2 = quantise<T, BPS, QUANT>(v.z, c);
+        uint32_t q3 = quantise<T, BPS, QUANT>(v.w, c);
+        if (E == 1) {
+            w[0] |= q0 << (i * BPS);
+            w[1 % G] |= q1 << (i * BPS);
+            w[2 % G] |= q2 << (i * BPS);
+            w[3 % G] |= q3 << (i * BPS);
+        } else {
+            w[0] |= (q0 | (q1 << BPS)) << (2 * i * BPS);
+            w[1 % G] |= (q2 | (q3 << BPS)) << (2 * i * BPS);
+        }
+    }
+    const long long *uo = p.unit_offset + (size_t)set * p.nthread + g * G;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        long long off = uo[j];
+        if (off >= 0) store_u32(p.dst + off + 4ull * k, w[j]);
+    }
+}
+
+// RUN / SCALAR: item = output word index over all units of the launch.
+template <typename T, int BPS, int QUANT, bool VEC>
+BB_HD void enc_word(const EncGeom &p, const QuantConsts<T> &c,
+                    uint32_t item) {
+    constexpr int CPW = 32 / BPS;
+    uint32_t unit, k, set, slot;
+    p.div_nword.divmod(item, unit, k);
+    p.div_nthread.divmod(unit, set, slot);
+    long long off = p.unit_offset[unit];
+    if (off < 0) return;
+    const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
+    const size_t rowlen = (size_t)p.nthread * p.nelem;
+    const size_t set_base = (size_t)set * p.spf * rowlen;
+    uint32_t w = 0u;
+    if (VEC) {
+#pragma unroll
+        for (int m = 0; m < CPW / 4; ++m) {
+            uint32_t pc = k * CPW + 4 * m;
+            size_t idx;
+            if (p.nthread == 1) {
+                idx = set_base + pc;
+            } else {
+                uint32_t t = pc >> p.log2_nelem, e = pc & (p.nelem - 1u);
+                idx = set_base + ((size_t)t * p.nthread + slot) * p.nelem + e;
+            }
+            Vec4<T> v = Vec4<T>::load(in + idx);
+            uint32_t f = quantise<T, BPS, QUANT>(v.x, c)
+                | (quantise<T, BPS, QUANT>(v.y, c) << BPS)
+                | (quantise<T, BPS, QUANT>(v.z, c) << (2 * BPS))
+                | (quantise<T, BPS, QUANT>(v.w, c) << (3 * BPS));
+            w |= f << (4 * m * BPS);
+        }
+    } else {
+        for (int i = 0; i < CPW; ++i) {
+            uint32_t pc = k * CPW + i;
+            uint32_t t = pc / p.nelem, e = pc % p.nelem;
+            size_t idx = set_base + ((size_t)t * p.nthread + slot) * p.nelem + e;
+            w |= quantise<T, BPS, QUANT>(in[idx], c) << (i * BPS);
+        }
+    }
+    store_u32(p.dst + off + 4ull * k, w);
+}
+
+}  // namespace bb

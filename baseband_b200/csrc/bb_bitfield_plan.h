@@ -1,0 +1,171 @@
+// Host-side planning for the bit-field codec: validates a call, picks the
+// work decomposition and splits it into launches whose item counts fit in 32
+// bits.  Pure C++ so the CPU emulation in tests/emu shares it.
+#pragma once
+#include <vector>
+#include <string>
+#include "bb_bitfield.cuh"
+
+namespace bb {
+
+enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3 };
+
+struct DecLaunch { int mode; DecGeom g; };
+struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
+
+inline bool plan_geometry(int64_t payload_nbytes, int bps, int nelem,
+                          int nthread, int64_t nset, uint32_t &nword,
+                          uint32_t &spf, std::string &err) {
+    if (!(bps == 1 || bps == 2 || bps == 4 || bps == 8)) {
+        err = "bps must be 1, 2, 4 or 8";
+        return false;
+    }
+    if (nelem < 1 || nthread < 1 || nset < 0 || payload_nbytes <= 0) {
+        err = "nelem, nthread >= 1, nset >= 0, payload_nbytes > 0 required";
+        return false;
+    }
+    if (payload_nbytes % 4) {
+        err = "payload_nbytes must be a multiple of 4";
+        return false;
+    }
+    int64_t bits = payload_nbytes * 8;
+    if (bits % ((int64_t)bps * nelem)) {
+        err = "payload does not hold a whole number of complete samples";
+        return false;
+    }
+    int64_t s = bits / ((int64_t)bps * nelem);
+    if (payload_nbytes / 4 > 0x3fffffff || s > 0x7fffffff) {
+        err = "payload too large for one unit; split it along time";
+        return false;
+    }
+    nword = (uint32_t)(payload_nbytes / 4);
+    spf = (uint32_t)s;
+    return true;
+}
+
+inline int pick_mode(int nelem, int nthread, bool aligned_rows) {
+    if (nthread > 1 && nelem == 1 && nthread % 4 == 0) return MODE_ROWGROUP4;
+    if (nthread > 1 && nelem == 2 && nthread % 2 == 0) return MODE_ROWGROUP2;
+    if (aligned_rows && (nthread == 1
+                         || (nelem % 4 == 0 && ilog2_exact(nelem) >= 0)))
+        return MODE_RUN;
+    return MODE_SCALAR;
+}
+
+inline bool plan_decode(const void *src, const int64_t *unit_offset,
+                        int64_t nset, int nthread, int64_t payload_nbytes,
+                        int bps, int nelem, int complex_data, float fill,
+                        int64_t sample_start, int64_t nsample, float *out,
+                        std::vector<DecLaunch> &launches, std::string &err) {
+    uint32_t nword, spf;
+    if (!plan_geometry(payload_nbytes, bps, nelem, nthread, nset, nword, spf,
+                       err))
+        return false;
+    if (sample_start < 0 || nsample < 0
+        || sample_start + nsample > nset * (int64_t)spf) {
+        err = "sample range outside the given frames";
+        return false;
+    }
+    if (nsample == 0) return true;
+    const int64_t rowlen = (int64_t)nthread * nelem;
+    const bool aligned_rows = (sample_start * rowlen) % 4 == 0
+        && (nsample * rowlen) % 4 == 0;
+    const int mode = pick_mode(nelem, nthread, aligned_rows);
+    const int cpw = 32 / bps;
+    int64_t first = sample_start / spf;
+    int64_t last = (sample_start + nsample + spf - 1) / spf;
+    // items per set and the 32-bit budget for one launch
+    uint64_t per_set;
+    uint32_t ngroup = 1;
+    if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
+        ngroup = nthread / (mode == MODE_ROWGROUP4 ? 4 : 2);
+        per_set = (uint64_t)nword * ngroup;
+    } else if (mode == MODE_RUN) {
+        per_set = (uint64_t)spf * rowlen / 4;
+    } else {
+        per_set = (uint64_t)spf * rowlen;
+    }
+    const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull : 0x7fffffffull;
+    if (per_set > budget) {
+        err = "one frame set is too large for a launch; split it along time";
+        return false;
+    }
+    int64_t max_sets = (int64_t)(budget / per_set);
+    for (int64_t s0 = first; s0 < last; s0 += max_sets) {
+        int64_t s1 = s0 + max_sets < last ? s0 + max_sets : last;
+        DecGeom g;
+        g.src = (const uint8_t *)src;
+        g.unit_offset = (const long long *)unit_offset + s0 * nthread;
+        g.out = out;
+        g.row_base = s0 * (int64_t)spf - sample_start;
+        g.nsample = nsample;
+        g.nset = (uint32_t)(s1 - s0);
+        g.nthread = nthread;
+        g.nelem = nelem;
+        g.nword = nword;
+        g.tpw = cpw / nelem ? cpw / nelem : 1;
+        g.spf = spf;
+        g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
+        g.ngroup = ngroup;
+        g.log2_nelem = ilog2_exact(nelem);
+        g.complex_fill = complex_data ? 1 : 0;
+        g.fill = fill;
+        g.div_nword = make_fastdiv(nword);
+        g.div_ngroup = make_fastdiv(ngroup);
+        g.div_rowlen = make_fastdiv((uint32_t)rowlen);
+        g.div_spf = make_fastdiv(spf);
+        g.div_nelem = make_fastdiv(nelem);
+        g.div_unitlen = make_fastdiv((uint32_t)((uint64_t)spf * nelem));
+        launches.push_back({mode, g});
+    }
+    return true;
+}
+
+inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
+                        int64_t nset, int nthread, int64_t payload_nbytes,
+                        int bps, int nelem, std::vector<EncLaunch> &launches,
+                        std::string &err) {
+    uint32_t nword, spf;
+    if (!plan_geometry(payload_nbytes, bps, nelem, nthread, nset, nword, spf,
+                       err))
+        return false;
+    if (nset == 0) return true;
+    const int64_t rowlen = (int64_t)nthread * nelem;
+    int mode = pick_mode(nelem, nthread, true);
+    uint64_t per_set;
+    uint32_t ngroup = 1;
+    if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
+        ngroup = nthread / (mode == MODE_ROWGROUP4 ? 4 : 2);
+        per_set = (uint64_t)nword * ngroup;
+    } else {
+        per_set = (uint64_t)nword * nthread;
+    }
+    if (per_set > 0x7fffffffull) {
+        err = "one frame set is too large for a launch; split it along time";
+        return false;
+    }
+    int64_t max_sets = (int64_t)(0x7fffffffull / per_set);
+    for (int64_t s0 = 0; s0 < nset; s0 += max_sets) {
+        int64_t s1 = s0 + max_sets < nset ? s0 + max_sets : nset;
+        EncGeom g;
+        g.in = in;
+        g.in_elem_offset = (unsigned long long)(s0 * (int64_t)spf * rowlen);
+        g.dst = (uint8_t *)dst;
+        g.unit_offset = (const long long *)unit_offset + s0 * nthread;
+        g.nset = (uint32_t)(s1 - s0);
+        g.nthread = nthread;
+        g.nelem = nelem;
+        g.nword = nword;
+        g.spf = spf;
+        g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
+        g.ngroup = ngroup;
+        g.log2_nelem = ilog2_exact(nelem);
+        g.div_nword = make_fastdiv(nword);
+        g.div_ngroup = make_fastdiv(ngroup);
+        g.div_nthread = make_fastdiv(nthread);
+        launches.push_back({mode, g});
+    }
+    return true;
+}
+
+}  // namespace bb

@@ -1,0 +1,93 @@
+// Shared helpers for the baseband_b200 kernels.
+//
+// The per-thread bodies of the streaming kernels are written as
+// host/device inline functions over plain structs so that the index
+// arithmetic can also be compiled by g++ for the CPU emulation used by
+// tests/test_emulation.py (test infrastructure; the shipped library only
+// contains the CUDA instantiations).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BB_HD __host__ __device__ __forceinline__
+#else
+#define BB_HD inline
+#endif
+
+namespace bb {
+
+struct alignas(16) F4 { float x, y, z, w; };
+struct alignas(16) D2 { double x, y; };
+struct alignas(8) F2 { float x, y; };
+
+BB_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+// Division of any 32-bit unsigned n by a runtime-constant d >= 1
+// (Granlund & Montgomery round-up method): 4 integer instructions.
+struct FastDiv {
+    uint32_t d, mul, sh1, sh2;
+    BB_HD uint32_t div(uint32_t n) const {
+        uint32_t t = umulhi32(mul, n);
+        return (t + ((n - t) >> sh1)) >> sh2;
+    }
+    BB_HD void divmod(uint32_t n, uint32_t &q, uint32_t &r) const {
+        q = div(n);
+        r = n - q * d;
+    }
+};
+
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                 // ceil(log2 d)
+    f.mul = (uint32_t)((((1ull << l) - d) << 32) / d + 1);
+    f.sh1 = l < 1 ? l : 1;
+    f.sh2 = l > 1 ? l - 1 : 0;
+    return f;
+}
+
+inline int ilog2_exact(uint32_t v) {            // -1 if not a power of two
+    if (v == 0 || (v & (v - 1))) return -1;
+    int l = 0;
+    while ((1u << l) < v) ++l;
+    return l;
+}
+
+// Arithmetic that must round exactly once per numpy ufunc (no FMA fusion).
+BB_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+BB_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+BB_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+BB_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+
+}  // namespace bb

@@ -1,0 +1,239 @@
+/*
+ * baseband_b200 — C ABI of the B200 (sm_100a) sample codec library.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * mhvk/baseband (reference paths below are relative to the reference
+ * checkout, `file:line`).  The reference is pure Python + numpy; each entry
+ * point replaces one family of numpy ufunc chains and is what a ctypes
+ * binding inside the reference's `_decoders` / `_encoders` tables, `Frame`
+ * classes and `StreamReaderBase.read` / `StreamWriterBase.write` would call
+ * (see INTEGRATION.md for the reference-side stubs).
+ *
+ * Conventions
+ *  - plain C types only; every buffer is caller-owned; the library never
+ *    allocates result memory and keeps no state besides the last error text.
+ *  - `src`, `dst`, `out`, `in`, `unit_offset`, `valid` ... are DEVICE
+ *    pointers unless the name ends in `_host`.
+ *  - `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream).
+ *    All work is stream-ordered; nothing synchronises the host.
+ *  - return value: BB_OK or a negative bb_status; `bb_last_error()` gives a
+ *    thread-local text.  No exceptions cross this boundary.
+ *  - "unit" = the payload of one frame (VDIF: one thread-frame).  A decode
+ *    call is handed a table `unit_offset[nset * nthread]` of byte offsets of
+ *    each payload inside `src`; a negative offset marks an invalid or missing
+ *    frame whose samples are replaced by `fill_value`
+ *    (baseband/base/frame.py:191-199).
+ *  - sample order and bit layouts are those of SURVEY.md appendix A; results
+ *    are bit-identical to the reference numpy path.
+ */
+#ifndef BASEBAND_B200_H
+#define BASEBAND_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+typedef enum bb_status {
+    BB_OK = 0,
+    BB_ERR_ARGUMENT = -1,     /* bad size / combination (ValueError upstream) */
+    BB_ERR_ALIGNMENT = -2,    /* pointer or offset not aligned as required */
+    BB_ERR_UNSUPPORTED = -3,  /* no such codec (KeyError upstream) */
+    BB_ERR_CUDA = -4          /* CUDA runtime error, see bb_last_error() */
+} bb_status;
+
+/* Code -> value rule for the generic bit-field codec. */
+typedef enum bb_codec {
+    BB_CODEC_LEVELS = 0,  /* value = levels[code]; VDIF offset binary
+                             (baseband/vdif/payload.py:25-103), Mark 5B
+                             sign/magnitude (baseband/mark5b/payload.py:27-94),
+                             VDIF 8 bit (baseband/base/encoding.py:131-144) */
+    BB_CODEC_SINT = 1     /* value = two's complement integer of the code;
+                             GSB nibbles (baseband/gsb/payload.py:24-42),
+                             DADA/GUPPI/GSB int8 (dada/payload.py:13-14) */
+} bb_codec;
+
+/* Quantiser family for encoding. */
+typedef enum bb_quantiser {
+    BB_QUANT_OFFSET_BINARY = 0, /* baseband/base/encoding.py:63-128,147-158
+                                   packed LSB first, vdif/payload.py:77-114 */
+    BB_QUANT_MARK5B = 1,        /* 1 bit = signbit, 2 bit codes 1<->2 swapped
+                                   (baseband/mark5b/payload.py:86-106) */
+    BB_QUANT_SINT = 2           /* clip(rint(v)) two's complement; 4 and 8 bit
+                                   (gsb/payload.py:45-53, guppi/payload.py:17) */
+} bb_quantiser;
+
+typedef enum bb_dtype { BB_F32 = 0, BB_F64 = 1 } bb_dtype;
+
+/* ---------------------------------------------------------------- runtime */
+int bb_abi_version(void);
+const char *bb_last_error(void);
+int bb_device_count(void);
+int bb_set_device(int device);
+int bb_device_sm_count(int device);
+/* Raw memory/stream helpers so that a host without torch can drive the
+ * library (the Python layer uses torch allocations and these copies). */
+int bb_malloc(void **ptr, int64_t nbytes);
+int bb_free(void *ptr);
+int bb_host_alloc(void **ptr_host, int64_t nbytes);      /* pinned */
+int bb_host_free(void *ptr_host);
+int bb_host_register(void *ptr_host, int64_t nbytes);    /* pin in place */
+int bb_host_unregister(void *ptr_host);
+int bb_memcpy_h2d(void *dst, const void *src_host, int64_t nbytes, void *stream);
+int bb_memcpy_d2h(void *dst_host, const void *src, int64_t nbytes, void *stream);
+int bb_memset(void *dst, int value, int64_t nbytes, void *stream);
+int bb_stream_create(void **stream);
+int bb_stream_destroy(void *stream);
+int bb_stream_synchronize(void *stream);
+
+/* ------------------------------------------------- generic bit-field codec
+ * Replaces: VDIF `decode_1bit/2bit/4bit` (baseband/vdif/payload.py:69-103),
+ * `decode_8bit` (baseband/base/encoding.py:131-144), Mark 5B
+ * `decode_1bit/2bit` (baseband/mark5b/payload.py:78-94), GSB
+ * `decode_4bit/8bit` (baseband/gsb/payload.py:24-42), DADA `decode_8bit`
+ * (baseband/dada/payload.py:13-14), the `.view(dtype).reshape` of
+ * `PayloadBase._decode/__getitem__` (baseband/base/payload.py:314-330), the
+ * per-frame validity fill (baseband/base/frame.py:191-199) and the thread
+ * interleave of `VDIFFrameSet.__getitem__` (baseband/vdif/frame.py:402-434),
+ * batched over all frames a `StreamReaderBase.read` call touches
+ * (baseband/base/base.py:919-969).
+ *
+ * Layout: a unit holds `payload_nbytes` bytes = codes of `bps` bits, LSB
+ * first, in order [time][nelem]; nelem = nchan * (2 if complex).
+ * out[(set*spf + t - sample_start) * nthread * nelem + slot * nelem + e]
+ *   for rows 0 <= set*spf + t - sample_start < nsample,
+ * spf = payload_nbytes*8 / (bps*nelem).  complex_data only affects the fill
+ * (fill_value + 0j).  levels_host: 2^bps floats (BB_CODEC_LEVELS), ignored
+ * for BB_CODEC_SINT.  Requirements: payload offsets and payload_nbytes
+ * multiples of 4; out 16-byte aligned.
+ */
+int bb_decode_bitfield(const void *src, const int64_t *unit_offset,
+                       int64_t nset, int32_t nthread, int64_t payload_nbytes,
+                       int32_t bps, int32_t nelem, int32_t complex_data,
+                       int32_t codec, const float *levels_host,
+                       float fill_value, int64_t sample_start,
+                       int64_t nsample, float *out, void *stream);
+
+/* Inverse: quantise + pack `in` (same logical layout as `out` above, float32
+ * or float64 — arithmetic is done in the input width exactly as numpy does,
+ * baseband/base/encoding.py:63-128) into the payload of every unit with a
+ * non-negative offset.  Whole frames only (sample_start = 0, nsample =
+ * nset*spf).  Replaces `encode_*` (baseband/vdif/payload.py:77-114,
+ * baseband/mark5b/payload.py:86-106, baseband/gsb/payload.py:45-53),
+ * `PayloadBase._encode/__setitem__` (baseband/base/payload.py:317-348),
+ * `VDIFFrameSet.fromdata` thread split (baseband/vdif/frame.py:288-289) and
+ * the per-frame loop of `StreamWriterBase.write`
+ * (baseband/base/base.py:1276-1308). */
+int bb_encode_bitfield(const void *in, int32_t in_dtype, void *dst,
+                       const int64_t *unit_offset, int64_t nset,
+                       int32_t nthread, int64_t payload_nbytes, int32_t bps,
+                       int32_t nelem, int32_t quantiser, void *stream);
+
+/* ------------------------------------------------------------------ Mark 4
+ * Replaces `reorder32/64/64_Ft` + the five `decode_*`/`encode_*` functions
+ * (baseband/mark4/payload.py:48-69, :122-300), keyed like
+ * `Mark4Payload._decoders` (baseband/mark4/payload.py:333-342) by
+ * (nchan, fanout, ft) with ntrack = nchan*2*fanout, plus the
+ * header-overwritten-sample fill of `Mark4Frame.__getitem__`
+ * (baseband/mark4/frame.py:239-263): each frame contributes
+ * spf = 20000*fanout rows of which the first 160*fanout are fill_value.
+ * unit_offset[frame] = byte offset of the payload (frame start + ntrack*20),
+ * negative = invalid frame (all fill).  levels_host: 4 floats indexed
+ * 2*sign+magnitude.  out[(frame*spf + t - sample_start)*nchan + c]. */
+int bb_mark4_decode(const void *src, const int64_t *unit_offset,
+                    int64_t nframe, int32_t nchan, int32_t fanout, int32_t ft,
+                    const float *levels_host, float fill_value,
+                    int64_t sample_start, int64_t nsample, float *out,
+                    void *stream);
+/* Inverse for whole frames; rows falling in the header region are ignored. */
+int bb_mark4_encode(const void *in, int32_t in_dtype, void *dst,
+                    const int64_t *unit_offset, int64_t nframe, int32_t nchan,
+                    int32_t fanout, int32_t ft, void *stream);
+/* Payload-only variants (Mark4Payload.data / .fromdata): nword track words,
+ * no header region.  words/out are device pointers. */
+int bb_mark4_decode_words(const void *words, int64_t nword, int32_t nchan,
+                          int32_t fanout, int32_t ft, const float *levels_host,
+                          float *out, void *stream);
+int bb_mark4_encode_words(const void *in, int32_t in_dtype, void *words,
+                          int64_t nword, int32_t nchan, int32_t fanout,
+                          int32_t ft, void *stream);
+
+/* -------------------------------------------- int8 with an axis transpose
+ * GUPPI channels-first payloads (baseband/guppi/payload.py:90-110): stored
+ * [chan][time][pol][re,im], decoded (time, pol, chan); and MKBF heaps
+ * (baseband/dada/payload.py:54-89).  Both are a batched 2-D transpose of
+ * `item_nbytes`-byte items (1 = real, 2 = complex) with int8 -> float32:
+ *   in  unit u: [nrow][ncol] items        (ncol fastest)
+ *   out unit u: [ncol_take][nrow] items   (nrow fastest)
+ * Output position of (unit u, column j): row-of-output =
+ *   out_col0[u] + j for j in [col_begin[u], col_end[u]) — this expresses the
+ * GUPPI overlap rule (baseband/guppi/base.py:203-206, :270-278;
+ * baseband/base/base.py:957-967): later frames skip their first `overlap`
+ * samples.  All three tables are device int64[nunit]; out_col0 counts output
+ * columns (= items of nrow) from `out`. */
+int bb_decode_int8_transposed(const void *src, const int64_t *unit_offset,
+                              int64_t nunit, int64_t nrow, int64_t ncol,
+                              int32_t item_nbytes, const int64_t *col_begin,
+                              const int64_t *col_end, const int64_t *out_col0,
+                              float *out, void *stream);
+int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
+                              const int64_t *unit_offset, int64_t nunit,
+                              int64_t nrow, int64_t ncol, int32_t item_nbytes,
+                              void *stream);
+
+/* ------------------------------------------------------- header batches
+ * VDIF: extract the bit-fields of baseband/vdif/header.py:529-542, :557-559
+ * (generic extractor baseband/base/header.py:35-87) for `nframe` headers at
+ * src + frame_offset[i] (or i*frame_stride if frame_offset is NULL) into
+ * fields[f * nframe + i], f indexing bb_vdif_field.  Then build the unit
+ * table of a regular stream: frames_per_set consecutive frames form a set
+ * (baseband/vdif/frame.py:201-243); slot = thread_slot[thread_id] (device
+ * int32[1024], -1 = thread not selected, baseband/vdif/base.py:464-490);
+ * unit_offset[set*nthread + slot] = payload offset, or -1 if invalid_data
+ * (baseband/vdif/frame.py:79-90).  *n_inconsistent (device int32) counts
+ * frames whose frame_nr/seconds differ from the first frame of their set or
+ * whose slot is duplicated, so the host can fall back to its recovery path
+ * (baseband/vdif/base.py:536-755, out of scope here). */
+typedef enum bb_vdif_field {
+    BB_VDIF_INVALID = 0, BB_VDIF_LEGACY, BB_VDIF_SECONDS, BB_VDIF_REF_EPOCH,
+    BB_VDIF_FRAME_NR, BB_VDIF_VERSION, BB_VDIF_LG2_NCHAN,
+    BB_VDIF_FRAME_LENGTH, BB_VDIF_COMPLEX, BB_VDIF_BITS_PER_SAMPLE,
+    BB_VDIF_THREAD_ID, BB_VDIF_STATION_ID, BB_VDIF_EDV, BB_VDIF_WORD4,
+    BB_VDIF_WORD5, BB_VDIF_WORD6, BB_VDIF_WORD7, BB_VDIF_NFIELD
+} bb_vdif_field;
+int bb_vdif_scan(const void *src, const int64_t *frame_offset,
+                 int64_t frame_stride, int64_t nframe, int32_t header_nbytes,
+                 int32_t frames_per_set, int32_t nthread,
+                 const int32_t *thread_slot, int32_t *fields,
+                 int64_t *unit_offset, int32_t *n_inconsistent, void *stream);
+
+/* Mark 5B: header fields (baseband/mark5b/header.py:60-68), BCD decode
+ * (baseband/base/utils.py:18-34, header.py:192-233 incl. the 156250 ns
+ * "unrounding") and payload validity = not all 2500 words equal 0x11223344
+ * (baseband/mark5b/frame.py:62-72).  unit_offset[i] = payload offset or -1. */
+typedef enum bb_mark5b_field {
+    BB_M5B_SYNC = 0, BB_M5B_USER, BB_M5B_INTERNAL_TVG, BB_M5B_FRAME_NR,
+    BB_M5B_BCD_JDAY, BB_M5B_BCD_SECONDS, BB_M5B_BCD_FRACTION, BB_M5B_CRC,
+    BB_M5B_JDAY, BB_M5B_SECONDS, BB_M5B_FRACTION_NS, BB_M5B_VALID,
+    BB_M5B_NFIELD
+} bb_mark5b_field;
+int bb_mark5b_scan(const void *src, const int64_t *frame_offset,
+                   int64_t frame_stride, int64_t nframe, int32_t *fields,
+                   int64_t *unit_offset, void *stream);
+
+/* Mark 4: track-header bit transpose (`stream2words`,
+ * baseband/mark4/header.py:47-63) for one chosen track -> 5 words per frame
+ * in words5[i*5 + w], and frame validity = no error flag on any track
+ * (baseband/mark4/frame.py:78-87).  unit_offset[i] = payload offset or -1. */
+int bb_mark4_scan(const void *src, const int64_t *frame_offset,
+                  int64_t frame_stride, int64_t nframe, int32_t ntrack,
+                  int32_t track, uint32_t *words5, int64_t *unit_offset,
+                  void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BASEBAND_B200_H */

@@ -1,0 +1,218 @@
+"""Shared case tables for the bit-field codec: used by the CPU emulation
+tests and by the GPU parity tests, with the oracle as the checker."""
+import zlib
+
+import numpy as np
+
+from baseband_b200 import levels
+from oracle import codec
+
+
+def _case(id, bps, nelem, nthread, nset, payload_nbytes, cplx=False,
+          kind='vdif', start=0, count=None, invalid=(), shuffle=True,
+          fill=0.0):
+    return dict(id=id, bps=bps, nelem=nelem, nthread=nthread, nset=nset,
+                payload_nbytes=payload_nbytes, complex=cplx, kind=kind,
+                start=start, count=count, invalid=invalid, shuffle=shuffle,
+                fill=fill)
+
+
+DECODE_CASES = [
+    # ROWGROUP4: VDIF multi-thread single channel (configs C1, C2)
+    _case('c1_2bit_8thr', 2, 1, 8, 2, 5000),
+    _case('c2_2bit_16thr', 2, 1, 16, 3, 8000),
+    _case('2bit_16thr_partial', 2, 1, 16, 3, 800, start=3217, count=4001),
+    _case('2bit_8thr_invalid', 2, 1, 8, 3, 400, invalid=(1, 9, 10, 23),
+          fill=-999.0),
+    _case('2bit_4thr_one_sample', 2, 1, 4, 2, 64, start=255, count=2),
+    _case('1bit_8thr', 1, 1, 8, 2, 128, start=5, count=1999),
+    _case('4bit_4thr', 4, 1, 4, 2, 256, invalid=(3,), fill=7.5),
+    _case('8bit_12thr', 8, 1, 12, 2, 200, start=1, count=300),
+    # ROWGROUP2: complex single channel / two channels
+    _case('2bit_cplx_2thr', 2, 2, 2, 3, 512, cplx=True, invalid=(2,),
+          fill=-3.0),
+    _case('8bit_cplx_2thr_mwa', 8, 2, 2, 2, 1024, cplx=True, start=100,
+          count=700),
+    _case('4bit_2chan_6thr', 4, 2, 6, 2, 96, start=7, count=150),
+    _case('1bit_2chan_4thr', 1, 2, 4, 2, 64),
+    # RUN: one thread, any nelem; or nelem power of two >= 4
+    _case('m5b_2bit_16ch', 2, 16, 1, 4, 10000, kind='mark5b',
+          invalid=(2,), fill=-999.0),
+    _case('m5b_2bit_8ch_partial', 2, 8, 1, 3, 10000, kind='mark5b',
+          start=4999, count=7002),
+    _case('m5b_1bit_4ch', 1, 4, 1, 2, 10000, kind='mark5b'),
+    _case('2bit_1thr_1ch', 2, 1, 1, 3, 5000, start=4, count=59992),
+    _case('2bit_1thr_3ch', 2, 3, 1, 2, 12 * 25),
+    _case('1bit_16ch_bps1', 1, 16, 1, 2, 8000),
+    _case('4bit_cplx_1024ch_aro', 4, 2048, 1, 2, 2048 * 5, cplx=True),
+    _case('2bit_4thr_8ch', 2, 8, 4, 3, 640, invalid=(5,), fill=2.0,
+          start=16, count=500),
+    _case('8bit_2thr_cplx_4ch', 8, 8, 2, 2, 800, cplx=True, invalid=(0,),
+          fill=-1.0),
+    _case('4bit_3thr_4ch', 4, 4, 3, 2, 240),
+    # SCALAR: odd geometries / unaligned row ranges
+    _case('2bit_3thr_1ch', 2, 1, 3, 3, 100, invalid=(4,), fill=9.0),
+    _case('2bit_1thr_1ch_unaligned', 2, 1, 1, 2, 500, start=3, count=1001),
+    _case('2bit_5thr_cplx', 2, 2, 5, 2, 200, cplx=True, invalid=(7,),
+          fill=-999.0),
+    _case('4bit_2thr_6ch', 4, 6, 2, 2, 240, start=1, count=77),
+    _case('8bit_1thr_3ch_unaligned', 8, 3, 1, 2, 300, start=1, count=150),
+    # signed-integer codecs
+    _case('gsb_4bit_rawdump', 4, 1, 1, 2, 4096, kind='sint'),
+    _case('dada_8bit_cplx_2pol', 8, 4, 1, 2, 6400, cplx=True, kind='sint'),
+    _case('gsb_8bit_phased_2thr_cplx', 8, 1024, 2, 2, 4096, cplx=True,
+          kind='sint', invalid=(1,), fill=0.5),
+    _case('sint8_3thr', 8, 1, 3, 2, 120, kind='sint', start=5, count=100),
+]
+
+
+def _levels(kind, bps):
+    if kind == 'vdif':
+        return np.ascontiguousarray(levels.offset_binary(bps), np.float32), 0
+    if kind == 'mark5b':
+        return np.ascontiguousarray(levels.mark5b(bps), np.float32), 0
+    return None, 1
+
+
+def make_decode_case(case):
+    rng = np.random.default_rng(zlib.crc32(case['id'].encode()))
+    nunit = case['nset'] * case['nthread']
+    nbytes = case['payload_nbytes']
+    stride = nbytes + 32          # leave room for a (random) header
+    order = rng.permutation(nunit) if case['shuffle'] else np.arange(nunit)
+    raw = rng.integers(0, 256, nunit * stride + 64, dtype=np.uint8)
+    unit_offset = (order * stride + 32).astype(np.int64)
+    truth = unit_offset.copy()
+    for u in case['invalid']:
+        unit_offset[u] = -1
+    spf = nbytes * 8 // (case['bps'] * case['nelem'])
+    count = case['count']
+    if count is None:
+        count = case['nset'] * spf - case['start']
+    lv, codec_id = _levels(case['kind'], case['bps'])
+    return dict(case, raw=raw, unit_offset=unit_offset, truth=truth, spf=spf,
+                sample_start=case['start'], nsample=count, levels=lv,
+                codec=codec_id)
+
+
+def _decode_unit(words, kind, bps):
+    if kind == 'vdif':
+        return codec.vdif_decode(words, bps).ravel()
+    if kind == 'mark5b':
+        return codec.mark5b_decode(words, bps).ravel()
+    b = words.view(np.int8)
+    return (codec.gsb4_decode(b) if bps == 4 else codec.int8_decode(b)).ravel()
+
+
+def oracle_decode(c):
+    nset, nthread, nelem, spf = c['nset'], c['nthread'], c['nelem'], c['spf']
+    full = np.empty((nset * spf, nthread, nelem), np.float32)
+    for s in range(nset):
+        for t in range(nthread):
+            u = s * nthread + t
+            blk = full[s * spf:(s + 1) * spf, t]
+            if c['unit_offset'][u] < 0:
+                blk[:] = c['fill']
+                if c['complex']:
+                    blk[:, 1::2] = 0.0
+            else:
+                o = c['truth'][u]
+                words = c['raw'][o:o + c['payload_nbytes']].view('<u4')
+                blk[:] = _decode_unit(words, c['kind'], c['bps']).reshape(
+                    spf, nelem)
+    return full[c['sample_start']:c['sample_start'] + c['nsample']]
+
+
+def _ecase(id, bps, nelem, nthread, nset, payload_nbytes, quant='vdif',
+           dtype='f4', invalid=()):
+    return dict(id=id, bps=bps, nelem=nelem, nthread=nthread, nset=nset,
+                payload_nbytes=payload_nbytes, quant=quant, dtype=dtype,
+                invalid=invalid)
+
+
+ENCODE_CASES = [
+    _ecase('c2_2bit_16thr', 2, 1, 16, 3, 8000),
+    _ecase('c2_2bit_16thr_f64', 2, 1, 16, 2, 800, dtype='f8'),
+    _ecase('2bit_8thr_skip', 2, 1, 8, 3, 400, invalid=(1, 9)),
+    _ecase('1bit_8thr', 1, 1, 8, 2, 128),
+    _ecase('4bit_4thr', 4, 1, 4, 2, 256),
+    _ecase('8bit_12thr', 8, 1, 12, 2, 200),
+    _ecase('2bit_cplx_2thr', 2, 2, 2, 3, 512),
+    _ecase('8bit_cplx_2thr_f64', 8, 2, 2, 2, 1024, dtype='f8'),
+    _ecase('1bit_2chan_4thr', 1, 2, 4, 2, 64),
+    _ecase('m5b_2bit_16ch', 2, 16, 1, 3, 10000, quant='mark5b'),
+    _ecase('m5b_1bit_4ch_f64', 1, 4, 1, 2, 10000, quant='mark5b',
+           dtype='f8'),
+    _ecase('2bit_1thr_1ch', 2, 1, 1, 3, 5000),
+    _ecase('2bit_1thr_3ch', 2, 3, 1, 2, 300),
+    _ecase('4bit_cplx_1024ch', 4, 2048, 1, 2, 2048 * 5),
+    _ecase('2bit_4thr_8ch', 2, 8, 4, 3, 640, invalid=(5,)),
+    _ecase('4bit_3thr_4ch_f64', 4, 4, 3, 2, 240, dtype='f8'),
+    _ecase('2bit_3thr_1ch', 2, 1, 3, 3, 100),
+    _ecase('2bit_5thr_cplx', 2, 2, 5, 2, 200),
+    _ecase('4bit_2thr_6ch', 4, 6, 2, 2, 240),
+    _ecase('gsb_4bit', 4, 1, 1, 2, 4096, quant='sint'),
+    _ecase('dada_8bit_cplx', 8, 4, 1, 2, 6400, quant='sint'),
+    _ecase('gsb_8bit_2thr_f64', 8, 1024, 2, 2, 4096, quant='sint',
+           dtype='f8'),
+]
+
+_QUANT = {'vdif': 0, 'mark5b': 1, 'sint': 2}
+
+
+def make_encode_case(case):
+    rng = np.random.default_rng(zlib.crc32(case['id'].encode()))
+    nset, nthread, nelem = case['nset'], case['nthread'], case['nelem']
+    nbytes = case['payload_nbytes']
+    spf = nbytes * 8 // (case['bps'] * nelem)
+    scale = 40.0 if case['bps'] == 8 and case['quant'] == 'sint' else 2.5
+    dtype = np.dtype(case['dtype'])
+    data = (rng.standard_normal((nset * spf, nthread, nelem)) * scale
+            ).astype(dtype)
+    # sprinkle exact thresholds and half-integers
+    flat = data.reshape(-1)
+    marks = np.array([0.0, -0.0, 2.174564, -2.174564, 0.5, 1.5, 2.5, -0.5,
+                      3.2618460000000002, 1e30, -1e30], dtype)
+    flat[rng.integers(0, flat.size, marks.size * 4)] = np.tile(marks, 4)
+    nunit = nset * nthread
+    stride = nbytes + 32
+    order = rng.permutation(nunit)
+    unit_offset = (order * stride + 32).astype(np.int64)
+    truth = unit_offset.copy()
+    for u in case['invalid']:
+        unit_offset[u] = -1
+    # 16-byte aligned input
+    buf = np.zeros(data.size + 4, dtype)
+    shift = (-buf.ctypes.data // dtype.itemsize) % (16 // dtype.itemsize)
+    aligned = buf[shift:shift + data.size]
+    aligned[:] = flat
+    return dict(case, data=aligned, shaped=aligned.reshape(data.shape),
+                unit_offset=unit_offset, truth=truth, spf=spf,
+                dst_nbytes=nunit * stride + 64,
+                dtype_code=0 if dtype.itemsize == 4 else 1,
+                quantiser=_QUANT[case['quant']])
+
+
+def oracle_encode(c):
+    dst = np.full(c['dst_nbytes'], 0xEE, np.uint8)
+    spf, nthread = c['spf'], c['nthread']
+    for s in range(c['nset']):
+        for t in range(nthread):
+            u = s * nthread + t
+            if c['unit_offset'][u] < 0:
+                continue
+            vals = np.ascontiguousarray(
+                c['shaped'][s * spf:(s + 1) * spf, t]).ravel()
+            with np.errstate(all='ignore'):
+                if c['quant'] == 'vdif':
+                    enc = codec.vdif_encode(vals.copy(), c['bps'])
+                elif c['quant'] == 'mark5b':
+                    enc = codec.mark5b_encode(vals.copy(), c['bps'])
+                elif c['bps'] == 4:
+                    enc = codec.gsb4_encode(vals)
+                else:
+                    enc = codec.int8_encode(vals)
+            o = c['truth'][u]
+            dst[o:o + c['payload_nbytes']] = np.ascontiguousarray(
+                enc).ravel().view(np.uint8)
+    return dst

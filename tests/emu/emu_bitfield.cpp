@@ -1,0 +1,107 @@
+// CPU emulation of the bit-field kernels — TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the very same per-thread bodies and launch planning that the CUDA
+// library uses (baseband_b200/csrc/bb_bitfield.cuh, bb_bitfield_plan.h) with
+// g++ and runs every "thread" in a loop, so the index arithmetic, the fast /
+// edge paths and the quantisers can be checked against the oracle on a box
+// without a GPU.  Never loaded by baseband_b200.
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../baseband_b200/csrc/bb_bitfield_plan.h"
+#include "../../include/baseband_b200.h"
+
+using namespace bb;
+
+static std::string g_err;
+
+template <int BPS, int CODEC>
+static void run_decode(const std::vector<DecLaunch> &launches,
+                       const float *levels) {
+    using Lut = DecodeLut<BPS>;
+    alignas(16) float lut[Lut::kFloats];
+    if (CODEC == CODEC_LEVELS)
+        for (int i = 0; i < Lut::kFloats; ++i) lut[i] = Lut::value(levels, i);
+    for (const DecLaunch &l : launches)
+        for (uint32_t item = 0; item < l.g.nitems; ++item) {
+            if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
+            else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
+            else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);
+            else dec_scalar<BPS, CODEC>(l.g, lut, item);
+        }
+}
+
+template <typename T, int BPS, int QUANT>
+static void run_encode(const std::vector<EncLaunch> &launches) {
+    const QuantConsts<T> c = make_quant_consts<T>();
+    for (const EncLaunch &l : launches)
+        for (uint32_t item = 0; item < l.g.nitems; ++item) {
+            if (l.mode == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(l.g, c, item);
+            else if (l.mode == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(l.g, c, item);
+            else if (l.mode == MODE_RUN) enc_word<T, BPS, QUANT, true>(l.g, c, item);
+            else enc_word<T, BPS, QUANT, false>(l.g, c, item);
+        }
+}
+
+template <typename T>
+static int enc_dispatch(int bps, int q, const std::vector<EncLaunch> &l) {
+    if (q == BB_QUANT_OFFSET_BINARY) {
+        if (bps == 1) return run_encode<T, 1, QUANT_OFFSET>(l), 0;
+        if (bps == 2) return run_encode<T, 2, QUANT_OFFSET>(l), 0;
+        if (bps == 4) return run_encode<T, 4, QUANT_OFFSET>(l), 0;
+        if (bps == 8) return run_encode<T, 8, QUANT_OFFSET>(l), 0;
+    } else if (q == BB_QUANT_MARK5B) {
+        if (bps == 1) return run_encode<T, 1, QUANT_MARK5B>(l), 0;
+        if (bps == 2) return run_encode<T, 2, QUANT_MARK5B>(l), 0;
+    } else if (q == BB_QUANT_SINT) {
+        if (bps == 4) return run_encode<T, 4, QUANT_SINT>(l), 0;
+        if (bps == 8) return run_encode<T, 8, QUANT_SINT>(l), 0;
+    }
+    return BB_ERR_UNSUPPORTED;
+}
+
+extern "C" {
+
+const char *bb_last_error(void) { return g_err.c_str(); }
+
+// Which decomposition the planner picks (for test coverage assertions).
+int emu_decode_mode(int32_t nelem, int32_t nthread, int aligned_rows) {
+    return pick_mode(nelem, nthread, aligned_rows != 0);
+}
+
+int bb_decode_bitfield(const void *src, const int64_t *unit_offset,
+                       int64_t nset, int32_t nthread, int64_t payload_nbytes,
+                       int32_t bps, int32_t nelem, int32_t complex_data,
+                       int32_t codec, const float *levels_host,
+                       float fill_value, int64_t sample_start,
+                       int64_t nsample, float *out, void *stream) {
+    std::vector<DecLaunch> launches;
+    if (!plan_decode(src, unit_offset, nset, nthread, payload_nbytes, bps,
+                     nelem, complex_data, fill_value, sample_start, nsample,
+                     out, launches, g_err))
+        return BB_ERR_ARGUMENT;
+    if (codec == BB_CODEC_LEVELS) {
+        if (bps == 1) return run_decode<1, CODEC_LEVELS>(launches, levels_host), 0;
+        if (bps == 2) return run_decode<2, CODEC_LEVELS>(launches, levels_host), 0;
+        if (bps == 4) return run_decode<4, CODEC_LEVELS>(launches, levels_host), 0;
+        if (bps == 8) return run_decode<8, CODEC_LEVELS>(launches, levels_host), 0;
+    } else {
+        if (bps == 4) return run_decode<4, CODEC_SINT>(launches, nullptr), 0;
+        if (bps == 8) return run_decode<8, CODEC_SINT>(launches, nullptr), 0;
+    }
+    return BB_ERR_UNSUPPORTED;
+}
+
+int bb_encode_bitfield(const void *in, int32_t in_dtype, void *dst,
+                       const int64_t *unit_offset, int64_t nset,
+                       int32_t nthread, int64_t payload_nbytes, int32_t bps,
+                       int32_t nelem, int32_t quantiser, void *stream) {
+    std::vector<EncLaunch> launches;
+    if (!plan_encode(in, dst, unit_offset, nset, nthread, payload_nbytes, bps,
+                     nelem, launches, g_err))
+        return BB_ERR_ARGUMENT;
+    return in_dtype == BB_F32 ? enc_dispatch<float>(bps, quantiser, launches)
+                              : enc_dispatch<double>(bps, quantiser, launches);
+}
+
+}  // extern "C"
