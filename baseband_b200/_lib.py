@@ -105,7 +105,10 @@ def load():
                 'baseband_b200: CUDA library not built ({}). Run '
                 '`python -m baseband_b200.build` (needs nvcc); there is no '
                 'CPU fallback.'.format(LIB_PATH))
-        _lib = bind(ctypes.CDLL(LIB_PATH))
+        # Every symbol of include/baseband_b200.h must be there; a partial
+        # library is a build error, not something to work around.
+        _lib = bind(ctypes.CDLL(LIB_PATH),
+                    required=() if os.environ.get('BB_ALLOW_PARTIAL') else EXPORTS)
         if _lib.bb_abi_version() != 1:
             raise ImportError('baseband_b200: ABI version mismatch')
     return _lib

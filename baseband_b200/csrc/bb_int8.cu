@@ -1,0 +1,98 @@
+// int8 transposed decode/encode kernels and C entry points (sm_100a).
+#include "bb_runtime.cuh"
+#include "bb_int8.cuh"
+
+namespace bb {
+
+__global__ void __launch_bounds__(kI8Threads) k_int8_decode_t(const I8Geom p) {
+    __shared__ __align__(16) uint8_t tile[kI8SmemBytes];
+    i8_dec_load(p, tile, blockIdx.x, threadIdx.x);
+    __syncthreads();
+    i8_dec_store(p, tile, blockIdx.x, threadIdx.x);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kI8Threads) k_int8_encode_t(const I8Geom p) {
+    __shared__ __align__(16) uint8_t tile[kI8SmemBytes];
+    i8_enc_load<T>(p, tile, blockIdx.x, threadIdx.x);
+    __syncthreads();
+    i8_enc_store(p, tile, blockIdx.x, threadIdx.x);
+}
+
+static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
+                     int item_nbytes, uint64_t &nblocks) {
+    if (item_nbytes != 1 && item_nbytes != 2)
+        return set_error(BB_ERR_ARGUMENT, "item_nbytes must be 1 or 2");
+    if (nunit < 0 || nrow < 1 || ncol < 1 || nrow > 0x7fffffff
+        || ncol > 0x7fffffff || nunit > 0x7fffffff)
+        return set_error(BB_ERR_ARGUMENT, "bad nunit/nrow/ncol");
+    g.nunit = (uint32_t)nunit;
+    g.nrow = (uint32_t)nrow;
+    g.ncol = (uint32_t)ncol;
+    g.ib = item_nbytes;
+    g.tiles_r = (uint32_t)((nrow + kI8Rows - 1) / kI8Rows);
+    uint32_t tc = kI8RowBytes / item_nbytes;
+    g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
+    nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
+    if (nblocks > 0x7fffffffull)
+        return set_error(BB_ERR_ARGUMENT, "too many tiles for one call");
+    return BB_OK;
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_decode_int8_transposed(
+    const void *src, const int64_t *unit_offset, int64_t nunit, int64_t nrow,
+    int64_t ncol, int32_t item_nbytes, const int64_t *col_begin,
+    const int64_t *col_end, const int64_t *out_col0, float *out,
+    void *stream) {
+    if (!src || !unit_offset || !col_begin || !col_end || !out_col0 || !out)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(out, 8))
+        return set_error(BB_ERR_ALIGNMENT, "out must be 8-byte aligned");
+    I8Geom g;
+    uint64_t nblocks;
+    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks);
+    if (rc != BB_OK) return rc;
+    if (nblocks == 0) return BB_OK;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.col_begin = (const long long *)col_begin;
+    g.col_end = (const long long *)col_end;
+    g.out_col0 = (const long long *)out_col0;
+    g.out = out;
+    g.in = nullptr;
+    k_int8_decode_t<<<(unsigned)nblocks, kI8Threads, 0, as_stream(stream)>>>(g);
+    BB_CHECK_LAUNCH("bb_decode_int8_transposed launch");
+    return BB_OK;
+}
+
+extern "C" int bb_encode_int8_transposed(
+    const void *in, int32_t in_dtype, void *dst, const int64_t *unit_offset,
+    int64_t nunit, int64_t nrow, int64_t ncol, int32_t item_nbytes,
+    void *stream) {
+    if (!in || !dst || !unit_offset)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    I8Geom g;
+    uint64_t nblocks;
+    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks);
+    if (rc != BB_OK) return rc;
+    if (nblocks == 0) return BB_OK;
+    g.src = (const uint8_t *)dst;
+    g.unit_offset = (const long long *)unit_offset;
+    g.col_begin = g.col_end = g.out_col0 = nullptr;
+    g.out = nullptr;
+    g.in = in;
+    if (in_dtype == BB_F32)
+        k_int8_encode_t<float><<<(unsigned)nblocks, kI8Threads, 0,
+                                 as_stream(stream)>>>(g);
+    else if (in_dtype == BB_F64)
+        k_int8_encode_t<double><<<(unsigned)nblocks, kI8Threads, 0,
+                                  as_stream(stream)>>>(g);
+    else
+        return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+    BB_CHECK_LAUNCH("bb_encode_int8_transposed launch");
+    return BB_OK;
+}

@@ -1,0 +1,157 @@
+// Mark 4 decode/encode kernels and C entry points (sm_100a).
+#include <string>
+#include <vector>
+#include "bb_runtime.cuh"
+#include "bb_bitfield.cuh"      // DecodeLut
+#include "bb_mark4_plan.h"
+
+namespace bb {
+
+constexpr int kM4Block = 256;
+constexpr int kM4CtasPerSm = 8;
+
+template <int MODE>
+__global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
+    // pair LUT over the raw code (sign | magnitude << 1), see DecodeLut<2>
+    __shared__ __align__(16) float lut[DecodeLut<2>::kFloats];
+    if (MODE == M4_FAST) {
+        if (threadIdx.x < DecodeLut<2>::kFloats) {
+            int entry = threadIdx.x >> 1, which = threadIdx.x & 1;
+            int code = which ? (entry >> 2) : (entry & 3);
+            lut[threadIdx.x] = p.levels[2 * (code & 1) + (code >> 1)];
+        }
+        __syncthreads();
+    }
+    const uint32_t stride = gridDim.x * kM4Block;
+    for (uint32_t item = blockIdx.x * kM4Block + threadIdx.x; item < p.nitems;
+         item += stride) {
+        if (MODE == M4_FAST) m4_dec_fast(p, lut, item);
+        else if (MODE == M4_GENERIC_VEC) m4_dec_generic<true>(p, item);
+        else m4_dec_generic<false>(p, item);
+        if (item + stride < item) break;
+    }
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kM4Block)
+k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
+    const uint32_t stride = gridDim.x * kM4Block;
+    for (uint32_t item = blockIdx.x * kM4Block + threadIdx.x; item < p.nitems;
+         item += stride) {
+        if (MODE == M4_FAST) m4_enc_fast<T>(p, c, item);
+        else m4_enc_generic<T>(p, c, item);
+        if (item + stride < item) break;
+    }
+}
+
+static int run_decode(const std::vector<M4Launch> &launches, cudaStream_t s) {
+    for (const M4Launch &l : launches) {
+        unsigned grid = stream_grid(l.g.nitems, kM4Block, kM4CtasPerSm);
+        if (l.mode == M4_FAST)
+            k_mark4_decode<M4_FAST><<<grid, kM4Block, 0, s>>>(l.g);
+        else if (l.mode == M4_GENERIC_VEC)
+            k_mark4_decode<M4_GENERIC_VEC><<<grid, kM4Block, 0, s>>>(l.g);
+        else
+            k_mark4_decode<M4_GENERIC_SCALAR><<<grid, kM4Block, 0, s>>>(l.g);
+        BB_CHECK_LAUNCH("bb_mark4_decode launch");
+    }
+    return BB_OK;
+}
+
+template <typename T>
+static int run_encode(const std::vector<M4Launch> &launches, cudaStream_t s) {
+    static const QuantConsts<T> consts = make_quant_consts<T>();
+    for (const M4Launch &l : launches) {
+        unsigned grid = stream_grid(l.g.nitems, kM4Block, kM4CtasPerSm);
+        if (l.mode == M4_FAST)
+            k_mark4_encode<T, M4_FAST><<<grid, kM4Block, 0, s>>>(l.g, consts);
+        else
+            k_mark4_encode<T, M4_GENERIC_SCALAR>
+                <<<grid, kM4Block, 0, s>>>(l.g, consts);
+        BB_CHECK_LAUNCH("bb_mark4_encode launch");
+    }
+    return BB_OK;
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_mark4_decode(
+    const void *src, const int64_t *unit_offset, int64_t nframe, int32_t nchan,
+    int32_t fanout, int32_t ft, const float *levels_host, float fill_value,
+    int64_t sample_start, int64_t nsample, float *out, void *stream) {
+    if (!src || !unit_offset || !out || !levels_host)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(out, 16) || !aligned(src, 8))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "out must be 16-byte and src 8-byte aligned");
+    std::vector<M4Launch> launches;
+    std::string err;
+    if (!plan_m4_frames(false, src, unit_offset, nframe, nchan, fanout, ft,
+                        levels_host, fill_value, sample_start, nsample, out,
+                        nullptr, launches, err))
+        return set_error(err.rfind("no Mark 4 codec", 0) == 0
+                         ? BB_ERR_UNSUPPORTED : BB_ERR_ARGUMENT, "%s",
+                         err.c_str());
+    return run_decode(launches, as_stream(stream));
+}
+
+extern "C" int bb_mark4_encode(
+    const void *in, int32_t in_dtype, void *dst, const int64_t *unit_offset,
+    int64_t nframe, int32_t nchan, int32_t fanout, int32_t ft, void *stream) {
+    if (!in || !dst || !unit_offset)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(in, 16) || !aligned(dst, 8))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "in must be 16-byte and dst 8-byte aligned");
+    std::vector<M4Launch> launches;
+    std::string err;
+    if (!plan_m4_frames(true, dst, unit_offset, nframe, nchan, fanout, ft,
+                        nullptr, 0.f, 0, nframe * 20000ll * fanout, nullptr, in,
+                        launches, err))
+        return set_error(err.rfind("no Mark 4 codec", 0) == 0
+                         ? BB_ERR_UNSUPPORTED : BB_ERR_ARGUMENT, "%s",
+                         err.c_str());
+    if (in_dtype == BB_F32) return run_encode<float>(launches, as_stream(stream));
+    if (in_dtype == BB_F64) return run_encode<double>(launches, as_stream(stream));
+    return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+}
+
+extern "C" int bb_mark4_decode_words(
+    const void *words, int64_t nword, int32_t nchan, int32_t fanout,
+    int32_t ft, const float *levels_host, float *out, void *stream) {
+    if (!words || !out || !levels_host)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(out, 16) || !aligned(words, 8))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "out must be 16-byte and words 8-byte aligned");
+    std::vector<M4Launch> launches;
+    std::string err;
+    if (!plan_m4_words(false, words, nword, nchan, fanout, ft, levels_host,
+                       out, nullptr, launches, err))
+        return set_error(err.rfind("no Mark 4 codec", 0) == 0
+                         ? BB_ERR_UNSUPPORTED : BB_ERR_ARGUMENT, "%s",
+                         err.c_str());
+    return run_decode(launches, as_stream(stream));
+}
+
+extern "C" int bb_mark4_encode_words(
+    const void *in, int32_t in_dtype, void *words, int64_t nword,
+    int32_t nchan, int32_t fanout, int32_t ft, void *stream) {
+    if (!in || !words)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(in, 16) || !aligned(words, 8))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "in must be 16-byte and words 8-byte aligned");
+    std::vector<M4Launch> launches;
+    std::string err;
+    if (!plan_m4_words(true, words, nword, nchan, fanout, ft, nullptr, nullptr,
+                       in, launches, err))
+        return set_error(err.rfind("no Mark 4 codec", 0) == 0
+                         ? BB_ERR_UNSUPPORTED : BB_ERR_ARGUMENT, "%s",
+                         err.c_str());
+    if (in_dtype == BB_F32) return run_encode<float>(launches, as_stream(stream));
+    if (in_dtype == BB_F64) return run_encode<double>(launches, as_stream(stream));
+    return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+}

@@ -1,0 +1,206 @@
+// Mark 4 track-word codec: per-thread bodies (host/device).
+//
+// A frame is 20000 time steps of one ntrack-bit little-endian word; the first
+// 160 steps hold the header, so the first 160*fanout samples of every frame
+// decode to fill_value (baseband/mark4/frame.py:185-189, :253-258).  A payload
+// word holds fanout consecutive samples of nchan channels as (sign, magnitude)
+// bit pairs scattered over the tracks.
+//
+//  FAST     standard fan-out 4 layouts with 32 or 64 tracks (4 or 8 channels;
+//           C3).  Each 32-bit half word carries 4 channels x 4 samples.  The
+//           reference's `reorder32/64` bit swap (mark4/payload.py:48-69) is
+//           applied in registers; afterwards byte perm[c] holds channel c as
+//           four 2-bit codes (sign | magnitude << 1), which is exactly the
+//           pair-LUT layout of the VDIF kernel.  A thread decodes one half
+//           word into four float4 rows.
+//  GENERIC  any of the five modes, table driven: bit position of sign and
+//           magnitude for every (sample-in-word, channel).  Output-centric
+//           float4 (or scalar) items.
+#pragma once
+#include "bb_common.cuh"
+#include "bb_quant.cuh"
+
+namespace bb {
+
+struct M4Geom {
+    const uint8_t *src;              // decode input / encode output base
+    const long long *unit_offset;    // per frame payload offset; null => 0
+    float *out;                      // decode output (row 0 of the call)
+    const void *in;                  // encode input
+    unsigned long long in_elem_offset;
+    long long row_base, nsample;
+    uint32_t nframe, nchan, fanout, wordbytes, nitems;
+    uint32_t steps;                  // time steps per frame (20000) or nword
+    uint32_t header_steps;           // 160, or 0 for bare payload words
+    int32_t log2_nchan;
+    float fill;
+    FastDiv div_steps, div_spf;
+    uint16_t pos[32];                // sign bit | magnitude bit << 8
+    float levels[4];                 // indexed 2*sign + magnitude
+};
+
+BB_HD uint32_t m4_reorder32(uint32_t x) {
+    return (x & 0xAA55AA55u) | ((x & 0x55005500u) >> 7)
+        | ((x & 0x00AA00AAu) << 7);
+}
+
+// Pair LUT as DecodeLut<2> builds it from levels indexed by the raw 2-bit
+// code (sign | magnitude << 1): idx = nibble -> (value of low code, high code)
+BB_HD F2 m4_pair(uint32_t byte_, uint32_t fp, const float *lut) {
+    return reinterpret_cast<const F2 *>(lut)[(byte_ >> (4 * fp)) & 15u];
+}
+
+// FAST decode.  item = (frame, step, half).
+BB_HD void m4_dec_fast(const M4Geom &p, const float *lut, uint32_t item) {
+    const uint32_t nhalf = p.wordbytes >> 2;           // 1 or 2
+    const uint32_t h = item & (nhalf - 1u);
+    const uint32_t fs = nhalf == 2 ? item >> 1 : item;
+    uint32_t frame, step;
+    p.div_steps.divmod(fs, frame, step);
+    const long long row0 = p.row_base
+        + ((long long)frame * p.steps + step) * 4;
+    if (row0 + 4 <= 0 || row0 >= p.nsample) return;
+    const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
+    const bool data = off >= 0 && step >= p.header_steps;
+    float *dst = p.out + row0 * (long long)p.nchan + 4 * h;
+    F4 rows[4];
+    if (data) {
+        uint32_t w = *reinterpret_cast<const uint32_t *>(
+            p.src + off + (size_t)(step - p.header_steps) * p.wordbytes
+            + 4 * h);
+        uint32_t r = m4_reorder32(w);
+        uint32_t b0 = r & 0xffu, b1 = (r >> 16) & 0xffu,   // perm 0,2,1,3
+            b2 = (r >> 8) & 0xffu, b3 = r >> 24;
+#pragma unroll
+        for (int fp = 0; fp < 2; ++fp) {
+            F2 a = m4_pair(b0, fp, lut), b = m4_pair(b1, fp, lut),
+                c = m4_pair(b2, fp, lut), d = m4_pair(b3, fp, lut);
+            rows[2 * fp] = F4{a.x, b.x, c.x, d.x};
+            rows[2 * fp + 1] = F4{a.y, b.y, c.y, d.y};
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rows[i] = F4{p.fill, p.fill, p.fill, p.fill};
+    }
+    if (row0 >= 0 && row0 + 4 <= p.nsample) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<F4 *>(dst + (size_t)i * p.nchan) = rows[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (row0 + i >= 0 && row0 + i < p.nsample)
+                *reinterpret_cast<F4 *>(dst + (long long)i * p.nchan) = rows[i];
+    }
+}
+
+BB_HD unsigned long long m4_load_word(const uint8_t *p, uint32_t wordbytes) {
+    if (wordbytes == 8) return *reinterpret_cast<const unsigned long long *>(p);
+    if (wordbytes == 4) return *reinterpret_cast<const uint32_t *>(p);
+    if (wordbytes == 2) return *reinterpret_cast<const uint16_t *>(p);
+    return *p;
+}
+
+BB_HD float m4_value(const M4Geom &p, unsigned long long w, uint32_t f,
+                     uint32_t c) {
+    uint32_t pp = p.pos[(f << p.log2_nchan) + c];
+    uint32_t s = (uint32_t)(w >> (pp & 0xffu)) & 1u;
+    uint32_t m = (uint32_t)(w >> (pp >> 8)) & 1u;
+    return p.levels[2 * s + m];
+}
+
+// GENERIC decode of one output element (row_local, c) of the launch.
+BB_HD float m4_dec_element(const M4Geom &p, uint32_t row_local, uint32_t c) {
+    uint32_t frame, t;
+    p.div_spf.divmod(row_local, frame, t);
+    const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
+    const uint32_t step = t / p.fanout, f = t % p.fanout;
+    if (off < 0 || step < p.header_steps) return p.fill;
+    unsigned long long w = m4_load_word(
+        p.src + off + (size_t)(step - p.header_steps) * p.wordbytes,
+        p.wordbytes);
+    return m4_value(p, w, f, c);
+}
+
+template <bool VEC>
+BB_HD void m4_dec_generic(const M4Geom &p, uint32_t item) {
+    const uint32_t n = VEC ? item * 4u : item;
+    long long gidx = p.row_base * (long long)p.nchan + n;
+    if (gidx < 0 || gidx >= p.nsample * (long long)p.nchan) return;
+    if (VEC) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t e = n + i;
+            v[i] = m4_dec_element(p, e >> p.log2_nchan, e & (p.nchan - 1u));
+        }
+        *reinterpret_cast<F4 *>(p.out + gidx) = F4{v[0], v[1], v[2], v[3]};
+    } else {
+        p.out[gidx] = m4_dec_element(p, n >> p.log2_nchan, n & (p.nchan - 1u));
+    }
+}
+
+// ------------------------------------------------------------------ encode
+// FAST encode: item = (frame, step, half); header steps are skipped.
+template <typename T>
+BB_HD void m4_enc_fast(const M4Geom &p, const QuantConsts<T> &c,
+                       uint32_t item) {
+    const uint32_t nhalf = p.wordbytes >> 2;
+    const uint32_t h = item & (nhalf - 1u);
+    const uint32_t fs = nhalf == 2 ? item >> 1 : item;
+    uint32_t frame, step;
+    p.div_steps.divmod(fs, frame, step);
+    const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
+    if (off < 0 || step < p.header_steps) return;
+    const T *src = reinterpret_cast<const T *>(p.in) + p.in_elem_offset
+        + (((size_t)frame * p.steps + step) * 4) * p.nchan + 4 * h;
+    uint32_t bytes[4] = {0u, 0u, 0u, 0u};       // per channel j of this half
+#pragma unroll
+    for (int f = 0; f < 4; ++f) {
+        T v[4];
+        if (sizeof(T) == 4) {
+            F4 r = *reinterpret_cast<const F4 *>(src + (size_t)f * p.nchan);
+            v[0] = (T)r.x; v[1] = (T)r.y; v[2] = (T)r.z; v[3] = (T)r.w;
+        } else {
+            const D2 *q = reinterpret_cast<const D2 *>(src + (size_t)f * p.nchan);
+            D2 a = q[0], b = q[1];
+            v[0] = (T)a.x; v[1] = (T)a.y; v[2] = (T)b.x; v[3] = (T)b.y;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)             // raw code = sign | mag << 1
+            bytes[j] |= quantise<T, 2, QUANT_MARK5B>(v[j], c) << (2 * f);
+    }
+    // channel j lives in byte perm[j] = {0, 2, 1, 3} before the bit reorder
+    uint32_t r = bytes[0] | (bytes[1] << 16) | (bytes[2] << 8)
+        | (bytes[3] << 24);
+    *reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(p.src) + off
+        + (size_t)(step - p.header_steps) * p.wordbytes + 4 * h)
+        = m4_reorder32(r);
+}
+
+// GENERIC encode: item = (frame, step) -> one whole track word.
+template <typename T>
+BB_HD void m4_enc_generic(const M4Geom &p, const QuantConsts<T> &c,
+                          uint32_t item) {
+    uint32_t frame, step;
+    p.div_steps.divmod(item, frame, step);
+    const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
+    if (off < 0 || step < p.header_steps) return;
+    const T *src = reinterpret_cast<const T *>(p.in) + p.in_elem_offset
+        + (((size_t)frame * p.steps + step) * p.fanout) * p.nchan;
+    unsigned long long w = 0ull;
+    const uint32_t nval = p.fanout * p.nchan;
+    for (uint32_t i = 0; i < nval; ++i) {
+        uint32_t q = quantise<T, 2, QUANT_OFFSET>(src[i], c);   // 2*s + m
+        uint32_t pp = p.pos[i];
+        w |= (unsigned long long)(q >> 1) << (pp & 0xffu);
+        w |= (unsigned long long)(q & 1u) << (pp >> 8);
+    }
+    uint8_t *dst = const_cast<uint8_t *>(p.src) + off
+        + (size_t)(step - p.header_steps) * p.wordbytes;
+    if (p.wordbytes == 8) *reinterpret_cast<unsigned long long *>(dst) = w;
+    else if (p.wordbytes == 4) *reinterpret_cast<uint32_t *>(dst) = (uint32_t)w;
+    else *reinterpret_cast<uint16_t *>(dst) = (uint16_t)w;
+}
+
+}  // namespace bb

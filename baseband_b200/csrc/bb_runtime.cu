@@ -1,6 +1,7 @@
 // Runtime part of the C ABI: errors, device/stream/memory helpers.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include "bb_runtime.cuh"
 
 namespace bb {
@@ -33,6 +34,14 @@ int sm_count() {
         cached_dev = dev;
     }
     return cached;
+}
+
+int grid_override() {
+    static int value = [] {
+        const char *e = getenv("BB_CTAS_PER_SM");
+        return e ? atoi(e) : -1;
+    }();
+    return value;
 }
 
 }  // namespace bb

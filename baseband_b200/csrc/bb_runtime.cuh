@@ -14,8 +14,13 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 // Grid for a grid-stride streaming kernel: enough CTAs of `block` threads to
 // fill every SM `ctas_per_sm` deep, never more than the work needs.
+int grid_override();                  // BB_CTAS_PER_SM (tuning): -1 unset, 0 = full
+
 inline unsigned stream_grid(uint64_t nitems, unsigned block, unsigned ctas_per_sm) {
     uint64_t need = (nitems + block - 1) / block;
+    int ov = grid_override();
+    if (ov == 0) return (unsigned)(need ? need : 1);
+    if (ov > 0) ctas_per_sm = (unsigned)ov;
     uint64_t cap = (uint64_t)sm_count() * ctas_per_sm;
     uint64_t g = need < cap ? need : cap;
     return (unsigned)(g ? g : 1);

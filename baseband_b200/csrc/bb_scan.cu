@@ -1,0 +1,274 @@
+// Batched header parse / validity kernels (sm_100a): the producers of the
+// unit-offset tables the decode kernels consume.  Tiny traffic (headers
+// only, plus a short-circuited payload check for Mark 5B), integer only.
+#include "bb_runtime.cuh"
+
+namespace bb {
+
+constexpr int kScanBlock = 256;
+constexpr long long kMissing = -2;     // slot never written by the scan
+
+__device__ __forceinline__ uint32_t ldw(const uint8_t *p) {
+    return *reinterpret_cast<const uint32_t *>(p);
+}
+
+__device__ __forceinline__ uint32_t bits(uint32_t w, int lo, int n) {
+    return (w >> lo) & ((n >= 32) ? 0xffffffffu : ((1u << n) - 1u));
+}
+
+__global__ void k_fill_i64(long long *p, long long v, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------- VDIF
+// Field table: baseband/vdif/header.py:529-542 (+ edv :557-559).
+__global__ void __launch_bounds__(kScanBlock)
+k_vdif_scan(const uint8_t *src, const long long *frame_offset,
+            long long frame_stride, long long nframe, int header_nbytes,
+            int frames_per_set, int nthread, const int *thread_slot,
+            int *fields, long long *unit_offset, int *n_bad) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nframe) return;
+    long long off = frame_offset ? frame_offset[i] : i * frame_stride;
+    const uint8_t *h = src + off;
+    uint32_t w[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        w[k] = (k < 4 || header_nbytes >= 32) ? ldw(h + 4 * k) : 0u;
+    const uint32_t invalid = bits(w[0], 31, 1), seconds = bits(w[0], 0, 30);
+    const uint32_t frame_nr = bits(w[1], 0, 24), tid = bits(w[3], 16, 10);
+    if (fields) {
+        int *f = fields + i;
+        f[BB_VDIF_INVALID * nframe] = invalid;
+        f[BB_VDIF_LEGACY * nframe] = bits(w[0], 30, 1);
+        f[BB_VDIF_SECONDS * nframe] = seconds;
+        f[BB_VDIF_REF_EPOCH * nframe] = bits(w[1], 24, 6);
+        f[BB_VDIF_FRAME_NR * nframe] = frame_nr;
+        f[BB_VDIF_VERSION * nframe] = bits(w[2], 29, 3);
+        f[BB_VDIF_LG2_NCHAN * nframe] = bits(w[2], 24, 5);
+        f[BB_VDIF_FRAME_LENGTH * nframe] = bits(w[2], 0, 24);
+        f[BB_VDIF_COMPLEX * nframe] = bits(w[3], 31, 1);
+        f[BB_VDIF_BITS_PER_SAMPLE * nframe] = bits(w[3], 26, 5);
+        f[BB_VDIF_THREAD_ID * nframe] = tid;
+        f[BB_VDIF_STATION_ID * nframe] = bits(w[3], 0, 16);
+        f[BB_VDIF_EDV * nframe] = bits(w[4], 24, 8);
+        f[BB_VDIF_WORD4 * nframe] = (int)w[4];
+        f[BB_VDIF_WORD5 * nframe] = (int)w[5];
+        f[BB_VDIF_WORD6 * nframe] = (int)w[6];
+        f[BB_VDIF_WORD7 * nframe] = (int)w[7];
+    }
+    if (!unit_offset) return;
+    long long set = i / frames_per_set;
+    if ((set + 1) * (long long)frames_per_set > nframe) return;  // partial set
+    // All frames of a set share seconds and frame_nr with its first frame
+    // (baseband/vdif/frame.py:207-216).
+    long long i0 = set * frames_per_set;
+    if (i != i0) {
+        long long off0 = frame_offset ? frame_offset[i0] : i0 * frame_stride;
+        uint32_t a = ldw(src + off0), b = ldw(src + off0 + 4);
+        if (bits(a, 0, 30) != seconds || bits(b, 0, 24) != frame_nr)
+            atomicAdd(n_bad, 1);
+    }
+    int slot = thread_slot[tid];
+    if (slot < 0 || slot >= nthread) return;      // thread not selected
+    long long value = invalid ? -1 : off + header_nbytes;
+    unsigned long long prev = atomicExch(
+        reinterpret_cast<unsigned long long *>(unit_offset + set * nthread
+                                               + slot),
+        (unsigned long long)value);
+    if ((long long)prev != kMissing) atomicAdd(n_bad, 1);   // duplicate id
+}
+
+__global__ void k_count_missing(long long *unit_offset, long long n,
+                                int *n_bad) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && unit_offset[i] == kMissing) {
+        unit_offset[i] = -1;
+        atomicAdd(n_bad, 1);
+    }
+}
+
+// ---------------------------------------------------------------- Mark 5B
+__device__ __forceinline__ int bcd(uint32_t v, int ndigit) {
+    int out = 0, scale = 1;
+    for (int d = 0; d < ndigit; ++d) {
+        uint32_t nib = (v >> (4 * d)) & 0xfu;
+        if (nib > 9) return -1;                   // base/utils.py:27-31
+        out += nib * scale;
+        scale *= 10;
+    }
+    return out;
+}
+
+// One lane per frame for the header; frames whose first three payload words
+// equal the fill pattern (baseband/mark5b/frame.py:62-72 short-circuit) are
+// then checked in full by the whole warp, coalesced.
+__global__ void __launch_bounds__(kScanBlock)
+k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
+              long long frame_stride, long long nframe, int *fields,
+              long long *unit_offset) {
+    const uint32_t kFill = 0x11223344u;
+    const int lane = threadIdx.x & 31;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < nframe;
+    long long off = 0;
+    bool candidate = false;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    if (live) {
+        off = frame_offset ? frame_offset[i] : i * frame_stride;
+        const uint8_t *h = src + off;
+        w0 = ldw(h); w1 = ldw(h + 4); w2 = ldw(h + 8); w3 = ldw(h + 12);
+        candidate = ldw(h + 16) == kFill && ldw(h + 20) == kFill
+            && ldw(h + 24) == kFill;
+    }
+    bool valid = !candidate;
+    unsigned todo = __ballot_sync(0xffffffffu, candidate);
+    while (todo) {
+        int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        long long boff = __shfl_sync(0xffffffffu, off, b);
+        const uint8_t *pl = src + boff + 16;
+        bool diff = false;
+        for (int k = 3 + lane; k < 2500 && !diff; k += 32)
+            diff = ldw(pl + 4 * k) != kFill;
+        bool any = __any_sync(0xffffffffu, diff);
+        if (lane == b) valid = any;
+    }
+    if (!live) return;
+    if (fields) {
+        int *f = fields + i;
+        const int bj = bits(w2, 20, 12), bs = bits(w2, 0, 20),
+            bf = bits(w3, 16, 16);
+        f[BB_M5B_SYNC * nframe] = (int)w0;
+        f[BB_M5B_USER * nframe] = bits(w1, 16, 16);
+        f[BB_M5B_INTERNAL_TVG * nframe] = bits(w1, 15, 1);
+        f[BB_M5B_FRAME_NR * nframe] = bits(w1, 0, 15);
+        f[BB_M5B_BCD_JDAY * nframe] = bj;
+        f[BB_M5B_BCD_SECONDS * nframe] = bs;
+        f[BB_M5B_BCD_FRACTION * nframe] = bf;
+        f[BB_M5B_CRC * nframe] = bits(w3, 0, 16);
+        f[BB_M5B_JDAY * nframe] = bcd(bj, 3);
+        f[BB_M5B_SECONDS * nframe] = bcd(bs, 5);
+        int frac = bcd(bf, 4);
+        // "unrounded" to the 156250 ns grid: mark5b/header.py:223-225
+        f[BB_M5B_FRACTION_NS * nframe] = frac < 0 ? -1
+            : 156250 * ((frac * 100000 + 156249) / 156250);
+        f[BB_M5B_VALID * nframe] = valid ? 1 : 0;
+    }
+    if (unit_offset) unit_offset[i] = valid ? off + 16 : -1;
+}
+
+// ---------------------------------------------------------------- Mark 4
+// One warp per frame.  Header = 160 steps of an ntrack-bit word; word w, bit
+// b of a track's header is step 32*w + 31 - b (baseband/mark4/header.py:47-63)
+// so a warp ballot over 32 consecutive steps, bit-reversed, is one header
+// word.  Error flags are bits 15..12 of word 1 = steps 48..51; the frame is
+// valid iff no track has one set (baseband/mark4/frame.py:78-87).
+template <typename W>
+__global__ void __launch_bounds__(kScanBlock)
+k_mark4_scan(const uint8_t *src, const long long *frame_offset,
+             long long frame_stride, long long nframe, int track,
+             uint32_t *words5, long long *unit_offset) {
+    const int lane = threadIdx.x & 31;
+    long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nframe) return;                     // warp-uniform
+    long long off = frame_offset ? frame_offset[i] : i * frame_stride;
+    const W *st = reinterpret_cast<const W *>(src + off);
+    bool bad = false;
+#pragma unroll
+    for (int w = 0; w < 5; ++w) {
+        W v = st[32 * w + lane];
+        unsigned m = __ballot_sync(0xffffffffu, (v >> track) & 1);
+        if (words5 && lane == 0) words5[i * 5 + w] = __brev(m);
+        if (w == 1 && lane >= 16 && lane < 20 && v != 0) bad = true;
+    }
+    bad = __any_sync(0xffffffffu, bad);
+    if (unit_offset && lane == 0)
+        unit_offset[i] = bad ? -1 : off + (long long)sizeof(W) * 160;
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_vdif_scan(
+    const void *src, const int64_t *frame_offset, int64_t frame_stride,
+    int64_t nframe, int32_t header_nbytes, int32_t frames_per_set,
+    int32_t nthread, const int32_t *thread_slot, int32_t *fields,
+    int64_t *unit_offset, int32_t *n_inconsistent, void *stream) {
+    if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
+    if (header_nbytes != 16 && header_nbytes != 32)
+        return set_error(BB_ERR_ARGUMENT, "header_nbytes must be 16 or 32");
+    if (unit_offset && (!thread_slot || !n_inconsistent || frames_per_set < 1
+                        || nthread < 1))
+        return set_error(BB_ERR_ARGUMENT,
+                         "thread_slot, n_inconsistent, frames_per_set and "
+                         "nthread are needed to build unit offsets");
+    if (!aligned(src, 4) || (frame_stride & 3))
+        return set_error(BB_ERR_ALIGNMENT, "frames must be 4-byte aligned");
+    if (nframe <= 0) return BB_OK;
+    cudaStream_t s = as_stream(stream);
+    long long nunit = unit_offset ? (nframe / frames_per_set) * nthread : 0;
+    if (nunit) {
+        k_fill_i64<<<(unsigned)((nunit + 255) / 256), 256, 0, s>>>(
+            (long long *)unit_offset, kMissing, nunit);
+        BB_CHECK_LAUNCH("bb_vdif_scan fill");
+    }
+    k_vdif_scan<<<(unsigned)((nframe + kScanBlock - 1) / kScanBlock),
+                  kScanBlock, 0, s>>>(
+        (const uint8_t *)src, (const long long *)frame_offset, frame_stride,
+        nframe, header_nbytes, frames_per_set, nthread, thread_slot, fields,
+        (long long *)unit_offset, n_inconsistent);
+    BB_CHECK_LAUNCH("bb_vdif_scan");
+    if (nunit) {
+        k_count_missing<<<(unsigned)((nunit + 255) / 256), 256, 0, s>>>(
+            (long long *)unit_offset, nunit, n_inconsistent);
+        BB_CHECK_LAUNCH("bb_vdif_scan count");
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_mark5b_scan(
+    const void *src, const int64_t *frame_offset, int64_t frame_stride,
+    int64_t nframe, int32_t *fields, int64_t *unit_offset, void *stream) {
+    if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
+    if (!aligned(src, 4) || (frame_stride & 3))
+        return set_error(BB_ERR_ALIGNMENT, "frames must be 4-byte aligned");
+    if (nframe <= 0) return BB_OK;
+    k_mark5b_scan<<<(unsigned)((nframe + kScanBlock - 1) / kScanBlock),
+                    kScanBlock, 0, as_stream(stream)>>>(
+        (const uint8_t *)src, (const long long *)frame_offset, frame_stride,
+        nframe, fields, (long long *)unit_offset);
+    BB_CHECK_LAUNCH("bb_mark5b_scan");
+    return BB_OK;
+}
+
+extern "C" int bb_mark4_scan(
+    const void *src, const int64_t *frame_offset, int64_t frame_stride,
+    int64_t nframe, int32_t ntrack, int32_t track, uint32_t *words5,
+    int64_t *unit_offset, void *stream) {
+    if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
+    if (ntrack != 16 && ntrack != 32 && ntrack != 64)
+        return set_error(BB_ERR_UNSUPPORTED, "ntrack must be 16, 32 or 64");
+    if (track < 0 || track >= ntrack)
+        return set_error(BB_ERR_ARGUMENT, "track out of range");
+    if (!aligned(src, ntrack / 8) || (frame_stride % (ntrack / 8)))
+        return set_error(BB_ERR_ALIGNMENT, "frames must be word aligned");
+    if (nframe <= 0) return BB_OK;
+    unsigned grid = (unsigned)((nframe * 32 + kScanBlock - 1) / kScanBlock);
+    cudaStream_t s = as_stream(stream);
+    const uint8_t *p = (const uint8_t *)src;
+    const long long *fo = (const long long *)frame_offset;
+    if (ntrack == 64)
+        k_mark4_scan<unsigned long long><<<grid, kScanBlock, 0, s>>>(
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+    else if (ntrack == 32)
+        k_mark4_scan<uint32_t><<<grid, kScanBlock, 0, s>>>(
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+    else
+        k_mark4_scan<uint16_t><<<grid, kScanBlock, 0, s>>>(
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+    BB_CHECK_LAUNCH("bb_mark4_scan");
+    return BB_OK;
+}

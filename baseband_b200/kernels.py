@@ -1,0 +1,282 @@
+"""Thin Python wrappers over the C ABI, using torch for device memory/streams.
+
+Every function takes CUDA ``torch.Tensor`` buffers, passes raw pointers and
+the current torch stream to ``libbaseband_b200.so`` and returns a tensor.
+torch is plumbing only: all arithmetic happens in the hand-written kernels.
+There is no CPU path; CPU tensors are rejected.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (CODEC_LEVELS, CODEC_SINT, QUANT_OFFSET_BINARY,  # noqa
+                   QUANT_MARK5B, QUANT_SINT, F32, F64)
+
+_FLOATP = ctypes.POINTER(ctypes.c_float)
+
+# Counter of kernel-launching C calls, for bench.py's ``gpu_launches`` claim.
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError('{} must be a CUDA torch.Tensor (there is no CPU '
+                        'fallback)'.format(name))
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError('{} must have dtype {}'.format(name, dtype))
+    if not t.is_contiguous():
+        raise ValueError('{} must be contiguous'.format(name))
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and (not isinstance(t, torch.Tensor)
+                              or not t.is_cuda):
+            raise TypeError('arguments must be CUDA torch.Tensors (there is '
+                            'no CPU fallback)')
+
+
+def _levels_arg(levels):
+    if levels is None:
+        return None, None
+    lv = np.ascontiguousarray(levels, dtype=np.float32)
+    return lv, lv.ctypes.data_as(_FLOATP)
+
+
+def to_device_bytes(raw, device, pinned=None):
+    """numpy/bytes -> uint8 CUDA tensor (async copy on the current stream
+    when the source is pinned)."""
+    if isinstance(raw, torch.Tensor):
+        return raw.to(device, non_blocking=True)
+    arr = np.frombuffer(raw, np.uint8) if isinstance(
+        raw, (bytes, bytearray, memoryview)) else np.ascontiguousarray(
+            raw).view(np.uint8).reshape(-1)
+    t = torch.from_numpy(arr) if arr.flags.writeable else torch.from_numpy(
+        arr.copy())
+    return t.to(device, non_blocking=True)
+
+
+def decode_bitfield(src, unit_offset, nset, nthread, payload_nbytes, bps,
+                    nelem, complex_data=False, codec=CODEC_LEVELS,
+                    levels=None, fill_value=0.0, sample_start=0,
+                    nsample=None, out=None):
+    """bb_decode_bitfield -> float32 tensor (nsample, nthread, nelem)."""
+    lib = _lib.load()
+    _require_cuda(src, unit_offset, out)
+    spf = payload_nbytes * 8 // (bps * nelem)
+    if nsample is None:
+        nsample = nset * spf - sample_start
+    if out is None:
+        out = torch.empty((nsample, nthread, nelem), dtype=torch.float32,
+                          device=src.device)
+    elif out.numel() != nsample * nthread * nelem:
+        raise ValueError('out has the wrong number of elements')
+    keep, lv = _levels_arg(levels)
+    with torch.cuda.device(src.device):
+        rc = lib.bb_decode_bitfield(
+            _dev(src, 'src', torch.uint8), _dev(unit_offset, 'unit_offset',
+                                                torch.int64),
+            nset, nthread, payload_nbytes, bps, nelem, int(bool(complex_data)),
+            codec, lv, float(fill_value), sample_start, nsample,
+            _dev(out, 'out', torch.float32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return out
+
+
+def encode_bitfield(data, dst, unit_offset, nset, nthread, payload_nbytes,
+                    bps, nelem, quantiser=QUANT_OFFSET_BINARY):
+    """bb_encode_bitfield: quantise+pack ``data`` (float32/float64, logical
+    shape (nset*spf, nthread, nelem)) into ``dst`` (uint8) at the unit
+    offsets."""
+    lib = _lib.load()
+    _require_cuda(data, dst, unit_offset)
+    if data.dtype == torch.float32:
+        code = F32
+    elif data.dtype == torch.float64:
+        code = F64
+    else:
+        raise TypeError('data must be float32 or float64')
+    with torch.cuda.device(dst.device):
+        rc = lib.bb_encode_bitfield(
+            _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nset, nthread,
+            payload_nbytes, bps, nelem, quantiser, _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst
+
+
+def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
+                 levels=None, fill_value=0.0, sample_start=0, nsample=None,
+                 out=None):
+    lib = _lib.load()
+    spf = 20000 * fanout
+    if nsample is None:
+        nsample = nframe * spf - sample_start
+    if out is None:
+        out = torch.empty((nsample, nchan), dtype=torch.float32,
+                          device=src.device)
+    keep, lv = _levels_arg(levels)
+    with torch.cuda.device(src.device):
+        rc = lib.bb_mark4_decode(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nframe, nchan,
+            fanout, int(bool(ft)), lv, float(fill_value), sample_start,
+            nsample, _dev(out, 'out', torch.float32),
+            _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return out
+
+
+def mark4_encode(data, dst, unit_offset, nframe, nchan, fanout, ft=False):
+    lib = _lib.load()
+    code = F32 if data.dtype == torch.float32 else F64
+    with torch.cuda.device(dst.device):
+        rc = lib.bb_mark4_encode(
+            _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nframe, nchan,
+            fanout, int(bool(ft)), _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst
+
+
+def mark4_decode_words(words, nword, nchan, fanout, ft=False, levels=None,
+                       out=None):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty((nword * fanout, nchan), dtype=torch.float32,
+                          device=words.device)
+    keep, lv = _levels_arg(levels)
+    with torch.cuda.device(words.device):
+        rc = lib.bb_mark4_decode_words(
+            _dev(words, 'words'), nword, nchan, fanout, int(bool(ft)), lv,
+            _dev(out, 'out', torch.float32), _stream_ptr(words.device))
+    _lib.check(rc, lib)
+    _count()
+    return out
+
+
+def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
+    lib = _lib.load()
+    code = F32 if data.dtype == torch.float32 else F64
+    with torch.cuda.device(words.device):
+        rc = lib.bb_mark4_encode_words(
+            _dev(data, 'data'), code, _dev(words, 'words'), nword, nchan,
+            fanout, int(bool(ft)), _stream_ptr(words.device))
+    _lib.check(rc, lib)
+    _count()
+    return words
+
+
+def decode_int8_transposed(src, unit_offset, nunit, nrow, ncol, item_nbytes,
+                           col_begin, col_end, out_col0, out):
+    lib = _lib.load()
+    with torch.cuda.device(src.device):
+        rc = lib.bb_decode_int8_transposed(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nunit, nrow, ncol,
+            item_nbytes, _dev(col_begin, 'col_begin', torch.int64),
+            _dev(col_end, 'col_end', torch.int64),
+            _dev(out_col0, 'out_col0', torch.int64),
+            _dev(out, 'out', torch.float32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return out
+
+
+def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
+                           item_nbytes):
+    lib = _lib.load()
+    code = F32 if data.dtype == torch.float32 else F64
+    with torch.cuda.device(dst.device):
+        rc = lib.bb_encode_int8_transposed(
+            _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nunit, nrow, ncol,
+            item_nbytes, _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst
+
+
+VDIF_NFIELD = 17
+M5B_NFIELD = 12
+
+
+def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
+              thread_slot, nthread, frame_offset=None):
+    """bb_vdif_scan -> (fields int32 (NFIELD, nframe), unit_offset int64
+    (nset*nthread,), n_inconsistent int)."""
+    lib = _lib.load()
+    dev = src.device
+    fields = torch.empty((VDIF_NFIELD, nframe), dtype=torch.int32, device=dev)
+    nset = nframe // frames_per_set
+    unit_offset = torch.full((max(nset * nthread, 1),), -1,
+                             dtype=torch.int64, device=dev)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bb_vdif_scan(
+            _dev(src, 'src', torch.uint8),
+            None if frame_offset is None else _dev(frame_offset,
+                                                   'frame_offset',
+                                                   torch.int64),
+            frame_stride, nframe, header_nbytes, frames_per_set, nthread,
+            _dev(thread_slot, 'thread_slot', torch.int32),
+            _dev(fields, 'fields'), _dev(unit_offset, 'unit_offset'),
+            _dev(bad, 'bad'), _stream_ptr(dev))
+    _lib.check(rc, lib)
+    _count()
+    return fields, unit_offset[:nset * nthread], bad
+
+
+def mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
+    lib = _lib.load()
+    dev = src.device
+    fields = torch.empty((M5B_NFIELD, nframe), dtype=torch.int32, device=dev)
+    unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bb_mark5b_scan(
+            _dev(src, 'src', torch.uint8),
+            None if frame_offset is None else _dev(frame_offset,
+                                                   'frame_offset',
+                                                   torch.int64),
+            frame_stride, nframe, _dev(fields, 'fields'),
+            _dev(unit_offset, 'unit_offset'), _stream_ptr(dev))
+    _lib.check(rc, lib)
+    _count()
+    return fields, unit_offset
+
+
+def mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
+               frame_offset=None):
+    lib = _lib.load()
+    dev = src.device
+    if frame_stride is None:
+        frame_stride = ntrack * 2500
+    words5 = torch.empty((nframe, 5), dtype=torch.int32, device=dev)
+    unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.bb_mark4_scan(
+            _dev(src, 'src', torch.uint8),
+            None if frame_offset is None else _dev(frame_offset,
+                                                   'frame_offset',
+                                                   torch.int64),
+            frame_stride, nframe, ntrack, track, _dev(words5, 'words5'),
+            _dev(unit_offset, 'unit_offset'), _stream_ptr(dev))
+    _lib.check(rc, lib)
+    _count()
+    return words5, unit_offset

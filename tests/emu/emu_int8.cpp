@@ -1,0 +1,67 @@
+// CPU emulation of the int8 transpose kernels — TEST INFRASTRUCTURE ONLY.
+// The two per-thread phases of each CTA are run as two loops.
+#include <vector>
+#include "../../baseband_b200/csrc/bb_int8.cuh"
+#include "../../include/baseband_b200.h"
+
+using namespace bb;
+
+static bool geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol, int ib,
+                 uint64_t &nblocks) {
+    if (ib != 1 && ib != 2) return false;
+    g.nunit = (uint32_t)nunit; g.nrow = (uint32_t)nrow; g.ncol = (uint32_t)ncol;
+    g.ib = ib;
+    g.tiles_r = (uint32_t)((nrow + kI8Rows - 1) / kI8Rows);
+    uint32_t tc = kI8RowBytes / ib;
+    g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
+    nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
+    return true;
+}
+
+extern "C" {
+
+int bb_decode_int8_transposed(const void *src, const int64_t *unit_offset,
+                              int64_t nunit, int64_t nrow, int64_t ncol,
+                              int32_t item_nbytes, const int64_t *col_begin,
+                              const int64_t *col_end, const int64_t *out_col0,
+                              float *out, void *stream) {
+    I8Geom g;
+    uint64_t nblocks;
+    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks)) return BB_ERR_ARGUMENT;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.col_begin = (const long long *)col_begin;
+    g.col_end = (const long long *)col_end;
+    g.out_col0 = (const long long *)out_col0;
+    g.out = out; g.in = nullptr;
+    alignas(16) uint8_t tile[kI8SmemBytes];
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        for (uint32_t t = 0; t < kI8Threads; ++t) i8_dec_load(g, tile, (uint32_t)b, t);
+        for (uint32_t t = 0; t < kI8Threads; ++t) i8_dec_store(g, tile, (uint32_t)b, t);
+    }
+    return 0;
+}
+
+int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
+                              const int64_t *unit_offset, int64_t nunit,
+                              int64_t nrow, int64_t ncol, int32_t item_nbytes,
+                              void *stream) {
+    I8Geom g;
+    uint64_t nblocks;
+    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks)) return BB_ERR_ARGUMENT;
+    g.src = (const uint8_t *)dst;
+    g.unit_offset = (const long long *)unit_offset;
+    g.col_begin = g.col_end = g.out_col0 = nullptr;
+    g.out = nullptr; g.in = in;
+    alignas(16) uint8_t tile[kI8SmemBytes];
+    for (uint64_t b = 0; b < nblocks; ++b) {
+        for (uint32_t t = 0; t < kI8Threads; ++t) {
+            if (in_dtype == BB_F32) i8_enc_load<float>(g, tile, (uint32_t)b, t);
+            else i8_enc_load<double>(g, tile, (uint32_t)b, t);
+        }
+        for (uint32_t t = 0; t < kI8Threads; ++t) i8_enc_store(g, tile, (uint32_t)b, t);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+"""Shared int8-transpose cases (GUPPI channels-first, MKBF heaps)."""
+import zlib
+
+import numpy as np
+
+from oracle import codec
+
+# (id, nunit, nrow, ncol, item_nbytes, windows [(col_begin, col_end)] or None)
+CASES = [
+    ('guppi_512ch_2pol', 2, 512, 256 * 2, 2, None),
+    ('guppi_overlap', 3, 64, 200 * 2, 2, [(0, 400), (32, 400), (32, 400)]),
+    ('guppi_4ch_puppi_like', 4, 4, 1024 * 2, 2, [(0, 2048)] + [(128, 2048)] * 3),
+    ('guppi_partial_read', 2, 96, 300, 2, [(7, 300), (0, 123)]),
+    ('real_1byte_items', 2, 40, 333, 1, [(5, 333), (0, 300)]),
+    ('mkbf_heaps', 6, 2 * 16, 256, 2, None),
+    ('odd_rows', 1, 33, 130, 2, None),
+    ('invalid_unit', 3, 32, 64, 2, None),
+]
+
+
+def make_case(case):
+    cid, nunit, nrow, ncol, ib, windows = case
+    rng = np.random.default_rng(zlib.crc32(cid.encode()))
+    unit_nbytes = nrow * ncol * ib
+    gap = 16
+    raw = rng.integers(0, 256, nunit * (unit_nbytes + gap) + 16,
+                       dtype=np.uint8)
+    order = rng.permutation(nunit)
+    truth = (order * (unit_nbytes + gap)).astype(np.int64)
+    unit_offset = truth.copy()
+    if cid == 'invalid_unit':
+        unit_offset[1] = -1
+    if windows is None:
+        windows = [(0, ncol)] * nunit
+    cb = np.array([w[0] for w in windows], np.int64)
+    ce = np.array([w[1] for w in windows], np.int64)
+    oc0 = np.concatenate([[0], np.cumsum(ce - cb)[:-1]]).astype(np.int64)
+    return dict(id=cid, nunit=nunit, nrow=nrow, ncol=ncol, ib=ib, raw=raw,
+                truth=truth, unit_offset=unit_offset, col_begin=cb,
+                col_end=ce, out_col0=oc0, ncols_out=int((ce - cb).sum()),
+                unit_nbytes=unit_nbytes)
+
+
+def oracle_decode(c, fill=np.nan):
+    """out[col][row][ib] float32; untouched (invalid) units keep ``fill``."""
+    out = np.full((c['ncols_out'], c['nrow'], c['ib']), np.float32(fill))
+    for u in range(c['nunit']):
+        if c['unit_offset'][u] < 0:
+            continue
+        o = c['truth'][u]
+        unit = c['raw'][o:o + c['unit_nbytes']].view(np.int8).reshape(
+            c['nrow'], c['ncol'], c['ib'])
+        dec = codec.int8_decode(unit.ravel()).reshape(unit.shape)
+        cb, ce, oc0 = c['col_begin'][u], c['col_end'][u], c['out_col0'][u]
+        out[oc0:oc0 + ce - cb] = dec[:, cb:ce].transpose(1, 0, 2)
+    return out

@@ -113,3 +113,173 @@ def test_golden_decode_vectors(emu, codec_vectors):
                                     _ptr(base), None)
         assert rc == 0
         assert np.array_equal(base, want), key
+
+
+# ------------------------------------------------------------------ Mark 4
+from mark4_cases import MODES, FRAME_CASES, make_frames, oracle_frames  # noqa
+from baseband_b200 import levels as _levels  # noqa
+
+_FP = ctypes.POINTER(ctypes.c_float)
+
+
+def _aligned_f32(n):
+    buf = np.full(n + 8, np.float32(np.nan))
+    return buf[(-buf.ctypes.data // 4) % 4:][:n]
+
+
+@pytest.mark.parametrize('tag', sorted(MODES))
+def test_mark4_words_golden(emu, codec_vectors, tag):
+    """One-hot and random words against the reference decoders, and the
+    reference encoders on threshold-hugging inputs."""
+    g = codec_vectors
+    nchan, fanout, ft = MODES[tag]
+    words = np.ascontiguousarray(g['m4_words_' + tag])
+    want = g['m4_dec_' + tag]
+    out = _aligned_f32(want.size)
+    lv = np.ascontiguousarray(_levels.sign_magnitude(), np.float32)
+    rc = emu.bb_mark4_decode_words(_ptr(words), words.size, nchan, fanout,
+                                   int(ft), lv.ctypes.data_as(_FP), _ptr(out),
+                                   None)
+    assert rc == 0
+    assert np.array_equal(out.reshape(want.shape).view('u4'), want.view('u4'))
+    for ftag, code in (('f32', 0), ('f64', 1)):
+        vals = g['m4_enc_in_%s_%s' % (tag, ftag)]
+        src = np.zeros(vals.size + 4, vals.dtype)
+        sh = (-src.ctypes.data // vals.itemsize) % (16 // vals.itemsize)
+        src = src[sh:sh + vals.size]
+        src[:] = vals.ravel()
+        wantw = g['m4_enc_%s_%s' % (tag, ftag)]
+        got = np.zeros(wantw.size, np.uint8)
+        nword = vals.shape[0] // fanout
+        rc = emu.bb_mark4_encode_words(_ptr(src), code, _ptr(got), nword,
+                                       nchan, fanout, int(ft), None)
+        assert rc == 0
+        assert np.array_equal(got, wantw), (tag, ftag)
+
+
+@pytest.mark.parametrize('case', FRAME_CASES, ids=lambda c: c[0])
+def test_mark4_frames(emu, case):
+    cid, mode, nframe, invalid, start, count, fill = case
+    c = make_frames(mode, nframe, invalid, cid)
+    want = oracle_frames(c, fill, start, count)
+    out = _aligned_f32(want.size)
+    lv = np.ascontiguousarray(_levels.sign_magnitude(), np.float32)
+    rc = emu.bb_mark4_decode(_ptr(c['raw']), _ptr(c['unit_offset']), nframe,
+                             c['nchan'], c['fanout'], int(c['ft']),
+                             lv.ctypes.data_as(_FP), fill, start,
+                             want.shape[0], _ptr(out), None)
+    assert rc == 0, emu.emu_mark4_error()
+    assert np.array_equal(out.reshape(want.shape).view('u4'), want.view('u4'))
+    # encode the full decoded frames back: payload words must be identical
+    full = oracle_frames(c, 0.0, 0, None)
+    src = _aligned_f32(full.size)
+    src[:] = full.ravel()
+    dst = c['raw'].copy()
+    for f in range(nframe):
+        if c['unit_offset'][f] >= 0:
+            o = c['truth'][f]
+            dst[o:o + c['payload_nbytes']] = 0
+    rc = emu.bb_mark4_encode(_ptr(src), 0, _ptr(dst), _ptr(c['unit_offset']),
+                             nframe, c['nchan'], c['fanout'], int(c['ft']),
+                             None)
+    assert rc == 0
+    assert np.array_equal(dst, c['raw'])
+
+
+def test_mark4_sample_file(emu, sample_outputs):
+    from conftest import sample_bytes
+    raw = sample_bytes('sample.m4')
+    off0 = int(sample_outputs['sample_m4_offset0'])
+    want = sample_outputs['sample_m4_data']
+    nframe = want.shape[0] // 80000
+    src = np.zeros(raw.size + 16, np.uint8)
+    sh = (-src.ctypes.data - off0) % 8
+    src = src[sh:sh + raw.size]
+    src[:] = raw
+    uo = (off0 + np.arange(nframe) * 160000 + 1280).astype(np.int64)
+    out = _aligned_f32(want.size)
+    lv = np.ascontiguousarray(_levels.sign_magnitude(), np.float32)
+    rc = emu.bb_mark4_decode(_ptr(src), _ptr(uo), nframe, 8, 4, 0,
+                             lv.ctypes.data_as(_FP), -7.0, 0, want.shape[0],
+                             _ptr(out), None)
+    assert rc == 0
+    assert np.array_equal(out.reshape(want.shape), want)
+
+
+# --------------------------------------------------------- int8 transposed
+import int8_cases  # noqa: E402
+
+
+@pytest.mark.parametrize('case', int8_cases.CASES, ids=lambda c: c[0])
+def test_int8_transposed(emu, case):
+    c = int8_cases.make_case(case)
+    want = int8_cases.oracle_decode(c)
+    out = _aligned_f32(want.size)
+    rc = emu.bb_decode_int8_transposed(
+        _ptr(c['raw']), _ptr(c['unit_offset']), c['nunit'], c['nrow'],
+        c['ncol'], c['ib'], _ptr(c['col_begin']), _ptr(c['col_end']),
+        _ptr(c['out_col0']), _ptr(out), None)
+    assert rc == 0
+    assert np.array_equal(out.reshape(want.shape), want, equal_nan=True)
+    # encode whole units back (full windows) and compare the packed bytes
+    full = dict(c, col_begin=np.zeros(c['nunit'], np.int64),
+                col_end=np.full(c['nunit'], c['ncol'], np.int64),
+                out_col0=np.arange(c['nunit'], dtype=np.int64) * c['ncol'],
+                ncols_out=c['nunit'] * c['ncol'])
+    data = int8_cases.oracle_decode(full, fill=0.0)
+    for dtype, code in ((np.float32, 0), (np.float64, 1)):
+        src = np.ascontiguousarray(data, dtype)
+        dst = c['raw'].copy()
+        for u in range(c['nunit']):
+            if c['unit_offset'][u] >= 0:
+                dst[c['truth'][u]:c['truth'][u] + c['unit_nbytes']] = 0
+        rc = emu.bb_encode_int8_transposed(
+            _ptr(src), code, _ptr(dst), _ptr(c['unit_offset']), c['nunit'],
+            c['nrow'], c['ncol'], c['ib'], None)
+        assert rc == 0
+        assert np.array_equal(dst, c['raw'])
+
+
+def test_int8_guppi_sample(emu, sample_outputs):
+    """sample_puppi.raw frames through the transpose path == reference
+    GUPPIPayload.data (channels first)."""
+    from conftest import sample_bytes
+    from oracle import stream
+    raw = sample_bytes('sample_puppi.raw')
+    frames = stream.guppi_scan(raw)
+    h = frames[0]
+    nrow, ncol = h['nchan'], h['samples_per_frame'] * h['npol']
+    uo = np.array([f['offset'] + f['header_nbytes'] for f in frames], np.int64)
+    n = len(frames)
+    cb = np.zeros(n, np.int64)
+    ce = np.full(n, ncol, np.int64)
+    oc0 = np.arange(n, dtype=np.int64) * ncol
+    want = sample_outputs['sample_puppi_frames']      # (n, spf, npol, nchan)
+    out = _aligned_f32(want.size * 2)
+    rc = emu.bb_decode_int8_transposed(_ptr(raw), _ptr(uo), n, nrow, ncol, 2,
+                                       _ptr(cb), _ptr(ce), _ptr(oc0),
+                                       _ptr(out), None)
+    assert rc == 0
+    got = out.view(np.complex64).reshape(want.shape)
+    assert np.array_equal(got, want)
+
+
+def test_int8_mkbf_sample(emu, sample_outputs):
+    from conftest import sample_bytes
+    from oracle import stream
+    raw = sample_bytes('sample_mkbf.dada')
+    h = stream.dada_parse_header(raw)
+    want = sample_outputs['sample_mkbf_dada_data']     # (nsample, npol, nchan)
+    nheap = want.shape[0] // 256
+    nrow = h['npol'] * h['nchan']
+    heap_nbytes = nrow * 256 * 2
+    uo = (h['header_nbytes'] + np.arange(nheap) * heap_nbytes).astype(np.int64)
+    cb = np.zeros(nheap, np.int64)
+    ce = np.full(nheap, 256, np.int64)
+    oc0 = np.arange(nheap, dtype=np.int64) * 256
+    out = _aligned_f32(want.size * 2)
+    rc = emu.bb_decode_int8_transposed(_ptr(raw), _ptr(uo), nheap, nrow, 256,
+                                       2, _ptr(cb), _ptr(ce), _ptr(oc0),
+                                       _ptr(out), None)
+    assert rc == 0
+    assert np.array_equal(out.view(np.complex64).reshape(want.shape), want)

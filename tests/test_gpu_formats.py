@@ -1,0 +1,191 @@
+"""GPU parity for the Mark 4, int8-transpose and header-scan kernels (through
+the C ABI) against the oracle, the reference golden vectors and the
+reference's sample files."""
+import numpy as np
+import pytest
+import torch
+
+from baseband_b200 import kernels, levels
+from oracle import codec, headers, stream
+from conftest import sample_bytes
+from mark4_cases import MODES, FRAME_CASES, make_frames, oracle_frames
+import int8_cases
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.mark.parametrize('tag', sorted(MODES))
+def test_mark4_words_golden(codec_vectors, tag):
+    g = codec_vectors
+    nchan, fanout, ft = MODES[tag]
+    words = g['m4_words_' + tag]
+    want = g['m4_dec_' + tag]
+    out = kernels.mark4_decode_words(_t(words.view(np.uint8)), words.size,
+                                     nchan, fanout, ft,
+                                     levels.sign_magnitude())
+    assert np.array_equal(out.cpu().numpy().view('u4'), want.view('u4'))
+    for ftag in ('f32', 'f64'):
+        vals = g['m4_enc_in_%s_%s' % (tag, ftag)]
+        wantw = g['m4_enc_%s_%s' % (tag, ftag)]
+        dst = torch.zeros(wantw.size, dtype=torch.uint8, device=DEV)
+        kernels.mark4_encode_words(_t(vals), dst, vals.shape[0] // fanout,
+                                   nchan, fanout, ft)
+        assert np.array_equal(dst.cpu().numpy(), wantw), (tag, ftag)
+    with pytest.raises(KeyError):       # no such decoder (fanout 1)
+        kernels.mark4_decode_words(_t(words.view(np.uint8)), 4, 16, 1, False,
+                                   levels.sign_magnitude())
+
+
+@pytest.mark.parametrize('case', FRAME_CASES, ids=lambda c: c[0])
+def test_mark4_frames(case):
+    cid, mode, nframe, invalid, start, count, fill = case
+    c = make_frames(mode, nframe, invalid, cid)
+    want = oracle_frames(c, fill, start, count)
+    raw, uo = _t(c['raw']), _t(c['unit_offset'])
+    out = kernels.mark4_decode(raw, uo, nframe, c['nchan'], c['fanout'],
+                               c['ft'], levels.sign_magnitude(), fill, start,
+                               want.shape[0])
+    assert np.array_equal(out.cpu().numpy().view('u4'), want.view('u4'))
+    full = oracle_frames(c, 0.0, 0, None)
+    dst = c['raw'].copy()
+    for f in range(nframe):
+        if c['unit_offset'][f] >= 0:
+            o = c['truth'][f]
+            dst[o:o + c['payload_nbytes']] = 0
+    dst = _t(dst)
+    kernels.mark4_encode(_t(full), dst, uo, nframe, c['nchan'], c['fanout'],
+                         c['ft'])
+    assert np.array_equal(dst.cpu().numpy(), c['raw'])
+
+
+@pytest.mark.parametrize('name,ntrack', [
+    ('sample.m4', 64), ('sample_32track.m4', 32),
+    ('sample_32track_fanout2.m4', 32), ('sample_16track.m4', 16),
+    ('sample_64track_fanout2_ft.m4', 64)])
+def test_mark4_sample_files(sample_outputs, name, ntrack):
+    """Frames located, header-parsed and decoded on the GPU == reference
+    Mark4Frame.data (incl. the header-overwritten fill region)."""
+    tag = name.replace('.', '_')
+    raw = sample_bytes(name)
+    off0 = int(sample_outputs[tag + '_offset0'])
+    want = sample_outputs[tag + '_data']
+    _, fanout, nchan, _, spf = [int(v) for v in sample_outputs[tag + '_geom']]
+    nframe = want.shape[0] // spf
+    frame_nbytes = ntrack * 2500
+    dev = _t(raw[off0:off0 + nframe * frame_nbytes])     # re-based, aligned
+    words5, uo = kernels.mark4_scan(dev, nframe, ntrack, track=0)
+    assert bool((uo >= 0).all())
+    ft = name.endswith('_ft.m4')
+    out = kernels.mark4_decode(dev, uo, nframe, nchan, fanout, ft,
+                               levels.sign_magnitude(), -7.0)
+    assert np.array_equal(out.cpu().numpy(), want)
+    # header words of track 0 against the oracle's stream2words
+    dt = codec.MARK4_WORD_DTYPE[ntrack]
+    for f in range(nframe):
+        st = raw[off0 + f * frame_nbytes:][:ntrack * 20].view(dt)
+        w = headers.mark4_stream2words(st)
+        assert np.array_equal(words5[f].cpu().numpy().view(np.uint32),
+                              w[:, 0])
+
+
+def test_mark4_scan_invalid():
+    c = make_frames('8_4', 3, (), 'scan')
+    raw = np.zeros(3 * 160000, np.uint8)
+    for f in range(3):
+        o = c['truth'][f] - 1280
+        raw[f * 160000:(f + 1) * 160000] = c['raw'][o:o + 160000]
+    st = raw.view('<u8')
+    st[:160] = 0                       # frame 0: no error flags
+    st[20000:20160] = 0
+    st[20000 + 50] = 1 << 37          # frame 1: an error flag on track 37
+    st[40000:40160] = 0
+    st[40000 + 52] = 1                 # frame 2: bit just outside the flags
+    _, uo = kernels.mark4_scan(_t(raw), 3, 64)
+    assert uo.cpu().tolist() == [1280, -1, 2 * 160000 + 1280]
+
+
+@pytest.mark.parametrize('case', int8_cases.CASES, ids=lambda c: c[0])
+def test_int8_transposed(case):
+    c = int8_cases.make_case(case)
+    want = int8_cases.oracle_decode(c)
+    out = torch.full((want.size,), float('nan'), dtype=torch.float32,
+                     device=DEV)
+    kernels.decode_int8_transposed(
+        _t(c['raw']), _t(c['unit_offset']), c['nunit'], c['nrow'], c['ncol'],
+        c['ib'], _t(c['col_begin']), _t(c['col_end']), _t(c['out_col0']), out)
+    assert np.array_equal(out.cpu().numpy().reshape(want.shape), want,
+                          equal_nan=True)
+    full = dict(c, col_begin=np.zeros(c['nunit'], np.int64),
+                col_end=np.full(c['nunit'], c['ncol'], np.int64),
+                out_col0=np.arange(c['nunit'], dtype=np.int64) * c['ncol'],
+                ncols_out=c['nunit'] * c['ncol'])
+    data = int8_cases.oracle_decode(full, fill=0.0)
+    for dtype in (np.float32, np.float64):
+        dst = c['raw'].copy()
+        for u in range(c['nunit']):
+            if c['unit_offset'][u] >= 0:
+                dst[c['truth'][u]:c['truth'][u] + c['unit_nbytes']] = 0
+        dst = _t(dst)
+        kernels.encode_int8_transposed(_t(data.astype(dtype)), dst,
+                                       _t(c['unit_offset']), c['nunit'],
+                                       c['nrow'], c['ncol'], c['ib'])
+        assert np.array_equal(dst.cpu().numpy(), c['raw'])
+
+
+def test_vdif_scan_sample(sample_outputs):
+    raw = sample_bytes('sample.vdif')
+    fields_want = sample_outputs['sample_vdif_fields']
+    nframe = len(fields_want)
+    slot = torch.full((1024,), -1, dtype=torch.int32, device=DEV)
+    slot[:8] = torch.arange(8, dtype=torch.int32)
+    fields, uo, bad = kernels.vdif_scan(_t(raw), nframe, 5032, 32, 8, slot, 8)
+    f = fields.cpu().numpy()
+    assert np.array_equal(f[:12].T, fields_want[:, :12])
+    assert np.array_equal(f[12], fields_want[:, 12])
+    assert int(bad.item()) == 0
+    # file order of thread ids is 1,3,5,7,0,2,4,6 -> slots sorted by id
+    tid = fields_want[:, 10]
+    want_uo = np.empty(16, np.int64)
+    for i in range(nframe):
+        want_uo[(i // 8) * 8 + tid[i]] = i * 5032 + 32
+    assert np.array_equal(uo.cpu().numpy(), want_uo)
+    # decode through the table == reference VDIFFrameSet data
+    out = kernels.decode_bitfield(_t(raw), uo, 2, 8, 5000, 2, 1, False, 0,
+                                  levels.offset_binary(2))
+    assert np.array_equal(out.cpu().numpy(), sample_outputs['sample_vdif_data'])
+    # subset of threads, invalid frames, and an inconsistent set
+    raw2 = raw.copy()
+    raw2[5032 * 2 + 3] |= 0x80                 # frame 2 (thread 5) invalid
+    slot2 = torch.full((1024,), -1, dtype=torch.int32, device=DEV)
+    slot2[5], slot2[2] = 0, 1
+    _, uo2, bad2 = kernels.vdif_scan(_t(raw2), nframe, 5032, 32, 8, slot2, 2)
+    assert uo2.cpu().tolist() == [-1, 5 * 5032 + 32,
+                                  10 * 5032 + 32, 13 * 5032 + 32]
+    assert int(bad2.item()) == 0
+    raw3 = raw.copy()
+    raw3[5032 * 3 + 4] ^= 1                    # frame_nr of one frame differs
+    _, _, bad3 = kernels.vdif_scan(_t(raw3), nframe, 5032, 32, 8, slot, 8)
+    assert int(bad3.item()) == 1
+
+
+def test_mark5b_scan_sample(sample_outputs):
+    raw = sample_bytes('sample.m5b').copy()
+    raw[10016 + 16:2 * 10016].view('<u4')[:] = 0x11223344   # frame 1 invalid
+    raw[2 * 10016 + 16:3 * 10016].view('<u4')[:] = 0x11223344
+    raw[2 * 10016 + 16 + 4 * 2499] ^= 0x10     # frame 2: last word differs
+    fields, uo = kernels.mark5b_scan(_t(raw), 4)
+    f = fields.cpu().numpy()
+    want = sample_outputs['sample_m5b_fields']
+    assert np.array_equal(f[:11].T.astype(np.int64) & 0xffffffff,
+                          want & 0xffffffff)
+    assert f[11].tolist() == [1, 0, 1, 1]
+    assert uo.cpu().tolist() == [16, -1, 2 * 10016 + 16, 3 * 10016 + 16]
+    out = kernels.decode_bitfield(_t(raw), uo, 4, 1, 10000, 2, 8, False, 0,
+                                  levels.mark5b(2), fill_value=-999.)
+    assert np.array_equal(out.cpu().numpy()[:, 0],
+                          stream.mark5b_read(raw, 8, fill_value=-999.))
