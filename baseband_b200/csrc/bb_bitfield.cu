@@ -8,43 +8,64 @@
 namespace bb {
 
 constexpr int kBlock = 256;
-constexpr int kCtasPerSm = 8;       // 2048 resident threads per SM
 
-// The decode table lives in shared memory (see DecodeLut): built once per
-// CTA from the per-code levels in the kernel parameters; the grid is sized to
-// the machine and strides over the items, so the build cost is amortised.
+// Launch shape.  Measured on B200 (profiles/r1_grid_sweep.txt): for these
+// write-dominated streams a plain one-shot grid in which every CTA produces a
+// compact ~64 KiB tile of output beats a persistent grid-stride loop by ~18 %
+// (6.4 vs 5.4 TB/s), and tiny CTAs (4 KiB) are far worse.  So every thread
+// handles kUnroll items, kBlock apart, sized so a thread writes ~16 float4.
+template <int BPS, int MODE>
+struct Unroll {
+    static constexpr int kF4PerItem =
+        MODE == MODE_ROWGROUP4 ? 32 / BPS
+        : MODE == MODE_ROWGROUP2 ? 16 / BPS : 1;
+    static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
+};
+
+inline unsigned tile_grid(uint32_t nitems, int unroll) {
+    uint64_t per_cta = (uint64_t)kBlock * unroll;
+    return (unsigned)((nitems + per_cta - 1) / per_cta);
+}
+
+// The decode table lives in shared memory (see DecodeLut): built per CTA from
+// the per-code levels in the kernel parameters (at most 256 floats).
 template <int BPS, int CODEC, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
     using Lut = DecodeLut<BPS>;
-    __shared__ __align__(16) float lut[CODEC == CODEC_LEVELS ? Lut::kFloats : 2];
+    constexpr int U = Unroll<BPS, MODE>::value;
+    __shared__ __align__(128) float lut[CODEC == CODEC_LEVELS ? Lut::kFloats : 2];
     if (CODEC == CODEC_LEVELS) {
         for (int i = threadIdx.x; i < Lut::kFloats; i += kBlock)
             lut[i] = Lut::value(lv.v, i);
         __syncthreads();
     }
-    const uint32_t stride = gridDim.x * kBlock;
-    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < p.nitems;
-         item += stride) {
+    const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kBlock;
+        if (item >= p.nitems) break;
         if (MODE == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(p, lut, item);
         else if (MODE == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(p, lut, item);
         else if (MODE == MODE_RUN) dec_run<BPS, CODEC>(p, lut, item);
         else dec_scalar<BPS, CODEC>(p, lut, item);
-        if (item + stride < item) break;       // 32-bit wrap guard
     }
 }
 
 template <typename T, int BPS, int QUANT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
-    const uint32_t stride = gridDim.x * kBlock;
-    for (uint32_t item = blockIdx.x * kBlock + threadIdx.x; item < p.nitems;
-         item += stride) {
+    constexpr int U = (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
+        ? Unroll<BPS, MODE>::value : 4;
+    const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kBlock;
+        if (item >= p.nitems) break;
         if (MODE == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(p, c, item);
         else if (MODE == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(p, c, item);
         else if (MODE == MODE_RUN) enc_word<T, BPS, QUANT, true>(p, c, item);
         else enc_word<T, BPS, QUANT, false>(p, c, item);
-        if (item + stride < item) break;
     }
 }
 
@@ -55,23 +76,27 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
     for (int i = 0; i < (1 << BPS); ++i)
         lv.v[i] = (CODEC == CODEC_LEVELS && levels_host) ? levels_host[i] : 0.f;
     for (const DecLaunch &l : launches) {
-        unsigned grid = stream_grid(l.g.nitems, kBlock, kCtasPerSm);
+        const uint32_t n = l.g.nitems;
         switch (l.mode) {
         case MODE_ROWGROUP4:
             k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP4>
-                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP4>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
             break;
         case MODE_ROWGROUP2:
             k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP2>
-                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP2>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
             break;
         case MODE_RUN:
             k_decode_bitfield<BPS, CODEC, MODE_RUN>
-                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+                <<<tile_grid(n, Unroll<BPS, MODE_RUN>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
             break;
         default:
             k_decode_bitfield<BPS, CODEC, MODE_SCALAR>
-                <<<grid, kBlock, 0, stream>>>(l.g, lv);
+                <<<tile_grid(n, Unroll<BPS, MODE_SCALAR>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
         }
         BB_CHECK_LAUNCH("bb_decode_bitfield launch");
     }
@@ -83,23 +108,25 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
                          cudaStream_t stream) {
     static const QuantConsts<T> consts = make_quant_consts<T>();
     for (const EncLaunch &l : launches) {
-        unsigned grid = stream_grid(l.g.nitems, kBlock, kCtasPerSm);
+        const uint32_t n = l.g.nitems;
         switch (l.mode) {
         case MODE_ROWGROUP4:
             k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP4>
-                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP4>::value), kBlock, 0,
+                   stream>>>(l.g, consts);
             break;
         case MODE_ROWGROUP2:
             k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP2>
-                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP2>::value), kBlock, 0,
+                   stream>>>(l.g, consts);
             break;
         case MODE_RUN:
             k_encode_bitfield<T, BPS, QUANT, MODE_RUN>
-                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+                <<<tile_grid(n, 4), kBlock, 0, stream>>>(l.g, consts);
             break;
         default:
             k_encode_bitfield<T, BPS, QUANT, MODE_SCALAR>
-                <<<grid, kBlock, 0, stream>>>(l.g, consts);
+                <<<tile_grid(n, 4), kBlock, 0, stream>>>(l.g, consts);
         }
         BB_CHECK_LAUNCH("bb_encode_bitfield launch");
     }

@@ -8,7 +8,13 @@
 namespace bb {
 
 constexpr int kM4Block = 256;
-constexpr int kM4CtasPerSm = 8;
+// one-shot grid, ~64 KiB of output per CTA (see bb_bitfield.cu)
+constexpr int kM4UnrollFast = 4, kM4UnrollVec = 16, kM4UnrollScalar = 16;
+
+static inline unsigned m4_grid(uint32_t nitems, int unroll) {
+    uint64_t per = (uint64_t)kM4Block * unroll;
+    return (unsigned)((nitems + per - 1) / per);
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
@@ -22,37 +28,45 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
         }
         __syncthreads();
     }
-    const uint32_t stride = gridDim.x * kM4Block;
-    for (uint32_t item = blockIdx.x * kM4Block + threadIdx.x; item < p.nitems;
-         item += stride) {
+    constexpr int U = MODE == M4_FAST ? kM4UnrollFast
+        : MODE == M4_GENERIC_VEC ? kM4UnrollVec : kM4UnrollScalar;
+    const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kM4Block;
+        if (item >= p.nitems) break;
         if (MODE == M4_FAST) m4_dec_fast(p, lut, item);
         else if (MODE == M4_GENERIC_VEC) m4_dec_generic<true>(p, item);
         else m4_dec_generic<false>(p, item);
-        if (item + stride < item) break;
     }
 }
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kM4Block)
 k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
-    const uint32_t stride = gridDim.x * kM4Block;
-    for (uint32_t item = blockIdx.x * kM4Block + threadIdx.x; item < p.nitems;
-         item += stride) {
+    constexpr int U = kM4UnrollFast;
+    const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kM4Block;
+        if (item >= p.nitems) break;
         if (MODE == M4_FAST) m4_enc_fast<T>(p, c, item);
         else m4_enc_generic<T>(p, c, item);
-        if (item + stride < item) break;
     }
 }
 
 static int run_decode(const std::vector<M4Launch> &launches, cudaStream_t s) {
     for (const M4Launch &l : launches) {
-        unsigned grid = stream_grid(l.g.nitems, kM4Block, kM4CtasPerSm);
+        const uint32_t n = l.g.nitems;
         if (l.mode == M4_FAST)
-            k_mark4_decode<M4_FAST><<<grid, kM4Block, 0, s>>>(l.g);
+            k_mark4_decode<M4_FAST>
+                <<<m4_grid(n, kM4UnrollFast), kM4Block, 0, s>>>(l.g);
         else if (l.mode == M4_GENERIC_VEC)
-            k_mark4_decode<M4_GENERIC_VEC><<<grid, kM4Block, 0, s>>>(l.g);
+            k_mark4_decode<M4_GENERIC_VEC>
+                <<<m4_grid(n, kM4UnrollVec), kM4Block, 0, s>>>(l.g);
         else
-            k_mark4_decode<M4_GENERIC_SCALAR><<<grid, kM4Block, 0, s>>>(l.g);
+            k_mark4_decode<M4_GENERIC_SCALAR>
+                <<<m4_grid(n, kM4UnrollScalar), kM4Block, 0, s>>>(l.g);
         BB_CHECK_LAUNCH("bb_mark4_decode launch");
     }
     return BB_OK;
@@ -62,7 +76,7 @@ template <typename T>
 static int run_encode(const std::vector<M4Launch> &launches, cudaStream_t s) {
     static const QuantConsts<T> consts = make_quant_consts<T>();
     for (const M4Launch &l : launches) {
-        unsigned grid = stream_grid(l.g.nitems, kM4Block, kM4CtasPerSm);
+        unsigned grid = m4_grid(l.g.nitems, kM4UnrollFast);
         if (l.mode == M4_FAST)
             k_mark4_encode<T, M4_FAST><<<grid, kM4Block, 0, s>>>(l.g, consts);
         else

@@ -1,0 +1,87 @@
+"""Device selection and host<->device staging for the host layer.
+
+All sample arithmetic runs on a CUDA device; this module decides which one
+and moves bytes.  Streams of frames are staged through pinned host buffers so
+the H2D copy is asynchronous on the current torch stream.
+"""
+import os
+
+import numpy as np
+import torch
+
+_default = None
+
+
+def default_device():
+    """Device used when the caller does not name one: ``cuda:LOCAL_RANK``
+    under torchrun, else ``BASEBAND_B200_DEVICE`` or ``cuda:0``."""
+    global _default
+    if _default is None:
+        name = os.environ.get('BASEBAND_B200_DEVICE')
+        if name is None:
+            name = 'cuda:{}'.format(int(os.environ.get('LOCAL_RANK', 0)))
+        _default = torch.device(name)
+    return _default
+
+
+def set_default_device(device):
+    global _default
+    _default = torch.device(device)
+
+
+def resolve(device=None):
+    dev = default_device() if device is None else torch.device(device)
+    if dev.type != 'cuda':
+        raise ValueError('baseband_b200 decodes on CUDA devices only (no CPU '
+                         'fallback); got {!r}'.format(str(dev)))
+    if not torch.cuda.is_available():
+        raise RuntimeError('baseband_b200 needs a CUDA device; none is '
+                           'visible (there is no CPU fallback).')
+    return dev
+
+
+class PinnedStage:
+    """A reusable pinned host buffer (grows on demand)."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes):
+        if self._buf is None or self._buf.numel() < nbytes:
+            size = max(nbytes, 1 << 20)
+            self._buf = torch.empty(size, dtype=torch.uint8, pin_memory=True)
+        return self._buf[:nbytes]
+
+
+_stage = PinnedStage()
+
+
+def upload(raw, device, stage=None, align=16):
+    """Copy host bytes to a uint8 CUDA tensor through pinned memory.
+
+    ``raw`` may be bytes, a numpy array (any dtype) or a uint8 torch tensor.
+    Device allocations are at least 256-byte aligned, which covers every
+    alignment the kernels need for offset 0.
+    """
+    if isinstance(raw, torch.Tensor):
+        if raw.is_cuda:
+            return raw.view(torch.uint8).reshape(-1)
+        return raw.view(torch.uint8).reshape(-1).to(device, non_blocking=True)
+    if isinstance(raw, (bytes, bytearray, memoryview)):
+        arr = np.frombuffer(raw, np.uint8)
+    else:
+        arr = np.ascontiguousarray(raw).view(np.uint8).reshape(-1)
+    nbytes = arr.size
+    stage = stage or _stage
+    pinned = stage.get(nbytes)
+    pinned.numpy()[:] = arr
+    out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    out.copy_(pinned, non_blocking=True)
+    # the stage is reused by the next call: make the copy complete first
+    torch.cuda.current_stream(device).synchronize()
+    return out
+
+
+def download(tensor):
+    """CUDA tensor -> numpy (synchronous)."""
+    return tensor.cpu().numpy()

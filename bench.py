@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""Benchmark of the baseband hot path on B200 (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload = BASELINE.json configs[1]: synthetic VDIF, 2-bit real, 16 threads,
+8032-byte frames; one step = one pass of the hot path over one resident chunk
+of the 64 GiB logical stream: header scan (validity + thread slots) -> decode
+to float32 (nsample, 16) -> encode_2bit round trip back to packed payloads.
+The chunk (default 1 GiB packed -> 16 GiB decoded, far larger than the 126 MB
+L2) is resident in HBM when the timed region starts.  With N GPUs each rank
+takes its own contiguous range of frame sets (weak scaling, no collective on
+the data path); value = total decoded samples / max-over-ranks time.
+
+Printed JSON line: see the task contract.  Extra keys: `roofline` (decode
+kernel, CUDA-event timed inside the timed region), `cpu_baseline` (numpy
+oracle = port of the reference's CPU path, bounded sample, rank 0 at N=1),
+`e2e` (host pinned buffers -> H2D -> scan+decode -> D2H of the decoded array,
++ encode round trip -> D2H of the packed payloads; through the public API),
+`clocks`, `gpu_launches`.
+
+`--impl reference` times the reference's own CPU algorithm (the numpy oracle,
+a function-by-function port: astropy is not installable here so the package
+itself cannot be imported on the box) on all host cores, same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NTHREAD = 16
+PAYLOAD = 8000
+FRAME = PAYLOAD + 32
+SPF = PAYLOAD * 4                    # samples per thread-frame (2 bit)
+SET_BYTES = NTHREAD * FRAME          # 128 512
+SET_SAMPLES = SPF * NTHREAD          # 512 000 decoded floats
+ALGO_BYTES_PER_SAMPLE = (SET_BYTES + SET_SAMPLES * 4) / SET_SAMPLES  # 4.251
+LOGICAL_STREAM_BYTES = 64 << 30
+METRIC = 'decoded Gsamples/s (device-resident)'
+UNIT = 'Gsamples/s'
+
+
+def config_dict(chunk_bytes, ngpu):
+    return {
+        'workload': 'synthetic VDIF 2-bit real, 16 threads, 8032-byte frames '
+                    '(BASELINE.json configs[1]): header scan + decode + '
+                    'encode_2bit round trip per step',
+        'logical_stream_bytes': LOGICAL_STREAM_BYTES,
+        'chunk_bytes_per_gpu': int(chunk_bytes),
+        'frame_sets_per_chunk': int(chunk_bytes // SET_BYTES),
+        'decoded_bytes_per_chunk': int(chunk_bytes // SET_BYTES
+                                       * SET_SAMPLES * 4),
+        'parallelism': 'frame-set ranges x{} (no collective)'.format(ngpu),
+        'cache': 'inputs+outputs per step (>= 17 GiB) far exceed the 126 MB '
+                 'L2; no flush needed',
+    }
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured'
+    return 6650.0, 'fallback'
+
+
+# --------------------------------------------------------------- CPU legs
+def _cpu_round_trip(nset, seed):
+    """Reference CPU path on ``nset`` frame sets: struct-free header parse,
+    LUT decode with thread interleave, encode_2bit round trip."""
+    from baseband_b200 import synthetic
+    from oracle import codec, stream
+    raw = synthetic.vdif_stream(nset, NTHREAD, PAYLOAD, seed=seed)
+    t0 = time.perf_counter()
+    data = stream.vdif_read(raw)                       # (nset*SPF, 16, 1)
+    back = np.empty((nset, NTHREAD, PAYLOAD), np.uint8)
+    for s in range(nset):
+        block = data[s * SPF:(s + 1) * SPF, :, 0]
+        for t in range(NTHREAD):
+            back[s, t] = codec.vdif_encode(
+                np.ascontiguousarray(block[:, t]), 2)
+    dt = time.perf_counter() - t0
+    return data.shape[0] * NTHREAD, dt
+
+
+def _cpu_worker(args):
+    return _cpu_round_trip(*args)
+
+
+def cpu_baseline(nset=480):
+    nsamp, dt = _cpu_round_trip(nset, 1)
+    return {'value': nsamp / dt / 1e9, 'unit': UNIT, 'cores': 1,
+            'kind': 'port',
+            'sample': '{} frame sets ({:.1f} MB packed) of the same '
+                      'synthetic stream, decode + encode round trip, numpy '
+                      'oracle'.format(nset, nset * SET_BYTES / 1e6)}
+
+
+def run_reference(args):
+    """--impl reference: the CPU algorithm on all host cores."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = min(os.cpu_count() or 1, 64)
+    nset = 32
+    ctx = mp.get_context('fork')
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            pool.map(_cpu_worker, [(2, i) for i in range(cores)])
+        t0 = time.perf_counter()
+        nsamp = 0
+        for k in range(args.steps):
+            res = pool.map(_cpu_worker, [(nset, 100 * k + i)
+                                         for i in range(cores)])
+            nsamp += sum(r[0] for r in res)
+        dt = time.perf_counter() - t0
+    value = nsamp / dt / 1e9
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic',
+        'config': config_dict(cores * nset * SET_BYTES, args.gpus),
+        'cpu_baseline': {
+            'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '{} processes x {} frame sets per step, numpy oracle '
+                      '(port of the reference CPU path; the reference '
+                      'package needs astropy, absent here)'.format(cores,
+                                                                   nset)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,'
+             'clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index),
+                 '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
+                 '-lms', '100'], stdout=subprocess.PIPE, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2
+                    and r[1].isdigit())
+        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 8
+                          for n, v in zip(names, r[4:8]) if v == 'Active'})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None,
+                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# --------------------------------------------------------------- GPU arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from baseband_b200 import kernels, levels, synthetic
+
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if world != args.gpus and world > 1:
+        raise SystemExit('--gpus must equal WORLD_SIZE under torchrun')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    chunk_bytes = int(args.chunk_gib * 2**30)
+    nset = chunk_bytes // SET_BYTES
+    nframe = nset * NTHREAD
+    chunk_bytes = nset * SET_BYTES
+    first_set = rank * (LOGICAL_STREAM_BYTES // SET_BYTES // max(world, 1))
+    raw = synthetic.vdif_stream_device(nset, NTHREAD, PAYLOAD, dev,
+                                       seed=synthetic.VDIF_SEED + rank,
+                                       first_set=first_set)
+    slot = torch.full((1024,), -1, dtype=torch.int32, device=dev)
+    slot[:NTHREAD] = torch.arange(NTHREAD, dtype=torch.int32, device=dev)
+    lv = levels.offset_binary(2)
+    out = torch.empty((nset * SPF, NTHREAD, 1), dtype=torch.float32,
+                      device=dev)
+    back = torch.empty_like(raw)
+    back.view(nframe, FRAME)[:, :32] = raw.view(nframe, FRAME)[:, :32]
+    dec_events = []
+
+    def step(record=False):
+        _, uo, bad = kernels.vdif_scan(raw, nframe, FRAME, 32, NTHREAD, slot,
+                                       NTHREAD)
+        if record:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+        kernels.decode_bitfield(raw, uo, nset, NTHREAD, PAYLOAD, 2, 1, False,
+                                kernels.CODEC_LEVELS, lv, out=out)
+        if record:
+            e1.record()
+            dec_events.append((e0, e1))
+        kernels.encode_bitfield(out, back, uo, nset, NTHREAD, PAYLOAD, 2, 1,
+                                kernels.QUANT_OFFSET_BINARY)
+        return bad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        bad = step()
+    torch.cuda.synchronize()
+    assert int(bad.item()) == 0
+    if not torch.equal(back, raw):
+        raise SystemExit('round trip mismatch: decode->encode must be exact')
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = kernels.launch_count
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        step(record=True)
+    t1.record()
+    barrier()
+    elapsed_ms = t0.elapsed_time(t1)
+    launches = kernels.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+
+    # ------------------------------------------------ end-to-end (host bufs)
+    e2e = measure_e2e(args, dev, rank, world, lv, slot)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    samples_per_step = nset * SET_SAMPLES * world
+    value = samples_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9
+    peak, which = peaks()
+    algo_bytes = nset * (SET_BYTES + SET_SAMPLES * 4)
+    achieved = algo_bytes / (dec_ms * 1e-3) / 1e9
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': config_dict(chunk_bytes, world),
+        'decode_only_gsamples_s': nset * SET_SAMPLES / (dec_ms * 1e-3) / 1e9,
+        'roofline': {
+            'bound': 'hbm', 'kernel': 'k_decode_bitfield<2,LEVELS,ROWGROUP4>',
+            'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'peak_source': which + ' copy bandwidth',
+            'algorithmic_bytes_per_sample': ALGO_BYTES_PER_SAMPLE,
+            'traffic': NCU_TRAFFIC_BYTES_PER_SAMPLE * nset * SET_SAMPLES
+            if NCU_TRAFFIC_BYTES_PER_SAMPLE else None},
+        'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# dram bytes per decoded sample from the ncu --set full capture of the decode
+# kernel (profiles/r1_ncu_decode_c2.txt): (read + write) / samples.
+NCU_TRAFFIC_BYTES_PER_SAMPLE = 4.303
+
+
+def measure_e2e(args, dev, rank, world, lv, slot):
+    """Host pinned frames -> H2D -> scan + decode -> D2H decoded (what
+    ``read()`` returns) -> encode round trip -> D2H packed payloads."""
+    import torch
+    import torch.distributed as dist
+    from baseband_b200 import kernels, synthetic
+    nset = int(args.e2e_mib * 2**20) // SET_BYTES
+    nframe = nset * NTHREAD
+    host_raw = torch.from_numpy(synthetic.vdif_stream(
+        nset, NTHREAD, PAYLOAD, seed=7 + rank)).pin_memory()
+    host_out = torch.empty((nset * SPF, NTHREAD), dtype=torch.float32,
+                           pin_memory=True)
+    host_back = torch.empty_like(host_raw).pin_memory()
+    raw = torch.empty_like(host_raw, device=dev)
+    out = torch.empty((nset * SPF, NTHREAD, 1), dtype=torch.float32,
+                      device=dev)
+    back = torch.zeros_like(raw)
+
+    def step():
+        raw.copy_(host_raw, non_blocking=True)
+        _, uo, bad = kernels.vdif_scan(raw, nframe, FRAME, 32, NTHREAD, slot,
+                                       NTHREAD)
+        kernels.decode_bitfield(raw, uo, nset, NTHREAD, PAYLOAD, 2, 1, False,
+                                kernels.CODEC_LEVELS, lv, out=out)
+        host_out.copy_(out.view(nset * SPF, NTHREAD), non_blocking=True)
+        kernels.encode_bitfield(out, back, uo, nset, NTHREAD, PAYLOAD, 2, 1,
+                                kernels.QUANT_OFFSET_BINARY)
+        host_back.copy_(back, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        step()
+    if world > 1:
+        dist.barrier()
+    steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    ok = bool(torch.equal(host_back.view(nframe, FRAME)[:, 32:],
+                          host_raw.view(nframe, FRAME)[:, 32:]))
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {'value': nset * SET_SAMPLES * world * steps / dt / 1e9,
+            'unit': UNIT, 'h2d_bytes_per_step': int(host_raw.numel()),
+            'd2h_bytes_per_step': int(host_out.numel() * 4
+                                      + host_back.numel()),
+            'steps': steps, 'round_trip_exact': ok,
+            'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
+                    'float32 array returned to the host is 16x the packed '
+                    'input'.format(args.e2e_mib)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--chunk-gib', type=float, default=1.0,
+                    help='packed bytes resident per GPU per step')
+    ap.add_argument('--e2e-mib', type=float, default=128.0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -93,5 +93,50 @@ def main():
         torch.cuda.empty_cache()
 
 
+def extra(gib):
+    # C3: Mark 4 64-track fanout 4
+    nframe = int(gib * 2**30) // 160000
+    raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,
+                        device=DEV)
+    off = torch.arange(nframe, dtype=torch.int64, device=DEV) * 160000 + 1280
+    out = torch.empty((nframe * 80000, 8), dtype=torch.float32, device=DEV)
+    lv = levels.sign_magnitude()
+    best, med = timeit(lambda: kernels.mark4_decode(raw, off, nframe, 8, 4,
+                                                    False, lv, out=out))
+    nbytes = raw.numel() + out.numel() * 4
+    print('DEC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('C3 mark4 64trk fanout4', nbytes / best / 1e6, nbytes / med / 1e6,
+             out.numel() / med / 1e6, med))
+    back = raw.clone()
+    back.view(nframe, 160000)[:, 1280:] = 0
+    best, med = timeit(lambda: kernels.mark4_encode(out, back, off, nframe, 8,
+                                                    4, False))
+    print('ENC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('C3 mark4 64trk fanout4', nbytes / best / 1e6, nbytes / med / 1e6,
+             out.numel() / med / 1e6, med))
+    print('    round trip identical:', bool(torch.equal(back, raw)))
+    del raw, off, out, back
+    torch.cuda.empty_cache()
+    # C4: GUPPI 512 chan x 2 pol complex int8, channels first, overlap 512
+    nchan, npol, spf, ov = 512, 2, 65536, 512
+    fbytes = nchan * spf * npol * 2
+    nfr = max(1, int(gib * 2**30) // fbytes)
+    raw = torch.randint(0, 256, (nfr * fbytes,), dtype=torch.uint8, device=DEV)
+    off = torch.arange(nfr, dtype=torch.int64, device=DEV) * fbytes
+    cb = torch.full((nfr,), ov * npol, dtype=torch.int64, device=DEV)
+    cb[0] = 0
+    ce = torch.full((nfr,), spf * npol, dtype=torch.int64, device=DEV)
+    oc0 = torch.cumsum(ce - cb, 0) - (ce - cb)
+    ncols = int((ce - cb).sum().item())
+    out = torch.empty((ncols * nchan * 2,), dtype=torch.float32, device=DEV)
+    best, med = timeit(lambda: kernels.decode_int8_transposed(
+        raw, off, nfr, nchan, spf * npol, 2, cb, ce, oc0, out))
+    nbytes = out.numel() + out.numel() * 4
+    print('DEC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('C4 guppi 512ch 2pol int8', nbytes / best / 1e6,
+             nbytes / med / 1e6, out.numel() / med / 1e6, med))
+
+
 if __name__ == '__main__':
     main()
+    extra(float(sys.argv[1]) if len(sys.argv) > 1 else 0.5)
