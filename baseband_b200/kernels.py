@@ -239,7 +239,7 @@ def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
             _dev(fields, 'fields'), _dev(unit_offset, 'unit_offset'),
             _dev(bad, 'bad'), _stream_ptr(dev))
     _lib.check(rc, lib)
-    _count()
+    _count(3)          # fill, scan, count-missing kernels
     return fields, unit_offset[:nset * nthread], bad
 
 

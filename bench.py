@@ -161,7 +161,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index),
                  '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
-                 '-lms', '100'], stdout=subprocess.PIPE, text=True)
+                 '-lms', '50'], stdout=subprocess.PIPE, text=True)
         except OSError:
             self.proc = None
             return
@@ -369,7 +369,7 @@ def measure_e2e(args, dev, rank, world, lv, slot):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chunk-gib', type=float, default=1.0,
