@@ -1,0 +1,60 @@
+"""``open(name, mode, **kwargs)`` factories for the format modules.
+
+Behaviour of the reference's ``FileOpener`` (baseband/base/base.py:1650-1902):
+modes 'rb', 'wb', 'rs', 'ws' ('r'/'w' default to stream mode); ``name`` is a
+path or an open binary file handle; for writing, keyword arguments that are
+not reader/writer options are used to build ``header0`` through
+``Header.fromvalues``.  The extra stream options of this implementation
+(``device``, ``chunk_nbytes``) are non-header keys, so they are never fed to
+the header ("Config / flag system").
+"""
+import io
+import os
+
+__all__ = ['make_opener', 'normalize_mode']
+
+COMMON_NON_HEADER = {'squeeze', 'subset', 'fill_value', 'verify',
+                     'file_size', 'device', 'chunk_nbytes'}
+
+
+def normalize_mode(mode):
+    if mode in ('r', 'w'):
+        mode += 's'
+    if mode not in ('rb', 'wb', 'rs', 'ws'):
+        raise ValueError("invalid mode {!r}; should be one of 'rb', 'wb', "
+                         "'rs' or 'ws'.".format(mode))
+    return mode
+
+
+def make_opener(fmt, classes, header_class=None, non_header_keys=(),
+                doc=None):
+    """``classes``: dict mode -> class; stream classes are called as
+    ``cls(fh, **kwargs)`` (writers get ``header0=``)."""
+    non_header = COMMON_NON_HEADER | set(non_header_keys) | {'header0'}
+
+    def open(name, mode='rs', **kwargs):
+        mode = normalize_mode(mode)
+        if mode[0] == 'w' and mode[1] == 's' and header_class is not None \
+                and kwargs.get('header0') is None:
+            header_kwargs = {k: kwargs.pop(k) for k in list(kwargs)
+                             if k not in non_header}
+            kwargs.pop('header0', None)
+            sample_rate = kwargs.get('sample_rate')
+            if sample_rate is not None and fmt == 'vdif':
+                header_kwargs.setdefault('sample_rate', sample_rate)
+            kwargs['header0'] = header_class.fromvalues(**header_kwargs)
+        if isinstance(name, (str, bytes, os.PathLike)):
+            fh = io.open(name, mode[0] + 'b')
+            opened = True
+        else:
+            fh, opened = name, False
+        try:
+            return classes[mode](fh, **kwargs)
+        except Exception:
+            if opened:
+                fh.close()
+            raise
+
+    open.__name__ = 'open'
+    open.__doc__ = doc or 'Open a {} file for reading or writing.'.format(fmt)
+    return open

@@ -61,14 +61,14 @@ k_vdif_scan(const uint8_t *src, const long long *frame_offset,
     if (!unit_offset) return;
     long long set = i / frames_per_set;
     if ((set + 1) * (long long)frames_per_set > nframe) return;  // partial set
-    // All frames of a set share seconds and frame_nr with its first frame
-    // (baseband/vdif/frame.py:207-216).
+    // All frames of a set share frame_nr with its first frame; `seconds` is
+    // deliberately not compared: some recorders get it wrong in part of the
+    // threads (baseband/vdif/frame.py:207-216, sample_vlbi.vdif).
     long long i0 = set * frames_per_set;
     if (i != i0) {
         long long off0 = frame_offset ? frame_offset[i0] : i0 * frame_stride;
-        uint32_t a = ldw(src + off0), b = ldw(src + off0 + 4);
-        if (bits(a, 0, 30) != seconds || bits(b, 0, 24) != frame_nr)
-            atomicAdd(n_bad, 1);
+        uint32_t b = ldw(src + off0 + 4);
+        if (bits(b, 0, 24) != frame_nr) atomicAdd(n_bad, 1);
     }
     int slot = thread_slot[tid];
     if (slot < 0 || slot >= nthread) return;      // thread not selected

@@ -85,3 +85,66 @@ def upload(raw, device, stage=None, align=16):
 def download(tensor):
     """CUDA tensor -> numpy (synchronous)."""
     return tensor.cpu().numpy()
+
+
+def register_host(arr):
+    """Page-lock a numpy array in place (``cudaHostRegister`` through the C
+    ABI) so a D2H copy can land in it asynchronously at full PCIe rate.
+    Returns a token for `unregister_host`, or None if pinning failed."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    ptr = ctypes.c_void_p(arr.ctypes.data)
+    if lib.bb_host_register(ptr, arr.nbytes) != 0:
+        return None
+    return ptr
+
+
+def unregister_host(token):
+    from . import _lib
+    _lib.load().bb_host_unregister(token)
+
+
+def pinned_empty(shape, dtype):
+    """Page-locked host tensor (D2H / H2D copies to it are asynchronous)."""
+    return torch.empty(shape, dtype=dtype, pin_memory=True)
+
+
+class Streams:
+    """The three CUDA streams of the read pipeline: 0 = H2D copies,
+    1 = kernels, 2 = D2H copies.  All CUDA stream/event plumbing of the host
+    layer goes through this class."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.streams = [torch.cuda.Stream(dev) for _ in range(3)]
+
+    def use(self, i):
+        return torch.cuda.stream(self.streams[i])
+
+    def wait(self, i, j):
+        """Stream i waits for everything queued so far on stream j."""
+        self.streams[i].wait_stream(self.streams[j])
+
+    def after_caller(self, i):
+        self.streams[i].wait_stream(torch.cuda.current_stream(self.dev))
+
+    def caller_after(self, i):
+        torch.cuda.current_stream(self.dev).wait_stream(self.streams[i])
+
+    def event(self, i):
+        ev = torch.cuda.Event()
+        ev.record(self.streams[i])
+        return ev
+
+    def synchronize(self):
+        for s in self.streams:
+            s.synchronize()
+
+
+def current_stream_synchronize(dev):
+    torch.cuda.current_stream(dev).synchronize()
+
+
+def is_device_tensor(t):
+    return isinstance(t, torch.Tensor) and t.is_cuda

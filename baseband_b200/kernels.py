@@ -25,6 +25,10 @@ def _count(n=1):
     launch_count += n
 
 
+def _on(device):
+    return torch.cuda.device(device)
+
+
 def _stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
@@ -84,7 +88,7 @@ def decode_bitfield(src, unit_offset, nset, nthread, payload_nbytes, bps,
     elif out.numel() != nsample * nthread * nelem:
         raise ValueError('out has the wrong number of elements')
     keep, lv = _levels_arg(levels)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         rc = lib.bb_decode_bitfield(
             _dev(src, 'src', torch.uint8), _dev(unit_offset, 'unit_offset',
                                                 torch.int64),
@@ -109,7 +113,7 @@ def encode_bitfield(data, dst, unit_offset, nset, nthread, payload_nbytes,
         code = F64
     else:
         raise TypeError('data must be float32 or float64')
-    with torch.cuda.device(dst.device):
+    with _on(dst.device):
         rc = lib.bb_encode_bitfield(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
             _dev(unit_offset, 'unit_offset', torch.int64), nset, nthread,
@@ -130,7 +134,7 @@ def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
         out = torch.empty((nsample, nchan), dtype=torch.float32,
                           device=src.device)
     keep, lv = _levels_arg(levels)
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         rc = lib.bb_mark4_decode(
             _dev(src, 'src', torch.uint8),
             _dev(unit_offset, 'unit_offset', torch.int64), nframe, nchan,
@@ -145,7 +149,7 @@ def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
 def mark4_encode(data, dst, unit_offset, nframe, nchan, fanout, ft=False):
     lib = _lib.load()
     code = F32 if data.dtype == torch.float32 else F64
-    with torch.cuda.device(dst.device):
+    with _on(dst.device):
         rc = lib.bb_mark4_encode(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
             _dev(unit_offset, 'unit_offset', torch.int64), nframe, nchan,
@@ -162,7 +166,7 @@ def mark4_decode_words(words, nword, nchan, fanout, ft=False, levels=None,
         out = torch.empty((nword * fanout, nchan), dtype=torch.float32,
                           device=words.device)
     keep, lv = _levels_arg(levels)
-    with torch.cuda.device(words.device):
+    with _on(words.device):
         rc = lib.bb_mark4_decode_words(
             _dev(words, 'words'), nword, nchan, fanout, int(bool(ft)), lv,
             _dev(out, 'out', torch.float32), _stream_ptr(words.device))
@@ -174,7 +178,7 @@ def mark4_decode_words(words, nword, nchan, fanout, ft=False, levels=None,
 def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
     lib = _lib.load()
     code = F32 if data.dtype == torch.float32 else F64
-    with torch.cuda.device(words.device):
+    with _on(words.device):
         rc = lib.bb_mark4_encode_words(
             _dev(data, 'data'), code, _dev(words, 'words'), nword, nchan,
             fanout, int(bool(ft)), _stream_ptr(words.device))
@@ -186,7 +190,7 @@ def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
 def decode_int8_transposed(src, unit_offset, nunit, nrow, ncol, item_nbytes,
                            col_begin, col_end, out_col0, out):
     lib = _lib.load()
-    with torch.cuda.device(src.device):
+    with _on(src.device):
         rc = lib.bb_decode_int8_transposed(
             _dev(src, 'src', torch.uint8),
             _dev(unit_offset, 'unit_offset', torch.int64), nunit, nrow, ncol,
@@ -203,7 +207,7 @@ def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
                            item_nbytes):
     lib = _lib.load()
     code = F32 if data.dtype == torch.float32 else F64
-    with torch.cuda.device(dst.device):
+    with _on(dst.device):
         rc = lib.bb_encode_int8_transposed(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
             _dev(unit_offset, 'unit_offset', torch.int64), nunit, nrow, ncol,
@@ -214,6 +218,14 @@ def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
 
 
 VDIF_NFIELD = 17
+# row indices of the ``fields`` array (enum bb_vdif_field / bb_mark5b_field)
+(VDIF_INVALID, VDIF_LEGACY, VDIF_SECONDS, VDIF_REF_EPOCH, VDIF_FRAME_NR,
+ VDIF_VERSION, VDIF_LG2_NCHAN, VDIF_FRAME_LENGTH, VDIF_COMPLEX,
+ VDIF_BITS_PER_SAMPLE, VDIF_THREAD_ID, VDIF_STATION_ID, VDIF_EDV, VDIF_WORD4,
+ VDIF_WORD5, VDIF_WORD6, VDIF_WORD7) = range(17)
+(M5B_SYNC, M5B_USER, M5B_INTERNAL_TVG, M5B_FRAME_NR, M5B_BCD_JDAY,
+ M5B_BCD_SECONDS, M5B_BCD_FRACTION, M5B_CRC, M5B_JDAY, M5B_SECONDS,
+ M5B_FRACTION_NS, M5B_VALID) = range(12)
 M5B_NFIELD = 12
 
 
@@ -228,7 +240,7 @@ def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
     unit_offset = torch.full((max(nset * nthread, 1),), -1,
                              dtype=torch.int64, device=dev)
     bad = torch.zeros(1, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib.bb_vdif_scan(
             _dev(src, 'src', torch.uint8),
             None if frame_offset is None else _dev(frame_offset,
@@ -248,7 +260,7 @@ def mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
     dev = src.device
     fields = torch.empty((M5B_NFIELD, nframe), dtype=torch.int32, device=dev)
     unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib.bb_mark5b_scan(
             _dev(src, 'src', torch.uint8),
             None if frame_offset is None else _dev(frame_offset,
@@ -269,7 +281,7 @@ def mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
         frame_stride = ntrack * 2500
     words5 = torch.empty((nframe, 5), dtype=torch.int32, device=dev)
     unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib.bb_mark4_scan(
             _dev(src, 'src', torch.uint8),
             None if frame_offset is None else _dev(frame_offset,

@@ -194,7 +194,7 @@ int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
  * int32[1024], -1 = thread not selected, baseband/vdif/base.py:464-490);
  * unit_offset[set*nthread + slot] = payload offset, or -1 if invalid_data
  * (baseband/vdif/frame.py:79-90).  *n_inconsistent (device int32) counts
- * frames whose frame_nr/seconds differ from the first frame of their set or
+ * frames whose frame_nr differs from the first frame of their set or
  * whose slot is duplicated, so the host can fall back to its recovery path
  * (baseband/vdif/base.py:536-755, out of scope here). */
 typedef enum bb_vdif_field {

@@ -1,0 +1,161 @@
+"""TEST INFRASTRUCTURE: run the host layer on a box without a GPU.
+
+``install(monkeypatch)`` points ``baseband_b200``'s narrow device seam
+(``_lib.load``, a few helpers of ``kernels`` and ``device``) at the CPU
+emulation of the kernel bodies (tests/emu, compiled from the very same
+``csrc/*.cuh`` bodies with g++) and at numpy restatements of the header-scan
+kernels built on the oracle.  This exists only so that the *host logic*
+(frame-range planning, chunking, squeeze/subset, header generation, file
+I/O) is covered by ``pytest -m "not gpu"``; the shipped package has no such
+path and refuses CPU tensors.  The same tests run against the real CUDA
+library under ``-m gpu`` (tests/test_gpu_streams.py).
+"""
+import contextlib
+import ctypes
+
+import numpy as np
+import torch
+
+import emu_build
+from oracle import headers as oheaders
+
+
+class _NoStreams:
+    def __init__(self, dev):
+        self.dev = dev
+
+    def use(self, i):
+        return contextlib.nullcontext()
+
+    def wait(self, i, j):
+        pass
+
+    after_caller = caller_after = lambda self, i: None
+
+    def event(self, i):
+        class _Ev:
+            def synchronize(self):
+                pass
+        return _Ev()
+
+    def synchronize(self):
+        pass
+
+
+def _vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
+               thread_slot, nthread, frame_offset=None):
+    from baseband_b200 import kernels
+    buf = src.numpy()
+    fields = np.zeros((kernels.VDIF_NFIELD, nframe), np.int32)
+    nset = nframe // frames_per_set
+    uo = np.full(max(nset * nthread, 1), -2, np.int64)
+    slots = thread_slot.numpy()
+    bad = 0
+    names = ['invalid_data', 'legacy_mode', 'seconds', 'ref_epoch',
+             'frame_nr', 'vdif_version', 'lg2_nchan', 'frame_length',
+             'complex_data', 'bits_per_sample', 'thread_id', 'station_id']
+    first = None
+    for i in range(nframe):
+        off = int(frame_offset[i]) if frame_offset is not None \
+            else i * frame_stride
+        w = buf[off:off + 32].view('<u4') if header_nbytes == 32 else \
+            np.concatenate([buf[off:off + 16].view('<u4'),
+                            np.zeros(4, '<u4')])
+        for k, name in enumerate(names):
+            fields[k, i] = oheaders.field(w, *oheaders.VDIF_BASE_FIELDS[name])
+        fields[12, i] = (int(w[4]) >> 24) & 0xff
+        fields[13:17, i] = w[4:8].view(np.int32)
+        s = i // frames_per_set
+        if s >= nset:
+            continue
+        if i % frames_per_set == 0:
+            first = fields[4, i]
+        elif fields[4, i] != first:
+            bad += 1
+        slot = slots[fields[10, i]]
+        if 0 <= slot < nthread:
+            if uo[s * nthread + slot] != -2:
+                bad += 1
+            uo[s * nthread + slot] = -1 if fields[0, i] else off + header_nbytes
+    missing = uo[:nset * nthread] == -2
+    bad += int(missing.sum())
+    uo[:nset * nthread][missing] = -1
+    return (torch.from_numpy(fields), torch.from_numpy(uo[:nset * nthread]),
+            torch.tensor([bad], dtype=torch.int32))
+
+
+def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
+    from baseband_b200 import kernels
+    buf = src.numpy()
+    fields = np.zeros((kernels.M5B_NFIELD, nframe), np.int32)
+    uo = np.empty(nframe, np.int64)
+    for i in range(nframe):
+        off = int(frame_offset[i]) if frame_offset is not None \
+            else i * frame_stride
+        h = oheaders.mark5b_parse(buf[off:off + 16].view('<u4'))
+        pl = buf[off + 16:off + 10016].view('<u4')
+        valid = not bool((pl == 0x11223344).all())
+        row = [h['sync_pattern'], h['user'], h['internal_tvg'], h['frame_nr'],
+               h['bcd_jday'], h['bcd_seconds'], h['bcd_fraction'], h['crc'],
+               h['jday'], h['seconds'], h['fraction_ns'], int(valid)]
+        fields[:, i] = np.array(row, np.int64).astype(np.uint32).view(np.int32)
+        uo[i] = off + 16 if valid else -1
+    return torch.from_numpy(fields), torch.from_numpy(uo)
+
+
+def _mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
+                frame_offset=None):
+    buf = src.numpy()
+    dtype = {16: '<u2', 32: '<u4', 64: '<u8'}[ntrack]
+    if frame_stride is None:
+        frame_stride = ntrack * 2500
+    words5 = np.zeros((nframe, 5), np.uint32)
+    uo = np.empty(nframe, np.int64)
+    for i in range(nframe):
+        off = int(frame_offset[i]) if frame_offset is not None \
+            else i * frame_stride
+        stream = buf[off:off + ntrack * 20].view(dtype)
+        h = oheaders.mark4_parse(stream)
+        words5[i] = oheaders.mark4_stream2words(stream)[:, track]
+        uo[i] = off + ntrack * 20 if h['valid'] else -1
+    return torch.from_numpy(words5.view(np.int32)), torch.from_numpy(uo)
+
+
+def install(monkeypatch):
+    from baseband_b200 import _lib, device, kernels
+    emu = emu_build.load()
+    monkeypatch.setattr(_lib, '_lib', emu)
+    monkeypatch.setattr(_lib, 'load', lambda: emu)
+    cpu = torch.device('cpu')
+    monkeypatch.setattr(device, 'resolve', lambda d=None: cpu)
+    monkeypatch.setattr(device, 'default_device', lambda: cpu)
+    monkeypatch.setattr(
+        device, 'upload', lambda raw, dev, stage=None, align=16:
+        raw.view(torch.uint8).reshape(-1) if isinstance(raw, torch.Tensor)
+        else torch.from_numpy(np.ascontiguousarray(
+            np.frombuffer(raw, np.uint8) if isinstance(
+                raw, (bytes, bytearray, memoryview)) else raw
+        ).view(np.uint8).reshape(-1).copy()))
+    monkeypatch.setattr(device, 'download', lambda t: t.numpy())
+    monkeypatch.setattr(device, 'pinned_empty',
+                        lambda shape, dtype: torch.empty(shape, dtype=dtype))
+    monkeypatch.setattr(device, 'Streams', _NoStreams)
+    monkeypatch.setattr(device, 'register_host', lambda arr: None)
+    monkeypatch.setattr(device, 'current_stream_synchronize', lambda d: None)
+
+    def _dev(t, name, dtype=None):
+        assert isinstance(t, torch.Tensor) and t.is_contiguous(), name
+        if dtype is not None:
+            assert t.dtype == dtype, name
+        return ctypes.c_void_p(t.data_ptr())
+
+    monkeypatch.setattr(kernels, '_dev', _dev)
+    monkeypatch.setattr(kernels, '_require_cuda', lambda *a: None)
+    monkeypatch.setattr(kernels, '_stream_ptr', lambda d: None)
+    monkeypatch.setattr(kernels, 'vdif_scan', _vdif_scan)
+    monkeypatch.setattr(kernels, 'mark5b_scan', _mark5b_scan)
+    monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
+    monkeypatch.setattr(kernels, '_on', lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(device, 'is_device_tensor',
+                        lambda t: isinstance(t, torch.Tensor))
+    return emu

@@ -1,0 +1,218 @@
+"""Stream-level checks shared by the CPU-backend run (host logic) and the GPU
+run (parity proper): each function takes nothing and asserts, comparing the
+public API of baseband_b200 with the oracle / golden fixtures."""
+import io
+import os
+
+import numpy as np
+import torch
+
+import baseband_b200 as bb
+from baseband_b200 import synthetic
+from oracle import stream as ostream
+from conftest import GOLDEN, sample_path
+
+OUT = np.load(os.path.join(GOLDEN, 'sample_outputs.npz'))
+
+
+def _same(a, b):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape and a.dtype == b.dtype, (a.shape, b.shape,
+                                                       a.dtype, b.dtype)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+# ------------------------------------------------------------------ VDIF
+def vdif_sample_read():
+    """BASELINE config 1: sample.vdif through open(...,'rs').read()."""
+    want = OUT['sample_vdif_data']
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
+        assert fh.shape == (40000, 8)
+        assert fh.sample_shape == (8,)
+        assert fh.sample_shape.nthread == 8
+        assert fh.samples_per_frame == 20000
+        assert fh.bps == 2 and not fh.complex_data
+        assert fh.sample_rate == 32e6
+        assert fh.start_time.isot.startswith('2014-06-16T05:56:07.000000000')
+        data = fh.read()
+        assert fh.tell() == 40000
+        _same(data, want[:, :, 0])
+        # values the reference's own test asserts (test_vdif.py:930-931)
+        assert np.all(data[:12, 0].astype(int)
+                      == np.array([-1, -1, 3, -1, 1, -1, 3, -1, 1, 3, -1, 1]))
+        fh.seek(19990)
+        part = fh.read(20)
+        _same(part, want[19990:20010, :, 0])
+        fh.seek(-7, 2)
+        _same(fh.read(), want[-7:, :, 0])
+        try:
+            fh.seek(-3, 2)
+            fh.read(4)
+        except EOFError:
+            pass
+        else:
+            raise AssertionError('expected EOFError')
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs', squeeze=False) as fh:
+        assert fh.sample_shape == (8, 1)
+        _same(fh.read(), want)
+
+
+def vdif_sample_subset():
+    want = OUT['sample_vdif_data'][:, :, 0]
+    for subset, pick in [(3, want[:, 3]), ([1, 6], want[:, [1, 6]]),
+                         (slice(2, 7, 2), want[:, 2:7:2]),
+                         ([5], want[:, [5]])]:
+        with bb.vdif.open(sample_path('sample.vdif'), 'rs',
+                          subset=subset) as fh:
+            assert fh.shape == pick.shape
+            fh.seek(10)
+            _same(fh.read(30000), pick[10:30010])
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs', subset=(2, 0),
+                      squeeze=False) as fh:
+        _same(fh.read(5), OUT['sample_vdif_data'][:5, 2, 0])
+
+
+def vdif_other_samples():
+    for name in ('sample_vlbi.vdif', 'sample_mwa.vdif',
+                 'sample_arochime.vdif', 'sample_bps1.vdif'):
+        tag = name.replace('.', '_')
+        want = OUT[tag + '_data']
+        kw = {}
+        if name in ('sample_mwa.vdif', 'sample_bps1.vdif',
+                    'sample_arochime.vdif'):
+            kw['sample_rate'] = 1e6     # legacy / EDV 0 headers hold no rate
+        with bb.vdif.open(sample_path(name), 'rs', squeeze=False,
+                          **kw) as fh:
+            data = fh.read()
+            _same(data, want[:data.shape[0]])
+            assert data.shape[0] == want.shape[0]
+
+
+def vdif_invalid_fill():
+    want = OUT['sample_vdif_set0_invalid_1_4_7_fill_m999']
+    raw = np.fromfile(sample_path('sample.vdif'), np.uint8).copy()
+    frames = raw.reshape(16, 5032)
+    # reference test marks the frames of threads 1, 4, 7 of set 0 invalid
+    tid = (frames[:, 12:16].view('<u4')[:, 0] >> 16) & 0x3ff
+    for i in range(8):
+        if tid[i] in (1, 4, 7):
+            frames[i, 3] |= 0x80
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', squeeze=False,
+                      fill_value=-999.) as fh:
+        _same(fh.read(20000), want)
+
+
+def vdif_synthetic_chunked(nset=23):
+    """Config 2 geometry, tiny chunks so the pipeline runs many stages."""
+    raw = synthetic.vdif_stream(nset, 16, 8000, seed=5, invalid=[3, 77, 78])
+    want = ostream.vdif_read(raw, fill_value=2.5)[:, :, 0]
+    for chunk in (16 * 8032 * 3, 1 << 30):
+        with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=64e6,
+                          fill_value=2.5, chunk_nbytes=chunk) as fh:
+            assert fh.shape == want.shape
+            _same(fh.read(), want)
+            fh.seek(31999)
+            _same(fh.read(5 * 32000 + 3), want[31999:31999 + 5 * 32000 + 3])
+            out = np.empty((70001, 16), np.float32)
+            fh.seek(123)
+            assert fh.read(out=out) is out
+            _same(out, want[123:70124])
+
+
+def vdif_device_output(dev):
+    raw = synthetic.vdif_stream(7, 16, 8000, seed=9)
+    want = ostream.vdif_read(raw)[:, :, 0]
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=64e6,
+                      device=dev, chunk_nbytes=16 * 8032 * 2) as fh:
+        data = fh.read()
+        assert isinstance(data, torch.Tensor)
+        assert str(data.device) == str(torch.device(dev))
+        _same(data.cpu().numpy(), want)
+        fh.seek(1001)
+        out = torch.empty((64000, 16), dtype=torch.float32, device=dev)
+        fh.read(out=out)
+        _same(out.cpu().numpy(), want[1001:65001])
+
+
+def vdif_write_roundtrip():
+    """Stream writer: decode -> write -> bytes identical to the input."""
+    raw = synthetic.vdif_stream(5, 4, 8000, seed=3, thread_order=[0, 1, 2, 3],
+                                edv=1)
+    # EDV 1 needs sample rate + sync pattern in the header
+    w = raw.reshape(-1, 8032)[:, :32].view('<u4')
+    w[:, 4] = (1 << 24) | (1 << 23) | 32        # 32 MHz complex => 64 MHz real
+    w[:, 5] = 0xACABFEED
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs') as fr:
+        assert fr.sample_rate == 64e6
+        data = fr.read()
+        header0 = fr.header0
+    buf = io.BytesIO()
+    fw = bb.vdif.open(buf, 'ws', header0=header0, nthread=4)
+    fw.write(data[:1000])
+    fw.write(data[1000:90000])
+    fw.write(data[90000:])
+    fw._flush(final=False)
+    got = np.frombuffer(buf.getvalue(), np.uint8)
+    fw.fh_raw = io.BytesIO()        # keep ``buf`` readable after close
+    fw.close()
+    _same(got, raw)
+    # float64 input and invalid + partial last frame
+    buf = io.BytesIO()
+    import warnings
+    fw = bb.vdif.open(buf, 'ws', nthread=4, edv=1, time='2014-06-16T05:56:07',
+                      samples_per_frame=32000, bps=2, nchan=1,
+                      sample_rate=64e6, station='me')
+    fw.write(data[:32000].astype(np.float64))
+    fw.write(data[32000:40000], valid=False)
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        fw._flush(final=True)
+    assert any('partial buffer' in str(r.message) for r in rec)
+    got = np.frombuffer(buf.getvalue(), np.uint8).reshape(8, 8032)
+    _same(got[:4, 32:], raw.reshape(-1, 8032)[:4, 32:])
+    inv = (got[:, 3] >> 7).astype(bool)
+    assert list(inv) == [False] * 4 + [True] * 4
+    back = bb.vdif.open(io.BytesIO(buf.getvalue()), 'rs')
+    assert back.header0.station == 'me'
+    assert back.start_time.isot.startswith('2014-06-16T05:56:07.0')
+    d2 = back.read()
+    _same(d2[:32000], data[:32000])
+    assert np.all(d2[32000:] == 0)
+
+
+def vdif_frameset_api():
+    want = OUT['sample_vdif_data']
+    with bb.vdif.open(sample_path('sample.vdif'), 'rb') as fh:
+        header = fh.read_header()
+        assert header['thread_id'] == 1 and header.edv == 3
+        assert header.samples_per_frame == 20000
+        fh.seek(0)
+        fs = fh.read_frameset()
+        assert fs.shape == (20000, 8, 1)
+        assert list(fs['thread_id']) == list(range(8))
+        _same(fs.data, want[:20000])
+        _same(fs[5:11, 3], want[5:11, 3])
+        _same(fs[7], want[7])
+        _same(fs[::1000, 2:4, 0], want[:20000:1000, 2:4, 0])
+        fs.fill_value = -7.
+        fs.frames[2].header.mutable = True
+        fs.frames[2].valid = False
+        d = fs.data
+        assert np.all(d[:, 2] == -7.) and np.array_equal(d[:, 3], want[:20000, 3])
+        fs.frames[2].valid = True
+        fs2 = bb.vdif.VDIFFrameSet.fromdata(fs.data, fs.frames[0].header)
+        for a, b in zip(fs.frames, fs2.frames):
+            assert np.array_equal(a.payload.words, b.payload.words)
+        fs3 = fh.read_frameset([3, 5])
+        _same(fs3.data, want[20000:, [3, 5]])
+    frame = bb.vdif.VDIFFrame.fromfile(open(sample_path('sample.vdif'), 'rb'))
+    _same(frame.data, want[:20000, 1])
+    _same(frame[11:17], want[11:17, 1])
+    pl = frame.payload
+    assert pl.shape == (20000, 1)
+    pl2 = bb.vdif.VDIFPayload.fromdata(pl.data, frame.header)
+    assert pl2 == pl
+    pl2[10:13] = np.array([[3.316505], [1.], [-1.]], np.float32)
+    assert np.array_equal(pl2[10:13].ravel(),
+                          np.array([3.316505, 1., -1.], np.float32))
+    assert np.array_equal(pl2[:10], pl[:10]) and np.array_equal(pl2[13:], pl[13:])
