@@ -7,8 +7,8 @@ frame; not part of the GPU hot path.
 """
 import numpy as np
 
-__all__ = ['bcd_decode', 'bcd_encode', 'crc_remainder', 'crc_of_bits',
-           'lcm']
+__all__ = ['bcd_decode', 'bcd_encode', 'crc_remainder', 'crc_array',
+           'crc_of_bits', 'lcm']
 
 
 def lcm(a, b):
@@ -50,6 +50,19 @@ def crc_remainder(value, polynomial, extend=True):
         value ^= polynomial << (nbit - npol)
         nbit = value.bit_length()
     return value
+
+
+def crc_array(values, nbits, polynomial):
+    """CRC of every ``nbits``-bit message in an integer array (vectorised
+    long division; nbits + CRC width must fit in 64 bits)."""
+    ncrc = polynomial.bit_length() - 1
+    assert nbits + ncrc <= 64
+    work = np.asarray(values).astype(np.uint64) << np.uint64(ncrc)
+    pol = np.uint64(polynomial)
+    for bit in range(nbits + ncrc - 1, ncrc - 1, -1):
+        top = (work >> np.uint64(bit)) & np.uint64(1)
+        work ^= (pol << np.uint64(bit - ncrc)) * top
+    return work.astype(np.int64)
 
 
 def crc_of_bits(stream, polynomial):

@@ -1,0 +1,259 @@
+"""Mark 5B file and stream readers/writers (API of baseband/mark5b/base.py).
+
+Stream reads are batched on the GPU: ``bb_mark5b_scan`` parses all headers of
+a chunk (bit fields + BCD) and decides validity from the payload fill pattern;
+``bb_decode_bitfield`` then unpacks every payload to ``(nsample, nchan)`` with
+invalid frames replaced by ``fill_value``.
+"""
+import numpy as np
+import torch
+
+from .. import kernels, levels
+from ..base.opener import make_opener
+from ..base.stream import StreamReaderBase, StreamWriterBase, as_hertz
+from ..base.utils import bcd_encode, crc_array, crc_remainder
+from ..vdif.base import _FileBase
+from .frame import Mark5BFrame, FILL_PATTERN
+from .header import Mark5BHeader, CRC16
+from .payload import Mark5BPayload
+
+__all__ = ['Mark5BFileReader', 'Mark5BFileWriter', 'Mark5BStreamReader',
+           'Mark5BStreamWriter', 'open']
+
+
+class Mark5BFileReader(_FileBase):
+    def __init__(self, fh_raw, kday=None, ref_time=None, nchan=None, bps=2):
+        super().__init__(fh_raw)
+        self.kday, self.ref_time, self.nchan, self.bps = (kday, ref_time,
+                                                          nchan, bps)
+
+    def read_header(self):
+        return Mark5BHeader.fromfile(self.fh_raw, kday=self.kday,
+                                     ref_time=self.ref_time)
+
+    def read_frame(self, verify=True):
+        if self.nchan is None:
+            raise TypeError('In order to read frames, the file handle '
+                            'should be initialized with nchan set.')
+        return Mark5BFrame.fromfile(self.fh_raw, kday=self.kday,
+                                    ref_time=self.ref_time, nchan=self.nchan,
+                                    bps=self.bps, verify=verify)
+
+    def get_frame_rate(self):
+        """Highest frame number within a second, plus one
+        (base/base.py:371-406)."""
+        with self.temporary_offset(0):
+            header = self.read_header()
+            frame_nr0 = header['frame_nr']
+            while header['frame_nr'] == frame_nr0:
+                self.fh_raw.seek(10000, 1)
+                header = self.read_header()
+            highest = frame_nr0
+            while header['frame_nr'] > 0:
+                highest = max(highest, header['frame_nr'])
+                self.fh_raw.seek(10000, 1)
+                header = self.read_header()
+        return float(highest + 1)
+
+    def locate_frame(self, maximum=None):
+        """Offset of the first sync pattern that is followed by another one a
+        frame ahead (or the end of file) and has a correct CRC
+        (mark5b/base.py:95-155, forward search only)."""
+        start = self.fh_raw.tell()
+        size = self.fh_raw.seek(0, 2)
+        maximum = 10016 if maximum is None else maximum
+        self.fh_raw.seek(start)
+        block = np.frombuffer(self.fh_raw.read(maximum + 10016 + 16),
+                              np.uint8)
+        sync = np.array([0xED, 0xDE, 0xAD, 0xAB], np.uint8)
+        hits = np.flatnonzero((block[:-3] == sync[0]) & (block[1:-2] == sync[1])
+                              & (block[2:-1] == sync[2])
+                              & (block[3:] == sync[3]))
+        for h in hits:
+            if h > maximum:
+                break
+            nxt = h + 10016
+            if start + nxt + 4 <= size and nxt + 4 <= block.size \
+                    and not np.array_equal(block[nxt:nxt + 4], sync):
+                continue
+            w = block[h:h + 16].copy().view('<u4')
+            message = (int(w[2]) << 32) | int(w[3])
+            if crc_remainder(message, CRC16, extend=False) == 0:
+                self.fh_raw.seek(start + int(h))
+                return start + int(h)
+        self.fh_raw.seek(start)
+        return None
+
+
+class Mark5BFileWriter(_FileBase):
+    def write_frame(self, data, header=None, bps=2, valid=True, **kwargs):
+        if not isinstance(data, Mark5BFrame):
+            data = Mark5BFrame.fromdata(data, header, bps=bps, valid=valid,
+                                        **kwargs)
+        return data.tofile(self.fh_raw)
+
+
+class _Mark5BStreamBase:
+    def _get_index(self, header):
+        # mark5b/base.py:206-213
+        h0 = self.header0
+        return int(round(self._frame_rate * (
+            header.seconds - h0.seconds
+            + 86400 * (header.kday + header.jday - h0.kday - h0.jday))
+            + header['frame_nr'] - h0['frame_nr']))
+
+    def _get_time(self, header):
+        return header.get_time(frame_rate=self._frame_rate)
+
+    def _set_time(self, header, time):
+        header.update(time=time, frame_rate=self._frame_rate)
+
+
+class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
+    """Mark 5B stream reader (GPU decode).  ``nchan`` is required; ``kday``
+    or ``ref_time`` complete the header time."""
+    _sample_shape_maker = Mark5BPayload._sample_shape_maker
+
+    def __init__(self, fh_raw, sample_rate=None, kday=None, ref_time=None,
+                 nchan=None, bps=2, squeeze=True, subset=(), fill_value=0.,
+                 verify=True, device=None, chunk_nbytes=None):
+        if nchan is None:
+            raise TypeError('Mark 5B stream reader requires nchan to be '
+                            'passed in explicitly.')
+        fh_raw = Mark5BFileReader(fh_raw, kday=kday, ref_time=ref_time,
+                                  nchan=nchan, bps=bps)
+        offset0 = fh_raw.locate_frame()
+        if offset0 is None:
+            raise OSError('could not find a Mark 5B frame header.')
+        self._file_offset0 = offset0
+        header0 = fh_raw.read_header()
+        sample_rate = as_hertz(sample_rate)
+        spf = 10000 * 8 // (bps * nchan)
+        if sample_rate is None:
+            fh_raw.seek(offset0)
+            with fh_raw.temporary_offset(offset0):
+                # frame-rate scan starts from the first frame found
+                rate = _scan_frame_rate(fh_raw, offset0)
+            sample_rate = rate * spf
+        size = fh_raw.seek(0, 2)
+        self._nframe = (size - offset0) // 10016
+        super().__init__(
+            fh_raw, header0, sample_rate=sample_rate, samples_per_frame=spf,
+            sample_shape=(nchan,), bps=bps, complex_data=False,
+            squeeze=squeeze, subset=subset, fill_value=fill_value,
+            verify=verify, device=device, chunk_nbytes=chunk_nbytes)
+        self._levels = levels.mark5b(bps)
+        self._checks = []
+
+    _frame_nbytes = 10016
+
+    def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
+        fields, uo = kernels.mark5b_scan(raw, nframe)
+        if self.verify:
+            h0 = self.header0
+            fps = int(round(self._frame_rate))
+            day = fields[kernels.M5B_JDAY].to(torch.int64)
+            # jday wraps every 1000 days; index arithmetic modulo that
+            dday = torch.remainder(day - h0.jday + 500, 1000) - 500
+            index = ((fields[kernels.M5B_SECONDS].to(torch.int64) - h0.seconds
+                      + 86400 * dday) * fps
+                     + fields[kernels.M5B_FRAME_NR].to(torch.int64)
+                     - h0['frame_nr'])
+            want = torch.arange(frame0, frame0 + nframe, device=raw.device)
+            sync_ok = fields[kernels.M5B_SYNC] == -1414668563  # 0xABADDEED
+            self._checks.append(((index != want) | ~sync_ok).sum())
+        kernels.decode_bitfield(
+            raw, uo, nframe, 1, 10000, self._bps, self._sample_shape[0],
+            False, kernels.CODEC_LEVELS, self._levels, self._fill_value,
+            sample_start, nsample, out)
+
+    def read(self, count=None, out=None):
+        self._checks = []
+        result = super().read(count, out)
+        if self._checks and int(torch.stack(self._checks).sum().item()):
+            raise OSError('Mark 5B stream is not a regular sequence of '
+                          'frames; recovery of corrupt files is not part of '
+                          'the GPU path.')
+        return result
+
+
+def _scan_frame_rate(fh_raw, offset0):
+    fh = fh_raw.fh_raw
+    fh.seek(offset0)
+    header = fh_raw.read_header()
+    frame_nr0 = header['frame_nr']
+    while header['frame_nr'] == frame_nr0:
+        fh.seek(10000, 1)
+        header = fh_raw.read_header()
+    highest = frame_nr0
+    while header['frame_nr'] > 0:
+        highest = max(highest, header['frame_nr'])
+        fh.seek(10000, 1)
+        header = fh_raw.read_header()
+    return float(highest + 1)
+
+
+class Mark5BStreamWriter(_Mark5BStreamBase, StreamWriterBase):
+    """Mark 5B stream writer (GPU encode)."""
+    _sample_shape_maker = Mark5BPayload._sample_shape_maker
+
+    def __init__(self, fh_raw, header0=None, sample_rate=None, nchan=1,
+                 bps=2, squeeze=True, device=None):
+        fh_raw = Mark5BFileWriter(fh_raw)
+        spf = 10000 * 8 // (bps * nchan)
+        super().__init__(fh_raw, header0, sample_rate=sample_rate,
+                         samples_per_frame=spf, sample_shape=(nchan,),
+                         bps=bps, complex_data=False, squeeze=squeeze,
+                         device=device)
+
+    def _encode_frames(self, flat, index0, nframe, valid):
+        h0 = self.header0
+        dev = flat.device
+        fps = int(round(self._frame_rate))
+        # header words per frame: mark5b/base.py:215-225 (_set_index)
+        index = np.arange(index0, index0 + nframe, dtype=np.int64)
+        dt, frame_nr = np.divmod(index + h0['frame_nr'], fps)
+        seconds = h0.seconds + dt
+        dday, seconds = np.divmod(seconds, 86400)
+        jday = (h0.jday + dday) % 1000
+        # fraction: ns rounded, then truncated to 0.1 ms (header.py:223-230)
+        ns = np.round(frame_nr / self._frame_rate * 1e9).astype(np.int64)
+        frac = ns // 100000
+        bj, bs, bf = bcd_encode(jday), bcd_encode(seconds), bcd_encode(frac)
+        words = np.empty((nframe, 4), np.uint32)
+        words[:, 0] = h0.words[0]
+        words[:, 1] = ((np.uint32(h0.words[1]) & np.uint32(0xffff8000))
+                       | frame_nr.astype(np.uint32))
+        words[:, 2] = ((bj << 20) | bs).astype(np.uint32)
+        stream = (((bj << 20) | bs) << 16) | bf
+        crc = crc_array(stream, 48, CRC16)
+        words[:, 3] = ((bf << 16) | crc).astype(np.uint32)
+        frames = torch.empty((nframe, 10016), dtype=torch.uint8, device=dev)
+        frames[:, :16] = torch.from_numpy(words.view(np.uint8)).to(dev)
+        uo_host = np.arange(nframe, dtype=np.int64) * 10016 + 16
+        uo_host[~valid] = -1
+        kernels.encode_bitfield(flat, frames.view(-1),
+                                torch.from_numpy(uo_host).to(dev), nframe, 1,
+                                10000, self._bps, self._sample_shape[0],
+                                kernels.QUANT_MARK5B)
+        if not valid.all():
+            # invalid frames carry the fill pattern (mark5b/frame.py:126-133)
+            fill = torch.from_numpy(np.full(2500, FILL_PATTERN, '<u4')
+                                    .view(np.uint8)).to(dev)
+            frames[torch.from_numpy(~valid).to(dev), 16:] = fill
+        return frames.view(-1)
+
+
+open = make_opener('mark5b', {'rb': Mark5BFileReader, 'wb': Mark5BFileWriter,
+                              'rs': Mark5BStreamReader,
+                              'ws': Mark5BStreamWriter},
+                   header_class=Mark5BHeader,
+                   non_header_keys={'sample_rate', 'nchan', 'bps', 'kday',
+                                    'ref_time'},
+                   doc="""Open Mark 5B file(s) for reading or writing.
+
+Reader options: ``sample_rate``, ``kday`` or ``ref_time``, ``nchan``
+(required), ``bps``, ``squeeze``, ``subset``, ``fill_value``, ``verify``,
+``device``.  Writer: ``header0`` or header keywords (``time=...``),
+``sample_rate``, ``nchan``, ``bps``, ``squeeze``, ``device``.
+""")

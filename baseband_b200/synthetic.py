@@ -88,6 +88,10 @@ def mark5b_stream(nframe, seed=MARK5B_SEED, invalid_fraction=0.01,
     w[:, 2] = (bcd(jday, 3) << 20) | bcd_sec[sec - seconds0]
     frac = (fnr * 10000 // frames_per_second)
     w[:, 3] = np.array([bcd(int(f), 4) for f in frac], np.uint32) << 16
+    from .base.utils import crc_array
+    w[:, 3] |= crc_array((w[:, 2].astype(np.uint64) << np.uint64(16))
+                         | (w[:, 3] >> np.uint32(16)).astype(np.uint64),
+                         48, 0x18005).astype(np.uint32)
     return frames.reshape(-1), ~bad
 
 
