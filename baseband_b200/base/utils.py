@@ -70,7 +70,8 @@ def crc_of_bits(stream, polynomial):
     stream (one per bit level of the integers).  Returns the ncrc words to
     append (baseband/base/utils.py:200-248 semantics)."""
     ncrc = polynomial.bit_length() - 1
-    work = np.concatenate([stream, np.zeros(ncrc, stream.dtype)])
+    work = np.concatenate([stream, np.zeros((ncrc,) + stream.shape[1:],
+                                            stream.dtype)])
     pol_bits = [(polynomial >> (ncrc - k)) & 1 for k in range(ncrc + 1)]
     for i in range(len(stream)):
         bits = work[i].copy()

@@ -300,3 +300,107 @@ def mark5b_write_roundtrip():
     assert np.all(got[1, 16:].view('<u4') == 0x11223344)
     _same(got[2, 16:], raw.reshape(4, 10016)[2, 16:])
     _same(got[:, 8:16], raw.reshape(4, 10016)[:3, 8:16])     # time code + CRC
+
+
+# ------------------------------------------------------------------ Mark 4
+M4_SAMPLES = [('sample.m4', 64), ('sample_32track.m4', 32),
+              ('sample_32track_fanout2.m4', 32), ('sample_16track.m4', 16),
+              ('sample_64track_fanout2_ft.m4', 64)]
+
+
+def mark4_sample_read():
+    for name, ntrack in M4_SAMPLES:
+        tag = name.replace('.', '_')
+        want = OUT[tag + '_data']
+        for kw in ({'ntrack': ntrack}, {}):
+            with bb.mark4.open(sample_path(name), 'rs', decade=2010,
+                               fill_value=-7., **kw) as fh:
+                assert fh.shape == want.shape, (name, fh.shape)
+                assert fh.fh_raw.ntrack == ntrack
+                assert fh._file_offset0 == int(OUT[tag + '_offset0'])
+                data = fh.read()
+                ref = want                  # golden made with fill_value -7
+                _same(data, ref)
+                spf = fh.samples_per_frame
+                fh.seek(spf - 3)
+                n = min(703, fh.shape[0] - (spf - 3))
+                _same(fh.read(n), ref[spf - 3:spf - 3 + n])
+    with bb.mark4.open(sample_path('sample.m4'), 'rs', ntrack=64,
+                       ref_time='2013-01-01T00:00:00') as fh:
+        assert fh.sample_rate == 32e6
+        assert fh.start_time.isot == '2014-06-16T07:38:12.475000000'
+        assert fh.header0.decade == 2010
+        data = fh.read(80000)
+        # values asserted by the reference (test_mark4.py:324-327, :757-765)
+        assert np.all(data[640:642].astype(int) == np.array(
+            [[-1, +1, +1, -3, -3, -3, +1, -1],
+             [+1, +1, -3, +1, +1, -3, -1, -1]]))
+        assert np.all(data[:640] == 0.)
+
+
+def mark4_frame_api():
+    want = OUT['sample_m4_data']
+    with bb.mark4.open(sample_path('sample.m4'), 'rb', ntrack=64,
+                       decade=2010) as fb:
+        assert fb.locate_frame() == 0xa88
+        frame = fb.read_frame()
+    assert frame.shape == (80000, 8) and frame.valid
+    assert np.all(frame[3] == 0.)
+    frame.fill_value = -7.
+    _same(frame.data, want[:80000])
+    _same(frame[630:650], want[630:650])
+    _same(frame[700:720, 3], want[700:720, 3])
+    _same(frame[635::7][:5], want[635:80000:7][:5])
+    frame2 = bb.mark4.Mark4Frame.fromdata(frame.data, frame.header)
+    assert np.array_equal(frame2.payload.words, frame.payload.words)
+    buf = io.BytesIO()
+    frame2.tofile(buf)
+    raw = np.fromfile(sample_path('sample.m4'), np.uint8)[0xa88:0xa88 + 160000]
+    _same(np.frombuffer(buf.getvalue(), np.uint8), raw)
+    frame.header.mutable = True
+    frame.valid = False
+    frame.fill_value = 9.
+    assert np.all(frame[1000:1010] == 9.)
+
+
+def mark4_synthetic_and_write():
+    """Config 3 geometry: 64 tracks, fanout 4; invalid frame; byte-identical
+    rewrite through the stream writer."""
+    h0 = bb.mark4.Mark4Header.fromvalues(
+        64, time='2014-06-16T07:38:12.475', bps=2, fanout=4, nsb=1,
+        system_id=108)
+    rng = np.random.default_rng(31)
+    data = rng.choice(np.array([-3.316505, -1., 1., 3.316505], np.float32),
+                      size=(7 * 80000, 8))
+    buf = io.BytesIO()
+    fw = bb.mark4.open(buf, 'ws', header0=h0, sample_rate=32e6)
+    fw.write(data[:100000])
+    fw.write(data[100000:3 * 80000])
+    fw.write(data[3 * 80000:4 * 80000], valid=False)
+    fw.write(data[4 * 80000:])
+    raw = np.frombuffer(buf.getvalue(), np.uint8)
+    assert raw.size == 7 * 160000
+    # oracle reading of what was written
+    want = ostream.mark4_read(raw, 64, fill_value=-2.)
+    expect = data.copy()
+    for f in range(7):
+        expect[f * 80000:f * 80000 + 640] = -2.
+    expect[3 * 80000:4 * 80000] = -2.
+    _same(want, expect)
+    with bb.mark4.open(io.BytesIO(raw.tobytes()), 'rs', ntrack=64,
+                       decade=2010, fill_value=-2.,
+                       chunk_nbytes=2 * 160000) as fh:
+        assert fh.sample_rate == 32e6
+        _same(fh.read(), expect)
+        assert fh.stop_time.isot == '2014-06-16T07:38:12.492500000'
+    # the reference's own sample, rewritten byte for byte
+    src = np.fromfile(sample_path('sample.m4'), np.uint8)[0xa88:]
+    with bb.mark4.open(sample_path('sample.m4'), 'rs', ntrack=64,
+                       decade=2010) as fh:
+        header0, sdata = fh.header0, fh.read()
+    buf = io.BytesIO()
+    fw = bb.mark4.open(buf, 'ws', header0=header0, sample_rate=32e6)
+    fw.write(sdata)
+    got = np.frombuffer(buf.getvalue(), np.uint8)
+    _same(got, src[:got.size])
+    assert got.size == 2 * 160000
