@@ -404,3 +404,111 @@ def mark4_synthetic_and_write():
     got = np.frombuffer(buf.getvalue(), np.uint8)
     _same(got, src[:got.size])
     assert got.size == 2 * 160000
+
+
+# ------------------------------------------------------------------ GUPPI
+def _guppi_expected(frames, overlap, start, count):
+    """Reference read loop on per-frame decoded arrays (full length incl.
+    overlap): [start, len) of the first frame, [overlap, len) of later."""
+    stride = frames.shape[1] - overlap
+    total = stride * len(frames) + overlap
+    normal_end = total - overlap
+    pieces, pos, done = [], start, 0
+    while done < count:
+        if normal_end <= pos < total:
+            index, local = divmod(normal_end - 1, stride)
+            local += 1 + pos - normal_end
+        else:
+            index, local = divmod(pos, stride)
+        n = min(count - done, frames.shape[1] - local)
+        pieces.append(frames[index][local:local + n])
+        done += n
+        pos += n
+    return np.concatenate(pieces)
+
+
+def guppi_sample_read():
+    frames = OUT['sample_puppi_frames']            # (4, 1024, 2, 4)
+    with bb.guppi.open(sample_path('sample_puppi.raw'), 'rs') as fh:
+        assert fh.shape == (3904, 2, 4)
+        assert fh.sample_shape.npol == 2 and fh.sample_shape.nchan == 4
+        assert fh.samples_per_frame == 960
+        assert fh.sample_rate == 250.
+        assert fh.complex_data and fh.bps == 8
+        assert fh.start_time.isot == '2018-01-14T14:11:33.000000000'
+        data = fh.read()
+        _same(data, _guppi_expected(frames, 64, 0, 3904))
+        for start, count in ((0, 1), (959, 3), (1000, 1500), (3839, 65),
+                             (3850, 54), (30, 3000)):
+            fh.seek(start)
+            _same(fh.read(count), _guppi_expected(frames, 64, start, count))
+        # values the reference asserts (test_guppi.py:236-249 region)
+        assert data[0, 0, 0] == frames[0][0, 0, 0]
+    with bb.guppi.open(sample_path('sample_puppi.raw'), 'rs',
+                       subset=(0, [1, 3]), chunk_nbytes=1) as fh:
+        fh.seek(900)
+        _same(fh.read(200),
+              _guppi_expected(frames, 64, 900, 200)[:, 0][:, [1, 3]])
+    with bb.guppi.open(sample_path('sample_puppi.raw'), 'rb') as fb:
+        frame = fb.read_frame()
+        assert frame.shape == (1024, 2, 4)
+        _same(frame.data, frames[0])
+        _same(frame[100:200, 1], frames[0][100:200, 1])
+        _same(frame.payload[37], frames[0][37])
+        fb.seek(3 * 22784)
+        f3 = fb.read_frame(memmap=False)
+        _same(f3.data, frames[3])
+        pl = bb.guppi.GUPPIPayload(f3.payload.words, sample_shape=(2, 4),
+                                   bps=8, complex_data=True,
+                                   channels_first=False)
+        _same(pl.data, OUT['sample_puppi_frame3_timefirst'])
+        for cf in (True, False):
+            pl2 = bb.guppi.GUPPIPayload.fromdata(
+                frames[2], bps=8, channels_first=cf)
+            _same(pl2.data, frames[2])
+            pl2[10:12, 1] = np.array([[1 - 2j] * 4, [3 + 4j] * 4],
+                                     np.complex64)
+            assert np.all(pl2[10, 1] == 1 - 2j) and np.all(pl2[11, 1] == 3 + 4j)
+            _same(pl2[12:], frames[2][12:])
+        pl3 = bb.guppi.GUPPIPayload.fromdata(frames[3], f3.header)
+        assert np.array_equal(pl3.words, f3.payload.words)
+
+
+def guppi_synthetic_and_write():
+    """Config 4 geometry (scaled): 512 channels, 2 pol, overlap."""
+    raw, truth = synthetic.guppi_stream(5, nchan=512, npol=2,
+                                        samples_per_frame=128, overlap=16,
+                                        seed=2)
+    want = ostream.guppi_read(raw)
+    cube = truth.astype(np.float32).transpose(1, 2, 0, 3)  # (t, pol, ch, 2)
+    direct = (cube[..., 0] + 1j * cube[..., 1]).astype(np.complex64)
+    _same(want, direct)
+    with bb.guppi.open(io.BytesIO(raw.tobytes()), 'rs',
+                       chunk_nbytes=2 * (raw.size // 5)) as fh:
+        assert fh.shape == want.shape
+        _same(fh.read(), want)
+        fh.seek(100)
+        _same(fh.read(400), want[100:500])
+    # writer: no overlap; channels first and time first; read back
+    rng = np.random.default_rng(8)
+    data = (rng.integers(-128, 128, (3 * 64, 2, 32))
+            + 1j * rng.integers(-128, 128, (3 * 64, 2, 32))).astype(
+                np.complex64)
+    for pktfmt in ('1SFA', 'SIMPLE'):
+        buf = io.BytesIO()
+        fw = bb.guppi.open(buf, 'ws', time='2018-01-14T14:11:33',
+                           sample_rate=250., samples_per_frame=64,
+                           sample_shape=(2, 32), pktfmt=pktfmt, pktsize=1024)
+        fw.write(data[:100])
+        fw.write(data[100:] + 0.25)     # rounds back to the integers
+        raw2 = buf.getvalue()
+        hdr = bb.guppi.GUPPIHeader.fromfile(io.BytesIO(raw2))
+        assert hdr.channels_first == (pktfmt == '1SFA')
+        assert len(raw2) == 3 * hdr.frame_nbytes
+        _same(ostream.guppi_read(np.frombuffer(raw2, np.uint8)), data)
+        with bb.guppi.open(io.BytesIO(raw2), 'rs') as fr:
+            assert fr.start_time.isot == '2018-01-14T14:11:33.000000000'
+            _same(fr.read(), data)
+            h2 = bb.guppi.GUPPIHeader.fromfile(
+                io.BytesIO(raw2[2 * hdr.frame_nbytes:]))
+            assert fr._get_index(h2) == 2
