@@ -396,7 +396,11 @@ class StreamReaderBase(StreamBase):
     def _frames_per_chunk(self):
         return max(1, self._chunk_nbytes // self._frame_nbytes)
 
-    def _read_raw(self, frame0, nframe, pinned):
+    def _chunk_nbytes_of(self, frame0, nframe, sample_start, nsample):
+        """Raw bytes a chunk needs on the device."""
+        return nframe * self._frame_nbytes
+
+    def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
         """Fill ``pinned`` (uint8 tensor) with the bytes of frames
         [frame0, frame0 + nframe)."""
         self.fh_raw.seek(self._file_offset0 + frame0 * self._frame_nbytes)
@@ -478,11 +482,11 @@ class StreamReaderBase(StreamBase):
         ss.after_caller(1)
         for k, (f0, nf, s0, ns, row) in enumerate(self._chunks(start, count)):
             st = stages[k % 2]
-            nbytes = nf * self._frame_nbytes
+            nbytes = self._chunk_nbytes_of(f0, nf, s0, ns)
             if st.done is not None:
                 st.done.synchronize()        # pinned buffer free again
             pin, raw = st.buffers(nbytes, 0, dev, False)
-            self._read_raw(f0, nf, pin)
+            self._read_raw(f0, nf, pin, s0, ns)
             with ss.use(0):
                 ss.wait(0, 1)                # raw[k%2] no longer being read
                 raw.copy_(pin, non_blocking=True)
@@ -533,11 +537,11 @@ class StreamReaderBase(StreamBase):
             for k, (f0, nf, s0, ns, row) in enumerate(
                     self._chunks(start, count)):
                 st = stages[k % 2]
-                nbytes = nf * self._frame_nbytes
+                nbytes = self._chunk_nbytes_of(f0, nf, s0, ns)
                 if st.done is not None:
                     st.done.synchronize()
                 pin, raw = st.buffers(nbytes, ns * fps, dev, True)
-                self._read_raw(f0, nf, pin)
+                self._read_raw(f0, nf, pin, s0, ns)
                 with ss.use(0):
                     raw.copy_(pin, non_blocking=True)
                 with ss.use(1):

@@ -1,0 +1,5 @@
+"""DADA format reader/writer, decoded on the GPU."""
+from .base import open  # noqa: F401
+from .header import DADAHeader  # noqa: F401
+from .payload import DADAPayload, MKBFPayload  # noqa: F401
+from .frame import DADAFrame  # noqa: F401

@@ -1,0 +1,216 @@
+"""DADA file and stream readers/writers (API of baseband/dada/base.py).
+
+A DADA file is one (possibly very large) frame, or a sequence of equal frames
+the last of which may be cut short (dada/base.py:277-332).  Since samples are
+stored time-major, the stream reader does not batch by frames but cuts the
+payloads into pieces of ``chunk_nbytes`` on sample boundaries; each piece is
+one launch of the int8 kernel.
+"""
+import numpy as np
+
+from ..base.opener import make_opener
+from ..base.stream import StreamReaderBase, StreamWriterBase
+from ..base.utils import lcm
+from ..vdif.base import _FileBase
+from .frame import DADAFrame
+from .header import DADAHeader
+from .payload import DADAPayload, decode_device, HEAP
+
+__all__ = ['DADAFileReader', 'DADAFileWriter', 'DADAStreamReader',
+           'DADAStreamWriter', 'open']
+
+
+class DADAFileReader(_FileBase):
+    def read_header(self):
+        return DADAHeader.fromfile(self.fh_raw)
+
+    def read_frame(self, memmap=True, verify=True):
+        return DADAFrame.fromfile(self.fh_raw, memmap=memmap, verify=verify)
+
+    def get_frame_rate(self):
+        with self.temporary_offset(0):
+            header = self.read_header()
+        return header.sample_rate / header.samples_per_frame
+
+
+class DADAFileWriter(_FileBase):
+    def write_frame(self, data, header=None, **kwargs):
+        if not isinstance(data, DADAFrame):
+            data = DADAFrame.fromdata(data, header, **kwargs)
+        return data.tofile(self.fh_raw)
+
+
+class _DADAStreamBase:
+    _sample_shape_maker = DADAPayload._sample_shape_maker
+
+    def _get_index(self, header):
+        return int(round((header['OBS_OFFSET'] - self.header0['OBS_OFFSET'])
+                         / self.header0.payload_nbytes))
+
+    def _set_index(self, header, index):
+        header.update(obs_offset=self.header0['OBS_OFFSET']
+                      + index * self.header0.payload_nbytes)
+
+
+class DADAStreamReader(_DADAStreamBase, StreamReaderBase):
+    """DADA stream reader (GPU decode)."""
+
+    def __init__(self, fh_raw, squeeze=True, subset=(), verify=True,
+                 device=None, chunk_nbytes=None):
+        fh_raw = DADAFileReader(fh_raw)
+        header0 = fh_raw.read_header()
+        size = fh_raw.seek(0, 2)
+        nframe, partial = divmod(size, header0.frame_nbytes)
+        self._last_nbytes = header0.payload_nbytes
+        if partial > header0.nbytes:
+            # truncated last frame: whole words and whole samples only
+            sample_nbytes = (header0.bps * (2 if header0.complex_data else 1)
+                             * header0['NPOL'] * header0['NCHAN']) // 8
+            block = lcm(4, sample_nbytes)
+            self._last_nbytes = (partial - header0.nbytes) // block * block
+            nframe += 1
+        elif nframe == 0:
+            raise EOFError('file (of {0} bytes) appears to end without any '
+                           'payload.'.format(partial))
+        self._nframe = nframe
+        spf = header0.samples_per_frame
+        if nframe == 1 and self._last_nbytes != header0.payload_nbytes:
+            spf = self._last_nbytes * 8 // header0._bits_per_sample
+        self._mkbf = header0.get('INSTRUMENT') == 'MKBF'
+        super().__init__(fh_raw, header0, squeeze=squeeze, subset=subset,
+                         verify=verify, samples_per_frame=spf, device=device,
+                         chunk_nbytes=chunk_nbytes)
+        self._sample_nbytes = header0._bits_per_sample // 8
+        self._last_nsample = self._last_nbytes // self._sample_nbytes
+
+    @property
+    def _nsample(self):
+        return (self._nframe - 1) * self._samples_per_frame \
+            + self._last_nsample
+
+    @property
+    def _frame_nbytes(self):
+        return self.header0.frame_nbytes
+
+    def _chunks(self, start, count):
+        """Pieces never span frames: (frame, 1, local start, n, row)."""
+        if count == 0:
+            return
+        spf = self._samples_per_frame
+        step = max(1, self._chunk_nbytes // self._sample_nbytes)
+        if self._mkbf:
+            step = max(HEAP, step // HEAP * HEAP)
+        pos, row = start, 0
+        while row < count:
+            frame, local = divmod(pos, spf)
+            in_frame = (self._last_nsample if frame == self._nframe - 1
+                        else spf)
+            n = min(count - row, in_frame - local, step - local % step
+                    if self._mkbf else step)
+            yield frame, 1, local, n, row
+            pos += n
+            row += n
+
+    def _piece(self, local, n):
+        """Byte range (relative to the payload) needed for samples
+        [local, local + n), 4-byte aligned, and the sample it starts at."""
+        unit = HEAP if self._mkbf else 1
+        s0 = local // unit * unit
+        b0 = s0 * self._sample_nbytes
+        shift = b0 % 4
+        if shift:          # align start down to a word: whole samples only
+            per = lcm(4, self._sample_nbytes) // self._sample_nbytes
+            s0 = s0 // per * per
+            b0 = s0 * self._sample_nbytes
+        s1 = -(-(local + n) // unit) * unit
+        b1 = -(-(s1 * self._sample_nbytes) // 4) * 4
+        return s0, b0, b1
+
+    def _chunk_nbytes_of(self, frame0, nframe, sample_start, nsample):
+        s0, b0, b1 = self._piece(sample_start, nsample)
+        limit = (self._last_nbytes if frame0 == self._nframe - 1
+                 else self.header0.payload_nbytes)
+        return min(b1, limit) - b0
+
+    def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
+        s0, b0, b1 = self._piece(sample_start, nsample)
+        self.fh_raw.seek(frame0 * self.header0.frame_nbytes
+                         + self.header0.nbytes + b0)
+        view = pinned.numpy()
+        if self.fh_raw.readinto(memoryview(view)) != view.size:
+            raise EOFError('could not read payload bytes of frame {}.'
+                           .format(frame0))
+
+    def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
+        h0 = self.header0
+        if h0.bps != 8:
+            raise KeyError(h0.bps)
+        s0, b0, b1 = self._piece(sample_start, nsample)
+        decode_device(raw, 0, raw.numel(), h0['NPOL'], h0['NCHAN'],
+                      h0.complex_data, self._mkbf, sample_start - s0,
+                      nsample, out)
+
+    @property
+    def stop_time(self):
+        return self.start_time + self._offset_seconds(self._nsample)
+
+
+class DADAStreamWriter(_DADAStreamBase, StreamWriterBase):
+    """DADA stream writer (GPU encode): every frame is ``header0`` with
+    ``OBS_OFFSET`` advanced, followed by the encoded payload."""
+
+    def __init__(self, fh_raw, header0, squeeze=True, device=None):
+        fh_raw = DADAFileWriter(fh_raw)
+        super().__init__(fh_raw, header0, squeeze=squeeze, device=device)
+
+    def _encode_frames(self, flat, index0, nframe, valid):
+        import io
+        import torch
+        from .. import kernels
+        h0 = self.header0
+        dev = flat.device
+        if h0.bps != 8:
+            raise ValueError('DADAPayload cannot encode data with {} bits'
+                             .format(h0.bps))
+        frames = torch.empty((nframe, h0.frame_nbytes), dtype=torch.uint8,
+                             device=dev)
+        texts = []
+        for i in range(nframe):
+            header = h0.copy()
+            header.mutable = True
+            self._set_index(header, index0 + i)
+            with io.BytesIO() as s:
+                header.tofile(s)
+                texts.append(np.frombuffer(s.getvalue(), np.uint8))
+        frames[:, :h0.nbytes] = torch.from_numpy(np.stack(texts)).to(dev)
+        ib = 2 if h0.complex_data else 1
+        nelem = h0['NPOL'] * h0['NCHAN'] * ib
+        if h0.get('INSTRUMENT') == 'MKBF':
+            heap_nbytes = nelem * HEAP
+            per = h0.payload_nbytes // heap_nbytes
+            uo = ((torch.arange(nframe, dtype=torch.int64, device=dev)
+                   * h0.frame_nbytes + h0.nbytes)[:, None]
+                  + torch.arange(per, dtype=torch.int64, device=dev)
+                  * heap_nbytes).reshape(-1)
+            kernels.encode_int8_transposed(flat, frames.view(-1), uo,
+                                           nframe * per,
+                                           h0['NPOL'] * h0['NCHAN'], HEAP, ib)
+        else:
+            uo = (torch.arange(nframe, dtype=torch.int64, device=dev)
+                  * h0.frame_nbytes + h0.nbytes)
+            kernels.encode_bitfield(flat, frames.view(-1), uo, nframe, 1,
+                                    h0.payload_nbytes, 8, nelem,
+                                    kernels.QUANT_SINT)
+        return frames.view(-1)
+
+
+open = make_opener('dada', {'rb': DADAFileReader, 'wb': DADAFileWriter,
+                            'rs': DADAStreamReader, 'ws': DADAStreamWriter},
+                   header_class=DADAHeader,
+                   doc="""Open DADA file(s) for reading or writing.
+
+Reader options: ``squeeze``, ``subset``, ``verify``, ``device``.  Writer:
+``header0`` or header keywords (``time``, ``sample_rate``,
+``samples_per_frame``, ``sample_shape``, ``bps``, ``complex_data`` ...),
+``squeeze``, ``device``.
+""")

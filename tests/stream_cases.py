@@ -512,3 +512,74 @@ def guppi_synthetic_and_write():
             h2 = bb.guppi.GUPPIHeader.fromfile(
                 io.BytesIO(raw2[2 * hdr.frame_nbytes:]))
             assert fr._get_index(h2) == 2
+
+
+# ------------------------------------------------------------------ DADA
+def dada_sample_read():
+    for name in ('sample.dada', 'sample_meerkat.dada', 'sample_mkbf.dada'):
+        want = OUT[name.replace('.', '_') + '_data']
+        for chunk in (None, 3000):
+            with bb.dada.open(sample_path(name), 'rs', squeeze=False,
+                              chunk_nbytes=chunk) as fh:
+                assert fh.shape == want.shape, (name, fh.shape, want.shape)
+                _same(fh.read(), want)
+                fh.seek(250)
+                _same(fh.read(777), want[250:1027]) if want.shape[0] > 1027 \
+                    else _same(fh.read(5), want[250:255])
+    with bb.dada.open(sample_path('sample.dada'), 'rs') as fh:
+        assert fh.sample_shape == (2,) and fh.sample_shape.npol == 2
+        assert fh.sample_rate == 16e6 and fh.complex_data
+        assert fh.start_time.isot == '2013-07-02T01:39:20.000000000'
+        data = fh.read(12)
+        # values asserted by the reference (test_dada.py:180-183)
+        assert np.all(data[:3] == np.array(
+            [[-38 - 38j, -38 - 38j], [-38 - 38j, -40 + 0j],
+             [-105 + 60j, 85 - 15j]], np.complex64))
+        assert fh.stop_time.isot == '2013-07-02T01:39:20.001000000'
+    with bb.dada.open(sample_path('sample.dada'), 'rb') as fb:
+        frame = fb.read_frame(memmap=False)
+        assert frame.shape == (16000, 2, 1)
+        _same(frame.data, OUT['sample_dada_data'])
+        _same(frame[100:110, 1], OUT['sample_dada_data'][100:110, 1])
+        pl = bb.dada.DADAPayload.fromdata(frame.data, frame.header)
+        assert np.array_equal(pl.words, frame.payload.words)
+    # MKBF payload object: heaps decoded and re-encoded on the GPU
+    want = OUT['sample_mkbf_dada_data']
+    raw = np.fromfile(sample_path('sample_mkbf.dada'), np.uint8)[4096:]
+    hdr = bb.dada.DADAHeader.fromfile(open(sample_path('sample_mkbf.dada'),
+                                           'rb'))
+    h2 = hdr.copy()
+    h2.mutable = True
+    h2.payload_nbytes = raw.size
+    pl = bb.dada.DADAPayload(raw.view('<u4'), header=h2)
+    assert type(pl) is bb.dada.MKBFPayload and pl.shape == want.shape
+    _same(pl.data, want)
+    _same(pl[100:300, 1, 5:9], want[100:300, 1, 5:9])
+    pl2 = bb.dada.DADAPayload.fromdata(want, h2)
+    assert np.array_equal(pl2.words, pl.words)
+
+
+def dada_write_roundtrip():
+    rng = np.random.default_rng(4)
+    data = (rng.integers(-128, 128, (3000, 2, 4))
+            + 1j * rng.integers(-128, 128, (3000, 2, 4))).astype(np.complex64)
+    buf = io.BytesIO()
+    fw = bb.dada.open(buf, 'ws', time='2013-07-02T01:39:20',
+                      sample_rate=16e6, samples_per_frame=1000,
+                      sample_shape=(2, 4), complex_data=True, bps=8)
+    fw.write(data[:1500])
+    fw.write(data[1500:])
+    raw = buf.getvalue()
+    assert len(raw) == 3 * (4096 + 16000)
+    _same(ostream.dada_read(np.frombuffer(raw, np.uint8)), data)
+    with bb.dada.open(io.BytesIO(raw), 'rs', chunk_nbytes=5000) as fr:
+        assert fr.start_time.isot == '2013-07-02T01:39:20.000000000'
+        assert fr.shape == (3000, 2, 4)
+        _same(fr.read(), data)
+        fr.seek(999)
+        _same(fr.read(1003), data[999:2002])
+    # truncated last frame
+    cut = raw[:2 * 20096 + 4096 + 16 * 333 + 7]
+    with bb.dada.open(io.BytesIO(cut), 'rs') as fr:
+        assert fr.shape[0] == 2333
+        _same(fr.read(), data[:2333])
