@@ -583,3 +583,79 @@ def dada_write_roundtrip():
     with bb.dada.open(io.BytesIO(cut), 'rs') as fr:
         assert fr.shape[0] == 2333
         _same(fr.read(), data[:2333])
+
+
+# ------------------------------------------------------------------ GSB
+GSB = os.path.join(os.path.dirname(sample_path('x')), 'gsb')
+
+
+def gsb_rawdump_read():
+    want = ostream.gsb_rawdump_read(
+        np.fromfile(os.path.join(GSB, 'sample_gsb_rawdump.dat'), np.uint8),
+        payload_nbytes=4096, nframe=10)
+    _same(want[:16384], OUT['gsb_rawdump_8192_data'])
+    with bb.gsb.open(os.path.join(GSB, 'sample_gsb_rawdump.timestamp'), 'rs',
+                     raw=os.path.join(GSB, 'sample_gsb_rawdump.dat'),
+                     sample_rate=1e8 / 3 / 2 ** 10, payload_nbytes=4096,
+                     squeeze=False, chunk_nbytes=3 * 4096) as fh:
+        assert fh.header0.mode == 'rawdump'
+        assert fh.samples_per_frame == 8192 and fh.bps == 4
+        assert fh.shape == (10 * 8192, 1), fh.shape
+        assert fh.start_time.isot == '2015-04-27T13:15:00.000000240'
+        _same(fh.read(), want)
+        fh.seek(8190)
+        _same(fh.read(9000), want[8190:17190])
+    with bb.gsb.open(os.path.join(GSB, 'sample_gsb_rawdump.timestamp'), 'rs',
+                     raw=os.path.join(GSB, 'sample_gsb_rawdump.dat')) as fh:
+        assert fh.samples_per_frame == 2 ** 23
+        assert fh.payload_nbytes == 2 ** 22
+        assert abs(fh.sample_rate - 1e8 / 3) < 1e-6
+    with bb.gsb.open(os.path.join(GSB, 'sample_gsb_rawdump.timestamp'),
+                     'rt') as ft:
+        h = ft.read_timestamp()
+        assert h['gps'] == '2015 04 27 18 45 00 0.000000240'
+        h2 = bb.gsb.GSBHeader.fromvalues(mode='rawdump', time=h.time)
+        assert h2 == h
+
+
+def gsb_phased_read_write():
+    frames = OUT['gsb_phased_8192_frames']            # (5, 16, 2, 512)
+    want = frames.reshape(-1, 2, 512)
+    raw = [[os.path.join(GSB, 'sample_gsb_phased.Pol-%s%d.dat' % (p, k))
+            for k in (1, 2)] for p in 'LR']
+    ts = os.path.join(GSB, 'sample_gsb_phased.timestamp')
+    with bb.gsb.open(ts, 'rs', raw=raw, sample_rate=1e8 / 3 / 2 ** 19,
+                     payload_nbytes=8192, chunk_nbytes=2 * 4 * 8192) as fh:
+        assert fh.header0.mode == 'phased'
+        assert fh.sample_shape == (2, 512)
+        assert fh.sample_shape.nthread == 2
+        assert fh.samples_per_frame == 16 and fh.complex_data
+        assert fh.shape == (80, 2, 512)
+        assert fh.header0['seq_nr'] == 9995
+        assert fh.start_time.isot == '2013-07-27T21:23:55.324108800'
+        data = fh.read()
+        _same(data, want)
+        fh.seek(15)
+        _same(fh.read(33), want[15:48])
+        header0 = fh.header0
+    with bb.gsb.open(ts, 'rs', raw=raw[1], payload_nbytes=8192,
+                     sample_rate=1e8 / 3 / 2 ** 19, squeeze=False) as fh:
+        assert fh.shape == (80, 1, 512)
+        _same(fh.read()[:, 0], want[:, 1])
+    # write it back: raw files and timestamps identical to the sample's
+    bufs = [[io.BytesIO(), io.BytesIO()], [io.BytesIO(), io.BytesIO()]]
+    bts = io.StringIO()
+    fw = bb.gsb.open(bts, 'ws', raw=bufs, header0=header0,
+                     sample_rate=1e8 / 3 / 2 ** 19, payload_nbytes=8192)
+    fw.write(data[:40])
+    fw.write(data[40:])
+    for group, names in zip(bufs, raw):
+        for b, name in zip(group, names):
+            _same(np.frombuffer(b.getvalue(), np.uint8),
+                  np.fromfile(name, np.uint8)[:5 * 8192])
+    lines = bts.getvalue().split('\n')
+    with open(ts) as f:
+        orig = [ln.strip() for ln in f.read().split('\n')]
+    # GPS time, sequence number and memory block follow from the index
+    for got, ref in zip(lines[:5], orig[:5]):
+        assert got.split()[7:] == ref.split()[7:], (got, ref)
