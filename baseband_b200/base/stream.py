@@ -403,12 +403,20 @@ class StreamReaderBase(StreamBase):
     def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
         """Fill ``pinned`` (uint8 tensor) with the bytes of frames
         [frame0, frame0 + nframe)."""
-        self.fh_raw.seek(self._file_offset0 + frame0 * self._frame_nbytes)
+        offset = self._file_offset0 + frame0 * self._frame_nbytes
+        zero_copy = getattr(self.fh_raw, 'pinned_view', None)
+        if zero_copy is not None:
+            # frames already sit in pinned host memory: no staging copy
+            view = zero_copy(offset, pinned.numel())
+            if view is not None:
+                return view
+        self.fh_raw.seek(offset)
         view = pinned.numpy()
         got = self.fh_raw.readinto(memoryview(view))
         if got != view.size:
             raise EOFError('could not read {} frames at frame {}.'.format(
                 nframe, frame0))
+        return pinned
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
         """Decode ``nsample`` samples starting ``sample_start`` samples into
@@ -486,7 +494,8 @@ class StreamReaderBase(StreamBase):
             if st.done is not None:
                 st.done.synchronize()        # pinned buffer free again
             pin, raw = st.buffers(nbytes, 0, dev, False)
-            self._read_raw(f0, nf, pin, s0, ns)
+            got = self._read_raw(f0, nf, pin, s0, ns)
+            pin = pin if got is None else got
             with ss.use(0):
                 ss.wait(0, 1)                # raw[k%2] no longer being read
                 raw.copy_(pin, non_blocking=True)
@@ -541,7 +550,8 @@ class StreamReaderBase(StreamBase):
                 if st.done is not None:
                     st.done.synchronize()
                 pin, raw = st.buffers(nbytes, ns * fps, dev, True)
-                self._read_raw(f0, nf, pin, s0, ns)
+                got = self._read_raw(f0, nf, pin, s0, ns)
+                pin = pin if got is None else got
                 with ss.use(0):
                     raw.copy_(pin, non_blocking=True)
                 with ss.use(1):
@@ -704,6 +714,12 @@ class StreamWriterBase(StreamBase):
         raise NotImplementedError
 
     def _write_raw(self, frames):
+        reserve = getattr(self.fh_raw, 'reserve', None)
+        if reserve is not None:
+            # sink is pinned host memory: let the D2H copy land in it
+            reserve(frames.numel()).copy_(frames.view(-1), non_blocking=True)
+            _device.current_stream_synchronize(frames.device)
+            return
         host = _device.pinned_empty(frames.shape, torch.uint8)
         host.copy_(frames, non_blocking=True)
         _device.current_stream_synchronize(frames.device)

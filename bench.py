@@ -95,7 +95,7 @@ def _cpu_worker(args):
     return _cpu_round_trip(*args)
 
 
-def cpu_baseline(nset=480):
+def cpu_baseline(nset=960):
     nsamp, dt = _cpu_round_trip(nset, 1)
     return {'value': nsamp / dt / 1e9, 'unit': UNIT, 'cores': 1,
             'kind': 'port',
@@ -312,34 +312,40 @@ NCU_TRAFFIC_BYTES_PER_SAMPLE = 4.303
 
 
 def measure_e2e(args, dev, rank, world, lv, slot):
-    """Host pinned frames -> H2D -> scan + decode -> D2H decoded (what
-    ``read()`` returns) -> encode round trip -> D2H packed payloads."""
+    """End to end through the public API with HOST buffers: pinned host
+    frames -> ``vdif.open(..., 'rs', device=dev).read()`` (H2D of the packed
+    frames, header scan, decode) -> D2H of the decoded samples (what a numpy
+    user of ``read()`` receives) -> ``vdif.open(..., 'ws').write(data)``
+    (encode_2bit round trip, D2H of the re-packed frames into a pinned
+    host sink).  Every byte crosses PCIe inside the timed region."""
     import torch
     import torch.distributed as dist
-    from baseband_b200 import kernels, synthetic
+    import baseband_b200 as bb
+    from baseband_b200 import synthetic
+    from baseband_b200.base.memory import HostBuffer
     nset = int(args.e2e_mib * 2**20) // SET_BYTES
-    nframe = nset * NTHREAD
-    host_raw = torch.from_numpy(synthetic.vdif_stream(
-        nset, NTHREAD, PAYLOAD, seed=7 + rank)).pin_memory()
+    src = HostBuffer(synthetic.vdif_stream(
+        nset, NTHREAD, PAYLOAD, seed=7 + rank,
+        thread_order=np.arange(NTHREAD)))
+    sink = HostBuffer(src.size)
     host_out = torch.empty((nset * SPF, NTHREAD), dtype=torch.float32,
                            pin_memory=True)
-    host_back = torch.empty_like(host_raw).pin_memory()
-    raw = torch.empty_like(host_raw, device=dev)
-    out = torch.empty((nset * SPF, NTHREAD, 1), dtype=torch.float32,
-                      device=dev)
-    back = torch.zeros_like(raw)
+    reader = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+                          chunk_nbytes=32 << 20)
+    side = torch.cuda.Stream(dev)
 
     def step():
-        raw.copy_(host_raw, non_blocking=True)
-        _, uo, bad = kernels.vdif_scan(raw, nframe, FRAME, 32, NTHREAD, slot,
-                                       NTHREAD)
-        kernels.decode_bitfield(raw, uo, nset, NTHREAD, PAYLOAD, 2, 1, False,
-                                kernels.CODEC_LEVELS, lv, out=out)
-        host_out.copy_(out.view(nset * SPF, NTHREAD), non_blocking=True)
-        kernels.encode_bitfield(out, back, uo, nset, NTHREAD, PAYLOAD, 2, 1,
-                                kernels.QUANT_OFFSET_BINARY)
-        host_back.copy_(back, non_blocking=True)
-        torch.cuda.synchronize()
+        reader.seek(0)
+        data = reader.read()                      # device tensor
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):             # result back to the host
+            host_out.copy_(data, non_blocking=True)
+        sink.seek(0)
+        writer = bb.vdif.open(sink, 'ws', header0=reader.header0,
+                              nthread=NTHREAD, sample_rate=64e6, device=dev)
+        writer.write(data)                        # encode + D2H of frames
+        writer._flush(final=False)
+        torch.cuda.synchronize(dev)
 
     for _ in range(2):
         step()
@@ -350,17 +356,17 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    ok = bool(torch.equal(host_back.view(nframe, FRAME)[:, 32:],
-                          host_raw.view(nframe, FRAME)[:, 32:]))
+    ok = bool(np.array_equal(sink.getvalue(), src.getvalue()))
     if world > 1:
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     return {'value': nset * SET_SAMPLES * world * steps / dt / 1e9,
-            'unit': UNIT, 'h2d_bytes_per_step': int(host_raw.numel()),
-            'd2h_bytes_per_step': int(host_out.numel() * 4
-                                      + host_back.numel()),
+            'unit': UNIT, 'h2d_bytes_per_step': int(src.size),
+            'd2h_bytes_per_step': int(host_out.numel() * 4 + src.size),
             'steps': steps, 'round_trip_exact': ok,
+            'api': "vdif.open(HostBuffer,'rs',device=).read() -> D2H -> "
+                   "vdif.open(HostBuffer,'ws').write()",
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
                     'float32 array returned to the host is 16x the packed '
                     'input'.format(args.e2e_mib)}

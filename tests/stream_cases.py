@@ -659,3 +659,31 @@ def gsb_phased_read_write():
     # GPS time, sequence number and memory block follow from the index
     for got, ref in zip(lines[:5], orig[:5]):
         assert got.split()[7:] == ref.split()[7:], (got, ref)
+
+
+def vdif_host_buffer(dev):
+    """Pinned-host source and sink (zero-copy staging)."""
+    from baseband_b200.base.memory import HostBuffer
+    raw = synthetic.vdif_stream(6, 16, 8000, seed=12, edv=0)
+    want = ostream.vdif_read(raw)[:, :, 0]
+    src = HostBuffer(raw)
+    with bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+                      chunk_nbytes=2 * 16 * 8032) as fh:
+        data = fh.read()
+        _same(data.cpu().numpy(), want)
+        header0 = fh.header0
+    with bb.vdif.open(HostBuffer(raw), 'rs', sample_rate=64e6) as fh:
+        fh.seek(5)
+        _same(fh.read(100000), want[5:100005])
+    sink = HostBuffer(raw.size)
+    fw = bb.vdif.open(sink, 'ws', header0=header0, nthread=16,
+                      sample_rate=64e6, device=dev)
+    fw.write(data)                       # device tensor in, no H2D of floats
+    fw._flush(final=False)
+    got = sink.getvalue().reshape(-1, 8032)
+    ref = raw.reshape(-1, 8032)
+    order = np.argsort(
+        (ref[:, 12:16].view('<u4')[:, 0] >> 16 & 0x3ff).reshape(6, 16), 1)
+    ref_sorted = ref.reshape(6, 16, 8032)[np.arange(6)[:, None], order]
+    _same(got.reshape(6, 16, 8032)[:, :, 32:], ref_sorted[:, :, 32:])
+    _same(got.reshape(6, 16, 8032)[:, :, :8], ref_sorted[:, :, :8])
