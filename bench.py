@@ -26,7 +26,6 @@ itself cannot be imported on the box) on all host cores, same metric/config.
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -145,47 +144,62 @@ def run_reference(args):
 
 # --------------------------------------------------------------- clocks
 class ClockSampler:
-    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,'
-             'clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,'
-             'clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
+    """SM clock + throttle reasons sampled every ~5 ms through NVML in a
+    background thread while the timed region runs."""
+    BAD = {'hw_slowdown': 0x8, 'hw_thermal_slowdown': 0x40,
+           'sw_thermal_slowdown': 0x20, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ['nvidia-smi', '-i', str(self.index),
-                 '--query-gpu=' + self.QUERY, '--format=csv,noheader,nounits',
-                 '-lms', '50'], stdout=subprocess.PIPE, text=True)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            # honour CUDA_VISIBLE_DEVICES when mapping the torch index
+            visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+            index = self.index
+            if visible:
+                ids = [v for v in visible.split(',') if v.strip() != '']
+                if index < len(ids) and ids[index].strip().isdigit():
+                    index = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(
+                self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
             return
-        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread = threading.Thread(target=self._run, daemon=True)
         self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([v.strip() for v in line.split(',')])
+    def _run(self):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.handle,
+                                                         nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                for name, bit in self.BAD.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        self.proc.terminate()
+        if self.thread is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [],
+                    'samples': 0}
+        self._stop.set()
         self.thread.join(timeout=2)
-        sm = sorted(int(r[1]) for r in self.rows if len(r) > 2
-                    and r[1].isdigit())
-        mx = [int(r[2]) for r in self.rows if len(r) > 2 and r[2].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
-                 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 8
-                          for n, v in zip(names, r[4:8]) if v == 'Active'})
+        sm = sorted(self.sm)
         return {'sm_mhz': sm[len(sm) // 2] if sm else None,
-                'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
                 'samples': len(sm)}
 
 
@@ -357,6 +371,19 @@ def measure_e2e(args, dev, rank, world, lv, slot):
         step()
     dt = time.perf_counter() - t0
     ok = bool(np.array_equal(sink.getvalue(), src.getvalue()))
+
+    # Device-output option: same ingest, decoded samples stay in HBM for a
+    # consumer on the GPU; only a spot value is read back.
+    def step_dev():
+        reader.seek(0)
+        data = reader.read()
+        return float(data[-1, -1].item())
+
+    step_dev()
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        step_dev()
+    dt_dev = time.perf_counter() - t1
     if world > 1:
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -365,6 +392,8 @@ def measure_e2e(args, dev, rank, world, lv, slot):
             'unit': UNIT, 'h2d_bytes_per_step': int(src.size),
             'd2h_bytes_per_step': int(host_out.numel() * 4 + src.size),
             'steps': steps, 'round_trip_exact': ok,
+            'device_output_gsamples_s': nset * SET_SAMPLES * steps / dt_dev
+            / 1e9,
             'api': "vdif.open(HostBuffer,'rs',device=).read() -> D2H -> "
                    "vdif.open(HostBuffer,'ws').write()",
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
