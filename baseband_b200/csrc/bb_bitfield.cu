@@ -18,7 +18,8 @@ template <int BPS, int MODE>
 struct Unroll {
     static constexpr int kF4PerItem =
         MODE == MODE_ROWGROUP4 ? 32 / BPS
-        : MODE == MODE_ROWGROUP2 ? 16 / BPS : 1;
+        : MODE == MODE_ROWGROUP2 ? 16 / BPS
+        : MODE == MODE_WORDRUN ? 8 / BPS : 1;
     static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
 };
 
@@ -41,6 +42,36 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         __syncthreads();
     }
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+    if (MODE == MODE_WORDRUN) {
+        // kBlock and nitems are multiples of 32, so `live` is warp uniform.
+        constexpr int F = 8 / BPS;
+        constexpr int B = U < 4 ? U : 4;          // chunks loaded up front
+        const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            uint32_t w[B];
+            bool ok[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                ok[b] = item < p.nitems && wr_load(p, item >> 5, lane, w[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                if (item >= p.nitems) break;
+                const unsigned okmask = __ballot_sync(0xffffffffu, ok[b]);
+#pragma unroll
+                for (int j = 0; j < F; ++j) {
+                    const uint32_t src = wr_src_lane<BPS>(lane, j);
+                    const uint32_t ws = __shfl_sync(0xffffffffu, w[b], src);
+                    wr_emit<BPS, CODEC>(p, lut, item >> 5, lane, j, ws,
+                                        (okmask >> src) & 1u);
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kBlock;
@@ -91,6 +122,11 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         case MODE_RUN:
             k_decode_bitfield<BPS, CODEC, MODE_RUN>
                 <<<tile_grid(n, Unroll<BPS, MODE_RUN>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
+            break;
+        case MODE_WORDRUN:
+            k_decode_bitfield<BPS, CODEC, MODE_WORDRUN>
+                <<<tile_grid(n, Unroll<BPS, MODE_WORDRUN>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         default:

@@ -11,7 +11,15 @@
 //                float4 covering the G slots.  Lanes are ordered (group
 //                fastest, then word) so every warp store covers whole rows.
 //                This is the VDIF multi-thread single-channel path (C1, C2).
-//   RUN          nthread == 1, or E a power of two >= 4.  Output-centric: a
+//   WORDRUN      nthread == 1 (Mark 5B, DADA, GSB, single-thread VDIF).  The
+//                output is then one flat run of codes.  A warp takes 32
+//                consecutive payload words with ONE coalesced 128-byte load,
+//                and redistributes them with warp shuffles so that every
+//                store instruction again covers 512 contiguous bytes (lane L
+//                stores float4 L + 32 j of the warp's chunk).  Several chunks
+//                are loaded before the first is decoded (memory-level
+//                parallelism; the RUN mode it replaces was latency bound).
+//   RUN          nthread > 1 and E a power of two >= 4.  Output-centric: a
 //                thread owns one float4 of the output (4 consecutive codes of
 //                one unit), so a warp store is 512 contiguous bytes.
 //   SCALAR       anything else: one output element per thread.
@@ -58,6 +66,7 @@ struct DecGeom {
     uint32_t tpw;                   // times per word (ROWGROUP)
     uint32_t spf;                   // samples (times) per unit
     uint32_t nitems;
+    uint32_t nwords_total;          // WORDRUN: nset * nword
     uint32_t ngroup;                // nthread / G
     int32_t log2_nelem;             // RUN with nthread > 1
     uint32_t complex_fill;
@@ -198,6 +207,52 @@ BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
         uint32_t j = (pcode % CPW) >> 1;       // pair index, even
         F2 a = decode_pair<BPS, CODEC>(w, j, lut);
         F2 b = decode_pair<BPS, CODEC>(w, j + 1, lut);
+        v = F4{a.x, a.y, b.x, b.y};
+    } else {
+        const float fill_im = p.complex_fill ? 0.f : p.fill;
+        v = F4{p.fill, fill_im, p.fill, fill_im};
+    }
+    *reinterpret_cast<F4 *>(p.out + gidx) = v;
+}
+
+// WORDRUN: a warp owns chunk = 32 consecutive words of the launch (nthread
+// == 1, so word idx of the launch sits at float offset idx * CPW).  Phase 1:
+// lane loads word chunk*32 + lane.  Phase 2 (j = 0 .. F-1, F = float4 per
+// word): lane stores float4 q = lane + 32 j of the chunk, decoded from the word
+// of lane wr_src_lane(lane, j), which the caller fetches with a shuffle.
+template <int BPS>
+BB_HD uint32_t wr_src_lane(uint32_t lane, int j) {
+    constexpr int F = 8 / BPS;            // float4 per 32-bit word
+    return (lane + 32u * j) / F;
+}
+
+BB_HD bool wr_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
+                   uint32_t &w) {
+    w = 0u;
+    const uint32_t idx = chunk * 32u + lane;
+    if (idx >= p.nwords_total) return false;
+    uint32_t unit, k;
+    p.div_nword.divmod(idx, unit, k);
+    const long long off = p.unit_offset[unit];
+    if (off < 0) return false;
+    w = load_u32(p.src + off + 4ull * k);
+    return true;
+}
+
+template <int BPS, int CODEC>
+BB_HD void wr_emit(const DecGeom &p, const float *lut, uint32_t chunk,
+                   uint32_t lane, int j, uint32_t w, bool valid) {
+    constexpr int F = 8 / BPS;
+    const uint32_t q = lane + 32u * j;                 // float4 in the chunk
+    if (chunk * 32u + q / F >= p.nwords_total) return;
+    const long long n = ((long long)chunk * (32 * F) + q) * 4;
+    const long long gidx = p.row_base * (long long)p.nelem + n;
+    if (gidx < 0 || gidx >= p.nsample * (long long)p.nelem) return;
+    F4 v;
+    if (valid) {
+        const uint32_t pr = 2u * (q % F);              // first pair index
+        F2 a = decode_pair<BPS, CODEC>(w, pr, lut);
+        F2 b = decode_pair<BPS, CODEC>(w, pr + 1, lut);
         v = F4{a.x, a.y, b.x, b.y};
     } else {
         const float fill_im = p.complex_fill ? 0.f : p.fill;

@@ -8,7 +8,8 @@
 
 namespace bb {
 
-enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3 };
+enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
+       MODE_WORDRUN = 4 };
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -46,8 +47,8 @@ inline bool plan_geometry(int64_t payload_nbytes, int bps, int nelem,
 inline int pick_mode(int nelem, int nthread, bool aligned_rows) {
     if (nthread > 1 && nelem == 1 && nthread % 4 == 0) return MODE_ROWGROUP4;
     if (nthread > 1 && nelem == 2 && nthread % 2 == 0) return MODE_ROWGROUP2;
-    if (aligned_rows && (nthread == 1
-                         || (nelem % 4 == 0 && ilog2_exact(nelem) >= 0)))
+    if (aligned_rows && nthread == 1) return MODE_WORDRUN;
+    if (aligned_rows && nelem % 4 == 0 && ilog2_exact(nelem) >= 0)
         return MODE_RUN;
     return MODE_SCALAR;
 }
@@ -82,10 +83,13 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup;
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
+    } else if (mode == MODE_WORDRUN) {
+        per_set = nword;                  // items are lanes = words
     } else {
         per_set = (uint64_t)spf * rowlen;
     }
-    const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull : 0x7fffffffull;
+    const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull
+        : mode == MODE_WORDRUN ? 0x0fffffffull : 0x7fffffffull;
     if (per_set > budget) {
         err = "one frame set is too large for a launch; split it along time";
         return false;
@@ -106,6 +110,9 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.tpw = cpw / nelem ? cpw / nelem : 1;
         g.spf = spf;
         g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
+        g.nwords_total = (uint32_t)((uint64_t)nword * (uint64_t)(s1 - s0));
+        if (mode == MODE_WORDRUN)         // whole warps: 32 lanes per chunk
+            g.nitems = (g.nwords_total + 31u) / 32u * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);
         g.complex_fill = complex_data ? 1 : 0;

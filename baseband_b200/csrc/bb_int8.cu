@@ -11,6 +11,13 @@ __global__ void __launch_bounds__(kI8Threads) k_int8_decode_t(const I8Geom p) {
     i8_dec_store(p, tile, blockIdx.x, threadIdx.x);
 }
 
+__global__ void __launch_bounds__(kF8Threads) k_int8_decode_t64(const I8Geom p) {
+    __shared__ __align__(16) uint32_t tile[kF8SmemWords];
+    f8_dec_load(p, tile, blockIdx.x, threadIdx.x);
+    __syncthreads();
+    f8_dec_store(p, tile, blockIdx.x, threadIdx.x);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kI8Threads) k_int8_encode_t(const I8Geom p) {
     __shared__ __align__(16) uint8_t tile[kI8SmemBytes];
@@ -20,7 +27,7 @@ __global__ void __launch_bounds__(kI8Threads) k_int8_encode_t(const I8Geom p) {
 }
 
 static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
-                     int item_nbytes, uint64_t &nblocks) {
+                     int item_nbytes, uint64_t &nblocks, bool fast = false) {
     if (item_nbytes != 1 && item_nbytes != 2)
         return set_error(BB_ERR_ARGUMENT, "item_nbytes must be 1 or 2");
     if (nunit < 0 || nrow < 1 || ncol < 1 || nrow > 0x7fffffff
@@ -30,8 +37,9 @@ static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
     g.nrow = (uint32_t)nrow;
     g.ncol = (uint32_t)ncol;
     g.ib = item_nbytes;
-    g.tiles_r = (uint32_t)((nrow + kI8Rows - 1) / kI8Rows);
-    uint32_t tc = kI8RowBytes / item_nbytes;
+    const int rows = fast ? kF8Rows : kI8Rows;
+    g.tiles_r = (uint32_t)((nrow + rows - 1) / rows);
+    uint32_t tc = (fast ? kF8Words * 4 : kI8RowBytes) / item_nbytes;
     g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
     nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
     if (nblocks > 0x7fffffffull)
@@ -54,7 +62,9 @@ extern "C" int bb_decode_int8_transposed(
         return set_error(BB_ERR_ALIGNMENT, "out must be 8-byte aligned");
     I8Geom g;
     uint64_t nblocks;
-    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks);
+    // Fast tile kernel: rows paired into 16-byte (complex) / 8-byte stores.
+    const bool fast = nrow % 2 == 0 && aligned(out, 16);
+    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks, fast);
     if (rc != BB_OK) return rc;
     if (nblocks == 0) return BB_OK;
     g.src = (const uint8_t *)src;
@@ -64,7 +74,12 @@ extern "C" int bb_decode_int8_transposed(
     g.out_col0 = (const long long *)out_col0;
     g.out = out;
     g.in = nullptr;
-    k_int8_decode_t<<<(unsigned)nblocks, kI8Threads, 0, as_stream(stream)>>>(g);
+    if (fast)
+        k_int8_decode_t64<<<(unsigned)nblocks, kF8Threads, 0,
+                            as_stream(stream)>>>(g);
+    else
+        k_int8_decode_t<<<(unsigned)nblocks, kI8Threads, 0,
+                          as_stream(stream)>>>(g);
     BB_CHECK_LAUNCH("bb_decode_int8_transposed launch");
     return BB_OK;
 }

@@ -150,4 +150,120 @@ BB_HD void i8_enc_store(const I8Geom &p, const uint8_t *smem, uint32_t block,
     }
 }
 
+// ------------------------------------------------------------------------
+// Fast decode path (even nrow, 16-byte aligned out): a CTA moves a tile of
+// 64 rows x 256 bytes.  Shared memory is addressed in 32-bit words with an
+// XOR swizzle instead of padding: word wl of row r lives at
+//     r * 64 + ((wl & 32) | ((wl ^ (r >> 1)) & 31))
+// so that (phase 1) a warp writing 32 consecutive words of one row and
+// (phase 2) a warp reading word wc of rows 2l and 2l+1 (l = lane) both hit 32
+// different banks.  In phase 2 a lane combines rows 2l and 2l+1: for complex
+// items one float4 = (re, im) of two neighbouring rows, so every warp store
+// instruction writes 512 contiguous bytes of one output column.  Tiles are
+// ordered row-tile fastest, so neighbouring CTAs complete whole output rows.
+constexpr int kF8Rows = 64;
+constexpr int kF8Words = 64;               // 256 bytes per tile row
+constexpr int kF8Threads = 256;
+constexpr int kF8SmemWords = kF8Rows * kF8Words;
+
+struct F8Tile { uint32_t unit, r0, w0; };  // w0: first 32-bit word in the row
+
+BB_HD F8Tile f8_tile(const I8Geom &p, uint32_t block) {
+    F8Tile t;
+    const uint32_t per_unit = p.tiles_r * p.tiles_c;
+    t.unit = block / per_unit;
+    const uint32_t rem = block - t.unit * per_unit;
+    const uint32_t tc = rem / p.tiles_r;
+    t.r0 = (rem - tc * p.tiles_r) * kF8Rows;
+    t.w0 = tc * kF8Words;
+    return t;
+}
+
+BB_HD uint32_t f8_swz(uint32_t r, uint32_t wl) {
+    return r * kF8Words + ((wl & 32u) | ((wl ^ (r >> 1)) & 31u));
+}
+
+// Does the tile hold any column of the unit's window?
+BB_HD bool f8_live(const I8Geom &p, const F8Tile &t, long long off) {
+    if (off < 0) return false;
+    const long long j0 = (long long)t.w0 * 4 / p.ib;
+    const long long j1 = j0 + kF8Words * 4 / p.ib;
+    return j0 < p.col_end[t.unit] && j1 > p.col_begin[t.unit];
+}
+
+BB_HD void f8_dec_load(const I8Geom &p, uint32_t *smem, uint32_t block,
+                       uint32_t tid) {
+    const F8Tile t = f8_tile(p, block);
+    const long long off = p.unit_offset[t.unit];
+    if (!f8_live(p, t, off)) return;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const size_t rowbytes = (size_t)p.ncol * p.ib;
+    const uint8_t *base = p.src + off;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(base) | rowbytes) & 3u)
+        == 0;
+#pragma unroll 4
+    for (uint32_t r = warp; r < (uint32_t)kF8Rows; r += kF8Threads / 32) {
+        if (t.r0 + r >= p.nrow) break;
+        const uint8_t *row = base + (size_t)(t.r0 + r) * rowbytes;
+#pragma unroll
+        for (uint32_t seg = 0; seg < 2; ++seg) {
+            const uint32_t wl = seg * 32u + lane;
+            const size_t b = ((size_t)t.w0 + wl) * 4;
+            uint32_t w = 0;
+            if (aligned && b + 4 <= rowbytes) {
+                w = *reinterpret_cast<const uint32_t *>(row + b);
+            } else {
+                for (int k = 0; k < 4; ++k)
+                    if (b + k < rowbytes) w |= (uint32_t)row[b + k] << (8 * k);
+            }
+            smem[f8_swz(r, wl)] = w;
+        }
+    }
+}
+
+BB_HD float f8_byte(uint32_t w, int k) {
+    return (float)(int8_t)(w >> (8 * k));
+}
+
+BB_HD void f8_dec_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
+                        uint32_t tid) {
+    const F8Tile t = f8_tile(p, block);
+    const long long off = p.unit_offset[t.unit];
+    if (!f8_live(p, t, off)) return;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t ra = 2u * lane;
+    if (t.r0 + ra >= p.nrow) return;                 // nrow is even
+    const long long cb = p.col_begin[t.unit], ce = p.col_end[t.unit];
+    const long long lim = ce < (long long)p.ncol ? ce : (long long)p.ncol;
+    const long long oc0 = p.out_col0[t.unit];
+    const size_t row = (size_t)t.r0 + ra;
+#pragma unroll 2
+    for (uint32_t wc = warp; wc < (uint32_t)kF8Words; wc += kF8Threads / 32) {
+        const uint32_t a = smem[f8_swz(ra, wc)];
+        const uint32_t b = smem[f8_swz(ra + 1, wc)];
+        if (p.ib == 2) {
+            const long long j = ((long long)t.w0 + wc) * 2;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long long jk = j + k;
+                if (jk < cb || jk >= lim) continue;
+                const size_t o = (size_t)(oc0 + jk - cb) * p.nrow + row;
+                *reinterpret_cast<F4 *>(p.out + 2 * o) = F4{
+                    f8_byte(a, 2 * k), f8_byte(a, 2 * k + 1),
+                    f8_byte(b, 2 * k), f8_byte(b, 2 * k + 1)};
+            }
+        } else {
+            const long long j = ((long long)t.w0 + wc) * 4;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long jk = j + k;
+                if (jk < cb || jk >= lim) continue;
+                const size_t o = (size_t)(oc0 + jk - cb) * p.nrow + row;
+                *reinterpret_cast<F2 *>(p.out + o) = F2{f8_byte(a, k),
+                                                        f8_byte(b, k)};
+            }
+        }
+    }
+}
+
 }  // namespace bb

@@ -22,13 +22,31 @@ static void run_decode(const std::vector<DecLaunch> &launches,
     alignas(16) float lut[Lut::kFloats];
     if (CODEC == CODEC_LEVELS)
         for (int i = 0; i < Lut::kFloats; ++i) lut[i] = Lut::value(levels, i);
-    for (const DecLaunch &l : launches)
+    for (const DecLaunch &l : launches) {
+        if (l.mode == MODE_WORDRUN) {
+            // warp-cooperative mode: emulate the shuffle with a 32-word array
+            constexpr int F = 8 / BPS;
+            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
+                uint32_t w[32];
+                bool ok[32];
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    ok[lane] = wr_load(l.g, chunk, lane, w[lane]);
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < F; ++j) {
+                        uint32_t src = wr_src_lane<BPS>(lane, j);
+                        wr_emit<BPS, CODEC>(l.g, lut, chunk, lane, j, w[src],
+                                            ok[src]);
+                    }
+            }
+            continue;
+        }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
             else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);
             else dec_scalar<BPS, CODEC>(l.g, lut, item);
         }
+    }
 }
 
 template <typename T, int BPS, int QUANT>

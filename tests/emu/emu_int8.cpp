@@ -7,12 +7,13 @@
 using namespace bb;
 
 static bool geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol, int ib,
-                 uint64_t &nblocks) {
+                 uint64_t &nblocks, bool fast = false) {
     if (ib != 1 && ib != 2) return false;
     g.nunit = (uint32_t)nunit; g.nrow = (uint32_t)nrow; g.ncol = (uint32_t)ncol;
     g.ib = ib;
-    g.tiles_r = (uint32_t)((nrow + kI8Rows - 1) / kI8Rows);
-    uint32_t tc = kI8RowBytes / ib;
+    const int rows = fast ? kF8Rows : kI8Rows;
+    g.tiles_r = (uint32_t)((nrow + rows - 1) / rows);
+    uint32_t tc = (fast ? kF8Words * 4 : kI8RowBytes) / ib;
     g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
     nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
     return true;
@@ -27,13 +28,26 @@ int bb_decode_int8_transposed(const void *src, const int64_t *unit_offset,
                               float *out, void *stream) {
     I8Geom g;
     uint64_t nblocks;
-    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks)) return BB_ERR_ARGUMENT;
+    const bool fast = nrow % 2 == 0
+        && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks, fast))
+        return BB_ERR_ARGUMENT;
     g.src = (const uint8_t *)src;
     g.unit_offset = (const long long *)unit_offset;
     g.col_begin = (const long long *)col_begin;
     g.col_end = (const long long *)col_end;
     g.out_col0 = (const long long *)out_col0;
     g.out = out; g.in = nullptr;
+    if (fast) {
+        std::vector<uint32_t> tile64(kF8SmemWords);
+        for (uint64_t b = 0; b < nblocks; ++b) {
+            for (uint32_t t = 0; t < kF8Threads; ++t)
+                f8_dec_load(g, tile64.data(), (uint32_t)b, t);
+            for (uint32_t t = 0; t < kF8Threads; ++t)
+                f8_dec_store(g, tile64.data(), (uint32_t)b, t);
+        }
+        return 0;
+    }
     alignas(16) uint8_t tile[kI8SmemBytes];
     for (uint64_t b = 0; b < nblocks; ++b) {
         for (uint32_t t = 0; t < kI8Threads; ++t) i8_dec_load(g, tile, (uint32_t)b, t);
