@@ -139,6 +139,7 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
     if (nset == 0) return true;
     const int64_t rowlen = (int64_t)nthread * nelem;
     int mode = pick_mode(nelem, nthread, true);
+    if (mode == MODE_WORDRUN) mode = MODE_RUN;   // encode: vectorised words
     uint64_t per_set;
     uint32_t ngroup = 1;
     if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {

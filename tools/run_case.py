@@ -1,0 +1,61 @@
+"""Run one kernel case a few times (for ncu captures).
+usage: python tools/run_case.py {guppi|mark5b|mark4enc|vdif48|c2} [gib]"""
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from baseband_b200 import kernels, levels  # noqa: E402
+
+DEV = 'cuda:0'
+case = sys.argv[1]
+gib = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
+reps = 3
+if case == 'guppi':
+    nchan, npol, spf, ov = 512, 2, 65536, 512
+    fbytes = nchan * spf * npol * 2
+    nfr = max(1, int(gib * 2**30) // fbytes)
+    raw = torch.randint(0, 256, (nfr * fbytes,), dtype=torch.uint8, device=DEV)
+    off = torch.arange(nfr, dtype=torch.int64, device=DEV) * fbytes
+    cb = torch.full((nfr,), ov * npol, dtype=torch.int64, device=DEV)
+    cb[0] = 0
+    ce = torch.full((nfr,), spf * npol, dtype=torch.int64, device=DEV)
+    oc0 = torch.cumsum(ce - cb, 0) - (ce - cb)
+    ncols = int((ce - cb).sum().item())
+    out = torch.empty((ncols * nchan * 2,), dtype=torch.float32, device=DEV)
+    for _ in range(reps):
+        kernels.decode_int8_transposed(raw, off, nfr, nchan, spf * npol, 2,
+                                       cb, ce, oc0, out)
+elif case in ('mark5b', 'c2', 'vdif48'):
+    bps, nthread, nelem, payload, hdr = {
+        'mark5b': (2, 1, 16, 10000, 16), 'c2': (2, 16, 1, 8000, 32),
+        'vdif48': (2, 4, 8, 8000, 32)}[case]
+    frame = payload + hdr
+    nset = int(gib * 2**30) // frame // nthread
+    nunit = nset * nthread
+    raw = torch.randint(0, 256, (nunit * frame,), dtype=torch.uint8,
+                        device=DEV)
+    uo = torch.arange(nunit, dtype=torch.int64, device=DEV) * frame + hdr
+    lv = levels.mark5b(2) if case == 'mark5b' else levels.offset_binary(2)
+    out = None
+    for _ in range(reps):
+        out = kernels.decode_bitfield(raw, uo, nset, nthread, payload, bps,
+                                      nelem, False, kernels.CODEC_LEVELS, lv,
+                                      out=out)
+    back = torch.zeros_like(raw)
+    for _ in range(reps):
+        kernels.encode_bitfield(out, back, uo, nset, nthread, payload, bps,
+                                nelem, kernels.QUANT_MARK5B if case == 'mark5b'
+                                else kernels.QUANT_OFFSET_BINARY)
+elif case == 'mark4enc':
+    nframe = int(gib * 2**30) // 160000
+    raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,
+                        device=DEV)
+    off = torch.arange(nframe, dtype=torch.int64, device=DEV) * 160000 + 1280
+    out = kernels.mark4_decode(raw, off, nframe, 8, 4, False,
+                               levels.sign_magnitude())
+    back = raw.clone()
+    for _ in range(reps):
+        kernels.mark4_encode(out, back, off, nframe, 8, 4, False)
+torch.cuda.synchronize()
+print('done', case)
