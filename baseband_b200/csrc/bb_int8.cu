@@ -1,4 +1,5 @@
 // int8 transposed decode/encode kernels and C entry points (sm_100a).
+#include <stdlib.h>
 #include "bb_runtime.cuh"
 #include "bb_int8.cuh"
 
@@ -41,6 +42,10 @@ static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
     g.tiles_r = (uint32_t)((nrow + rows - 1) / rows);
     uint32_t tc = (fast ? kF8Words * 4 : kI8RowBytes) / item_nbytes;
     g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
+    g.group = 16;
+    if (const char *e = getenv("BB_I8_GROUP")) g.group = (uint32_t)atoi(e);
+    if (g.group < 1) g.group = 1;
+    if (g.group > g.tiles_c) g.group = g.tiles_c;
     nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
     if (nblocks > 0x7fffffffull)
         return set_error(BB_ERR_ARGUMENT, "too many tiles for one call");

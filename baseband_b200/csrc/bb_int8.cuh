@@ -33,6 +33,7 @@ struct I8Geom {
     const void *in;                  // encode input (float or double)
     uint32_t nunit, nrow, ncol, ib;  // ib = item bytes (1 or 2)
     uint32_t tiles_r, tiles_c;       // tiles per unit
+    uint32_t group;                  // fast path: column tiles per group
 };
 
 struct I8Tile { uint32_t unit, r0, j0; };
@@ -168,14 +169,24 @@ constexpr int kF8SmemWords = kF8Rows * kF8Words;
 
 struct F8Tile { uint32_t unit, r0, w0; };  // w0: first 32-bit word in the row
 
+// Tile order within a unit: groups of `group` column tiles x all row tiles,
+// column tile fastest inside a group.  CTAs that run at the same time then
+// read `group` * 256 contiguous bytes of every row (spread over the DRAM
+// channels, no power-of-two row-stride camping) and together complete whole
+// output rows.
 BB_HD F8Tile f8_tile(const I8Geom &p, uint32_t block) {
     F8Tile t;
     const uint32_t per_unit = p.tiles_r * p.tiles_c;
     t.unit = block / per_unit;
     const uint32_t rem = block - t.unit * per_unit;
-    const uint32_t tc = rem / p.tiles_r;
-    t.r0 = (rem - tc * p.tiles_r) * kF8Rows;
-    t.w0 = tc * kF8Words;
+    const uint32_t per_group = p.group * p.tiles_r;
+    const uint32_t g = rem / per_group;
+    const uint32_t in = rem - g * per_group;
+    const uint32_t left = p.tiles_c - g * p.group;
+    const uint32_t width = left < p.group ? left : p.group;
+    const uint32_t tr = in / width;
+    t.r0 = tr * kF8Rows;
+    t.w0 = (g * p.group + (in - tr * width)) * kF8Words;
     return t;
 }
 
@@ -201,22 +212,46 @@ BB_HD void f8_dec_load(const I8Geom &p, uint32_t *smem, uint32_t block,
     const uint8_t *base = p.src + off;
     const bool aligned = ((reinterpret_cast<uintptr_t>(base) | rowbytes) & 3u)
         == 0;
-#pragma unroll 4
-    for (uint32_t r = warp; r < (uint32_t)kF8Rows; r += kF8Threads / 32) {
+    constexpr int kIter = kF8Rows / (kF8Threads / 32);       // 8
+    if (aligned && ((size_t)t.w0 + kF8Words) * 4 <= rowbytes
+        && t.r0 + kF8Rows <= p.nrow) {
+        // Interior tile (CTA-uniform test): 16 unconditional loads per thread
+        // are issued back to back before the first shared-memory store, so
+        // 2 KiB per warp are in flight; the load phase is latency bound.
+        uint32_t w[kIter][2];
+        const uint8_t *col = base + (size_t)t.r0 * rowbytes
+            + ((size_t)t.w0 + lane) * 4;
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const uint8_t *q = col + (size_t)(warp + i * (kF8Threads / 32))
+                * rowbytes;
+            w[i][0] = *reinterpret_cast<const uint32_t *>(q);
+            w[i][1] = *reinterpret_cast<const uint32_t *>(q + 128);
+        }
+#pragma unroll
+        for (int i = 0; i < kIter; ++i) {
+            const uint32_t r = warp + i * (kF8Threads / 32);
+            smem[f8_swz(r, lane)] = w[i][0];
+            smem[f8_swz(r, 32u + lane)] = w[i][1];
+        }
+        return;
+    }
+    // Edge tile or unaligned rows: bounds-checked, bytewise if needed.
+#pragma unroll 1
+    for (int i = 0; i < kIter; ++i) {
+        const uint32_t r = warp + i * (kF8Threads / 32);
         if (t.r0 + r >= p.nrow) break;
         const uint8_t *row = base + (size_t)(t.r0 + r) * rowbytes;
-#pragma unroll
         for (uint32_t seg = 0; seg < 2; ++seg) {
-            const uint32_t wl = seg * 32u + lane;
-            const size_t b = ((size_t)t.w0 + wl) * 4;
-            uint32_t w = 0;
+            const size_t b = ((size_t)t.w0 + seg * 32u + lane) * 4;
+            uint32_t v = 0;
             if (aligned && b + 4 <= rowbytes) {
-                w = *reinterpret_cast<const uint32_t *>(row + b);
+                v = *reinterpret_cast<const uint32_t *>(row + b);
             } else {
                 for (int k = 0; k < 4; ++k)
-                    if (b + k < rowbytes) w |= (uint32_t)row[b + k] << (8 * k);
+                    if (b + k < rowbytes) v |= (uint32_t)row[b + k] << (8 * k);
             }
-            smem[f8_swz(r, wl)] = w;
+            smem[f8_swz(r, seg * 32u + lane)] = v;
         }
     }
 }

@@ -15,6 +15,8 @@ static bool geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol, int ib,
     g.tiles_r = (uint32_t)((nrow + rows - 1) / rows);
     uint32_t tc = (fast ? kF8Words * 4 : kI8RowBytes) / ib;
     g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
+    g.group = 16 < g.tiles_c ? 16 : g.tiles_c;
+    if (g.group < 1) g.group = 1;
     nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;
     return true;
 }
