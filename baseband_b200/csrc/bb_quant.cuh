@@ -23,9 +23,13 @@ template <typename T>
 struct QuantConsts {
     T clip_lo, clip_hi, two_sigma;   // encoding.py:59-60
     T t1, t2, t3;                    // exact thresholds for floor_divide
+    T x1, x2, x3;                    // the same thresholds referred to v
     T four_bit_scale;                // encoding.py:47  (2.95)
     T eight_bit_scale;               // encoding.py:49  (35.5)
 };
+
+inline float next_toward(float x, float to) { return nextafterf(x, to); }
+inline double next_toward(double x, double to) { return nextafter(x, to); }
 
 template <typename T>
 inline QuantConsts<T> make_quant_consts() {
@@ -39,8 +43,35 @@ inline QuantConsts<T> make_quant_consts() {
     c.t2 = (T)2 * s;                              // exact
     long double exact3 = 3.0L * (long double)s;   // exact in 64-bit mantissa
     T t3 = (T)exact3;
-    if ((long double)t3 < exact3) t3 = nextafter(t3, (T)INFINITY);
+    if ((long double)t3 < exact3) t3 = next_toward(t3, (T)INFINITY);
     c.t3 = t3;
+    // x_k = smallest v with fl(clip(v) + 2s) >= t_k.  Rounding is monotonic,
+    // so (a >= t_k) <=> (v >= x_k) for every v, including +-inf and values
+    // beyond the clip range (x_k lies strictly inside it); NaN compares false
+    // both ways.  This folds clip + add into the comparison constants.
+    const T tk[3] = {c.t1, c.t2, c.t3};
+    T xk[3];
+    for (int k = 0; k < 3; ++k) {
+        const T two = c.two_sigma, t = tk[k];
+        auto reaches = [&](T y) {
+            volatile T a = y + two;          // one IEEE rounding in type T
+            return a >= t;
+        };
+        // Bisection on the (monotonic) predicate between the clip bounds:
+        // !reaches(lo), reaches(hi); stop when hi is the successor of lo.
+        T lo = c.clip_lo, hi = c.clip_hi;
+        for (;;) {
+            T mid = lo + (hi - lo) / 2;
+            if (!(mid > lo && mid < hi)) {   // interval no longer splits
+                T nx = next_toward(lo, hi);
+                if (nx == hi) break;
+                mid = nx;
+            }
+            if (reaches(mid)) hi = mid; else lo = mid;
+        }
+        xk[k] = hi;
+    }
+    c.x1 = xk[0]; c.x2 = xk[1]; c.x3 = xk[2];
     c.four_bit_scale = (T)2.95;
     c.eight_bit_scale = (T)35.5;
     return c;
@@ -96,6 +127,14 @@ BB_HD uint32_t quant1_signbit(double v) {
 // encoding.py:77-102
 template <typename T>
 BB_HD uint32_t quant2_offset(T v, const QuantConsts<T> &c) {
+    // == floor_divide(clip(v, -1.5s, 1.5s) + 2s, s); see make_quant_consts.
+    return (uint32_t)(v >= c.x1) + (uint32_t)(v >= c.x2)
+        + (uint32_t)(v >= c.x3);
+}
+
+// The literal ufunc chain, kept to cross-check the folded thresholds.
+template <typename T>
+BB_HD uint32_t quant2_offset_chain(T v, const QuantConsts<T> &c) {
     T a = add_rn(clip_nan(v, c.clip_lo, c.clip_hi), c.two_sigma);
     return (uint32_t)(a >= c.t1) + (uint32_t)(a >= c.t2)
         + (uint32_t)(a >= c.t3);
@@ -135,7 +174,7 @@ BB_HD uint32_t quantise(T v, const QuantConsts<T> &c) {
     } else if (BPS == 2) {
         uint32_t q = quant2_offset(v, c);
         if (QUANT == QUANT_MARK5B)            // swap codes 1 <-> 2
-            q = ((q & 1u) << 1) | (q >> 1);
+            q = (0xD8u >> (2u * q)) & 3u;
         return q;
     } else if (BPS == 4) {
         return quant4_offset(v, c);

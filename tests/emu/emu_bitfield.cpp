@@ -123,3 +123,47 @@ int bb_encode_bitfield(const void *in, int32_t in_dtype, void *dst,
 }
 
 }  // extern "C"
+
+// Folded-threshold 2-bit quantiser == literal clip/add/floor_divide chain for
+// every value in a neighbourhood of each threshold (and specials).
+extern "C" long long emu_quant2_check(int is_double, int nulp) {
+    long long bad = 0;
+    if (is_double) {
+        const QuantConsts<double> c = make_quant_consts<double>();
+        const double marks[] = {c.x1, c.x2, c.x3, c.clip_lo, c.clip_hi, 0.0,
+                                -0.0, 1e300, -1e300, INFINITY, -INFINITY, NAN};
+        for (double m : marks) {
+            double up = m, dn = m;
+            for (int i = 0; i <= nulp; ++i) {
+                bad += quant2_offset(up, c) != quant2_offset_chain(up, c);
+                bad += quant2_offset(dn, c) != quant2_offset_chain(dn, c);
+                up = nextafter(up, INFINITY);
+                dn = nextafter(dn, -INFINITY);
+            }
+        }
+    } else {
+        const QuantConsts<float> c = make_quant_consts<float>();
+        // every 1021st float of either sign, and +-nulp ulp around each
+        // threshold and clip bound
+        for (uint32_t bits = 0; bits < 0x7f800000u; bits += 1021u) {
+            float v;
+            std::memcpy(&v, &bits, 4);
+            bad += quant2_offset(v, c) != quant2_offset_chain(v, c);
+            bad += quant2_offset(-v, c) != quant2_offset_chain(-v, c);
+        }
+        const float marks[] = {c.x1, c.x2, c.x3, c.clip_lo, c.clip_hi, 0.f};
+        for (float m : marks) {
+            float up = m, dn = m;
+            for (int i = 0; i <= nulp; ++i) {
+                bad += quant2_offset(up, c) != quant2_offset_chain(up, c);
+                bad += quant2_offset(dn, c) != quant2_offset_chain(dn, c);
+                up = nextafterf(up, INFINITY);
+                dn = nextafterf(dn, -INFINITY);
+            }
+        }
+        const float sp[] = {1e30f, -1e30f, INFINITY, -INFINITY, NAN};
+        for (float v : sp)
+            bad += quant2_offset(v, c) != quant2_offset_chain(v, c);
+    }
+    return bad;
+}

@@ -283,3 +283,14 @@ def test_int8_mkbf_sample(emu, sample_outputs):
                                        _ptr(out), None)
     assert rc == 0
     assert np.array_equal(out.view(np.complex64).reshape(want.shape), want)
+
+
+def test_quant2_folded_thresholds(emu):
+    """The 2-bit quantiser compares v with pre-folded thresholds; check it
+    against the literal clip/add/floor-divide chain: every 1021st float32 of
+    either sign plus +-200000 ulp around each threshold / clip bound, and
+    +-200000 ulp around each for float64."""
+    emu.emu_quant2_check.restype = ctypes.c_longlong
+    emu.emu_quant2_check.argtypes = [ctypes.c_int, ctypes.c_int]
+    assert emu.emu_quant2_check(0, 200000) == 0
+    assert emu.emu_quant2_check(1, 200000) == 0
