@@ -321,8 +321,9 @@ def run_b200(args):
 
 
 # dram bytes per decoded sample from the ncu --set full capture of the decode
-# kernel (profiles/r1_ncu_decode_c2.txt): (read + write) / samples.
-NCU_TRAFFIC_BYTES_PER_SAMPLE = 4.303
+# kernel (profiles/r1_decode_c2_summary.txt: 537.5 MB read + 8.499 GB written
+# for 4177 frame sets): (read + write) / samples.
+NCU_TRAFFIC_BYTES_PER_SAMPLE = 4.2256
 
 
 def measure_e2e(args, dev, rank, world, lv, slot):
