@@ -148,3 +148,34 @@ def current_stream_synchronize(dev):
 
 def is_device_tensor(t):
     return isinstance(t, torch.Tensor) and t.is_cuda
+
+
+def bind_host_to_device(index=None):
+    """Pin this process to the CPU cores that are local (same NUMA node) to
+    CUDA device ``index`` so that pinned staging buffers allocated afterwards
+    are first-touched next to the GPU's PCIe root.  With one process per GPU
+    this keeps every rank's H2D/D2H traffic on its own socket.  Returns the
+    CPU list used, or None if the topology could not be determined."""
+    try:
+        if index is None:
+            index = default_device().index or 0
+        props = torch.cuda.get_device_properties(index)
+        bus = '{:04x}:{:02x}:{:02x}.0'.format(props.pci_domain_id,
+                                              props.pci_bus_id,
+                                              props.pci_device_id)
+        with open('/sys/bus/pci/devices/{}/local_cpulist'.format(bus)) as fh:
+            text = fh.read().strip()
+        cpus = set()
+        for part in text.split(','):
+            if '-' in part:
+                a, b = part.split('-')
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        return None

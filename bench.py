@@ -216,6 +216,8 @@ def run_b200(args):
         raise SystemExit('--gpus must equal WORLD_SIZE under torchrun')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from baseband_b200 import device as bb_device
+    numa_cpus = bb_device.bind_host_to_device(local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
@@ -312,6 +314,8 @@ def run_b200(args):
             'traffic': NCU_TRAFFIC_BYTES_PER_SAMPLE * nset * SET_SAMPLES
             if NCU_TRAFFIC_BYTES_PER_SAMPLE else None},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        'host_binding': ('rank pinned to the {} CPUs local to its GPU'
+                         .format(len(numa_cpus)) if numa_cpus else 'none'),
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline()
@@ -403,6 +407,10 @@ def measure_e2e(args, dev, rank, world, lv, slot):
 
 
 def main():
+    # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; the
+    # contract is ONE JSON line on stdout.
+    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+        os.environ['NCCL_DEBUG'] = 'WARN'
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
