@@ -6,10 +6,12 @@ reads the header, anything else reads samples; an invalid frame yields
 """
 import numpy as np
 
+from .shape import ArrayLike
+
 __all__ = ['FrameBase']
 
 
-class FrameBase:
+class FrameBase(ArrayLike):
     _header_class = None
     _payload_class = None
     _fill_value = 0.
@@ -57,32 +59,12 @@ class FrameBase:
         payload = cls._payload_class.fromdata(data, header=header)
         return cls(header, payload, valid=valid, verify=verify)
 
-    @property
-    def sample_shape(self):
-        return self.payload.sample_shape
+    sample_shape = property(lambda self: self.payload.sample_shape)
+    dtype = property(lambda self: self.payload.dtype)
+    nbytes = property(lambda self: self.header.nbytes + self.payload.nbytes)
 
     def __len__(self):
         return len(self.payload)
-
-    @property
-    def shape(self):
-        return (len(self),) + tuple(self.sample_shape)
-
-    @property
-    def size(self):
-        return int(np.prod(self.shape))
-
-    @property
-    def ndim(self):
-        return len(self.shape)
-
-    @property
-    def dtype(self):
-        return self.payload.dtype
-
-    @property
-    def nbytes(self):
-        return self.header.nbytes + self.payload.nbytes
 
     @property
     def fill_value(self):
@@ -91,11 +73,6 @@ class FrameBase:
     @fill_value.setter
     def fill_value(self, fill_value):
         self._fill_value = fill_value
-
-    def __array__(self, dtype=None, copy=None):
-        if not copy and (dtype is None or dtype == self.dtype):
-            return self.data
-        return self.data.astype(dtype, copy=True)
 
     def __getitem__(self, item=()):
         if isinstance(item, str):

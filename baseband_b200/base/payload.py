@@ -15,10 +15,12 @@ from functools import reduce
 
 import numpy as np
 
+from .shape import ArrayLike
+
 __all__ = ['PayloadBase']
 
 
-class PayloadBase:
+class PayloadBase(ArrayLike):
     _nbytes = None                      # fixed payload size, if any
     _memmap = False
     _dtype_word = np.dtype('<u4')
@@ -115,29 +117,10 @@ class PayloadBase:
         return self
 
     # ---------------------------------------------------------- geometry
-    def __array__(self, dtype=None, copy=None):
-        if not copy and (dtype is None or dtype == self.dtype):
-            return self.data
-        return self.data.astype(dtype, copy=True)
-
-    @property
-    def nbytes(self):
-        return self.words.nbytes
+    nbytes = property(lambda self: self.words.nbytes)
 
     def __len__(self):
         return self.words.nbytes * 8 // self._bpfs
-
-    @property
-    def shape(self):
-        return (len(self),) + tuple(self.sample_shape)
-
-    @property
-    def size(self):
-        return len(self) * self._sample_size
-
-    @property
-    def ndim(self):
-        return 1 + len(self.sample_shape)
 
     @property
     def dtype(self):

@@ -1,0 +1,133 @@
+"""Parity at BASELINE-like sizes through size-independent properties:
+decode -> encode round trips are the identity on the packed bytes, chunked
+reads equal one-shot reads, invalid frames are exactly fill, and randomly
+chosen frames agree with the oracle."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+import baseband_b200 as bb
+from baseband_b200 import kernels, levels, synthetic
+from baseband_b200.base.memory import HostBuffer
+from oracle import codec, stream as ostream
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def test_c2_vdif_round_trip_256mib():
+    nthread, payload, frame = 16, 8000, 8032
+    nset = (256 << 20) // (nthread * frame)
+    raw = synthetic.vdif_stream_device(nset, nthread, payload, DEV, seed=99)
+    nframe = nset * nthread
+    slot = torch.arange(1024, dtype=torch.int32, device=DEV)
+    slot[nthread:] = -1
+    fields, uo, bad = kernels.vdif_scan(raw, nframe, frame, 32, nthread, slot,
+                                        nthread)
+    assert int(bad.item()) == 0
+    out = kernels.decode_bitfield(raw, uo, nset, nthread, payload, 2, 1,
+                                  False, kernels.CODEC_LEVELS,
+                                  levels.offset_binary(2))
+    back = torch.zeros_like(raw)
+    back.view(nframe, frame)[:, :32] = raw.view(nframe, frame)[:, :32]
+    kernels.encode_bitfield(out, back, uo, nset, nthread, payload, 2, 1,
+                            kernels.QUANT_OFFSET_BINARY)
+    assert torch.equal(back, raw)
+    # only the four levels occur, equally often within 1 %
+    vals, counts = torch.unique(out[:1 << 22], return_counts=True)
+    assert vals.numel() == 4
+    assert float(counts.max() - counts.min()) / float(counts.sum()) < 0.01
+    # randomly chosen thread-frames against the oracle
+    rng = np.random.default_rng(0)
+    host = raw.view(nframe, frame)
+    tid = fields[kernels.VDIF_THREAD_ID].cpu().numpy()
+    for i in rng.integers(0, nframe, 12):
+        words = host[i, 32:].cpu().numpy().view('<u4')
+        want = codec.vdif_payload_decode(words, 2, (1,), False)[:, 0]
+        s = i // nthread
+        got = out[s * 32000:(s + 1) * 32000, tid[i], 0].cpu().numpy()
+        assert np.array_equal(got.view('u4'), want.view('u4'))
+
+
+def test_c5_mark5b_invalid_frames_large():
+    nframe = 20000                                   # 200 MB
+    raw, valid = synthetic.mark5b_stream(nframe, invalid_fraction=0.01,
+                                         seed=5)
+    assert 100 < (~valid).sum() < 320
+    src = HostBuffer(raw)
+    with bb.mark5b.open(src, 'rs', nchan=16, sample_rate=16e6, kday=56000,
+                        fill_value=-999., device=DEV,
+                        chunk_nbytes=32 << 20) as fh:
+        data = fh.read()
+    per = data.view(nframe, 2500 * 16)
+    is_fill = (per == -999.).all(1).cpu().numpy()
+    assert np.array_equal(is_fill, ~valid)
+    assert not bool((per[torch.from_numpy(valid).to(DEV)] == -999.).any())
+    for i in np.random.default_rng(1).integers(0, nframe, 8):
+        want = ostream.mark5b_read(raw[i * 10016:(i + 1) * 10016], 16,
+                                   fill_value=-999.)
+        assert np.array_equal(data[i * 2500:(i + 1) * 2500].cpu().numpy(),
+                              want)
+    # header fields parsed on the GPU for the whole stream
+    d_raw = torch.from_numpy(raw).to(DEV)
+    fields, uo = kernels.mark5b_scan(d_raw, nframe)
+    f = fields.cpu().numpy()
+    assert np.array_equal(f[kernels.M5B_FRAME_NR],
+                          np.arange(nframe) % 6400)
+    assert np.array_equal(f[kernels.M5B_SECONDS],
+                          3600 + np.arange(nframe) // 6400)
+    assert np.array_equal(f[kernels.M5B_VALID].astype(bool), valid)
+    assert np.all(f[kernels.M5B_JDAY] == 123)
+
+
+def test_c3_mark4_round_trip_large():
+    nframe = 1200                                    # 192 MB
+    raw = torch.from_numpy(synthetic.mark4_stream(nframe, seed=8)).to(DEV)
+    off = torch.arange(nframe, dtype=torch.int64, device=DEV) * 160000 + 1280
+    out = kernels.mark4_decode(raw, off, nframe, 8, 4, False,
+                               levels.sign_magnitude(), fill_value=7.)
+    rows = out.view(nframe, 80000, 8)
+    assert bool((rows[:, :640] == 7.).all())
+    assert not bool((rows[:, 640:] == 7.).any())
+    back = raw.clone()
+    back.view(nframe, 160000)[:, 1280:] = 0
+    kernels.mark4_encode(out, back, off, nframe, 8, 4, False)
+    assert torch.equal(back, raw)
+    i = 777
+    want, _ = ostream.mark4_frame_decode(
+        raw.view(nframe, 160000)[i].cpu().numpy(), 64, fill_value=7.)
+    assert np.array_equal(rows[i].cpu().numpy(), want)
+
+
+def test_c4_guppi_overlap_large():
+    raw, truth = synthetic.guppi_stream(6, nchan=512, npol=2,
+                                        samples_per_frame=8192, overlap=512,
+                                        seed=3)              # 100 MB
+    cube = truth.astype(np.float32).transpose(1, 2, 0, 3)
+    want = (cube[..., 0] + 1j * cube[..., 1]).astype(np.complex64)
+    with bb.guppi.open(io.BytesIO(raw.tobytes()), 'rs', device=DEV,
+                       chunk_nbytes=40 << 20) as fh:
+        assert fh.shape == want.shape
+        data = fh.read()
+        assert torch.equal(data, torch.from_numpy(want).to(DEV))
+        fh.seek(7000)
+        part = fh.read(20000)
+        assert torch.equal(part, torch.from_numpy(want[7000:27000]).to(DEV))
+    with bb.guppi.open(io.BytesIO(raw.tobytes()), 'rs') as fh:
+        fh.seek(100)
+        assert np.array_equal(fh.read(9000), want[100:9100])
+
+
+def test_chunked_equals_one_shot_and_pickle():
+    import pickle
+    raw = synthetic.vdif_stream(40, 8, 5000, seed=1, invalid=[17])
+    a = bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=32e6,
+                     fill_value=3.).read()
+    fh = bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=32e6,
+                      fill_value=3., chunk_nbytes=3 * 8 * 5032)
+    b = fh.read()
+    assert np.array_equal(a, b)
+    state = fh.__getstate__()
+    assert state['_stages'] is None and state['_streams'] is None
