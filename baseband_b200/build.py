@@ -40,6 +40,7 @@ def _deps_mtime():
 
 def _compile(src, verbose, extra):
     obj = os.path.join(OBJ, src[:-3] + '.o')
+    extra = extra + os.environ.get('NVCC_EXTRA', '').split()
     cmd = [NVCC] + NVCC_FLAGS + extra + ['-c', os.path.join(CSRC, src),
                                          '-o', obj]
     if verbose:

@@ -72,14 +72,67 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
+    // Batches of B items: all loads of a batch are issued before the first
+    // item is decoded (memory-level parallelism).
+    constexpr int B = U < 4 ? U : 4;
+    if (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2) {
+        constexpr int G = MODE == MODE_ROWGROUP4 ? 4 : 2;
+#ifndef BB_ROW_BATCH
+#define BB_ROW_BATCH 2
+#endif
+        constexpr int RB = U < BB_ROW_BATCH ? U : BB_ROW_BATCH;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += RB) {
+            RowItem<G> it[RB];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].live = false;
+                if (item < p.nitems) rowgroup_fetch<BPS, G>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < RB; ++b)
+                rowgroup_emit<BPS, CODEC, G>(p, lut, it[b]);
+        }
+        return;
+    }
+    if (MODE == MODE_ROWRUN4 || MODE == MODE_ROWRUN2) {
+        constexpr int G = MODE == MODE_ROWRUN4 ? 4 : 2;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            RowRunItem<G> it[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].gidx = -1;
+                if (item < p.nitems) rowrun_fetch<BPS, G>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b)
+                rowrun_emit<BPS, CODEC, G>(p, lut, it[b]);
+        }
+        return;
+    }
+    if (MODE == MODE_RUN) {
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            RunItem it[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].gidx = -1;
+                if (item < p.nitems) run_fetch<BPS>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) run_emit<BPS, CODEC>(p, lut, it[b]);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kBlock;
         if (item >= p.nitems) break;
-        if (MODE == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(p, lut, item);
-        else if (MODE == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(p, lut, item);
-        else if (MODE == MODE_RUN) dec_run<BPS, CODEC>(p, lut, item);
-        else dec_scalar<BPS, CODEC>(p, lut, item);
+        dec_scalar<BPS, CODEC>(p, lut, item);
     }
 }
 
@@ -127,6 +180,16 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         case MODE_WORDRUN:
             k_decode_bitfield<BPS, CODEC, MODE_WORDRUN>
                 <<<tile_grid(n, Unroll<BPS, MODE_WORDRUN>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
+            break;
+        case MODE_ROWRUN4:
+            k_decode_bitfield<BPS, CODEC, MODE_ROWRUN4>
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWRUN4>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
+            break;
+        case MODE_ROWRUN2:
+            k_decode_bitfield<BPS, CODEC, MODE_ROWRUN2>
+                <<<tile_grid(n, Unroll<BPS, MODE_ROWRUN2>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         default:

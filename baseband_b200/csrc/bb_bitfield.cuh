@@ -107,32 +107,50 @@ BB_HD uint32_t load_u32(const uint8_t *p) {
 }
 
 // ROWGROUP: item = lw * ngroup + g, lw = word index over the launch's sets.
-template <int BPS, int CODEC, int G>
-BB_HD void dec_rowgroup(const DecGeom &p, const float *lut, uint32_t item) {
-    constexpr int E = 4 / G;
-    constexpr int CPW = 32 / BPS;          // codes per word
-    constexpr int TPW = CPW / E;           // times per word
-    uint32_t lw, g;
-    p.div_ngroup.divmod(item, lw, g);
-    uint32_t set, k;
-    p.div_nword.divmod(lw, set, k);
-    const long long row0 = p.row_base + (long long)lw * TPW;
-    if (row0 + TPW <= 0 || row0 >= p.nsample) return;
+// Split into a fetch (address arithmetic + global loads) and an emit (decode +
+// stores) so the kernel can issue the loads of several items before decoding
+// the first: these kernels are latency bound otherwise.
+template <int G>
+struct RowItem {
     uint32_t w[G];
-    bool all_ok = true;
-    long long off[G];
-    const long long *uo = p.unit_offset + (size_t)set * p.nthread + g * G;
+    uint32_t okmask;                // bit j: slot j valid
+    uint32_t g;
+    long long row0;
+    bool live;
+};
+
+template <int BPS, int G>
+BB_HD void rowgroup_fetch(const DecGeom &p, uint32_t item, RowItem<G> &it) {
+    constexpr int E = 4 / G;
+    constexpr int TPW = (32 / BPS) / E;
+    uint32_t lw, set, k;
+    p.div_ngroup.divmod(item, lw, it.g);
+    p.div_nword.divmod(lw, set, k);
+    it.row0 = p.row_base + (long long)lw * TPW;
+    it.live = !(it.row0 + TPW <= 0 || it.row0 >= p.nsample);
+    it.okmask = 0u;
+    if (!it.live) return;
+    const long long *uo = p.unit_offset + (size_t)set * p.nthread + it.g * G;
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-        off[j] = uo[j];
-        all_ok = all_ok && off[j] >= 0;
+        const long long off = uo[j];
+        it.w[j] = off >= 0 ? load_u32(p.src + off + 4ull * k) : 0u;
+        it.okmask |= (off >= 0 ? 1u : 0u) << j;
     }
-#pragma unroll
-    for (int j = 0; j < G; ++j)
-        w[j] = off[j] >= 0 ? load_u32(p.src + off[j] + 4ull * k) : 0u;
+}
+
+template <int BPS, int CODEC, int G>
+BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
+                         const RowItem<G> &it) {
+    constexpr int E = 4 / G;
+    constexpr int TPW = (32 / BPS) / E;
+    if (!it.live) return;
+    const uint32_t *w = it.w;
+    const long long row0 = it.row0;
     const size_t rowlen = (size_t)p.nthread * E;
-    float *dst = p.out + row0 * (long long)rowlen + g * 4;
-    if (all_ok && row0 >= 0 && row0 + TPW <= p.nsample) {
+    float *dst = p.out + row0 * (long long)rowlen + it.g * 4;
+    if (it.okmask == (1u << G) - 1u && row0 >= 0
+        && row0 + TPW <= p.nsample) {
         // Fast path: whole word inside the requested rows, every slot valid.
         if (E == 1) {
 #pragma unroll
@@ -159,35 +177,124 @@ BB_HD void dec_rowgroup(const DecGeom &p, const float *lut, uint32_t item) {
     }
     // Edge path: partial word at either end of the read, or invalid frames.
     const float fill_im = p.complex_fill ? 0.f : p.fill;
+    const bool ok0 = it.okmask & 1u, ok1 = (it.okmask >> (1 % G)) & 1u,
+        ok2 = (it.okmask >> (2 % G)) & 1u, ok3 = (it.okmask >> (3 % G)) & 1u;
 #pragma unroll 1
     for (int i = 0; i < TPW; ++i, dst += rowlen) {
         if (row0 + i < 0 || row0 + i >= p.nsample) continue;
         F4 v;
         if (E == 1) {
-            v.x = off[0] >= 0 ? decode_one<BPS, CODEC>(w[0], i, lut) : p.fill;
-            v.y = off[1 % G] >= 0 ? decode_one<BPS, CODEC>(w[1 % G], i, lut) : p.fill;
-            v.z = off[2 % G] >= 0 ? decode_one<BPS, CODEC>(w[2 % G], i, lut) : p.fill;
-            v.w = off[3 % G] >= 0 ? decode_one<BPS, CODEC>(w[3 % G], i, lut) : p.fill;
+            v.x = ok0 ? decode_one<BPS, CODEC>(w[0], i, lut) : p.fill;
+            v.y = ok1 ? decode_one<BPS, CODEC>(w[1 % G], i, lut) : p.fill;
+            v.z = ok2 ? decode_one<BPS, CODEC>(w[2 % G], i, lut) : p.fill;
+            v.w = ok3 ? decode_one<BPS, CODEC>(w[3 % G], i, lut) : p.fill;
         } else {
             F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
             F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
-            v.x = off[0] >= 0 ? a.x : p.fill;
-            v.y = off[0] >= 0 ? a.y : fill_im;
-            v.z = off[1 % G] >= 0 ? b.x : p.fill;
-            v.w = off[1 % G] >= 0 ? b.y : fill_im;
+            v.x = ok0 ? a.x : p.fill;
+            v.y = ok0 ? a.y : fill_im;
+            v.z = ok1 ? b.x : p.fill;
+            v.w = ok1 ? b.y : fill_im;
         }
         *reinterpret_cast<F4 *>(dst) = v;
     }
 }
 
-// RUN: item = float4 index within the launch's block of rows.
-template <int BPS, int CODEC>
-BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
+template <int BPS, int CODEC, int G>
+BB_HD void dec_rowgroup(const DecGeom &p, const float *lut, uint32_t item) {
+    RowItem<G> it;
+    rowgroup_fetch<BPS, G>(p, item, it);
+    rowgroup_emit<BPS, CODEC, G>(p, lut, it);
+}
+
+// ROWRUN<G>: nthread * E == 4 (4 real threads, or 2 complex ones), i.e. one
+// output row IS one float4.  ROWGROUP would make each lane write TPW rows =
+// 16-byte pieces 16*TPW bytes apart; here instead a lane owns ONE row and
+// gathers its G codes (pairs) from the G slots, so a warp store is 512
+// contiguous bytes.  Lanes that share a payload word hit the same L1 line.
+template <int G>
+struct RowRunItem {
+    uint32_t w[G];
+    uint32_t okmask, c0;            // first code of the row within the word
+    long long gidx;                 // output float index, < 0: nothing to do
+};
+
+template <int BPS, int G>
+BB_HD void rowrun_fetch(const DecGeom &p, uint32_t item, RowRunItem<G> &it) {
+    constexpr int E = 4 / G;
+    constexpr int CPW = 32 / BPS;
+    const long long row = p.row_base + item;    // row of the whole call
+    it.gidx = -1;
+    it.okmask = 0u;
+    if (row < 0 || row >= p.nsample) return;
+    it.gidx = row * 4;
+    uint32_t set, t;
+    p.div_spf.divmod(item, set, t);
+    const uint32_t code = t * E;
+    it.c0 = code % CPW;
+    const long long *uo = p.unit_offset + (size_t)set * G;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const long long off = uo[j];
+        it.w[j] = off >= 0 ? load_u32(p.src + off + 4ull * (code / CPW)) : 0u;
+        it.okmask |= (off >= 0 ? 1u : 0u) << j;
+    }
+}
+
+template <int BPS, int CODEC, int G>
+BB_HD void rowrun_emit(const DecGeom &p, const float *lut,
+                       const RowRunItem<G> &it) {
+    if (it.gidx < 0) return;
+    F4 v;
+    if (G == 4) {
+        v.x = (it.okmask & 1u) ? decode_one<BPS, CODEC>(it.w[0], it.c0, lut)
+                               : p.fill;
+        v.y = (it.okmask & 2u) ? decode_one<BPS, CODEC>(it.w[1 % G], it.c0, lut)
+                               : p.fill;
+        v.z = (it.okmask & 4u) ? decode_one<BPS, CODEC>(it.w[2 % G], it.c0, lut)
+                               : p.fill;
+        v.w = (it.okmask & 8u) ? decode_one<BPS, CODEC>(it.w[3 % G], it.c0, lut)
+                               : p.fill;
+    } else {
+        const float fill_im = p.complex_fill ? 0.f : p.fill;
+        F2 a = decode_pair<BPS, CODEC>(it.w[0], it.c0 >> 1, lut);
+        F2 b = decode_pair<BPS, CODEC>(it.w[1 % G], it.c0 >> 1, lut);
+        v.x = (it.okmask & 1u) ? a.x : p.fill;
+        v.y = (it.okmask & 1u) ? a.y : fill_im;
+        v.z = (it.okmask & 2u) ? b.x : p.fill;
+        v.w = (it.okmask & 2u) ? b.y : fill_im;
+    }
+    *reinterpret_cast<F4 *>(p.out + it.gidx) = v;
+}
+
+template <int BPS, int CODEC, int G>
+BB_HD void dec_rowrun(const DecGeom &p, const float *lut, uint32_t item) {
+    RowRunItem<G> it;
+    rowrun_fetch<BPS, G>(p, item, it);
+    rowrun_emit<BPS, CODEC, G>(p, lut, it);
+}
+
+// RUN: item = float4 index within the launch's block of rows; again split
+// into fetch and emit.
+struct RunItem {
+    uint32_t w, pair;               // word and first pair index within it
+    long long gidx;                 // output float index, < 0: nothing to do
+    bool valid;
+};
+
+template <int BPS>
+BB_HD void run_fetch(const DecGeom &p, uint32_t item, RunItem &it) {
     constexpr int CPW = 32 / BPS;
     const uint32_t n = item * 4u;              // element index in the launch
     const uint32_t rowlen = p.nthread * p.nelem;
-    long long gidx = p.row_base * (long long)rowlen + n;
-    if (gidx < 0 || gidx >= p.nsample * (long long)rowlen) return;
+    it.gidx = p.row_base * (long long)rowlen + n;
+    it.w = 0u;
+    it.pair = 0u;
+    it.valid = false;
+    if (it.gidx < 0 || it.gidx >= p.nsample * (long long)rowlen) {
+        it.gidx = -1;
+        return;
+    }
     uint32_t set, pcode, slot;
     if (p.nthread == 1) {
         p.div_unitlen.divmod(n, set, pcode);     // unitlen = spf * nelem
@@ -200,19 +307,34 @@ BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
         p.div_spf.divmod(row, set, t);
         pcode = (t << p.log2_nelem) + e;
     }
-    long long off = p.unit_offset[(size_t)set * p.nthread + slot];
-    F4 v;
+    const long long off = p.unit_offset[(size_t)set * p.nthread + slot];
     if (off >= 0) {
-        uint32_t w = load_u32(p.src + off + 4ull * (pcode / CPW));
-        uint32_t j = (pcode % CPW) >> 1;       // pair index, even
-        F2 a = decode_pair<BPS, CODEC>(w, j, lut);
-        F2 b = decode_pair<BPS, CODEC>(w, j + 1, lut);
+        it.valid = true;
+        it.w = load_u32(p.src + off + 4ull * (pcode / CPW));
+        it.pair = (pcode % CPW) >> 1;
+    }
+}
+
+template <int BPS, int CODEC>
+BB_HD void run_emit(const DecGeom &p, const float *lut, const RunItem &it) {
+    if (it.gidx < 0) return;
+    F4 v;
+    if (it.valid) {
+        F2 a = decode_pair<BPS, CODEC>(it.w, it.pair, lut);
+        F2 b = decode_pair<BPS, CODEC>(it.w, it.pair + 1, lut);
         v = F4{a.x, a.y, b.x, b.y};
     } else {
         const float fill_im = p.complex_fill ? 0.f : p.fill;
         v = F4{p.fill, fill_im, p.fill, fill_im};
     }
-    *reinterpret_cast<F4 *>(p.out + gidx) = v;
+    *reinterpret_cast<F4 *>(p.out + it.gidx) = v;
+}
+
+template <int BPS, int CODEC>
+BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
+    RunItem it;
+    run_fetch<BPS>(p, item, it);
+    run_emit<BPS, CODEC>(p, lut, it);
 }
 
 // WORDRUN: a warp owns chunk = 32 consecutive words of the launch (nthread

@@ -9,7 +9,7 @@
 namespace bb {
 
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
-       MODE_WORDRUN = 4 };
+       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6 };
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -44,7 +44,10 @@ inline bool plan_geometry(int64_t payload_nbytes, int bps, int nelem,
     return true;
 }
 
-inline int pick_mode(int nelem, int nthread, bool aligned_rows) {
+inline int pick_mode(int nelem, int nthread, bool aligned_rows,
+                     bool decode = false) {
+    if (decode && nthread == 4 && nelem == 1) return MODE_ROWRUN4;
+    if (decode && nthread == 2 && nelem == 2) return MODE_ROWRUN2;
     if (nthread > 1 && nelem == 1 && nthread % 4 == 0) return MODE_ROWGROUP4;
     if (nthread > 1 && nelem == 2 && nthread % 2 == 0) return MODE_ROWGROUP2;
     if (aligned_rows && nthread == 1) return MODE_WORDRUN;
@@ -71,7 +74,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     const int64_t rowlen = (int64_t)nthread * nelem;
     const bool aligned_rows = (sample_start * rowlen) % 4 == 0
         && (nsample * rowlen) % 4 == 0;
-    const int mode = pick_mode(nelem, nthread, aligned_rows);
+    const int mode = pick_mode(nelem, nthread, aligned_rows, true);
     const int cpw = 32 / bps;
     int64_t first = sample_start / spf;
     int64_t last = (sample_start + nsample + spf - 1) / spf;
@@ -85,6 +88,8 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)spf * rowlen / 4;
     } else if (mode == MODE_WORDRUN) {
         per_set = nword;                  // items are lanes = words
+    } else if (mode == MODE_ROWRUN4 || mode == MODE_ROWRUN2) {
+        per_set = spf;                    // items are output rows
     } else {
         per_set = (uint64_t)spf * rowlen;
     }

@@ -44,6 +44,8 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
             else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);
+            else if (l.mode == MODE_ROWRUN4) dec_rowrun<BPS, CODEC, 4>(l.g, lut, item);
+            else if (l.mode == MODE_ROWRUN2) dec_rowrun<BPS, CODEC, 2>(l.g, lut, item);
             else dec_scalar<BPS, CODEC>(l.g, lut, item);
         }
     }
@@ -84,7 +86,7 @@ const char *bb_last_error(void) { return g_err.c_str(); }
 
 // Which decomposition the planner picks (for test coverage assertions).
 int emu_decode_mode(int32_t nelem, int32_t nthread, int aligned_rows) {
-    return pick_mode(nelem, nthread, aligned_rows != 0);
+    return pick_mode(nelem, nthread, aligned_rows != 0, true);
 }
 
 int bb_decode_bitfield(const void *src, const int64_t *unit_offset,

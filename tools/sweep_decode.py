@@ -51,7 +51,13 @@ def main():
         ('vdif 8bit 2thr cplx', 8, 2, 2, 8000, 32, 'vdif'),
         ('vdif 2bit 4thr 8ch', 2, 4, 8, 8000, 32, 'vdif'),
         ('dada int8 cplx 2pol', 8, 1, 4, 1 << 20, 0, 'sint'),
+        ('vdif 4bit 4thr 1ch', 4, 4, 1, 8000, 32, 'vdif'),
+        ('vdif 8bit 4thr 1ch', 8, 4, 1, 8000, 32, 'vdif'),
+        ('vdif 4bit 2thr cplx', 4, 2, 2, 8000, 32, 'vdif'),
+        ('vdif 2bit 2thr cplx', 2, 2, 2, 8000, 32, 'vdif'),
     ]
+    if len(sys.argv) > 2:
+        configs = [c for c in configs if sys.argv[2] in c[0]]
     for name, bps, nthread, nelem, payload, hdr, kind in configs:
         frame = payload + hdr
         nunit = int(gib * 2**30) // frame
@@ -139,4 +145,5 @@ def extra(gib):
 
 if __name__ == '__main__':
     main()
-    extra(float(sys.argv[1]) if len(sys.argv) > 1 else 0.5)
+    if len(sys.argv) <= 2:
+        extra(float(sys.argv[1]) if len(sys.argv) > 1 else 0.5)
