@@ -19,7 +19,8 @@ struct Unroll {
     static constexpr int kF4PerItem =
         MODE == MODE_ROWGROUP4 ? 32 / BPS
         : MODE == MODE_ROWGROUP2 ? 16 / BPS
-        : MODE == MODE_WORDRUN ? 8 / BPS : 1;
+        : MODE == MODE_WORDRUN ? 8 / BPS
+        : MODE == MODE_WORDROW4 ? 32 / BPS : 1;
     static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
 };
 
@@ -72,6 +73,38 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
+    if (MODE == MODE_WORDROW4) {
+        constexpr int TPW = 32 / BPS;
+        constexpr int WB = U < 2 ? U : 2;         // chunks loaded up front
+        const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += WB) {
+            uint32_t w[WB][4], ok[WB];
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                ok[b] = 0u;
+                w[b][0] = w[b][1] = w[b][2] = w[b][3] = 0u;
+                if (item < p.nitems) ok[b] = wrow_load(p, item >> 5, lane, w[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < WB; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                if (item >= p.nitems) break;
+#pragma unroll
+                for (int j = 0; j < TPW; ++j) {
+                    const uint32_t src = wrow_src_lane<BPS>(lane, j);
+                    uint32_t ws[4];
+#pragma unroll
+                    for (int s4 = 0; s4 < 4; ++s4)
+                        ws[s4] = __shfl_sync(0xffffffffu, w[b][s4], src);
+                    const uint32_t oks = __shfl_sync(0xffffffffu, ok[b], src);
+                    wrow_emit<BPS, CODEC>(p, lut, item >> 5, lane, j, ws, oks);
+                }
+            }
+        }
+        return;
+    }
     // Batches of B items: all loads of a batch are issued before the first
     // item is decoded (memory-level parallelism).
     constexpr int B = U < 4 ? U : 4;
@@ -96,8 +129,8 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
-    if (MODE == MODE_ROWRUN4 || MODE == MODE_ROWRUN2) {
-        constexpr int G = MODE == MODE_ROWRUN4 ? 4 : 2;
+    if (MODE == MODE_ROWRUN2) {
+        constexpr int G = 2;
 #pragma unroll 1
         for (int u0 = 0; u0 < U; u0 += B) {
             RowRunItem<G> it[B];
@@ -182,9 +215,9 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
                 <<<tile_grid(n, Unroll<BPS, MODE_WORDRUN>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
-        case MODE_ROWRUN4:
-            k_decode_bitfield<BPS, CODEC, MODE_ROWRUN4>
-                <<<tile_grid(n, Unroll<BPS, MODE_ROWRUN4>::value), kBlock, 0,
+        case MODE_WORDROW4:
+            k_decode_bitfield<BPS, CODEC, MODE_WORDROW4>
+                <<<tile_grid(n, Unroll<BPS, MODE_WORDROW4>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         case MODE_ROWRUN2:

@@ -9,7 +9,7 @@
 namespace bb {
 
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
-       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6 };
+       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6, MODE_WORDROW4 = 7 };
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -46,7 +46,7 @@ inline bool plan_geometry(int64_t payload_nbytes, int bps, int nelem,
 
 inline int pick_mode(int nelem, int nthread, bool aligned_rows,
                      bool decode = false) {
-    if (decode && nthread == 4 && nelem == 1) return MODE_ROWRUN4;
+    if (decode && nthread == 4 && nelem == 1) return MODE_WORDROW4;
     if (decode && nthread == 2 && nelem == 2) return MODE_ROWRUN2;
     if (nthread > 1 && nelem == 1 && nthread % 4 == 0) return MODE_ROWGROUP4;
     if (nthread > 1 && nelem == 2 && nthread % 2 == 0) return MODE_ROWGROUP2;
@@ -86,7 +86,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup;
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
-    } else if (mode == MODE_WORDRUN) {
+    } else if (mode == MODE_WORDRUN || mode == MODE_WORDROW4) {
         per_set = nword;                  // items are lanes = words
     } else if (mode == MODE_ROWRUN4 || mode == MODE_ROWRUN2) {
         per_set = spf;                    // items are output rows
@@ -94,7 +94,8 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)spf * rowlen;
     }
     const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull
-        : mode == MODE_WORDRUN ? 0x0fffffffull : 0x7fffffffull;
+        : (mode == MODE_WORDRUN || mode == MODE_WORDROW4) ? 0x03ffffffull
+        : 0x7fffffffull;
     if (per_set > budget) {
         err = "one frame set is too large for a launch; split it along time";
         return false;
@@ -116,7 +117,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.spf = spf;
         g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
         g.nwords_total = (uint32_t)((uint64_t)nword * (uint64_t)(s1 - s0));
-        if (mode == MODE_WORDRUN)         // whole warps: 32 lanes per chunk
+        if (mode == MODE_WORDRUN || mode == MODE_WORDROW4)   // whole warps
             g.nitems = (g.nwords_total + 31u) / 32u * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);

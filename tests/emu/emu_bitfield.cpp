@@ -40,6 +40,21 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             }
             continue;
         }
+        if (l.mode == MODE_WORDROW4) {
+            constexpr int TPW = 32 / BPS;
+            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
+                uint32_t w[32][4], ok[32];
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    ok[lane] = wrow_load(l.g, chunk, lane, w[lane]);
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < TPW; ++j) {
+                        uint32_t src = wrow_src_lane<BPS>(lane, j);
+                        wrow_emit<BPS, CODEC>(l.g, lut, chunk, lane, j, w[src],
+                                              ok[src]);
+                    }
+            }
+            continue;
+        }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
