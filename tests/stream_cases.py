@@ -687,3 +687,57 @@ def vdif_host_buffer(dev):
     ref_sorted = ref.reshape(6, 16, 8032)[np.arange(6)[:, None], order]
     _same(got.reshape(6, 16, 8032)[:, :, 32:], ref_sorted[:, :, 32:])
     _same(got.reshape(6, 16, 8032)[:, :, :8], ref_sorted[:, :, :8])
+
+
+def vdif_missing_frames():
+    """Frame-level losses (dropped / duplicated frames): gaps are filled with
+    fill_value, as the reference's verify='fix' recovery does one frame at a
+    time (vdif/tests/test_corrupt_files.py)."""
+    import warnings
+    nset, nthread = 9, 8
+    raw = synthetic.vdif_stream(nset, nthread, 5000, seed=41,
+                                thread_order=np.arange(nthread))
+    full = ostream.vdif_read(raw)[:, :, 0]
+    frames = raw.reshape(nset * nthread, 5032)
+    tid = (frames[:, 12:16].view('<u4')[:, 0] >> 16) & 0x3ff
+    drop = [3, 20, 21, 22, 47]                 # physical frames lost
+    keep = np.array([i for i in range(nset * nthread) if i not in drop])
+    lossy = frames[keep]
+    lossy = np.concatenate([lossy[:30], lossy[29:30], lossy[30:]])  # a dup
+    want = full.copy()
+    for i in drop:
+        s = i // nthread
+        want[s * 20000:(s + 1) * 20000, tid[i]] = -7.
+    for chunk in (None, 2 * nthread * 5032):
+        with warnings.catch_warnings(record=True):
+            warnings.simplefilter('always')
+            with bb.vdif.open(io.BytesIO(lossy.tobytes()), 'rs',
+                              sample_rate=32e6, fill_value=-7.,
+                              chunk_nbytes=chunk) as fh:
+                assert fh.shape == want.shape
+                _same(fh.read(), want)
+                fh.seek(59990)
+                _same(fh.read(20020), want[59990:80010])
+    # a loss that keeps the file a whole number of sets long is found from
+    # the time of the last frame
+    drop8 = list(range(16, 24))                # one complete frame set
+    lossy8 = frames[[i for i in range(nset * nthread) if i not in drop8]]
+    want8 = full.copy()
+    want8[2 * 20000:3 * 20000] = -7.
+    with bb.vdif.open(io.BytesIO(lossy8.tobytes()), 'rs', sample_rate=32e6,
+                      fill_value=-7.) as fh:
+        assert fh._index is not None
+        _same(fh.read(), want8)
+    # two sets swapped: same length, same last frame -> caught by the GPU
+    # consistency check during the read, which then re-reads via the index
+    order = np.arange(nset * nthread).reshape(nset, nthread)
+    order[[3, 4]] = order[[4, 3]]
+    swapped = frames[order.reshape(-1)]
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter('always')
+        with bb.vdif.open(io.BytesIO(swapped.tobytes()), 'rs',
+                          sample_rate=32e6) as fh:
+            assert fh._index is None
+            _same(fh.read(), full)
+            assert fh._index is not None
+    assert any('missing or out-of-order' in str(r.message) for r in rec)
