@@ -409,8 +409,9 @@ def measure_e2e(args, dev, rank, world, lv, slot):
 def main():
     # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; the
     # contract is ONE JSON line on stdout.
-    if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-        os.environ['NCCL_DEBUG'] = 'WARN'
+    # (NCCL prints it at every level >= VERSION, so send NCCL's own log to a
+    # file instead of stdout.)
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/bb_nccl_%h_%p.log')
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
