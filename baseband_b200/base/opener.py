@@ -43,7 +43,15 @@ def make_opener(fmt, classes, header_class=None, non_header_keys=(),
             if sample_rate is not None and fmt == 'vdif':
                 header_kwargs.setdefault('sample_rate', sample_rate)
             kwargs['header0'] = header_class.fromvalues(**header_kwargs)
-        if isinstance(name, (str, bytes, os.PathLike)):
+        file_size = kwargs.pop('file_size', None)
+        if isinstance(name, (tuple, list)) or (
+                isinstance(name, str) and '{' in name and mode[0] == 'w'):
+            # a sequence of files (or a name template) as one byte stream
+            from ..helpers import sequentialfile
+            fh = sequentialfile.open(name, mode[0] + 'b',
+                                     file_size=file_size)
+            opened = True
+        elif isinstance(name, (str, bytes, os.PathLike)):
             fh = io.open(name, mode[0] + 'b')
             opened = True
         else:

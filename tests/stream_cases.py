@@ -741,3 +741,31 @@ def vdif_missing_frames():
             _same(fh.read(), full)
             assert fh._index is not None
     assert any('missing or out-of-order' in str(r.message) for r in rec)
+
+
+def dada_file_sequence():
+    """A list of files read as one stream; a template written as several
+    files (helpers/sequentialfile)."""
+    import tempfile
+    rng = np.random.default_rng(6)
+    data = (rng.integers(-128, 128, (4000, 2, 2))
+            + 1j * rng.integers(-128, 128, (4000, 2, 2))).astype(np.complex64)
+    with tempfile.TemporaryDirectory() as tmp:
+        template = os.path.join(tmp, 'seq_{file_nr:02d}.dada')
+        fw = bb.dada.open(template, 'ws', time='2013-07-02T01:39:20',
+                          sample_rate=16e6, samples_per_frame=1000,
+                          sample_shape=(2, 2), complex_data=True, bps=8,
+                          file_size=4096 + 8000)
+        fw.write(data)
+        fw.close()
+        names = sorted(os.path.join(tmp, n) for n in os.listdir(tmp))
+        assert len(names) == 4
+        assert all(os.path.getsize(n) == 4096 + 8000 for n in names)
+        with bb.dada.open(names, 'rs', chunk_nbytes=3000) as fr:
+            assert fr.shape == (4000, 2, 2)
+            _same(fr.read(), data)
+            fr.seek(1990)
+            _same(fr.read(1020), data[1990:3010])
+        with bb.dada.open(names[2], 'rs') as fr:
+            assert fr.header0['OBS_OFFSET'] == 2 * 8000
+            _same(fr.read(), data[2000:3000])
