@@ -43,6 +43,7 @@ SET_BYTES = NTHREAD * FRAME          # 128 512
 SET_SAMPLES = SPF * NTHREAD          # 512 000 decoded floats
 ALGO_BYTES_PER_SAMPLE = (SET_BYTES + SET_SAMPLES * 4) / SET_SAMPLES  # 4.251
 LOGICAL_STREAM_BYTES = 64 << 30
+_REAL_STDOUT = sys.stdout
 METRIC = 'decoded Gsamples/s (device-resident)'
 UNIT = 'Gsamples/s'
 
@@ -139,7 +140,7 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # --------------------------------------------------------------- clocks
@@ -319,7 +320,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -409,9 +410,13 @@ def measure_e2e(args, dev, rank, world, lv, slot):
 def main():
     # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; the
     # contract is ONE JSON line on stdout.
-    # (NCCL prints it at every level >= VERSION, so send NCCL's own log to a
-    # file instead of stdout.)
-    os.environ.setdefault('NCCL_DEBUG_FILE', '/tmp/bb_nccl_%h_%p.log')
+    # Libraries (NCCL's version banner) write to fd 1 behind Python's back:
+    # point fd 1 at stderr for the whole run and keep the real stdout for the
+    # one JSON line.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=100)
