@@ -31,6 +31,14 @@ BASE_FIELDS = FieldTable((
 VDIF_HEADER_CLASSES = {}
 
 
+def header_class_for(edv, default=None):
+    """Class for an extended-data version; ``False`` means a legacy header
+    (looked up by identity: ``False == 0`` would clash with EDV 0)."""
+    if edv is False:
+        return VDIF_HEADER_CLASSES['legacy']
+    return VDIF_HEADER_CLASSES.get(int(edv), default)
+
+
 def ref_epoch_start(ref_epoch):
     """Half-year epochs counted from 2000-01-01 (VDIF spec section 5)."""
     return Time(ymd_to_mjd(2000 + ref_epoch // 2, 1 if ref_epoch % 2 == 0
@@ -54,7 +62,7 @@ class VDIFHeader(BitFieldHeader):
                     raise ValueError('need words or edv to pick a class')
                 edv = (False if (words[0] >> 30) & 1
                        else (words[4] >> 24) & 0xff)
-            cls = VDIF_HEADER_CLASSES.get(edv, VDIFBaseHeader)
+            cls = header_class_for(edv, VDIFBaseHeader)
         return super().__new__(cls)
 
     def __init__(self, words=None, edv=None, verify=True, **kwargs):
@@ -93,7 +101,7 @@ class VDIFHeader(BitFieldHeader):
 
     @classmethod
     def fromvalues(cls, edv=False, *, verify=True, **kwargs):
-        klass = VDIF_HEADER_CLASSES.get(edv)
+        klass = header_class_for(edv)
         if klass is None:
             raise ValueError('no VDIF header class for EDV {}'.format(edv))
         self = klass(None, verify=False)
@@ -397,6 +405,6 @@ class VDIFMark5BHeader(VDIFBaseHeader):
         assert self['frame_length'] == 1254
 
 
-VDIF_HEADER_CLASSES.update({False: VDIFLegacyHeader, 0: VDIFHeader0,
+VDIF_HEADER_CLASSES.update({'legacy': VDIFLegacyHeader, 0: VDIFHeader0,
                             1: VDIFHeader1, 2: VDIFHeader2, 3: VDIFHeader3,
                             0xab: VDIFMark5BHeader})

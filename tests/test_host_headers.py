@@ -1,0 +1,157 @@
+"""Host header classes (bit fields, derived sizes, times, CRCs) against the
+golden field values produced by the unmodified reference, and round trips
+through ``fromvalues`` / ``tofile`` / ``fromfile``.  Pure host code: no GPU."""
+import io
+
+import numpy as np
+import pytest
+
+from baseband_b200.vdif.header import VDIFHeader
+from baseband_b200.mark5b.header import Mark5BHeader
+from baseband_b200.mark4.header import Mark4Header, stream2words, words2stream
+from baseband_b200.base.utils import (bcd_decode, bcd_encode, crc_remainder,
+                                      crc_array, crc_of_bits)
+from baseband_b200.timeutil import Time
+from conftest import sample_path
+
+VDIF_KEYS = ('invalid_data', 'legacy_mode', 'seconds', 'ref_epoch',
+             'frame_nr', 'vdif_version', 'lg2_nchan', 'frame_length',
+             'complex_data', 'bits_per_sample', 'thread_id', 'station_id')
+
+
+@pytest.mark.parametrize('name', ['sample.vdif', 'sample_vlbi.vdif',
+                                  'sample_mwa.vdif', 'sample_arochime.vdif',
+                                  'sample_bps1.vdif'])
+def test_vdif_header_fields(sample_outputs, name):
+    want = sample_outputs[name.replace('.', '_') + '_fields']
+    with open(sample_path(name), 'rb') as fh:
+        for row in want:
+            h = VDIFHeader.fromfile(fh)
+            got = [int(h[k]) for k in VDIF_KEYS] + [
+                h.edv if h.edv else 0, h.payload_nbytes, h.samples_per_frame]
+            assert got == list(row)
+            # write it back unchanged
+            buf = io.BytesIO()
+            h.tofile(buf)
+            fh.seek(-h.nbytes, 1)
+            assert buf.getvalue() == fh.read(h.nbytes)
+            fh.seek(h.payload_nbytes, 1)
+
+
+def test_vdif_header_fromvalues_and_time():
+    with open(sample_path('sample.vdif'), 'rb') as fh:
+        h = VDIFHeader.fromfile(fh)
+    assert h.edv == 3 and h.station == 65532 and h.bps == 2 and h.nchan == 1
+    assert h.sample_rate == 32e6 and h.frame_rate == 1600.
+    assert h.time.isot == '2014-06-16T05:56:07.000000000'
+    h2 = VDIFHeader.fromvalues(
+        edv=3, time=h.time, samples_per_frame=20000, station=65532, bps=2,
+        nchan=1, complex_data=False, thread_id=1, sample_rate=32e6,
+        loif_tuning=h['loif_tuning'], dbe_unit=h['dbe_unit'],
+        if_nr=h['if_nr'], subband=h['subband'], sideband=h['sideband'],
+        major_rev=h['major_rev'], minor_rev=h['minor_rev'],
+        personality=h['personality'], _7_28_4=h['_7_28_4'])
+    assert h2 == h
+    # times off the second boundary need the frame rate
+    h3 = h.copy()
+    h3.mutable = True
+    h3.set_time(h.time + 0.5, frame_rate=1600.)
+    assert h3['frame_nr'] == 800 and h3['seconds'] == h['seconds']
+    assert h3.get_time(frame_rate=1600.) - h.time == 0.5
+    # legacy and EDV 1 round trips
+    legacy = VDIFHeader.fromvalues(edv=False, time='2015-01-01T00:00:00',
+                                   payload_nbytes=8000, bps=2, nchan=4,
+                                   station=65)
+    assert legacy.nbytes == 16 and legacy['legacy_mode']
+    assert legacy.samples_per_frame == 8000
+    buf = io.BytesIO()
+    legacy.tofile(buf)
+    buf.seek(0)
+    assert VDIFHeader.fromfile(buf) == legacy
+    with pytest.raises(TypeError):
+        h['frame_nr'] = 5                      # read from file: immutable
+    with pytest.raises(KeyError):
+        h['no_such_key']
+
+
+def test_mark5b_header(sample_outputs):
+    want = sample_outputs['sample_m5b_fields']
+    with open(sample_path('sample.m5b'), 'rb') as fh:
+        for row in want:
+            h = Mark5BHeader.fromfile(fh, kday=56000)
+            got = [int(h[k]) for k in ('sync_pattern', 'user', 'internal_tvg',
+                                       'frame_nr', 'bcd_jday', 'bcd_seconds',
+                                       'bcd_fraction', 'crc')]
+            got += [h.jday, h.seconds, int(round(h.fraction * 1e9))]
+            assert got == list(row)
+            # CRC and BCD time regenerate exactly
+            h2 = h.copy()
+            h2.mutable = True
+            h2.update(time=h.time, frame_rate=6400.)
+            assert h2 == h
+            fh.seek(10000, 1)
+    assert h.time.isot == '2014-06-13T05:30:01.000468750'
+    h3 = Mark5BHeader.fromvalues(time=Time.from_isot('2014-06-13T05:30:01'),
+                                 user=3901, internal_tvg=False)
+    assert h3.kday == 56000 and h3.jday == 821 and h3['frame_nr'] == 0
+    hr = Mark5BHeader(h.words, ref_time='2014-01-01T00:00:00')
+    assert hr.kday == 56000
+
+
+@pytest.mark.parametrize('name,ntrack', [
+    ('sample.m4', 64), ('sample_32track.m4', 32),
+    ('sample_32track_fanout2.m4', 32), ('sample_16track.m4', 16),
+    ('sample_64track_fanout2_ft.m4', 64)])
+def test_mark4_header(sample_outputs, name, ntrack):
+    tag = name.replace('.', '_')
+    off0 = int(sample_outputs[tag + '_offset0'])
+    want = sample_outputs[tag + '_track_fields']
+    _, fanout, nchan, bps, spf = [int(v) for v in sample_outputs[tag + '_geom']]
+    # the golden fields are those of the LAST frame of the sample
+    nframe = sample_outputs[tag + '_data'].shape[0] // spf
+    start = off0 + (nframe - 1) * ntrack * 2500
+    with open(sample_path(name), 'rb') as fh:
+        fh.seek(start)
+        raw = fh.read(ntrack * 20)
+        fh.seek(start)
+        h = Mark4Header.fromfile(fh, ntrack, decade=2010)
+    keys = ('fan_out', 'magnitude_bit', 'lsb_output', 'converter_id',
+            'bcd_unit_year', 'bcd_day', 'bcd_hour', 'bcd_minute',
+            'bcd_second', 'bcd_fraction', 'crc', 'sync_pattern')
+    got = np.array([np.asarray(h[k]).astype(np.int64) for k in keys])
+    assert np.array_equal(got, want)
+    assert (h.fanout, h.nchan, h.bps, h.samples_per_frame) == (fanout, nchan,
+                                                               bps, spf)
+    # bit transpose and CRC-12 regenerate the bytes on disk
+    stream = np.frombuffer(raw, h.stream_dtype)
+    assert np.array_equal(words2stream(stream2words(stream)), stream)
+    h2 = h.copy()
+    h2.update(time=h.time)
+    buf = io.BytesIO()
+    h2.tofile(buf)
+    assert buf.getvalue() == raw
+    assert Mark4Header(h.words, ref_time=h.time + 86400 * 400).decade == 2010
+
+
+def test_bcd_and_crc():
+    assert bcd_decode(0x1234) == 1234 and bcd_encode(8765) == 0x8765
+    arr = np.array([0x0821, 0x0999], np.uint32)
+    assert list(bcd_decode(arr)) == [821, 999]
+    assert list(bcd_encode(np.array([821, 999]))) == [0x821, 0x999]
+    with pytest.raises(ValueError):
+        bcd_decode(np.array([0x1a], np.uint32))
+    # CRC-16 of the Mark 5B sample time code (mark5b/tests: crc 38749)
+    stream = (((0x821 << 20) + 0x19801) << 16) + 0
+    assert crc_remainder(stream, 0x18005) == 38749
+    assert crc_array(np.array([stream]), 48, 0x18005)[0] == 38749
+    assert crc_remainder((stream << 16) | 38749, 0x18005, extend=False) == 0
+    # bit-parallel CRC agrees with the scalar one on every bit lane
+    rng = np.random.default_rng(2)
+    bits = rng.integers(0, 2, (40, 8))
+    lanes = (bits << np.arange(8)).sum(1).astype(np.uint8)
+    crc = crc_of_bits(lanes, 0x180f)
+    for lane in range(8):
+        value = int(''.join(str(b) for b in bits[:, lane]), 2)
+        want = crc_remainder(value, 0x180f)
+        got = int(''.join(str((int(c) >> lane) & 1) for c in crc), 2)
+        assert got == want
