@@ -769,3 +769,33 @@ def dada_file_sequence():
         with bb.dada.open(names[2], 'rs') as fr:
             assert fr.header0['OBS_OFFSET'] == 2 * 8000
             _same(fr.read(), data[2000:3000])
+
+
+def vdif_legacy_headers():
+    """Legacy VDIF: 16-byte headers (vdif/header.py:529-542 legacy_mode)."""
+    nset, nthread, payload = 5, 2, 4000
+    raw32 = synthetic.vdif_stream(nset, nthread, payload, seed=17, bps=4,
+                                  nchan=2, thread_order=[1, 0])
+    f32 = raw32.reshape(-1, payload + 32)
+    legacy = np.concatenate([f32[:, :16], f32[:, 32:]], axis=1).copy()
+    w = legacy[:, :16].view('<u4')
+    w[:, 0] |= np.uint32(1 << 30)                       # legacy_mode
+    w[:, 2] = (w[:, 2] & np.uint32(0xff000000)) | np.uint32(
+        (payload + 16) // 8)
+    want = ostream.vdif_read(legacy.reshape(-1))
+    assert want.shape == (nset * 4000, 2, 2)
+    with bb.vdif.open(io.BytesIO(legacy.tobytes()), 'rs', sample_rate=2e6,
+                      squeeze=False) as fh:
+        assert fh.header0.nbytes == 16 and fh.header0.edv is False
+        assert fh.shape == want.shape
+        _same(fh.read(), want)
+        header0 = fh.header0
+    buf = io.BytesIO()
+    fw = bb.vdif.open(buf, 'ws', header0=header0, nthread=2, sample_rate=2e6)
+    fw.write(want)
+    got = np.frombuffer(buf.getvalue(), np.uint8).reshape(-1, payload + 16)
+    # writer emits thread 0 first; the source had thread 1 first
+    src = legacy.reshape(nset, 2, payload + 16)[:, ::-1].reshape(
+        -1, payload + 16)
+    _same(got[:, 16:], src[:, 16:])
+    _same(got[:, :12], src[:, :12])
