@@ -390,6 +390,25 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     for _ in range(steps):
         step_dev()
     dt_dev = time.perf_counter() - t1
+
+    # Link rates for context: plain pinned <-> device copies of the same
+    # buffers (what PCIe delivers on this box).
+    def copy_rate(dst, srcbuf):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        dst.copy_(srcbuf, non_blocking=True)
+        e0.record()
+        for _ in range(3):
+            dst.copy_(srcbuf, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return 3 * srcbuf.numel() * srcbuf.element_size() / (
+            e0.elapsed_time(e1) * 1e-3) / 1e9
+
+    probe = torch.empty_like(host_out, device=dev)
+    d2h_gbs = copy_rate(host_out, probe)
+    h2d_gbs = copy_rate(probe, host_out)
+    del probe
     if world > 1:
         t = torch.tensor([dt], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -400,6 +419,15 @@ def measure_e2e(args, dev, rank, world, lv, slot):
             'steps': steps, 'round_trip_exact': ok,
             'device_output_gsamples_s': nset * SET_SAMPLES * steps / dt_dev
             / 1e9,
+            'pcie': {
+                'h2d_copy_gbs': h2d_gbs, 'd2h_copy_gbs': d2h_gbs,
+                'e2e_d2h_gbs': (host_out.numel() * 4 + src.size) * steps
+                / dt / 1e9,
+                'ingest_h2d_gbs': src.size * steps / dt_dev / 1e9,
+                'note': 'e2e moves 4 B/sample device->host: e2e_d2h_gbs vs '
+                        'd2h_copy_gbs is the fraction of the link it '
+                        'reaches; ingest_h2d_gbs is the packed-frame ingest '
+                        'rate of the device-output path'},
             'api': "vdif.open(HostBuffer,'rs',device=).read() -> D2H -> "
                    "vdif.open(HostBuffer,'ws').write()",
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
