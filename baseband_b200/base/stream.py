@@ -396,14 +396,40 @@ class StreamReaderBase(StreamBase):
     def _frames_per_chunk(self):
         return max(1, self._chunk_nbytes // self._frame_nbytes)
 
+    # Streams with frame-level losses (missing / duplicated / re-ordered
+    # frames): a reader may install ``_index``, an int64 table (nframe, nslot)
+    # of PHYSICAL frame numbers in the file (-1 = absent).  Chunks are then
+    # read as the span of physical frames they touch.
+    _index = None
+
+    def _set_index_table(self, table, phys_frame_nbytes):
+        self._index = table
+        self._index_lo = np.where(table >= 0, table,
+                                  np.iinfo(np.int64).max)
+        self._phys_frame_nbytes = phys_frame_nbytes
+        self._nframe = table.shape[0]
+
+    def _chunk_first_frame(self, frame0, nframe):
+        lo = self._index_lo[frame0:frame0 + nframe].min()
+        return 0 if lo == np.iinfo(np.int64).max else int(lo)
+
     def _chunk_nbytes_of(self, frame0, nframe, sample_start, nsample):
         """Raw bytes a chunk needs on the device."""
-        return nframe * self._frame_nbytes
+        if self._index is None:
+            return nframe * self._frame_nbytes
+        table = self._index[frame0:frame0 + nframe]
+        first = self._chunk_first_frame(frame0, nframe)
+        last = int(table.max()) + 1 if (table >= 0).any() else first + 1
+        return (last - first) * self._phys_frame_nbytes
 
     def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
         """Fill ``pinned`` (uint8 tensor) with the bytes of frames
         [frame0, frame0 + nframe)."""
-        offset = self._file_offset0 + frame0 * self._frame_nbytes
+        if self._index is not None:
+            offset = self._file_offset0 + self._chunk_first_frame(
+                frame0, nframe) * self._phys_frame_nbytes
+        else:
+            offset = self._file_offset0 + frame0 * self._frame_nbytes
         zero_copy = getattr(self.fh_raw, 'pinned_view', None)
         if zero_copy is not None:
             # frames already sit in pinned host memory: no staging copy

@@ -144,36 +144,107 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
             verify=verify, device=device, chunk_nbytes=chunk_nbytes)
         self._levels = levels.mark5b(bps)
         self._checks = []
+        if self.verify and self._nframe > 1:
+            # time of the last frame must match its position, else frames
+            # were lost: index all headers
+            fh_raw.seek(offset0 + (self._nframe - 1) * 10016)
+            try:
+                lossy = self._get_index(fh_raw.read_header()) != (
+                    self._nframe - 1)
+            except Exception:
+                lossy = True
+            if lossy:
+                self._build_index()
 
     _frame_nbytes = 10016
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
-        fields, uo = kernels.mark5b_scan(raw, nframe)
-        if self.verify:
-            h0 = self.header0
-            fps = int(round(self._frame_rate))
-            day = fields[kernels.M5B_JDAY].to(torch.int64)
-            # jday wraps every 1000 days; index arithmetic modulo that
-            dday = torch.remainder(day - h0.jday + 500, 1000) - 500
-            index = ((fields[kernels.M5B_SECONDS].to(torch.int64) - h0.seconds
-                      + 86400 * dday) * fps
-                     + fields[kernels.M5B_FRAME_NR].to(torch.int64)
-                     - h0['frame_nr'])
-            want = torch.arange(frame0, frame0 + nframe, device=raw.device)
-            sync_ok = fields[kernels.M5B_SYNC] == -1414668563  # 0xABADDEED
-            self._checks.append(((index != want) | ~sync_ok).sum())
+        if self._index is not None:
+            # lossy stream: scan the physical frames of the chunk (payload
+            # validity), then pick each stream frame's entry from the index
+            nphys = raw.numel() // 10016
+            fields, uo_phys = kernels.mark5b_scan(raw, nphys)
+            table = self._index[frame0:frame0 + nframe, 0]
+            rel = torch.from_numpy(np.where(
+                table >= 0, table - self._chunk_first_frame(frame0, nframe),
+                0)).to(raw.device)
+            present = torch.from_numpy(table >= 0).to(raw.device)
+            uo = torch.where(present, uo_phys[rel],
+                             torch.full_like(rel, -1))
+        else:
+            fields, uo = kernels.mark5b_scan(raw, nframe)
+            if self.verify:
+                index = self._frame_index(
+                    fields[kernels.M5B_JDAY].to(torch.int64),
+                    fields[kernels.M5B_SECONDS].to(torch.int64),
+                    fields[kernels.M5B_FRAME_NR].to(torch.int64))
+                want = torch.arange(frame0, frame0 + nframe,
+                                    device=raw.device)
+                sync_ok = fields[kernels.M5B_SYNC] == -1414668563  # ABADDEED
+                self._checks.append(((index != want) | ~sync_ok).sum())
         kernels.decode_bitfield(
             raw, uo, nframe, 1, 10000, self._bps, self._sample_shape[0],
             False, kernels.CODEC_LEVELS, self._levels, self._fill_value,
             sample_start, nsample, out)
 
+    def _frame_index(self, jday, seconds, frame_nr):
+        """mark5b/base.py:206-213 on arrays (torch or numpy); jday wraps
+        every 1000 days."""
+        h0 = self.header0
+        fps = int(round(self._frame_rate))
+        dday = (jday - h0.jday + 500) % 1000 - 500
+        return ((seconds - h0.seconds + 86400 * dday) * fps
+                + frame_nr - h0['frame_nr'])
+
+    def _build_index(self):
+        """Index of a stream with missing / duplicated / re-ordered frames
+        from one strided pass over all headers (cf. VDIFStreamReader)."""
+        from ..base.utils import bcd_decode
+        fh = self.fh_raw
+        size = fh.seek(0, 2)
+        nphys = (size - self._file_offset0) // 10016
+        words = np.empty((nphys, 4), '<u4')
+        step = 4096
+        for first in range(0, nphys, step):
+            n = min(step, nphys - first)
+            fh.seek(self._file_offset0 + first * 10016)
+            block = np.frombuffer(fh.read(n * 10016), np.uint8)
+            words[first:first + n] = block.reshape(n, 10016)[
+                :, :16].copy().view('<u4')
+        ok = words[:, 0] == 0xABADDEED
+        jday = np.zeros(nphys, np.int64)
+        seconds = np.zeros(nphys, np.int64)
+        try:
+            jday[ok] = bcd_decode((words[ok, 2] >> 20).astype(np.uint32))
+            seconds[ok] = bcd_decode((words[ok, 2] & 0xfffff).astype(
+                np.uint32))
+        except ValueError:
+            raise OSError('Mark 5B headers with invalid BCD time codes.')
+        frame_nr = (words[:, 1] & 0x7fff).astype(np.int64)
+        index = self._frame_index(jday, seconds, frame_nr)
+        ok &= (index >= 0) & (index < 2 * nphys + int(self._frame_rate))
+        nset = int(index[ok].max()) + 1 if ok.any() else 0
+        table = np.full((nset, 1), -1, np.int64)
+        sel = np.flatnonzero(ok)[::-1]               # first occurrence wins
+        table[index[sel], 0] = sel
+        self._set_index_table(table, 10016)
+
     def read(self, count=None, out=None):
         self._checks = []
+        offset = self.offset
         result = super().read(count, out)
         if self._checks and int(torch.stack(self._checks).sum().item()):
-            raise OSError('Mark 5B stream is not a regular sequence of '
-                          'frames; recovery of corrupt files is not part of '
-                          'the GPU path.')
+            if not self.verify:
+                raise OSError('Mark 5B stream is not a regular sequence of '
+                              'frames and verify is off.')
+            import warnings
+            warnings.warn('Mark 5B stream has missing or out-of-order '
+                          'frames; indexing all headers and filling the '
+                          'gaps with fill_value.')
+            self._build_index()
+            self.offset = offset
+            self._checks = []
+            return super().read(result.shape[0], out)
         return result
 
 

@@ -332,34 +332,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         bad = np.flatnonzero(ok & invalid)
         hit = table[index[bad], slot[bad]] == phys[bad]
         table[index[bad][hit], slot[bad][hit]] = -1
-        self._index = table
-        self._index_raw = np.where(table >= 0, table, np.iinfo(np.int64).max)
-        self._nframe = nset
-        self._nphys = nphys
-
-    def _chunk_first_frame(self, frame0, nframe):
-        lo = self._index_raw[frame0:frame0 + nframe].min()
-        return 0 if lo == np.iinfo(np.int64).max else int(lo)
-
-    def _chunk_nbytes_of(self, frame0, nframe, sample_start, nsample):
-        if self._index is None:
-            return nframe * self._frame_nbytes
-        table = self._index[frame0:frame0 + nframe]
-        first = self._chunk_first_frame(frame0, nframe)
-        last = int(table.max()) + 1 if (table >= 0).any() else first + 1
-        return (last - first) * self.header0.frame_nbytes
-
-    def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
-        if self._index is None:
-            return super()._read_raw(frame0, nframe, pinned, sample_start,
-                                     nsample)
-        first = self._chunk_first_frame(frame0, nframe)
-        self.fh_raw.seek(first * self.header0.frame_nbytes)
-        view = pinned.numpy()
-        if self.fh_raw.readinto(memoryview(view)) != view.size:
-            raise EOFError('could not read frames at frame set {}.'.format(
-                frame0))
-        return pinned
+        self._set_index_table(table, h0.frame_nbytes)
 
     def read(self, count=None, out=None):
         self._checks = []

@@ -799,3 +799,23 @@ def vdif_legacy_headers():
         -1, payload + 16)
     _same(got[:, 16:], src[:, 16:])
     _same(got[:, :12], src[:, :12])
+
+
+def mark5b_missing_frames():
+    raw, valid = synthetic.mark5b_stream(30, invalid_fraction=0.1, seed=9)
+    full = ostream.mark5b_read(raw, 8, fill_value=-1.)
+    frames = raw.reshape(30, 10016)
+    drop = [4, 5, 17]
+    lossy = frames[[i for i in range(30) if i not in drop]]
+    want = full.copy()
+    for i in drop:
+        want[i * 5000:(i + 1) * 5000] = -1.
+    for chunk in (None, 4 * 10016):
+        with bb.mark5b.open(io.BytesIO(lossy.tobytes()), 'rs', nchan=8,
+                            sample_rate=32e6, kday=56000, fill_value=-1.,
+                            chunk_nbytes=chunk) as fh:
+            assert fh._index is not None
+            assert fh.shape == want.shape
+            _same(fh.read(), want)
+            fh.seek(19990)
+            _same(fh.read(10020), want[19990:30010])
