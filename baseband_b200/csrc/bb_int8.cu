@@ -20,6 +20,14 @@ __global__ void __launch_bounds__(kF8Threads) k_int8_decode_t64(const I8Geom p) 
 }
 
 template <typename T>
+__global__ void __launch_bounds__(kF8Threads) k_int8_encode_t64(const I8Geom p) {
+    __shared__ __align__(16) uint32_t tile[kF8SmemWords];
+    f8_enc_load<T>(p, tile, blockIdx.x, threadIdx.x);
+    __syncthreads();
+    f8_enc_store(p, tile, blockIdx.x, threadIdx.x);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kI8Threads) k_int8_encode_t(const I8Geom p) {
     __shared__ __align__(16) uint8_t tile[kI8SmemBytes];
     i8_enc_load<T>(p, tile, blockIdx.x, threadIdx.x);
@@ -97,7 +105,8 @@ extern "C" int bb_encode_int8_transposed(
         return set_error(BB_ERR_ARGUMENT, "null pointer argument");
     I8Geom g;
     uint64_t nblocks;
-    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks);
+    const bool fast = nrow % 2 == 0 && aligned(in, 16);
+    int rc = fill_geom(g, nunit, nrow, ncol, item_nbytes, nblocks, fast);
     if (rc != BB_OK) return rc;
     if (nblocks == 0) return BB_OK;
     g.src = (const uint8_t *)dst;
@@ -105,14 +114,17 @@ extern "C" int bb_encode_int8_transposed(
     g.col_begin = g.col_end = g.out_col0 = nullptr;
     g.out = nullptr;
     g.in = in;
-    if (in_dtype == BB_F32)
-        k_int8_encode_t<float><<<(unsigned)nblocks, kI8Threads, 0,
-                                 as_stream(stream)>>>(g);
-    else if (in_dtype == BB_F64)
-        k_int8_encode_t<double><<<(unsigned)nblocks, kI8Threads, 0,
-                                  as_stream(stream)>>>(g);
-    else
+    if (in_dtype != BB_F32 && in_dtype != BB_F64)
         return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+    cudaStream_t s = as_stream(stream);
+    if (fast && in_dtype == BB_F32)
+        k_int8_encode_t64<float><<<(unsigned)nblocks, kF8Threads, 0, s>>>(g);
+    else if (fast)
+        k_int8_encode_t64<double><<<(unsigned)nblocks, kF8Threads, 0, s>>>(g);
+    else if (in_dtype == BB_F32)
+        k_int8_encode_t<float><<<(unsigned)nblocks, kI8Threads, 0, s>>>(g);
+    else
+        k_int8_encode_t<double><<<(unsigned)nblocks, kI8Threads, 0, s>>>(g);
     BB_CHECK_LAUNCH("bb_encode_int8_transposed launch");
     return BB_OK;
 }

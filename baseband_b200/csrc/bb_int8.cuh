@@ -301,4 +301,96 @@ BB_HD void f8_dec_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
     }
 }
 
+// ---- fast encode: the mirror image.  Phase 1: a lane reads the (re, im) of
+// rows 2l and 2l+1 of one output column as one float4 (a warp load is 512
+// contiguous bytes), quantises and writes two swizzled words; phase 2: a warp
+// writes 128 contiguous bytes of one packed row.
+template <typename T>
+BB_HD void f8_load4(const T *q, T v[4]) {
+    if (sizeof(T) == 4) {
+        F4 r = *reinterpret_cast<const F4 *>(q);
+        v[0] = (T)r.x; v[1] = (T)r.y; v[2] = (T)r.z; v[3] = (T)r.w;
+    } else {
+        D2 a = reinterpret_cast<const D2 *>(q)[0];
+        D2 b = reinterpret_cast<const D2 *>(q)[1];
+        v[0] = (T)a.x; v[1] = (T)a.y; v[2] = (T)b.x; v[3] = (T)b.y;
+    }
+}
+
+template <typename T>
+BB_HD void f8_enc_load(const I8Geom &p, uint32_t *smem, uint32_t block,
+                       uint32_t tid) {
+    const F8Tile t = f8_tile(p, block);
+    if (p.unit_offset[t.unit] < 0) return;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const uint32_t ra = 2u * lane;
+    const bool rows_ok = t.r0 + ra < p.nrow;              // nrow is even
+    const T *in = reinterpret_cast<const T *>(p.in);
+    const size_t row = (size_t)t.r0 + ra;
+    const size_t col0 = (size_t)t.unit * p.ncol;
+    constexpr int kIter = kF8Words / (kF8Threads / 32);    // 8
+#pragma unroll 2
+    for (int i = 0; i < kIter; ++i) {
+        const uint32_t wc = warp + i * (kF8Threads / 32);
+        uint32_t a = 0u, b = 0u;
+        if (rows_ok) {
+            if (p.ib == 2) {
+                const size_t j = ((size_t)t.w0 + wc) * 2;
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (j + k >= p.ncol) continue;
+                    T v[4];
+                    f8_load4(in + 2 * ((col0 + j + k) * p.nrow + row), v);
+                    a |= (quant_sint<T, 8>(v[0])
+                          | (quant_sint<T, 8>(v[1]) << 8)) << (16 * k);
+                    b |= (quant_sint<T, 8>(v[2])
+                          | (quant_sint<T, 8>(v[3]) << 8)) << (16 * k);
+                }
+            } else {
+                const size_t j = ((size_t)t.w0 + wc) * 4;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (j + k >= p.ncol) continue;
+                    const T *q = in + (col0 + j + k) * p.nrow + row;
+                    a |= quant_sint<T, 8>(q[0]) << (8 * k);
+                    b |= quant_sint<T, 8>(q[1]) << (8 * k);
+                }
+            }
+        }
+        smem[f8_swz(ra, wc)] = a;
+        smem[f8_swz(ra + 1, wc)] = b;
+    }
+}
+
+BB_HD void f8_enc_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
+                        uint32_t tid) {
+    const F8Tile t = f8_tile(p, block);
+    const long long off = p.unit_offset[t.unit];
+    if (off < 0) return;
+    const uint32_t lane = tid & 31u, warp = tid >> 5;
+    const size_t rowbytes = (size_t)p.ncol * p.ib;
+    uint8_t *base = const_cast<uint8_t *>(p.src) + off;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(base) | rowbytes) & 3u)
+        == 0;
+    constexpr int kIter = kF8Rows / (kF8Threads / 32);
+#pragma unroll 2
+    for (int i = 0; i < kIter; ++i) {
+        const uint32_t r = warp + i * (kF8Threads / 32);
+        if (t.r0 + r >= p.nrow) break;
+        uint8_t *row = base + (size_t)(t.r0 + r) * rowbytes;
+#pragma unroll
+        for (uint32_t seg = 0; seg < 2; ++seg) {
+            const uint32_t wl = seg * 32u + lane;
+            const size_t b = ((size_t)t.w0 + wl) * 4;
+            const uint32_t w = smem[f8_swz(r, wl)];
+            if (aligned && b + 4 <= rowbytes) {
+                *reinterpret_cast<uint32_t *>(row + b) = w;
+            } else {
+                for (int k = 0; k < 4; ++k)
+                    if (b + k < rowbytes) row[b + k] = (uint8_t)(w >> (8 * k));
+            }
+        }
+    }
+}
+
 }  // namespace bb

@@ -64,11 +64,28 @@ int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
                               void *stream) {
     I8Geom g;
     uint64_t nblocks;
-    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks)) return BB_ERR_ARGUMENT;
+    const bool fast = nrow % 2 == 0
+        && (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    if (!geom(g, nunit, nrow, ncol, item_nbytes, nblocks, fast))
+        return BB_ERR_ARGUMENT;
     g.src = (const uint8_t *)dst;
     g.unit_offset = (const long long *)unit_offset;
     g.col_begin = g.col_end = g.out_col0 = nullptr;
     g.out = nullptr; g.in = in;
+    if (fast) {
+        std::vector<uint32_t> tile64(kF8SmemWords);
+        for (uint64_t b = 0; b < nblocks; ++b) {
+            for (uint32_t t = 0; t < kF8Threads; ++t) {
+                if (in_dtype == BB_F32)
+                    f8_enc_load<float>(g, tile64.data(), (uint32_t)b, t);
+                else
+                    f8_enc_load<double>(g, tile64.data(), (uint32_t)b, t);
+            }
+            for (uint32_t t = 0; t < kF8Threads; ++t)
+                f8_enc_store(g, tile64.data(), (uint32_t)b, t);
+        }
+        return 0;
+    }
     alignas(16) uint8_t tile[kI8SmemBytes];
     for (uint64_t b = 0; b < nblocks; ++b) {
         for (uint32_t t = 0; t < kI8Threads; ++t) {

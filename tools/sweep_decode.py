@@ -141,6 +141,22 @@ def extra(gib):
     print('DEC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
           % ('C4 guppi 512ch 2pol int8', nbytes / best / 1e6,
              nbytes / med / 1e6, out.numel() / med / 1e6, med))
+    # encode: whole frames (writers have no overlap)
+    del out
+    cb0 = torch.zeros(nfr, dtype=torch.int64, device=DEV)
+    oc = torch.arange(nfr, dtype=torch.int64, device=DEV) * (spf * npol)
+    full = torch.empty((nfr * spf * npol * nchan * 2,), dtype=torch.float32,
+                       device=DEV)
+    kernels.decode_int8_transposed(raw, off, nfr, nchan, spf * npol, 2, cb0,
+                                   ce, oc, full)
+    back = torch.zeros_like(raw)
+    best, med = timeit(lambda: kernels.encode_int8_transposed(
+        full, back, off, nfr, nchan, spf * npol, 2))
+    nbytes = full.numel() * 5
+    print('ENC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('C4 guppi 512ch 2pol int8', nbytes / best / 1e6,
+             nbytes / med / 1e6, full.numel() / med / 1e6, med))
+    print('    round trip identical:', bool(torch.equal(back, raw)))
 
 
 if __name__ == '__main__':
