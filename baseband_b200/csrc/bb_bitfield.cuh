@@ -533,9 +533,12 @@ template <typename T, int BPS, int QUANT, bool VEC>
 BB_HD void enc_word(const EncGeom &p, const QuantConsts<T> &c,
                     uint32_t item) {
     constexpr int CPW = 32 / BPS;
-    uint32_t unit, k, set, slot;
-    p.div_nword.divmod(item, unit, k);
-    p.div_nthread.divmod(unit, set, slot);
+    // item = (set, k, slot), slot fastest: neighbouring lanes read the slots
+    // of the same rows, i.e. neighbouring bytes of the input.
+    uint32_t rest, k, set, slot;
+    p.div_nthread.divmod(item, rest, slot);
+    p.div_nword.divmod(rest, set, k);
+    const uint32_t unit = set * p.nthread + slot;
     long long off = p.unit_offset[unit];
     if (off < 0) return;
     const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
