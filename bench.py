@@ -354,26 +354,17 @@ def measure_e2e(args, dev, rank, world, lv, slot):
                           chunk_nbytes=32 << 20)
     side = torch.cuda.Stream(dev)
 
-    # A streaming user works through the file in pieces: while piece i is on
-    # its way back to the host, piece i+1 is uploaded and decoded.
-    npiece = 8
-    piece_sets = -(-nset // npiece)
-
     def step():
         reader.seek(0)
+        data = reader.read()                      # device tensor
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):             # result back to the host
+            host_out.copy_(data, non_blocking=True)
         sink.seek(0)
         writer = bb.vdif.open(sink, 'ws', header0=reader.header0,
                               nthread=NTHREAD, sample_rate=64e6, device=dev)
-        row = 0
-        for first in range(0, nset, piece_sets):
-            n = min(piece_sets, nset - first) * SPF
-            data = reader.read(n)                 # H2D + scan + decode
-            side.wait_stream(torch.cuda.current_stream(dev))
-            with torch.cuda.stream(side):         # result back to the host
-                host_out[row:row + n].copy_(data, non_blocking=True)
-                data.record_stream(side)
-            writer.write(data)                    # encode + D2H of frames
-            row += n
+        writer.write(data)                        # encode + D2H of frames
+        writer._flush(final=False)
         torch.cuda.synchronize(dev)
 
     for _ in range(2):
