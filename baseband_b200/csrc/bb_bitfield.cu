@@ -173,36 +173,8 @@ template <typename T, int BPS, int QUANT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
     constexpr int U = (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
-        ? Unroll<BPS, MODE>::value
-        : (MODE == MODE_ROWRUN4 || MODE == MODE_ROWRUN2) ? 16 : 4;
+        ? Unroll<BPS, MODE>::value : 4;
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
-    if (MODE == MODE_ROWRUN4 || MODE == MODE_ROWRUN2) {
-        // spf is a multiple of TPW and nitems of spf, so groups of TPW lanes
-        // (TPW <= 16 divides 32) are entirely inside or outside the launch.
-        constexpr int G = MODE == MODE_ROWRUN4 ? 4 : 2;
-        constexpr int TPW = (32 / BPS) / (4 / G);
-        const uint32_t lane = threadIdx.x & 31u;
-        const uint32_t gmask = TPW >= 32 ? 0xffffffffu
-            : (((1u << TPW) - 1u) << (lane / TPW * TPW));
-#pragma unroll 2
-        for (int u = 0; u < U; ++u) {
-            const uint32_t row = item0 + u * kBlock;
-            if (row >= p.nitems) break;
-            uint32_t piece[G];
-            enc_rowrun_piece<T, BPS, QUANT, G>(p, c, row, piece);
-#pragma unroll
-            for (int s = 0; s < G; ++s)
-                piece[s] = __reduce_or_sync(gmask, piece[s]);
-            const uint32_t me = lane % TPW;
-            if (me < G) {
-                uint32_t word = piece[0];
-#pragma unroll
-                for (int s = 1; s < G; ++s) if (me == s) word = piece[s];
-                enc_rowrun_store<BPS, G>(p, row, me, word);
-            }
-        }
-        return;
-    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kBlock;
@@ -283,14 +255,6 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
         case MODE_RUN:
             k_encode_bitfield<T, BPS, QUANT, MODE_RUN>
                 <<<tile_grid(n, 4), kBlock, 0, stream>>>(l.g, consts);
-            break;
-        case MODE_ROWRUN4:
-            k_encode_bitfield<T, BPS, QUANT, MODE_ROWRUN4>
-                <<<tile_grid(n, 16), kBlock, 0, stream>>>(l.g, consts);
-            break;
-        case MODE_ROWRUN2:
-            k_encode_bitfield<T, BPS, QUANT, MODE_ROWRUN2>
-                <<<tile_grid(n, 16), kBlock, 0, stream>>>(l.g, consts);
             break;
         default:
             k_encode_bitfield<T, BPS, QUANT, MODE_SCALAR>

@@ -463,7 +463,7 @@ struct EncGeom {
     const long long *unit_offset;
     uint32_t nset, nthread, nelem, nword, spf, nitems, ngroup;
     int32_t log2_nelem;
-    FastDiv div_nword, div_ngroup, div_nthread, div_spf;
+    FastDiv div_nword, div_ngroup, div_nthread;
 };
 
 template <typename T> struct Vec4;
@@ -526,45 +526,6 @@ BB_HD void enc_rowgroup(const EncGeom &p, const QuantConsts<T> &c,
         long long off = uo[j];
         if (off >= 0) store_u32(p.dst + off + 4ull * k, w[j]);
     }
-}
-
-// ROWRUN encode (nthread * E == 4): a lane owns one input row = one float4
-// (a warp load is 512 contiguous bytes), quantises it and places its codes at
-// the row's position inside the payload word; the TPW lanes whose rows share
-// a word then OR their pieces (warp reduce), and lane s of the group stores
-// the word of slot s.  `enc_rowrun_piece` is the per-lane part.
-template <typename T, int BPS, int QUANT, int G>
-BB_HD void enc_rowrun_piece(const EncGeom &p, const QuantConsts<T> &c,
-                            uint32_t row, uint32_t piece[G]) {
-    constexpr int E = 4 / G;
-    constexpr int TPW = (32 / BPS) / E;
-    const T *src = reinterpret_cast<const T *>(p.in) + p.in_elem_offset
-        + (size_t)row * 4;
-    Vec4<T> v = Vec4<T>::load(src);
-    const uint32_t q0 = quantise<T, BPS, QUANT>(v.x, c);
-    const uint32_t q1 = quantise<T, BPS, QUANT>(v.y, c);
-    const uint32_t q2 = quantise<T, BPS, QUANT>(v.z, c);
-    const uint32_t q3 = quantise<T, BPS, QUANT>(v.w, c);
-    const uint32_t sh = (row % TPW) * (BPS * E);
-    if (E == 1) {
-        piece[0] = q0 << sh; piece[1 % G] = q1 << sh;
-        piece[2 % G] = q2 << sh; piece[3 % G] = q3 << sh;
-    } else {
-        piece[0] = (q0 | (q1 << BPS)) << sh;
-        piece[1 % G] = (q2 | (q3 << BPS)) << sh;
-    }
-}
-
-// Store the word of slot `s` that covers row `row` (row % TPW == s).
-template <int BPS, int G>
-BB_HD void enc_rowrun_store(const EncGeom &p, uint32_t row, uint32_t s,
-                            uint32_t word) {
-    constexpr int E = 4 / G;
-    constexpr int TPW = (32 / BPS) / E;
-    uint32_t set, t;
-    p.div_spf.divmod(row, set, t);
-    const long long off = p.unit_offset[(size_t)set * G + s];
-    if (off >= 0) store_u32(p.dst + off + 4ull * (t / TPW), word);
 }
 
 // RUN / SCALAR: item = output word index over all units of the launch.

@@ -146,13 +146,9 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
     const int64_t rowlen = (int64_t)nthread * nelem;
     int mode = pick_mode(nelem, nthread, true);
     if (mode == MODE_WORDRUN) mode = MODE_RUN;   // encode: vectorised words
-    if (nthread == 4 && nelem == 1) mode = MODE_ROWRUN4;
-    if (nthread == 2 && nelem == 2) mode = MODE_ROWRUN2;
     uint64_t per_set;
     uint32_t ngroup = 1;
-    if (mode == MODE_ROWRUN4 || mode == MODE_ROWRUN2) {
-        per_set = spf;                    // items are input rows
-    } else if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
+    if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
         ngroup = nthread / (mode == MODE_ROWGROUP4 ? 4 : 2);
         per_set = (uint64_t)nword * ngroup;
     } else {
@@ -181,7 +177,6 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
         g.div_nword = make_fastdiv(nword);
         g.div_ngroup = make_fastdiv(ngroup);
         g.div_nthread = make_fastdiv(nthread);
-        g.div_spf = make_fastdiv(spf);
         launches.push_back({mode, g});
     }
     return true;

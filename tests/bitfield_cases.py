@@ -143,11 +143,6 @@ ENCODE_CASES = [
     _ecase('1bit_8thr', 1, 1, 8, 2, 128),
     _ecase('4bit_4thr', 4, 1, 4, 2, 256),
     _ecase('8bit_12thr', 8, 1, 12, 2, 200),
-    _ecase('1bit_4thr_rowrun', 1, 1, 4, 3, 68, invalid=(6,)),
-    _ecase('2bit_4thr_rowrun_f64', 2, 1, 4, 2, 404, dtype='f8'),
-    _ecase('8bit_4thr_rowrun', 8, 1, 4, 2, 404),
-    _ecase('4bit_cplx_2thr_rowrun', 4, 2, 2, 3, 100, invalid=(3,)),
-    _ecase('1bit_cplx_2thr_rowrun', 1, 2, 2, 2, 60),
     _ecase('2bit_cplx_2thr', 2, 2, 2, 3, 512),
     _ecase('8bit_cplx_2thr_f64', 8, 2, 2, 2, 1024, dtype='f8'),
     _ecase('1bit_2chan_4thr', 1, 2, 4, 2, 64),

@@ -69,38 +69,13 @@ static void run_decode(const std::vector<DecLaunch> &launches,
 template <typename T, int BPS, int QUANT>
 static void run_encode(const std::vector<EncLaunch> &launches) {
     const QuantConsts<T> c = make_quant_consts<T>();
-    for (const EncLaunch &l : launches) {
-        if (l.mode == MODE_ROWRUN4 || l.mode == MODE_ROWRUN2) {
-            // group OR-reduction emulated over the TPW rows of each word
-            const int G = l.mode == MODE_ROWRUN4 ? 4 : 2;
-            const uint32_t tpw = (32 / BPS) / (4 / G);
-            for (uint32_t row0 = 0; row0 < l.g.nitems; row0 += tpw) {
-                uint32_t word[4] = {0u, 0u, 0u, 0u};
-                for (uint32_t r = row0; r < row0 + tpw; ++r) {
-                    if (G == 4) {
-                        uint32_t piece[4];
-                        enc_rowrun_piece<T, BPS, QUANT, 4>(l.g, c, r, piece);
-                        for (int s = 0; s < 4; ++s) word[s] |= piece[s];
-                    } else {
-                        uint32_t piece[2];
-                        enc_rowrun_piece<T, BPS, QUANT, 2>(l.g, c, r, piece);
-                        for (int s = 0; s < 2; ++s) word[s] |= piece[s];
-                    }
-                }
-                for (int s = 0; s < G; ++s) {
-                    if (G == 4) enc_rowrun_store<BPS, 4>(l.g, row0 + s, s, word[s]);
-                    else enc_rowrun_store<BPS, 2>(l.g, row0 + s, s, word[s]);
-                }
-            }
-            continue;
-        }
+    for (const EncLaunch &l : launches)
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(l.g, c, item);
             else if (l.mode == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(l.g, c, item);
             else if (l.mode == MODE_RUN) enc_word<T, BPS, QUANT, true>(l.g, c, item);
             else enc_word<T, BPS, QUANT, false>(l.g, c, item);
         }
-    }
 }
 
 template <typename T>
