@@ -602,12 +602,39 @@ class StreamReaderBase(StreamBase):
                 _device.unregister_host(registered)
         return result
 
-    # pickling drops device state (base/base.py:1020-1032 drops the frame)
+    # Pickling (base/base.py:123-151, :1020-1032): device buffers and streams
+    # are dropped and re-created lazily; the raw file is re-opened by name in
+    # the unpickling process and the sample pointer restored.
     def __getstate__(self):
         state = self.__dict__.copy()
         state['_stages'] = None
         state['_streams'] = None
+        state.pop('_slots_dev', None)
+        state.pop('_sample_shape_cache', None)    # namedtuple made on the fly
+        wrapper = state['fh_raw']
+        fh = getattr(wrapper, 'fh_raw', wrapper)
+        name = getattr(fh, 'name', None)
+        if isinstance(name, str) and not getattr(fh, 'closed', False):
+            import copy
+            clone = copy.copy(wrapper) if fh is not wrapper else None
+            state['fh_raw'] = ('__reopen__', name, clone)
+            if clone is not None:
+                clone.fh_raw = None
         return state
+
+    def __setstate__(self, state):
+        marker = state.get('fh_raw')
+        if isinstance(marker, tuple) and marker and marker[0] == '__reopen__':
+            _, name, clone = marker
+            import io
+            fh = io.open(name, 'rb')
+            if clone is not None:
+                clone.fh_raw = fh
+                fh = clone
+            state['fh_raw'] = fh
+        self.__dict__.update(state)
+        if '_slots_host' in state:
+            self._slots_dev = None
 
 
 def _torch_index(subset, dev):

@@ -819,3 +819,24 @@ def mark5b_missing_frames():
             _same(fh.read(), want)
             fh.seek(19990)
             _same(fh.read(10020), want[19990:30010])
+
+
+def vdif_pickle_reader():
+    """Readers can be sent to other processes (base/base.py:123-151): the
+    file is re-opened by name, the offset kept, device state re-created."""
+    import pickle
+    want = OUT['sample_vdif_data'][:, :, 0]
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
+        fh.seek(6)
+        _same(fh.read(3), want[6:9])
+        clone = pickle.loads(pickle.dumps(fh))
+        assert clone.tell() == 9
+        _same(clone.read(20001), want[9:20010])
+        assert fh.tell() == 9
+        _same(fh.read(2), want[9:11])
+        clone.close()
+    with bb.mark5b.open(sample_path('sample.m5b'), 'rs', sample_rate=32e6,
+                        kday=56000, nchan=8) as fh:
+        clone = pickle.loads(pickle.dumps(fh))
+        _same(clone.read(), OUT['sample_m5b_data'])
+        clone.close()
