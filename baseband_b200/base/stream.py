@@ -243,6 +243,7 @@ class StreamReaderBase(StreamBase):
         self.verify = verify
         self._device_output = device is not None
         self._chunk_nbytes = int(chunk_nbytes or DEFAULT_CHUNK_NBYTES)
+        self._on_device = None
         self._stages = None
         self._streams = None
         self.sample_shape            # validates the subset
@@ -351,13 +352,19 @@ class StreamReaderBase(StreamBase):
         return self.offset
 
     # ----------------------------------------------------------------- read
-    def read(self, count=None, out=None):
+    def read(self, count=None, out=None, *, on_device=None):
         """Read and decode ``count`` complete samples.
 
         Returns an array ``(count,) + sample_shape`` of float32/complex64:
         a `numpy.ndarray`, or a CUDA `torch.Tensor` if the stream was opened
         with ``device=`` or ``out`` is a CUDA tensor.  ``out`` may be a numpy
         array or a torch tensor whose leading dimension sets ``count``.
+
+        ``on_device`` (extension): a callable that is handed every decoded
+        chunk as a CUDA tensor ``(n,) + sample_shape``, in order, on the
+        compute stream, before the chunk is copied to the host -- the hook
+        for consumers that work on the GPU (e.g. ``writer.write`` to
+        re-encode while the samples are still in HBM).
         """
         if self.closed:
             raise ValueError('I/O operation on closed file.')
@@ -374,10 +381,14 @@ class StreamReaderBase(StreamBase):
             raise EOFError('cannot read from beyond end of input.')
         to_device = _device.is_device_tensor(out) or (
             out is None and self._device_output)
-        if to_device:
-            result = self._read_to_device(self.offset, count, out)
-        else:
-            result = self._read_to_host(self.offset, count, out)
+        self._on_device = on_device
+        try:
+            if to_device:
+                result = self._read_to_device(self.offset, count, out)
+            else:
+                result = self._read_to_host(self.offset, count, out)
+        finally:
+            self._on_device = None
         self.offset += count
         return result
 
@@ -536,6 +547,8 @@ class StreamReaderBase(StreamBase):
                     piece.copy_(tmp)
                 else:
                     self._decode_chunk(raw, f0, nf, s0, ns, piece)
+                if self._on_device is not None:
+                    self._on_device(self._finish(piece, ns))
         ss.caller_after(1)
         result = self._finish(flat, count)
         if out is not None and not direct:
@@ -584,6 +597,8 @@ class StreamReaderBase(StreamBase):
                     ss.wait(1, 0)
                     self._decode_chunk(raw, f0, nf, s0, ns, st.dec[:ns * fps])
                     piece = self._finish(st.dec, ns)
+                    if self._on_device is not None:
+                        self._on_device(piece)
                     if self._subset and not piece.is_contiguous():
                         piece = piece.contiguous()
                 with ss.use(2):
@@ -731,6 +746,9 @@ class StreamWriterBase(StreamBase):
             self._npending += pad
             nframe += 1
         if nframe == 0:
+            # keep our own copy: the caller's tensor may be a view of a
+            # buffer that is about to be reused (read(on_device=...))
+            self._pending = [(t.clone(), ok) for t, ok in self._pending]
             return
         take = nframe * spf
         # validity per frame = AND over the writes that touch it
@@ -758,7 +776,7 @@ class StreamWriterBase(StreamBase):
                                      nframe, valid)
         self._write_raw(frames)
         self._frame_index += nframe
-        self._pending = [(rest, rest_valid)] if rest.shape[0] else []
+        self._pending = [(rest.clone(), rest_valid)] if rest.shape[0] else []
         self._npending = int(rest.shape[0])
 
     def _encode_frames(self, flat, index0, nframe, valid):

@@ -173,9 +173,9 @@ class Mark4StreamReader(StreamReaderBase):
                              self._levels, self._fill_value, sample_start,
                              nsample, out)
 
-    def read(self, count=None, out=None):
+    def read(self, count=None, out=None, **kwargs):
         self._checks = []
-        result = super().read(count, out)
+        result = super().read(count, out, **kwargs)
         if self._checks and int(torch.stack(self._checks).sum().item()):
             raise OSError('Mark 4 stream is not a regular sequence of '
                           'frames; recovery of corrupt files is not part of '

@@ -229,10 +229,10 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
         table[index[sel], 0] = sel
         self._set_index_table(table, 10016)
 
-    def read(self, count=None, out=None):
+    def read(self, count=None, out=None, **kwargs):
         self._checks = []
         offset = self.offset
-        result = super().read(count, out)
+        result = super().read(count, out, **kwargs)
         if self._checks and int(torch.stack(self._checks).sum().item()):
             if not self.verify:
                 raise OSError('Mark 5B stream is not a regular sequence of '
@@ -244,7 +244,7 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
             self._build_index()
             self.offset = offset
             self._checks = []
-            return super().read(result.shape[0], out)
+            return super().read(result.shape[0], out, **kwargs)
         return result
 
 

@@ -332,10 +332,10 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         table[index[bad][hit], slot[bad][hit]] = -1
         self._set_index_table(table, h0.frame_nbytes)
 
-    def read(self, count=None, out=None):
+    def read(self, count=None, out=None, **kwargs):
         self._checks = []
         offset = self.offset
-        result = super().read(count, out)
+        result = super().read(count, out, **kwargs)
         if self._checks:
             nbad = int(torch.stack([c.reshape(()) for c in self._checks])
                        .sum().item())
@@ -353,7 +353,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
                 self.offset = offset
                 self._checks = []
                 n = result.shape[0]
-                return super().read(n, out if out is not None else None)
+                return super().read(n, out if out is not None else None, **kwargs)
         return result
 
 

@@ -350,20 +350,21 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     sink = HostBuffer(src.size)
     host_out = torch.empty((nset * SPF, NTHREAD), dtype=torch.float32,
                            pin_memory=True)
-    reader = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+    reader = bb.vdif.open(src, 'rs', sample_rate=64e6,
                           chunk_nbytes=32 << 20)
-    side = torch.cuda.Stream(dev)
+    dev_reader = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+                              chunk_nbytes=32 << 20)
+    host_view = host_out.numpy()
 
     def step():
+        # read() streams the frames through the GPU in chunks (H2D, scan,
+        # decode, D2H overlapped); each decoded chunk is also handed to the
+        # writer while it is still in HBM (encode + D2H of the frames).
         reader.seek(0)
-        data = reader.read()                      # device tensor
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):             # result back to the host
-            host_out.copy_(data, non_blocking=True)
         sink.seek(0)
         writer = bb.vdif.open(sink, 'ws', header0=reader.header0,
                               nthread=NTHREAD, sample_rate=64e6, device=dev)
-        writer.write(data)                        # encode + D2H of frames
+        reader.read(out=host_view, on_device=writer.write)
         writer._flush(final=False)
         torch.cuda.synchronize(dev)
 
@@ -381,8 +382,8 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     # Device-output option: same ingest, decoded samples stay in HBM for a
     # consumer on the GPU; only a spot value is read back.
     def step_dev():
-        reader.seek(0)
-        data = reader.read()
+        dev_reader.seek(0)
+        data = dev_reader.read()
         return float(data[-1, -1].item())
 
     step_dev()
@@ -428,8 +429,8 @@ def measure_e2e(args, dev, rank, world, lv, slot):
                         'd2h_copy_gbs is the fraction of the link it '
                         'reaches; ingest_h2d_gbs is the packed-frame ingest '
                         'rate of the device-output path'},
-            'api': "vdif.open(HostBuffer,'rs',device=).read() -> D2H -> "
-                   "vdif.open(HostBuffer,'ws').write()",
+            'api': "vdif.open(HostBuffer,'rs').read(out=pinned numpy, "
+                   "on_device=vdif.open(HostBuffer,'ws').write)",
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
                     'float32 array returned to the host is 16x the packed '
                     'input'.format(args.e2e_mib)}

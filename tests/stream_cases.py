@@ -840,3 +840,35 @@ def vdif_pickle_reader():
         clone = pickle.loads(pickle.dumps(fh))
         _same(clone.read(), OUT['sample_m5b_data'])
         clone.close()
+
+
+def vdif_on_device_hook(dev):
+    """``read(on_device=...)``: every decoded chunk is handed to a GPU
+    consumer (here the stream writer) before it is copied to the host."""
+    from baseband_b200.base.memory import HostBuffer
+    raw = synthetic.vdif_stream(12, 8, 5000, seed=23,
+                                thread_order=np.arange(8))
+    want = ostream.vdif_read(raw)[:, :, 0]
+    sink = HostBuffer(raw.size)
+    seen = []
+    with bb.vdif.open(HostBuffer(raw), 'rs', sample_rate=32e6,
+                      chunk_nbytes=3 * 8 * 5032) as fh:
+        fw = bb.vdif.open(sink, 'ws', header0=fh.header0, nthread=8,
+                          sample_rate=32e6, device=dev)
+
+        def consume(piece):
+            seen.append(tuple(piece.shape))
+            fw.write(piece)
+
+        out = np.empty(want.shape, np.float32)
+        fh.read(out=out, on_device=consume)
+        _same(out, want)
+        fw._flush(final=False)
+    assert len(seen) == 4 and sum(s[0] for s in seen) == want.shape[0]
+    _same(sink.getvalue(), raw)
+    with bb.vdif.open(HostBuffer(raw), 'rs', sample_rate=32e6, device=dev,
+                      chunk_nbytes=5 * 8 * 5032) as fh:
+        total = []
+        data = fh.read(on_device=lambda p: total.append(p.shape[0]))
+        assert sum(total) == want.shape[0] and len(total) == 3
+        _same(data.cpu().numpy(), want)
