@@ -15,8 +15,10 @@ the data path); value = total decoded samples / max-over-ranks time.
 Printed JSON line: see the task contract.  Extra keys: `roofline` (decode
 kernel, CUDA-event timed inside the timed region), `cpu_baseline` (numpy
 oracle = port of the reference's CPU path, bounded sample, rank 0 at N=1),
-`e2e` (host pinned buffers -> H2D -> scan+decode -> D2H of the decoded array,
-+ encode round trip -> D2H of the packed payloads; through the public API),
+`e2e` (public API, pinned host buffers on both ends: `read(out=host array,
+on_device=writer.write)` = chunked H2D -> scan+decode -> D2H of the decoded
+samples, with every decoded chunk re-encoded in HBM and its frames copied
+back),
 `clocks`, `gpu_launches`.
 
 `--impl reference` times the reference's own CPU algorithm (the numpy oracle,
