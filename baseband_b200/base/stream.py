@@ -207,7 +207,8 @@ class _Stage:
         self.pin = None
         self.raw = None
         self.dec = None
-        self.done = None          # event: stage's D2H finished
+        self.done = None          # event: stage's D2H (or H2D) finished
+        self.free = None          # event: kernels no longer read ``raw``
 
     def buffers(self, nbytes, nfloat, dev, need_dec):
         if self.pin is None or self.pin.numel() < nbytes:
@@ -534,11 +535,13 @@ class StreamReaderBase(StreamBase):
             got = self._read_raw(f0, nf, pin, s0, ns)
             pin = pin if got is None else got
             with ss.use(0):
-                ss.wait(0, 1)                # raw[k%2] no longer being read
+                # raw[k%2] must no longer be read by the decode of chunk k-2
+                # (only that: the copy overlaps the decode of chunk k-1)
+                ss.wait_event(0, st.free)
                 raw.copy_(pin, non_blocking=True)
                 st.done = ss.event(0)
             with ss.use(1):
-                ss.wait(1, 0)
+                ss.wait_event(1, st.done)
                 piece = flat[row * fps:(row + ns) * fps]
                 if piece.data_ptr() % 16:
                     tmp = torch.empty(ns * fps, dtype=torch.float32,
@@ -549,6 +552,7 @@ class StreamReaderBase(StreamBase):
                     self._decode_chunk(raw, f0, nf, s0, ns, piece)
                 if self._on_device is not None:
                     self._on_device(self._finish(piece, ns))
+                st.free = ss.event(1)
         ss.caller_after(1)
         result = self._finish(flat, count)
         if out is not None and not direct:

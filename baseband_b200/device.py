@@ -137,6 +137,11 @@ class Streams:
         ev.record(self.streams[i])
         return ev
 
+    def wait_event(self, i, ev):
+        """Stream i waits for one recorded event only."""
+        if ev is not None:
+            self.streams[i].wait_event(ev)
+
     def synchronize(self):
         for s in self.streams:
             s.synchronize()

@@ -32,6 +32,9 @@ class _NoStreams:
 
     after_caller = caller_after = lambda self, i: None
 
+    def wait_event(self, i, ev):
+        pass
+
     def event(self, i):
         class _Ev:
             def synchronize(self):
