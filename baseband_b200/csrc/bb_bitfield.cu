@@ -175,6 +175,24 @@ k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
     constexpr int U = (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
         ? Unroll<BPS, MODE>::value : 4;
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+    if (MODE == MODE_RUN && BPS >= 4) {
+        // few float4 per word: keep the loads of several words in flight
+        constexpr int B = BPS == 8 ? 4 : 2;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            EncWordItem<T, BPS> it[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].dst = nullptr;
+                if (item < p.nitems) enc_word_fetch<T, BPS>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b)
+                enc_word_emit<T, BPS, QUANT>(c, it[b]);
+        }
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kBlock;

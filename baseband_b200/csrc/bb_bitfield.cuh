@@ -528,6 +528,60 @@ BB_HD void enc_rowgroup(const EncGeom &p, const QuantConsts<T> &c,
     }
 }
 
+// Vectorised word encode split into fetch (addresses + float4 loads) and
+// emit (quantise, pack, store) so a kernel can have the loads of several words
+// in flight (8- and 4-bit words need only one or two float4 each).
+template <typename T, int BPS>
+struct EncWordItem {
+    Vec4<T> v[(32 / BPS) / 4];
+    uint8_t *dst;                   // null: nothing to do
+};
+
+template <typename T, int BPS>
+BB_HD void enc_word_fetch(const EncGeom &p, uint32_t item,
+                          EncWordItem<T, BPS> &it) {
+    constexpr int CPW = 32 / BPS;
+    uint32_t rest, k, set, slot;
+    p.div_nthread.divmod(item, rest, slot);
+    p.div_nword.divmod(rest, set, k);
+    const long long off = p.unit_offset[set * p.nthread + slot];
+    it.dst = nullptr;
+    if (off < 0) return;
+    it.dst = p.dst + off + 4ull * k;
+    const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
+    const size_t rowlen = (size_t)p.nthread * p.nelem;
+    const size_t set_base = (size_t)set * p.spf * rowlen;
+#pragma unroll
+    for (int m = 0; m < CPW / 4; ++m) {
+        const uint32_t pc = k * CPW + 4 * m;
+        size_t idx;
+        if (p.nthread == 1) {
+            idx = set_base + pc;
+        } else {
+            const uint32_t t = pc >> p.log2_nelem, e = pc & (p.nelem - 1u);
+            idx = set_base + ((size_t)t * p.nthread + slot) * p.nelem + e;
+        }
+        it.v[m] = Vec4<T>::load(in + idx);
+    }
+}
+
+template <typename T, int BPS, int QUANT>
+BB_HD void enc_word_emit(const QuantConsts<T> &c,
+                         const EncWordItem<T, BPS> &it) {
+    constexpr int CPW = 32 / BPS;
+    if (it.dst == nullptr) return;
+    uint32_t w = 0u;
+#pragma unroll
+    for (int m = 0; m < CPW / 4; ++m) {
+        const uint32_t f = quantise<T, BPS, QUANT>(it.v[m].x, c)
+            | (quantise<T, BPS, QUANT>(it.v[m].y, c) << BPS)
+            | (quantise<T, BPS, QUANT>(it.v[m].z, c) << (2 * BPS))
+            | (quantise<T, BPS, QUANT>(it.v[m].w, c) << (3 * BPS));
+        w |= f << (4 * m * BPS);
+    }
+    store_u32(it.dst, w);
+}
+
 // RUN / SCALAR: item = output word index over all units of the launch.
 template <typename T, int BPS, int QUANT, bool VEC>
 BB_HD void enc_word(const EncGeom &p, const QuantConsts<T> &c,
@@ -546,23 +600,10 @@ BB_HD void enc_word(const EncGeom &p, const QuantConsts<T> &c,
     const size_t set_base = (size_t)set * p.spf * rowlen;
     uint32_t w = 0u;
     if (VEC) {
-#pragma unroll
-        for (int m = 0; m < CPW / 4; ++m) {
-            uint32_t pc = k * CPW + 4 * m;
-            size_t idx;
-            if (p.nthread == 1) {
-                idx = set_base + pc;
-            } else {
-                uint32_t t = pc >> p.log2_nelem, e = pc & (p.nelem - 1u);
-                idx = set_base + ((size_t)t * p.nthread + slot) * p.nelem + e;
-            }
-            Vec4<T> v = Vec4<T>::load(in + idx);
-            uint32_t f = quantise<T, BPS, QUANT>(v.x, c)
-                | (quantise<T, BPS, QUANT>(v.y, c) << BPS)
-                | (quantise<T, BPS, QUANT>(v.z, c) << (2 * BPS))
-                | (quantise<T, BPS, QUANT>(v.w, c) << (3 * BPS));
-            w |= f << (4 * m * BPS);
-        }
+        EncWordItem<T, BPS> it;
+        enc_word_fetch<T, BPS>(p, item, it);
+        enc_word_emit<T, BPS, QUANT>(c, it);
+        return;
     } else {
         for (int i = 0; i < CPW; ++i) {
             uint32_t pc = k * CPW + i;
