@@ -155,3 +155,16 @@ def test_bcd_and_crc():
         want = crc_remainder(value, 0x180f)
         got = int(''.join(str((int(c) >> lane) & 1) for c in crc), 2)
         assert got == want
+
+
+def test_guess_format():
+    import baseband_b200 as bb
+    expected = {'sample.vdif': 'vdif', 'sample_vlbi.vdif': 'vdif',
+                'sample_mwa.vdif': 'vdif', 'sample_arochime.vdif': 'vdif',
+                'sample_bps1.vdif': 'vdif', 'sample.m5b': 'mark5b',
+                'sample.m4': 'mark4', 'sample_32track.m4': 'mark4',
+                'sample_16track.m4': 'mark4', 'sample_puppi.raw': 'guppi',
+                'sample.dada': 'dada', 'sample_mkbf.dada': 'dada',
+                'gsb/sample_gsb_rawdump.dat': None}
+    for name, fmt in expected.items():
+        assert bb.guess_format(sample_path(name)) == fmt, name
