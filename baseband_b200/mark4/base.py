@@ -184,18 +184,27 @@ class Mark4StreamReader(StreamReaderBase):
 
 
 def _time_fields(h0, frame_rate, index0, nframe):
-    """BCD time-code fields for frames index0.. relative to ``h0``."""
+    """BCD time-code fields (unit year, day of year, hour, minute, second,
+    millisecond) for frames index0.. relative to ``h0``, vectorised.  Mark 4
+    times sit on a 1.25 ms grid, so everything is done in integer ticks of
+    0.25 ms."""
     from fractions import Fraction
     t0 = h0.time
-    rate = Fraction(frame_rate).limit_denominator(10**9)
-    out = np.empty((nframe, 6), np.int64)
-    for i in range(nframe):
-        t = t0 + Fraction(index0 + i) / rate
-        whole = int(t.sec)
-        ms = float(t.sec - whole) * 1000.
-        out[i] = (t.year % 10, t.yday, whole // 3600, whole // 60 % 60,
-                  whole % 60, int(np.floor(ms + 1e-6)))
-    return out
+    step = Fraction(4000) / Fraction(frame_rate).limit_denominator(10**9)
+    start = t0.sec * 4000
+    if step.denominator != 1 or Fraction(start).denominator != 1:
+        raise ValueError('Mark 4 frame times must lie on the 0.25 ms grid.')
+    ticks = int(start) + int(step) * np.arange(index0, index0 + nframe,
+                                               dtype=np.int64)
+    day, tick = np.divmod(ticks, 86400 * 4000)
+    date = (np.datetime64('1858-11-17') + (t0.mjd + day).astype(
+        'timedelta64[D]'))
+    year = date.astype('datetime64[Y]')
+    yday = (date - year.astype('datetime64[D]')).astype(np.int64) + 1
+    year = year.astype(np.int64) + 1970
+    sec, quarter_ms = np.divmod(tick, 4000)
+    return np.stack([year % 10, yday, sec // 3600, sec // 60 % 60, sec % 60,
+                     quarter_ms // 4], 1)
 
 
 def _time_words(h0, frame_rate, index0, nframe):
