@@ -127,6 +127,7 @@ class Mark4StreamReader(StreamReaderBase):
                             'ref_time to be passed in.')
         fh_raw = Mark4FileReader(fh_raw, ntrack=ntrack, decade=decade,
                                  ref_time=ref_time)
+        fh_raw.seek(0)
         if ntrack is None:
             fh_raw.determine_ntrack()
         offset0 = fh_raw.locate_frame()

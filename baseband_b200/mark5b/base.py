@@ -122,6 +122,7 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
                             'passed in explicitly.')
         fh_raw = Mark5BFileReader(fh_raw, kday=kday, ref_time=ref_time,
                                   nchan=nchan, bps=bps)
+        fh_raw.seek(0)
         offset0 = fh_raw.locate_frame()
         if offset0 is None:
             raise OSError('could not find a Mark 5B frame header.')
