@@ -222,3 +222,43 @@ def oracle_encode(c):
             dst[o:o + c['payload_nbytes']] = np.ascontiguousarray(
                 enc).ravel().view(np.uint8)
     return dst
+
+
+def fuzz_cases(n, seed):
+    """Seeded random decode / encode geometries covering every mode of the
+    planner (thread counts 1-9, 1-16 elements, odd payload sizes, partial
+    sample ranges, invalid units, all codecs)."""
+    rng = np.random.default_rng(seed)
+    dec, enc = [], []
+    for i in range(n):
+        kind = rng.choice(['vdif', 'vdif', 'mark5b', 'sint'])
+        bps = int(rng.choice({'vdif': [1, 2, 4, 8], 'mark5b': [1, 2],
+                              'sint': [4, 8]}[kind]))
+        nthread = int(rng.choice([1, 1, 2, 2, 3, 4, 4, 5, 8, 9]))
+        nelem = int(rng.choice([1, 1, 2, 2, 3, 4, 8, 16]))
+        cplx = bool(nelem % 2 == 0 and rng.random() < 0.4)
+        nset = int(rng.integers(1, 4))
+        # payload: whole 32-bit words holding whole samples
+        bits = bps * nelem
+        unit = bits * 32 // np.gcd(bits, 32)          # lcm(bits, 32) bits
+        payload = int(unit // 8 * rng.integers(1, 40))
+        spf = payload * 8 // bits
+        total = nset * spf
+        if rng.random() < 0.5:
+            start = int(rng.integers(0, total))
+            count = int(rng.integers(1, total - start + 1))
+        else:
+            start, count = 0, None
+        ninv = int(rng.integers(0, 3))
+        invalid = tuple(int(v) for v in rng.choice(
+            nset * nthread, size=min(ninv, nset * nthread), replace=False))
+        fill = float(rng.choice([0.0, -999.0, 2.5]))
+        cid = 'fuzz%d_%s_b%d_t%d_e%d' % (i, kind, bps, nthread, nelem)
+        dec.append(_case(cid, bps, nelem, nthread, nset, payload, cplx=cplx,
+                         kind=kind, start=start, count=count,
+                         invalid=invalid, fill=fill))
+        quant = {'vdif': 'vdif', 'mark5b': 'mark5b', 'sint': 'sint'}[kind]
+        enc.append(_ecase(cid, bps, nelem, nthread, nset, payload,
+                          quant=quant, invalid=invalid,
+                          dtype='f8' if rng.random() < 0.3 else 'f4'))
+    return dec, enc

@@ -294,3 +294,13 @@ def test_quant2_folded_thresholds(emu):
     emu.emu_quant2_check.argtypes = [ctypes.c_int, ctypes.c_int]
     assert emu.emu_quant2_check(0, 200000) == 0
     assert emu.emu_quant2_check(1, 200000) == 0
+
+
+def test_fuzz_bitfield(emu):
+    """Random geometries through the planner + kernel bodies vs the oracle."""
+    from bitfield_cases import fuzz_cases
+    dec, enc = fuzz_cases(120, seed=20260101)
+    for case in dec:
+        test_decode_bitfield(emu, case)
+    for case in enc:
+        test_encode_bitfield(emu, case)

@@ -143,3 +143,14 @@ def test_errors():
     with pytest.raises(TypeError):    # no CPU fallback
         kernels.decode_bitfield(raw.cpu(), off, 1, 1, 64, 2, 1, False, 0,
                                 levels.offset_binary(2))
+
+
+def test_fuzz_bitfield():
+    """400 seeded random geometries (all planner modes, partial ranges,
+    invalid units, both float widths) through the C ABI vs the oracle."""
+    from bitfield_cases import fuzz_cases
+    dec, enc = fuzz_cases(400, seed=20260102)
+    for case in dec:
+        test_decode_bitfield(case)
+    for case in enc:
+        test_encode_bitfield(case)
