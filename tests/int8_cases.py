@@ -54,3 +54,26 @@ def oracle_decode(c, fill=np.nan):
         cb, ce, oc0 = c['col_begin'][u], c['col_end'][u], c['out_col0'][u]
         out[oc0:oc0 + ce - cb] = dec[:, cb:ce].transpose(1, 0, 2)
     return out
+
+
+def fuzz_cases(n, seed):
+    """Random transposed-int8 geometries: odd/even rows (fast and generic
+    kernels), ragged tiles, random column windows."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for i in range(n):
+        nunit = int(rng.integers(1, 4))
+        nrow = int(rng.choice([2, 4, 30, 64, 66, 128, 130, 33, 7]))
+        ncol = int(rng.integers(1, 400))
+        ib = int(rng.choice([1, 2]))
+        if rng.random() < 0.5:
+            windows = None
+        else:
+            windows = []
+            for _ in range(nunit):
+                a = int(rng.integers(0, ncol))
+                b = int(rng.integers(a + 1, ncol + 1))
+                windows.append((a, b))
+        cases.append(('fuzz%d_r%d_c%d_ib%d' % (i, nrow, ncol, ib), nunit, nrow,
+                      ncol, ib, windows))
+    return cases

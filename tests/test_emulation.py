@@ -304,3 +304,8 @@ def test_fuzz_bitfield(emu):
         test_decode_bitfield(emu, case)
     for case in enc:
         test_encode_bitfield(emu, case)
+
+
+def test_fuzz_int8_transposed(emu):
+    for case in int8_cases.fuzz_cases(60, seed=77):
+        test_int8_transposed(emu, case)

@@ -189,3 +189,8 @@ def test_mark5b_scan_sample(sample_outputs):
                                   levels.mark5b(2), fill_value=-999.)
     assert np.array_equal(out.cpu().numpy()[:, 0],
                           stream.mark5b_read(raw, 8, fill_value=-999.))
+
+
+def test_fuzz_int8_transposed():
+    for case in int8_cases.fuzz_cases(150, seed=78):
+        test_int8_transposed(case)
