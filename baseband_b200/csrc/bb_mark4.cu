@@ -9,7 +9,8 @@ namespace bb {
 
 constexpr int kM4Block = 256;
 // one-shot grid, ~64 KiB of output per CTA (see bb_bitfield.cu)
-constexpr int kM4UnrollFast = 4, kM4UnrollVec = 16, kM4UnrollScalar = 16;
+constexpr int kM4UnrollFast = 4, kM4UnrollVec = 16, kM4UnrollScalar = 16,
+    kM4UnrollWarp = 4;
 
 static inline unsigned m4_grid(uint32_t nitems, int unroll) {
     uint64_t per = (uint64_t)kM4Block * unroll;
@@ -29,8 +30,38 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
         __syncthreads();
     }
     constexpr int U = MODE == M4_FAST ? kM4UnrollFast
+        : MODE == M4_WARP ? kM4UnrollWarp
         : MODE == M4_GENERIC_VEC ? kM4UnrollVec : kM4UnrollScalar;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
+    if (MODE == M4_WARP) {
+        __shared__ uint16_t spos[32];
+        __shared__ float slv[4];
+        if (threadIdx.x < 32) spos[threadIdx.x] = p.pos[threadIdx.x];
+        if (threadIdx.x < 4) slv[threadIdx.x] = p.levels[threadIdx.x];
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t w[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t item = item0 + u * kM4Block;
+            ok[u] = item < p.nitems && m4w_load(p, item >> 5, lane, w[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t item = item0 + u * kM4Block;
+            if (item >= p.nitems) break;           // warp uniform
+            const unsigned okmask = __ballot_sync(0xffffffffu, ok[u]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t q = lane + 32u * j;
+                const uint32_t src = m4w_src_lane(p, spos, q);
+                const uint32_t ws = __shfl_sync(0xffffffffu, w[u], src);
+                m4w_emit(p, spos, slv, item >> 5, q, ws, (okmask >> src) & 1u);
+            }
+        }
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kM4Block;
@@ -61,6 +92,9 @@ static int run_decode(const std::vector<M4Launch> &launches, cudaStream_t s) {
         if (l.mode == M4_FAST)
             k_mark4_decode<M4_FAST>
                 <<<m4_grid(n, kM4UnrollFast), kM4Block, 0, s>>>(l.g);
+        else if (l.mode == M4_WARP)
+            k_mark4_decode<M4_WARP>
+                <<<m4_grid(n, kM4UnrollWarp), kM4Block, 0, s>>>(l.g);
         else if (l.mode == M4_GENERIC_VEC)
             k_mark4_decode<M4_GENERIC_VEC>
                 <<<m4_grid(n, kM4UnrollVec), kM4Block, 0, s>>>(l.g);

@@ -37,6 +37,10 @@ struct M4Geom {
     FastDiv div_steps, div_spf;
     uint16_t pos[32];                // sign bit | magnitude bit << 8
     float levels[4];                 // indexed 2*sign + magnitude
+    // WARP mode: the launch seen as 32-bit values, frame after frame
+    uint32_t per_frame32, total32;   // values per frame / in the launch
+    int32_t log2_wordbytes;
+    FastDiv div_frame32;
 };
 
 BB_HD uint32_t m4_reorder32(uint32_t x) {
@@ -138,6 +142,67 @@ BB_HD void m4_dec_generic(const M4Geom &p, uint32_t item) {
     } else {
         p.out[gidx] = m4_dec_element(p, n >> p.log2_nchan, n & (p.nchan - 1u));
     }
+}
+
+// WARP decode, every layout.  A track word of W bytes decodes to W float4
+// that are contiguous in the output, so the launch is one flat run: a warp
+// loads 32 consecutive 32-bit values (128 B coalesced) = 128 float4 of
+// output and each lane stores float4 q = lane + 32 j (j = 0..3) -- 512
+// contiguous bytes per store instruction -- fetching the 32-bit value that
+// holds its four (sign, magnitude) pairs from another lane by shuffle.  The
+// bit positions come from the same table as the GENERIC path (staged in shared
+// memory); all eight bits of a float4 lie in one 32-bit half for the five
+// supported layouts (checked by the planner).
+BB_HD bool m4w_load(const M4Geom &p, uint32_t chunk, uint32_t lane,
+                    uint32_t &w) {
+    w = 0u;
+    const uint32_t g32 = chunk * 32u + lane;
+    if (g32 >= p.total32) return false;
+    uint32_t frame, i32;
+    p.div_frame32.divmod(g32, frame, i32);
+    const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
+    const uint32_t step = (i32 * 4u) >> p.log2_wordbytes;
+    if (off < 0 || step < p.header_steps) return false;
+    w = *reinterpret_cast<const uint32_t *>(
+        p.src + off - (long long)p.header_steps * p.wordbytes + 4ull * i32);
+    return true;
+}
+
+// Lane (within the chunk) holding the bits of float4 q of the chunk.
+BB_HD uint32_t m4w_src_lane(const M4Geom &p, const uint16_t *pos, uint32_t q) {
+    const uint32_t n = q >> p.log2_wordbytes;          // track word in chunk
+    const uint32_t pp = q & (p.wordbytes - 1u);        // float4 within word
+    const uint32_t half = (pos[4u * pp] & 0xffu) >> 5;
+    return ((n << p.log2_wordbytes) >> 2) + half;
+}
+
+BB_HD void m4w_emit(const M4Geom &p, const uint16_t *pos, const float *lv,
+                    uint32_t chunk, uint32_t q, uint32_t w, bool valid) {
+    const uint32_t n = q >> p.log2_wordbytes;
+    const uint32_t pp = q & (p.wordbytes - 1u);
+    const uint32_t half = (pos[4u * pp] & 0xffu) >> 5;
+    if (chunk * 32u + ((n << p.log2_wordbytes) >> 2) + half >= p.total32)
+        return;
+    const long long gidx = p.row_base * (long long)p.nchan
+        + ((long long)chunk * 128 + q) * 4;
+    if (gidx < 0 || gidx >= p.nsample * (long long)p.nchan) return;
+    F4 v;
+    if (valid) {
+        // 16-track words: two words share a 32-bit value
+        const uint32_t base = ((n << p.log2_wordbytes) & 3u) * 8u;
+        float e[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t sm = pos[4u * pp + k];
+            const uint32_t sb = (w >> (((sm & 0xffu) & 31u) + base)) & 1u;
+            const uint32_t mb = (w >> (((sm >> 8) & 31u) + base)) & 1u;
+            e[k] = lv[2u * sb + mb];
+        }
+        v = F4{e[0], e[1], e[2], e[3]};
+    } else {
+        v = F4{p.fill, p.fill, p.fill, p.fill};
+    }
+    *reinterpret_cast<F4 *>(p.out + gidx) = v;
 }
 
 // ------------------------------------------------------------------ encode

@@ -6,7 +6,7 @@
 
 namespace bb {
 
-enum { M4_FAST = 0, M4_GENERIC_VEC = 1, M4_GENERIC_SCALAR = 2 };
+enum { M4_FAST = 0, M4_GENERIC_VEC = 1, M4_GENERIC_SCALAR = 2, M4_WARP = 3 };
 
 struct M4Launch { int mode; M4Geom g; };
 
@@ -89,6 +89,36 @@ inline bool m4_is_fast(int nchan, int fanout, int ft) {
     return !ft && fanout == 4 && (nchan == 4 || nchan == 8);
 }
 
+// Decode: the per-half-word FAST path only where a row is >= 32 bytes (8
+// channels); the 4-channel layout stores 16-byte pieces 64 bytes apart there
+// and is faster through the WARP path.
+inline bool m4_dec_fast(int nchan, int fanout, int ft) {
+    return !ft && fanout == 4 && nchan == 8;
+}
+
+// WARP decode needs the 8 bits of every output float4 inside one 32-bit half
+// of the track word.
+inline bool m4_warp_ok(const M4Geom &g) {
+    const int n = g.fanout * g.nchan;
+    if (n % 4) return false;
+    for (int i = 0; i < n; i += 4) {
+        const int half = (g.pos[i] & 0xff) >> 5;
+        for (int k = 0; k < 4; ++k)
+            if (((g.pos[i + k] & 0xff) >> 5) != half
+                || ((g.pos[i + k] >> 8) >> 5) != half)
+                return false;
+    }
+    return true;
+}
+
+inline void m4_warp_geom(M4Geom &g, uint32_t nframe) {
+    g.log2_wordbytes = ilog2_exact(g.wordbytes);
+    g.per_frame32 = g.steps * g.wordbytes / 4;
+    g.total32 = g.per_frame32 * nframe;
+    g.div_frame32 = make_fastdiv(g.per_frame32);
+    g.nitems = (g.total32 + 31u) / 32u * 32u;         // lanes, whole warps
+}
+
 // Frames API.  steps = 20000, header_steps = 160.
 inline bool plan_m4_frames(bool encode, const void *src_or_dst,
                            const int64_t *unit_offset, int64_t nframe,
@@ -108,14 +138,16 @@ inline bool plan_m4_frames(bool encode, const void *src_or_dst,
     if (nsample == 0 || nframe == 0) return true;
     int mode;
     uint64_t per_frame;
-    if (m4_is_fast(nchan, fanout, ft)) {
+    if (encode ? m4_is_fast(nchan, fanout, ft)
+               : m4_dec_fast(nchan, fanout, ft)) {
         mode = M4_FAST;
         per_frame = (uint64_t)steps * (base.wordbytes / 4);
     } else if (encode) {
         mode = M4_GENERIC_SCALAR;              // one item per track word
         per_frame = steps;
     } else if ((sample_start * nchan) % 4 == 0 && (nsample * nchan) % 4 == 0) {
-        mode = M4_GENERIC_VEC;
+        mode = (m4_warp_ok(base) && ((uintptr_t)src_or_dst & 3u) == 0)
+            ? M4_WARP : M4_GENERIC_VEC;
         per_frame = (uint64_t)spf * nchan / 4;
     } else {
         mode = M4_GENERIC_SCALAR;
@@ -141,6 +173,7 @@ inline bool plan_m4_frames(bool encode, const void *src_or_dst,
         g.nitems = (uint32_t)(per_frame * (uint64_t)(f1 - f0));
         g.div_steps = make_fastdiv(steps);
         g.div_spf = make_fastdiv((uint32_t)spf);
+        if (mode == M4_WARP) m4_warp_geom(g, g.nframe);
         launches.push_back({mode, g});
     }
     return true;
@@ -171,12 +204,17 @@ inline bool plan_m4_words(bool encode, const void *words, int64_t nword,
         g.div_steps = make_fastdiv((uint32_t)n);
         g.div_spf = make_fastdiv((uint32_t)(n * fanout));
         int mode;
-        if (m4_is_fast(nchan, fanout, ft)) {
+        if (encode ? m4_is_fast(nchan, fanout, ft)
+                   : m4_dec_fast(nchan, fanout, ft)) {
             mode = M4_FAST;
             g.nitems = (uint32_t)(n * (base.wordbytes / 4));
         } else if (encode) {
             mode = M4_GENERIC_SCALAR;
             g.nitems = (uint32_t)n;
+        } else if (m4_warp_ok(g) && (n * base.wordbytes) % 4 == 0
+                   && ((uintptr_t)g.src & 3u) == 0) {
+            mode = M4_WARP;
+            m4_warp_geom(g, 1);
         } else {
             mode = M4_GENERIC_VEC;             // fanout*nchan % 4 == 0 always
             g.nitems = (uint32_t)(n * fanout * nchan / 4);

@@ -18,6 +18,20 @@ static void run_dec(const std::vector<M4Launch> &launches) {
             int code = which ? (entry >> 2) : (entry & 3);
             lut[i] = l.g.levels[2 * (code & 1) + (code >> 1)];
         }
+        if (l.mode == M4_WARP) {
+            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
+                uint32_t w[32];
+                bool ok[32];
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    ok[lane] = m4w_load(l.g, chunk, lane, w[lane]);
+                for (uint32_t q = 0; q < 128; ++q) {
+                    uint32_t src = m4w_src_lane(l.g, l.g.pos, q);
+                    m4w_emit(l.g, l.g.pos, l.g.levels, chunk, q, w[src],
+                             ok[src]);
+                }
+            }
+            continue;
+        }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == M4_FAST) m4_dec_fast(l.g, lut, item);
             else if (l.mode == M4_GENERIC_VEC) m4_dec_generic<true>(l.g, item);
