@@ -34,12 +34,10 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
         : MODE == M4_GENERIC_VEC ? kM4UnrollVec : kM4UnrollScalar;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
     if (MODE == M4_WARP) {
-        __shared__ uint16_t spos[32];
-        __shared__ float slv[4];
-        if (threadIdx.x < 32) spos[threadIdx.x] = p.pos[threadIdx.x];
-        if (threadIdx.x < 4) slv[threadIdx.x] = p.levels[threadIdx.x];
-        __syncthreads();
         const uint32_t lane = threadIdx.x & 31u;
+        const M4Lane lc = m4w_lane(p, p.pos, lane);
+        const float lv[4] = {p.levels[0], p.levels[1], p.levels[2],
+                             p.levels[3]};
         uint32_t w[U];
         bool ok[U];
 #pragma unroll
@@ -55,9 +53,9 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t q = lane + 32u * j;
-                const uint32_t src = m4w_src_lane(p, spos, q);
+                const uint32_t src = m4w_src_lane(p, lc, q);
                 const uint32_t ws = __shfl_sync(0xffffffffu, w[u], src);
-                m4w_emit(p, spos, slv, item >> 5, q, ws, (okmask >> src) & 1u);
+                m4w_emit(p, lc, lv, item >> 5, q, ws, (okmask >> src) & 1u);
             }
         }
         return;

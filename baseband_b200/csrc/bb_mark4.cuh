@@ -168,35 +168,49 @@ BB_HD bool m4w_load(const M4Geom &p, uint32_t chunk, uint32_t lane,
     return true;
 }
 
-// Lane (within the chunk) holding the bits of float4 q of the chunk.
-BB_HD uint32_t m4w_src_lane(const M4Geom &p, const uint16_t *pos, uint32_t q) {
-    const uint32_t n = q >> p.log2_wordbytes;          // track word in chunk
-    const uint32_t pp = q & (p.wordbytes - 1u);        // float4 within word
-    const uint32_t half = (pos[4u * pp] & 0xffu) >> 5;
-    return ((n << p.log2_wordbytes) >> 2) + half;
+// Since the word size W divides 32, float4 q = lane + 32 j sits at the same
+// position q % W of its track word for every j: the eight bit positions a
+// lane needs are loop invariant.
+struct M4Lane {
+    uint32_t sbit[4], mbit[4];      // shifts inside the 32-bit value
+    uint32_t half;                  // which 32-bit half of a 64-track word
+};
+
+BB_HD M4Lane m4w_lane(const M4Geom &p, const uint16_t *pos, uint32_t lane) {
+    M4Lane c;
+    const uint32_t pp = lane & (p.wordbytes - 1u);     // float4 within word
+    // 16-track words: two words share a 32-bit value
+    const uint32_t base = (((lane >> p.log2_wordbytes) << p.log2_wordbytes)
+                           & 3u) * 8u;
+    c.half = (pos[4u * pp] & 0xffu) >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t sm = pos[4u * pp + k];
+        c.sbit[k] = ((sm & 0xffu) & 31u) + base;
+        c.mbit[k] = ((sm >> 8) & 31u) + base;
+    }
+    return c;
 }
 
-BB_HD void m4w_emit(const M4Geom &p, const uint16_t *pos, const float *lv,
+// Lane (within the chunk) holding the bits of float4 q of the chunk.
+BB_HD uint32_t m4w_src_lane(const M4Geom &p, const M4Lane &c, uint32_t q) {
+    const uint32_t n = q >> p.log2_wordbytes;          // track word in chunk
+    return ((n << p.log2_wordbytes) >> 2) + c.half;
+}
+
+BB_HD void m4w_emit(const M4Geom &p, const M4Lane &c, const float lv[4],
                     uint32_t chunk, uint32_t q, uint32_t w, bool valid) {
-    const uint32_t n = q >> p.log2_wordbytes;
-    const uint32_t pp = q & (p.wordbytes - 1u);
-    const uint32_t half = (pos[4u * pp] & 0xffu) >> 5;
-    if (chunk * 32u + ((n << p.log2_wordbytes) >> 2) + half >= p.total32)
-        return;
+    if (chunk * 32u + m4w_src_lane(p, c, q) >= p.total32) return;
     const long long gidx = p.row_base * (long long)p.nchan
         + ((long long)chunk * 128 + q) * 4;
     if (gidx < 0 || gidx >= p.nsample * (long long)p.nchan) return;
     F4 v;
     if (valid) {
-        // 16-track words: two words share a 32-bit value
-        const uint32_t base = ((n << p.log2_wordbytes) & 3u) * 8u;
         float e[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t sm = pos[4u * pp + k];
-            const uint32_t sb = (w >> (((sm & 0xffu) & 31u) + base)) & 1u;
-            const uint32_t mb = (w >> (((sm >> 8) & 31u) + base)) & 1u;
-            e[k] = lv[2u * sb + mb];
+            const bool sb = (w >> c.sbit[k]) & 1u, mb = (w >> c.mbit[k]) & 1u;
+            e[k] = sb ? (mb ? lv[3] : lv[2]) : (mb ? lv[1] : lv[0]);
         }
         v = F4{e[0], e[1], e[2], e[3]};
     } else {

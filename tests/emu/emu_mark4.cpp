@@ -25,9 +25,9 @@ static void run_dec(const std::vector<M4Launch> &launches) {
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     ok[lane] = m4w_load(l.g, chunk, lane, w[lane]);
                 for (uint32_t q = 0; q < 128; ++q) {
-                    uint32_t src = m4w_src_lane(l.g, l.g.pos, q);
-                    m4w_emit(l.g, l.g.pos, l.g.levels, chunk, q, w[src],
-                             ok[src]);
+                    const M4Lane lc = m4w_lane(l.g, l.g.pos, q & 31u);
+                    uint32_t src = m4w_src_lane(l.g, lc, q);
+                    m4w_emit(l.g, lc, l.g.levels, chunk, q, w[src], ok[src]);
                 }
             }
             continue;
