@@ -80,6 +80,7 @@ k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
         const uint32_t item = item0 + u * kM4Block;
         if (item >= p.nitems) break;
         if (MODE == M4_FAST) m4_enc_fast<T>(p, c, item);
+        else if (MODE == M4_HALF) m4_enc_half<T>(p, c, item);
         else m4_enc_generic<T>(p, c, item);
     }
 }
@@ -111,6 +112,8 @@ static int run_encode(const std::vector<M4Launch> &launches, cudaStream_t s) {
         unsigned grid = m4_grid(l.g.nitems, kM4UnrollFast);
         if (l.mode == M4_FAST)
             k_mark4_encode<T, M4_FAST><<<grid, kM4Block, 0, s>>>(l.g, consts);
+        else if (l.mode == M4_HALF)
+            k_mark4_encode<T, M4_HALF><<<grid, kM4Block, 0, s>>>(l.g, consts);
         else
             k_mark4_encode<T, M4_GENERIC_SCALAR>
                 <<<grid, kM4Block, 0, s>>>(l.g, consts);

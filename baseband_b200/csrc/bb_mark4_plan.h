@@ -6,7 +6,8 @@
 
 namespace bb {
 
-enum { M4_FAST = 0, M4_GENERIC_VEC = 1, M4_GENERIC_SCALAR = 2, M4_WARP = 3 };
+enum { M4_FAST = 0, M4_GENERIC_VEC = 1, M4_GENERIC_SCALAR = 2, M4_WARP = 3,
+       M4_HALF = 4 };
 
 struct M4Launch { int mode; M4Geom g; };
 
@@ -142,6 +143,11 @@ inline bool plan_m4_frames(bool encode, const void *src_or_dst,
                : m4_dec_fast(nchan, fanout, ft)) {
         mode = M4_FAST;
         per_frame = (uint64_t)steps * (base.wordbytes / 4);
+    } else if (encode && m4_warp_ok(base)
+               && ((uintptr_t)src_or_dst & 3u) == 0
+               && ((uintptr_t)in & 15u) == 0) {
+        mode = M4_HALF;                        // one item per 32-bit value
+        per_frame = (uint64_t)steps * base.wordbytes / 4;
     } else if (encode) {
         mode = M4_GENERIC_SCALAR;              // one item per track word
         per_frame = steps;
@@ -174,6 +180,10 @@ inline bool plan_m4_frames(bool encode, const void *src_or_dst,
         g.div_steps = make_fastdiv(steps);
         g.div_spf = make_fastdiv((uint32_t)spf);
         if (mode == M4_WARP) m4_warp_geom(g, g.nframe);
+        if (mode == M4_HALF) {
+            m4_warp_geom(g, g.nframe);
+            g.nitems = g.total32;
+        }
         launches.push_back({mode, g});
     }
     return true;
@@ -208,6 +218,12 @@ inline bool plan_m4_words(bool encode, const void *words, int64_t nword,
                    : m4_dec_fast(nchan, fanout, ft)) {
             mode = M4_FAST;
             g.nitems = (uint32_t)(n * (base.wordbytes / 4));
+        } else if (encode && m4_warp_ok(g) && (n * base.wordbytes) % 4 == 0
+                   && ((uintptr_t)g.src & 3u) == 0
+                   && ((uintptr_t)in & 15u) == 0) {
+            mode = M4_HALF;
+            m4_warp_geom(g, 1);
+            g.nitems = g.total32;
         } else if (encode) {
             mode = M4_GENERIC_SCALAR;
             g.nitems = (uint32_t)n;
