@@ -75,12 +75,17 @@ __global__ void __launch_bounds__(kM4Block)
 k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
     constexpr int U = kM4UnrollFast;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
+    __shared__ uint16_t spos[32];
+    if (MODE == M4_HALF) {
+        if (threadIdx.x < 32) spos[threadIdx.x] = p.pos[threadIdx.x];
+        __syncthreads();
+    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kM4Block;
         if (item >= p.nitems) break;
         if (MODE == M4_FAST) m4_enc_fast<T>(p, c, item);
-        else if (MODE == M4_HALF) m4_enc_half<T>(p, c, item);
+        else if (MODE == M4_HALF) m4_enc_half<T>(p, spos, c, item);
         else m4_enc_generic<T>(p, c, item);
     }
 }

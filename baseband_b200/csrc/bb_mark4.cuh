@@ -40,6 +40,7 @@ struct M4Geom {
     // WARP mode: the launch seen as 32-bit values, frame after frame
     uint32_t per_frame32, total32;   // values per frame / in the launch
     int32_t log2_wordbytes;
+    uint8_t psel[8];                 // 64-track: float4 positions of half 0, 1
     FastDiv div_frame32;
 };
 
@@ -288,51 +289,61 @@ BB_HD void m4_enc_generic(const M4Geom &p, const QuantConsts<T> &c,
 // 32 bytes apart for the 64-track layouts -- loaded as vectors; sign and
 // magnitude bits are placed with the per-layout table.  Stores are 128
 // contiguous bytes per warp.
-template <typename T>
-BB_HD void m4_enc_half(const M4Geom &p, const QuantConsts<T> &c,
-                       uint32_t item) {
+template <typename T, int W>
+BB_HD void m4_enc_half_w(const M4Geom &p, const uint16_t *pos,
+                         const QuantConsts<T> &c, uint32_t item) {
     if (item >= p.total32) return;
     uint32_t frame, i32;
     p.div_frame32.divmod(item, frame, i32);
     const long long off = p.unit_offset ? p.unit_offset[frame] : 0;
-    const uint32_t step = (i32 * 4u) >> p.log2_wordbytes;
+    const uint32_t step = W == 8 ? i32 >> 1 : W == 4 ? i32 : i32 << 1;
     if (off < 0 || step < p.header_steps) return;
-    const uint32_t W = p.wordbytes;
     // first track word of this value, counted over the launch
     const size_t word0 = (size_t)frame * p.steps + step;
     const uint32_t h = W == 8 ? (i32 & 1u) : 0u;
     const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
-    uint32_t out = 0u;
-    uint32_t found = 0u;                     // float4 of this half taken so far
-#pragma unroll 1
-    for (uint32_t m = 0; m < (W == 8 ? 8u : 4u); ++m) {
-        // m-th float4 candidate: (word, position in word, bit base)
+    T v[4][4];
+    uint32_t pps[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        // m-th float4 of this value: (word, position in word)
         const uint32_t wsel = W == 2 ? (m >> 1) : 0u;
-        const uint32_t pp = W == 2 ? (m & 1u) : m;
-        if (W == 8 && ((p.pos[4u * pp] & 0xffu) >> 5) != h) continue;
-        const uint32_t base = W == 2 ? 16u * wsel : 0u;
-        T v[4];
-        const T *q = in + ((word0 + wsel) * W + pp) * 4;
+        pps[m] = W == 2 ? (m & 1u) : W == 4 ? (uint32_t)m
+                                            : (uint32_t)p.psel[4u * h + m];
+        const T *q = in + ((word0 + wsel) * W + pps[m]) * 4;
         if (sizeof(T) == 4) {
             F4 r = *reinterpret_cast<const F4 *>(q);
-            v[0] = (T)r.x; v[1] = (T)r.y; v[2] = (T)r.z; v[3] = (T)r.w;
+            v[m][0] = (T)r.x; v[m][1] = (T)r.y; v[m][2] = (T)r.z;
+            v[m][3] = (T)r.w;
         } else {
             D2 a = reinterpret_cast<const D2 *>(q)[0];
             D2 b = reinterpret_cast<const D2 *>(q)[1];
-            v[0] = (T)a.x; v[1] = (T)a.y; v[2] = (T)b.x; v[3] = (T)b.y;
+            v[m][0] = (T)a.x; v[m][1] = (T)a.y; v[m][2] = (T)b.x;
+            v[m][3] = (T)b.y;
         }
+    }
+    uint32_t out = 0u;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const uint32_t base = W == 2 ? 16u * (m >> 1) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t code = quantise<T, 2, QUANT_OFFSET>(v[k], c);
-            const uint32_t sm = p.pos[4u * pp + k];
+            const uint32_t code = quantise<T, 2, QUANT_OFFSET>(v[m][k], c);
+            const uint32_t sm = pos[4u * pps[m] + k];
             out |= (code >> 1) << (((sm & 0xffu) & 31u) + base);
             out |= (code & 1u) << (((sm >> 8) & 31u) + base);
         }
-        ++found;
     }
-    (void)found;
     *reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(p.src) + off
         - (long long)p.header_steps * W + 4ull * i32) = out;
+}
+
+template <typename T>
+BB_HD void m4_enc_half(const M4Geom &p, const uint16_t *pos,
+                       const QuantConsts<T> &c, uint32_t item) {
+    if (p.wordbytes == 8) m4_enc_half_w<T, 8>(p, pos, c, item);
+    else if (p.wordbytes == 4) m4_enc_half_w<T, 4>(p, pos, c, item);
+    else m4_enc_half_w<T, 2>(p, pos, c, item);
 }
 
 }  // namespace bb

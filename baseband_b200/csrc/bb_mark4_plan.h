@@ -118,6 +118,14 @@ inline void m4_warp_geom(M4Geom &g, uint32_t nframe) {
     g.total32 = g.per_frame32 * nframe;
     g.div_frame32 = make_fastdiv(g.per_frame32);
     g.nitems = (g.total32 + 31u) / 32u * 32u;         // lanes, whole warps
+    for (int i = 0; i < 8; ++i) g.psel[i] = (uint8_t)(i & 3);
+    if (g.wordbytes == 8) {
+        int n[2] = {0, 0};
+        for (int pp = 0; pp < 8; ++pp) {
+            const int half = (g.pos[4 * pp] & 0xff) >> 5;
+            if (n[half] < 4) g.psel[4 * half + n[half]++] = (uint8_t)pp;
+        }
+    }
 }
 
 // Frames API.  steps = 20000, header_steps = 160.

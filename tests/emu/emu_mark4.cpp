@@ -46,7 +46,7 @@ static void run_enc(const std::vector<M4Launch> &launches) {
     for (const M4Launch &l : launches)
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == M4_FAST) m4_enc_fast<T>(l.g, c, item);
-            else if (l.mode == M4_HALF) m4_enc_half<T>(l.g, c, item);
+            else if (l.mode == M4_HALF) m4_enc_half<T>(l.g, l.g.pos, c, item);
             else m4_enc_generic<T>(l.g, c, item);
         }
 }
