@@ -69,3 +69,16 @@ class Mark4Payload(PayloadBase):
         self = cls(words, header)
         self[:] = data
         return self
+
+    def todevice(self, device=None):
+        """Decoded payload as a CUDA tensor (nsample, nchan) float32."""
+        from .. import device as _device
+        from .. import kernels, levels
+        dev = _device.resolve(device)
+        try:
+            nchan, fanout, ft = codecs._M4_MODES[self._coder]
+        except KeyError:
+            raise KeyError(self._coder) from None
+        raw = _device.upload(self.words, dev)
+        return kernels.mark4_decode_words(raw, self.words.size, nchan, fanout,
+                                          ft, levels.sign_magnitude())

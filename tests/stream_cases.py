@@ -872,3 +872,33 @@ def vdif_on_device_hook(dev):
         data = fh.read(on_device=lambda p: total.append(p.shape[0]))
         assert sum(total) == want.shape[0] and len(total) == 3
         _same(data.cpu().numpy(), want)
+
+
+def payload_todevice(dev):
+    """``Payload.todevice()`` / ``FrameSet.todevice()``: decoded samples as a
+    tensor on the GPU for every format's payload class."""
+    with bb.vdif.open(sample_path('sample.vdif'), 'rb') as fh:
+        fs = fh.read_frameset()
+    t = fs.todevice(dev)
+    assert isinstance(t, torch.Tensor) and tuple(t.shape) == (20000, 8, 1)
+    _same(t.cpu().numpy(), OUT['sample_vdif_data'][:20000])
+    _same(fs.frames[2].payload.todevice(dev).cpu().numpy(),
+          OUT['sample_vdif_data'][:20000, 2])
+    with bb.mark5b.open(sample_path('sample.m5b'), 'rb', kday=56000,
+                        nchan=8) as fh:
+        frame = fh.read_frame()
+    _same(frame.payload.todevice(dev).cpu().numpy(),
+          OUT['sample_m5b_data'][:5000])
+    with bb.mark4.open(sample_path('sample.m4'), 'rb', ntrack=64,
+                       decade=2010) as fh:
+        fh.locate_frame()
+        frame = fh.read_frame()
+    _same(frame.payload.todevice(dev).cpu().numpy(),
+          OUT['sample_m4_data'][640:80000])
+    with bb.guppi.open(sample_path('sample_puppi.raw'), 'rb') as fh:
+        frame = fh.read_frame(memmap=False)
+    _same(frame.payload.todevice(dev).cpu().numpy(),
+          OUT['sample_puppi_frames'][0])
+    with bb.dada.open(sample_path('sample.dada'), 'rb') as fh:
+        frame = fh.read_frame(memmap=False)
+    _same(frame.payload.todevice(dev).cpu().numpy(), OUT['sample_dada_data'])

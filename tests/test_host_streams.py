@@ -15,7 +15,7 @@ def backend(monkeypatch):
 
 CASES = [n for n in dir(stream_cases)
          if n.split('_')[0] in ('vdif', 'mark5b', 'mark4', 'guppi', 'dada',
-                                'gsb', 'shard')
+                                'gsb', 'shard', 'payload')
          and callable(getattr(stream_cases, n))]
 
 
