@@ -74,19 +74,28 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         return;
     }
     if (MODE == MODE_WORDROW4) {
+        // The four slot words of every lane go through shared memory (one
+        // STS.128 per lane and chunk); a row then costs one LDS.128 instead
+        // of five shuffles.
         constexpr int TPW = 32 / BPS;
         constexpr int WB = U < 2 ? U : 2;         // chunks loaded up front
-        const uint32_t lane = threadIdx.x & 31u;
+        __shared__ __align__(16) uint32_t wbuf[kBlock / 32][WB][32][4];
+        __shared__ uint32_t okbuf[kBlock / 32][WB][32];
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll 1
         for (int u0 = 0; u0 < U; u0 += WB) {
-            uint32_t w[WB][4], ok[WB];
+            __syncwarp();                         // previous batch consumed
 #pragma unroll
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
-                ok[b] = 0u;
-                w[b][0] = w[b][1] = w[b][2] = w[b][3] = 0u;
-                if (item < p.nitems) ok[b] = wrow_load(p, item >> 5, lane, w[b]);
+                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                uint32_t ok = 0u;
+                if (item < p.nitems) ok = wrow_load(p, item >> 5, lane, w);
+                *reinterpret_cast<uint4 *>(wbuf[warp][b][lane]) =
+                    make_uint4(w[0], w[1], w[2], w[3]);
+                okbuf[warp][b][lane] = ok;
             }
+            __syncwarp();
 #pragma unroll
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
@@ -94,12 +103,11 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 #pragma unroll
                 for (int j = 0; j < TPW; ++j) {
                     const uint32_t src = wrow_src_lane<BPS>(lane, j);
-                    uint32_t ws[4];
-#pragma unroll
-                    for (int s4 = 0; s4 < 4; ++s4)
-                        ws[s4] = __shfl_sync(0xffffffffu, w[b][s4], src);
-                    const uint32_t oks = __shfl_sync(0xffffffffu, ok[b], src);
-                    wrow_emit<BPS, CODEC>(p, lut, item >> 5, lane, j, ws, oks);
+                    const uint4 v = *reinterpret_cast<const uint4 *>(
+                        wbuf[warp][b][src]);
+                    const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+                    wrow_emit<BPS, CODEC>(p, lut, item >> 5, lane, j, ws,
+                                          okbuf[warp][b][src]);
                 }
             }
         }
