@@ -62,8 +62,12 @@ class VDIFFrame(FrameBase):
     @classmethod
     def from_mark5b_frame(cls, mark5b_frame, verify=True, **kwargs):
         """Wrap a Mark 5B frame as VDIF EDV 0xab (vdif/frame.py:104-128)."""
+        from ..timeutil import Time
         m5h = mark5b_frame.header
-        kwargs.update(edv=0xab, time=m5h.time, bps=mark5b_frame.payload.bps,
+        # whole seconds go into the VDIF time code; the position within the
+        # second is the Mark 5B frame number (vdif/header.py:799-843)
+        whole = Time(m5h.kday + m5h.jday, m5h.seconds)
+        kwargs.update(edv=0xab, time=whole, bps=mark5b_frame.payload.bps,
                       nchan=mark5b_frame.payload.sample_shape[0],
                       complex_data=False)
         header = VDIFHeader.fromvalues(verify=False, **kwargs)

@@ -902,3 +902,27 @@ def payload_todevice(dev):
     with bb.dada.open(sample_path('sample.dada'), 'rb') as fh:
         frame = fh.read_frame(memmap=False)
     _same(frame.payload.todevice(dev).cpu().numpy(), OUT['sample_dada_data'])
+
+
+def vdif_mark5b_payload_edv_ab():
+    """Mark 5B frames wrapped in VDIF EDV 0xab keep the Mark 5B codec
+    (vdif/payload.py:151-154, tests/test_conversion.py in the reference)."""
+    want = OUT['sample_m5b_data']
+    buf = io.BytesIO()
+    with bb.mark5b.open(sample_path('sample.m5b'), 'rb', kday=56000,
+                        nchan=8) as fh:
+        for _ in range(4):
+            m5f = fh.read_frame()
+            vf = bb.vdif.VDIFFrame.from_mark5b_frame(m5f, verify=False)
+            assert vf.header.edv == 0xab and vf.header.nchan == 8
+            vf.tofile(buf)
+    raw = buf.getvalue()
+    assert len(raw) == 4 * 10032
+    with bb.vdif.open(io.BytesIO(raw), 'rs', sample_rate=32e6) as fv:
+        assert fv.shape == (20000, 8)
+        assert fv.header0['mark5b_frame_nr'] == 0
+        _same(fv.read(), want)
+    frame = bb.vdif.VDIFFrame.fromfile(io.BytesIO(raw))
+    _same(frame.data, want[:5000])
+    pl = bb.vdif.VDIFPayload.fromdata(want[:5000], frame.header)
+    assert np.array_equal(pl.words, frame.payload.words)
