@@ -11,7 +11,7 @@ the header ("Config / flag system").
 import io
 import os
 
-__all__ = ['make_opener', 'normalize_mode']
+__all__ = ['make_opener', 'make_info', 'normalize_mode']
 
 COMMON_NON_HEADER = {'squeeze', 'subset', 'fill_value', 'verify',
                      'file_size', 'device', 'chunk_nbytes'}
@@ -66,3 +66,51 @@ def make_opener(fmt, classes, header_class=None, non_header_keys=(),
     open.__name__ = 'open'
     open.__doc__ = doc or 'Open a {} file for reading or writing.'.format(fmt)
     return open
+
+
+class FormatInfo:
+    """Minimal stand-in for the reference's ``info`` objects
+    (baseband/base/file_info.py): truthy if the file looks like ``format``;
+    for readable streams also carries the basic stream properties."""
+
+    def __init__(self, format, ok, **attrs):
+        self.format = format if ok else None
+        self._ok = bool(ok)
+        self.__dict__.update(attrs)
+
+    def __bool__(self):
+        return self._ok
+
+    def __repr__(self):
+        keys = [k for k in self.__dict__ if not k.startswith('_')]
+        return '\n'.join('{} = {}'.format(k, getattr(self, k)) for k in keys)
+
+
+def make_info(fmt):
+    """``info(name, **kwargs)`` for a format module: the entry-point group
+    ``baseband.io`` expects ``open`` and ``info`` (io/__init__.py:139-154)."""
+
+    def info(name, **kwargs):
+        from .. import guess_format
+        try:
+            ok = guess_format(name) == fmt
+        except (OSError, TypeError):
+            ok = False
+        attrs = {}
+        if ok:
+            import importlib
+            module = importlib.import_module('baseband_b200.' + fmt)
+            try:
+                with module.open(name, 'rs', **kwargs) as fh:
+                    attrs = dict(sample_rate=fh.sample_rate,
+                                 sample_shape=tuple(fh.sample_shape),
+                                 samples_per_frame=fh.samples_per_frame,
+                                 bps=fh.bps, complex_data=fh.complex_data,
+                                 shape=fh.shape, start_time=fh.start_time,
+                                 stop_time=fh.stop_time, readable=True)
+            except Exception as exc:     # needs more arguments, e.g. nchan
+                attrs = dict(readable=False, errors={'open': str(exc)})
+        return FormatInfo(fmt, ok, **attrs)
+
+    info.__name__ = 'info'
+    return info

@@ -168,3 +168,20 @@ def test_guess_format():
                 'gsb/sample_gsb_rawdump.dat': None}
     for name, fmt in expected.items():
         assert bb.guess_format(sample_path(name)) == fmt, name
+
+
+def test_plugin_protocol():
+    """Every format module offers what the reference's ``baseband.io`` entry
+    points need: ``open`` and (except GSB, which has no file signature)
+    ``info`` that is truthy only for its own format."""
+    import importlib
+    import baseband_b200 as bb
+    for fmt in bb.FORMATS:
+        module = importlib.import_module('baseband_b200.' + fmt)
+        assert callable(module.open)
+    assert bb.vdif.info(sample_path('sample.vdif'))
+    assert not bb.vdif.info(sample_path('sample.m5b'))
+    assert not bb.mark5b.info(sample_path('sample.vdif'))
+    m5 = bb.mark5b.info(sample_path('sample.m5b'))
+    assert m5 and m5.format == 'mark5b' and m5.readable is False  # needs nchan
+    assert bb.dada.info(sample_path('sample.dada')).format == 'dada'
