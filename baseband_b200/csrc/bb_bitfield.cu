@@ -24,6 +24,18 @@ struct Unroll {
     static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
 };
 
+// Encode: ROWGROUP as decode; ROWWORD sized so a warp reads ~8 KiB of rows
+// per chunk and a CTA ~64 KiB; word-per-thread modes take 4 words.
+template <int BPS, int MODE>
+struct EncUnroll {
+    static constexpr int kTpw = MODE == MODE_ROWWORD4 ? 32 / BPS : 16 / BPS;
+    static constexpr int value =
+        (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
+        ? Unroll<BPS, MODE>::value
+        : (MODE == MODE_ROWWORD4 || MODE == MODE_ROWWORD2)
+        ? (kTpw >= 16 ? 1 : 16 / kTpw) : 4;
+};
+
 inline unsigned tile_grid(uint32_t nitems, int unroll) {
     uint64_t per_cta = (uint64_t)kBlock * unroll;
     return (unsigned)((nitems + per_cta - 1) / per_cta);
@@ -180,9 +192,25 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 template <typename T, int BPS, int QUANT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
-    constexpr int U = (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
-        ? Unroll<BPS, MODE>::value : 4;
+    constexpr int U = EncUnroll<BPS, MODE>::value;
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+    if (MODE == MODE_ROWWORD4 || MODE == MODE_ROWWORD2) {
+        // kBlock and nitems are multiples of 32: chunks are warp uniform.
+        constexpr int G = MODE == MODE_ROWWORD4 ? 4 : 2;
+        constexpr int TPW = (32 / BPS) / (4 / G);
+        __shared__ uint32_t cbuf[kBlock / 32][32 * TPW];
+        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            const uint32_t item = item0 + u * kBlock;
+            if (item >= p.nitems) break;
+            rw_stage<T, BPS, QUANT, G>(p, c, item >> 5, lane, cbuf[warp]);
+            __syncwarp();
+            rw_emit<BPS, G>(p, item >> 5, lane, cbuf[warp]);
+            __syncwarp();                         // before the buffer is reused
+        }
+        return;
+    }
     if (MODE == MODE_RUN && BPS >= 4) {
         // few float4 per word: keep the loads of several words in flight
         constexpr int B = BPS == 8 ? 4 : 2;
@@ -277,6 +305,16 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
             k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP2>
                 <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP2>::value), kBlock, 0,
                    stream>>>(l.g, consts);
+            break;
+        case MODE_ROWWORD4:
+            k_encode_bitfield<T, BPS, QUANT, MODE_ROWWORD4>
+                <<<tile_grid(n, EncUnroll<BPS, MODE_ROWWORD4>::value), kBlock,
+                   0, stream>>>(l.g, consts);
+            break;
+        case MODE_ROWWORD2:
+            k_encode_bitfield<T, BPS, QUANT, MODE_ROWWORD2>
+                <<<tile_grid(n, EncUnroll<BPS, MODE_ROWWORD2>::value), kBlock,
+                   0, stream>>>(l.g, consts);
             break;
         case MODE_RUN:
             k_encode_bitfield<T, BPS, QUANT, MODE_RUN>

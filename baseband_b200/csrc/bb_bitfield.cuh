@@ -98,6 +98,10 @@ BB_HD F2 decode_pair(uint32_t w, uint32_t j, const float *lut) {
 
 template <int BPS, int CODEC>
 BB_HD float decode_one(uint32_t w, uint32_t c, const float *lut) {
+    // one table access per value: the pair table serves 1/2 bit, wider codes
+    // index the per-code table directly
+    if (CODEC == CODEC_SINT) return sint_code<BPS>(w, c * BPS);
+    if (BPS > 2) return lut[(w >> (c * BPS)) & ((1u << BPS) - 1u)];
     F2 r = decode_pair<BPS, CODEC>(w, c >> 1, lut);
     return (c & 1u) ? r.y : r.x;
 }
@@ -462,6 +466,7 @@ struct EncGeom {
     uint8_t *dst;
     const long long *unit_offset;
     uint32_t nset, nthread, nelem, nword, spf, nitems, ngroup;
+    uint32_t nwords_total;          // ROWWORD: nset * nword
     int32_t log2_nelem;
     FastDiv div_nword, div_ngroup, div_nthread;
 };
@@ -524,6 +529,96 @@ BB_HD void enc_rowgroup(const EncGeom &p, const QuantConsts<T> &c,
 #pragma unroll
     for (int j = 0; j < G; ++j) {
         long long off = uo[j];
+        if (off >= 0) store_u32(p.dst + off + 4ull * k, w[j]);
+    }
+}
+
+// ROWWORD<G>: nthread * E == 4 (4 real threads or 2 complex ones), i.e. an
+// input row IS one float4 and ROWGROUP's lanes would each read their own
+// 16 * TPW-byte piece (32 sectors per warp load).  Instead a warp takes the
+// 32 * TPW rows behind 32 consecutive word positions: (stage) lane L loads
+// rows q = L + 32 j -- every warp load is 512 contiguous bytes -- quantises
+// them and parks the four codes of a row as one 32-bit value in shared
+// memory; (emit) lane L collects rows L * TPW .. + TPW - 1 = its word
+// position, merges them and stores one word per slot.  The XOR swizzle makes
+// both the strided writes and the TPW-strided reads bank-conflict free.
+template <int TPW>
+BB_HD uint32_t rw_swz(uint32_t q) { return q ^ ((q >> 5) & (TPW - 1)); }
+
+// The codes of one row: G == 4: one per byte; G == 2: (re, im) of slot 0 in
+// the low half word, of slot 1 in the high one.
+template <typename T, int BPS, int QUANT, int G>
+BB_HD uint32_t rw_pack_row(const Vec4<T> &v, const QuantConsts<T> &c) {
+    const uint32_t q0 = quantise<T, BPS, QUANT>(v.x, c),
+        q1 = quantise<T, BPS, QUANT>(v.y, c),
+        q2 = quantise<T, BPS, QUANT>(v.z, c),
+        q3 = quantise<T, BPS, QUANT>(v.w, c);
+    if (G == 4) return q0 | (q1 << 8) | (q2 << 16) | (q3 << 24);
+    return (q0 | (q1 << BPS)) | ((q2 | (q3 << BPS)) << 16);
+}
+
+template <typename T, int BPS, int QUANT, int G>
+BB_HD void rw_stage(const EncGeom &p, const QuantConsts<T> &c, uint32_t chunk,
+                    uint32_t lane, uint32_t *buf) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    constexpr int LB = TPW < 8 ? TPW : 8;         // loads in flight per lane
+    const size_t nrows = (size_t)p.nwords_total * TPW;
+    const size_t row0 = (size_t)chunk * (32 * TPW);
+    const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
+#pragma unroll
+    for (int j0 = 0; j0 < TPW; j0 += LB) {
+        Vec4<T> v[LB];
+#pragma unroll
+        for (int j = 0; j < LB; ++j) {
+            const size_t row = row0 + lane + 32u * (j0 + j);
+            if (row < nrows) v[j] = Vec4<T>::load(in + row * 4);
+            else v[j] = Vec4<T>{(T)0, (T)0, (T)0, (T)0};
+        }
+#pragma unroll
+        for (int j = 0; j < LB; ++j)
+            buf[rw_swz<TPW>(lane + 32u * (j0 + j))] =
+                rw_pack_row<T, BPS, QUANT, G>(v[j], c);
+    }
+}
+
+template <int BPS, int G>
+BB_HD void rw_emit(const EncGeom &p, uint32_t chunk, uint32_t lane,
+                   const uint32_t *buf) {
+    constexpr int E = 4 / G;
+    constexpr int TPW = (32 / BPS) / E;
+    constexpr int NC = E == 1 ? 4 : 2;            // merged values per word set
+    constexpr int PER = TPW / NC;                 // rows merged into each
+    const uint32_t idx = chunk * 32u + lane;      // word position, all sets
+    if (idx >= p.nwords_total) return;
+    uint32_t m[NC];
+#pragma unroll
+    for (int n = 0; n < NC; ++n) {
+        m[n] = 0u;
+#pragma unroll
+        for (int r = 0; r < PER; ++r)
+            m[n] |= buf[rw_swz<TPW>(lane * TPW + n * PER + r)]
+                << (r * BPS * E);
+    }
+    uint32_t w[G];
+    if (G == 4) {                                 // 4 x 4 byte transpose
+        const uint32_t lo01 = byte_perm(m[0], m[1 % NC], 0x5140),
+            lo23 = byte_perm(m[2 % NC], m[3 % NC], 0x5140),
+            hi01 = byte_perm(m[0], m[1 % NC], 0x7362),
+            hi23 = byte_perm(m[2 % NC], m[3 % NC], 0x7362);
+        w[0] = byte_perm(lo01, lo23, 0x5410);
+        w[1 % G] = byte_perm(lo01, lo23, 0x7632);
+        w[2 % G] = byte_perm(hi01, hi23, 0x5410);
+        w[3 % G] = byte_perm(hi01, hi23, 0x7632);
+    } else {
+        w[0] = byte_perm(m[0], m[1 % NC], 0x5410);
+        w[1 % G] = byte_perm(m[0], m[1 % NC], 0x7632);
+    }
+    uint32_t set, k;
+    p.div_nword.divmod(idx, set, k);
+    const long long *uo = p.unit_offset + (size_t)set * G;
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+        const long long off = uo[j];
         if (off >= 0) store_u32(p.dst + off + 4ull * k, w[j]);
     }
 }

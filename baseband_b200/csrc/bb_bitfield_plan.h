@@ -9,7 +9,8 @@
 namespace bb {
 
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
-       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6, MODE_WORDROW4 = 7 };
+       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6, MODE_WORDROW4 = 7,
+       MODE_ROWWORD4 = 8, MODE_ROWWORD2 = 9 };
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -146,11 +147,19 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
     const int64_t rowlen = (int64_t)nthread * nelem;
     int mode = pick_mode(nelem, nthread, true);
     if (mode == MODE_WORDRUN) mode = MODE_RUN;   // encode: vectorised words
+    // a row is one float4: warp-cooperative rows -> words
+    const uint64_t rw_budget = 0x03ffffffull;    // word positions per launch
+    if (mode == MODE_ROWGROUP4 && nthread == 4 && nword <= rw_budget)
+        mode = MODE_ROWWORD4;
+    if (mode == MODE_ROWGROUP2 && nthread == 2 && nword <= rw_budget)
+        mode = MODE_ROWWORD2;
     uint64_t per_set;
     uint32_t ngroup = 1;
     if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
         ngroup = nthread / (mode == MODE_ROWGROUP4 ? 4 : 2);
         per_set = (uint64_t)nword * ngroup;
+    } else if (mode == MODE_ROWWORD4 || mode == MODE_ROWWORD2) {
+        per_set = nword;                  // items are lanes = word positions
     } else {
         per_set = (uint64_t)nword * nthread;
     }
@@ -158,7 +167,9 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
         err = "one frame set is too large for a launch; split it along time";
         return false;
     }
-    int64_t max_sets = (int64_t)(0x7fffffffull / per_set);
+    int64_t max_sets = (int64_t)(((mode == MODE_ROWWORD4
+                                   || mode == MODE_ROWWORD2) ? rw_budget
+                                  : 0x7fffffffull) / per_set);
     for (int64_t s0 = 0; s0 < nset; s0 += max_sets) {
         int64_t s1 = s0 + max_sets < nset ? s0 + max_sets : nset;
         EncGeom g;
@@ -172,6 +183,9 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
         g.nword = nword;
         g.spf = spf;
         g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
+        g.nwords_total = (uint32_t)((uint64_t)nword * (uint64_t)(s1 - s0));
+        if (mode == MODE_ROWWORD4 || mode == MODE_ROWWORD2)   // whole warps
+            g.nitems = (g.nwords_total + 31u) / 32u * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);
         g.div_nword = make_fastdiv(nword);

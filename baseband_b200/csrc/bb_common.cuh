@@ -28,6 +28,20 @@ BB_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
+// PRMT: byte i of the result is byte (s >> 4i) & 7 of the pair {x, y}
+// (selector nibbles 0..7 only: no sign replication).
+BB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(x, y, s);
+#else
+    const uint64_t xy = ((uint64_t)y << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i)
+        r |= (uint32_t)((xy >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
+
 // Division of any 32-bit unsigned n by a runtime-constant d >= 1
 // (Granlund & Montgomery round-up method): 4 integer instructions.
 struct FastDiv {

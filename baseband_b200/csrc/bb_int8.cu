@@ -19,8 +19,10 @@ __global__ void __launch_bounds__(kF8Threads) k_int8_decode_t64(const I8Geom p) 
     f8_dec_store(p, tile, blockIdx.x, threadIdx.x);
 }
 
+// Min-blocks hint of 4: lets ptxas keep eight float4 loads in flight (64
+// registers) instead of serialising them to stay within 32.
 template <typename T>
-__global__ void __launch_bounds__(kF8Threads) k_int8_encode_t64(const I8Geom p) {
+__global__ void __launch_bounds__(kF8Threads, 4) k_int8_encode_t64(const I8Geom p) {
     __shared__ __align__(16) uint32_t tile[kF8SmemWords];
     f8_enc_load<T>(p, tile, blockIdx.x, threadIdx.x);
     __syncthreads();

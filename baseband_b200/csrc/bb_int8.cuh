@@ -329,6 +329,42 @@ BB_HD void f8_enc_load(const I8Geom &p, uint32_t *smem, uint32_t block,
     const size_t row = (size_t)t.r0 + ra;
     const size_t col0 = (size_t)t.unit * p.ncol;
     constexpr int kIter = kF8Words / (kF8Threads / 32);    // 8
+    if (sizeof(T) == 4 && p.ib == 2 && t.r0 + kF8Rows <= p.nrow
+        && ((size_t)t.w0 + kF8Words) * 2 <= p.ncol) {
+        // Interior complex float32 tile (CTA-uniform test): the eight float4
+        // loads of four word columns are issued back to back before the
+        // first is quantised (4 KiB per warp in flight), as in the decode.
+        const float *fin = reinterpret_cast<const float *>(p.in);
+        const size_t colstride = 2 * (size_t)p.nrow;       // floats per column
+        constexpr int kBatch = 4;
+#pragma unroll
+        for (int i0 = 0; i0 < kIter; i0 += kBatch) {
+            F4 v[kBatch][2];
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                const uint32_t wc = warp + (i0 + i) * (kF8Threads / 32);
+                const float *q = fin
+                    + 2 * ((col0 + ((size_t)t.w0 + wc) * 2) * p.nrow + row);
+                v[i][0] = *reinterpret_cast<const F4 *>(q);
+                v[i][1] = *reinterpret_cast<const F4 *>(q + colstride);
+            }
+#pragma unroll
+            for (int i = 0; i < kBatch; ++i) {
+                const uint32_t wc = warp + (i0 + i) * (kF8Threads / 32);
+                const uint32_t a = quant_sint<float, 8>(v[i][0].x)
+                    | (quant_sint<float, 8>(v[i][0].y) << 8)
+                    | (quant_sint<float, 8>(v[i][1].x) << 16)
+                    | (quant_sint<float, 8>(v[i][1].y) << 24);
+                const uint32_t b = quant_sint<float, 8>(v[i][0].z)
+                    | (quant_sint<float, 8>(v[i][0].w) << 8)
+                    | (quant_sint<float, 8>(v[i][1].z) << 16)
+                    | (quant_sint<float, 8>(v[i][1].w) << 24);
+                smem[f8_swz(ra, wc)] = a;
+                smem[f8_swz(ra + 1, wc)] = b;
+            }
+        }
+        return;
+    }
 #pragma unroll 2
     for (int i = 0; i < kIter; ++i) {
         const uint32_t wc = warp + i * (kF8Threads / 32);

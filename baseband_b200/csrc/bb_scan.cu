@@ -129,10 +129,13 @@ k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
         todo &= todo - 1;
         long long boff = __shfl_sync(0xffffffffu, off, b);
         const uint8_t *pl = src + boff + 16;
-        bool diff = false;
-        for (int k = 3 + lane; k < 2500 && !diff; k += 32)
-            diff = ldw(pl + 4 * k) != kFill;
-        bool any = __any_sync(0xffffffffu, diff);
+        // no early exit: the loads stay independent, so a batch of them is
+        // in flight at once (a true fill frame costs ~10 latencies, not 78)
+        uint32_t acc = 0u;
+#pragma unroll 8
+        for (int k = 3 + lane; k < 2500; k += 32)
+            acc |= ldw(pl + 4 * k) ^ kFill;
+        bool any = __any_sync(0xffffffffu, acc != 0u);
         if (lane == b) valid = any;
     }
     if (!live) return;

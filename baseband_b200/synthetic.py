@@ -70,6 +70,34 @@ def bcd(value, ndigit):
     return out
 
 
+def bcd_array(values, ndigit):
+    """Vectorised `bcd`."""
+    values = np.asarray(values, np.int64)
+    out = np.zeros(values.shape, np.int64)
+    for d in range(ndigit):
+        out |= ((values // 10 ** d) % 10) << (4 * d)
+    return out
+
+
+def mark5b_headers(nframe, frames_per_second=6400, jday=123, seconds0=3600):
+    """(nframe, 4) uint32 Mark 5B header words (mark5b/header.py:60-75):
+    sync, frame_nr, BCD jday/seconds, BCD fraction + CRC-16."""
+    from .base.utils import crc_array
+    idx = np.arange(nframe, dtype=np.int64)
+    sec = seconds0 + idx // frames_per_second
+    fnr = idx % frames_per_second
+    w = np.empty((nframe, 4), np.uint32)
+    w[:, 0] = 0xABADDEED
+    w[:, 1] = fnr.astype(np.uint32)
+    w[:, 2] = ((bcd(jday, 3) << 20) | bcd_array(sec, 5)).astype(np.uint32)
+    frac = fnr * 10000 // frames_per_second
+    w[:, 3] = bcd_array(frac, 4).astype(np.uint32) << 16
+    w[:, 3] |= crc_array((w[:, 2].astype(np.uint64) << np.uint64(16))
+                         | (w[:, 3] >> np.uint32(16)).astype(np.uint64),
+                         48, 0x18005).astype(np.uint32)
+    return w
+
+
 def mark5b_stream(nframe, seed=MARK5B_SEED, invalid_fraction=0.01,
                   frames_per_second=6400, jday=123, seconds0=3600):
     """Mark 5B frames (16-byte header + 10000-byte payload); a Bernoulli
@@ -79,19 +107,23 @@ def mark5b_stream(nframe, seed=MARK5B_SEED, invalid_fraction=0.01,
     bad = rng.random(nframe) < invalid_fraction
     w = frames.view('<u4').reshape(nframe, 2504)
     w[bad, 4:] = 0x11223344
-    idx = np.arange(nframe, dtype=np.int64)
-    sec = seconds0 + idx // frames_per_second
-    fnr = idx % frames_per_second
-    w[:, 0] = 0xABADDEED
-    w[:, 1] = fnr.astype(np.uint32)
-    bcd_sec = np.array([bcd(int(s), 5) for s in np.unique(sec)], np.uint32)
-    w[:, 2] = (bcd(jday, 3) << 20) | bcd_sec[sec - seconds0]
-    frac = (fnr * 10000 // frames_per_second)
-    w[:, 3] = np.array([bcd(int(f), 4) for f in frac], np.uint32) << 16
-    from .base.utils import crc_array
-    w[:, 3] |= crc_array((w[:, 2].astype(np.uint64) << np.uint64(16))
-                         | (w[:, 3] >> np.uint32(16)).astype(np.uint64),
-                         48, 0x18005).astype(np.uint32)
+    w[:, :4] = mark5b_headers(nframe, frames_per_second, jday, seconds0)
+    return frames.reshape(-1), ~bad
+
+
+def mark5b_stream_device(nframe, device, seed=MARK5B_SEED,
+                         invalid_fraction=0.01, **kwargs):
+    """Same layout with the payload drawn on the GPU (multi-GiB chunks);
+    returns (uint8 CUDA tensor, host bool array of valid frames)."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    frames = torch.randint(0, 256, (nframe, 10016), dtype=torch.uint8,
+                           device=device, generator=g)
+    bad = np.random.default_rng(seed).random(nframe) < invalid_fraction
+    w = frames.view(torch.int32)
+    w[torch.from_numpy(bad).to(device), 4:] = 0x11223344
+    hdr = mark5b_headers(nframe, **kwargs).view(np.int32)
+    w[:, :4] = torch.from_numpy(hdr).to(device)
     return frames.reshape(-1), ~bad
 
 
@@ -104,6 +136,18 @@ def mark4_stream(nframe, seed=MARK4_SEED):
     frames[:, :160] = 0
     frames[:, 64:96] = np.uint64(0xffffffffffffffff)
     return frames.view(np.uint8).reshape(-1)
+
+
+def mark4_stream_device(nframe, device, seed=MARK4_SEED):
+    """`mark4_stream` with the payload drawn on the GPU."""
+    import torch
+    g = torch.Generator(device=device).manual_seed(seed)
+    frames = torch.randint(0, 256, (nframe, 160000), dtype=torch.uint8,
+                           device=device, generator=g)
+    w = frames.view(torch.int64)
+    w[:, :160] = 0
+    w[:, 64:96] = -1
+    return frames.reshape(-1)
 
 
 def guppi_header(nchan, npol, blocsize, overlap, pktidx, tbin=1e-6):

@@ -292,6 +292,9 @@ def run_b200(args):
 
     # ------------------------------------------------ end-to-end (host bufs)
     e2e = measure_e2e(args, dev, rank, world, lv, slot)
+    del out, back, raw
+    torch.cuda.empty_cache()
+    named = measure_named_configs(args, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -317,6 +320,7 @@ def run_b200(args):
             'traffic': NCU_TRAFFIC_BYTES_PER_SAMPLE * nset * SET_SAMPLES
             if NCU_TRAFFIC_BYTES_PER_SAMPLE else None},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+        'named_configs': named,
         'host_binding': ('rank pinned to the {} CPUs local to its GPU'
                          .format(len(numa_cpus)) if numa_cpus else 'none'),
     }
@@ -438,6 +442,112 @@ def measure_e2e(args, dev, rank, world, lv, slot):
                     'input'.format(args.e2e_mib)}
 
 
+def measure_named_configs(args, dev, rank, world):
+    """Device-resident header scan + decode of the other shapes BASELINE.json
+    names (configs[2..4]), outside the headline timed
+    region: per-GPU chunk resident in HBM, CUDA events around each pass, max
+    over ranks, Gsamples/s summed over ranks, GB/s = (frame bytes read +
+    float32 written) / time per GPU against the measured copy peak."""
+    import torch
+    import torch.distributed as dist
+    from baseband_b200 import kernels, levels, synthetic
+    peak, _ = peaks()
+    nbytes = int(args.named_mib * 2**20)
+    if nbytes <= 0:
+        return None
+    steps = max(3, min(args.steps, 10))
+    result = {}
+
+    def timed(name, fn, algo_bytes, nsamp, note):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        ev = [(torch.cuda.Event(enable_timing=True),
+               torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        gbs = algo_bytes / (ms * 1e-3) / 1e9
+        result[name] = {'gsamples_s': nsamp * world / (ms * 1e-3) / 1e9,
+                        'hbm_gbs_per_gpu': gbs, 'frac': gbs / peak,
+                        'ms_per_pass': ms, 'chunk_bytes_per_gpu': algo_bytes
+                        - 4 * nsamp, 'what': note}
+
+    # C3: Mark 4, 64 tracks, fan-out 4, 2 bit, 8 channels
+    nframe = max(1, nbytes // 160000)
+    raw = synthetic.mark4_stream_device(nframe, dev,
+                                        seed=synthetic.MARK4_SEED + rank)
+    out = torch.empty((nframe * 80000, 8), dtype=torch.float32, device=dev)
+    lv4 = levels.sign_magnitude()
+
+    def c3():
+        _, uo = kernels.mark4_scan(raw, nframe, 64)
+        kernels.mark4_decode(raw, uo, nframe, 8, 4, False, lv4, out=out)
+
+    timed('C3_mark4_64track_fanout4', c3, raw.numel() + out.numel() * 4,
+          out.numel(), 'bb_mark4_scan + bb_mark4_decode (track reorder, '
+          'header-overwritten rows -> fill)')
+    del raw, out
+    torch.cuda.empty_cache()
+
+    # C4: GUPPI 8-bit complex, 2 pol, 512 channels, channels first, overlap
+    nchan, npol, spf, ov = 512, 2, 65536, 512
+    fbytes = nchan * spf * npol * 2
+    nfr = max(1, nbytes // fbytes)
+    g = torch.Generator(device=dev).manual_seed(synthetic.GUPPI_SEED + rank)
+    raw = torch.randint(0, 256, (nfr * fbytes,), dtype=torch.uint8,
+                        device=dev, generator=g)
+    off = torch.arange(nfr, dtype=torch.int64, device=dev) * fbytes
+    cb = torch.zeros(nfr, dtype=torch.int64, device=dev)
+    ce = torch.full((nfr,), (spf - ov) * npol, dtype=torch.int64, device=dev)
+    ce[-1] = spf * npol
+    oc0 = torch.cumsum(ce - cb, 0) - (ce - cb)
+    ncols = int((ce - cb).sum().item())
+    out = torch.empty((ncols * nchan * 2,), dtype=torch.float32, device=dev)
+    timed('C4_guppi_512chan_2pol_int8_complex',
+          lambda: kernels.decode_int8_transposed(
+              raw, off, nfr, nchan, spf * npol, 2, cb, ce, oc0, out),
+          out.numel() * 5, out.numel(),
+          'bb_decode_int8_transposed (channels-first -> (time, pol, chan) '
+          'complex64, overlap columns skipped; bytes count non-overlap input)')
+    del raw, out
+    torch.cuda.empty_cache()
+
+    # C5: Mark 5B 2 bit, 16 channels, 1 % invalid (fill pattern) frames
+    nframe = max(1, nbytes // 10016)
+    raw, valid = synthetic.mark5b_stream_device(
+        nframe, dev, seed=synthetic.MARK5B_SEED + rank)
+    out = torch.empty((nframe * 2500, 16), dtype=torch.float32, device=dev)
+    lv5 = levels.mark5b(2)
+
+    def c5():
+        fields, uo = kernels.mark5b_scan(raw, nframe)
+        kernels.decode_bitfield(raw, uo, nframe, 1, 10000, 2, 16, False,
+                                kernels.CODEC_LEVELS, lv5, -999.0, out=out)
+        return fields
+
+    timed('C5_mark5b_2bit_16chan_1pct_invalid', c5,
+          raw.numel() + out.numel() * 4, out.numel(),
+          'bb_mark5b_scan (BCD fields, fill-pattern validity) + '
+          'bb_decode_bitfield with fill_value for invalid frames')
+    fields = c5()
+    torch.cuda.synchronize(dev)
+    got_valid = fields[kernels.M5B_VALID].cpu().numpy().astype(bool)
+    filled = (out.view(nframe, -1)[:, 0] == -999.0).cpu().numpy()
+    result['C5_mark5b_2bit_16chan_1pct_invalid']['validity_exact'] = bool(
+        np.array_equal(got_valid, valid) and np.array_equal(~filled, valid))
+    return result
+
+
 def main():
     # NCCL prints a version banner on stdout when NCCL_DEBUG=VERSION; the
     # contract is ONE JSON line on stdout.
@@ -456,6 +566,8 @@ def main():
     ap.add_argument('--chunk-gib', type=float, default=1.0,
                     help='packed bytes resident per GPU per step')
     ap.add_argument('--e2e-mib', type=float, default=128.0)
+    ap.add_argument('--named-mib', type=float, default=1024.0,
+                    help='packed MiB per GPU for the C3-C5 shapes (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -157,6 +157,15 @@ ENCODE_CASES = [
     _ecase('2bit_3thr_1ch', 2, 1, 3, 3, 100),
     _ecase('2bit_5thr_cplx', 2, 2, 5, 2, 200),
     _ecase('4bit_2thr_6ch', 4, 6, 2, 2, 240),
+    # a row is one float4 (4 real / 2 complex threads): warp-cooperative
+    # ROWWORD mode, chunks of 32 word positions crossing frame-set boundaries
+    _ecase('1bit_4thr_rowword', 1, 1, 4, 3, 200),
+    _ecase('2bit_4thr_rowword', 2, 1, 4, 3, 200, invalid=(2, 7)),
+    _ecase('2bit_4thr_rowword_f64', 2, 1, 4, 2, 132, dtype='f8'),
+    _ecase('8bit_4thr_rowword', 8, 1, 4, 3, 200),
+    _ecase('1bit_cplx_2thr_rowword', 1, 2, 2, 3, 200),
+    _ecase('4bit_cplx_2thr_rowword', 4, 2, 2, 3, 200, invalid=(0,)),
+    _ecase('8bit_cplx_2thr_rowword', 8, 2, 2, 3, 200),
     _ecase('gsb_4bit', 4, 1, 1, 2, 4096, quant='sint'),
     _ecase('dada_8bit_cplx', 8, 4, 1, 2, 6400, quant='sint'),
     _ecase('gsb_8bit_2thr_f64', 8, 1024, 2, 2, 4096, quant='sint',

@@ -69,13 +69,33 @@ static void run_decode(const std::vector<DecLaunch> &launches,
 template <typename T, int BPS, int QUANT>
 static void run_encode(const std::vector<EncLaunch> &launches) {
     const QuantConsts<T> c = make_quant_consts<T>();
-    for (const EncLaunch &l : launches)
+    for (const EncLaunch &l : launches) {
+        if (l.mode == MODE_ROWWORD4 || l.mode == MODE_ROWWORD2) {
+            // warp-cooperative mode: the staging buffer is the shared memory
+            std::vector<uint32_t> buf(32 * 32);
+            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    if (l.mode == MODE_ROWWORD4)
+                        rw_stage<T, BPS, QUANT, 4>(l.g, c, chunk, lane, buf.data());
+                    else
+                        rw_stage<T, BPS, QUANT, 2>(l.g, c, chunk, lane, buf.data());
+                }
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    if (l.mode == MODE_ROWWORD4)
+                        rw_emit<BPS, 4>(l.g, chunk, lane, buf.data());
+                    else
+                        rw_emit<BPS, 2>(l.g, chunk, lane, buf.data());
+                }
+            }
+            continue;
+        }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
             if (l.mode == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(l.g, c, item);
             else if (l.mode == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(l.g, c, item);
             else if (l.mode == MODE_RUN) enc_word<T, BPS, QUANT, true>(l.g, c, item);
             else enc_word<T, BPS, QUANT, false>(l.g, c, item);
         }
+    }
 }
 
 template <typename T>
