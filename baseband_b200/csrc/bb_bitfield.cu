@@ -189,28 +189,36 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
     }
 }
 
+// ROWWORD (rows of one float4 -> words through shared memory).  A kernel of
+// its own so that it can carry a min-blocks hint of 4 (<= 64 registers): that
+// lets ptxas keep the eight float4 loads of a lane in flight instead of
+// serialising them to stay within 40 registers.
+template <typename T, int BPS, int QUANT, int G>
+__global__ void __launch_bounds__(kBlock, 4)
+k_encode_rowword(const EncGeom p, const QuantConsts<T> c) {
+    constexpr int MODE = G == 4 ? MODE_ROWWORD4 : MODE_ROWWORD2;
+    constexpr int U = EncUnroll<BPS, MODE>::value;
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    __shared__ uint32_t cbuf[kBlock / 32][32 * TPW];
+    // kBlock and nitems are multiples of 32: chunks are warp uniform.
+    const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kBlock;
+        if (item >= p.nitems) break;
+        rw_stage<T, BPS, QUANT, G>(p, c, item >> 5, lane, cbuf[warp]);
+        __syncwarp();
+        rw_emit<BPS, G>(p, item >> 5, lane, cbuf[warp]);
+        __syncwarp();                             // before the buffer is reused
+    }
+}
+
 template <typename T, int BPS, int QUANT, int MODE>
 __global__ void __launch_bounds__(kBlock)
 k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
     constexpr int U = EncUnroll<BPS, MODE>::value;
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
-    if (MODE == MODE_ROWWORD4 || MODE == MODE_ROWWORD2) {
-        // kBlock and nitems are multiples of 32: chunks are warp uniform.
-        constexpr int G = MODE == MODE_ROWWORD4 ? 4 : 2;
-        constexpr int TPW = (32 / BPS) / (4 / G);
-        __shared__ uint32_t cbuf[kBlock / 32][32 * TPW];
-        const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-#pragma unroll 1
-        for (int u = 0; u < U; ++u) {
-            const uint32_t item = item0 + u * kBlock;
-            if (item >= p.nitems) break;
-            rw_stage<T, BPS, QUANT, G>(p, c, item >> 5, lane, cbuf[warp]);
-            __syncwarp();
-            rw_emit<BPS, G>(p, item >> 5, lane, cbuf[warp]);
-            __syncwarp();                         // before the buffer is reused
-        }
-        return;
-    }
     if (MODE == MODE_RUN && BPS >= 4) {
         // few float4 per word: keep the loads of several words in flight
         constexpr int B = BPS == 8 ? 4 : 2;
@@ -307,12 +315,12 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
                    stream>>>(l.g, consts);
             break;
         case MODE_ROWWORD4:
-            k_encode_bitfield<T, BPS, QUANT, MODE_ROWWORD4>
+            k_encode_rowword<T, BPS, QUANT, 4>
                 <<<tile_grid(n, EncUnroll<BPS, MODE_ROWWORD4>::value), kBlock,
                    0, stream>>>(l.g, consts);
             break;
         case MODE_ROWWORD2:
-            k_encode_bitfield<T, BPS, QUANT, MODE_ROWWORD2>
+            k_encode_rowword<T, BPS, QUANT, 2>
                 <<<tile_grid(n, EncUnroll<BPS, MODE_ROWWORD2>::value), kBlock,
                    0, stream>>>(l.g, consts);
             break;

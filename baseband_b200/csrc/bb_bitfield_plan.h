@@ -149,9 +149,13 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
     if (mode == MODE_WORDRUN) mode = MODE_RUN;   // encode: vectorised words
     // a row is one float4: warp-cooperative rows -> words
     const uint64_t rw_budget = 0x03ffffffull;    // word positions per launch
-    if (mode == MODE_ROWGROUP4 && nthread == 4 && nword <= rw_budget)
+    // (measured: it wins from 8 rows per word on; below that ROWGROUP's
+    // 32/64-byte pieces per lane coalesce well enough)
+    if (mode == MODE_ROWGROUP4 && nthread == 4 && nword <= rw_budget
+        && bps <= 4)
         mode = MODE_ROWWORD4;
-    if (mode == MODE_ROWGROUP2 && nthread == 2 && nword <= rw_budget)
+    if (mode == MODE_ROWGROUP2 && nthread == 2 && nword <= rw_budget
+        && bps <= 2)
         mode = MODE_ROWWORD2;
     uint64_t per_set;
     uint32_t ngroup = 1;
