@@ -20,7 +20,8 @@ struct Unroll {
         MODE == MODE_ROWGROUP4 ? 32 / BPS
         : MODE == MODE_ROWGROUP2 ? 16 / BPS
         : MODE == MODE_WORDRUN ? 8 / BPS
-        : MODE == MODE_WORDROW4 ? 32 / BPS : 1;
+        : MODE == MODE_WORDROW4 ? 32 / BPS
+        : MODE == MODE_WORDROW2 ? 16 / BPS : 1;
     static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
 };
 
@@ -85,13 +86,14 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
-    if (MODE == MODE_WORDROW4) {
-        // The four slot words of every lane go through shared memory (one
-        // STS.128 per lane and chunk); a row then costs one LDS.128 instead
-        // of five shuffles.
-        constexpr int TPW = 32 / BPS;
+    if (MODE == MODE_WORDROW4 || MODE == MODE_WORDROW2) {
+        // The G slot words of every lane go through shared memory (one
+        // STS.128 / STS.64 per lane and chunk); a row then costs one LDS
+        // instead of G + 1 shuffles.
+        constexpr int G = MODE == MODE_WORDROW4 ? 4 : 2;
+        constexpr int TPW = (32 / BPS) / (4 / G);
         constexpr int WB = U < 2 ? U : 2;         // chunks loaded up front
-        __shared__ __align__(16) uint32_t wbuf[kBlock / 32][WB][32][4];
+        __shared__ __align__(16) uint32_t wbuf[kBlock / 32][WB][32][G];
         __shared__ uint32_t okbuf[kBlock / 32][WB][32];
         const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll 1
@@ -100,11 +102,13 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 #pragma unroll
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
-                uint32_t w[4] = {0u, 0u, 0u, 0u};
+                uint32_t w[G];
                 uint32_t ok = 0u;
-                if (item < p.nitems) ok = wrow_load(p, item >> 5, lane, w);
-                *reinterpret_cast<uint4 *>(wbuf[warp][b][lane]) =
-                    make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+                for (int g = 0; g < G; ++g) w[g] = 0u;
+                if (item < p.nitems) ok = wrow_load<G>(p, item >> 5, lane, w);
+#pragma unroll
+                for (int g = 0; g < G; ++g) wbuf[warp][b][lane][g] = w[g];
                 okbuf[warp][b][lane] = ok;
             }
             __syncwarp();
@@ -114,12 +118,12 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
                 if (item >= p.nitems) break;
 #pragma unroll
                 for (int j = 0; j < TPW; ++j) {
-                    const uint32_t src = wrow_src_lane<BPS>(lane, j);
-                    const uint4 v = *reinterpret_cast<const uint4 *>(
-                        wbuf[warp][b][src]);
-                    const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
-                    wrow_emit<BPS, CODEC>(p, lut, item >> 5, lane, j, ws,
-                                          okbuf[warp][b][src]);
+                    const uint32_t src = wrow_src_lane<BPS, G>(lane, j);
+                    uint32_t ws[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) ws[g] = wbuf[warp][b][src][g];
+                    wrow_emit<BPS, CODEC, G>(p, lut, item >> 5, lane, j, ws,
+                                             okbuf[warp][b][src]);
                 }
             }
         }
@@ -280,6 +284,11 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         case MODE_WORDROW4:
             k_decode_bitfield<BPS, CODEC, MODE_WORDROW4>
                 <<<tile_grid(n, Unroll<BPS, MODE_WORDROW4>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
+            break;
+        case MODE_WORDROW2:
+            k_decode_bitfield<BPS, CODEC, MODE_WORDROW2>
+                <<<tile_grid(n, Unroll<BPS, MODE_WORDROW2>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         case MODE_ROWRUN2:

@@ -19,6 +19,7 @@
 //                stores float4 L + 32 j of the warp's chunk).  Several chunks
 //                are loaded before the first is decoded (memory-level
 //                parallelism; the RUN mode it replaces was latency bound).
+//   WORDROW<G>   nthread * E == 4: as WORDRUN over the G slots of a row.
 //   RUN          nthread > 1 and E a power of two >= 4.  Output-centric: a
 //                thread owns one float4 of the output (4 consecutive codes of
 //                one unit), so a warp store is 512 contiguous bytes.
@@ -387,28 +388,31 @@ BB_HD void wr_emit(const DecGeom &p, const float *lut, uint32_t chunk,
     *reinterpret_cast<F4 *>(p.out + gidx) = v;
 }
 
-// WORDROW4: exactly 4 single-channel threads, so an output row is one float4
-// (one code from each slot).  Like WORDRUN, a warp takes 32 consecutive word
-// positions -- here of all four slots, four coalesced 128-byte loads -- whose
-// decoded rows form one contiguous run of 32 * TPW float4 (TPW = codes per
-// word).  Store j: lane L writes row q = L + 32 j of the chunk, fetching the
-// four words of lane q / TPW by shuffle.
-template <int BPS>
+// WORDROW<G>: nthread * E == 4 (G = 4 single-channel threads, or G = 2
+// threads of one complex channel), so an output row is one float4.  Like
+// WORDRUN, a warp takes 32 consecutive word positions -- here of all G
+// slots, G coalesced 128-byte loads -- whose decoded rows form one contiguous
+// run of 32 * TPW float4 (TPW = rows per word).  Store j: lane L writes row
+// q = L + 32 j of the chunk from the G words of lane q / TPW (staged in
+// shared memory by the kernel).
+template <int BPS, int G>
 BB_HD uint32_t wrow_src_lane(uint32_t lane, int j) {
-    return (lane + 32u * j) / (32 / BPS);
+    return (lane + 32u * j) / ((32 / BPS) / (4 / G));
 }
 
+template <int G>
 BB_HD uint32_t wrow_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
-                         uint32_t w[4]) {
-    w[0] = w[1] = w[2] = w[3] = 0u;
+                         uint32_t w[G]) {
+#pragma unroll
+    for (int j = 0; j < G; ++j) w[j] = 0u;
     const uint32_t idx = chunk * 32u + lane;   // word position over all sets
     if (idx >= p.nwords_total) return 0u;
     uint32_t set, k;
     p.div_nword.divmod(idx, set, k);
-    const long long *uo = p.unit_offset + (size_t)set * 4;
+    const long long *uo = p.unit_offset + (size_t)set * G;
     uint32_t okmask = 0u;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < G; ++j) {
         const long long off = uo[j];
         if (off >= 0) {
             w[j] = load_u32(p.src + off + 4ull * k);
@@ -418,21 +422,31 @@ BB_HD uint32_t wrow_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
     return okmask;
 }
 
-template <int BPS, int CODEC>
+template <int BPS, int CODEC, int G>
 BB_HD void wrow_emit(const DecGeom &p, const float *lut, uint32_t chunk,
-                     uint32_t lane, int j, const uint32_t w[4],
+                     uint32_t lane, int j, const uint32_t w[G],
                      uint32_t okmask) {
-    constexpr int TPW = 32 / BPS;
+    constexpr int TPW = (32 / BPS) / (4 / G);
     const uint32_t q = lane + 32u * j;                 // row within the chunk
     if (chunk * 32u + q / TPW >= p.nwords_total) return;
     const long long row = p.row_base + ((long long)chunk * 32 * TPW + q);
     if (row < 0 || row >= p.nsample) return;
     const uint32_t c = q % TPW;
     F4 v;
-    v.x = (okmask & 1u) ? decode_one<BPS, CODEC>(w[0], c, lut) : p.fill;
-    v.y = (okmask & 2u) ? decode_one<BPS, CODEC>(w[1], c, lut) : p.fill;
-    v.z = (okmask & 4u) ? decode_one<BPS, CODEC>(w[2], c, lut) : p.fill;
-    v.w = (okmask & 8u) ? decode_one<BPS, CODEC>(w[3], c, lut) : p.fill;
+    if (G == 4) {
+        v.x = (okmask & 1u) ? decode_one<BPS, CODEC>(w[0], c, lut) : p.fill;
+        v.y = (okmask & 2u) ? decode_one<BPS, CODEC>(w[1 % G], c, lut) : p.fill;
+        v.z = (okmask & 4u) ? decode_one<BPS, CODEC>(w[2 % G], c, lut) : p.fill;
+        v.w = (okmask & 8u) ? decode_one<BPS, CODEC>(w[3 % G], c, lut) : p.fill;
+    } else {
+        const float fill_im = p.complex_fill ? 0.f : p.fill;
+        const F2 a = decode_pair<BPS, CODEC>(w[0], c, lut);
+        const F2 b = decode_pair<BPS, CODEC>(w[1 % G], c, lut);
+        v.x = (okmask & 1u) ? a.x : p.fill;
+        v.y = (okmask & 1u) ? a.y : fill_im;
+        v.z = (okmask & 2u) ? b.x : p.fill;
+        v.w = (okmask & 2u) ? b.y : fill_im;
+    }
     *reinterpret_cast<F4 *>(p.out + row * 4) = v;
 }
 

@@ -28,12 +28,16 @@ DECODE_CASES = [
     _case('1bit_8thr', 1, 1, 8, 2, 128, start=5, count=1999),
     _case('4bit_4thr', 4, 1, 4, 2, 256, invalid=(3,), fill=7.5),
     _case('8bit_12thr', 8, 1, 12, 2, 200, start=1, count=300),
-    # ROWRUN: rows that are exactly one float4 (4 real / 2 complex threads)
+    # WORDROW: rows that are exactly one float4 (4 real / 2 complex threads)
     _case('1bit_4thr_rowrun', 1, 1, 4, 3, 68, start=33, count=1200,
           invalid=(6,), fill=-2.0),
     _case('8bit_4thr_rowrun', 8, 1, 4, 2, 404, start=3, count=700),
     _case('4bit_cplx_2thr_rowrun', 4, 2, 2, 3, 100, cplx=True, start=1,
           count=250, invalid=(3,), fill=5.0),
+    _case('1bit_cplx_2thr_wordrow', 1, 2, 2, 3, 68, cplx=True, start=17,
+          count=700, invalid=(4,), fill=-7.0),
+    _case('2bit_cplx_2thr_wordrow', 2, 2, 2, 3, 200, cplx=True, start=399,
+          count=403),
     # ROWGROUP2: complex single channel / two channels
     _case('2bit_cplx_2thr', 2, 2, 2, 3, 512, cplx=True, invalid=(2,),
           fill=-3.0),

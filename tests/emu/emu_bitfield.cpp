@@ -45,12 +45,27 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
                 uint32_t w[32][4], ok[32];
                 for (uint32_t lane = 0; lane < 32; ++lane)
-                    ok[lane] = wrow_load(l.g, chunk, lane, w[lane]);
+                    ok[lane] = wrow_load<4>(l.g, chunk, lane, w[lane]);
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     for (int j = 0; j < TPW; ++j) {
-                        uint32_t src = wrow_src_lane<BPS>(lane, j);
-                        wrow_emit<BPS, CODEC>(l.g, lut, chunk, lane, j, w[src],
-                                              ok[src]);
+                        uint32_t src = wrow_src_lane<BPS, 4>(lane, j);
+                        wrow_emit<BPS, CODEC, 4>(l.g, lut, chunk, lane, j,
+                                                 w[src], ok[src]);
+                    }
+            }
+            continue;
+        }
+        if (l.mode == MODE_WORDROW2) {
+            constexpr int TPW = 16 / BPS;
+            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
+                uint32_t w[32][2], ok[32];
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    ok[lane] = wrow_load<2>(l.g, chunk, lane, w[lane]);
+                for (uint32_t lane = 0; lane < 32; ++lane)
+                    for (int j = 0; j < TPW; ++j) {
+                        uint32_t src = wrow_src_lane<BPS, 2>(lane, j);
+                        wrow_emit<BPS, CODEC, 2>(l.g, lut, chunk, lane, j,
+                                                 w[src], ok[src]);
                     }
             }
             continue;
