@@ -62,6 +62,12 @@ SIGNATURES = {
     'bb_encode_int8_transposed': (c_int, [
         _pv, c_int32, _pv, _pi64, c_int64, c_int64, c_int64, c_int32,
         c_void_p]),
+    'bb_decode_int8_timefirst': (c_int, [
+        _pv, _pi64, c_int64, c_int64, c_int32, c_int32, c_int32, _pi64,
+        _pi64, _pi64, _pv, c_void_p]),
+    'bb_encode_int8_timefirst': (c_int, [
+        _pv, c_int32, _pv, _pi64, c_int64, c_int64, c_int32, c_int32,
+        c_int32, c_void_p]),
     'bb_vdif_scan': (c_int, [
         _pv, _pi64, c_int64, c_int64, c_int32, c_int32, c_int32, _pv, _pv,
         _pi64, _pv, c_void_p]),

@@ -37,6 +37,25 @@ __global__ void __launch_bounds__(kI8Threads) k_int8_encode_t(const I8Geom p) {
     i8_enc_store(p, tile, blockIdx.x, threadIdx.x);
 }
 
+constexpr int kTFThreads = 256, kTFUnroll = 4;
+
+__global__ void __launch_bounds__(kTFThreads) k_int8_decode_timefirst(
+    const TFGeom p) {
+    const uint32_t item0 = blockIdx.x * (kTFThreads * kTFUnroll) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kTFUnroll; ++u)
+        tf_decode(p, blockIdx.y, item0 + u * kTFThreads);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kTFThreads) k_int8_encode_timefirst(
+    const TFGeom p) {
+    const uint32_t item0 = blockIdx.x * (kTFThreads * kTFUnroll) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kTFUnroll; ++u)
+        tf_encode<T>(p, blockIdx.y, item0 + u * kTFThreads);
+}
+
 static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
                      int item_nbytes, uint64_t &nblocks, bool fast = false) {
     if (item_nbytes != 1 && item_nbytes != 2)
@@ -128,5 +147,62 @@ extern "C" int bb_encode_int8_transposed(
     else
         k_int8_encode_t<double><<<(unsigned)nblocks, kI8Threads, 0, s>>>(g);
     BB_CHECK_LAUNCH("bb_encode_int8_transposed launch");
+    return BB_OK;
+}
+
+extern "C" int bb_decode_int8_timefirst(
+    const void *src, const int64_t *unit_offset, int64_t nunit,
+    int64_t nsample, int32_t nchan, int32_t npol, int32_t item_nbytes,
+    const int64_t *t_begin, const int64_t *t_end, const int64_t *out_t0,
+    float *out, void *stream) {
+    if (!src || !unit_offset || !t_begin || !t_end || !out_t0 || !out)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (!aligned(out, 4))
+        return set_error(BB_ERR_ALIGNMENT, "out must be 4-byte aligned");
+    TFGeom g;
+    if (const char *msg = tf_fill_geom(g, nunit, nsample, nchan, npol,
+                                       item_nbytes, aligned(out, 16)))
+        return set_error(BB_ERR_ARGUMENT, "%s", msg);
+    if (nunit == 0) return BB_OK;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.t_begin = (const long long *)t_begin;
+    g.t_end = (const long long *)t_end;
+    g.out_t0 = (const long long *)out_t0;
+    g.out = out;
+    g.in = nullptr;
+    const uint32_t per = kTFThreads * kTFUnroll;
+    dim3 grid((g.items_per_unit + per - 1) / per, (unsigned)nunit);
+    k_int8_decode_timefirst<<<grid, kTFThreads, 0, as_stream(stream)>>>(g);
+    BB_CHECK_LAUNCH("bb_decode_int8_timefirst launch");
+    return BB_OK;
+}
+
+extern "C" int bb_encode_int8_timefirst(
+    const void *in, int32_t in_dtype, void *dst, const int64_t *unit_offset,
+    int64_t nunit, int64_t nsample, int32_t nchan, int32_t npol,
+    int32_t item_nbytes, void *stream) {
+    if (!in || !dst || !unit_offset)
+        return set_error(BB_ERR_ARGUMENT, "null pointer argument");
+    if (in_dtype != BB_F32 && in_dtype != BB_F64)
+        return set_error(BB_ERR_ARGUMENT, "in_dtype must be BB_F32 or BB_F64");
+    TFGeom g;
+    if (const char *msg = tf_fill_geom(g, nunit, nsample, nchan, npol,
+                                       item_nbytes, aligned(in, 16)))
+        return set_error(BB_ERR_ARGUMENT, "%s", msg);
+    if (nunit == 0) return BB_OK;
+    g.src = (const uint8_t *)dst;
+    g.unit_offset = (const long long *)unit_offset;
+    g.t_begin = g.t_end = g.out_t0 = nullptr;
+    g.out = nullptr;
+    g.in = in;
+    const uint32_t per = kTFThreads * kTFUnroll;
+    dim3 grid((g.items_per_unit + per - 1) / per, (unsigned)nunit);
+    cudaStream_t s = as_stream(stream);
+    if (in_dtype == BB_F32)
+        k_int8_encode_timefirst<float><<<grid, kTFThreads, 0, s>>>(g);
+    else
+        k_int8_encode_timefirst<double><<<grid, kTFThreads, 0, s>>>(g);
+    BB_CHECK_LAUNCH("bb_encode_int8_timefirst launch");
     return BB_OK;
 }

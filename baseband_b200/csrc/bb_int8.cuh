@@ -429,4 +429,135 @@ BB_HD void f8_enc_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
     }
 }
 
+// ------------------------------------------------------------------------
+// Time-first GUPPI payloads (baseband/guppi/payload.py:97-102, :131-134):
+//     in  unit: [nsample][nchan][npol] items of IB int8 (1 real, 2 complex)
+//     out     : [sample][npol][nchan] items -> IB floats each
+// i.e. within every time sample the (chan, pol) axes swap.  An item of work
+// is V consecutive output floats of one (sample, pol) row -- V = 4 when
+// nchan * IB is a multiple of 4 (one float4 store; a warp store covers 512
+// contiguous bytes), else 1.  The int8 reads are strided by npol * IB bytes
+// but stay within the sample's contiguous bytes, which neighbouring threads
+// read too (L1 hits); the input is a fifth of the traffic.
+struct TFGeom {
+    const uint8_t *src;              // decode input / encode output
+    const long long *unit_offset;    // [nunit]
+    const long long *t_begin, *t_end, *out_t0;      // decode only
+    float *out;
+    const void *in;                  // encode input
+    uint32_t nunit, nsample, nchan, npol, ib, vec;
+    uint32_t sample_floats;          // npol * nchan * ib
+    uint32_t items_per_unit;         // nsample * sample_floats / vec
+    FastDiv div_sample_items, div_row_items;
+};
+
+struct TFItem { uint32_t t, pol, chan, k, o; };
+
+BB_HD TFItem tf_item(const TFGeom &p, uint32_t item) {
+    TFItem it;
+    uint32_t r, cc;
+    p.div_sample_items.divmod(item, it.t, r);
+    p.div_row_items.divmod(r, it.pol, cc);
+    it.o = r * p.vec;                              // float within the sample
+    const uint32_t f = cc * p.vec;                 // float within the row
+    it.chan = p.ib == 2 ? f >> 1 : f;
+    it.k = p.ib == 2 ? (f & 1u) : 0u;
+    return it;
+}
+
+// byte of (sample t, chan, pol, component k) within the unit
+BB_HD size_t tf_byte(const TFGeom &p, size_t t, uint32_t chan, uint32_t pol,
+                     uint32_t k) {
+    return ((t * p.nchan + chan) * p.npol + pol) * p.ib + k;
+}
+
+BB_HD void tf_decode(const TFGeom &p, uint32_t unit, uint32_t item) {
+    if (item >= p.items_per_unit) return;
+    const long long off = p.unit_offset[unit];
+    if (off < 0) return;
+    const TFItem it = tf_item(p, item);
+    const long long t = p.t_begin[unit] + it.t;
+    if (t >= p.t_end[unit] || t >= (long long)p.nsample) return;
+    const int8_t *s = reinterpret_cast<const int8_t *>(p.src + off);
+    float *dst = p.out + ((size_t)(p.out_t0[unit] + it.t) * p.sample_floats
+                          + it.o);
+    if (p.vec == 4) {
+        F4 v;
+        if (p.ib == 2) {
+            const size_t b0 = tf_byte(p, (size_t)t, it.chan, it.pol, 0);
+            const size_t b1 = tf_byte(p, (size_t)t, it.chan + 1, it.pol, 0);
+            v = F4{(float)s[b0], (float)s[b0 + 1], (float)s[b1],
+                   (float)s[b1 + 1]};
+        } else {
+            const size_t b0 = tf_byte(p, (size_t)t, it.chan, it.pol, 0);
+            const size_t st = p.npol;
+            v = F4{(float)s[b0], (float)s[b0 + st], (float)s[b0 + 2 * st],
+                   (float)s[b0 + 3 * st]};
+        }
+        *reinterpret_cast<F4 *>(dst) = v;
+    } else {
+        *dst = (float)s[tf_byte(p, (size_t)t, it.chan, it.pol, it.k)];
+    }
+}
+
+template <typename T>
+BB_HD void tf_encode(const TFGeom &p, uint32_t unit, uint32_t item) {
+    if (item >= p.items_per_unit) return;
+    const long long off = p.unit_offset[unit];
+    if (off < 0) return;
+    const TFItem it = tf_item(p, item);
+    uint8_t *d = const_cast<uint8_t *>(p.src) + off;
+    const T *q = reinterpret_cast<const T *>(p.in)
+        + (((size_t)unit * p.nsample + it.t) * p.sample_floats + it.o);
+    if (p.vec == 4) {
+        T v[4];
+        f8_load4(q, v);
+        if (p.ib == 2) {
+            const size_t b0 = tf_byte(p, it.t, it.chan, it.pol, 0);
+            const size_t b1 = tf_byte(p, it.t, it.chan + 1, it.pol, 0);
+            d[b0] = (uint8_t)quant_sint<T, 8>(v[0]);
+            d[b0 + 1] = (uint8_t)quant_sint<T, 8>(v[1]);
+            d[b1] = (uint8_t)quant_sint<T, 8>(v[2]);
+            d[b1 + 1] = (uint8_t)quant_sint<T, 8>(v[3]);
+        } else {
+            const size_t b0 = tf_byte(p, it.t, it.chan, it.pol, 0);
+            const size_t st = p.npol;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                d[b0 + j * st] = (uint8_t)quant_sint<T, 8>(v[j]);
+        }
+    } else {
+        d[tf_byte(p, it.t, it.chan, it.pol, it.k)] =
+            (uint8_t)quant_sint<T, 8>(q[0]);
+    }
+}
+
+// Host-side validation / geometry shared with the CPU emulation.
+inline const char *tf_fill_geom(TFGeom &g, int64_t nunit, int64_t nsample,
+                                int32_t nchan, int32_t npol,
+                                int32_t item_nbytes, bool aligned16) {
+    if (item_nbytes != 1 && item_nbytes != 2)
+        return "item_nbytes must be 1 or 2";
+    if (nunit < 0 || nunit > 65535 || nsample < 1 || nchan < 1 || npol < 1)
+        return "bad nunit/nsample/nchan/npol";
+    const uint64_t sf = (uint64_t)npol * nchan * item_nbytes;
+    const uint32_t vec = (aligned16 && ((uint64_t)nchan * item_nbytes) % 4 == 0)
+        ? 4 : 1;
+    const uint64_t items = (uint64_t)nsample * sf / vec;
+    if (sf > 0x7fffffffull || items > 0xffffffffull)
+        return "unit too large for one call; split it along time";
+    g.nunit = (uint32_t)nunit;
+    g.nsample = (uint32_t)nsample;
+    g.nchan = (uint32_t)nchan;
+    g.npol = (uint32_t)npol;
+    g.ib = (uint32_t)item_nbytes;
+    g.vec = vec;
+    g.sample_floats = (uint32_t)sf;
+    g.items_per_unit = (uint32_t)items;
+    g.div_sample_items = make_fastdiv((uint32_t)(sf / vec));
+    g.div_row_items = make_fastdiv((uint32_t)((uint64_t)nchan * item_nbytes
+                                              / vec));
+    return nullptr;
+}
+
 }  // namespace bb

@@ -164,11 +164,8 @@ class GUPPIStreamWriter(_GUPPIStreamBase, StreamWriterBase):
             kernels.encode_int8_transposed(flat, frames.view(-1), uo, nframe,
                                            h0.nchan, spf * h0.npol, ib)
         else:
-            t = flat.view(nframe * spf, h0.npol, h0.nchan, ib).permute(
-                0, 2, 1, 3).contiguous()
-            kernels.encode_bitfield(t.reshape(-1), frames.view(-1), uo,
-                                    nframe, 1, h0.payload_nbytes, 8, 1,
-                                    kernels.QUANT_SINT)
+            kernels.encode_int8_timefirst(flat, frames.view(-1), uo, nframe,
+                                          spf, h0.nchan, h0.npol, ib)
         return frames.view(-1)
 
 

@@ -50,20 +50,11 @@ def decode_device(raw, offsets, nsample, npol, nchan, complex_data,
                                        nsample * npol, ib, tables[1],
                                        tables[2], tables[3], out)
         return out
-    # time first: plain int8 -> float32 of the wanted rows, then swap the
-    # (chan, pol) axes on the device
-    uo = torch.from_numpy(np.asarray(offsets, np.int64)).to(dev)
-    nelem = nchan * npol * ib
-    row = 0
-    for u in range(nunit):
-        n = int(end[u] - begin[u])
-        tmp = kernels.decode_bitfield(
-            raw, uo[u:u + 1], 1, 1, nsample * nelem, 8, nelem, complex_data,
-            kernels.CODEC_SINT, None, 0., int(begin[u]), n)
-        dst = out[int(first[u]) * nelem:(int(first[u]) + n) * nelem]
-        dst.view(n, npol, nchan, ib).copy_(
-            tmp.view(n, nchan, npol, ib).permute(0, 2, 1, 3))
-        row += n
+    # time first: the (chan, pol) axes of every sample swap in the kernel
+    tables = torch.from_numpy(np.stack(
+        [np.asarray(offsets, np.int64), begin, end, first])).to(dev)
+    kernels.decode_int8_timefirst(raw, tables[0], nunit, nsample, nchan, npol,
+                                  ib, tables[1], tables[2], tables[3], out)
     return out
 
 
@@ -195,9 +186,10 @@ class GUPPIPayload(PayloadBase):
             words.reshape(nchan, -1)[:, start * npol * ib:
                                      stop * npol * ib] = rows
         else:
-            t = t.view(n, npol, nchan, ib).permute(0, 2, 1, 3).contiguous()
-            packed = torch.empty(t.numel(), dtype=torch.uint8, device=dev)
-            kernels.encode_bitfield(t.reshape(-1), packed, _const(dev, 0), 1,
-                                    1, t.numel(), 8, 1, kernels.QUANT_SINT)
+            packed = torch.empty(n * nchan * npol * ib, dtype=torch.uint8,
+                                 device=dev)
+            kernels.encode_int8_timefirst(t.reshape(-1), packed,
+                                          _const(dev, 0), 1, n, nchan, npol,
+                                          ib)
             per = nchan * npol * ib
             words[start * per:stop * per] = _device.download(packed)

@@ -217,6 +217,38 @@ def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
     return dst
 
 
+def decode_int8_timefirst(src, unit_offset, nunit, nsample, nchan, npol,
+                          item_nbytes, t_begin, t_end, out_t0, out):
+    """bb_decode_int8_timefirst: [time][chan][pol] int8 -> (time, pol, chan)
+    float32 rows of ``out``."""
+    lib = _lib.load()
+    with _on(src.device):
+        rc = lib.bb_decode_int8_timefirst(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nunit, nsample,
+            nchan, npol, item_nbytes, _dev(t_begin, 't_begin', torch.int64),
+            _dev(t_end, 't_end', torch.int64),
+            _dev(out_t0, 'out_t0', torch.int64),
+            _dev(out, 'out', torch.float32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return out
+
+
+def encode_int8_timefirst(data, dst, unit_offset, nunit, nsample, nchan, npol,
+                          item_nbytes):
+    lib = _lib.load()
+    code = F32 if data.dtype == torch.float32 else F64
+    with _on(dst.device):
+        rc = lib.bb_encode_int8_timefirst(
+            _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nunit, nsample,
+            nchan, npol, item_nbytes, _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst
+
+
 VDIF_NFIELD = 17
 # row indices of the ``fields`` array (enum bb_vdif_field / bb_mark5b_field)
 (VDIF_INVALID, VDIF_LEGACY, VDIF_SECONDS, VDIF_REF_EPOCH, VDIF_FRAME_NR,

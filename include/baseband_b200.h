@@ -184,6 +184,23 @@ int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
                               int64_t nrow, int64_t ncol, int32_t item_nbytes,
                               void *stream);
 
+/* Time-first GUPPI payloads (PKTFMT other than '1SFA';
+ * baseband/guppi/payload.py:97-102 decode, :131-134 encode): unit u at
+ * src + unit_offset[u] holds [nsample][nchan][npol] items of item_nbytes
+ * int8; samples [t_begin[u], t_end[u]) are written as float32
+ * [npol][nchan][item] starting at output sample out_t0[u] (the same window
+ * tables as above, counted in samples).  Encode takes whole units,
+ * in = [nunit * nsample][npol][nchan][item] float32/float64. */
+int bb_decode_int8_timefirst(const void *src, const int64_t *unit_offset,
+                             int64_t nunit, int64_t nsample, int32_t nchan,
+                             int32_t npol, int32_t item_nbytes,
+                             const int64_t *t_begin, const int64_t *t_end,
+                             const int64_t *out_t0, float *out, void *stream);
+int bb_encode_int8_timefirst(const void *in, int32_t in_dtype, void *dst,
+                             const int64_t *unit_offset, int64_t nunit,
+                             int64_t nsample, int32_t nchan, int32_t npol,
+                             int32_t item_nbytes, void *stream);
+
 /* ------------------------------------------------------- header batches
  * VDIF: extract the bit-fields of baseband/vdif/header.py:529-542, :557-559
  * (generic extractor baseband/base/header.py:35-87) for `nframe` headers at

@@ -97,4 +97,44 @@ int bb_encode_int8_transposed(const void *in, int32_t in_dtype, void *dst,
     return 0;
 }
 
+int bb_decode_int8_timefirst(const void *src, const int64_t *unit_offset,
+                             int64_t nunit, int64_t nsample, int32_t nchan,
+                             int32_t npol, int32_t item_nbytes,
+                             const int64_t *t_begin, const int64_t *t_end,
+                             const int64_t *out_t0, float *out, void *stream) {
+    TFGeom g;
+    if (tf_fill_geom(g, nunit, nsample, nchan, npol, item_nbytes,
+                     (reinterpret_cast<uintptr_t>(out) & 15u) == 0))
+        return BB_ERR_ARGUMENT;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.t_begin = (const long long *)t_begin;
+    g.t_end = (const long long *)t_end;
+    g.out_t0 = (const long long *)out_t0;
+    g.out = out; g.in = nullptr;
+    for (uint32_t u = 0; u < g.nunit; ++u)
+        for (uint32_t i = 0; i < g.items_per_unit; ++i) tf_decode(g, u, i);
+    return 0;
+}
+
+int bb_encode_int8_timefirst(const void *in, int32_t in_dtype, void *dst,
+                             const int64_t *unit_offset, int64_t nunit,
+                             int64_t nsample, int32_t nchan, int32_t npol,
+                             int32_t item_nbytes, void *stream) {
+    TFGeom g;
+    if (tf_fill_geom(g, nunit, nsample, nchan, npol, item_nbytes,
+                     (reinterpret_cast<uintptr_t>(in) & 15u) == 0))
+        return BB_ERR_ARGUMENT;
+    g.src = (const uint8_t *)dst;
+    g.unit_offset = (const long long *)unit_offset;
+    g.t_begin = g.t_end = g.out_t0 = nullptr;
+    g.out = nullptr; g.in = in;
+    for (uint32_t u = 0; u < g.nunit; ++u)
+        for (uint32_t i = 0; i < g.items_per_unit; ++i) {
+            if (in_dtype == BB_F32) tf_encode<float>(g, u, i);
+            else tf_encode<double>(g, u, i);
+        }
+    return 0;
+}
+
 }  // extern "C"

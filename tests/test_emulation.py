@@ -240,6 +240,42 @@ def test_int8_transposed(emu, case):
         assert np.array_equal(dst, c['raw'])
 
 
+@pytest.mark.parametrize('case', int8_cases.TF_CASES, ids=lambda c: c[0])
+def test_int8_timefirst(emu, case):
+    c = int8_cases.make_tf_case(case)
+    want = int8_cases.oracle_tf_decode(c)
+    out = _aligned_f32(want.size)
+    out[:] = np.nan
+    rc = emu.bb_decode_int8_timefirst(
+        _ptr(c['raw']), _ptr(c['unit_offset']), c['nunit'], c['nsample'],
+        c['nchan'], c['npol'], c['ib'], _ptr(c['t_begin']), _ptr(c['t_end']),
+        _ptr(c['out_t0']), _ptr(out), None)
+    assert rc == 0
+    assert np.array_equal(out.reshape(want.shape), want, equal_nan=True)
+    full = dict(c, t_begin=np.zeros(c['nunit'], np.int64),
+                t_end=np.full(c['nunit'], c['nsample'], np.int64),
+                out_t0=np.arange(c['nunit'], dtype=np.int64) * c['nsample'],
+                nout=c['nunit'] * c['nsample'])
+    data = int8_cases.oracle_tf_decode(full, fill=0.0)
+    for dtype, code in ((np.float32, 0), (np.float64, 1)):
+        src = _aligned_f32(data.size * (2 if code else 1)).view(dtype)
+        src[:] = data.ravel()
+        dst = c['raw'].copy()
+        for u in range(c['nunit']):
+            if c['unit_offset'][u] >= 0:
+                dst[c['truth'][u]:c['truth'][u] + c['unit_nbytes']] = 0
+        rc = emu.bb_encode_int8_timefirst(
+            _ptr(src), code, _ptr(dst), _ptr(c['unit_offset']), c['nunit'],
+            c['nsample'], c['nchan'], c['npol'], c['ib'], None)
+        assert rc == 0
+        assert np.array_equal(dst, c['raw'])
+
+
+def test_fuzz_int8_timefirst(emu):
+    for case in int8_cases.tf_fuzz_cases(60, seed=78):
+        test_int8_timefirst(emu, case)
+
+
 def test_int8_guppi_sample(emu, sample_outputs):
     """sample_puppi.raw frames through the transpose path == reference
     GUPPIPayload.data (channels first)."""

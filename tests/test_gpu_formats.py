@@ -137,6 +137,38 @@ def test_int8_transposed(case):
         assert np.array_equal(dst.cpu().numpy(), c['raw'])
 
 
+@pytest.mark.parametrize('case', int8_cases.TF_CASES
+                         + int8_cases.tf_fuzz_cases(40, seed=78),
+                         ids=lambda c: c[0])
+def test_int8_timefirst(case):
+    c = int8_cases.make_tf_case(case)
+    want = int8_cases.oracle_tf_decode(c)
+    out = torch.full((want.size,), float('nan'), dtype=torch.float32,
+                     device=DEV)
+    kernels.decode_int8_timefirst(
+        _t(c['raw']), _t(c['unit_offset']), c['nunit'], c['nsample'],
+        c['nchan'], c['npol'], c['ib'], _t(c['t_begin']), _t(c['t_end']),
+        _t(c['out_t0']), out)
+    assert np.array_equal(out.cpu().numpy().reshape(want.shape), want,
+                          equal_nan=True)
+    full = dict(c, t_begin=np.zeros(c['nunit'], np.int64),
+                t_end=np.full(c['nunit'], c['nsample'], np.int64),
+                out_t0=np.arange(c['nunit'], dtype=np.int64) * c['nsample'],
+                nout=c['nunit'] * c['nsample'])
+    data = int8_cases.oracle_tf_decode(full, fill=0.0)
+    for dtype in (np.float32, np.float64):
+        dst = c['raw'].copy()
+        for u in range(c['nunit']):
+            if c['unit_offset'][u] >= 0:
+                dst[c['truth'][u]:c['truth'][u] + c['unit_nbytes']] = 0
+        dst = _t(dst)
+        kernels.encode_int8_timefirst(_t(data.astype(dtype)), dst,
+                                      _t(c['unit_offset']), c['nunit'],
+                                      c['nsample'], c['nchan'], c['npol'],
+                                      c['ib'])
+        assert np.array_equal(dst.cpu().numpy(), c['raw'])
+
+
 def test_vdif_scan_sample(sample_outputs):
     raw = sample_bytes('sample.vdif')
     fields_want = sample_outputs['sample_vdif_fields']

@@ -157,6 +157,28 @@ def extra(gib):
           % ('C4 guppi 512ch 2pol int8', nbytes / best / 1e6,
              nbytes / med / 1e6, full.numel() / med / 1e6, med))
     print('    round trip identical:', bool(torch.equal(back, raw)))
+    del full, back
+    torch.cuda.empty_cache()
+    # GUPPI time first (PKTFMT other than 1SFA): [time][chan][pol] per frame
+    nt = fbytes // (nchan * npol * 2)
+    tb = torch.zeros(nfr, dtype=torch.int64, device=DEV)
+    te = torch.full((nfr,), nt, dtype=torch.int64, device=DEV)
+    t0 = torch.arange(nfr, dtype=torch.int64, device=DEV) * nt
+    out = torch.empty((nfr * nt * npol * nchan * 2,), dtype=torch.float32,
+                      device=DEV)
+    best, med = timeit(lambda: kernels.decode_int8_timefirst(
+        raw, off, nfr, nt, nchan, npol, 2, tb, te, t0, out))
+    nbytes = out.numel() * 5
+    print('DEC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('guppi time-first 512ch 2pol', nbytes / best / 1e6,
+             nbytes / med / 1e6, out.numel() / med / 1e6, med))
+    back = torch.zeros_like(raw)
+    best, med = timeit(lambda: kernels.encode_int8_timefirst(
+        out, back, off, nfr, nt, nchan, npol, 2))
+    print('ENC %-28s %7.1f GB/s best %7.1f med  %7.1f Gsamp/s  (%.2f ms)'
+          % ('guppi time-first 512ch 2pol', nbytes / best / 1e6,
+             nbytes / med / 1e6, out.numel() / med / 1e6, med))
+    print('    round trip identical:', bool(torch.equal(back, raw)))
 
 
 if __name__ == '__main__':
