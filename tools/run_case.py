@@ -1,5 +1,7 @@
 """Run one kernel case a few times (for ncu captures).
-usage: python tools/run_case.py {guppi|mark5b|mark4enc|vdif48|c2} [gib]"""
+usage: python tools/run_case.py {guppi|guppitf|mark5b|mark4enc|vdif48|vdif44|
+vdif22c|vdif84|c2} [gib]   (REPS=n launches per kernel, default 3)"""
+import os
 import sys
 
 import torch
@@ -10,7 +12,7 @@ from baseband_b200 import kernels, levels  # noqa: E402
 DEV = 'cuda:0'
 case = sys.argv[1]
 gib = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
-reps = 3
+reps = int(os.environ.get('REPS', 3))
 if case == 'guppi':
     nchan, npol, spf, ov = 512, 2, 65536, 512
     fbytes = nchan * spf * npol * 2
@@ -26,17 +28,35 @@ if case == 'guppi':
     for _ in range(reps):
         kernels.decode_int8_transposed(raw, off, nfr, nchan, spf * npol, 2,
                                        cb, ce, oc0, out)
-elif case in ('mark5b', 'c2', 'vdif48'):
+elif case == 'guppitf':
+    nchan, npol, nt = 512, 2, 65536
+    fbytes = nchan * nt * npol * 2
+    nfr = max(1, int(gib * 2**30) // fbytes)
+    raw = torch.randint(0, 256, (nfr * fbytes,), dtype=torch.uint8, device=DEV)
+    off = torch.arange(nfr, dtype=torch.int64, device=DEV) * fbytes
+    tb = torch.zeros(nfr, dtype=torch.int64, device=DEV)
+    te = torch.full((nfr,), nt, dtype=torch.int64, device=DEV)
+    t0 = torch.arange(nfr, dtype=torch.int64, device=DEV) * nt
+    out = torch.empty((nfr * nt * npol * nchan * 2,), dtype=torch.float32,
+                      device=DEV)
+    back = torch.zeros_like(raw)
+    for _ in range(reps):
+        kernels.decode_int8_timefirst(raw, off, nfr, nt, nchan, npol, 2, tb,
+                                      te, t0, out)
+    for _ in range(reps):
+        kernels.encode_int8_timefirst(out, back, off, nfr, nt, nchan, npol, 2)
+elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84'):
     bps, nthread, nelem, payload, hdr = {
         'mark5b': (2, 1, 16, 10000, 16), 'c2': (2, 16, 1, 8000, 32),
-        'vdif48': (2, 4, 8, 8000, 32)}[case]
+        'vdif48': (2, 4, 8, 8000, 32), 'vdif44': (4, 4, 1, 8000, 32),
+        'vdif22c': (2, 2, 2, 8000, 32), 'vdif84': (8, 4, 1, 8000, 32)}[case]
     frame = payload + hdr
     nset = int(gib * 2**30) // frame // nthread
     nunit = nset * nthread
     raw = torch.randint(0, 256, (nunit * frame,), dtype=torch.uint8,
                         device=DEV)
     uo = torch.arange(nunit, dtype=torch.int64, device=DEV) * frame + hdr
-    lv = levels.mark5b(2) if case == 'mark5b' else levels.offset_binary(2)
+    lv = levels.mark5b(2) if case == 'mark5b' else levels.offset_binary(bps)
     out = None
     for _ in range(reps):
         out = kernels.decode_bitfield(raw, uo, nset, nthread, payload, bps,
