@@ -433,12 +433,12 @@ BB_HD void f8_enc_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
 // Time-first GUPPI payloads (baseband/guppi/payload.py:97-102, :131-134):
 //     in  unit: [nsample][nchan][npol] items of IB int8 (1 real, 2 complex)
 //     out     : [sample][npol][nchan] items -> IB floats each
-// i.e. within every time sample the (chan, pol) axes swap.  An item of work
-// is V consecutive output floats of one (sample, pol) row -- V = 4 when
-// nchan * IB is a multiple of 4 (one float4 store; a warp store covers 512
-// contiguous bytes), else 1.  The int8 reads are strided by npol * IB bytes
-// but stay within the sample's contiguous bytes, which neighbouring threads
-// read too (L1 hits); the input is a fifth of the traffic.
+// i.e. within every time sample the (chan, pol) axes swap.  Vector path
+// (nchan * IB a multiple of 4, npol 1, 2 or 4): an item is one group of
+// 4 / IB channels of one sample = 4 * npol CONTIGUOUS input bytes, read with
+// one 4/8/16-byte load (consecutive lanes read consecutive groups), and npol
+// float4 stores, one per polarisation row; each of those warp stores covers
+// 512 contiguous bytes.  Anything else: one float per item, bytewise.
 struct TFGeom {
     const uint8_t *src;              // decode input / encode output
     const long long *unit_offset;    // [nunit]
@@ -447,57 +447,145 @@ struct TFGeom {
     const void *in;                  // encode input
     uint32_t nunit, nsample, nchan, npol, ib, vec;
     uint32_t sample_floats;          // npol * nchan * ib
-    uint32_t items_per_unit;         // nsample * sample_floats / vec
-    FastDiv div_sample_items, div_row_items;
+    uint32_t row_floats;             // nchan * ib
+    uint32_t items_per_unit;
+    FastDiv div_sample_items, div_row_floats;
 };
 
-struct TFItem { uint32_t t, pol, chan, k, o; };
-
-BB_HD TFItem tf_item(const TFGeom &p, uint32_t item) {
-    TFItem it;
-    uint32_t r, cc;
-    p.div_sample_items.divmod(item, it.t, r);
-    p.div_row_items.divmod(r, it.pol, cc);
-    it.o = r * p.vec;                              // float within the sample
-    const uint32_t f = cc * p.vec;                 // float within the row
-    it.chan = p.ib == 2 ? f >> 1 : f;
-    it.k = p.ib == 2 ? (f & 1u) : 0u;
-    return it;
+BB_HD uint32_t tf_get_byte(const uint32_t *w, int i) {
+    return (w[i >> 2] >> (8 * (i & 3))) & 0xffu;
 }
 
-// byte of (sample t, chan, pol, component k) within the unit
-BB_HD size_t tf_byte(const TFGeom &p, size_t t, uint32_t chan, uint32_t pol,
-                     uint32_t k) {
-    return ((t * p.nchan + chan) * p.npol + pol) * p.ib + k;
+// The 4 * NPOL bytes of (sample t, channel group cg), as NPOL words.
+template <int NPOL>
+BB_HD void tf_load_group(const uint8_t *s, uint32_t w[NPOL]) {
+    if ((reinterpret_cast<uintptr_t>(s) & (4 * NPOL - 1)) == 0) {
+        if (NPOL == 4) {
+            const F4 v = *reinterpret_cast<const F4 *>(s);   // 16-byte load
+            const uint32_t *u = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+            for (int i = 0; i < NPOL; ++i) w[i] = u[i];
+        } else if (NPOL == 2) {
+            const F2 v = *reinterpret_cast<const F2 *>(s);   // 8-byte load
+            const uint32_t *u = reinterpret_cast<const uint32_t *>(&v);
+#pragma unroll
+            for (int i = 0; i < NPOL; ++i) w[i] = u[i];
+        } else {
+            w[0] = *reinterpret_cast<const uint32_t *>(s);
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < NPOL; ++i)
+        w[i] = (uint32_t)s[4 * i] | ((uint32_t)s[4 * i + 1] << 8)
+            | ((uint32_t)s[4 * i + 2] << 16) | ((uint32_t)s[4 * i + 3] << 24);
+}
+
+template <int NPOL>
+BB_HD void tf_store_group(uint8_t *d, const uint32_t w[NPOL]) {
+    if ((reinterpret_cast<uintptr_t>(d) & (4 * NPOL - 1)) == 0) {
+        if (NPOL == 4) {
+            F4 v;
+            uint32_t *u = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+            for (int i = 0; i < NPOL; ++i) u[i] = w[i];
+            *reinterpret_cast<F4 *>(d) = v;
+        } else if (NPOL == 2) {
+            F2 v;
+            uint32_t *u = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+            for (int i = 0; i < NPOL; ++i) u[i] = w[i];
+            *reinterpret_cast<F2 *>(d) = v;
+        } else {
+            *reinterpret_cast<uint32_t *>(d) = w[0];
+        }
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < 4 * NPOL; ++i) d[i] = (uint8_t)tf_get_byte(w, i);
+}
+
+BB_HD float tf_f(uint32_t b) { return (float)(int8_t)b; }
+
+template <int NPOL>
+BB_HD void tf_decode_group(const TFGeom &p, uint32_t unit, uint32_t item,
+                           long long off) {
+    uint32_t t_rel, cg;
+    p.div_sample_items.divmod(item, t_rel, cg);
+    const long long t = p.t_begin[unit] + t_rel;
+    if (t >= p.t_end[unit] || t >= (long long)p.nsample) return;
+    uint32_t w[NPOL];
+    tf_load_group<NPOL>(p.src + off
+                        + ((size_t)t * (p.row_floats / 4) + cg) * (4 * NPOL), w);
+    float *dst = p.out + ((size_t)(p.out_t0[unit] + t_rel) * p.sample_floats
+                          + 4 * cg);
+#pragma unroll
+    for (int pol = 0; pol < NPOL; ++pol) {
+        F4 v;
+        if (p.ib == 2) {             // bytes [chan 0..1][pol][re, im]
+            const int i0 = 2 * pol, i1 = 2 * (NPOL + pol);
+            v = F4{tf_f(tf_get_byte(w, i0)), tf_f(tf_get_byte(w, i0 + 1)),
+                   tf_f(tf_get_byte(w, i1)), tf_f(tf_get_byte(w, i1 + 1))};
+        } else {                     // bytes [chan 0..3][pol]
+            v = F4{tf_f(tf_get_byte(w, pol)), tf_f(tf_get_byte(w, NPOL + pol)),
+                   tf_f(tf_get_byte(w, 2 * NPOL + pol)),
+                   tf_f(tf_get_byte(w, 3 * NPOL + pol))};
+        }
+        *reinterpret_cast<F4 *>(dst + (size_t)pol * p.row_floats) = v;
+    }
 }
 
 BB_HD void tf_decode(const TFGeom &p, uint32_t unit, uint32_t item) {
     if (item >= p.items_per_unit) return;
     const long long off = p.unit_offset[unit];
     if (off < 0) return;
-    const TFItem it = tf_item(p, item);
-    const long long t = p.t_begin[unit] + it.t;
-    if (t >= p.t_end[unit] || t >= (long long)p.nsample) return;
-    const int8_t *s = reinterpret_cast<const int8_t *>(p.src + off);
-    float *dst = p.out + ((size_t)(p.out_t0[unit] + it.t) * p.sample_floats
-                          + it.o);
     if (p.vec == 4) {
-        F4 v;
-        if (p.ib == 2) {
-            const size_t b0 = tf_byte(p, (size_t)t, it.chan, it.pol, 0);
-            const size_t b1 = tf_byte(p, (size_t)t, it.chan + 1, it.pol, 0);
-            v = F4{(float)s[b0], (float)s[b0 + 1], (float)s[b1],
-                   (float)s[b1 + 1]};
-        } else {
-            const size_t b0 = tf_byte(p, (size_t)t, it.chan, it.pol, 0);
-            const size_t st = p.npol;
-            v = F4{(float)s[b0], (float)s[b0 + st], (float)s[b0 + 2 * st],
-                   (float)s[b0 + 3 * st]};
-        }
-        *reinterpret_cast<F4 *>(dst) = v;
-    } else {
-        *dst = (float)s[tf_byte(p, (size_t)t, it.chan, it.pol, it.k)];
+        if (p.npol == 2) tf_decode_group<2>(p, unit, item, off);
+        else if (p.npol == 4) tf_decode_group<4>(p, unit, item, off);
+        else tf_decode_group<1>(p, unit, item, off);
+        return;
     }
+    // one float per item: (sample, pol, chan, component)
+    uint32_t t_rel, r, pol, f;
+    p.div_sample_items.divmod(item, t_rel, r);
+    p.div_row_floats.divmod(r, pol, f);
+    const long long t = p.t_begin[unit] + t_rel;
+    if (t >= p.t_end[unit] || t >= (long long)p.nsample) return;
+    const uint32_t chan = p.ib == 2 ? f >> 1 : f, k = p.ib == 2 ? (f & 1u) : 0u;
+    const int8_t *s = reinterpret_cast<const int8_t *>(p.src + off);
+    p.out[(size_t)(p.out_t0[unit] + t_rel) * p.sample_floats + r] =
+        (float)s[(((size_t)t * p.nchan + chan) * p.npol + pol) * p.ib + k];
+}
+
+template <typename T, int NPOL>
+BB_HD void tf_encode_group(const TFGeom &p, uint32_t unit, uint32_t item,
+                           long long off) {
+    uint32_t t, cg;
+    p.div_sample_items.divmod(item, t, cg);
+    const T *q = reinterpret_cast<const T *>(p.in)
+        + (((size_t)unit * p.nsample + t) * p.sample_floats + 4 * cg);
+    T v[NPOL][4];
+#pragma unroll
+    for (int pol = 0; pol < NPOL; ++pol)
+        f8_load4(q + (size_t)pol * p.row_floats, v[pol]);
+    uint32_t w[NPOL];
+#pragma unroll
+    for (int i = 0; i < NPOL; ++i) w[i] = 0u;
+#pragma unroll
+    for (int pol = 0; pol < NPOL; ++pol) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // float j of the row piece -> byte position within the group
+            const int i2 = 2 * ((j >> 1) * NPOL + pol) + (j & 1);
+            const int i1 = j * NPOL + pol;
+            const uint32_t code = quant_sint<T, 8>(v[pol][j]);
+            if (p.ib == 2) w[i2 >> 2] |= code << (8 * (i2 & 3));
+            else w[i1 >> 2] |= code << (8 * (i1 & 3));
+        }
+    }
+    tf_store_group<NPOL>(const_cast<uint8_t *>(p.src) + off
+                         + ((size_t)t * (p.row_floats / 4) + cg) * (4 * NPOL),
+                         w);
 }
 
 template <typename T>
@@ -505,31 +593,21 @@ BB_HD void tf_encode(const TFGeom &p, uint32_t unit, uint32_t item) {
     if (item >= p.items_per_unit) return;
     const long long off = p.unit_offset[unit];
     if (off < 0) return;
-    const TFItem it = tf_item(p, item);
-    uint8_t *d = const_cast<uint8_t *>(p.src) + off;
-    const T *q = reinterpret_cast<const T *>(p.in)
-        + (((size_t)unit * p.nsample + it.t) * p.sample_floats + it.o);
     if (p.vec == 4) {
-        T v[4];
-        f8_load4(q, v);
-        if (p.ib == 2) {
-            const size_t b0 = tf_byte(p, it.t, it.chan, it.pol, 0);
-            const size_t b1 = tf_byte(p, it.t, it.chan + 1, it.pol, 0);
-            d[b0] = (uint8_t)quant_sint<T, 8>(v[0]);
-            d[b0 + 1] = (uint8_t)quant_sint<T, 8>(v[1]);
-            d[b1] = (uint8_t)quant_sint<T, 8>(v[2]);
-            d[b1 + 1] = (uint8_t)quant_sint<T, 8>(v[3]);
-        } else {
-            const size_t b0 = tf_byte(p, it.t, it.chan, it.pol, 0);
-            const size_t st = p.npol;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                d[b0 + j * st] = (uint8_t)quant_sint<T, 8>(v[j]);
-        }
-    } else {
-        d[tf_byte(p, it.t, it.chan, it.pol, it.k)] =
-            (uint8_t)quant_sint<T, 8>(q[0]);
+        if (p.npol == 2) tf_encode_group<T, 2>(p, unit, item, off);
+        else if (p.npol == 4) tf_encode_group<T, 4>(p, unit, item, off);
+        else tf_encode_group<T, 1>(p, unit, item, off);
+        return;
     }
+    uint32_t t, r, pol, f;
+    p.div_sample_items.divmod(item, t, r);
+    p.div_row_floats.divmod(r, pol, f);
+    const uint32_t chan = p.ib == 2 ? f >> 1 : f, k = p.ib == 2 ? (f & 1u) : 0u;
+    const T *q = reinterpret_cast<const T *>(p.in)
+        + (((size_t)unit * p.nsample + t) * p.sample_floats + r);
+    const_cast<uint8_t *>(p.src)[off + (((size_t)t * p.nchan + chan) * p.npol
+                                        + pol) * p.ib + k] =
+        (uint8_t)quant_sint<T, 8>(q[0]);
 }
 
 // Host-side validation / geometry shared with the CPU emulation.
@@ -540,10 +618,13 @@ inline const char *tf_fill_geom(TFGeom &g, int64_t nunit, int64_t nsample,
         return "item_nbytes must be 1 or 2";
     if (nunit < 0 || nunit > 65535 || nsample < 1 || nchan < 1 || npol < 1)
         return "bad nunit/nsample/nchan/npol";
-    const uint64_t sf = (uint64_t)npol * nchan * item_nbytes;
-    const uint32_t vec = (aligned16 && ((uint64_t)nchan * item_nbytes) % 4 == 0)
-        ? 4 : 1;
-    const uint64_t items = (uint64_t)nsample * sf / vec;
+    const uint64_t rf = (uint64_t)nchan * item_nbytes;
+    const uint64_t sf = rf * npol;
+    const bool vec = aligned16 && rf % 4 == 0
+        && (npol == 1 || npol == 2 || npol == 4);
+    // items per sample: channel groups (vector path) or floats
+    const uint64_t per_sample = vec ? rf / 4 : sf;
+    const uint64_t items = (uint64_t)nsample * per_sample;
     if (sf > 0x7fffffffull || items > 0xffffffffull)
         return "unit too large for one call; split it along time";
     g.nunit = (uint32_t)nunit;
@@ -551,12 +632,12 @@ inline const char *tf_fill_geom(TFGeom &g, int64_t nunit, int64_t nsample,
     g.nchan = (uint32_t)nchan;
     g.npol = (uint32_t)npol;
     g.ib = (uint32_t)item_nbytes;
-    g.vec = vec;
+    g.vec = vec ? 4 : 1;
     g.sample_floats = (uint32_t)sf;
+    g.row_floats = (uint32_t)rf;
     g.items_per_unit = (uint32_t)items;
-    g.div_sample_items = make_fastdiv((uint32_t)(sf / vec));
-    g.div_row_items = make_fastdiv((uint32_t)((uint64_t)nchan * item_nbytes
-                                              / vec));
+    g.div_sample_items = make_fastdiv((uint32_t)per_sample);
+    g.div_row_floats = make_fastdiv((uint32_t)rf);
     return nullptr;
 }
 

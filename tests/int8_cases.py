@@ -89,6 +89,10 @@ TF_CASES = [
     ('tf_real_3ch_scalar', 1, 40, 3, 2, 1, None),
     ('tf_1pol', 2, 64, 12, 1, 2, None),
     ('tf_invalid_unit', 3, 16, 8, 2, 2, None),
+    # units at odd byte offsets: the bytewise group load / store
+    ('tf_shift4_2pol', 2, 20, 8, 2, 2, [(2, 20), (0, 11)]),
+    ('tf_shift2_4pol_real', 2, 20, 8, 4, 1, None),
+    ('tf_shift1_1pol', 2, 9, 4, 1, 2, None),
 ]
 
 
@@ -101,6 +105,8 @@ def make_tf_case(case):
                        dtype=np.uint8)
     order = rng.permutation(nunit)
     truth = (order * (unit_nbytes + gap)).astype(np.int64)
+    if 'shift' in cid:
+        truth += int(cid.split('shift')[1][0])
     unit_offset = truth.copy()
     if cid == 'tf_invalid_unit':
         unit_offset[1] = -1
