@@ -19,6 +19,7 @@ CUDA ``torch.Tensor`` as ``out`` keeps the decoded samples on the GPU.
 There is no CPU decode path: without the CUDA library every read raises.
 """
 import operator
+import os
 from collections import namedtuple
 
 import numpy as np
@@ -33,6 +34,64 @@ __all__ = ['StreamBase', 'StreamReaderBase', 'StreamWriterBase',
 # Packed bytes per pipeline stage.  A 2-bit stream expands 16x, so 64 MiB of
 # frames become 1 GiB of float32 per stage (two stages in flight).
 DEFAULT_CHUNK_NBYTES = 64 << 20
+
+# File -> pinned staging buffer: one readinto() copies out of the page cache on
+# a single core (a few GB/s), far below the PCIe link.  Large chunks of plain
+# files are therefore read as several slices with os.preadv on a small thread
+# pool (the system call releases the GIL), which keeps the H2D copy fed.
+PARALLEL_READ_MIN_NBYTES = 8 << 20
+PARALLEL_READ_THREADS = max(1, min(8, len(os.sched_getaffinity(0))
+                                   if hasattr(os, 'sched_getaffinity')
+                                   else (os.cpu_count() or 1)))
+_read_pool = None
+
+
+def _parallel_readinto(fh, offset, view):
+    """Fill the writable uint8 numpy array ``view`` from absolute byte
+    ``offset`` of the plain file behind ``fh``.  Returns the bytes read, or
+    None if ``fh`` is not a plain file (the caller falls back to
+    ``readinto``)."""
+    global _read_pool
+    if PARALLEL_READ_THREADS < 2 or not hasattr(os, 'preadv'):
+        return None
+    # only genuine binary files: anything else with a fileno() (gzip, ...)
+    # would hand out the bytes of the file underneath it
+    import io
+    import stat
+    plain = fh
+    while hasattr(plain, 'fh_raw'):
+        plain = plain.fh_raw
+    raw = plain.raw if isinstance(plain, (io.BufferedReader,
+                                          io.BufferedRandom)) else plain
+    if not isinstance(raw, io.FileIO):
+        return None
+    try:
+        fd = raw.fileno()
+        if not stat.S_ISREG(os.fstat(fd).st_mode):
+            return None
+    except (OSError, ValueError):
+        return None
+    if _read_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _read_pool = ThreadPoolExecutor(PARALLEL_READ_THREADS,
+                                        thread_name_prefix='bb-read')
+    n = view.size
+    step = -(-n // PARALLEL_READ_THREADS)
+    step = (step + 4095) // 4096 * 4096
+
+    def piece(lo):
+        hi = min(lo + step, n)
+        mv = memoryview(view[lo:hi])
+        got = 0
+        while got < hi - lo:
+            k = os.preadv(fd, [mv[got:]], offset + lo + got)
+            if k <= 0:
+                break
+            got += k
+        return got
+
+    return sum(_read_pool.map(piece, range(0, n, step)))
+
 
 _TIME_UNITS = {'s': 1.0, 'ms': 1e3, 'us': 1e6, 'ns': 1e9, 'min': 1 / 60.,
                'h': 1 / 3600., 'day': 1 / 86400.}
@@ -448,9 +507,15 @@ class StreamReaderBase(StreamBase):
             view = zero_copy(offset, pinned.numel())
             if view is not None:
                 return view
-        self.fh_raw.seek(offset)
         view = pinned.numpy()
-        got = self.fh_raw.readinto(memoryview(view))
+        got = None
+        if view.size >= PARALLEL_READ_MIN_NBYTES:
+            got = _parallel_readinto(self.fh_raw, offset, view)
+            if got is not None:
+                self.fh_raw.seek(offset + got)
+        if got is None:
+            self.fh_raw.seek(offset)
+            got = self.fh_raw.readinto(memoryview(view))
         if got != view.size:
             raise EOFError('could not read {} frames at frame {}.'.format(
                 nframe, frame0))

@@ -514,6 +514,46 @@ def guppi_synthetic_and_write():
             assert fr._get_index(h2) == 2
 
 
+def vdif_parallel_file_read():
+    """Large chunks of plain files are read with os.preadv on a thread pool
+    (base/stream.py:_parallel_readinto): same bytes, same samples; other
+    file-like objects fall back to readinto."""
+    import tempfile
+    from baseband_b200.base import stream
+    raw = synthetic.vdif_stream(40, 4, 1000, seed=5)
+    want = ostream.vdif_read(raw)[:, :, 0]
+    calls = []
+    saved = (stream.PARALLEL_READ_MIN_NBYTES, stream.PARALLEL_READ_THREADS,
+             stream._parallel_readinto)
+
+    def spy(fh, offset, view):
+        got = saved[2](fh, offset, view)
+        calls.append(got)
+        return got
+
+    stream.PARALLEL_READ_MIN_NBYTES = 1
+    stream.PARALLEL_READ_THREADS = 3
+    stream._parallel_readinto = spy
+    try:
+        with tempfile.NamedTemporaryFile(suffix='.vdif') as tmp:
+            tmp.write(raw.tobytes())
+            tmp.flush()
+            with bb.vdif.open(tmp.name, 'rs', sample_rate=1e6,
+                              chunk_nbytes=30000) as fh:
+                _same(fh.read(), want)
+                fh.seek(12345)
+                _same(fh.read(7000), want[12345:19345])
+        assert calls and all(c is not None and c > 0 for c in calls)
+        calls.clear()
+        with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs',
+                          sample_rate=1e6) as fh:
+            _same(fh.read(), want)
+        assert calls and all(c is None for c in calls)
+    finally:
+        (stream.PARALLEL_READ_MIN_NBYTES, stream.PARALLEL_READ_THREADS,
+         stream._parallel_readinto) = saved
+
+
 # ------------------------------------------------------------------ DADA
 def dada_sample_read():
     for name in ('sample.dada', 'sample_meerkat.dada', 'sample_mkbf.dada'):

@@ -26,3 +26,4 @@ def test_case(name):
         fn('cpu')
     else:
         fn()
+
