@@ -20,7 +20,7 @@ nbytes = raw.size
 del raw
 print('host CPUs available:', len(os.sched_getaffinity(0)))
 try:
-    for threads in (1, 2, 4, 8):
+    for threads in (1, 2, 4, 8, 12, 16):
         stream.PARALLEL_READ_THREADS = threads
         stream._read_pool = None
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
