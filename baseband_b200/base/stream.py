@@ -93,6 +93,23 @@ def _parallel_readinto(fh, offset, view):
     return sum(_read_pool.map(piece, range(0, n, step)))
 
 
+def read_file_into(fh, offset, view):
+    """Read ``view.size`` bytes at absolute ``offset`` of ``fh`` into the
+    uint8 numpy array ``view`` (normally pinned memory) -- in parallel slices
+    for large requests on plain files, with ``seek`` + ``readinto``
+    otherwise.  Leaves ``fh`` positioned after the bytes read; returns the
+    number of bytes read."""
+    got = None
+    if view.size >= PARALLEL_READ_MIN_NBYTES:
+        got = _parallel_readinto(fh, offset, view)
+        if got is not None:
+            fh.seek(offset + got)
+    if got is None:
+        fh.seek(offset)
+        got = fh.readinto(memoryview(view))
+    return got
+
+
 _TIME_UNITS = {'s': 1.0, 'ms': 1e3, 'us': 1e6, 'ns': 1e9, 'min': 1 / 60.,
                'h': 1 / 3600., 'day': 1 / 86400.}
 
@@ -508,14 +525,7 @@ class StreamReaderBase(StreamBase):
             if view is not None:
                 return view
         view = pinned.numpy()
-        got = None
-        if view.size >= PARALLEL_READ_MIN_NBYTES:
-            got = _parallel_readinto(self.fh_raw, offset, view)
-            if got is not None:
-                self.fh_raw.seek(offset + got)
-        if got is None:
-            self.fh_raw.seek(offset)
-            got = self.fh_raw.readinto(memoryview(view))
+        got = read_file_into(self.fh_raw, offset, view)
         if got != view.size:
             raise EOFError('could not read {} frames at frame {}.'.format(
                 nframe, frame0))

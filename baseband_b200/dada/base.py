@@ -9,7 +9,8 @@ one launch of the int8 kernel.
 import numpy as np
 
 from ..base.opener import make_opener
-from ..base.stream import StreamReaderBase, StreamWriterBase
+from ..base.stream import (StreamReaderBase, StreamWriterBase,
+                           read_file_into)
 from ..base.utils import lcm
 from ..vdif.base import _FileBase
 from .frame import DADAFrame
@@ -134,10 +135,9 @@ class DADAStreamReader(_DADAStreamBase, StreamReaderBase):
 
     def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
         s0, b0, b1 = self._piece(sample_start, nsample)
-        self.fh_raw.seek(frame0 * self.header0.frame_nbytes
-                         + self.header0.nbytes + b0)
         view = pinned.numpy()
-        if self.fh_raw.readinto(memoryview(view)) != view.size:
+        if read_file_into(self.fh_raw, frame0 * self.header0.frame_nbytes
+                          + self.header0.nbytes + b0, view) != view.size:
             raise EOFError('could not read payload bytes of frame {}.'
                            .format(frame0))
 

@@ -15,7 +15,8 @@ import torch
 
 from .. import kernels
 from ..base.opener import normalize_mode
-from ..base.stream import StreamReaderBase, StreamWriterBase, as_hertz
+from ..base.stream import (StreamReaderBase, StreamWriterBase, as_hertz,
+                           read_file_into)
 from ..vdif.base import _FileBase
 from .frame import GSBFrame
 from .header import GSBHeader
@@ -174,8 +175,8 @@ class GSBStreamReader(_GSBStreamBase, StreamReaderBase):
         k = 0
         for group in self._files():
             for fh in group:
-                fh.seek(frame0 * self._payload_nbytes)
-                got = fh.readinto(memoryview(view[k * span:(k + 1) * span]))
+                got = read_file_into(fh, frame0 * self._payload_nbytes,
+                                     view[k * span:(k + 1) * span])
                 if got != span:
                     raise EOFError('could not read {} frames at frame {}.'
                                    .format(nframe, frame0))
