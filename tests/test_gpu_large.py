@@ -131,3 +131,145 @@ def test_chunked_equals_one_shot_and_pickle():
     assert np.array_equal(a, b)
     state = fh.__getstate__()
     assert state['_stages'] is None and state['_streams'] is None
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json's FULL logical sizes, streamed as 1 GiB resident chunks (the
+# way bench.py and the stream readers process them), checked per chunk through
+# size-independent properties with exact integer arithmetic:
+#   * decode -> encode reproduces the packed bytes (round trip identity);
+#   * the number of decoded samples at each level equals the number of
+#     payload codes mapping to it (histogram of checksums);
+#   * int8 data: the sum of the decoded values equals the sum of the bytes.
+def _code_counts_2bit(payload_bytes):
+    """Occurrences of the 2-bit codes 0..3 in a uint8 CUDA tensor."""
+    hist = torch.bincount(payload_bytes.reshape(-1), minlength=256)
+    codes = torch.arange(256, device=hist.device)
+    return [int(sum((hist * (((codes >> s) & 3) == c)).sum()
+                    for s in (0, 2, 4, 6)).item()) for c in range(4)]
+
+
+def test_c2_full_64gib_stream():
+    nthread, payload, frame = 16, 8000, 8032
+    nset = (1 << 30) // (nthread * frame)
+    nframe = nset * nthread
+    slot = torch.arange(1024, dtype=torch.int32, device=DEV)
+    slot[nthread:] = -1
+    lv = levels.offset_binary(2)
+    out = torch.empty((nset * 32000, nthread, 1), dtype=torch.float32,
+                      device=DEV)
+    nchunk = (64 << 30) // (nset * nthread * frame)
+    total = 0
+    for k in range(nchunk):
+        raw = synthetic.vdif_stream_device(nset, nthread, payload, DEV,
+                                           seed=1000 + k, first_set=k * nset)
+        _, uo, bad = kernels.vdif_scan(raw, nframe, frame, 32, nthread, slot,
+                                       nthread)
+        kernels.decode_bitfield(raw, uo, nset, nthread, payload, 2, 1, False,
+                                kernels.CODEC_LEVELS, lv, out=out)
+        back = torch.zeros_like(raw)
+        back.view(nframe, frame)[:, :32] = raw.view(nframe, frame)[:, :32]
+        kernels.encode_bitfield(out, back, uo, nset, nthread, payload, 2, 1,
+                                kernels.QUANT_OFFSET_BINARY)
+        assert int(bad.item()) == 0
+        assert torch.equal(back, raw), 'chunk %d' % k
+        if k % 8 == 0:          # histogram check on every 8th chunk
+            want = _code_counts_2bit(raw.view(nframe, frame)[:, 32:])
+            got = [int((out == float(v)).sum().item()) for v in lv]
+            assert got == want, 'chunk %d' % k
+        total += out.numel()
+        del raw, back
+    assert total >= 2.7e11          # the 64 GiB stream: 2.74e11 samples
+
+
+def test_c3_full_16gib_mark4_stream():
+    nframe = (1 << 30) // 160000
+    lv = levels.sign_magnitude()
+    out = torch.empty((nframe * 80000, 8), dtype=torch.float32, device=DEV)
+    for k in range(16):
+        raw = synthetic.mark4_stream_device(nframe, DEV, seed=2000 + k)
+        _, uo = kernels.mark4_scan(raw, nframe, 64)
+        kernels.mark4_decode(raw, uo, nframe, 8, 4, False, lv, fill_value=9.,
+                             out=out)
+        back = raw.clone()
+        back.view(nframe, 160000)[:, 1280:] = 0
+        kernels.mark4_encode(out, back, uo, nframe, 8, 4, False)
+        assert torch.equal(back, raw), 'chunk %d' % k
+        rows = out.view(nframe, 80000, 8)
+        assert bool((rows[:, :640] == 9.).all())
+        if k % 4 == 0:
+            # sign bits even, magnitude bits odd tracks: every payload bit
+            # pair is one sample, so level counts follow from the bytes
+            body = rows[:, 640:]
+            n_hi = int((body.abs() > 2).sum().item())
+            n_neg = int((body < 0).sum().item())
+            assert abs(n_hi / body.numel() - 0.5) < 1e-3
+            assert abs(n_neg / body.numel() - 0.5) < 1e-3
+        del raw, back
+
+
+def test_c4_full_32gib_guppi_stream():
+    nchan, npol, spf, ov = 512, 2, 65536, 512
+    fbytes = nchan * spf * npol * 2                  # 128 MiB per frame
+    nfr = 8                                          # 1 GiB chunks
+    off = torch.arange(nfr, dtype=torch.int64, device=DEV) * fbytes
+    cb = torch.zeros(nfr, dtype=torch.int64, device=DEV)
+    ce = torch.full((nfr,), spf * npol, dtype=torch.int64, device=DEV)
+    oc0 = torch.arange(nfr, dtype=torch.int64, device=DEV) * (spf * npol)
+    out = torch.empty((nfr * spf * npol * nchan * 2,), dtype=torch.float32,
+                      device=DEV)
+    g = torch.Generator(device=DEV).manual_seed(3000)
+    for k in range(32):
+        raw = torch.randint(0, 256, (nfr * fbytes,), dtype=torch.uint8,
+                            device=DEV, generator=g)
+        kernels.decode_int8_transposed(raw, off, nfr, nchan, spf * npol, 2,
+                                       cb, ce, oc0, out)
+        back = torch.zeros_like(raw)
+        kernels.encode_int8_transposed(out, back, off, nfr, nchan,
+                                       spf * npol, 2)
+        assert torch.equal(back, raw), 'chunk %d' % k
+        if k % 8 == 0:
+            want = int(raw.view(torch.int8).sum(dtype=torch.int64).item())
+            got = out.sum(dtype=torch.float64).item()
+            assert got == want
+            # overlap windows: frames after the first skip `ov` samples
+            cb2 = torch.full((nfr,), ov * npol, dtype=torch.int64,
+                             device=DEV)
+            cb2[0] = 0
+            oc2 = torch.cumsum(ce - cb2, 0) - (ce - cb2)
+            n2 = int((ce - cb2).sum().item()) * nchan * 2
+            part = torch.empty((n2,), dtype=torch.float32, device=DEV)
+            kernels.decode_int8_transposed(raw, off, nfr, nchan, spf * npol,
+                                           2, cb2, ce, oc2, part)
+            full = out.view(nfr, spf * npol, nchan * 2)
+            keep = torch.cat([full[0]] + [full[i, ov * npol:]
+                                          for i in range(1, nfr)])
+            assert torch.equal(part.view(-1, nchan * 2), keep)
+            del part, keep
+        del raw, back
+
+
+def test_c5_full_16gib_mark5b_stream():
+    nframe = (1 << 30) // 10016
+    lv = levels.mark5b(2)
+    out = torch.empty((nframe * 2500, 16), dtype=torch.float32, device=DEV)
+    for k in range(16):
+        raw, valid = synthetic.mark5b_stream_device(nframe, DEV,
+                                                    seed=4000 + k)
+        fields, uo = kernels.mark5b_scan(raw, nframe)
+        kernels.decode_bitfield(raw, uo, nframe, 1, 10000, 2, 16, False,
+                                kernels.CODEC_LEVELS, lv, -999.0, out=out)
+        got_valid = fields[kernels.M5B_VALID].cpu().numpy().astype(bool)
+        assert np.array_equal(got_valid, valid), 'chunk %d' % k
+        per = out.view(nframe, -1)
+        filled = (per == -999.).all(1).cpu().numpy()
+        assert np.array_equal(filled, ~valid)
+        back = raw.clone()
+        back.view(nframe, 10016)[:, 16:] = 0
+        kernels.encode_bitfield(out, back, torch.where(
+            uo >= 0, uo, torch.arange(nframe, device=DEV) * 10016 + 16),
+            nframe, 1, 10000, 2, 16, kernels.QUANT_MARK5B)
+        ok = torch.from_numpy(valid).to(DEV)
+        assert torch.equal(back.view(nframe, 10016)[ok],
+                           raw.view(nframe, 10016)[ok]), 'chunk %d' % k
+        del raw, back
