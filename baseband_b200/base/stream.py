@@ -790,7 +790,11 @@ class StreamWriterBase(StreamBase):
                                  else np.complex128, copy=False)
             elif arr.dtype not in (np.float32, np.float64):
                 arr = arr.astype(np.float64)
-            t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+            arr = np.ascontiguousarray(arr)
+            if arr.nbytes >= _device.STAGED_UPLOAD_MIN_NBYTES:
+                t = _device.staged_upload(arr, dev)
+            else:
+                t = torch.from_numpy(arr).to(dev)
         if t.is_complex() != self._complex_data:
             if self._complex_data:
                 raise ValueError('stream holds complex data but real values '
@@ -799,9 +803,25 @@ class StreamWriterBase(StreamBase):
                              'were given')
         return t
 
+    # Large host arrays are sent to the GPU in slices of this many bytes, so
+    # device memory holds one slice, not the whole array; each slice goes
+    # through `device.staged_upload` (threaded copy into pinned staging,
+    # overlapped with the PCIe transfer).
+    HOST_WRITE_SLICE_NBYTES = 256 << 20
+
     def write(self, data, valid=True):
         if self.closed:
             raise ValueError('I/O operation on closed file.')
+        if isinstance(data, np.ndarray) and data.ndim >= 1 \
+                and data.nbytes >= 2 * self.HOST_WRITE_SLICE_NBYTES:
+            rows = max(1, self.HOST_WRITE_SLICE_NBYTES
+                       // max(1, data.nbytes // data.shape[0]))
+            for lo in range(0, data.shape[0], rows):
+                self._write_one(data[lo:lo + rows], valid)
+            return
+        self._write_one(data, valid)
+
+    def _write_one(self, data, valid):
         t = self._unsqueeze(self._to_device(data))
         if t.shape[0] == 0:
             return
