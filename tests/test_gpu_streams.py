@@ -77,8 +77,7 @@ def test_writer_large_host_array_staged_upload(monkeypatch):
                             'HOST_WRITE_SLICE_NBYTES', slice_nbytes)
         buf = io.BytesIO()
         fw = bb.vdif.open(buf, 'ws', header0=h0, nthread=4, sample_rate=1e6)
-        fw.write(arr)
-        fw.close()
+        fw.write(arr)                 # whole frames: all flushed by now
         return buf.getvalue()
 
     monkeypatch.setattr(bbdev, 'STAGED_UPLOAD_MIN_NBYTES', 1 << 60)
