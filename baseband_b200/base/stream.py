@@ -40,6 +40,9 @@ DEFAULT_CHUNK_NBYTES = 64 << 20
 # files are therefore read as several slices with os.preadv on a small thread
 # pool (the system call releases the GIL), which keeps the H2D copy fed.
 PARALLEL_READ_MIN_NBYTES = 8 << 20
+# read(out=<pageable numpy array>) at least this large: staged D2H (see
+# StreamReaderBase._read_to_host).
+STAGED_HOST_OUT_MIN_NBYTES = 4 << 20
 PARALLEL_READ_THREADS = max(1, min(8, len(os.sched_getaffinity(0))
                                    if hasattr(os, 'sched_getaffinity')
                                    else (os.cpu_count() or 1)))
@@ -285,6 +288,27 @@ class _Stage:
         self.dec = None
         self.done = None          # event: stage's D2H (or H2D) finished
         self.free = None          # event: kernels no longer read ``raw``
+        self.host = None          # pinned staging of the decoded output
+        self.pending = None       # (host view, destination) still to copy
+
+    def host_out(self, like):
+        """Pinned staging tensor shaped and typed like the device tensor
+        ``like``."""
+        nbytes = like.numel() * like.element_size()
+        if self.host is None or self.host.numel() < nbytes:
+            self.host = _device.pinned_empty(nbytes, torch.uint8)
+        return self.host[:nbytes].view(like.dtype).view(like.shape)
+
+    def flush(self):
+        """Finish a staged host copy: wait for the D2H into the pinned
+        staging, then copy (several threads) into the caller's array."""
+        if self.pending is None:
+            return
+        src, dst = self.pending
+        self.pending = None
+        self.done.synchronize()
+        _device._threaded_copy(dst.reshape(-1).view(np.uint8),
+                               src.numpy().reshape(-1).view(np.uint8))
 
     def buffers(self, nbytes, nfloat, dev, need_dec):
         if self.pin is None or self.pin.numel() < nbytes:
@@ -642,7 +666,7 @@ class StreamReaderBase(StreamBase):
         shape = (count,) + tuple(self.sample_shape)
         np_dtype = self.dtype
         t_dtype = torch.complex64 if self._complex_data else torch.float32
-        registered = None
+        staged = False
         if out is None:
             # The result itself is pinned memory: D2H lands in it directly.
             holder = (_device.pinned_empty(shape, t_dtype) if count > 0
@@ -654,9 +678,12 @@ class StreamReaderBase(StreamBase):
         else:
             result = out
             target = _as_host_tensor(out, np_dtype)
-            if target is not None and not target.is_pinned() and \
-                    out.nbytes >= (1 << 22):
-                registered = _device.register_host(out)
+            # A large pageable destination: page-locking it in place costs
+            # more than it saves (cudaHostRegister pins ~10 GB/s), so each
+            # chunk lands in the stage's pinned buffer and is copied on by a
+            # few threads while the next chunk is in flight.
+            staged = (target is not None and not target.is_pinned()
+                      and out.nbytes >= STAGED_HOST_OUT_MIN_NBYTES)
         if count == 0:
             return result
         stages, ss = self._pipeline(dev)
@@ -665,6 +692,7 @@ class StreamReaderBase(StreamBase):
                     self._chunks(start, count)):
                 st = stages[k % 2]
                 nbytes = self._chunk_nbytes_of(f0, nf, s0, ns)
+                st.flush()
                 if st.done is not None:
                     st.done.synchronize()
                 pin, raw = st.buffers(nbytes, ns * fps, dev, True)
@@ -682,18 +710,26 @@ class StreamReaderBase(StreamBase):
                         piece = piece.contiguous()
                 with ss.use(2):
                     ss.wait(2, 1)
-                    if target is not None:
+                    if staged:
+                        hostbuf = st.host_out(piece)
+                        hostbuf.copy_(piece, non_blocking=True)
+                        st.pending = (hostbuf, result[row:row + ns])
+                    elif target is not None:
                         target[row:row + ns].copy_(piece, non_blocking=True)
                     else:
                         # exotic ``out`` (wrong dtype / non-contiguous)
                         out[row:row + ns] = piece.cpu().numpy()
                     st.done = ss.event(2)
+                # the other stage's chunk: its D2H has had a whole chunk's
+                # time; copy it on while this chunk is in flight
+                stages[(k + 1) % 2].flush()
             for st in stages:
+                st.flush()
                 if st.done is not None:
                     st.done.synchronize()
         finally:
-            if registered is not None:
-                _device.unregister_host(registered)
+            for st in stages:
+                st.pending = None        # nothing stale after an error
         return result
 
     # Pickling (base/base.py:123-151, :1020-1032): device buffers and streams

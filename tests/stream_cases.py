@@ -554,6 +554,37 @@ def vdif_parallel_file_read():
          stream._parallel_readinto) = saved
 
 
+def vdif_pageable_out_staged():
+    """read(out=<large pageable numpy array>): chunks land in pinned staging
+    and are copied on by threads (base/stream.py:_read_to_host)."""
+    from baseband_b200.base import stream
+    raw = synthetic.vdif_stream(30, 4, 1000, seed=9, invalid=[5])
+    want = ostream.vdif_read(raw, fill_value=-1.)[:, :, 0]
+    saved = stream.STAGED_HOST_OUT_MIN_NBYTES
+    stream.STAGED_HOST_OUT_MIN_NBYTES = 1
+    try:
+        for chunk in (None, 9000, 40000):
+            with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs',
+                              sample_rate=1e6, fill_value=-1.,
+                              chunk_nbytes=chunk) as fh:
+                out = np.full(want.shape, np.nan, np.float32)
+                assert fh.read(out=out) is out
+                _same(out, want)
+                fh.seek(777)
+                part = np.full((50001, 4), np.nan, np.float32)
+                fh.read(out=part)
+                _same(part, want[777:777 + 50001])
+                # subset: non-contiguous device piece
+            with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs',
+                              sample_rate=1e6, fill_value=-1.,
+                              subset=[3, 1], chunk_nbytes=chunk) as fh:
+                out = np.full((want.shape[0], 2), np.nan, np.float32)
+                fh.read(out=out)
+                _same(out, want[:, [3, 1]])
+    finally:
+        stream.STAGED_HOST_OUT_MIN_NBYTES = saved
+
+
 # ------------------------------------------------------------------ DADA
 def dada_sample_read():
     for name in ('sample.dada', 'sample_meerkat.dada', 'sample_mkbf.dada'):
