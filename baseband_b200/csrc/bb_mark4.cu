@@ -21,7 +21,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
     // pair LUT over the raw code (sign | magnitude << 1), see DecodeLut<2>
     __shared__ __align__(16) float lut[DecodeLut<2>::kFloats];
-    if (MODE == M4_FAST) {
+    if (MODE == M4_FAST || MODE == M4_WARP) {
         if (threadIdx.x < DecodeLut<2>::kFloats) {
             int entry = threadIdx.x >> 1, which = threadIdx.x & 1;
             int code = which ? (entry >> 2) : (entry & 3);
@@ -45,11 +45,24 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
             const uint32_t item = item0 + u * kM4Block;
             ok[u] = item < p.nitems && m4w_load(p, item >> 5, lane, w[u]);
         }
+        uint32_t srcl[4];                          // loop-invariant per lane
+#pragma unroll
+        for (int j = 0; j < 4; ++j) srcl[j] = m4w_src_lane(p, lc, lane + 32u * j);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t item = item0 + u * kM4Block;
             if (item >= p.nitems) break;           // warp uniform
             const unsigned okmask = __ballot_sync(0xffffffffu, ok[u]);
+            if (m4w_interior(p, item >> 5)) {      // warp uniform
+                float *chunk_out = m4w_chunk_out(p, item >> 5);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t ws = __shfl_sync(0xffffffffu, w[u], srcl[j]);
+                    m4w_emit_fast(p, lc, lut, chunk_out, lane + 32u * j, ws,
+                                  (okmask >> srcl[j]) & 1u);
+                }
+                continue;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const uint32_t q = lane + 32u * j;

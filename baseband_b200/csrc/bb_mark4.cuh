@@ -220,6 +220,40 @@ BB_HD void m4w_emit(const M4Geom &p, const M4Lane &c, const float lv[4],
     *reinterpret_cast<F4 *>(p.out + gidx) = v;
 }
 
+// Interior chunks (all 32 values inside the launch, all 128 float4 inside the
+// requested rows; warp uniform): no per-float4 bounds checks, one 64-bit
+// output base per chunk, and the levels come from the pair table of the FAST
+// path (index = s0 | m0 << 1 | s1 << 2 | m1 << 3 -> two floats per LDS.64).
+BB_HD bool m4w_interior(const M4Geom &p, uint32_t chunk) {
+    if ((unsigned long long)chunk * 32u + 32u > p.total32) return false;
+    const long long g0 = p.row_base * (long long)p.nchan
+        + (long long)chunk * 512;
+    return g0 >= 0 && g0 + 512 <= p.nsample * (long long)p.nchan;
+}
+
+BB_HD float *m4w_chunk_out(const M4Geom &p, uint32_t chunk) {
+    return p.out + (p.row_base * (long long)p.nchan + (long long)chunk * 512);
+}
+
+BB_HD uint32_t m4w_pair_index(const M4Lane &c, uint32_t w, int k) {
+    return ((w >> c.sbit[k]) & 1u) | (((w >> c.mbit[k]) & 1u) << 1)
+        | (((w >> c.sbit[k + 1]) & 1u) << 2)
+        | (((w >> c.mbit[k + 1]) & 1u) << 3);
+}
+
+BB_HD void m4w_emit_fast(const M4Geom &p, const M4Lane &c, const float *lut,
+                         float *chunk_out, uint32_t q, uint32_t w, bool valid) {
+    F4 v;
+    if (valid) {
+        const F2 a = reinterpret_cast<const F2 *>(lut)[m4w_pair_index(c, w, 0)];
+        const F2 b = reinterpret_cast<const F2 *>(lut)[m4w_pair_index(c, w, 2)];
+        v = F4{a.x, a.y, b.x, b.y};
+    } else {
+        v = F4{p.fill, p.fill, p.fill, p.fill};
+    }
+    *reinterpret_cast<F4 *>(chunk_out + 4u * q) = v;
+}
+
 // ------------------------------------------------------------------ encode
 // FAST encode: item = (frame, step, half); header steps are skipped.
 template <typename T>

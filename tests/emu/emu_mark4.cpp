@@ -24,10 +24,16 @@ static void run_dec(const std::vector<M4Launch> &launches) {
                 bool ok[32];
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     ok[lane] = m4w_load(l.g, chunk, lane, w[lane]);
+                const bool interior = m4w_interior(l.g, chunk);
                 for (uint32_t q = 0; q < 128; ++q) {
                     const M4Lane lc = m4w_lane(l.g, l.g.pos, q & 31u);
                     uint32_t src = m4w_src_lane(l.g, lc, q);
-                    m4w_emit(l.g, lc, l.g.levels, chunk, q, w[src], ok[src]);
+                    if (interior)
+                        m4w_emit_fast(l.g, lc, lut, m4w_chunk_out(l.g, chunk),
+                                      q, w[src], ok[src]);
+                    else
+                        m4w_emit(l.g, lc, l.g.levels, chunk, q, w[src],
+                                 ok[src]);
                 }
             }
             continue;
