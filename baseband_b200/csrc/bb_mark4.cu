@@ -88,18 +88,29 @@ __global__ void __launch_bounds__(kM4Block)
 k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
     constexpr int U = kM4UnrollFast;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
-    __shared__ uint16_t spos[32];
-    if (MODE == M4_HALF) {
-        if (threadIdx.x < 32) spos[threadIdx.x] = p.pos[threadIdx.x];
-        __syncthreads();
-    }
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
         const uint32_t item = item0 + u * kM4Block;
         if (item >= p.nitems) break;
         if (MODE == M4_FAST) m4_enc_fast<T>(p, c, item);
-        else if (MODE == M4_HALF) m4_enc_half<T>(p, spos, c, item);
         else m4_enc_generic<T>(p, c, item);
+    }
+}
+
+// HALF encode, one kernel per track-word size: the bit masks of a thread are
+// built once (they only depend on the layout and the parity of the item).
+template <typename T, int W>
+__global__ void __launch_bounds__(kM4Block)
+k_mark4_encode_half(const M4Geom p, const QuantConsts<T> c) {
+    constexpr int U = kM4UnrollFast;
+    const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
+    // kM4Block is even: every item of this thread has the parity of item0
+    const M4HalfMasks mk = m4_half_masks<W>(p, p.pos, item0 & 1u);
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        const uint32_t item = item0 + u * kM4Block;
+        if (item >= p.nitems) break;
+        m4_enc_half_w<T, W>(p, mk, c, item);
     }
 }
 
@@ -130,8 +141,12 @@ static int run_encode(const std::vector<M4Launch> &launches, cudaStream_t s) {
         unsigned grid = m4_grid(l.g.nitems, kM4UnrollFast);
         if (l.mode == M4_FAST)
             k_mark4_encode<T, M4_FAST><<<grid, kM4Block, 0, s>>>(l.g, consts);
+        else if (l.mode == M4_HALF && l.g.wordbytes == 8)
+            k_mark4_encode_half<T, 8><<<grid, kM4Block, 0, s>>>(l.g, consts);
+        else if (l.mode == M4_HALF && l.g.wordbytes == 4)
+            k_mark4_encode_half<T, 4><<<grid, kM4Block, 0, s>>>(l.g, consts);
         else if (l.mode == M4_HALF)
-            k_mark4_encode<T, M4_HALF><<<grid, kM4Block, 0, s>>>(l.g, consts);
+            k_mark4_encode_half<T, 2><<<grid, kM4Block, 0, s>>>(l.g, consts);
         else
             k_mark4_encode<T, M4_GENERIC_SCALAR>
                 <<<grid, kM4Block, 0, s>>>(l.g, consts);

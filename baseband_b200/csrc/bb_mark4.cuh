@@ -323,8 +323,37 @@ BB_HD void m4_enc_generic(const M4Geom &p, const QuantConsts<T> &c,
 // 32 bytes apart for the 64-track layouts -- loaded as vectors; sign and
 // magnitude bits are placed with the per-layout table.  Stores are 128
 // contiguous bytes per warp.
+// The bit positions a thread needs depend only on the layout and, for 64-track
+// words, on which 32-bit half the value is (h = value index & 1; the number of
+// values per frame is even, so h is the parity of the item): they are turned
+// into 16 sign masks and 16 magnitude masks once per thread, and a sample
+// then costs three compares and two predicated ORs.
+struct M4HalfMasks {
+    uint32_t s[16], m[16];           // [4 * float4 + element]
+    uint32_t pps[4];                 // float4 position in the track word
+};
+
+template <int W>
+BB_HD M4HalfMasks m4_half_masks(const M4Geom &p, const uint16_t *pos,
+                                uint32_t h) {
+    M4HalfMasks mk;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        mk.pps[m] = W == 2 ? (m & 1u) : W == 4 ? (uint32_t)m
+                                               : (uint32_t)p.psel[4u * h + m];
+        const uint32_t base = W == 2 ? 16u * (m >> 1) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t sm = pos[4u * mk.pps[m] + k];
+            mk.s[4 * m + k] = 1u << (((sm & 0xffu) & 31u) + base);
+            mk.m[4 * m + k] = 1u << (((sm >> 8) & 31u) + base);
+        }
+    }
+    return mk;
+}
+
 template <typename T, int W>
-BB_HD void m4_enc_half_w(const M4Geom &p, const uint16_t *pos,
+BB_HD void m4_enc_half_w(const M4Geom &p, const M4HalfMasks &mk,
                          const QuantConsts<T> &c, uint32_t item) {
     if (item >= p.total32) return;
     uint32_t frame, i32;
@@ -334,17 +363,13 @@ BB_HD void m4_enc_half_w(const M4Geom &p, const uint16_t *pos,
     if (off < 0 || step < p.header_steps) return;
     // first track word of this value, counted over the launch
     const size_t word0 = (size_t)frame * p.steps + step;
-    const uint32_t h = W == 8 ? (i32 & 1u) : 0u;
     const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
     T v[4][4];
-    uint32_t pps[4];
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         // m-th float4 of this value: (word, position in word)
         const uint32_t wsel = W == 2 ? (m >> 1) : 0u;
-        pps[m] = W == 2 ? (m & 1u) : W == 4 ? (uint32_t)m
-                                            : (uint32_t)p.psel[4u * h + m];
-        const T *q = in + ((word0 + wsel) * W + pps[m]) * 4;
+        const T *q = in + ((word0 + wsel) * W + mk.pps[m]) * 4;
         if (sizeof(T) == 4) {
             F4 r = *reinterpret_cast<const F4 *>(q);
             v[m][0] = (T)r.x; v[m][1] = (T)r.y; v[m][2] = (T)r.z;
@@ -359,25 +384,31 @@ BB_HD void m4_enc_half_w(const M4Geom &p, const uint16_t *pos,
     uint32_t out = 0u;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-        const uint32_t base = W == 2 ? 16u * (m >> 1) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t code = quantise<T, 2, QUANT_OFFSET>(v[m][k], c);
-            const uint32_t sm = pos[4u * pps[m] + k];
-            out |= (code >> 1) << (((sm & 0xffu) & 31u) + base);
-            out |= (code & 1u) << (((sm >> 8) & 31u) + base);
+            // code = (v >= x1) + (v >= x2) + (v >= x3) (quant2_offset); its
+            // high bit is the sign, its low bit the magnitude
+            const T x = v[m][k];
+            const bool sign = x >= c.x2;
+            const bool mag = (x >= c.x3) | ((x >= c.x1) & !sign);
+            out |= sign ? mk.s[4 * m + k] : 0u;
+            out |= mag ? mk.m[4 * m + k] : 0u;
         }
     }
     *reinterpret_cast<uint32_t *>(const_cast<uint8_t *>(p.src) + off
         - (long long)p.header_steps * W + 4ull * i32) = out;
 }
 
+// Per-item form (masks rebuilt for every value): the CPU emulation.
 template <typename T>
 BB_HD void m4_enc_half(const M4Geom &p, const uint16_t *pos,
                        const QuantConsts<T> &c, uint32_t item) {
-    if (p.wordbytes == 8) m4_enc_half_w<T, 8>(p, pos, c, item);
-    else if (p.wordbytes == 4) m4_enc_half_w<T, 4>(p, pos, c, item);
-    else m4_enc_half_w<T, 2>(p, pos, c, item);
+    if (p.wordbytes == 8)
+        m4_enc_half_w<T, 8>(p, m4_half_masks<8>(p, pos, item & 1u), c, item);
+    else if (p.wordbytes == 4)
+        m4_enc_half_w<T, 4>(p, m4_half_masks<4>(p, pos, 0u), c, item);
+    else
+        m4_enc_half_w<T, 2>(p, m4_half_masks<2>(p, pos, 0u), c, item);
 }
 
 }  // namespace bb
