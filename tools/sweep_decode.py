@@ -55,6 +55,8 @@ def main():
         ('vdif 8bit 4thr 1ch', 8, 4, 1, 8000, 32, 'vdif'),
         ('vdif 4bit 2thr cplx', 4, 2, 2, 8000, 32, 'vdif'),
         ('vdif 2bit 2thr cplx', 2, 2, 2, 8000, 32, 'vdif'),
+        ('gsb phased 8bit 2pol 512ch', 8, 2, 1024, 1 << 22, 0, 'sint'),
+        ('gsb rawdump 4bit', 4, 1, 1, 1 << 22, 0, 'sint'),
     ]
     if len(sys.argv) > 2:
         configs = [c for c in configs if sys.argv[2] in c[0]]
