@@ -400,7 +400,10 @@ extern "C" int bb_decode_bitfield(
         case 1: return launch_decode<1, CODEC_LEVELS>(launches, levels_host, s);
         case 2: return launch_decode<2, CODEC_LEVELS>(launches, levels_host, s);
         case 4: return launch_decode<4, CODEC_LEVELS>(launches, levels_host, s);
-        case 8: return launch_decode<8, CODEC_LEVELS>(launches, levels_host, s);
+        case 8:
+            if (affine8_matches(levels_host))       // the standard 8-bit table
+                return launch_decode<8, CODEC_AFFINE8>(launches, nullptr, s);
+            return launch_decode<8, CODEC_LEVELS>(launches, levels_host, s);
         }
     } else if (codec == BB_CODEC_SINT) {
         switch (bps) {

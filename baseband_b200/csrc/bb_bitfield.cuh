@@ -30,7 +30,9 @@
 
 namespace bb {
 
-enum { CODEC_LEVELS = 0, CODEC_SINT = 1 };
+// CODEC_AFFINE8 is internal: the launcher substitutes it for CODEC_LEVELS when
+// the 256 levels it was given are exactly those `affine8` computes.
+enum { CODEC_LEVELS = 0, CODEC_SINT = 1, CODEC_AFFINE8 = 2 };
 
 template <int BPS>
 struct LevelTable { float v[1 << BPS]; };
@@ -75,6 +77,30 @@ struct DecGeom {
     FastDiv div_nword, div_ngroup, div_rowlen, div_spf, div_nelem, div_unitlen;
 };
 
+// 8-bit offset-binary levels without a table: (code - 127.5) / 35.5 in float32
+// as numpy computes it (baseband/base/encoding.py:131-144).  A 256-entry table
+// in shared memory suffers ~3-way bank conflicts under random codes (the LSU
+// data pipe was 73 % busy); this is seven ALU operations instead.
+// code - 127.5: the byte is planted in the mantissa of 2^22 (ulp 0.5), so one
+// exact subtraction yields it; the division is a multiplication by the
+// rounded reciprocal corrected with two FMAs (Markstein) -- `affine8_matches`
+// checks on the host, for all 256 codes, that this equals the table given.
+BB_HD float affine8(uint32_t w, uint32_t c) {
+    const uint32_t u = (((w >> (8u * c)) & 0xffu) << 1) | 0x4A800000u;
+    const float x = add_rn(uint_as_float(u), -4194431.5f);
+    constexpr float r = 1.0f / 35.5f;
+    const float q = mul_rn(x, r);
+    return fma_rn(fma_rn(-q, 35.5f, x), r, q);
+}
+
+inline bool affine8_matches(const float *levels) {
+    for (uint32_t code = 0; code < 256; ++code) {
+        const float v = affine8(code, 0);
+        if (__builtin_memcmp(&v, &levels[code], 4) != 0) return false;
+    }
+    return true;
+}
+
 template <int BPS>
 BB_HD float sint_code(uint32_t w, uint32_t pos) {
     return (float)((int32_t)(w << (32 - BPS - pos)) >> (32 - BPS));
@@ -87,6 +113,9 @@ BB_HD F2 decode_pair(uint32_t w, uint32_t j, const float *lut) {
     if (CODEC == CODEC_SINT) {
         r.x = sint_code<BPS>(w, 2 * j * BPS);
         r.y = sint_code<BPS>(w, (2 * j + 1) * BPS);
+    } else if (CODEC == CODEC_AFFINE8) {
+        r.x = affine8(w, 2 * j);
+        r.y = affine8(w, 2 * j + 1);
     } else if (BPS <= 2) {
         uint32_t idx = (w >> (2 * BPS * j)) & ((1u << (2 * BPS)) - 1u);
         r = reinterpret_cast<const F2 *>(lut)[idx];
@@ -102,6 +131,7 @@ BB_HD float decode_one(uint32_t w, uint32_t c, const float *lut) {
     // one table access per value: the pair table serves 1/2 bit, wider codes
     // index the per-code table directly
     if (CODEC == CODEC_SINT) return sint_code<BPS>(w, c * BPS);
+    if (CODEC == CODEC_AFFINE8) return affine8(w, c);
     if (BPS > 2) return lut[(w >> (c * BPS)) & ((1u << BPS) - 1u)];
     F2 r = decode_pair<BPS, CODEC>(w, c >> 1, lut);
     return (c & 1u) ? r.y : r.x;

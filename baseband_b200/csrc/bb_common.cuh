@@ -89,6 +89,24 @@ BB_HD float mul_rn(float a, float b) {
     volatile float r = a * b; return r;
 #endif
 }
+// Fused multiply-add, one rounding (explicitly wanted: not an accidental
+// contraction, which the build disables with -fmad=false).
+BB_HD float fma_rn(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+BB_HD float uint_as_float(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    __builtin_memcpy(&f, &u, 4);
+    return f;
+#endif
+}
 BB_HD double add_rn(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);

@@ -356,10 +356,10 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     sink = HostBuffer(src.size)
     host_out = torch.empty((nset * SPF, NTHREAD), dtype=torch.float32,
                            pin_memory=True)
-    reader = bb.vdif.open(src, 'rs', sample_rate=64e6,
-                          chunk_nbytes=32 << 20)
+    chunk = int(args.e2e_chunk_mib * 2**20)
+    reader = bb.vdif.open(src, 'rs', sample_rate=64e6, chunk_nbytes=chunk)
     dev_reader = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
-                              chunk_nbytes=32 << 20)
+                              chunk_nbytes=chunk)
     host_view = host_out.numpy()
 
     def step():
@@ -566,6 +566,8 @@ def main():
     ap.add_argument('--chunk-gib', type=float, default=1.0,
                     help='packed bytes resident per GPU per step')
     ap.add_argument('--e2e-mib', type=float, default=128.0)
+    ap.add_argument('--e2e-chunk-mib', type=float, default=32.0,
+                    help='packed MiB per pipeline stage of the e2e reader')
     ap.add_argument('--named-mib', type=float, default=1024.0,
                     help='packed MiB per GPU for the C3-C5 shapes (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -67,6 +67,13 @@ DECODE_CASES = [
           fill=-999.0),
     _case('4bit_2thr_6ch', 4, 6, 2, 2, 240, start=1, count=77),
     _case('8bit_1thr_3ch_unaligned', 8, 3, 1, 2, 300, start=1, count=150),
+    # non-standard level tables (always the shared-memory table path)
+    _case('custom8_4thr', 8, 1, 4, 2, 404, kind='custom', start=3, count=700),
+    _case('custom8_1thr_cplx', 8, 2, 1, 2, 800, cplx=True, kind='custom'),
+    _case('custom8_12thr', 8, 1, 12, 2, 200, kind='custom', invalid=(5,),
+          fill=1.5),
+    _case('custom2_16thr', 2, 1, 16, 2, 800, kind='custom'),
+    _case('custom4_2thr_cplx', 4, 2, 2, 2, 100, cplx=True, kind='custom'),
     # signed-integer codecs
     _case('gsb_4bit_rawdump', 4, 1, 1, 2, 4096, kind='sint'),
     _case('dada_8bit_cplx_2pol', 8, 4, 1, 2, 6400, cplx=True, kind='sint'),
@@ -76,7 +83,18 @@ DECODE_CASES = [
 ]
 
 
+def custom_levels(bps):
+    """A level table that is NOT the standard one (exercises the table path
+    where the standard 8-bit levels are computed arithmetically)."""
+    lv = np.ascontiguousarray(levels.offset_binary(bps), np.float32).copy()
+    lv[::3] *= np.float32(1.25)
+    lv[1] = np.float32(-77.0)
+    return lv
+
+
 def _levels(kind, bps):
+    if kind == 'custom':
+        return custom_levels(bps), 0
     if kind == 'vdif':
         return np.ascontiguousarray(levels.offset_binary(bps), np.float32), 0
     if kind == 'mark5b':
@@ -106,6 +124,12 @@ def make_decode_case(case):
 
 
 def _decode_unit(words, kind, bps):
+    if kind == 'custom':
+        codes = words.view(np.uint8)
+        if bps < 8:
+            shifts = np.arange(0, 8, bps, dtype=np.uint8)
+            codes = (codes[:, None] >> shifts) & ((1 << bps) - 1)
+        return custom_levels(bps)[codes.ravel()]
     if kind == 'vdif':
         return codec.vdif_decode(words, bps).ravel()
     if kind == 'mark5b':

@@ -154,6 +154,8 @@ int bb_decode_bitfield(const void *src, const int64_t *unit_offset,
         if (bps == 1) return run_decode<1, CODEC_LEVELS>(launches, levels_host), 0;
         if (bps == 2) return run_decode<2, CODEC_LEVELS>(launches, levels_host), 0;
         if (bps == 4) return run_decode<4, CODEC_LEVELS>(launches, levels_host), 0;
+        if (bps == 8 && affine8_matches(levels_host))
+            return run_decode<8, CODEC_AFFINE8>(launches, nullptr), 0;
         if (bps == 8) return run_decode<8, CODEC_LEVELS>(launches, levels_host), 0;
     } else {
         if (bps == 4) return run_decode<4, CODEC_SINT>(launches, nullptr), 0;
