@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/check_nccl_gather.py
+"""torchrun --nproc-per-node N tests/check_nccl_gather.py
 Sharded read of a synthetic VDIF stream on N GPUs, with and without the
 optional NCCL all-gather, checked against the numpy oracle."""
 import io
