@@ -153,23 +153,6 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
-    if (MODE == MODE_ROWRUN2) {
-        constexpr int G = 2;
-#pragma unroll 1
-        for (int u0 = 0; u0 < U; u0 += B) {
-            RowRunItem<G> it[B];
-#pragma unroll
-            for (int b = 0; b < B; ++b) {
-                const uint32_t item = item0 + (u0 + b) * kBlock;
-                it[b].gidx = -1;
-                if (item < p.nitems) rowrun_fetch<BPS, G>(p, item, it[b]);
-            }
-#pragma unroll
-            for (int b = 0; b < B; ++b)
-                rowrun_emit<BPS, CODEC, G>(p, lut, it[b]);
-        }
-        return;
-    }
     if (MODE == MODE_RUN) {
 #pragma unroll 1
         for (int u0 = 0; u0 < U; u0 += B) {
@@ -289,11 +272,6 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         case MODE_WORDROW2:
             k_decode_bitfield<BPS, CODEC, MODE_WORDROW2>
                 <<<tile_grid(n, Unroll<BPS, MODE_WORDROW2>::value), kBlock, 0,
-                   stream>>>(l.g, lv);
-            break;
-        case MODE_ROWRUN2:
-            k_decode_bitfield<BPS, CODEC, MODE_ROWRUN2>
-                <<<tile_grid(n, Unroll<BPS, MODE_ROWRUN2>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         default:

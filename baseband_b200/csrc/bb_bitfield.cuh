@@ -242,73 +242,6 @@ BB_HD void dec_rowgroup(const DecGeom &p, const float *lut, uint32_t item) {
     rowgroup_emit<BPS, CODEC, G>(p, lut, it);
 }
 
-// ROWRUN<G>: nthread * E == 4 (4 real threads, or 2 complex ones), i.e. one
-// output row IS one float4.  ROWGROUP would make each lane write TPW rows =
-// 16-byte pieces 16*TPW bytes apart; here instead a lane owns ONE row and
-// gathers its G codes (pairs) from the G slots, so a warp store is 512
-// contiguous bytes.  Lanes that share a payload word hit the same L1 line.
-template <int G>
-struct RowRunItem {
-    uint32_t w[G];
-    uint32_t okmask, c0;            // first code of the row within the word
-    long long gidx;                 // output float index, < 0: nothing to do
-};
-
-template <int BPS, int G>
-BB_HD void rowrun_fetch(const DecGeom &p, uint32_t item, RowRunItem<G> &it) {
-    constexpr int E = 4 / G;
-    constexpr int CPW = 32 / BPS;
-    const long long row = p.row_base + item;    // row of the whole call
-    it.gidx = -1;
-    it.okmask = 0u;
-    if (row < 0 || row >= p.nsample) return;
-    it.gidx = row * 4;
-    uint32_t set, t;
-    p.div_spf.divmod(item, set, t);
-    const uint32_t code = t * E;
-    it.c0 = code % CPW;
-    const long long *uo = p.unit_offset + (size_t)set * G;
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-        const long long off = uo[j];
-        it.w[j] = off >= 0 ? load_u32(p.src + off + 4ull * (code / CPW)) : 0u;
-        it.okmask |= (off >= 0 ? 1u : 0u) << j;
-    }
-}
-
-template <int BPS, int CODEC, int G>
-BB_HD void rowrun_emit(const DecGeom &p, const float *lut,
-                       const RowRunItem<G> &it) {
-    if (it.gidx < 0) return;
-    F4 v;
-    if (G == 4) {
-        v.x = (it.okmask & 1u) ? decode_one<BPS, CODEC>(it.w[0], it.c0, lut)
-                               : p.fill;
-        v.y = (it.okmask & 2u) ? decode_one<BPS, CODEC>(it.w[1 % G], it.c0, lut)
-                               : p.fill;
-        v.z = (it.okmask & 4u) ? decode_one<BPS, CODEC>(it.w[2 % G], it.c0, lut)
-                               : p.fill;
-        v.w = (it.okmask & 8u) ? decode_one<BPS, CODEC>(it.w[3 % G], it.c0, lut)
-                               : p.fill;
-    } else {
-        const float fill_im = p.complex_fill ? 0.f : p.fill;
-        F2 a = decode_pair<BPS, CODEC>(it.w[0], it.c0 >> 1, lut);
-        F2 b = decode_pair<BPS, CODEC>(it.w[1 % G], it.c0 >> 1, lut);
-        v.x = (it.okmask & 1u) ? a.x : p.fill;
-        v.y = (it.okmask & 1u) ? a.y : fill_im;
-        v.z = (it.okmask & 2u) ? b.x : p.fill;
-        v.w = (it.okmask & 2u) ? b.y : fill_im;
-    }
-    *reinterpret_cast<F4 *>(p.out + it.gidx) = v;
-}
-
-template <int BPS, int CODEC, int G>
-BB_HD void dec_rowrun(const DecGeom &p, const float *lut, uint32_t item) {
-    RowRunItem<G> it;
-    rowrun_fetch<BPS, G>(p, item, it);
-    rowrun_emit<BPS, CODEC, G>(p, lut, it);
-}
-
 // RUN: item = float4 index within the launch's block of rows; again split
 // into fetch and emit.
 struct RunItem {

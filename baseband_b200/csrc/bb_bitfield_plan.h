@@ -9,8 +9,8 @@
 namespace bb {
 
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
-       MODE_WORDRUN = 4, MODE_ROWRUN4 = 5, MODE_ROWRUN2 = 6, MODE_WORDROW4 = 7,
-       MODE_ROWWORD4 = 8, MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10 };
+       MODE_WORDRUN = 4, MODE_WORDROW4 = 7, MODE_ROWWORD4 = 8,
+       MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10 };
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -90,8 +90,6 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     } else if (mode == MODE_WORDRUN || mode == MODE_WORDROW4
                || mode == MODE_WORDROW2) {
         per_set = nword;                  // items are lanes = words
-    } else if (mode == MODE_ROWRUN4 || mode == MODE_ROWRUN2) {
-        per_set = spf;                    // items are output rows
     } else {
         per_set = (uint64_t)spf * rowlen;
     }

@@ -74,8 +74,6 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
             else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);
-            else if (l.mode == MODE_ROWRUN4) dec_rowrun<BPS, CODEC, 4>(l.g, lut, item);
-            else if (l.mode == MODE_ROWRUN2) dec_rowrun<BPS, CODEC, 2>(l.g, lut, item);
             else dec_scalar<BPS, CODEC>(l.g, lut, item);
         }
     }
