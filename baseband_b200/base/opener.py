@@ -52,7 +52,9 @@ def make_opener(fmt, classes, header_class=None, non_header_keys=(),
                                      file_size=file_size)
             opened = True
         elif isinstance(name, (str, bytes, os.PathLike)):
-            fh = io.open(name, mode[0] + 'b')
+            # writers get 'w+b' so that payloads can be memory mapped
+            # (base/base.py:1763-1766)
+            fh = io.open(name, 'w+b' if mode[0] == 'w' else 'rb')
             opened = True
         else:
             fh, opened = name, False

@@ -70,10 +70,19 @@ class PayloadBase(ArrayLike):
                     'default payload size is defined on the class.')
         dtype = cls._dtype_word if dtype is None else np.dtype(dtype)
         memmap = cls._memmap if memmap is None else memmap
+        if memmap and hasattr(fh, 'memmap'):
+            return cls(fh.memmap(dtype=dtype, shape=(
+                payload_nbytes // dtype.itemsize,)), **kwargs)
         if memmap and hasattr(fh, 'fileno'):
             try:
                 offset = fh.tell()
-                words = np.memmap(fh, mode='r', dtype=dtype, offset=offset,
+                # map with the file's own mode (base/payload.py:126-131): a
+                # file opened for writing ('w+b') gives a writable map that
+                # extends the file, which is what ``memmap_frame`` relies on
+                mode = str(getattr(fh, 'mode', 'rb')).replace('b', '')
+                if mode not in ('r', 'r+', 'w+'):
+                    mode = 'r'
+                words = np.memmap(fh, mode=mode, dtype=dtype, offset=offset,
                                   shape=(payload_nbytes // dtype.itemsize,))
                 fh.seek(offset + words.nbytes)
                 return cls(words, **kwargs)

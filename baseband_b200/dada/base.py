@@ -40,6 +40,17 @@ class DADAFileWriter(_FileBase):
             data = DADAFrame.fromdata(data, header, **kwargs)
         return data.tofile(self.fh_raw)
 
+    def memmap_frame(self, header=None, **kwargs):
+        """Write the header now and map the payload, so that the frame can
+        be filled in pieces by assigning to slices of it
+        (dada/base.py:185-208)."""
+        if header is None:
+            header = DADAHeader.fromvalues(**kwargs)
+        header.tofile(self.fh_raw)
+        payload = DADAPayload.fromfile(self.fh_raw, memmap=True,
+                                       header=header)
+        return DADAFrame(header, payload)
+
 
 class _DADAStreamBase:
     _sample_shape_maker = DADAPayload._sample_shape_maker

@@ -41,6 +41,17 @@ class GUPPIFileWriter(_FileBase):
             data = GUPPIFrame.fromdata(data, header, **kwargs)
         return data.tofile(self.fh_raw)
 
+    def memmap_frame(self, header=None, **kwargs):
+        """Write the header now and map the payload, so that the frame can
+        be filled in pieces by assigning to slices of it
+        (guppi/base.py:169-192)."""
+        if header is None:
+            header = GUPPIHeader.fromvalues(**kwargs)
+        header.tofile(self.fh_raw)
+        payload = GUPPIPayload.fromfile(self.fh_raw, memmap=True,
+                                        header=header)
+        return GUPPIFrame(header, payload)
+
 
 class _GUPPIStreamBase:
     _sample_shape_maker = GUPPIPayload._sample_shape_maker

@@ -656,6 +656,55 @@ def dada_write_roundtrip():
         _same(fr.read(), data[:2333])
 
 
+def dada_guppi_memmap_frame():
+    """fw.memmap_frame(): header written at once, payload mapped and filled
+    in pieces (dada/tests/test_dada.py:275-316, guppi likewise)."""
+    import os
+    import tempfile
+    tmp = tempfile.mkdtemp()
+    # DADA
+    with bb.dada.open(sample_path('sample.dada'), 'rb') as fb:
+        frame = fb.read_frame(memmap=False)
+    name = os.path.join(tmp, 'a2.dada')
+    with bb.dada.open(name, 'wb') as fw:
+        frame4 = fw.memmap_frame(frame.header)
+    assert frame4 != frame                  # nothing filled in yet
+    with bb.dada.open(name, 'rb') as fr:
+        assert fr.read_frame() != frame
+    frame4[:20] = frame[:20]
+    _same(frame4[:20], frame[:20])
+    assert frame4 != frame
+    frame4[20:] = frame[20:]
+    assert frame4 == frame
+    del frame4
+    with bb.dada.open(name, 'rb') as fr:
+        assert fr.read_frame() == frame
+    # (the header text is re-formatted on writing; the payload bytes match)
+    assert open(name, 'rb').read()[4096:] == open(
+        sample_path('sample.dada'), 'rb').read()[4096:]
+    name = os.path.join(tmp, 'a4.dada')
+    with bb.dada.open(name, 'wb') as fw:
+        frame8 = fw.memmap_frame(**frame.header)
+        frame8[:] = frame.data
+    assert frame8 == frame
+    del frame8
+    with bb.dada.open(name, 'rb') as fr:
+        assert fr.read_frame() == frame
+    # GUPPI
+    with bb.guppi.open(sample_path('sample_puppi.raw'), 'rb') as fb:
+        gframe = fb.read_frame(memmap=False)
+    name = os.path.join(tmp, 'a2.raw')
+    with bb.guppi.open(name, 'wb') as fw:
+        g4 = fw.memmap_frame(gframe.header)
+    assert g4 != gframe
+    g4[:300] = gframe[:300]
+    g4[300:] = gframe[300:]
+    assert g4 == gframe
+    del g4
+    with bb.guppi.open(name, 'rb') as fr:
+        assert fr.read_frame() == gframe
+
+
 # ------------------------------------------------------------------ GSB
 GSB = os.path.join(os.path.dirname(sample_path('x')), 'gsb')
 
