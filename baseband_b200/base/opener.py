@@ -44,7 +44,8 @@ def make_opener(fmt, classes, header_class=None, non_header_keys=(),
                 header_kwargs.setdefault('sample_rate', sample_rate)
             kwargs['header0'] = header_class.fromvalues(**header_kwargs)
         file_size = kwargs.pop('file_size', None)
-        if isinstance(name, (tuple, list)) or (
+        from ..helpers.sequentialfile import FileNameSequencer
+        if isinstance(name, (tuple, list, FileNameSequencer)) or (
                 isinstance(name, str) and '{' in name and mode[0] == 'w'):
             # a sequence of files (or a name template) as one byte stream
             from ..helpers import sequentialfile

@@ -8,15 +8,52 @@ the same pinned-buffer pipeline as a single file.
 """
 import io
 import os
+import string
 
-__all__ = ['SequentialFileReader', 'SequentialFileWriter', 'open']
+__all__ = ['FileNameSequencer', 'SequentialFileReader',
+           'SequentialFileWriter', 'open']
+
+
+class FileNameSequencer:
+    """List-like source of file names made from a template
+    (baseband/helpers/sequentialfile.py:18-83): items in curly brackets are
+    filled from ``header`` (keys are case sensitive), ``{file_nr}`` with the
+    index.  ``len()`` counts the files that exist for file_nr = 0, 1, ...
+
+    >>> FileNameSequencer('a{file_nr:03d}.vdif')[10]
+    'a010.vdif'
+    """
+
+    def __init__(self, template, header={}):
+        self.template = template
+        self.items = {}
+        for _, field, _, _ in string.Formatter().parse(template):
+            if field and field != 'file_nr':
+                key = field.split('.')[0].split('[')[0]
+                self.items[key] = header[key]
+
+    def __getitem__(self, file_nr):
+        if file_nr < 0:
+            file_nr += len(self)
+            if file_nr < 0:
+                raise IndexError('file number out of range.')
+        return self.template.format(file_nr=file_nr, **self.items)
+
+    def __len__(self):
+        file_nr = 0
+        while os.path.isfile(self[file_nr]):
+            file_nr += 1
+        return file_nr
 
 
 class SequentialFileReader:
     def __init__(self, files, mode='rb'):
         if mode != 'rb':
             raise ValueError("can only read sequences in 'rb' mode.")
-        self.files = list(files)
+        # a FileNameSequencer: the files that exist, in order
+        self.files = ([files[i] for i in range(len(files))]
+                      if isinstance(files, FileNameSequencer)
+                      else list(files))
         if not self.files:
             raise ValueError('need at least one file.')
         self._sizes = [os.path.getsize(f) for f in self.files]
@@ -118,7 +155,7 @@ class SequentialFileWriter:
         self._file_nr += 1
         if isinstance(self.files, str):
             name = self.files.format(file_nr=self._file_nr, **self._fmt)
-        else:
+        else:                       # list of names or a FileNameSequencer
             name = self.files[self._file_nr]
         self.names.append(name)
         self._fh = io.open(name, 'wb')

@@ -656,6 +656,41 @@ def dada_write_roundtrip():
         _same(fr.read(), data[:2333])
 
 
+def vdif_file_name_sequencer():
+    """helpers.sequentialfile.FileNameSequencer: templates filled from a
+    header, used for writing and reading a stream split over files
+    (helpers/sequentialfile.py:18-83, tests/test_sequentialfile.py)."""
+    import os
+    import tempfile
+    from baseband_b200.helpers import sequentialfile as sf
+    assert sf.FileNameSequencer('a{file_nr:03d}.vdif')[10] == 'a010.vdif'
+    raw = synthetic.vdif_stream(12, 4, 1000, seed=21)
+    want = ostream.vdif_read(raw)[:, :, 0]
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=1e6) as fh:
+        header0 = fh.header0
+    tmp = tempfile.mkdtemp()
+    fns = sf.FileNameSequencer(
+        os.path.join(tmp, 'obs.edv{edv:d}.{file_nr:05d}.vdif'), header0)
+    assert fns[3].endswith('obs.edv0.00003.vdif') and len(fns) == 0
+    with bb.vdif.open(fns, 'ws', header0=header0, nthread=4,
+                      sample_rate=1e6, file_size=4 * 4 * 1032) as fw:
+        fw.write(want)
+    assert len(fns) == 3 and fns[-1] == fns[2]
+    assert os.path.getsize(fns[0]) == 4 * 4 * 1032
+    with bb.vdif.open(fns, 'rs', sample_rate=1e6) as fh:
+        _same(fh.read(), want)
+    with bb.vdif.open([fns[i] for i in range(3)], 'rs',
+                      sample_rate=1e6) as fh:
+        fh.seek(5000)
+        _same(fh.read(3000), want[5000:8000])
+    try:
+        sf.FileNameSequencer('x{nope}.vdif', header0)
+    except KeyError:
+        pass
+    else:
+        raise AssertionError('unknown template key should raise KeyError')
+
+
 def dada_guppi_memmap_frame():
     """fw.memmap_frame(): header written at once, payload mapped and filled
     in pieces (dada/tests/test_dada.py:275-316, guppi likewise)."""
