@@ -264,6 +264,43 @@ class VDIFHeader(BitFieldHeader):
     def verify(self):
         pass
 
+    # Header parts that do not change within one stream
+    # (vdif/header.py:109-115, :561-566, :600-605).
+    _stream_invariants = ('legacy_mode', 'vdif_version', 'lg2_nchan',
+                          'frame_length', 'complex_data', 'bits_per_sample',
+                          'station_id', 'edv', 'sync_pattern',
+                          'sampling_unit', 'sampling_rate')
+
+    def invariants(self):
+        return {key for key in self._stream_invariants if key in self.keys()}
+
+    def same_stream(self, other):
+        """Whether ``other`` can be a header of the same stream
+        (vdif/header.py:153-155)."""
+        return all(key in other.keys() and self[key] == other[key]
+                   for key in self.invariants())
+
+    @classmethod
+    def from_mark5b_header(cls, mark5b_header, bps, nchan, **kwargs):
+        """Mark 5B-over-VDIF header (EDV 0xab) for a Mark 5B header
+        (vdif/header.py:246-288): the time code carries the whole seconds,
+        ``frame_nr`` and the BCD fraction are taken over unchanged."""
+        assert 'time' not in kwargs, 'Time is inferred from Mark 5B Header.'
+        from ..timeutil import Time
+        for key in mark5b_header.keys():
+            kwargs.setdefault(key, mark5b_header[key])
+        kwargs.pop('sync_pattern', None)
+        frame_nr = kwargs.pop('frame_nr')
+        whole = Time(mark5b_header.kday + mark5b_header.jday,
+                     mark5b_header.seconds)
+        self = cls.fromvalues(edv=0xab, bps=bps, nchan=nchan,
+                              complex_data=False, time=whole, **kwargs)
+        self.mutable = True
+        self['frame_nr'] = frame_nr
+        self['mark5b_frame_nr'] = frame_nr
+        self['bcd_fraction'] = mark5b_header['bcd_fraction']
+        return self
+
 
 class VDIFLegacyHeader(VDIFHeader):
     _struct = four_word_struct

@@ -656,6 +656,30 @@ def dada_write_roundtrip():
         _same(fr.read(), data[:2333])
 
 
+def vdif_header_same_stream_and_mark5b():
+    """VDIFHeader.same_stream (vdif/header.py:153-155) and
+    VDIFHeader.from_mark5b_header (:246-288)."""
+    with bb.vdif.open(sample_path('sample.vdif'), 'rb') as fh:
+        h1 = fh.read_frame().header
+        h2 = fh.read_frame().header
+    assert h1.same_stream(h2) and h1 != h2
+    other = h2.copy()
+    other.mutable = True
+    other['station_id'] = 1
+    assert not h1.same_stream(other)
+    with bb.mark5b.open(sample_path('sample.m5b'), 'rb', kday=56000,
+                        nchan=8) as fb:
+        fb.read_frame()
+        m5f = fb.read_frame()
+    vf = bb.vdif.VDIFFrame.from_mark5b_frame(m5f)
+    vh = bb.vdif.VDIFHeader.from_mark5b_header(
+        m5f.header, bps=m5f.payload.bps, nchan=m5f.payload.sample_shape[0])
+    assert vh == vf.header and vh.edv == 0xab
+    assert vh['frame_nr'] == m5f.header['frame_nr'] == 1
+    assert vh['bcd_fraction'] == m5f.header['bcd_fraction']
+    assert not h1.same_stream(vh)
+
+
 def vdif_file_name_sequencer():
     """helpers.sequentialfile.FileNameSequencer: templates filled from a
     header, used for writing and reading a stream split over files
