@@ -10,7 +10,8 @@ import torch
 from .. import codecs, device as _device, kernels
 from ..base.payload import PayloadBase
 
-__all__ = ['DADAPayload', 'MKBFPayload', 'decode_device']
+__all__ = ['decode_8bit', 'encode_8bit', 'DADAPayload', 'MKBFPayload',
+           'decode_device']
 
 HEAP = 256
 
@@ -46,6 +47,17 @@ def decode_device(raw, offset, nbytes, npol, nchan, complex_data, mkbf,
     kernels.decode_int8_transposed(raw, tables[0], n, npol * nchan, HEAP, ib,
                                    tables[1], tables[2], tables[3], out)
     return out
+
+
+# codec callables under their reference names (dada/payload.py:13-18)
+def decode_8bit(words):
+    from .. import codecs
+    return codecs.INT8_DECODERS[8](words)
+
+
+def encode_8bit(values):
+    from .. import codecs
+    return codecs.INT8_ENCODERS[8](values)
 
 
 class DADAPayload(PayloadBase):

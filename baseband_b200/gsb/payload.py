@@ -9,10 +9,32 @@ import numpy as np
 from .. import codecs
 from ..base.payload import PayloadBase
 
-__all__ = ['GSBPayload']
+__all__ = ['decode_4bit', 'decode_8bit', 'encode_4bit', 'encode_8bit',
+           'GSBPayload']
 
 _Shape1 = namedtuple('SampleShape', 'nchan')
 _ShapeN = namedtuple('SampleShape', 'nthread, nchan')
+
+
+# codec callables under their reference names (gsb/payload.py:17-53)
+def decode_4bit(words):
+    from .. import codecs
+    return codecs.GSB_DECODERS[4](words)
+
+
+def decode_8bit(words):
+    from .. import codecs
+    return codecs.GSB_DECODERS[8](words)
+
+
+def encode_4bit(values):
+    from .. import codecs
+    return codecs.GSB_ENCODERS[4](values)
+
+
+def encode_8bit(values):
+    from .. import codecs
+    return codecs.GSB_ENCODERS[8](values)
 
 
 class GSBPayload(PayloadBase):

@@ -16,7 +16,7 @@ from .. import device as _device
 from .. import kernels
 from ..base.payload import PayloadBase
 
-__all__ = ['GUPPIPayload']
+__all__ = ['decode_8bit', 'encode_8bit', 'GUPPIPayload']
 
 
 def _const(dev, *values):
@@ -56,6 +56,17 @@ def decode_device(raw, offsets, nsample, npol, nchan, complex_data,
     kernels.decode_int8_timefirst(raw, tables[0], nunit, nsample, nchan, npol,
                                   ib, tables[1], tables[2], tables[3], out)
     return out
+
+
+# codec callables under their reference names (guppi/payload.py:13-18)
+def decode_8bit(words):
+    from .. import codecs
+    return codecs.INT8_DECODERS[8](words)
+
+
+def encode_8bit(values):
+    from .. import codecs
+    return codecs.INT8_ENCODERS[8](values)
 
 
 class GUPPIPayload(PayloadBase):

@@ -10,7 +10,23 @@ from .. import codecs
 from ..base.payload import PayloadBase
 from .header import MARK4_DTYPES
 
-__all__ = ['Mark4Payload']
+__all__ = ['decode_2chan_2bit_fanout4', 'decode_4chan_2bit_fanout4',
+           'decode_8chan_2bit_fanout2', 'decode_8chan_2bit_fanout4',
+           'decode_16chan_2bit_fanout2_ft', 'encode_2chan_2bit_fanout4',
+           'encode_4chan_2bit_fanout4', 'encode_8chan_2bit_fanout2',
+           'encode_8chan_2bit_fanout4', 'encode_16chan_2bit_fanout2_ft',
+           'Mark4Payload']
+
+
+# codec callables under their reference names (mark4/payload.py:122-300)
+def _export_codecs():
+    from .. import codecs
+    for table in (codecs.MARK4_DECODERS, codecs.MARK4_ENCODERS):
+        for fn in table.values():
+            globals()[fn.__name__] = fn
+
+
+_export_codecs()
 
 
 class Mark4Payload(PayloadBase):

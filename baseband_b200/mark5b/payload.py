@@ -7,7 +7,12 @@ import numpy as np
 from .. import codecs
 from ..base.payload import PayloadBase
 
-__all__ = ['Mark5BPayload']
+__all__ = ['decode_1bit', 'decode_2bit', 'encode_1bit', 'encode_2bit',
+           'Mark5BPayload']
+
+# codec callables under their reference names (mark5b/payload.py:78-106)
+decode_1bit, decode_2bit = (codecs.MARK5B_DECODERS[bps] for bps in (1, 2))
+encode_1bit, encode_2bit = (codecs.MARK5B_ENCODERS[bps] for bps in (1, 2))
 
 
 class Mark5BPayload(PayloadBase):

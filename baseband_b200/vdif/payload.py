@@ -11,7 +11,29 @@ import numpy as np
 from .. import codecs
 from ..base.payload import PayloadBase
 
-__all__ = ['VDIFPayload']
+__all__ = ['init_luts', 'decode_1bit', 'decode_2bit', 'decode_4bit',
+           'encode_1bit', 'encode_2bit', 'encode_4bit', 'VDIFPayload']
+
+
+def init_luts():
+    """Byte -> samples look-up tables of the reference (vdif/payload.py:
+    25-66), LSB-first offset binary: constants, kept for API parity (the GPU
+    kernels build their own shared-memory tables from the same levels)."""
+    from ..levels import decoder_levels
+    b = np.arange(256)[:, np.newaxis]
+    lut1bit = decoder_levels[1][(b >> np.arange(8)) & 1]
+    lut2bit = decoder_levels[2][(b >> np.arange(0, 8, 2)) & 3]
+    lut4bit = decoder_levels[4][(b >> np.arange(0, 8, 4)) & 0xf]
+    return lut1bit, lut2bit, lut4bit
+
+
+lut1bit, lut2bit, lut4bit = init_luts()
+# The operator callables of the codec tables under their reference names
+# (vdif/payload.py:69-114): words -> float32, values -> packed bytes, on GPU.
+decode_1bit, decode_2bit, decode_4bit = (codecs.VDIF_DECODERS[bps]
+                                         for bps in (1, 2, 4))
+encode_1bit, encode_2bit, encode_4bit = (codecs.VDIF_ENCODERS[bps]
+                                         for bps in (1, 2, 4))
 
 
 class VDIFPayload(PayloadBase):

@@ -656,6 +656,70 @@ def dada_write_roundtrip():
         _same(fr.read(), data[:2333])
 
 
+def payload_reference_named_operators():
+    """The operator-level names of the reference (base/encoding.py,
+    <format>/payload.py module functions and look-up tables) against the
+    golden vectors produced by the reference itself."""
+    import os
+    from baseband_b200.base import encoding
+    from baseband_b200.vdif import payload as vp
+    from baseband_b200.mark5b import payload as m5p
+    from baseband_b200.mark4 import payload as m4p
+    from baseband_b200.guppi import payload as gp
+    from baseband_b200.dada import payload as dp
+    from baseband_b200.gsb import payload as gsp
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden',
+                             'codec_vectors.npz'))
+    assert encoding.OPTIMAL_2BIT_HIGH == 3.316505
+    assert encoding.TWO_BIT_1_SIGMA == 2.174564
+    for bps in (1, 2, 4):
+        _same(encoding.decoder_levels[bps], g['levels%d' % bps])
+        _same(getattr(vp, 'lut%dbit' % bps), g['vdif_lut%d' % bps])
+        _same(getattr(vp, 'decode_%dbit' % bps)(g['words32']).ravel(),
+              g['vdif_dec%d' % bps].ravel())
+    _same(encoding.decode_8bit(g['words32']).ravel(), g['vdif_dec8'].ravel())
+    for tag in ('f32', 'f64'):
+        vals = g['enc_in_' + tag]
+        for bps in (1, 2, 4):
+            packed = g['vdif_enc%d_%s' % (bps, tag)].view(np.uint8).ravel()
+            _same(getattr(vp, 'encode_%dbit' % bps)(vals).view(
+                np.uint8).ravel()[:packed.size], packed)
+            # ..._base: one code per value = the packed codes, LSB first
+            shifts = np.arange(0, 8, bps, dtype=np.uint8)
+            codes = ((packed[:, None] >> shifts) & ((1 << bps) - 1)).ravel()
+            got = getattr(encoding, 'encode_%dbit_base' % bps)(vals)
+            assert got.dtype == np.uint8 and got.shape == vals.shape
+            _same(got.ravel(), codes[:vals.size])
+        _same(encoding.encode_8bit(vals).view(np.uint8).ravel(),
+              g['vdif_enc8_' + tag].view(np.uint8).ravel())
+        for bps in (1, 2):
+            _same(getattr(m5p, 'encode_%dbit' % bps)(vals).view(
+                np.uint8).ravel(),
+                g['m5b_enc%d_%s' % (bps, tag)].view(np.uint8).ravel())
+        vals = g['enc_in_finite_' + tag]
+        _same(gp.encode_8bit(vals).view(np.uint8).ravel(),
+              g['int8_enc_' + tag].view(np.uint8).ravel())
+        _same(dp.encode_8bit(vals).view(np.uint8).ravel(),
+              g['int8_enc_' + tag].view(np.uint8).ravel())
+        _same(gsp.encode_4bit(vals).view(np.uint8).ravel(),
+              g['gsb4_enc_' + tag].view(np.uint8).ravel())
+    for bps in (1, 2):
+        _same(getattr(m5p, 'decode_%dbit' % bps)(g['words32']).ravel(),
+              g['m5b_dec%d' % bps].ravel())
+    _same(gp.decode_8bit(g['bytes']).ravel(), g['int8_dec'].ravel())
+    _same(gsp.decode_8bit(g['bytes']).ravel(), g['int8_dec'].ravel())
+    for tag, name in (('2_4', '2chan_2bit_fanout4'),
+                      ('4_4', '4chan_2bit_fanout4'),
+                      ('8_2', '8chan_2bit_fanout2'),
+                      ('8_4', '8chan_2bit_fanout4'),
+                      ('16_2ft', '16chan_2bit_fanout2_ft')):
+        _same(getattr(m4p, 'decode_' + name)(g['m4_words_' + tag]),
+              g['m4_dec_' + tag])
+        _same(getattr(m4p, 'encode_' + name)(g['m4_enc_in_%s_f32' % tag]
+                                             ).view(np.uint8).ravel(),
+              g['m4_enc_%s_f32' % tag].view(np.uint8).ravel())
+
+
 def vdif_header_same_stream_and_mark5b():
     """VDIFHeader.same_stream (vdif/header.py:153-155) and
     VDIFHeader.from_mark5b_header (:246-288)."""
