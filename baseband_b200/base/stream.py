@@ -252,6 +252,22 @@ class StreamBase:
     def readable(self):
         return hasattr(self, 'read') and not self.closed
 
+    @property
+    def info(self):
+        """Basic stream properties as an info object (the reference's
+        ``fh.info``, baseband/base/file_info.py:322-430, without its
+        consistency checks)."""
+        from .opener import FormatInfo
+        fmt = type(self).__module__.split('.')[-2]
+        attrs = dict(sample_rate=self.sample_rate,
+                     sample_shape=tuple(self.sample_shape),
+                     samples_per_frame=self.samples_per_frame,
+                     bps=self.bps, complex_data=self.complex_data,
+                     start_time=self.start_time, readable=self.readable())
+        if hasattr(self, 'read'):
+            attrs.update(shape=self.shape, stop_time=self.stop_time)
+        return FormatInfo(fmt, True, **attrs)
+
     def writable(self):
         return hasattr(self, 'write') and not self.closed
 

@@ -720,6 +720,21 @@ def payload_reference_named_operators():
               g['m4_enc_%s_f32' % tag].view(np.uint8).ravel())
 
 
+def vdif_stream_info_property():
+    """fh.info on stream readers (base/file_info.py StreamReaderInfo)."""
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
+        info = fh.info
+        assert info and info.format == 'vdif' and info.readable
+        assert info.shape == (40000, 8) and info.bps == 2
+        assert info.sample_rate == 32e6 and not info.complex_data
+        assert info.start_time == fh.start_time
+        assert info.stop_time == fh.stop_time
+    with bb.dada.open(sample_path('sample.dada'), 'rs') as fh:
+        info = fh.info
+        assert info.format == 'dada' and info.complex_data
+        assert info.sample_shape == (2,)
+
+
 def vdif_header_same_stream_and_mark5b():
     """VDIFHeader.same_stream (vdif/header.py:153-155) and
     VDIFHeader.from_mark5b_header (:246-288)."""
