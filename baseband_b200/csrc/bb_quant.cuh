@@ -149,18 +149,52 @@ BB_HD uint32_t quant4_offset(T v, const QuantConsts<T> &c) {
 
 // encoding.py:147-158
 template <typename T>
-BB_HD uint32_t quant8_offset(T v, const QuantConsts<T> &c) {
-    T x = rint_t(add_rn(mul_rn(v, c.eight_bit_scale), (T)127.5));
-    return to_code(clip_nan(x, (T)0, (T)255));
-}
+BB_HD uint32_t quant8_offset(T v, const QuantConsts<T> &c);
 
 // guppi/payload.py:17-18, dada/payload.py:17-18, gsb/payload.py:45-53
+// = clip(rint(v), lo, hi) cast to int (rint = round half to even).  Clipping
+// to the integer bounds first gives the same result (both steps are monotonic
+// and the bounds are integers), and then the rounding is one addition: adding
+// 1.5 * 2^23 (2^52 for double) to a value in [-128, 127] leaves the
+// round-half-even integer in the low mantissa bits, in two's complement.
+// This avoids the FRND + F2I pair, which both issue on the quarter-rate
+// conversion pipe (the int8 encoders were limited by it).
+BB_HD uint32_t magic_round_bits(float y) {
+    const float t = add_rn(y, 12582912.0f);
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(t);
+#else
+    uint32_t u;
+    __builtin_memcpy(&u, &t, 4);
+    return u;
+#endif
+}
+BB_HD uint32_t magic_round_bits(double y) {
+    const double t = add_rn(y, 6755399441055744.0);
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__double2loint(t);
+#else
+    unsigned long long u;
+    __builtin_memcpy(&u, &t, 8);
+    return (uint32_t)u;
+#endif
+}
+
 template <typename T, int BPS>
 BB_HD uint32_t quant_sint(T v) {
     const T lo = (T)(-(1 << (BPS - 1))), hi = (T)((1 << (BPS - 1)) - 1);
-    T x = clip_nan(rint_t(v), lo, hi);
-    int32_t i = (x != x) ? 0 : (int32_t)x;
-    return (uint32_t)i & ((1u << BPS) - 1u);
+    const T y = clip_nan(v, lo, hi);
+    const uint32_t bits = (y != y) ? 0u : magic_round_bits(y);
+    return bits & ((1u << BPS) - 1u);
+}
+
+// encoding.py:147-158: clip(rint(v * 35.5 + 127.5), 0, 255), rounded the same
+// way (clip to the integer bounds, then one magic addition).
+template <typename T>
+BB_HD uint32_t quant8_offset(T v, const QuantConsts<T> &c) {
+    const T y = clip_nan(add_rn(mul_rn(v, c.eight_bit_scale), (T)127.5),
+                         (T)0, (T)255);
+    return (y != y) ? 0u : (magic_round_bits(y) & 0xffu);
 }
 
 enum { QUANT_OFFSET = 0, QUANT_MARK5B = 1, QUANT_SINT = 2 };
