@@ -103,7 +103,7 @@ inline bool affine8_matches(const float *levels) {
 
 template <int BPS>
 BB_HD float sint_code(uint32_t w, uint32_t pos) {
-    return (float)((int32_t)(w << (32 - BPS - pos)) >> (32 - BPS));
+    return small_int_to_float((int32_t)(w << (32 - BPS - pos)) >> (32 - BPS));
 }
 
 // Values of codes 2j and 2j+1 of word w.

@@ -107,6 +107,12 @@ BB_HD float uint_as_float(uint32_t u) {
     return f;
 #endif
 }
+// Small signed integer (|i| < 2^22) -> float without the conversion pipe: i is
+// added to the mantissa of 1.5 * 2^23, whose ulp is 1, and the offset removed
+// by one exact subtraction.
+BB_HD float small_int_to_float(int32_t i) {
+    return add_rn(uint_as_float(0x4B400000u + (uint32_t)i), -12582912.0f);
+}
 BB_HD double add_rn(double a, double b) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(a, b);

@@ -257,7 +257,7 @@ BB_HD void f8_dec_load(const I8Geom &p, uint32_t *smem, uint32_t block,
 }
 
 BB_HD float f8_byte(uint32_t w, int k) {
-    return (float)(int8_t)(w >> (8 * k));
+    return small_int_to_float((int32_t)(int8_t)(w >> (8 * k)));
 }
 
 BB_HD void f8_dec_store(const I8Geom &p, const uint32_t *smem, uint32_t block,
@@ -505,7 +505,9 @@ BB_HD void tf_store_group(uint8_t *d, const uint32_t w[NPOL]) {
     for (int i = 0; i < 4 * NPOL; ++i) d[i] = (uint8_t)tf_get_byte(w, i);
 }
 
-BB_HD float tf_f(uint32_t b) { return (float)(int8_t)b; }
+BB_HD float tf_f(uint32_t b) {
+    return small_int_to_float((int32_t)(int8_t)b);
+}
 
 template <int NPOL>
 BB_HD void tf_decode_group(const TFGeom &p, uint32_t unit, uint32_t item,
