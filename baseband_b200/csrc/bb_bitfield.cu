@@ -116,6 +116,21 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
                 if (item >= p.nitems) break;
+                if (wrow_interior<BPS, G>(p, item >> 5)) {   // warp uniform
+                    float *chunk_out = wrow_chunk_out<BPS, G>(p, item >> 5);
+#pragma unroll
+                    for (int j = 0; j < TPW; ++j) {
+                        const uint32_t src = wrow_src_lane<BPS, G>(lane, j);
+                        uint32_t ws[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            ws[g] = wbuf[warp][b][src][g];
+                        wrow_emit_fast<BPS, CODEC, G>(
+                            p, lut, chunk_out, lane + 32u * j, ws,
+                            okbuf[warp][b][src]);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < TPW; ++j) {
                     const uint32_t src = wrow_src_lane<BPS, G>(lane, j);

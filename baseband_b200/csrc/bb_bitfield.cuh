@@ -413,6 +413,54 @@ BB_HD void wrow_emit(const DecGeom &p, const float *lut, uint32_t chunk,
     *reinterpret_cast<F4 *>(p.out + row * 4) = v;
 }
 
+// Interior chunks (all 32 word positions inside the launch, all 32 * TPW rows
+// inside the requested range; warp uniform): no per-row bounds checks, one
+// 64-bit output base per chunk; the code position c = q % TPW and the source
+// lane are loop invariant per (lane, j).
+template <int BPS, int G>
+BB_HD bool wrow_interior(const DecGeom &p, uint32_t chunk) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    if ((unsigned long long)chunk * 32u + 32u > p.nwords_total) return false;
+    const long long row0 = p.row_base + (long long)chunk * (32 * TPW);
+    return row0 >= 0 && row0 + 32 * TPW <= p.nsample;
+}
+
+template <int BPS, int G>
+BB_HD float *wrow_chunk_out(const DecGeom &p, uint32_t chunk) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    return p.out + (p.row_base + (long long)chunk * (32 * TPW)) * 4;
+}
+
+template <int BPS, int CODEC, int G>
+BB_HD void wrow_emit_fast(const DecGeom &p, const float *lut, float *chunk_out,
+                          uint32_t q, const uint32_t w[G], uint32_t okmask) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    const uint32_t c = q % TPW;
+    F4 v;
+    if (G == 4) {
+        v = F4{decode_one<BPS, CODEC>(w[0], c, lut),
+               decode_one<BPS, CODEC>(w[1 % G], c, lut),
+               decode_one<BPS, CODEC>(w[2 % G], c, lut),
+               decode_one<BPS, CODEC>(w[3 % G], c, lut)};
+        if (okmask != 0xfu) {                      // some slot is fill
+            if (!(okmask & 1u)) v.x = p.fill;
+            if (!(okmask & 2u)) v.y = p.fill;
+            if (!(okmask & 4u)) v.z = p.fill;
+            if (!(okmask & 8u)) v.w = p.fill;
+        }
+    } else {
+        const F2 a = decode_pair<BPS, CODEC>(w[0], c, lut);
+        const F2 b = decode_pair<BPS, CODEC>(w[1 % G], c, lut);
+        v = F4{a.x, a.y, b.x, b.y};
+        if (okmask != 0x3u) {
+            const float fill_im = p.complex_fill ? 0.f : p.fill;
+            if (!(okmask & 1u)) { v.x = p.fill; v.y = fill_im; }
+            if (!(okmask & 2u)) { v.z = p.fill; v.w = fill_im; }
+        }
+    }
+    *reinterpret_cast<F4 *>(chunk_out + 4u * q) = v;
+}
+
 // SCALAR: item = element index within the launch's block of rows.
 template <int BPS, int CODEC>
 BB_HD void dec_scalar(const DecGeom &p, const float *lut, uint32_t item) {

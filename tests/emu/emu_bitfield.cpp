@@ -46,11 +46,17 @@ static void run_decode(const std::vector<DecLaunch> &launches,
                 uint32_t w[32][4], ok[32];
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     ok[lane] = wrow_load<4>(l.g, chunk, lane, w[lane]);
+                const bool interior = wrow_interior<BPS, 4>(l.g, chunk);
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     for (int j = 0; j < TPW; ++j) {
                         uint32_t src = wrow_src_lane<BPS, 4>(lane, j);
-                        wrow_emit<BPS, CODEC, 4>(l.g, lut, chunk, lane, j,
-                                                 w[src], ok[src]);
+                        if (interior)
+                            wrow_emit_fast<BPS, CODEC, 4>(
+                                l.g, lut, wrow_chunk_out<BPS, 4>(l.g, chunk),
+                                lane + 32u * j, w[src], ok[src]);
+                        else
+                            wrow_emit<BPS, CODEC, 4>(l.g, lut, chunk, lane, j,
+                                                     w[src], ok[src]);
                     }
             }
             continue;
@@ -61,11 +67,17 @@ static void run_decode(const std::vector<DecLaunch> &launches,
                 uint32_t w[32][2], ok[32];
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     ok[lane] = wrow_load<2>(l.g, chunk, lane, w[lane]);
+                const bool interior = wrow_interior<BPS, 2>(l.g, chunk);
                 for (uint32_t lane = 0; lane < 32; ++lane)
                     for (int j = 0; j < TPW; ++j) {
                         uint32_t src = wrow_src_lane<BPS, 2>(lane, j);
-                        wrow_emit<BPS, CODEC, 2>(l.g, lut, chunk, lane, j,
-                                                 w[src], ok[src]);
+                        if (interior)
+                            wrow_emit_fast<BPS, CODEC, 2>(
+                                l.g, lut, wrow_chunk_out<BPS, 2>(l.g, chunk),
+                                lane + 32u * j, w[src], ok[src]);
+                        else
+                            wrow_emit<BPS, CODEC, 2>(l.g, lut, chunk, lane, j,
+                                                     w[src], ok[src]);
                     }
             }
             continue;
