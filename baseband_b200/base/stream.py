@@ -498,6 +498,14 @@ class StreamReaderBase(StreamBase):
             raise EOFError('cannot read from beyond end of input.')
         to_device = _device.is_device_tensor(out) or (
             out is None and self._device_output)
+        if (not to_device and on_device is None and count > 0
+                and self._small_read_cache_ok
+                and (out is None or isinstance(out, np.ndarray))
+                and count * self._floats_per_sample * 4
+                <= self.SMALL_READ_NBYTES):
+            result = self._read_small_cached(self.offset, count, out)
+            self.offset += count
+            return result
         self._on_device = on_device
         try:
             if to_device:
@@ -508,6 +516,37 @@ class StreamReaderBase(StreamBase):
             self._on_device = None
         self.offset += count
         return result
+
+    # Small host reads.  The reference decodes a whole frame and keeps it, so
+    # a loop of small reads costs one decode per frame plus slicing
+    # (base/base.py:990-996).  A GPU round trip per call (copy in, launch,
+    # copy out: ~0.4 ms) would make exactly that pattern slower than the
+    # reference, so small reads are served from a decoded window of whole
+    # frames (at most SMALL_READ_WINDOW_NBYTES), refilled when a read leaves it.
+    SMALL_READ_NBYTES = 256 << 10
+    SMALL_READ_WINDOW_NBYTES = 8 << 20
+    _small_cache = None
+    # False where the samples returned depend on where a read starts (GUPPI
+    # frames with overlap: a read runs on through the overlap of the frame it
+    # starts in, guppi/base.py:203-221)
+    _small_read_cache_ok = True
+
+    def _read_small_cached(self, start, count, out):
+        nb = self._floats_per_sample * 4
+        block = max(1, min(self._samples_per_frame,
+                           self.SMALL_READ_WINDOW_NBYTES // nb))
+        cache = self._small_cache
+        if (cache is None or start < cache[0] or start + count > cache[1]
+                or cache[3] != self._fill_value):
+            w0 = start // block * block
+            w1 = min(self._nsample, -(-(start + count) // block) * block)
+            data = self._read_to_host(w0, w1 - w0, None)
+            cache = self._small_cache = (w0, w1, data, self._fill_value)
+        piece = cache[2][start - cache[0]:start - cache[0] + count]
+        if out is None:
+            return piece.copy()
+        out[...] = piece
+        return out
 
     # -- geometry hooks --------------------------------------------------
     _file_offset0 = 0            # byte offset of frame 0 in the file
@@ -755,6 +794,7 @@ class StreamReaderBase(StreamBase):
         state = self.__dict__.copy()
         state['_stages'] = None
         state['_streams'] = None
+        state['_small_cache'] = None
         state.pop('_slots_dev', None)
         state.pop('_sample_shape_cache', None)    # namedtuple made on the fly
         wrapper = state['fh_raw']

@@ -81,6 +81,7 @@ class GUPPIStreamReader(_GUPPIStreamBase, StreamReaderBase):
         header0 = fh_raw.read_header()
         self._full_spf = header0.samples_per_frame
         self._overlap = header0.overlap
+        self._small_read_cache_ok = self._overlap == 0
         self._frame_nbytes = header0.frame_nbytes
         size = fh_raw.seek(0, 2)
         self._nframe = size // header0.frame_nbytes

@@ -720,6 +720,53 @@ def payload_reference_named_operators():
               g['m4_enc_%s_f32' % tag].view(np.uint8).ravel())
 
 
+def vdif_small_reads_window_cache():
+    """Loops of small host reads are served from a decoded window of whole
+    frames (base/stream.py:_read_small_cached), like the reference's frame
+    cache (base/base.py:990-996): same values at every position, fill_value
+    changes and large reads bypass / invalidate it."""
+    raw = synthetic.vdif_stream(12, 4, 1000, seed=31, invalid=[9, 22])
+    want = ostream.vdif_read(raw, fill_value=-5.)[:, :, 0]
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=1e6,
+                      fill_value=-5.) as fh:
+        spf = fh.samples_per_frame
+        got = []
+        while fh.tell() < fh.shape[0]:
+            got.append(fh.read(min(777, fh.shape[0] - fh.tell())))
+        _same(np.concatenate(got), want)
+        assert fh._small_cache is not None
+        # random small reads, some straddling frames, into out= as well
+        rng = np.random.default_rng(3)
+        for _ in range(40):
+            start = int(rng.integers(0, want.shape[0] - 50))
+            n = int(rng.integers(1, 50))
+            fh.seek(start)
+            if rng.random() < 0.5:
+                _same(fh.read(n), want[start:start + n])
+            else:
+                out = np.empty((n, 4), np.float32)
+                assert fh.read(out=out) is out
+                _same(out, want[start:start + n])
+            assert fh.tell() == start + n
+        # a returned array is a copy: writing to it must not poison the cache
+        fh.seek(10)
+        a = fh.read(5)
+        a[:] = 99.
+        fh.seek(10)
+        _same(fh.read(5), want[10:15])
+        # the window spans whole frames around the read
+        w0, w1 = fh._small_cache[:2]
+        assert w0 % spf == 0 and w0 <= 10 < w1
+        fh.seek(0)
+        _same(fh.read(), want)                   # large read: direct path
+        fh.seek(spf * 3 - 2)
+        _same(fh.read(4), want[spf * 3 - 2:spf * 3 + 2])
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=1e6,
+                      subset=[2, 0]) as fh:
+        fh.seek(4000 * 2 + 17)                   # inside invalid frame 9
+        _same(fh.read(30), ostream.vdif_read(raw)[8017:8047, :, 0][:, [2, 0]])
+
+
 def vdif_stream_info_property():
     """fh.info on stream readers (base/file_info.py StreamReaderInfo)."""
     with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
