@@ -858,6 +858,7 @@ class StreamWriterBase(StreamBase):
         super().__init__(fh_raw, header0, squeeze=squeeze, device=device,
                          **kwargs)
         self._pending = []           # [(tensor (n, fps...), valid)]
+        self._nowned = 0             # leading entries that are our own copies
         self._npending = 0
         self._frame_index = 0
 
@@ -937,9 +938,12 @@ class StreamWriterBase(StreamBase):
             self._npending += pad
             nframe += 1
         if nframe == 0:
-            # keep our own copy: the caller's tensor may be a view of a
-            # buffer that is about to be reused (read(on_device=...))
-            self._pending = [(t.clone(), ok) for t, ok in self._pending]
+            # keep our own copy of what this call added: the caller's tensor
+            # may be a view of a buffer that is about to be reused
+            # (read(on_device=...)); earlier entries already are copies
+            self._pending[self._nowned:] = [
+                (t.clone(), ok) for t, ok in self._pending[self._nowned:]]
+            self._nowned = len(self._pending)
             return
         take = nframe * spf
         # validity per frame = AND over the writes that touch it
@@ -968,6 +972,7 @@ class StreamWriterBase(StreamBase):
         self._write_raw(frames)
         self._frame_index += nframe
         self._pending = [(rest.clone(), rest_valid)] if rest.shape[0] else []
+        self._nowned = len(self._pending)
         self._npending = int(rest.shape[0])
 
     def _encode_frames(self, flat, index0, nframe, valid):

@@ -767,6 +767,38 @@ def vdif_small_reads_window_cache():
         _same(fh.read(30), ostream.vdif_read(raw)[8017:8047, :, 0][:, [2, 0]])
 
 
+def vdif_many_small_writes():
+    """Frames assembled from many small write() calls (host arrays, mixed
+    valid flags) equal the frames of one big write."""
+    rng = np.random.default_rng(17)
+    data = (rng.standard_normal((5 * 4000, 4)) * 2.5).astype(np.float32)
+    h0 = bb.vdif.VDIFHeader.fromvalues(
+        edv=0, time='2020-01-01T00:00:00', nchan=1, bps=2,
+        complex_data=False, thread_id=0, samples_per_frame=4000,
+        station='bb', frame_nr=0)
+
+    def written(pieces, valid=None):
+        buf = io.BytesIO()
+        fw = bb.vdif.open(buf, 'ws', header0=h0, nthread=4, sample_rate=1e6)
+        pos = 0
+        for i, n in enumerate(pieces):
+            ok = True if valid is None else valid(pos, n)
+            fw.write(data[pos:pos + n], valid=ok)
+            pos += n
+        assert pos == data.shape[0]
+        return buf.getvalue()
+
+    whole = written([data.shape[0]])
+    sizes = [37] * (data.shape[0] // 37) + [data.shape[0] % 37]
+    assert written(sizes) == whole
+    assert written([3999, 1, 2, 7998, 8000]) == whole
+    # a piece flagged invalid marks exactly the frames it touches
+    bad = written(sizes, valid=lambda pos, n: not (pos <= 8100 < pos + n))
+    frames = np.frombuffer(bad, np.uint8).reshape(5 * 4, 1032)
+    invalid = (frames[:, 3] >> 7).reshape(5, 4)
+    assert invalid[2].all() and not invalid[[0, 1, 3, 4]].any()
+
+
 def vdif_stream_info_property():
     """fh.info on stream readers (base/file_info.py StreamReaderInfo)."""
     with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
