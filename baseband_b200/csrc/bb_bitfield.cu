@@ -21,7 +21,9 @@ struct Unroll {
         : MODE == MODE_ROWGROUP2 ? 16 / BPS
         : MODE == MODE_WORDRUN ? 8 / BPS
         : MODE == MODE_WORDROW4 ? 32 / BPS
-        : MODE == MODE_WORDROW2 ? 16 / BPS : 1;
+        : MODE == MODE_WORDROW2 ? 16 / BPS
+        : MODE == MODE_WORDROW4X2 ? 64 / BPS
+        : MODE == MODE_WORDROW2X2 ? 32 / BPS : 1;
     static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
 };
 
@@ -86,14 +88,20 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         }
         return;
     }
-    if (MODE == MODE_WORDROW4 || MODE == MODE_WORDROW2) {
-        // The G slot words of every lane go through shared memory (one
-        // STS.128 / STS.64 per lane and chunk); a row then costs one LDS
+    if (MODE == MODE_WORDROW4 || MODE == MODE_WORDROW2
+        || MODE == MODE_WORDROW4X2 || MODE == MODE_WORDROW2X2) {
+        // The slot words of every lane go through shared memory (one vector
+        // store per lane and chunk); a float4 then costs one LDS.128 / LDS.64
         // instead of G + 1 shuffles.
-        constexpr int G = MODE == MODE_WORDROW4 ? 4 : 2;
+        constexpr int G = (MODE == MODE_WORDROW4 || MODE == MODE_WORDROW4X2)
+            ? 4 : 2;
+        constexpr int NG = (MODE == MODE_WORDROW4X2
+                            || MODE == MODE_WORDROW2X2) ? 2 : 1;
+        constexpr int W = G * NG;                 // words (slots) per row
         constexpr int TPW = (32 / BPS) / (4 / G);
+        constexpr int NST = TPW * NG;             // stores per lane and chunk
         constexpr int WB = U < 2 ? U : 2;         // chunks loaded up front
-        __shared__ __align__(16) uint32_t wbuf[kBlock / 32][WB][32][G];
+        __shared__ __align__(16) uint32_t wbuf[kBlock / 32][WB][32][W];
         __shared__ uint32_t okbuf[kBlock / 32][WB][32];
         const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 #pragma unroll 1
@@ -102,13 +110,13 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 #pragma unroll
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
-                uint32_t w[G];
+                uint32_t w[W];
                 uint32_t ok = 0u;
 #pragma unroll
-                for (int g = 0; g < G; ++g) w[g] = 0u;
-                if (item < p.nitems) ok = wrow_load<G>(p, item >> 5, lane, w);
+                for (int g = 0; g < W; ++g) w[g] = 0u;
+                if (item < p.nitems) ok = wrow_load<W>(p, item >> 5, lane, w);
 #pragma unroll
-                for (int g = 0; g < G; ++g) wbuf[warp][b][lane][g] = w[g];
+                for (int g = 0; g < W; ++g) wbuf[warp][b][lane][g] = w[g];
                 okbuf[warp][b][lane] = ok;
             }
             __syncwarp();
@@ -116,29 +124,25 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
                 if (item >= p.nitems) break;
-                if (wrow_interior<BPS, G>(p, item >> 5)) {   // warp uniform
-                    float *chunk_out = wrow_chunk_out<BPS, G>(p, item >> 5);
+                const bool interior = wrow_interior<BPS, G>(p, item >> 5);
+                float *chunk_out = wrow_chunk_out<BPS, G, NG>(p, item >> 5);
 #pragma unroll
-                    for (int j = 0; j < TPW; ++j) {
-                        const uint32_t src = wrow_src_lane<BPS, G>(lane, j);
-                        uint32_t ws[G];
-#pragma unroll
-                        for (int g = 0; g < G; ++g)
-                            ws[g] = wbuf[warp][b][src][g];
-                        wrow_emit_fast<BPS, CODEC, G>(
-                            p, lut, chunk_out, lane + 32u * j, ws,
-                            okbuf[warp][b][src]);
-                    }
-                    continue;
-                }
-#pragma unroll
-                for (int j = 0; j < TPW; ++j) {
-                    const uint32_t src = wrow_src_lane<BPS, G>(lane, j);
+                for (int j = 0; j < NST; ++j) {
+                    const uint32_t q = lane + 32u * j;
+                    const uint32_t src = wrow_src_lane<BPS, G, NG>(lane, j);
+                    const uint32_t grp = q % NG;
                     uint32_t ws[G];
 #pragma unroll
-                    for (int g = 0; g < G; ++g) ws[g] = wbuf[warp][b][src][g];
-                    wrow_emit<BPS, CODEC, G>(p, lut, item >> 5, lane, j, ws,
-                                             okbuf[warp][b][src]);
+                    for (int g = 0; g < G; ++g)
+                        ws[g] = wbuf[warp][b][src][grp * G + g];
+                    const uint32_t ok = (okbuf[warp][b][src] >> (grp * G))
+                        & ((1u << G) - 1u);
+                    if (interior)                 // warp uniform
+                        wrow_emit_fast<BPS, CODEC, G, NG>(p, lut, chunk_out,
+                                                          q, ws, ok);
+                    else
+                        wrow_emit<BPS, CODEC, G, NG>(p, lut, item >> 5, lane,
+                                                     j, ws, ok);
                 }
             }
         }
@@ -288,6 +292,16 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
             k_decode_bitfield<BPS, CODEC, MODE_WORDROW2>
                 <<<tile_grid(n, Unroll<BPS, MODE_WORDROW2>::value), kBlock, 0,
                    stream>>>(l.g, lv);
+            break;
+        case MODE_WORDROW4X2:
+            k_decode_bitfield<BPS, CODEC, MODE_WORDROW4X2>
+                <<<tile_grid(n, Unroll<BPS, MODE_WORDROW4X2>::value), kBlock,
+                   0, stream>>>(l.g, lv);
+            break;
+        case MODE_WORDROW2X2:
+            k_decode_bitfield<BPS, CODEC, MODE_WORDROW2X2>
+                <<<tile_grid(n, Unroll<BPS, MODE_WORDROW2X2>::value), kBlock,
+                   0, stream>>>(l.g, lv);
             break;
         default:
             k_decode_bitfield<BPS, CODEC, MODE_SCALAR>

@@ -351,31 +351,35 @@ BB_HD void wr_emit(const DecGeom &p, const float *lut, uint32_t chunk,
     *reinterpret_cast<F4 *>(p.out + gidx) = v;
 }
 
-// WORDROW<G>: nthread * E == 4 (G = 4 single-channel threads, or G = 2
-// threads of one complex channel), so an output row is one float4.  Like
-// WORDRUN, a warp takes 32 consecutive word positions -- here of all G
-// slots, G coalesced 128-byte loads -- whose decoded rows form one contiguous
-// run of 32 * TPW float4 (TPW = rows per word).  Store j: lane L writes row
-// q = L + 32 j of the chunk from the G words of lane q / TPW (staged in
-// shared memory by the kernel).
-template <int BPS, int G>
+// WORDROW<G, NG>: nthread * E == 4 * NG (G = 4 single-channel threads or G = 2
+// threads of one complex channel per float4; NG = 1 or 2 float4 per output
+// row).  Like WORDRUN, a warp takes 32 consecutive word positions -- here of
+// all G * NG slots, that many coalesced 128-byte loads -- whose decoded rows
+// form one contiguous run of 32 * TPW * NG float4 (TPW = rows per word).
+// Store j: lane L writes float4 q = L + 32 j of the chunk = group q % NG of
+// row q / NG, from the G words of that group held by lane (q / NG) / TPW
+// (staged in shared memory by the kernel).  Every warp store is 512
+// contiguous bytes, where ROWGROUP's would be 16 pieces of 32 bytes for rows
+// of 8 floats.
+template <int BPS, int G, int NG>
 BB_HD uint32_t wrow_src_lane(uint32_t lane, int j) {
-    return (lane + 32u * j) / ((32 / BPS) / (4 / G));
+    return ((lane + 32u * j) / NG) / ((32 / BPS) / (4 / G));
 }
 
-template <int G>
+// W = G * NG words (all slots of a row) of word position chunk * 32 + lane.
+template <int W>
 BB_HD uint32_t wrow_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
-                         uint32_t w[G]) {
+                         uint32_t w[W]) {
 #pragma unroll
-    for (int j = 0; j < G; ++j) w[j] = 0u;
+    for (int j = 0; j < W; ++j) w[j] = 0u;
     const uint32_t idx = chunk * 32u + lane;   // word position over all sets
     if (idx >= p.nwords_total) return 0u;
     uint32_t set, k;
     p.div_nword.divmod(idx, set, k);
-    const long long *uo = p.unit_offset + (size_t)set * G;
+    const long long *uo = p.unit_offset + (size_t)set * W;
     uint32_t okmask = 0u;
 #pragma unroll
-    for (int j = 0; j < G; ++j) {
+    for (int j = 0; j < W; ++j) {
         const long long off = uo[j];
         if (off >= 0) {
             w[j] = load_u32(p.src + off + 4ull * k);
@@ -385,57 +389,10 @@ BB_HD uint32_t wrow_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
     return okmask;
 }
 
+// One float4: code position c of the G words w; okmask bit g: slot g valid.
 template <int BPS, int CODEC, int G>
-BB_HD void wrow_emit(const DecGeom &p, const float *lut, uint32_t chunk,
-                     uint32_t lane, int j, const uint32_t w[G],
-                     uint32_t okmask) {
-    constexpr int TPW = (32 / BPS) / (4 / G);
-    const uint32_t q = lane + 32u * j;                 // row within the chunk
-    if (chunk * 32u + q / TPW >= p.nwords_total) return;
-    const long long row = p.row_base + ((long long)chunk * 32 * TPW + q);
-    if (row < 0 || row >= p.nsample) return;
-    const uint32_t c = q % TPW;
-    F4 v;
-    if (G == 4) {
-        v.x = (okmask & 1u) ? decode_one<BPS, CODEC>(w[0], c, lut) : p.fill;
-        v.y = (okmask & 2u) ? decode_one<BPS, CODEC>(w[1 % G], c, lut) : p.fill;
-        v.z = (okmask & 4u) ? decode_one<BPS, CODEC>(w[2 % G], c, lut) : p.fill;
-        v.w = (okmask & 8u) ? decode_one<BPS, CODEC>(w[3 % G], c, lut) : p.fill;
-    } else {
-        const float fill_im = p.complex_fill ? 0.f : p.fill;
-        const F2 a = decode_pair<BPS, CODEC>(w[0], c, lut);
-        const F2 b = decode_pair<BPS, CODEC>(w[1 % G], c, lut);
-        v.x = (okmask & 1u) ? a.x : p.fill;
-        v.y = (okmask & 1u) ? a.y : fill_im;
-        v.z = (okmask & 2u) ? b.x : p.fill;
-        v.w = (okmask & 2u) ? b.y : fill_im;
-    }
-    *reinterpret_cast<F4 *>(p.out + row * 4) = v;
-}
-
-// Interior chunks (all 32 word positions inside the launch, all 32 * TPW rows
-// inside the requested range; warp uniform): no per-row bounds checks, one
-// 64-bit output base per chunk; the code position c = q % TPW and the source
-// lane are loop invariant per (lane, j).
-template <int BPS, int G>
-BB_HD bool wrow_interior(const DecGeom &p, uint32_t chunk) {
-    constexpr int TPW = (32 / BPS) / (4 / G);
-    if ((unsigned long long)chunk * 32u + 32u > p.nwords_total) return false;
-    const long long row0 = p.row_base + (long long)chunk * (32 * TPW);
-    return row0 >= 0 && row0 + 32 * TPW <= p.nsample;
-}
-
-template <int BPS, int G>
-BB_HD float *wrow_chunk_out(const DecGeom &p, uint32_t chunk) {
-    constexpr int TPW = (32 / BPS) / (4 / G);
-    return p.out + (p.row_base + (long long)chunk * (32 * TPW)) * 4;
-}
-
-template <int BPS, int CODEC, int G>
-BB_HD void wrow_emit_fast(const DecGeom &p, const float *lut, float *chunk_out,
-                          uint32_t q, const uint32_t w[G], uint32_t okmask) {
-    constexpr int TPW = (32 / BPS) / (4 / G);
-    const uint32_t c = q % TPW;
+BB_HD F4 wrow_decode(const DecGeom &p, const float *lut, uint32_t c,
+                     const uint32_t w[G], uint32_t okmask) {
     F4 v;
     if (G == 4) {
         v = F4{decode_one<BPS, CODEC>(w[0], c, lut),
@@ -458,7 +415,49 @@ BB_HD void wrow_emit_fast(const DecGeom &p, const float *lut, float *chunk_out,
             if (!(okmask & 2u)) { v.z = p.fill; v.w = fill_im; }
         }
     }
-    *reinterpret_cast<F4 *>(chunk_out + 4u * q) = v;
+    return v;
+}
+
+// Checked store (edges of the read / of the launch).  ``w`` and ``okmask``
+// are those of the float4's group.
+template <int BPS, int CODEC, int G, int NG>
+BB_HD void wrow_emit(const DecGeom &p, const float *lut, uint32_t chunk,
+                     uint32_t lane, int j, const uint32_t w[G],
+                     uint32_t okmask) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    const uint32_t q = lane + 32u * j;                 // float4 in the chunk
+    const uint32_t r = q / NG;                         // row within the chunk
+    if (chunk * 32u + r / TPW >= p.nwords_total) return;
+    const long long row = p.row_base + ((long long)chunk * 32 * TPW + r);
+    if (row < 0 || row >= p.nsample) return;
+    *reinterpret_cast<F4 *>(p.out + (row * NG + q % NG) * 4) =
+        wrow_decode<BPS, CODEC, G>(p, lut, r % TPW, w, okmask);
+}
+
+// Interior chunks (all 32 word positions inside the launch, all 32 * TPW rows
+// inside the requested range; warp uniform): no per-row bounds checks, one
+// 64-bit output base per chunk; the code position and the source lane are
+// loop invariant per (lane, j).
+template <int BPS, int G>
+BB_HD bool wrow_interior(const DecGeom &p, uint32_t chunk) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    if ((unsigned long long)chunk * 32u + 32u > p.nwords_total) return false;
+    const long long row0 = p.row_base + (long long)chunk * (32 * TPW);
+    return row0 >= 0 && row0 + 32 * TPW <= p.nsample;
+}
+
+template <int BPS, int G, int NG>
+BB_HD float *wrow_chunk_out(const DecGeom &p, uint32_t chunk) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    return p.out + (p.row_base + (long long)chunk * (32 * TPW)) * (4 * NG);
+}
+
+template <int BPS, int CODEC, int G, int NG>
+BB_HD void wrow_emit_fast(const DecGeom &p, const float *lut, float *chunk_out,
+                          uint32_t q, const uint32_t w[G], uint32_t okmask) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    *reinterpret_cast<F4 *>(chunk_out + 4u * q) =
+        wrow_decode<BPS, CODEC, G>(p, lut, (q / NG) % TPW, w, okmask);
 }
 
 // SCALAR: item = element index within the launch's block of rows.

@@ -10,7 +10,13 @@ namespace bb {
 
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
        MODE_WORDRUN = 4, MODE_WORDROW4 = 7, MODE_ROWWORD4 = 8,
-       MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10 };
+       MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10,
+       MODE_WORDROW4X2 = 11, MODE_WORDROW2X2 = 12 };   // rows of two float4
+
+inline bool is_wordrow(int mode) {
+    return mode == MODE_WORDROW4 || mode == MODE_WORDROW2
+        || mode == MODE_WORDROW4X2 || mode == MODE_WORDROW2X2;
+}
 
 struct DecLaunch { int mode; DecGeom g; };
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
@@ -49,6 +55,8 @@ inline int pick_mode(int nelem, int nthread, bool aligned_rows,
                      bool decode = false) {
     if (decode && nthread == 4 && nelem == 1) return MODE_WORDROW4;
     if (decode && nthread == 2 && nelem == 2) return MODE_WORDROW2;
+    if (decode && nthread == 8 && nelem == 1) return MODE_WORDROW4X2;
+    if (decode && nthread == 4 && nelem == 2) return MODE_WORDROW2X2;
     if (nthread > 1 && nelem == 1 && nthread % 4 == 0) return MODE_ROWGROUP4;
     if (nthread > 1 && nelem == 2 && nthread % 2 == 0) return MODE_ROWGROUP2;
     if (aligned_rows && nthread == 1) return MODE_WORDRUN;
@@ -87,15 +95,13 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup;
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
-    } else if (mode == MODE_WORDRUN || mode == MODE_WORDROW4
-               || mode == MODE_WORDROW2) {
+    } else if (mode == MODE_WORDRUN || is_wordrow(mode)) {
         per_set = nword;                  // items are lanes = words
     } else {
         per_set = (uint64_t)spf * rowlen;
     }
     const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull
-        : (mode == MODE_WORDRUN || mode == MODE_WORDROW4
-           || mode == MODE_WORDROW2) ? 0x03ffffffull
+        : (mode == MODE_WORDRUN || is_wordrow(mode)) ? 0x03ffffffull
         : 0x7fffffffull;
     if (per_set > budget) {
         err = "one frame set is too large for a launch; split it along time";
@@ -118,8 +124,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.spf = spf;
         g.nitems = (uint32_t)(per_set * (uint64_t)(s1 - s0));
         g.nwords_total = (uint32_t)((uint64_t)nword * (uint64_t)(s1 - s0));
-        if (mode == MODE_WORDRUN || mode == MODE_WORDROW4
-            || mode == MODE_WORDROW2)                        // whole warps
+        if (mode == MODE_WORDRUN || is_wordrow(mode))        // whole warps
             g.nitems = (g.nwords_total + 31u) / 32u * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);

@@ -15,6 +15,33 @@ using namespace bb;
 
 static std::string g_err;
 
+// warp-cooperative WORDROW modes: the shared-memory word buffer is an array
+template <int BPS, int CODEC, int G, int NG>
+static void run_wordrow(const DecGeom &g, const float *lut) {
+    constexpr int TPW = (32 / BPS) / (4 / G);
+    constexpr int W = G * NG;
+    for (uint32_t chunk = 0; chunk < g.nitems / 32; ++chunk) {
+        uint32_t w[32][W], ok[32];
+        for (uint32_t lane = 0; lane < 32; ++lane)
+            ok[lane] = wrow_load<W>(g, chunk, lane, w[lane]);
+        const bool interior = wrow_interior<BPS, G>(g, chunk);
+        for (uint32_t lane = 0; lane < 32; ++lane)
+            for (int j = 0; j < TPW * NG; ++j) {
+                const uint32_t q = lane + 32u * j;
+                const uint32_t src = wrow_src_lane<BPS, G, NG>(lane, j);
+                const uint32_t grp = q % NG;
+                const uint32_t okg = (ok[src] >> (grp * G)) & ((1u << G) - 1u);
+                if (interior)
+                    wrow_emit_fast<BPS, CODEC, G, NG>(
+                        g, lut, wrow_chunk_out<BPS, G, NG>(g, chunk), q,
+                        &w[src][grp * G], okg);
+                else
+                    wrow_emit<BPS, CODEC, G, NG>(g, lut, chunk, lane, j,
+                                                 &w[src][grp * G], okg);
+            }
+    }
+}
+
 template <int BPS, int CODEC>
 static void run_decode(const std::vector<DecLaunch> &launches,
                        const float *levels) {
@@ -40,46 +67,11 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             }
             continue;
         }
-        if (l.mode == MODE_WORDROW4) {
-            constexpr int TPW = 32 / BPS;
-            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
-                uint32_t w[32][4], ok[32];
-                for (uint32_t lane = 0; lane < 32; ++lane)
-                    ok[lane] = wrow_load<4>(l.g, chunk, lane, w[lane]);
-                const bool interior = wrow_interior<BPS, 4>(l.g, chunk);
-                for (uint32_t lane = 0; lane < 32; ++lane)
-                    for (int j = 0; j < TPW; ++j) {
-                        uint32_t src = wrow_src_lane<BPS, 4>(lane, j);
-                        if (interior)
-                            wrow_emit_fast<BPS, CODEC, 4>(
-                                l.g, lut, wrow_chunk_out<BPS, 4>(l.g, chunk),
-                                lane + 32u * j, w[src], ok[src]);
-                        else
-                            wrow_emit<BPS, CODEC, 4>(l.g, lut, chunk, lane, j,
-                                                     w[src], ok[src]);
-                    }
-            }
-            continue;
-        }
-        if (l.mode == MODE_WORDROW2) {
-            constexpr int TPW = 16 / BPS;
-            for (uint32_t chunk = 0; chunk < l.g.nitems / 32; ++chunk) {
-                uint32_t w[32][2], ok[32];
-                for (uint32_t lane = 0; lane < 32; ++lane)
-                    ok[lane] = wrow_load<2>(l.g, chunk, lane, w[lane]);
-                const bool interior = wrow_interior<BPS, 2>(l.g, chunk);
-                for (uint32_t lane = 0; lane < 32; ++lane)
-                    for (int j = 0; j < TPW; ++j) {
-                        uint32_t src = wrow_src_lane<BPS, 2>(lane, j);
-                        if (interior)
-                            wrow_emit_fast<BPS, CODEC, 2>(
-                                l.g, lut, wrow_chunk_out<BPS, 2>(l.g, chunk),
-                                lane + 32u * j, w[src], ok[src]);
-                        else
-                            wrow_emit<BPS, CODEC, 2>(l.g, lut, chunk, lane, j,
-                                                     w[src], ok[src]);
-                    }
-            }
+        if (is_wordrow(l.mode)) {
+            if (l.mode == MODE_WORDROW4) run_wordrow<BPS, CODEC, 4, 1>(l.g, lut);
+            else if (l.mode == MODE_WORDROW2) run_wordrow<BPS, CODEC, 2, 1>(l.g, lut);
+            else if (l.mode == MODE_WORDROW4X2) run_wordrow<BPS, CODEC, 4, 2>(l.g, lut);
+            else run_wordrow<BPS, CODEC, 2, 2>(l.g, lut);
             continue;
         }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {

@@ -45,11 +45,13 @@ elif case == 'guppitf':
                                       te, t0, out)
     for _ in range(reps):
         kernels.encode_int8_timefirst(out, back, off, nfr, nt, nchan, npol, 2)
-elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84'):
+elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84',
+              'vdif18', 'gsb'):
     bps, nthread, nelem, payload, hdr = {
         'mark5b': (2, 1, 16, 10000, 16), 'c2': (2, 16, 1, 8000, 32),
         'vdif48': (2, 4, 8, 8000, 32), 'vdif44': (4, 4, 1, 8000, 32),
-        'vdif22c': (2, 2, 2, 8000, 32), 'vdif84': (8, 4, 1, 8000, 32)}[case]
+        'vdif22c': (2, 2, 2, 8000, 32), 'vdif84': (8, 4, 1, 8000, 32),
+        'vdif18': (1, 8, 1, 8000, 32), 'gsb': (8, 2, 1024, 1 << 22, 0)}[case]
     frame = payload + hdr
     nset = int(gib * 2**30) // frame // nthread
     nunit = nset * nthread
@@ -57,15 +59,16 @@ elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84'):
                         device=DEV)
     uo = torch.arange(nunit, dtype=torch.int64, device=DEV) * frame + hdr
     lv = levels.mark5b(2) if case == 'mark5b' else levels.offset_binary(bps)
+    codec = kernels.CODEC_SINT if case == 'gsb' else kernels.CODEC_LEVELS
     out = None
     for _ in range(reps):
         out = kernels.decode_bitfield(raw, uo, nset, nthread, payload, bps,
-                                      nelem, False, kernels.CODEC_LEVELS, lv,
-                                      out=out)
+                                      nelem, False, codec, lv, out=out)
     back = torch.zeros_like(raw)
     for _ in range(reps):
         kernels.encode_bitfield(out, back, uo, nset, nthread, payload, bps,
                                 nelem, kernels.QUANT_MARK5B if case == 'mark5b'
+                                else kernels.QUANT_SINT if case == 'gsb'
                                 else kernels.QUANT_OFFSET_BINARY)
 elif case == 'mark4enc':
     nframe = int(gib * 2**30) // 160000
