@@ -124,8 +124,28 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
             for (int b = 0; b < WB; ++b) {
                 const uint32_t item = item0 + (u0 + b) * kBlock;
                 if (item >= p.nitems) break;
-                const bool interior = wrow_interior<BPS, G>(p, item >> 5);
-                float *chunk_out = wrow_chunk_out<BPS, G, NG>(p, item >> 5);
+                // two separate loops: the interior one stays free of the
+                // edge path's bounds arithmetic
+                if (wrow_interior<BPS, G>(p, item >> 5)) {   // warp uniform
+                    float *chunk_out = wrow_chunk_out<BPS, G, NG>(p,
+                                                                  item >> 5);
+#pragma unroll
+                    for (int j = 0; j < NST; ++j) {
+                        const uint32_t q = lane + 32u * j;
+                        const uint32_t src = wrow_src_lane<BPS, G, NG>(lane,
+                                                                       j);
+                        const uint32_t grp = q % NG;
+                        uint32_t ws[G];
+#pragma unroll
+                        for (int g = 0; g < G; ++g)
+                            ws[g] = wbuf[warp][b][src][grp * G + g];
+                        wrow_emit_fast<BPS, CODEC, G, NG>(
+                            p, lut, chunk_out, q, ws,
+                            (okbuf[warp][b][src] >> (grp * G))
+                            & ((1u << G) - 1u));
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int j = 0; j < NST; ++j) {
                     const uint32_t q = lane + 32u * j;
@@ -135,14 +155,10 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 #pragma unroll
                     for (int g = 0; g < G; ++g)
                         ws[g] = wbuf[warp][b][src][grp * G + g];
-                    const uint32_t ok = (okbuf[warp][b][src] >> (grp * G))
-                        & ((1u << G) - 1u);
-                    if (interior)                 // warp uniform
-                        wrow_emit_fast<BPS, CODEC, G, NG>(p, lut, chunk_out,
-                                                          q, ws, ok);
-                    else
-                        wrow_emit<BPS, CODEC, G, NG>(p, lut, item >> 5, lane,
-                                                     j, ws, ok);
+                    wrow_emit<BPS, CODEC, G, NG>(
+                        p, lut, item >> 5, lane, j, ws,
+                        (okbuf[warp][b][src] >> (grp * G))
+                        & ((1u << G) - 1u));
                 }
             }
         }
