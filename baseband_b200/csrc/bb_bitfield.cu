@@ -24,7 +24,11 @@ struct Unroll {
         : MODE == MODE_WORDROW2 ? 16 / BPS
         : MODE == MODE_WORDROW4X2 ? 64 / BPS
         : MODE == MODE_WORDROW2X2 ? 32 / BPS : 1;
-    static constexpr int value = kF4PerItem >= 16 ? 1 : 16 / kF4PerItem;
+#ifndef BB_F4_PER_THREAD
+#define BB_F4_PER_THREAD 16
+#endif
+    static constexpr int value = kF4PerItem >= BB_F4_PER_THREAD
+        ? 1 : BB_F4_PER_THREAD / kF4PerItem;
 };
 
 // Encode: ROWGROUP as decode; ROWWORD sized so a warp reads ~8 KiB of rows
