@@ -24,11 +24,20 @@ struct Unroll {
         : MODE == MODE_WORDROW2 ? 16 / BPS
         : MODE == MODE_WORDROW4X2 ? 64 / BPS
         : MODE == MODE_WORDROW2X2 ? 32 / BPS : 1;
-#ifndef BB_F4_PER_THREAD
-#define BB_F4_PER_THREAD 16
+    // float4 stores per thread.  Measured (profiles/README.md, per-thread
+    // work sweep): the warp-cooperative modes are 2-3 % faster with 8 than
+    // with 16 (WORDRUN 6.44 -> 6.63 TB/s, above the copy rate) and slower
+    // again with 4; RUN and the two-complex-thread WORDROW2 at 4/8 bit want
+    // 16.  -DBB_F4_PER_THREAD=n overrides for experiments.
+#ifdef BB_F4_PER_THREAD
+    static constexpr int kTarget = BB_F4_PER_THREAD;
+#else
+    static constexpr int kTarget =
+        (MODE == MODE_WORDRUN || MODE == MODE_WORDROW4
+         || (MODE == MODE_WORDROW2 && BPS <= 2)) ? 8 : 16;
 #endif
-    static constexpr int value = kF4PerItem >= BB_F4_PER_THREAD
-        ? 1 : BB_F4_PER_THREAD / kF4PerItem;
+    static constexpr int value = kF4PerItem >= kTarget
+        ? 1 : kTarget / kF4PerItem;
 };
 
 // Encode: ROWGROUP as decode; ROWWORD sized so a warp reads ~8 KiB of rows
