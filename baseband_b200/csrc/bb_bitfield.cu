@@ -17,8 +17,8 @@ constexpr int kBlock = 256;
 template <int BPS, int MODE>
 struct Unroll {
     static constexpr int kF4PerItem =
-        MODE == MODE_ROWGROUP4 ? 32 / BPS
-        : MODE == MODE_ROWGROUP2 ? 16 / BPS
+        MODE == MODE_ROWGROUP4 ? RowSplit<BPS, 4>::kRows
+        : MODE == MODE_ROWGROUP2 ? RowSplit<BPS, 2>::kRows
         : MODE == MODE_WORDRUN ? 8 / BPS
         : MODE == MODE_WORDROW4 ? 32 / BPS
         : MODE == MODE_WORDROW2 ? 16 / BPS
@@ -34,6 +34,7 @@ struct Unroll {
 #else
     static constexpr int kTarget =
         (MODE == MODE_WORDRUN || MODE == MODE_WORDROW4
+         || MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2
          || (MODE == MODE_WORDROW2 && BPS <= 2)) ? 8 : 16;
 #endif
     static constexpr int value = kF4PerItem >= kTarget
@@ -45,9 +46,10 @@ struct Unroll {
 template <int BPS, int MODE>
 struct EncUnroll {
     static constexpr int kTpw = MODE == MODE_ROWWORD4 ? 32 / BPS : 16 / BPS;
+    static constexpr int kRowF4 = (MODE == MODE_ROWGROUP4 ? 32 : 16) / BPS;
     static constexpr int value =
         (MODE == MODE_ROWGROUP4 || MODE == MODE_ROWGROUP2)
-        ? Unroll<BPS, MODE>::value
+        ? (kRowF4 >= 16 ? 1 : 16 / kRowF4)
         : (MODE == MODE_ROWWORD4 || MODE == MODE_ROWWORD2)
         ? (kTpw >= 16 ? 1 : 16 / kTpw) : 4;
 };
@@ -351,13 +353,13 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
         switch (l.mode) {
         case MODE_ROWGROUP4:
             k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP4>
-                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP4>::value), kBlock, 0,
-                   stream>>>(l.g, consts);
+                <<<tile_grid(n, EncUnroll<BPS, MODE_ROWGROUP4>::value), kBlock,
+                   0, stream>>>(l.g, consts);
             break;
         case MODE_ROWGROUP2:
             k_encode_bitfield<T, BPS, QUANT, MODE_ROWGROUP2>
-                <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP2>::value), kBlock, 0,
-                   stream>>>(l.g, consts);
+                <<<tile_grid(n, EncUnroll<BPS, MODE_ROWGROUP2>::value), kBlock,
+                   0, stream>>>(l.g, consts);
             break;
         case MODE_ROWWORD4:
             k_encode_rowword<T, BPS, QUANT, 4>

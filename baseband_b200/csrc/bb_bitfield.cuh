@@ -149,20 +149,34 @@ template <int G>
 struct RowItem {
     uint32_t w[G];
     uint32_t okmask;                // bit j: slot j valid
-    uint32_t g;
+    uint32_t g, h;                  // group; which part of the word's rows
     long long row0;
     bool live;
+};
+
+// An item is at most 8 rows: a word holding more (1 and 2 bit) is split over
+// SPLIT neighbouring threads, which read the same word (one broadcast load).
+// Fewer stores per thread measured faster (see Unroll in bb_bitfield.cu).
+template <int BPS, int G>
+struct RowSplit {
+    static constexpr int kTpw = (32 / BPS) / (4 / G);
+    static constexpr int kRows = kTpw < 8 ? kTpw : 8;     // rows per item
+    static constexpr int kSplit = kTpw / kRows;
 };
 
 template <int BPS, int G>
 BB_HD void rowgroup_fetch(const DecGeom &p, uint32_t item, RowItem<G> &it) {
     constexpr int E = 4 / G;
     constexpr int TPW = (32 / BPS) / E;
-    uint32_t lw, set, k;
-    p.div_ngroup.divmod(item, lw, it.g);
+    constexpr int RPI = RowSplit<BPS, G>::kRows;
+    constexpr int SPLIT = RowSplit<BPS, G>::kSplit;
+    uint32_t lwh, lw, set, k;
+    p.div_ngroup.divmod(item, lwh, it.g);
+    lw = lwh / SPLIT;
+    it.h = lwh % SPLIT;
     p.div_nword.divmod(lw, set, k);
-    it.row0 = p.row_base + (long long)lw * TPW;
-    it.live = !(it.row0 + TPW <= 0 || it.row0 >= p.nsample);
+    it.row0 = p.row_base + (long long)lw * TPW + it.h * RPI;
+    it.live = !(it.row0 + RPI <= 0 || it.row0 >= p.nsample);
     it.okmask = 0u;
     if (!it.live) return;
     const long long *uo = p.unit_offset + (size_t)set * p.nthread + it.g * G;
@@ -178,18 +192,20 @@ template <int BPS, int CODEC, int G>
 BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
                          const RowItem<G> &it) {
     constexpr int E = 4 / G;
-    constexpr int TPW = (32 / BPS) / E;
+    constexpr int TPW = RowSplit<BPS, G>::kRows;   // rows of this item
     if (!it.live) return;
+    const uint32_t c0 = it.h * TPW;                // first code (pair) used
     const uint32_t *w = it.w;
     const long long row0 = it.row0;
     const size_t rowlen = (size_t)p.nthread * E;
     float *dst = p.out + row0 * (long long)rowlen + it.g * 4;
     if (it.okmask == (1u << G) - 1u && row0 >= 0
         && row0 + TPW <= p.nsample) {
-        // Fast path: whole word inside the requested rows, every slot valid.
+        // Fast path: all rows inside the requested range, every slot valid.
         if (E == 1) {
 #pragma unroll
-            for (int m = 0; m < TPW / 2; ++m) {
+            for (int mm = 0; mm < TPW / 2; ++mm) {
+                const uint32_t m = c0 / 2 + mm;
                 F2 a = decode_pair<BPS, CODEC>(w[0], m, lut);
                 F2 b = decode_pair<BPS, CODEC>(w[1 % G], m, lut);
                 F2 c = decode_pair<BPS, CODEC>(w[2 % G], m, lut);
@@ -201,7 +217,8 @@ BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < TPW; ++i) {
+            for (int ii = 0; ii < TPW; ++ii) {
+                const uint32_t i = c0 + ii;
                 F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
                 F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
                 *reinterpret_cast<F4 *>(dst) = F4{a.x, a.y, b.x, b.y};
@@ -215,8 +232,9 @@ BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
     const bool ok0 = it.okmask & 1u, ok1 = (it.okmask >> (1 % G)) & 1u,
         ok2 = (it.okmask >> (2 % G)) & 1u, ok3 = (it.okmask >> (3 % G)) & 1u;
 #pragma unroll 1
-    for (int i = 0; i < TPW; ++i, dst += rowlen) {
-        if (row0 + i < 0 || row0 + i >= p.nsample) continue;
+    for (int ii = 0; ii < TPW; ++ii, dst += rowlen) {
+        if (row0 + ii < 0 || row0 + ii >= p.nsample) continue;
+        const uint32_t i = c0 + ii;
         F4 v;
         if (E == 1) {
             v.x = ok0 ? decode_one<BPS, CODEC>(w[0], i, lut) : p.fill;

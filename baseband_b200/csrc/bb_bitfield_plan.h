@@ -92,7 +92,9 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     uint32_t ngroup = 1;
     if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
         ngroup = nthread / (mode == MODE_ROWGROUP4 ? 4 : 2);
-        per_set = (uint64_t)nword * ngroup;
+        // words with more than 8 rows are split over several items
+        const int tpw = cpw / (mode == MODE_ROWGROUP4 ? 1 : 2);
+        per_set = (uint64_t)nword * ngroup * (tpw > 8 ? tpw / 8 : 1);
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
     } else if (mode == MODE_WORDRUN || is_wordrow(mode)) {
