@@ -9,8 +9,12 @@ namespace bb {
 
 constexpr int kM4Block = 256;
 // one-shot grid, ~64 KiB of output per CTA (see bb_bitfield.cu)
+// Items per thread, measured per kernel (profiles/README.md): the FAST decode
+// wants 4 (16 float4 per thread; 6.43 vs 6.14 / 5.65 TB/s with 2 / 1), the
+// WARP decode 2 chunks (+1.5 % over 4), the FAST encode 1 (6.86 vs 6.66 /
+// 6.41 with 2 / 4), the HALF encode 4.
 constexpr int kM4UnrollFast = 4, kM4UnrollVec = 16, kM4UnrollScalar = 16,
-    kM4UnrollWarp = 4;
+    kM4UnrollWarp = 2, kM4UnrollEncFast = 1, kM4UnrollHalf = 4;
 
 static inline unsigned m4_grid(uint32_t nitems, int unroll) {
     uint64_t per = (uint64_t)kM4Block * unroll;
@@ -86,7 +90,7 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kM4Block)
 k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
-    constexpr int U = kM4UnrollFast;
+    constexpr int U = kM4UnrollEncFast;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
 #pragma unroll 1
     for (int u = 0; u < U; ++u) {
@@ -102,7 +106,7 @@ k_mark4_encode(const M4Geom p, const QuantConsts<T> c) {
 template <typename T, int W>
 __global__ void __launch_bounds__(kM4Block)
 k_mark4_encode_half(const M4Geom p, const QuantConsts<T> c) {
-    constexpr int U = kM4UnrollFast;
+    constexpr int U = kM4UnrollHalf;
     const uint32_t item0 = blockIdx.x * (kM4Block * U) + threadIdx.x;
     // kM4Block is even: every item of this thread has the parity of item0
     const M4HalfMasks mk = m4_half_masks<W>(p, p.pos, item0 & 1u);
@@ -138,7 +142,8 @@ template <typename T>
 static int run_encode(const std::vector<M4Launch> &launches, cudaStream_t s) {
     static const QuantConsts<T> consts = make_quant_consts<T>();
     for (const M4Launch &l : launches) {
-        unsigned grid = m4_grid(l.g.nitems, kM4UnrollFast);
+        unsigned grid = m4_grid(l.g.nitems, l.mode == M4_HALF
+                                ? kM4UnrollHalf : kM4UnrollEncFast);
         if (l.mode == M4_FAST)
             k_mark4_encode<T, M4_FAST><<<grid, kM4Block, 0, s>>>(l.g, consts);
         else if (l.mode == M4_HALF && l.g.wordbytes == 8)
