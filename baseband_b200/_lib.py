@@ -76,6 +76,8 @@ SIGNATURES = {
     'bb_mark4_scan': (c_int, [
         _pv, _pi64, c_int64, c_int64, c_int32, c_int32, _pv, _pi64,
         c_void_p]),
+    'bb_probe_fill': (c_int, [_pv, c_int64, c_int32, c_void_p]),
+    'bb_probe_copy': (c_int, [_pv, _pv, c_int64, c_void_p]),
 }
 
 # every symbol include/baseband_b200.h declares

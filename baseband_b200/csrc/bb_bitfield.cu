@@ -61,13 +61,13 @@ inline unsigned tile_grid(uint32_t nitems, int unroll) {
 
 // The decode table lives in shared memory (see DecodeLut): built per CTA from
 // the per-code levels in the kernel parameters (at most 256 floats).
-template <int BPS, int CODEC, int MODE>
+template <int BPS, int CODEC, int MODE, bool SEL = false>
 __global__ void __launch_bounds__(kBlock)
 k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
     using Lut = DecodeLut<BPS>;
     constexpr int U = Unroll<BPS, MODE>::value;
     __shared__ __align__(128) float lut[CODEC == CODEC_LEVELS ? Lut::kFloats : 2];
-    if (CODEC == CODEC_LEVELS) {
+    if (CODEC == CODEC_LEVELS && !SEL) {
         for (int i = threadIdx.x; i < Lut::kFloats; i += kBlock)
             lut[i] = Lut::value(lv.v, i);
         __syncthreads();
@@ -199,7 +199,7 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
             }
 #pragma unroll
             for (int b = 0; b < RB; ++b)
-                rowgroup_emit<BPS, CODEC, G>(p, lut, it[b]);
+                rowgroup_emit<BPS, CODEC, G, SEL>(p, lut, it[b], lv);
         }
         return;
     }
@@ -223,6 +223,80 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
         const uint32_t item = item0 + u * kBlock;
         if (item >= p.nitems) break;
         dec_scalar<BPS, CODEC>(p, lut, item);
+    }
+}
+
+// TILE (rows of four float4, see bb_bitfield.cuh): warp-cooperative, words
+// staged in shared memory, every store instruction 512 contiguous bytes.
+template <int BPS, int CODEC, int G, int P, bool SEL, int U>
+__global__ void __launch_bounds__(kBlock)
+k_decode_tile(const DecGeom p, const LevelTable<BPS> lv) {
+    using Lut = DecodeLut<BPS>;
+    using T = Tile<BPS, G, P>;
+    constexpr int UB = U < 2 ? U : 2;             // chunks loaded up front
+    __shared__ __align__(128) float lut[(CODEC == CODEC_LEVELS && !SEL)
+                                        ? Lut::kFloats : 2];
+    __shared__ __align__(16) uint32_t wbuf[kBlock / 32][UB][T::kWords];
+    __shared__ uint32_t okbuf[kBlock / 32][UB][32];
+    if (CODEC == CODEC_LEVELS && !SEL) {
+        for (int i = threadIdx.x; i < Lut::kFloats; i += kBlock)
+            lut[i] = Lut::value(lv.v, i);
+        __syncthreads();
+    }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+#pragma unroll 1
+    for (int u0 = 0; u0 < U; u0 += UB) {
+        __syncwarp();                             // previous batch consumed
+        bool full[UB];
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+            const uint32_t item = item0 + (u0 + b) * kBlock;
+            uint32_t w[T::kNl];
+            uint32_t ok = 0u;
+#pragma unroll
+            for (int i = 0; i < T::kNl; ++i) w[i] = 0u;
+            if (item < p.nitems) ok = tile_load<BPS, G, P>(p, item >> 5, lane, w);
+#pragma unroll
+            for (int i = 0; i < T::kNl; ++i)
+                wbuf[warp][b][T::kNl * lane + i] = w[i];
+            full[b] = __all_sync(0xffffffffu, ok == (1u << T::kNl) - 1u);
+            if (!full[b]) okbuf[warp][b][lane] = ok;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int b = 0; b < UB; ++b) {
+            const uint32_t item = item0 + (u0 + b) * kBlock;
+            if (item >= p.nitems) break;          // warp uniform
+            const uint32_t chunk = item >> 5;
+            if (full[b] && tile_interior<BPS, G, P>(p, chunk)) {
+                float *chunk_out = tile_chunk_out<BPS, G, P>(p, chunk);
+#pragma unroll
+                for (int j = 0; j < T::kStores; ++j) {
+                    const uint32_t q = lane + 32u * j;
+                    const uint32_t at = ((q >> 2) / T::kTpw) * T::kSlots
+                        + (q & 3u) * G;
+                    uint32_t ws[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) ws[g] = wbuf[warp][b][at + g];
+                    *reinterpret_cast<F4 *>(chunk_out + 4u * q) =
+                        tile_decode<BPS, CODEC, G, P, SEL>(q, ws, lut, lv);
+                }
+                continue;
+            }
+#pragma unroll 1
+            for (int j = 0; j < T::kStores; ++j) {
+                const uint32_t q = lane + 32u * j;
+                const uint32_t at = ((q >> 2) / T::kTpw) * T::kSlots
+                    + (q & 3u) * G;
+                uint32_t ws[G];
+#pragma unroll
+                for (int g = 0; g < G; ++g) ws[g] = wbuf[warp][b][at + g];
+                const uint32_t okm = full[b] ? (1u << G) - 1u
+                    : tile_group_ok<BPS, G, P>(okbuf[warp][b], q);
+                tile_emit<BPS, CODEC, G, P, SEL>(p, lut, lv, chunk, q, ws, okm);
+            }
+        }
     }
 }
 
@@ -285,6 +359,52 @@ k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
     }
 }
 
+// The 2-bit level-table variants under evaluation (register select, TILE).
+// Returns false if the launch is not one of them.
+template <int BPS, int CODEC, int G, int P, bool SEL>
+static void launch_tile(const DecLaunch &l, const LevelTable<BPS> &lv,
+                        cudaStream_t stream) {
+    if (l.tile_u >= 2)
+        k_decode_tile<BPS, CODEC, G, P, SEL, 2>
+            <<<tile_grid(l.g.nitems, 2), kBlock, 0, stream>>>(l.g, lv);
+    else
+        k_decode_tile<BPS, CODEC, G, P, SEL, 1>
+            <<<tile_grid(l.g.nitems, 1), kBlock, 0, stream>>>(l.g, lv);
+}
+
+template <int BPS, int CODEC>
+static bool launch_c2(const DecLaunch &l, const LevelTable<BPS> &lv,
+                      cudaStream_t stream) {
+    const uint32_t n = l.g.nitems;
+    if (l.mode == MODE_ROWGROUP4 && l.sel) {
+        k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP4, true>
+            <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP4>::value), kBlock, 0,
+               stream>>>(l.g, lv);
+        return true;
+    }
+    if (l.mode == MODE_ROWGROUP2 && l.sel) {
+        k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP2, true>
+            <<<tile_grid(n, Unroll<BPS, MODE_ROWGROUP2>::value), kBlock, 0,
+               stream>>>(l.g, lv);
+        return true;
+    }
+    if (l.mode == MODE_TILE4) {
+        if (l.tile_p == 8 && l.sel) launch_tile<BPS, CODEC, 4, 8, true>(l, lv, stream);
+        else if (l.tile_p == 8) launch_tile<BPS, CODEC, 4, 8, false>(l, lv, stream);
+        else if (l.sel) launch_tile<BPS, CODEC, 4, 4, true>(l, lv, stream);
+        else launch_tile<BPS, CODEC, 4, 4, false>(l, lv, stream);
+        return true;
+    }
+    if (l.mode == MODE_TILE2) {
+        if (l.tile_p == 8 && l.sel) launch_tile<BPS, CODEC, 2, 8, true>(l, lv, stream);
+        else if (l.tile_p == 8) launch_tile<BPS, CODEC, 2, 8, false>(l, lv, stream);
+        else if (l.sel) launch_tile<BPS, CODEC, 2, 4, true>(l, lv, stream);
+        else launch_tile<BPS, CODEC, 2, 4, false>(l, lv, stream);
+        return true;
+    }
+    return false;
+}
+
 template <int BPS, int CODEC>
 static int launch_decode(const std::vector<DecLaunch> &launches,
                          const float *levels_host, cudaStream_t stream) {
@@ -293,6 +413,12 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         lv.v[i] = (CODEC == CODEC_LEVELS && levels_host) ? levels_host[i] : 0.f;
     for (const DecLaunch &l : launches) {
         const uint32_t n = l.g.nitems;
+        if constexpr (BPS == 2 && CODEC == CODEC_LEVELS) {
+            if (launch_c2<BPS, CODEC>(l, lv, stream)) {
+                BB_CHECK_LAUNCH("bb_decode_bitfield launch");
+                continue;
+            }
+        }
         switch (l.mode) {
         case MODE_ROWGROUP4:
             k_decode_bitfield<BPS, CODEC, MODE_ROWGROUP4>

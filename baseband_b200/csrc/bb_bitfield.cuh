@@ -137,6 +137,36 @@ BB_HD float decode_one(uint32_t w, uint32_t c, const float *lut) {
     return (c & 1u) ? r.y : r.x;
 }
 
+// Register-select decode (SEL variants): the 2^BPS levels come from the
+// kernel parameters (constant bank) and a value is picked with bit tests and
+// selects -- no shared-memory access at all.  Only 1- and 2-bit level tables;
+// `sh` is the bit position of the code in the word.
+template <int BPS>
+BB_HD float sel_level(uint32_t w, uint32_t sh, const LevelTable<BPS> &lv) {
+    if (BPS == 1) return ((w >> sh) & 1u) ? lv.v[1] : lv.v[0];
+    const bool b0 = (w >> sh) & 1u, b1 = (w >> (sh + 1u)) & 1u;
+    const float lo = b0 ? lv.v[1] : lv.v[0];
+    const float hi = b0 ? lv.v[3 % (1 << BPS)] : lv.v[2 % (1 << BPS)];
+    return b1 ? hi : lo;
+}
+
+template <int BPS, int CODEC, bool SEL>
+BB_HD F2 decode_pair_v(uint32_t w, uint32_t j, const float *lut,
+                       const LevelTable<BPS> &lv) {
+    if (SEL && CODEC == CODEC_LEVELS && BPS <= 2)
+        return F2{sel_level<BPS>(w, 2u * j * BPS, lv),
+                  sel_level<BPS>(w, (2u * j + 1u) * BPS, lv)};
+    return decode_pair<BPS, CODEC>(w, j, lut);
+}
+
+template <int BPS, int CODEC, bool SEL>
+BB_HD float decode_one_v(uint32_t w, uint32_t c, const float *lut,
+                         const LevelTable<BPS> &lv) {
+    if (SEL && CODEC == CODEC_LEVELS && BPS <= 2)
+        return sel_level<BPS>(w, c * BPS, lv);
+    return decode_one<BPS, CODEC>(w, c, lut);
+}
+
 BB_HD uint32_t load_u32(const uint8_t *p) {
     return *reinterpret_cast<const uint32_t *>(p);
 }
@@ -188,9 +218,10 @@ BB_HD void rowgroup_fetch(const DecGeom &p, uint32_t item, RowItem<G> &it) {
     }
 }
 
-template <int BPS, int CODEC, int G>
+template <int BPS, int CODEC, int G, bool SEL = false>
 BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
-                         const RowItem<G> &it) {
+                         const RowItem<G> &it,
+                         const LevelTable<BPS> &lv = LevelTable<BPS>()) {
     constexpr int E = 4 / G;
     constexpr int TPW = RowSplit<BPS, G>::kRows;   // rows of this item
     if (!it.live) return;
@@ -206,10 +237,10 @@ BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
 #pragma unroll
             for (int mm = 0; mm < TPW / 2; ++mm) {
                 const uint32_t m = c0 / 2 + mm;
-                F2 a = decode_pair<BPS, CODEC>(w[0], m, lut);
-                F2 b = decode_pair<BPS, CODEC>(w[1 % G], m, lut);
-                F2 c = decode_pair<BPS, CODEC>(w[2 % G], m, lut);
-                F2 d = decode_pair<BPS, CODEC>(w[3 % G], m, lut);
+                F2 a = decode_pair_v<BPS, CODEC, SEL>(w[0], m, lut, lv);
+                F2 b = decode_pair_v<BPS, CODEC, SEL>(w[1 % G], m, lut, lv);
+                F2 c = decode_pair_v<BPS, CODEC, SEL>(w[2 % G], m, lut, lv);
+                F2 d = decode_pair_v<BPS, CODEC, SEL>(w[3 % G], m, lut, lv);
                 *reinterpret_cast<F4 *>(dst) = F4{a.x, b.x, c.x, d.x};
                 dst += rowlen;
                 *reinterpret_cast<F4 *>(dst) = F4{a.y, b.y, c.y, d.y};
@@ -219,8 +250,8 @@ BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
 #pragma unroll
             for (int ii = 0; ii < TPW; ++ii) {
                 const uint32_t i = c0 + ii;
-                F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
-                F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
+                F2 a = decode_pair_v<BPS, CODEC, SEL>(w[0], i, lut, lv);
+                F2 b = decode_pair_v<BPS, CODEC, SEL>(w[1 % G], i, lut, lv);
                 *reinterpret_cast<F4 *>(dst) = F4{a.x, a.y, b.x, b.y};
                 dst += rowlen;
             }
@@ -476,6 +507,127 @@ BB_HD void wrow_emit_fast(const DecGeom &p, const float *lut, float *chunk_out,
     constexpr int TPW = (32 / BPS) / (4 / G);
     *reinterpret_cast<F4 *>(chunk_out + 4u * q) =
         wrow_decode<BPS, CODEC, G>(p, lut, (q / NG) % TPW, w, okmask);
+}
+
+// TILE<G, P>: rows of exactly four float4 (16 single-channel threads with
+// G = 4, or 8 threads of one complex channel with G = 2; NSLOT = 4 G slots):
+// the headline C2 shape.  ROWGROUP's warp stores are there 8 pieces of 64
+// bytes, 512 bytes apart.  Here a warp takes P consecutive word positions of
+// all NSLOT slots (lane L: position L / NGR, NL = NSLOT / NGR neighbouring
+// slots, NGR = 32 / P; every 32-byte sector of the packed input is used
+// whole), parks the words in shared memory at word address NL * L (linear:
+// conflict free) and then stores the P * TPW decoded rows as one contiguous
+// run: store j, lane L writes float4 q = L + 32 j = group q % 4 of row q / 4,
+// reading the G words of its group with one LDS.128 / LDS.64 (lanes of a group
+// broadcast; the 4 groups of a row are 16 consecutive words).  Every store
+// instruction covers 512 contiguous bytes.
+template <int BPS, int G, int P>
+struct Tile {
+    static constexpr int kSlots = 4 * G;
+    static constexpr int kNgr = 32 / P;                 // lane groups
+    static constexpr int kNl = kSlots / kNgr;           // words per lane
+    static constexpr int kTpw = (32 / BPS) / (4 / G);   // rows per word
+    static constexpr int kStores = P * kTpw / 8;        // float4 per lane
+    static constexpr int kWords = P * kSlots;           // words per chunk
+};
+
+// Words of lane `lane` of chunk `chunk`: w[i] = slot (lane % NGR) * NL + i at
+// word position chunk * P + lane / NGR.  Returns the valid bits.
+template <int BPS, int G, int P>
+BB_HD uint32_t tile_load(const DecGeom &p, uint32_t chunk, uint32_t lane,
+                         uint32_t w[Tile<BPS, G, P>::kNl]) {
+    using T = Tile<BPS, G, P>;
+#pragma unroll
+    for (int i = 0; i < T::kNl; ++i) w[i] = 0u;
+    const uint32_t idx = chunk * P + lane / T::kNgr;
+    if (idx >= p.nwords_total) return 0u;
+    uint32_t set, k;
+    p.div_nword.divmod(idx, set, k);
+    const long long *uo = p.unit_offset + (size_t)set * T::kSlots
+        + (lane % T::kNgr) * T::kNl;
+    uint32_t ok = 0u;
+#pragma unroll
+    for (int i = 0; i < T::kNl; ++i) {
+        const long long off = uo[i];
+        if (off >= 0) {
+            w[i] = load_u32(p.src + off + 4ull * k);
+            ok |= 1u << i;
+        }
+    }
+    return ok;
+}
+
+template <int BPS, int G, int P>
+BB_HD bool tile_interior(const DecGeom &p, uint32_t chunk) {
+    using T = Tile<BPS, G, P>;
+    if ((unsigned long long)chunk * P + P > p.nwords_total) return false;
+    const long long row0 = p.row_base + (long long)chunk * (P * T::kTpw);
+    return row0 >= 0 && row0 + P * T::kTpw <= p.nsample;
+}
+
+template <int BPS, int G, int P>
+BB_HD float *tile_chunk_out(const DecGeom &p, uint32_t chunk) {
+    using T = Tile<BPS, G, P>;
+    return p.out + (p.row_base + (long long)chunk * (P * T::kTpw)) * 16;
+}
+
+// float4 q of a chunk from the G words `w` of its group (all slots valid).
+template <int BPS, int CODEC, int G, int P, bool SEL>
+BB_HD F4 tile_decode(uint32_t q, const uint32_t w[G], const float *lut,
+                     const LevelTable<BPS> &lv) {
+    using T = Tile<BPS, G, P>;
+    const uint32_t t = (q >> 2) % T::kTpw;          // row within the word
+    if (G == 4)
+        return F4{decode_one_v<BPS, CODEC, SEL>(w[0], t, lut, lv),
+                  decode_one_v<BPS, CODEC, SEL>(w[1 % G], t, lut, lv),
+                  decode_one_v<BPS, CODEC, SEL>(w[2 % G], t, lut, lv),
+                  decode_one_v<BPS, CODEC, SEL>(w[3 % G], t, lut, lv)};
+    const F2 a = decode_pair_v<BPS, CODEC, SEL>(w[0], t, lut, lv);
+    const F2 b = decode_pair_v<BPS, CODEC, SEL>(w[1 % G], t, lut, lv);
+    return F4{a.x, a.y, b.x, b.y};
+}
+
+// Checked store for edge chunks / chunks with invalid units.  okmask: bit s =
+// slot s of the float4's group valid.
+template <int BPS, int CODEC, int G, int P, bool SEL>
+BB_HD void tile_emit(const DecGeom &p, const float *lut,
+                     const LevelTable<BPS> &lv, uint32_t chunk, uint32_t q,
+                     const uint32_t w[G], uint32_t okmask) {
+    using T = Tile<BPS, G, P>;
+    const uint32_t r = q >> 2;                       // row within the chunk
+    if (chunk * P + r / T::kTpw >= p.nwords_total) return;
+    const long long row = p.row_base + (long long)chunk * (P * T::kTpw) + r;
+    if (row < 0 || row >= p.nsample) return;
+    F4 v = tile_decode<BPS, CODEC, G, P, SEL>(q, w, lut, lv);
+    if (okmask != (1u << G) - 1u) {
+        const float fill_im = p.complex_fill ? 0.f : p.fill;
+        if (G == 4) {
+            if (!(okmask & 1u)) v.x = p.fill;
+            if (!(okmask & 2u)) v.y = p.fill;
+            if (!(okmask & 4u)) v.z = p.fill;
+            if (!(okmask & 8u)) v.w = p.fill;
+        } else {
+            if (!(okmask & 1u)) { v.x = p.fill; v.y = fill_im; }
+            if (!(okmask & 2u)) { v.z = p.fill; v.w = fill_im; }
+        }
+    }
+    *reinterpret_cast<F4 *>(p.out + (row * 4 + (q & 3u)) * 4) = v;
+}
+
+// Valid bits of group g = q & 3 of the row of float4 q, from the per-lane
+// valid bits of the whole chunk (oks[lane], bit i = word i of that lane).
+template <int BPS, int G, int P>
+BB_HD uint32_t tile_group_ok(const uint32_t *oks, uint32_t q) {
+    using T = Tile<BPS, G, P>;
+    const uint32_t pos = (q >> 2) / T::kTpw, g = q & 3u;
+    uint32_t m = 0u;
+#pragma unroll
+    for (int s = 0; s < G; ++s) {
+        const uint32_t slot = g * G + s;
+        const uint32_t lane = pos * T::kNgr + slot / T::kNl;
+        m |= ((oks[lane] >> (slot % T::kNl)) & 1u) << s;
+    }
+    return m;
 }
 
 // SCALAR: item = element index within the launch's block of rows.

@@ -2,6 +2,7 @@
 // work decomposition and splits it into launches whose item counts fit in 32
 // bits.  Pure C++ so the CPU emulation in tests/emu shares it.
 #pragma once
+#include <stdlib.h>
 #include <vector>
 #include <string>
 #include "bb_bitfield.cuh"
@@ -11,14 +12,28 @@ namespace bb {
 enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
        MODE_WORDRUN = 4, MODE_WORDROW4 = 7, MODE_ROWWORD4 = 8,
        MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10,
-       MODE_WORDROW4X2 = 11, MODE_WORDROW2X2 = 12 };   // rows of two float4
+       MODE_WORDROW4X2 = 11, MODE_WORDROW2X2 = 12,     // rows of two float4
+       MODE_TILE4 = 13, MODE_TILE2 = 14 };             // rows of four float4
+
+// Development tunables (BB_TUNE_<NAME> environment variables), read at every
+// call so that a sweep can change them inside one process.
+inline int tune(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
 
 inline bool is_wordrow(int mode) {
     return mode == MODE_WORDROW4 || mode == MODE_WORDROW2
         || mode == MODE_WORDROW4X2 || mode == MODE_WORDROW2X2;
 }
 
-struct DecLaunch { int mode; DecGeom g; };
+// sel: levels by register select instead of the shared-memory pair table;
+// tile_p / tile_u: word positions per chunk and chunks per warp (TILE modes).
+struct DecLaunch { int mode; DecGeom g; int sel = 0, tile_p = 8, tile_u = 1; };
+
+inline bool is_tile(int mode) {
+    return mode == MODE_TILE4 || mode == MODE_TILE2;
+}
 struct EncLaunch { int mode; EncGeom g; };   // MODE_RUN = vectorised words
 
 inline bool plan_geometry(int64_t payload_nbytes, int bps, int nelem,
@@ -83,7 +98,21 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     const int64_t rowlen = (int64_t)nthread * nelem;
     const bool aligned_rows = (sample_start * rowlen) % 4 == 0
         && (nsample * rowlen) % 4 == 0;
-    const int mode = pick_mode(nelem, nthread, aligned_rows, true);
+    int mode = pick_mode(nelem, nthread, aligned_rows, true);
+    // rows of four float4 (the C2 shape): BB_TUNE_C2 = 0 ROWGROUP + table,
+    // 1 ROWGROUP + select, 2/3 TILE (8 positions) table/select, 4/5 TILE (4)
+    const int c2 = tune("BB_TUNE_C2", 0);
+    int sel = 0, tile_p = 8;
+    const int tile_u = tune("BB_TUNE_TILE_U", 1) >= 2 ? 2 : 1;
+    if (bps == 2 && (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2)) {
+        sel = c2 & 1;
+        const bool row16 = (mode == MODE_ROWGROUP4 && nthread == 16)
+            || (mode == MODE_ROWGROUP2 && nthread == 8);
+        if (c2 >= 2 && row16) {
+            mode = mode == MODE_ROWGROUP4 ? MODE_TILE4 : MODE_TILE2;
+            tile_p = c2 >= 4 ? 4 : 8;
+        }
+    }
     const int cpw = 32 / bps;
     int64_t first = sample_start / spf;
     int64_t last = (sample_start + nsample + spf - 1) / spf;
@@ -97,14 +126,14 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup * (tpw > 8 ? tpw / 8 : 1);
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
-    } else if (mode == MODE_WORDRUN || is_wordrow(mode)) {
+    } else if (mode == MODE_WORDRUN || is_wordrow(mode) || is_tile(mode)) {
         per_set = nword;                  // items are lanes = words
     } else {
         per_set = (uint64_t)spf * rowlen;
     }
     const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull
-        : (mode == MODE_WORDRUN || is_wordrow(mode)) ? 0x03ffffffull
-        : 0x7fffffffull;
+        : (mode == MODE_WORDRUN || is_wordrow(mode) || is_tile(mode))
+        ? 0x03ffffffull : 0x7fffffffull;
     if (per_set > budget) {
         err = "one frame set is too large for a launch; split it along time";
         return false;
@@ -128,6 +157,8 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.nwords_total = (uint32_t)((uint64_t)nword * (uint64_t)(s1 - s0));
         if (mode == MODE_WORDRUN || is_wordrow(mode))        // whole warps
             g.nitems = (g.nwords_total + 31u) / 32u * 32u;
+        if (is_tile(mode))                // a warp per tile_p word positions
+            g.nitems = (g.nwords_total + tile_p - 1u) / tile_p * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);
         g.complex_fill = complex_data ? 1 : 0;
@@ -138,7 +169,13 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.div_spf = make_fastdiv(spf);
         g.div_nelem = make_fastdiv(nelem);
         g.div_unitlen = make_fastdiv((uint32_t)((uint64_t)spf * nelem));
-        launches.push_back({mode, g});
+        DecLaunch l;
+        l.mode = mode;
+        l.g = g;
+        l.sel = sel;
+        l.tile_p = tile_p;
+        l.tile_u = tile_u;
+        launches.push_back(l);
     }
     return true;
 }

@@ -49,6 +49,37 @@ __global__ void __launch_bounds__(kM4Block) k_mark4_decode(const M4Geom p) {
             const uint32_t item = item0 + u * kM4Block;
             ok[u] = item < p.nitems && m4w_load(p, item >> 5, lane, w[u]);
         }
+        if (p.std4) {                              // launch uniform
+            const uint32_t row = m4s_row(p, lane);
+            uint32_t ssrc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ssrc[j] = m4s_src_lane(p, lane + 32u * j);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t item = item0 + u * kM4Block;
+                if (item >= p.nitems) break;       // warp uniform
+                const unsigned okmask = __ballot_sync(0xffffffffu, ok[u]);
+                if (m4w_interior(p, item >> 5)) {
+                    float *chunk_out = m4w_chunk_out(p, item >> 5);
+                    const uint32_t r = m4_reorder32(w[u]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t rs = __shfl_sync(0xffffffffu, r, ssrc[j]);
+                        m4s_emit_fast(p, lut, chunk_out, lane + 32u * j, row,
+                                      rs, (okmask >> ssrc[j]) & 1u);
+                    }
+                    continue;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t q = lane + 32u * j;
+                    const uint32_t src = m4w_src_lane(p, lc, q);
+                    const uint32_t ws = __shfl_sync(0xffffffffu, w[u], src);
+                    m4w_emit(p, lc, lv, item >> 5, q, ws, (okmask >> src) & 1u);
+                }
+            }
+            return;
+        }
         uint32_t srcl[4];                          // loop-invariant per lane
 #pragma unroll
         for (int j = 0; j < 4; ++j) srcl[j] = m4w_src_lane(p, lc, lane + 32u * j);

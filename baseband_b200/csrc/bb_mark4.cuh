@@ -42,6 +42,7 @@ struct M4Geom {
     int32_t log2_wordbytes;
     uint8_t psel[8];                 // 64-track: float4 positions of half 0, 1
     FastDiv div_frame32;
+    uint32_t std4;                   // WARP mode: standard fan-out 4 fast decode
 };
 
 BB_HD uint32_t m4_reorder32(uint32_t x) {
@@ -252,6 +253,39 @@ BB_HD void m4w_emit_fast(const M4Geom &p, const M4Lane &c, const float *lut,
         v = F4{p.fill, p.fill, p.fill, p.fill};
     }
     *reinterpret_cast<F4 *>(chunk_out + 4u * q) = v;
+}
+
+// WARP decode specialised for the standard fan-out 4 layouts (32 and 64
+// tracks; C3): after `reorder32` (done once per loaded value, before the
+// shuffle) byte perm[c] of a 32-bit value holds channel c as four 2-bit codes,
+// so row i of its four channels is two pair-table look-ups -- no per-bit
+// extraction.  float4 q of a chunk is row i of value src: 64 tracks (8
+// channels, two values per track word): i = (q % 8) / 2, half q % 2; 32
+// tracks: i = q % 4.
+BB_HD uint32_t m4s_row(const M4Geom &p, uint32_t q) {
+    const uint32_t pp = q & (p.wordbytes - 1u);
+    return p.wordbytes == 8 ? pp >> 1 : pp;
+}
+
+BB_HD uint32_t m4s_src_lane(const M4Geom &p, uint32_t q) {
+    const uint32_t n = q >> p.log2_wordbytes;          // track word in chunk
+    return ((n << p.log2_wordbytes) >> 2)
+        + (p.wordbytes == 8 ? (q & 1u) : 0u);
+}
+
+BB_HD F4 m4s_decode(uint32_t r, uint32_t i, const float *lut) {
+    const uint32_t x = r >> (2u * i);
+    const F2 a = reinterpret_cast<const F2 *>(lut)[
+        (x & 3u) | ((x >> 14) & 12u)];                 // bytes 0, 2: ch 0, 1
+    const F2 b = reinterpret_cast<const F2 *>(lut)[
+        ((x >> 8) & 3u) | ((x >> 22) & 12u)];          // bytes 1, 3: ch 2, 3
+    return F4{a.x, a.y, b.x, b.y};
+}
+
+BB_HD void m4s_emit_fast(const M4Geom &p, const float *lut, float *chunk_out,
+                         uint32_t q, uint32_t i, uint32_t r, bool valid) {
+    *reinterpret_cast<F4 *>(chunk_out + 4u * q) = valid
+        ? m4s_decode(r, i, lut) : F4{p.fill, p.fill, p.fill, p.fill};
 }
 
 // ------------------------------------------------------------------ encode

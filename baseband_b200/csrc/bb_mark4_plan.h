@@ -1,5 +1,6 @@
 // Host-side planning for the Mark 4 codec (shared with the CPU emulation).
 #pragma once
+#include <stdlib.h>
 #include <string>
 #include <vector>
 #include "bb_mark4.cuh"
@@ -69,6 +70,17 @@ inline bool m4_build_pos(int nchan, int fanout, int ft, uint16_t pos[32],
     return true;
 }
 
+inline bool m4_is_fast(int nchan, int fanout, int ft) {
+    return !ft && fanout == 4 && (nchan == 4 || nchan == 8);
+}
+
+// BB_TUNE_M4 (development): 0 = FAST for 8 channels, generic WARP for 4;
+// 1 = generic WARP for both; 2 = WARP with the standard-layout decode.
+inline int m4_tune() {
+    const char *e = getenv("BB_TUNE_M4");
+    return (e && *e) ? atoi(e) : 0;
+}
+
 inline bool m4_base_geom(int nchan, int fanout, int ft, const float *levels,
                          M4Geom &g, std::string &err) {
     int ntrack;
@@ -83,18 +95,15 @@ inline bool m4_base_geom(int nchan, int fanout, int ft, const float *levels,
     g.src = nullptr; g.out = nullptr; g.in = nullptr;
     g.in_elem_offset = 0;
     g.fill = 0.f;
+    g.std4 = (m4_is_fast(nchan, fanout, ft) && m4_tune() == 2) ? 1u : 0u;
     return true;
-}
-
-inline bool m4_is_fast(int nchan, int fanout, int ft) {
-    return !ft && fanout == 4 && (nchan == 4 || nchan == 8);
 }
 
 // Decode: the per-half-word FAST path only where a row is >= 32 bytes (8
 // channels); the 4-channel layout stores 16-byte pieces 64 bytes apart there
 // and is faster through the WARP path.
 inline bool m4_dec_fast(int nchan, int fanout, int ft) {
-    return !ft && fanout == 4 && nchan == 8;
+    return !ft && fanout == 4 && nchan == 8 && m4_tune() == 0;
 }
 
 // WARP decode needs the 8 bits of every output float4 inside one 32-bit half

@@ -324,3 +324,30 @@ def mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
     _lib.check(rc, lib)
     _count()
     return words5, unit_offset
+
+
+def probe_fill(dst, pattern=0):
+    """bb_probe_fill: write the whole tensor ``dst`` with the decode kernels'
+    launch shape (pure-write bandwidth probe)."""
+    lib = _lib.load()
+    nbytes = dst.numel() * dst.element_size()
+    with _on(dst.device):
+        rc = lib.bb_probe_fill(_dev(dst, 'dst'), nbytes, pattern,
+                               _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst
+
+
+def probe_copy(dst, src):
+    """bb_probe_copy: vector copy of ``src`` into ``dst`` (read + write)."""
+    lib = _lib.load()
+    nbytes = src.numel() * src.element_size()
+    if dst.numel() * dst.element_size() != nbytes:
+        raise ValueError('dst and src must have the same size')
+    with _on(dst.device):
+        rc = lib.bb_probe_copy(_dev(dst, 'dst'), _dev(src, 'src'), nbytes,
+                               _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return dst

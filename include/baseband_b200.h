@@ -250,6 +250,16 @@ int bb_mark4_scan(const void *src, const int64_t *frame_offset,
                   int32_t track, uint32_t *words5, int64_t *unit_offset,
                   void *stream);
 
+/* ------------------------------------------------------ bandwidth probes
+ * Not part of the reference's path: the ceilings bench.py quotes next to the
+ * decode kernels, measured in the same run with the kernels' own launch shape
+ * (one-shot grid, 8 float4 per thread).  bb_probe_fill writes nbytes of
+ * float32 1.0 (pattern 0: every warp store 512 contiguous bytes; pattern 1:
+ * 8 pieces of 64 bytes per warp store, the row-group shape); bb_probe_copy is
+ * a 16-byte-vector copy (read + write). */
+int bb_probe_fill(void *dst, int64_t nbytes, int32_t pattern, void *stream);
+int bb_probe_copy(void *dst, const void *src, int64_t nbytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,13 @@ DECODE_CASES = [
     _case('2bit_16thr_partial', 2, 1, 16, 3, 800, start=3217, count=4001),
     _case('2bit_8thr_invalid', 2, 1, 8, 3, 400, invalid=(1, 9, 10, 23),
           fill=-999.0),
+    # rows of four float4 (TILE modes when selected)
+    _case('2bit_16thr_invalid_partial', 2, 1, 16, 4, 404, start=1619,
+          count=4200, invalid=(0, 17, 18, 35, 63), fill=-999.0),
+    _case('2bit_16thr_odd_words', 2, 1, 16, 3, 36, invalid=(40,), fill=3.0),
+    _case('2bit_cplx_8thr', 2, 2, 8, 3, 260, cplx=True, start=77, count=700,
+          invalid=(3, 12), fill=-5.0),
+    _case('2bit_cplx_8thr_full', 2, 2, 8, 2, 800, cplx=True),
     _case('2bit_4thr_one_sample', 2, 1, 4, 2, 64, start=255, count=2),
     _case('1bit_8thr', 1, 1, 8, 2, 128, start=5, count=1999),
     _case('4bit_4thr', 4, 1, 4, 2, 256, invalid=(3,), fill=7.5),

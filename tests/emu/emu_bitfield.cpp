@@ -42,6 +42,36 @@ static void run_wordrow(const DecGeom &g, const float *lut) {
     }
 }
 
+// warp-cooperative TILE modes
+template <int BPS, int CODEC, int G, int P, bool SEL>
+static void run_tile(const DecGeom &g, const float *lut, const float *levels) {
+    using T = Tile<BPS, G, P>;
+    LevelTable<BPS> lv;
+    for (int i = 0; i < (1 << BPS); ++i) lv.v[i] = levels ? levels[i] : 0.f;
+    for (uint32_t chunk = 0; chunk < g.nitems / 32; ++chunk) {
+        uint32_t wbuf[T::kWords], oks[32];
+        bool full = true;
+        for (uint32_t lane = 0; lane < 32; ++lane) {
+            uint32_t w[T::kNl];
+            oks[lane] = tile_load<BPS, G, P>(g, chunk, lane, w);
+            full = full && oks[lane] == (1u << T::kNl) - 1u;
+            for (int i = 0; i < T::kNl; ++i) wbuf[T::kNl * lane + i] = w[i];
+        }
+        const bool fast = full && tile_interior<BPS, G, P>(g, chunk);
+        for (uint32_t q = 0; q < 32u * T::kStores; ++q) {
+            const uint32_t at = ((q >> 2) / T::kTpw) * T::kSlots + (q & 3u) * G;
+            if (fast)
+                *reinterpret_cast<F4 *>(tile_chunk_out<BPS, G, P>(g, chunk)
+                                        + 4u * q) =
+                    tile_decode<BPS, CODEC, G, P, SEL>(q, &wbuf[at], lut, lv);
+            else
+                tile_emit<BPS, CODEC, G, P, SEL>(
+                    g, lut, lv, chunk, q, &wbuf[at],
+                    full ? (1u << G) - 1u : tile_group_ok<BPS, G, P>(oks, q));
+        }
+    }
+}
+
 template <int BPS, int CODEC>
 static void run_decode(const std::vector<DecLaunch> &launches,
                        const float *levels) {
@@ -67,6 +97,20 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             }
             continue;
         }
+        if (is_tile(l.mode)) {
+            if constexpr (BPS == 2 && CODEC == CODEC_LEVELS) {
+                const bool g4 = l.mode == MODE_TILE4;
+                if (g4 && l.tile_p == 8 && l.sel) run_tile<BPS, CODEC, 4, 8, true>(l.g, lut, levels);
+                else if (g4 && l.tile_p == 8) run_tile<BPS, CODEC, 4, 8, false>(l.g, lut, levels);
+                else if (g4 && l.sel) run_tile<BPS, CODEC, 4, 4, true>(l.g, lut, levels);
+                else if (g4) run_tile<BPS, CODEC, 4, 4, false>(l.g, lut, levels);
+                else if (l.tile_p == 8 && l.sel) run_tile<BPS, CODEC, 2, 8, true>(l.g, lut, levels);
+                else if (l.tile_p == 8) run_tile<BPS, CODEC, 2, 8, false>(l.g, lut, levels);
+                else if (l.sel) run_tile<BPS, CODEC, 2, 4, true>(l.g, lut, levels);
+                else run_tile<BPS, CODEC, 2, 4, false>(l.g, lut, levels);
+            }
+            continue;
+        }
         if (is_wordrow(l.mode)) {
             if (l.mode == MODE_WORDROW4) run_wordrow<BPS, CODEC, 4, 1>(l.g, lut);
             else if (l.mode == MODE_WORDROW2) run_wordrow<BPS, CODEC, 2, 1>(l.g, lut);
@@ -75,6 +119,23 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             continue;
         }
         for (uint32_t item = 0; item < l.g.nitems; ++item) {
+            if (l.sel && (l.mode == MODE_ROWGROUP4
+                          || l.mode == MODE_ROWGROUP2)) {
+                if constexpr (BPS <= 2 && CODEC == CODEC_LEVELS) {
+                    LevelTable<BPS> lv;
+                    for (int i = 0; i < (1 << BPS); ++i) lv.v[i] = levels[i];
+                    if (l.mode == MODE_ROWGROUP4) {
+                        RowItem<4> it;
+                        rowgroup_fetch<BPS, 4>(l.g, item, it);
+                        rowgroup_emit<BPS, CODEC, 4, true>(l.g, lut, it, lv);
+                    } else {
+                        RowItem<2> it;
+                        rowgroup_fetch<BPS, 2>(l.g, item, it);
+                        rowgroup_emit<BPS, CODEC, 2, true>(l.g, lut, it, lv);
+                    }
+                }
+                continue;
+            }
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
             else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);

@@ -28,7 +28,12 @@ static void run_dec(const std::vector<M4Launch> &launches) {
                 for (uint32_t q = 0; q < 128; ++q) {
                     const M4Lane lc = m4w_lane(l.g, l.g.pos, q & 31u);
                     uint32_t src = m4w_src_lane(l.g, lc, q);
-                    if (interior)
+                    if (interior && l.g.std4) {
+                        const uint32_t ss = m4s_src_lane(l.g, q);
+                        m4s_emit_fast(l.g, lut, m4w_chunk_out(l.g, chunk), q,
+                                      m4s_row(l.g, q), m4_reorder32(w[ss]),
+                                      ok[ss]);
+                    } else if (interior)
                         m4w_emit_fast(l.g, lc, lut, m4w_chunk_out(l.g, chunk),
                                       q, w[src], ok[src]);
                     else
