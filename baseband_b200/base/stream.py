@@ -570,6 +570,7 @@ class StreamReaderBase(StreamBase):
     _index = None
 
     def _set_index_table(self, table, phys_frame_nbytes):
+        self._small_cache = None     # decoded without the index: stale
         self._index = table
         self._index_lo = np.where(table >= 0, table,
                                   np.iinfo(np.int64).max)
@@ -763,6 +764,13 @@ class StreamReaderBase(StreamBase):
                         self._on_device(piece)
                     if self._subset and not piece.is_contiguous():
                         piece = piece.contiguous()
+                    if piece.untyped_storage().data_ptr() \
+                            != st.dec.untyped_storage().data_ptr():
+                        # a fresh tensor (subset gather / contiguous copy)
+                        # allocated under stream 1 but read by the D2H copy
+                        # on stream 2: keep its block out of stream 1's pool
+                        # until that copy is done
+                        ss.keep_alive(piece, 2)
                 with ss.use(2):
                     ss.wait(2, 1)
                     if staged:

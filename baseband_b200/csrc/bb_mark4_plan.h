@@ -74,11 +74,15 @@ inline bool m4_is_fast(int nchan, int fanout, int ft) {
     return !ft && fanout == 4 && (nchan == 4 || nchan == 8);
 }
 
-// BB_TUNE_M4 (development): 0 = FAST for 8 channels, generic WARP for 4;
-// 1 = generic WARP for both; 2 = WARP with the standard-layout decode.
+// Decode path of the standard fan-out 4 layouts (32 / 64 tracks), selectable
+// with BB_TUNE_M4 for comparison runs: 2 (default) = WARP with the
+// standard-layout decode (every warp store 512 contiguous bytes; C3 6.27 ->
+// 6.70 TB/s, 32 tracks 6.60 -> 6.72, profiles/r2_sweep_variants.txt); 1 =
+// table-driven WARP decode; 0 = per-half-word FAST decode for 8 channels
+// (16 pieces of 32 B per warp store) and table-driven WARP for 4.
 inline int m4_tune() {
     const char *e = getenv("BB_TUNE_M4");
-    return (e && *e) ? atoi(e) : 0;
+    return (e && *e) ? atoi(e) : 2;
 }
 
 inline bool m4_base_geom(int nchan, int fanout, int ft, const float *levels,

@@ -206,6 +206,12 @@ class Streams:
         if ev is not None:
             self.streams[i].wait_event(ev)
 
+    def keep_alive(self, tensor, i):
+        """``tensor`` (allocated under another stream) is about to be used on
+        stream i: the caching allocator must not hand its block out again
+        before that use has finished."""
+        tensor.record_stream(self.streams[i])
+
     def synchronize(self):
         for s in self.streams:
             s.synchronize()

@@ -52,6 +52,17 @@ def _require_cuda(*tensors):
                             'no CPU fallback)')
 
 
+def _float_code(data):
+    """bb_dtype of a float32/float64 tensor; anything else is refused (the
+    kernels read 4 or 8 bytes per element)."""
+    if data.dtype == torch.float32:
+        return F32
+    if data.dtype == torch.float64:
+        return F64
+    raise TypeError('data must be float32 or float64, not {}'.format(
+        data.dtype))
+
+
 def _levels_arg(levels):
     if levels is None:
         return None, None
@@ -107,12 +118,7 @@ def encode_bitfield(data, dst, unit_offset, nset, nthread, payload_nbytes,
     offsets."""
     lib = _lib.load()
     _require_cuda(data, dst, unit_offset)
-    if data.dtype == torch.float32:
-        code = F32
-    elif data.dtype == torch.float64:
-        code = F64
-    else:
-        raise TypeError('data must be float32 or float64')
+    code = _float_code(data)
     with _on(dst.device):
         rc = lib.bb_encode_bitfield(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -148,7 +154,7 @@ def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
 
 def mark4_encode(data, dst, unit_offset, nframe, nchan, fanout, ft=False):
     lib = _lib.load()
-    code = F32 if data.dtype == torch.float32 else F64
+    code = _float_code(data)
     with _on(dst.device):
         rc = lib.bb_mark4_encode(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -177,7 +183,7 @@ def mark4_decode_words(words, nword, nchan, fanout, ft=False, levels=None,
 
 def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
     lib = _lib.load()
-    code = F32 if data.dtype == torch.float32 else F64
+    code = _float_code(data)
     with _on(words.device):
         rc = lib.bb_mark4_encode_words(
             _dev(data, 'data'), code, _dev(words, 'words'), nword, nchan,
@@ -206,7 +212,7 @@ def decode_int8_transposed(src, unit_offset, nunit, nrow, ncol, item_nbytes,
 def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
                            item_nbytes):
     lib = _lib.load()
-    code = F32 if data.dtype == torch.float32 else F64
+    code = _float_code(data)
     with _on(dst.device):
         rc = lib.bb_encode_int8_transposed(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -238,7 +244,7 @@ def decode_int8_timefirst(src, unit_offset, nunit, nsample, nchan, npol,
 def encode_int8_timefirst(data, dst, unit_offset, nunit, nsample, nchan, npol,
                           item_nbytes):
     lib = _lib.load()
-    code = F32 if data.dtype == torch.float32 else F64
+    code = _float_code(data)
     with _on(dst.device):
         rc = lib.bb_encode_int8_timefirst(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),

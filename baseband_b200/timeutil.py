@@ -62,12 +62,17 @@ class Time:
 
     @property
     def isot(self):
-        y, m, d = mjd_to_ymd(self.mjd)
-        whole = int(self.sec)
-        frac = self.sec - whole
+        # round to whole nanoseconds first, so that a fraction that rounds
+        # up to 10^9 ns carries into the seconds (and the day)
+        total_ns = int(round(self.sec * 10**9))
+        mjd = self.mjd
+        if total_ns >= 86400 * 10**9:
+            total_ns -= 86400 * 10**9
+            mjd += 1
+        y, m, d = mjd_to_ymd(mjd)
+        whole, ns = divmod(total_ns, 10**9)
         h, rem = divmod(whole, 3600)
         mi, s = divmod(rem, 60)
-        ns = int(round(frac * 10**9))
         return '{:04d}-{:02d}-{:02d}T{:02d}:{:02d}:{:02d}.{:09d}'.format(
             y, m, d, h, mi, s, ns)
 
@@ -98,12 +103,22 @@ class Time:
 
 
 def as_time(value):
-    """Accept a Time, an ISO string, or anything with ``.mjd`` (e.g. an
-    astropy Time) or ``.isot``."""
+    """Accept a Time, an ISO string, an astropy-like Time (``.jd1``/``.jd2``)
+    or anything with ``.isot`` or ``.mjd``."""
     if value is None or isinstance(value, Time):
         return value
     if isinstance(value, str):
         return Time.from_isot(value)
+    # astropy-like objects: the two-double Julian date keeps sub-nanosecond
+    # resolution (``isot`` prints only 3 decimals by default, ``mjd`` is one
+    # double: ~1 us); rounded to whole nanoseconds
+    utc = getattr(value, 'utc', value)
+    if hasattr(utc, 'jd1') and hasattr(utc, 'jd2'):
+        days = (Fraction(float(utc.jd1)) + Fraction(float(utc.jd2))
+                - Fraction(24000005, 10))
+        whole = days.numerator // days.denominator
+        ns = int(round((days - whole) * 86400 * 10**9))
+        return Time(whole, Fraction(ns, 10**9))
     if hasattr(value, 'isot'):
         return Time.from_isot(str(value.isot))
     if hasattr(value, 'mjd'):

@@ -183,8 +183,16 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         else:
             self._post_subset = self._subset
             self._thread_ids = list(thread_ids)
+        # A selection may name a thread more than once (subset [0, -1] on a
+        # one-thread file): each thread is decoded once and duplicates are
+        # expanded by a gather on the decoded samples.
+        self._decode_ids = list(dict.fromkeys(self._thread_ids))
+        self._thread_expand = None
+        if len(self._decode_ids) != len(self._thread_ids):
+            self._thread_expand = [self._decode_ids.index(t)
+                                   for t in self._thread_ids]
         slots = np.full(1024, -1, np.int32)
-        for slot, tid in enumerate(self._thread_ids):
+        for slot, tid in enumerate(self._decode_ids):
             slots[tid] = slot
         self._slots_host = slots
         self._slots_dev = None
@@ -233,17 +241,20 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
     # decoded layout: selected threads only
     @property
     def _floats_per_sample(self):
-        return (len(self._thread_ids) * self._sample_shape[1]
+        return (len(self._decode_ids) * self._sample_shape[1]
                 * (2 if self._complex_data else 1))
 
     def _finish(self, flat, nsample):
-        nthread, nchan = len(self._thread_ids), self._sample_shape[1]
+        nthread, nchan = len(self._decode_ids), self._sample_shape[1]
         n = nsample * self._floats_per_sample
         if self._complex_data:
             data = torch.view_as_complex(flat[:n].view(nsample, nthread,
                                                        nchan, 2))
         else:
             data = flat[:n].view(nsample, nthread, nchan)
+        if self._thread_expand is not None:
+            data = data[:, torch.as_tensor(self._thread_expand,
+                                           device=data.device)]
         if self._squeeze:
             data = data.reshape((nsample,) + tuple(
                 d for d in data.shape[1:] if d > 1))
@@ -270,7 +281,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
             nthread_file = len(self._file_thread_ids)
             fields, uo, bad = kernels.vdif_scan(
                 raw, nframe * nthread_file, h0.frame_nbytes, h0.nbytes,
-                nthread_file, self._slots_dev, len(self._thread_ids))
+                nthread_file, self._slots_dev, len(self._decode_ids))
             if self.verify:
                 # every set must carry the frame index its position implies
                 sec = fields[kernels.VDIF_SECONDS].view(
@@ -284,7 +295,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
                 bad = bad + (index != want).sum().to(torch.int32)
             self._checks.append(bad)
         kernels.decode_bitfield(
-            raw, uo, nframe, len(self._thread_ids), h0.payload_nbytes,
+            raw, uo, nframe, len(self._decode_ids), h0.payload_nbytes,
             h0.bps, nelem, self._complex_data, self._codec[0],
             self._codec[1], self._fill_value, sample_start, nsample, out)
 
@@ -321,7 +332,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         slot = self._slots_host[tid].astype(np.int64)
         ok = (index >= 0) & (slot >= 0) & (index < 2 * nphys + fps)
         nset = int(index[ok].max()) + 1 if ok.any() else 0
-        table = np.full((nset, len(self._thread_ids)), -1, np.int64)
+        table = np.full((nset, len(self._decode_ids)), -1, np.int64)
         phys = np.arange(nphys, dtype=np.int64)
         # first occurrence wins: assign in reverse order
         sel = np.flatnonzero(ok)[::-1]

@@ -35,6 +35,9 @@ class _NoStreams:
     def wait_event(self, i, ev):
         pass
 
+    def keep_alive(self, tensor, i):
+        pass
+
     def event(self, i):
         class _Ev:
             def synchronize(self):

@@ -1078,6 +1078,53 @@ def vdif_missing_frames():
             _same(fh.read(), full)
             assert fh._index is not None
     assert any('missing or out-of-order' in str(r.message) for r in rec)
+    # the same through a SMALL read (served from the decoded-window cache):
+    # the window decoded before the index existed must not be reused
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        with bb.vdif.open(io.BytesIO(swapped.tobytes()), 'rs',
+                          sample_rate=32e6) as fh:
+            fh.seek(60000)
+            _same(fh.read(1000), full[60000:61000])
+            fh.seek(80000)
+            _same(fh.read(1000), full[80000:81000])
+            fh.seek(60500)
+            _same(fh.read(100), full[60500:60600])
+
+
+def vdif_duplicate_thread_selection():
+    """A subset that names a thread twice returns it twice (as numpy indexing
+    of the decoded frame set does in the reference, vdif/base.py:464-490)."""
+    raw = synthetic.vdif_stream(3, 8, 5000, seed=5)
+    full = ostream.vdif_read(raw)[:, :, 0]
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=32e6,
+                      subset=[1, 5, 1, -1]) as fh:
+        assert fh.sample_shape == (4,)
+        _same(fh.read(), full[:, [1, 5, 1, 7]])
+    one = synthetic.vdif_stream(4, 1, 5000, seed=6)
+    want = ostream.vdif_read(one)[:, :, 0]
+    with bb.vdif.open(io.BytesIO(one.tobytes()), 'rs', sample_rate=32e6,
+                      squeeze=False, subset=[0, -1]) as fh:
+        got = fh.read()
+        assert got.shape == (want.shape[0], 2, 1)
+        _same(got[:, 0, 0], want[:, 0])
+        _same(got[:, 1, 0], want[:, 0])
+
+
+def vdif_subset_multichunk_host_read():
+    """Host read with a non-contiguous subset over many chunks (the gathered
+    piece is a fresh tensor handed from the compute to the D2H stream)."""
+    nset, nthread = 40, 8
+    raw = synthetic.vdif_stream(nset, nthread, 5000, seed=77)
+    full = ostream.vdif_read(raw)[:, :, 0]
+    for subset in ([6, 1, 3], slice(1, 8, 3)):
+        with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=32e6,
+                          subset=subset, chunk_nbytes=2 * nthread * 5032) as fh:
+            _same(fh.read(), full[:, subset])
+            out = np.empty((300000,) + fh.sample_shape, np.float32)
+            fh.seek(1234)
+            fh.read(out=out)
+            _same(out, full[1234:301234][:, subset])
 
 
 def dada_file_sequence():

@@ -185,3 +185,27 @@ def test_plugin_protocol():
     m5 = bb.mark5b.info(sample_path('sample.m5b'))
     assert m5 and m5.format == 'mark5b' and m5.readable is False  # needs nchan
     assert bb.dada.info(sample_path('sample.dada')).format == 'dada'
+
+
+def test_as_time_two_double_julian_date():
+    """astropy-like times are taken from jd1/jd2 (sub-microsecond), not from
+    the 3-decimal ``isot``; a fraction that rounds to 10^9 ns carries."""
+    from fractions import Fraction
+    from baseband_b200.timeutil import Time, as_time
+
+    class FakeAstropy:
+        # 2014-06-16T05:56:07.000123456 UTC: MJD 56824
+        jd1 = 2456824.5
+        jd2 = (5 * 3600 + 56 * 60 + 7 + 0.000123456) / 86400.
+        isot = '2014-06-16T05:56:07.000'
+        mjd = 56824.24730324217
+
+    t = as_time(FakeAstropy())
+    assert t.mjd == 56824
+    assert abs(t.sec - Fraction(21367000123456, 10**9)) <= Fraction(2, 10**9)
+    assert t.isot.startswith('2014-06-16T05:56:07.00012345')
+    # carry: 0.9999999996 s prints as the next second, not '.1000000000'
+    t = Time(56824, Fraction(86399) + Fraction(9999999996, 10**10))
+    assert t.isot == '2014-06-17T00:00:00.000000000'
+    t = Time(56824, Fraction(59) + Fraction(9999999996, 10**10))
+    assert t.isot == '2014-06-16T00:01:00.000000000'

@@ -112,6 +112,19 @@ def main():
                                                   'ok' if same else 'MISMATCH'),
                        nbytes, fn, seconds)
         os.environ['BB_TUNE_C2'] = '0'
+        # where does the gap to the pure-write rate come from?  Same launch,
+        # but every set reads the frames of the first `alias` sets, so the
+        # packed input stays in L2 and DRAM sees writes only.
+        for alias in (64, 1024):
+            off_a = off.view(nset, nthread)[torch.arange(nset, device=DEV)
+                                            % alias].reshape(-1).contiguous()
+
+            def fn_alias():
+                kernels.decode_bitfield(raw, off_a, nset, nthread, payload,
+                                        2, nelem, cplx, kernels.CODEC_LEVELS,
+                                        lv, out=out)
+            report('%s DEC input aliased to %d sets (L2 hits)'
+                   % (name, alias), nbytes, fn_alias, seconds)
         del raw, out, ref
         torch.cuda.empty_cache()
 
