@@ -70,12 +70,13 @@ SIGNATURES = {
         c_int32, c_void_p]),
     'bb_vdif_scan': (c_int, [
         _pv, _pi64, c_int64, c_int64, c_int32, c_int32, c_int32, _pv, _pv,
-        _pi64, _pv, c_void_p]),
+        _pi64, _pv, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     'bb_mark5b_scan': (c_int, [
-        _pv, _pi64, c_int64, c_int64, _pv, _pi64, c_void_p]),
+        _pv, _pi64, c_int64, c_int64, _pv, _pi64, _pv, c_int64, c_int32,
+        c_int32, c_int32, c_int32, c_void_p]),
     'bb_mark4_scan': (c_int, [
-        _pv, _pi64, c_int64, c_int64, c_int32, c_int32, _pv, _pi64,
-        c_void_p]),
+        _pv, _pi64, c_int64, c_int64, c_int32, c_int32, _pv, _pi64, _pv,
+        c_int64, c_int32, c_int64, c_int64, c_void_p]),
     'bb_probe_fill': (c_int, [_pv, c_int64, c_int32, c_void_p]),
     'bb_probe_copy': (c_int, [_pv, _pv, c_int64, c_void_p]),
 }
@@ -117,7 +118,7 @@ def load():
         # library is a build error, not something to work around.
         _lib = bind(ctypes.CDLL(LIB_PATH),
                     required=() if os.environ.get('BB_ALLOW_PARTIAL') else EXPORTS)
-        if _lib.bb_abi_version() != 1:
+        if _lib.bb_abi_version() != 2:
             raise ImportError('baseband_b200: ABI version mismatch')
     return _lib
 

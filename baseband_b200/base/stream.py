@@ -661,6 +661,27 @@ class StreamReaderBase(StreamBase):
             yield c0, c1 - c0, first - self._frame_sample0(c0), last - first, row
             row += last - first
 
+    # Frame-regularity checks are folded into the scan kernels, which add to
+    # one device counter per reader; a read looks at it once, at its end.
+    _bad_dev = None
+    _bad_seen = 0
+
+    def _bad_counter(self, dev):
+        if self._bad_dev is None or self._bad_dev.device != dev:
+            from .. import kernels
+            self._bad_dev = kernels.new_counter(dev)
+            self._bad_seen = 0
+        return self._bad_dev
+
+    def _new_inconsistencies(self):
+        """Frames the scan kernels found out of place since the last call
+        (synchronises with the device)."""
+        if self._bad_dev is None:
+            return 0
+        now = int(self._bad_dev.item())
+        new, self._bad_seen = now - self._bad_seen, now
+        return new
+
     def _pipeline(self, dev):
         if self._stages is None:
             self._stages = [_Stage(), _Stage()]
@@ -804,6 +825,8 @@ class StreamReaderBase(StreamBase):
         state['_streams'] = None
         state['_small_cache'] = None
         state.pop('_slots_dev', None)
+        state.pop('_bad_dev', None)
+        state.pop('_bad_seen', None)
         state.pop('_sample_shape_cache', None)    # namedtuple made on the fly
         wrapper = state['fh_raw']
         fh = getattr(wrapper, 'fh_raw', wrapper)

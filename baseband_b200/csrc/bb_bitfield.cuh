@@ -73,6 +73,7 @@ struct DecGeom {
     uint32_t ngroup;                // nthread / G
     int32_t log2_nelem;             // RUN with nthread > 1
     uint32_t complex_fill;
+    uint32_t debug;                 // knock-out experiments (BB_TUNE_KNOCK)
     float fill;
     FastDiv div_nword, div_ngroup, div_rowlen, div_spf, div_nelem, div_unitlen;
 };
@@ -210,6 +211,17 @@ BB_HD void rowgroup_fetch(const DecGeom &p, uint32_t item, RowItem<G> &it) {
     it.okmask = 0u;
     if (!it.live) return;
     const long long *uo = p.unit_offset + (size_t)set * p.nthread + it.g * G;
+    if (p.debug) {
+        // knock-out runs (tools/sweep_variants.py): 1 = no payload loads,
+        // 2 = no loads at all; the words are a hash of the item
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+            const long long off = p.debug >= 2 ? 0 : uo[j];
+            it.w[j] = (item + (uint32_t)off) * 0x9E3779B1u + j;
+            it.okmask |= 1u << j;
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < G; ++j) {
         const long long off = uo[j];

@@ -162,6 +162,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);
         g.complex_fill = complex_data ? 1 : 0;
+        g.debug = (uint32_t)tune("BB_TUNE_KNOCK", 0);
         g.fill = fill;
         g.div_nword = make_fastdiv(nword);
         g.div_ngroup = make_fastdiv(ngroup);

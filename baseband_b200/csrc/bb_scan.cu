@@ -27,7 +27,8 @@ __global__ void __launch_bounds__(kScanBlock)
 k_vdif_scan(const uint8_t *src, const long long *frame_offset,
             long long frame_stride, long long nframe, int header_nbytes,
             int frames_per_set, int nthread, const int *thread_slot,
-            int *fields, long long *unit_offset, int *n_bad) {
+            int *fields, long long *unit_offset, int *n_bad,
+            long long index0, int seconds0, int frame_nr0, int fps) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nframe) return;
     long long off = frame_offset ? frame_offset[i] : i * frame_stride;
@@ -69,6 +70,12 @@ k_vdif_scan(const uint8_t *src, const long long *frame_offset,
         long long off0 = frame_offset ? frame_offset[i0] : i0 * frame_stride;
         uint32_t b = ldw(src + off0 + 4);
         if (bits(b, 0, 24) != frame_nr) atomicAdd(n_bad, 1);
+    } else if (fps > 0) {
+        // the set must carry the frame index its position implies
+        // (baseband/vdif/base.py:386-390, on the first frame of the set)
+        const long long index = ((long long)seconds - seconds0) * fps
+            + (long long)frame_nr - frame_nr0;
+        if (index != index0 + set) atomicAdd(n_bad, 1);
     }
     int slot = thread_slot[tid];
     if (slot < 0 || slot >= nthread) return;      // thread not selected
@@ -107,7 +114,8 @@ __device__ __forceinline__ int bcd(uint32_t v, int ndigit) {
 __global__ void __launch_bounds__(kScanBlock)
 k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
               long long frame_stride, long long nframe, int *fields,
-              long long *unit_offset) {
+              long long *unit_offset, int *n_bad, long long index0,
+              int jday0, int seconds0, int frame_nr0, int fps) {
     const uint32_t kFill = 0x11223344u;
     const int lane = threadIdx.x & 31;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,10 +147,22 @@ k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
         if (lane == b) valid = any;
     }
     if (!live) return;
+    const int bj = bits(w2, 20, 12), bs = bits(w2, 0, 20),
+        bf = bits(w3, 16, 16);
+    if (n_bad && fps > 0) {
+        // frame index from the header time must equal the position
+        // (baseband/mark5b/base.py:206-213; jday wraps every 1000 days)
+        const int jday = bcd(bj, 3), seconds = bcd(bs, 5);
+        const long long dday = (((long long)jday - jday0 + 1500) % 1000) - 500;
+        const long long index = ((long long)seconds - seconds0
+                                 + 86400ll * dday) * fps
+            + (long long)bits(w1, 0, 15) - frame_nr0;
+        if (w0 != 0xABADDEEDu || jday < 0 || seconds < 0
+            || index != index0 + i)
+            atomicAdd(n_bad, 1);
+    }
     if (fields) {
         int *f = fields + i;
-        const int bj = bits(w2, 20, 12), bs = bits(w2, 0, 20),
-            bf = bits(w3, 16, 16);
         f[BB_M5B_SYNC * nframe] = (int)w0;
         f[BB_M5B_USER * nframe] = bits(w1, 16, 16);
         f[BB_M5B_INTERNAL_TVG * nframe] = bits(w1, 15, 1);
@@ -168,25 +188,74 @@ k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
 // so a warp ballot over 32 consecutive steps, bit-reversed, is one header
 // word.  Error flags are bits 15..12 of word 1 = steps 48..51; the frame is
 // valid iff no track has one set (baseband/mark4/frame.py:78-87).
+// BCD of v < 1000 (three digits).
+__device__ __forceinline__ uint32_t bcd3(uint32_t v) {
+    return ((v / 100u) << 8) | (((v / 10u) % 10u) << 4) | (v % 10u);
+}
+
+// Time-code words 3 and 4 (CRC bits zero) of a Mark 4 header at `ticks`
+// quarter milliseconds after 00:00 of MJD mjd0
+// (baseband/mark4/header.py:223-262, :509-533): unit year, day of year,
+// hour, minute | second, millisecond.
+__device__ void mark4_time_words(int mjd0, long long ticks, uint32_t &w3,
+                                 uint32_t &w4) {
+    const long long kDay = 86400ll * 4000ll;
+    const long long day = ticks / kDay;
+    const uint32_t tick = (uint32_t)(ticks - day * kDay);
+    // civil date from the day count (days since 1970-01-01 = MJD - 40587)
+    const long long z = (long long)mjd0 + day - 40587 + 719468;
+    const long long era = (z >= 0 ? z : z - 146096) / 146097;
+    const uint32_t doe = (uint32_t)(z - era * 146097);
+    const uint32_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const uint32_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);  // from 1 Mar
+    long long year = (long long)yoe + era * 400;
+    uint32_t yday;
+    if (doy >= 306) {                    // January, February of the next year
+        year += 1;
+        yday = doy - 306 + 1;
+    } else {
+        const bool leap = (year % 4 == 0 && year % 100 != 0) || year % 400 == 0;
+        yday = doy + 59 + (leap ? 1 : 0) + 1;
+    }
+    const uint32_t sec = tick / 4000u, ms = (tick % 4000u) / 4u;
+    const uint32_t hour = sec / 3600u, minute = sec / 60u % 60u,
+        second = sec % 60u;
+    w3 = ((uint32_t)(year % 10) << 28) | (bcd3(yday) << 16)
+        | (bcd3(hour) << 8) | bcd3(minute);
+    w4 = (bcd3(second) << 24) | (bcd3(ms) << 12);
+}
+
 template <typename W>
 __global__ void __launch_bounds__(kScanBlock)
 k_mark4_scan(const uint8_t *src, const long long *frame_offset,
              long long frame_stride, long long nframe, int track,
-             uint32_t *words5, long long *unit_offset) {
+             uint32_t *words5, long long *unit_offset, int *n_bad,
+             long long index0, int mjd0, long long tick0,
+             long long tick_step) {
     const int lane = threadIdx.x & 31;
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nframe) return;                     // warp-uniform
     long long off = frame_offset ? frame_offset[i] : i * frame_stride;
     const W *st = reinterpret_cast<const W *>(src + off);
     bool bad = false;
+    uint32_t got3 = 0u, got4 = 0u;
 #pragma unroll
     for (int w = 0; w < 5; ++w) {
         W v = st[32 * w + lane];
-        unsigned m = __ballot_sync(0xffffffffu, (v >> track) & 1);
-        if (words5 && lane == 0) words5[i * 5 + w] = __brev(m);
+        unsigned m = __brev(__ballot_sync(0xffffffffu, (v >> track) & 1));
+        if (words5 && lane == 0) words5[i * 5 + w] = m;
+        if (w == 3) got3 = m;
+        if (w == 4) got4 = m;
         if (w == 1 && lane >= 16 && lane < 20 && v != 0) bad = true;
     }
     bad = __any_sync(0xffffffffu, bad);
+    if (n_bad && tick_step > 0 && lane == 0) {
+        // the time code of the chosen track must be the one the position of
+        // the frame implies (what the writer would generate; CRC bits aside)
+        uint32_t w3, w4;
+        mark4_time_words(mjd0, tick0 + tick_step * (index0 + i), w3, w4);
+        if (got3 != w3 || (got4 & 0xfffff000u) != w4) atomicAdd(n_bad, 1);
+    }
     if (unit_offset && lane == 0)
         unit_offset[i] = bad ? -1 : off + (long long)sizeof(W) * 160;
 }
@@ -199,7 +268,9 @@ extern "C" int bb_vdif_scan(
     const void *src, const int64_t *frame_offset, int64_t frame_stride,
     int64_t nframe, int32_t header_nbytes, int32_t frames_per_set,
     int32_t nthread, const int32_t *thread_slot, int32_t *fields,
-    int64_t *unit_offset, int32_t *n_inconsistent, void *stream) {
+    int64_t *unit_offset, int32_t *n_inconsistent, int64_t index0,
+    int32_t seconds0, int32_t frame_nr0, int32_t frames_per_second,
+    void *stream) {
     if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
     if (header_nbytes != 16 && header_nbytes != 32)
         return set_error(BB_ERR_ARGUMENT, "header_nbytes must be 16 or 32");
@@ -222,7 +293,8 @@ extern "C" int bb_vdif_scan(
                   kScanBlock, 0, s>>>(
         (const uint8_t *)src, (const long long *)frame_offset, frame_stride,
         nframe, header_nbytes, frames_per_set, nthread, thread_slot, fields,
-        (long long *)unit_offset, n_inconsistent);
+        (long long *)unit_offset, n_inconsistent, index0, seconds0, frame_nr0,
+        frames_per_second);
     BB_CHECK_LAUNCH("bb_vdif_scan");
     if (nunit) {
         k_count_missing<<<(unsigned)((nunit + 255) / 256), 256, 0, s>>>(
@@ -234,7 +306,9 @@ extern "C" int bb_vdif_scan(
 
 extern "C" int bb_mark5b_scan(
     const void *src, const int64_t *frame_offset, int64_t frame_stride,
-    int64_t nframe, int32_t *fields, int64_t *unit_offset, void *stream) {
+    int64_t nframe, int32_t *fields, int64_t *unit_offset,
+    int32_t *n_inconsistent, int64_t index0, int32_t jday0, int32_t seconds0,
+    int32_t frame_nr0, int32_t frames_per_second, void *stream) {
     if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
     if (!aligned(src, 4) || (frame_stride & 3))
         return set_error(BB_ERR_ALIGNMENT, "frames must be 4-byte aligned");
@@ -242,7 +316,8 @@ extern "C" int bb_mark5b_scan(
     k_mark5b_scan<<<(unsigned)((nframe + kScanBlock - 1) / kScanBlock),
                     kScanBlock, 0, as_stream(stream)>>>(
         (const uint8_t *)src, (const long long *)frame_offset, frame_stride,
-        nframe, fields, (long long *)unit_offset);
+        nframe, fields, (long long *)unit_offset, n_inconsistent, index0,
+        jday0, seconds0, frame_nr0, frames_per_second);
     BB_CHECK_LAUNCH("bb_mark5b_scan");
     return BB_OK;
 }
@@ -250,7 +325,8 @@ extern "C" int bb_mark5b_scan(
 extern "C" int bb_mark4_scan(
     const void *src, const int64_t *frame_offset, int64_t frame_stride,
     int64_t nframe, int32_t ntrack, int32_t track, uint32_t *words5,
-    int64_t *unit_offset, void *stream) {
+    int64_t *unit_offset, int32_t *n_inconsistent, int64_t index0,
+    int32_t mjd0, int64_t tick0, int64_t tick_step, void *stream) {
     if (!src) return set_error(BB_ERR_ARGUMENT, "null src");
     if (ntrack != 16 && ntrack != 32 && ntrack != 64)
         return set_error(BB_ERR_UNSUPPORTED, "ntrack must be 16, 32 or 64");
@@ -265,13 +341,16 @@ extern "C" int bb_mark4_scan(
     const long long *fo = (const long long *)frame_offset;
     if (ntrack == 64)
         k_mark4_scan<unsigned long long><<<grid, kScanBlock, 0, s>>>(
-            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset,
+            n_inconsistent, index0, mjd0, tick0, tick_step);
     else if (ntrack == 32)
         k_mark4_scan<uint32_t><<<grid, kScanBlock, 0, s>>>(
-            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset,
+            n_inconsistent, index0, mjd0, tick0, tick_step);
     else
         k_mark4_scan<uint16_t><<<grid, kScanBlock, 0, s>>>(
-            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset);
+            p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset,
+            n_inconsistent, index0, mjd0, tick0, tick_step);
     BB_CHECK_LAUNCH("bb_mark4_scan");
     return BB_OK;
 }

@@ -267,17 +267,34 @@ VDIF_NFIELD = 17
 M5B_NFIELD = 12
 
 
+def new_counter(device):
+    """Zeroed device int32[1]: the accumulating inconsistency counter the scan
+    kernels add to (one per reader, looked at once per ``read``)."""
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
 def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
-              thread_slot, nthread, frame_offset=None):
-    """bb_vdif_scan -> (fields int32 (NFIELD, nframe), unit_offset int64
-    (nset*nthread,), n_inconsistent int)."""
+              thread_slot, nthread, frame_offset=None, check=None, bad=None,
+              want_fields=True):
+    """bb_vdif_scan -> (fields int32 (NFIELD, nframe) or None, unit_offset
+    int64 (nset*nthread,), n_inconsistent int32[1]).
+
+    ``check = (index0, seconds0, frame_nr0, frames_per_second)`` folds the
+    frame-index check into the scan; ``bad`` is an accumulating counter from
+    `new_counter` (a fresh one is made if omitted)."""
     lib = _lib.load()
     dev = src.device
-    fields = torch.empty((VDIF_NFIELD, nframe), dtype=torch.int32, device=dev)
+    fields = (torch.empty((VDIF_NFIELD, nframe), dtype=torch.int32,
+                          device=dev) if want_fields else None)
     nset = nframe // frames_per_set
-    unit_offset = torch.full((max(nset * nthread, 1),), -1,
-                             dtype=torch.int64, device=dev)
-    bad = torch.zeros(1, dtype=torch.int32, device=dev)
+    unit_offset = torch.empty((max(nset * nthread, 1),), dtype=torch.int64,
+                              device=dev)
+    if nframe <= 0:
+        unit_offset.fill_(-1)
+    if bad is None:
+        bad = new_counter(dev)
+    index0, seconds0, frame_nr0, fps = check if check is not None \
+        else (0, 0, 0, 0)
     with _on(dev):
         rc = lib.bb_vdif_scan(
             _dev(src, 'src', torch.uint8),
@@ -286,47 +303,73 @@ def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
                                                    torch.int64),
             frame_stride, nframe, header_nbytes, frames_per_set, nthread,
             _dev(thread_slot, 'thread_slot', torch.int32),
-            _dev(fields, 'fields'), _dev(unit_offset, 'unit_offset'),
-            _dev(bad, 'bad'), _stream_ptr(dev))
+            None if fields is None else _dev(fields, 'fields'),
+            _dev(unit_offset, 'unit_offset'), _dev(bad, 'bad'),
+            int(index0), int(seconds0), int(frame_nr0), int(fps),
+            _stream_ptr(dev))
     _lib.check(rc, lib)
     _count(3)          # fill, scan, count-missing kernels
     return fields, unit_offset[:nset * nthread], bad
 
 
-def mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
+def mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None,
+                check=None, bad=None, want_fields=True):
+    """bb_mark5b_scan -> (fields or None, unit_offset).  ``check = (index0,
+    jday0, seconds0, frame_nr0, frames_per_second)`` with an accumulating
+    counter ``bad`` folds the frame-index check into the scan."""
     lib = _lib.load()
     dev = src.device
-    fields = torch.empty((M5B_NFIELD, nframe), dtype=torch.int32, device=dev)
+    fields = (torch.empty((M5B_NFIELD, nframe), dtype=torch.int32,
+                          device=dev) if want_fields else None)
     unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
+    if check is not None and bad is None:
+        raise ValueError('a frame-index check needs a counter')
+    index0, jday0, seconds0, frame_nr0, fps = check if check is not None \
+        else (0, 0, 0, 0, 0)
     with _on(dev):
         rc = lib.bb_mark5b_scan(
             _dev(src, 'src', torch.uint8),
             None if frame_offset is None else _dev(frame_offset,
                                                    'frame_offset',
                                                    torch.int64),
-            frame_stride, nframe, _dev(fields, 'fields'),
-            _dev(unit_offset, 'unit_offset'), _stream_ptr(dev))
+            frame_stride, nframe,
+            None if fields is None else _dev(fields, 'fields'),
+            _dev(unit_offset, 'unit_offset'),
+            None if bad is None else _dev(bad, 'bad'), int(index0),
+            int(jday0), int(seconds0), int(frame_nr0), int(fps),
+            _stream_ptr(dev))
     _lib.check(rc, lib)
     _count()
     return fields, unit_offset
 
 
 def mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
-               frame_offset=None):
+               frame_offset=None, check=None, bad=None, want_words=True):
+    """bb_mark4_scan -> (words5 or None, unit_offset).  ``check = (index0,
+    mjd0, tick0, tick_step)`` (quarter-millisecond ticks) with an
+    accumulating counter ``bad`` folds the time-code check into the scan."""
     lib = _lib.load()
     dev = src.device
     if frame_stride is None:
         frame_stride = ntrack * 2500
-    words5 = torch.empty((nframe, 5), dtype=torch.int32, device=dev)
+    words5 = (torch.empty((nframe, 5), dtype=torch.int32, device=dev)
+              if want_words else None)
     unit_offset = torch.empty((nframe,), dtype=torch.int64, device=dev)
+    if check is not None and bad is None:
+        raise ValueError('a time-code check needs a counter')
+    index0, mjd0, tick0, tick_step = check if check is not None \
+        else (0, 0, 0, 0)
     with _on(dev):
         rc = lib.bb_mark4_scan(
             _dev(src, 'src', torch.uint8),
             None if frame_offset is None else _dev(frame_offset,
                                                    'frame_offset',
                                                    torch.int64),
-            frame_stride, nframe, ntrack, track, _dev(words5, 'words5'),
-            _dev(unit_offset, 'unit_offset'), _stream_ptr(dev))
+            frame_stride, nframe, ntrack, track,
+            None if words5 is None else _dev(words5, 'words5'),
+            _dev(unit_offset, 'unit_offset'),
+            None if bad is None else _dev(bad, 'bad'), int(index0),
+            int(mjd0), int(tick0), int(tick_step), _stream_ptr(dev))
     _lib.check(rc, lib)
     _count()
     return words5, unit_offset

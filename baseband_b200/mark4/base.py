@@ -155,33 +155,46 @@ class Mark4StreamReader(StreamReaderBase):
             raise KeyError('no Mark 4 decoder for (nchan, bps, fanout) = '
                            '{}'.format(coder))
         self._levels = levels.sign_magnitude()
-        self._checks = []
+        self._tick = None
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
         h0 = self.header0
         nchan, fanout, ft = self._mode
-        words5, uo = kernels.mark4_scan(raw, nframe, h0.ntrack)
+        # with verify, the time code of track 0 must advance by one frame per
+        # frame: the scan kernel compares the BCD words with those the writer
+        # would generate for the frame's position
+        check = None
         if self.verify:
-            # time code of track 0 must advance by one frame per frame:
-            # compare the BCD words with those the writer would generate
-            want = _time_words(h0, self._frame_rate, frame0, nframe)
-            got = words5.view(nframe, 5)[:, 3:5]
-            mask = torch.tensor([-1, -4096], dtype=torch.int32,
-                                device=raw.device)      # drop the CRC bits
-            self._checks.append(((got & mask) != (
-                torch.from_numpy(want).to(raw.device) & mask)).any(1).sum())
+            if self._tick is None:
+                self._tick = _tick_grid(h0, self._frame_rate)
+            check = (frame0,) + self._tick
+        _, uo = kernels.mark4_scan(
+            raw, nframe, h0.ntrack, check=check,
+            bad=self._bad_counter(raw.device) if self.verify else None,
+            want_words=False)
         kernels.mark4_decode(raw, uo, nframe, nchan, fanout, ft,
                              self._levels, self._fill_value, sample_start,
                              nsample, out)
 
     def read(self, count=None, out=None, **kwargs):
-        self._checks = []
         result = super().read(count, out, **kwargs)
-        if self._checks and int(torch.stack(self._checks).sum().item()):
+        if self._new_inconsistencies():
             raise OSError('Mark 4 stream is not a regular sequence of '
                           'frames; recovery of corrupt files is not part of '
                           'the GPU path.')
         return result
+
+
+def _tick_grid(h0, frame_rate):
+    """(mjd0, tick0, tick_step): the frame times as integer ticks of 0.25 ms
+    after 00:00 of MJD mjd0 (Mark 4 times sit on a 1.25 ms grid)."""
+    from fractions import Fraction
+    t0 = h0.time
+    step = Fraction(4000) / Fraction(frame_rate).limit_denominator(10**9)
+    start = t0.sec * 4000
+    if step.denominator != 1 or Fraction(start).denominator != 1:
+        raise ValueError('Mark 4 frame times must lie on the 0.25 ms grid.')
+    return int(t0.mjd), int(start), int(step)
 
 
 def _time_fields(h0, frame_rate, index0, nframe):

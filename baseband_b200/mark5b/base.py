@@ -173,16 +173,15 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
             uo = torch.where(present, uo_phys[rel],
                              torch.full_like(rel, -1))
         else:
-            fields, uo = kernels.mark5b_scan(raw, nframe)
-            if self.verify:
-                index = self._frame_index(
-                    fields[kernels.M5B_JDAY].to(torch.int64),
-                    fields[kernels.M5B_SECONDS].to(torch.int64),
-                    fields[kernels.M5B_FRAME_NR].to(torch.int64))
-                want = torch.arange(frame0, frame0 + nframe,
-                                    device=raw.device)
-                sync_ok = fields[kernels.M5B_SYNC] == -1414668563  # ABADDEED
-                self._checks.append(((index != want) | ~sync_ok).sum())
+            # with verify, the frame index the header time implies
+            # (mark5b/base.py:206-213) is checked inside the scan kernel
+            h0 = self.header0
+            check = ((frame0, h0.jday, h0.seconds, h0['frame_nr'],
+                      int(round(self._frame_rate))) if self.verify else None)
+            _, uo = kernels.mark5b_scan(
+                raw, nframe, check=check,
+                bad=self._bad_counter(raw.device) if self.verify else None,
+                want_fields=False)
         kernels.decode_bitfield(
             raw, uo, nframe, 1, 10000, self._bps, self._sample_shape[0],
             False, kernels.CODEC_LEVELS, self._levels, self._fill_value,
@@ -231,10 +230,9 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
         self._set_index_table(table, 10016)
 
     def read(self, count=None, out=None, **kwargs):
-        self._checks = []
         offset = self.offset
         result = super().read(count, out, **kwargs)
-        if self._checks and int(torch.stack(self._checks).sum().item()):
+        if self._index is None and self._new_inconsistencies():
             if not self.verify:
                 raise OSError('Mark 5B stream is not a regular sequence of '
                               'frames and verify is off.')
@@ -244,7 +242,6 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
                           'gaps with fill_value.')
             self._build_index()
             self.offset = offset
-            self._checks = []
             return super().read(result.shape[0], out, **kwargs)
         return result
 

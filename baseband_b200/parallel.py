@@ -14,7 +14,7 @@ import os
 
 import torch
 
-__all__ = ['shard_bounds', 'shard_samples', 'read_sharded']
+__all__ = ['shard_bounds', 'shard_samples', 'gather_block', 'read_sharded']
 
 
 def shard_bounds(nitem, rank, world):
@@ -47,31 +47,65 @@ def _dist_env(rank, world):
     return rank, world
 
 
+def gather_block(fh, world):
+    """Samples per rank for a gathered read: equal blocks of whole frames
+    (the last ranks' blocks may be short or empty), so that rank r's shard
+    sits at row ``r * block`` of the gathered array and the all-gather can
+    write every shard straight to its final place."""
+    spf = fh.samples_per_frame
+    # from the sample count, so that a tail beyond the last whole frame
+    # (GUPPI's final overlap) is covered too
+    return -(-fh.shape[0] // (world * spf)) * spf
+
+
 def read_sharded(fh, rank=None, world=None, gather=False, group=None):
     """Decode this rank's contiguous share of ``fh``.
 
     Returns ``(data, (start, stop))``: the decoded samples of the shard (on
     the reader's device when it was opened with ``device=``) and the sample
-    range they cover.  With ``gather=True`` every rank instead receives the
-    whole stream: shards are padded to a common length, all-gathered
-    (NCCL over NVLink for CUDA tensors, gloo for host tensors) and trimmed.
+    range they cover.
+
+    With ``gather=True`` every rank instead receives the whole stream.  The
+    stream is then cut into equal blocks of whole frames (`gather_block`);
+    each rank decodes its block directly into its place in the full-length
+    result and ONE in-place ``all_gather_into_tensor`` (NCCL over NVLink for
+    CUDA tensors) fills in the others: no padding pass, no list of pieces, no
+    concatenation -- the only traffic besides the decode itself is the
+    collective's.
     """
     rank, world = _dist_env(rank, world)
-    start, stop = shard_samples(fh, rank, world)
-    fh.seek(start)
-    data = fh.read(stop - start)
     if not gather or world == 1:
+        start, stop = shard_samples(fh, rank, world)
+        fh.seek(start)
+        data = fh.read(stop - start)
         return data, (start, stop)
     import torch.distributed as dist
-    tensor = data if isinstance(data, torch.Tensor) else torch.from_numpy(data)
-    bounds = [shard_samples(fh, r, world) for r in range(world)]
-    longest = max(b - a for a, b in bounds)
-    padded = torch.zeros((longest,) + tuple(tensor.shape[1:]),
-                         dtype=tensor.dtype, device=tensor.device)
-    padded[:tensor.shape[0]] = tensor
-    pieces = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(pieces, padded, group=group)
-    whole = torch.cat([p[:b - a] for p, (a, b) in zip(pieces, bounds)])
-    if not isinstance(data, torch.Tensor):
+    import numpy as np
+    total = fh.shape[0]
+    block = gather_block(fh, world)
+    start, stop = min(total, rank * block), min(total, (rank + 1) * block)
+    on_device = getattr(fh, '_device_output', False)
+    t_dtype = torch.complex64 if fh.complex_data else torch.float32
+    shape = (world * block,) + tuple(fh.sample_shape)
+    if on_device:
+        whole = torch.empty(shape, dtype=t_dtype, device=fh.device)
+    else:
+        whole = torch.empty(shape, dtype=t_dtype)
+    mine = whole[rank * block:(rank + 1) * block]
+    if stop > start:
+        fh.seek(start)
+        fh.read(out=mine[:stop - start] if on_device
+                else mine[:stop - start].numpy())
+    # rows past the end of the stream (short last blocks) are never looked at
+    backend = dist.get_backend(group)
+    if on_device or backend != 'gloo':
+        dist.all_gather_into_tensor(whole, mine, group=group)
+    else:
+        # gloo has no all_gather_into_tensor on every build: views of the
+        # result serve as the output list (still no extra copy of our own)
+        dist.all_gather([whole[r * block:(r + 1) * block]
+                         for r in range(world)], mine.clone(), group=group)
+    whole = whole[:total]
+    if not on_device:
         whole = whole.numpy()
-    return whole, (0, fh.shape[0])
+    return whole, (0, total)

@@ -196,7 +196,6 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
             slots[tid] = slot
         self._slots_host = slots
         self._slots_dev = None
-        self._checks = []
         self._index = None
         if self.verify:
             # A partial frame set at the end of the file, or a last frame
@@ -279,21 +278,14 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
             if self._slots_dev is None or self._slots_dev.device != dev:
                 self._slots_dev = torch.from_numpy(self._slots_host).to(dev)
             nthread_file = len(self._file_thread_ids)
-            fields, uo, bad = kernels.vdif_scan(
+            # with verify, every set must also carry the frame index its
+            # position implies: checked inside the scan kernel
+            check = ((frame0, h0['seconds'], h0['frame_nr'],
+                      int(round(self._frame_rate))) if self.verify else None)
+            _, uo, _ = kernels.vdif_scan(
                 raw, nframe * nthread_file, h0.frame_nbytes, h0.nbytes,
-                nthread_file, self._slots_dev, len(self._decode_ids))
-            if self.verify:
-                # every set must carry the frame index its position implies
-                sec = fields[kernels.VDIF_SECONDS].view(
-                    nframe, nthread_file)[:, 0]
-                fnr = fields[kernels.VDIF_FRAME_NR].view(
-                    nframe, nthread_file)[:, 0]
-                fps = int(round(self._frame_rate))
-                index = ((sec.to(torch.int64) - h0['seconds']) * fps
-                         + fnr.to(torch.int64) - h0['frame_nr'])
-                want = torch.arange(frame0, frame0 + nframe, device=dev)
-                bad = bad + (index != want).sum().to(torch.int32)
-            self._checks.append(bad)
+                nthread_file, self._slots_dev, len(self._decode_ids),
+                check=check, bad=self._bad_counter(dev), want_fields=False)
         kernels.decode_bitfield(
             raw, uo, nframe, len(self._decode_ids), h0.payload_nbytes,
             h0.bps, nelem, self._complex_data, self._codec[0],
@@ -344,27 +336,23 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         self._set_index_table(table, h0.frame_nbytes)
 
     def read(self, count=None, out=None, **kwargs):
-        self._checks = []
         offset = self.offset
         result = super().read(count, out, **kwargs)
-        if self._checks:
-            nbad = int(torch.stack([c.reshape(()) for c in self._checks])
-                       .sum().item())
-            if nbad:
-                if not self.verify:
-                    raise OSError(
-                        'VDIF stream is not a regular sequence of complete '
-                        'frame sets ({} inconsistent frames) and verify is '
-                        'off.'.format(nbad))
-                import warnings
-                warnings.warn('VDIF stream has missing or out-of-order '
-                              'frames; indexing all headers and filling the '
-                              'gaps with fill_value.')
-                self._build_index()
-                self.offset = offset
-                self._checks = []
-                n = result.shape[0]
-                return super().read(n, out if out is not None else None, **kwargs)
+        nbad = self._new_inconsistencies() if self._index is None else 0
+        if nbad:
+            if not self.verify:
+                raise OSError(
+                    'VDIF stream is not a regular sequence of complete '
+                    'frame sets ({} inconsistent frames) and verify is '
+                    'off.'.format(nbad))
+            import warnings
+            warnings.warn('VDIF stream has missing or out-of-order '
+                          'frames; indexing all headers and filling the '
+                          'gaps with fill_value.')
+            self._build_index()
+            self.offset = offset
+            n = result.shape[0]
+            return super().read(n, out if out is not None else None, **kwargs)
         return result
 
 

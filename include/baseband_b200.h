@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 
 typedef enum bb_status {
     BB_OK = 0,
@@ -212,8 +212,18 @@ int bb_encode_int8_timefirst(const void *in, int32_t in_dtype, void *dst,
  * unit_offset[set*nthread + slot] = payload offset, or -1 if invalid_data
  * (baseband/vdif/frame.py:79-90).  *n_inconsistent (device int32) counts
  * frames whose frame_nr differs from the first frame of their set or
- * whose slot is duplicated, so the host can fall back to its recovery path
- * (baseband/vdif/base.py:536-755, out of scope here). */
+ * whose slot is duplicated or missing, so the host can fall back to its
+ * frame index (baseband/vdif/base.py:536-755).  The counter ACCUMULATES over
+ * calls (the caller zeroes it), so one read needs one look at it.
+ * Frame-index check (`VDIFStreamBase._get_index`,
+ * baseband/vdif/base.py:386-390; the read-ahead verification of
+ * baseband/base/base.py:1083-1125): with frames_per_second > 0 the first
+ * frame of set s must satisfy
+ *   (seconds - seconds0) * frames_per_second + frame_nr - frame_nr0
+ *       == index0 + s
+ * (seconds0 / frame_nr0 = fields of the stream's first header, index0 = frame
+ * index of the first set handed in), else it is counted as inconsistent.
+ * `fields` may be NULL when only the unit table is wanted. */
 typedef enum bb_vdif_field {
     BB_VDIF_INVALID = 0, BB_VDIF_LEGACY, BB_VDIF_SECONDS, BB_VDIF_REF_EPOCH,
     BB_VDIF_FRAME_NR, BB_VDIF_VERSION, BB_VDIF_LG2_NCHAN,
@@ -225,12 +235,21 @@ int bb_vdif_scan(const void *src, const int64_t *frame_offset,
                  int64_t frame_stride, int64_t nframe, int32_t header_nbytes,
                  int32_t frames_per_set, int32_t nthread,
                  const int32_t *thread_slot, int32_t *fields,
-                 int64_t *unit_offset, int32_t *n_inconsistent, void *stream);
+                 int64_t *unit_offset, int32_t *n_inconsistent,
+                 int64_t index0, int32_t seconds0, int32_t frame_nr0,
+                 int32_t frames_per_second, void *stream);
 
 /* Mark 5B: header fields (baseband/mark5b/header.py:60-68), BCD decode
  * (baseband/base/utils.py:18-34, header.py:192-233 incl. the 156250 ns
  * "unrounding") and payload validity = not all 2500 words equal 0x11223344
- * (baseband/mark5b/frame.py:62-72).  unit_offset[i] = payload offset or -1. */
+ * (baseband/mark5b/frame.py:62-72).  unit_offset[i] = payload offset or -1.
+ * Frame-index check (`Mark5BStreamBase._get_index`,
+ * baseband/mark5b/base.py:206-213): with frames_per_second > 0 and
+ * n_inconsistent non-NULL, frame i is counted in *n_inconsistent (accumulating
+ * device int32) unless its sync word is 0xABADDEED, its BCD time is valid and
+ *   (seconds - seconds0 + 86400 * dday) * frames_per_second
+ *       + frame_nr - frame_nr0 == index0 + i,
+ * dday = jday - jday0 wrapped into [-500, 500).  `fields` may be NULL. */
 typedef enum bb_mark5b_field {
     BB_M5B_SYNC = 0, BB_M5B_USER, BB_M5B_INTERNAL_TVG, BB_M5B_FRAME_NR,
     BB_M5B_BCD_JDAY, BB_M5B_BCD_SECONDS, BB_M5B_BCD_FRACTION, BB_M5B_CRC,
@@ -239,16 +258,27 @@ typedef enum bb_mark5b_field {
 } bb_mark5b_field;
 int bb_mark5b_scan(const void *src, const int64_t *frame_offset,
                    int64_t frame_stride, int64_t nframe, int32_t *fields,
-                   int64_t *unit_offset, void *stream);
+                   int64_t *unit_offset, int32_t *n_inconsistent,
+                   int64_t index0, int32_t jday0, int32_t seconds0,
+                   int32_t frame_nr0, int32_t frames_per_second,
+                   void *stream);
 
 /* Mark 4: track-header bit transpose (`stream2words`,
  * baseband/mark4/header.py:47-63) for one chosen track -> 5 words per frame
  * in words5[i*5 + w], and frame validity = no error flag on any track
- * (baseband/mark4/frame.py:78-87).  unit_offset[i] = payload offset or -1. */
+ * (baseband/mark4/frame.py:78-87).  unit_offset[i] = payload offset or -1.
+ * Frame-index check (the time-based `_get_index` of
+ * baseband/base/base.py:497-502 on the BCD time code,
+ * baseband/mark4/header.py:223-262): with tick_step > 0 and n_inconsistent
+ * non-NULL, frame i is counted in *n_inconsistent (accumulating) unless the
+ * time code of `track` (unit year, day of year, h, m, s, ms) is that of
+ * tick0 + tick_step * (index0 + i) quarter-milliseconds after 00:00 of MJD
+ * mjd0.  `words5` may be NULL. */
 int bb_mark4_scan(const void *src, const int64_t *frame_offset,
                   int64_t frame_stride, int64_t nframe, int32_t ntrack,
                   int32_t track, uint32_t *words5, int64_t *unit_offset,
-                  void *stream);
+                  int32_t *n_inconsistent, int64_t index0, int32_t mjd0,
+                  int64_t tick0, int64_t tick_step, void *stream);
 
 /* ------------------------------------------------------ bandwidth probes
  * Not part of the reference's path: the ceilings bench.py quotes next to the

@@ -63,7 +63,7 @@ int main(int argc, char **argv) {
     p_bb_memset(d_bad, 0, 4, stream);
     p_bb_memset(d_back, 0, (int64_t)NFRAME * FRAME, stream);
     int rc = p_bb_vdif_scan(d_raw, NULL, FRAME, NFRAME, HDR, NTHREAD, NTHREAD,
-                            d_slot, d_fields, d_uo, d_bad, stream);
+                            d_slot, d_fields, d_uo, d_bad, 0, 0, 0, 0, stream);
     if (rc) { fprintf(stderr, "scan: %s\n", p_bb_last_error()); return 7; }
     rc = p_bb_decode_bitfield(d_raw, d_uo, NSET, NTHREAD, PAYLOAD, 2, 1, 0,
                               BB_CODEC_LEVELS, levels, -9.f, 0, NSAMPLE,

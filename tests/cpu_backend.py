@@ -49,13 +49,15 @@ class _NoStreams:
 
 
 def _vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
-               thread_slot, nthread, frame_offset=None):
+               thread_slot, nthread, frame_offset=None, check=None, bad=None,
+               want_fields=True):
     from baseband_b200 import kernels
     buf = src.numpy()
     fields = np.zeros((kernels.VDIF_NFIELD, nframe), np.int32)
     nset = nframe // frames_per_set
     uo = np.full(max(nset * nthread, 1), -2, np.int64)
     slots = thread_slot.numpy()
+    counter = bad if bad is not None else torch.zeros(1, dtype=torch.int32)
     bad = 0
     names = ['invalid_data', 'legacy_mode', 'seconds', 'ref_epoch',
              'frame_nr', 'vdif_version', 'lg2_nchan', 'frame_length',
@@ -76,6 +78,11 @@ def _vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
             continue
         if i % frames_per_set == 0:
             first = fields[4, i]
+            if check is not None and check[3] > 0:
+                index0, seconds0, frame_nr0, fps = check
+                index = ((int(fields[2, i]) - seconds0) * fps
+                         + int(fields[4, i]) - frame_nr0)
+                bad += index != index0 + s
         elif fields[4, i] != first:
             bad += 1
         slot = slots[fields[10, i]]
@@ -86,11 +93,13 @@ def _vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,
     missing = uo[:nset * nthread] == -2
     bad += int(missing.sum())
     uo[:nset * nthread][missing] = -1
-    return (torch.from_numpy(fields), torch.from_numpy(uo[:nset * nthread]),
-            torch.tensor([bad], dtype=torch.int32))
+    counter += int(bad)
+    return (torch.from_numpy(fields) if want_fields else None,
+            torch.from_numpy(uo[:nset * nthread]), counter)
 
 
-def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
+def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None,
+                 check=None, bad=None, want_fields=True):
     from baseband_b200 import kernels
     buf = src.numpy()
     fields = np.zeros((kernels.M5B_NFIELD, nframe), np.int32)
@@ -106,11 +115,39 @@ def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None):
                h['jday'], h['seconds'], h['fraction_ns'], int(valid)]
         fields[:, i] = np.array(row, np.int64).astype(np.uint32).view(np.int32)
         uo[i] = off + 16 if valid else -1
-    return torch.from_numpy(fields), torch.from_numpy(uo)
+        if check is not None and check[4] > 0:
+            index0, jday0, seconds0, frame_nr0, fps = check
+            dday = (h['jday'] - jday0 + 1500) % 1000 - 500
+            index = ((h['seconds'] - seconds0 + 86400 * dday) * fps
+                     + h['frame_nr'] - frame_nr0)
+            if (h['sync_pattern'] != 0xABADDEED or h['jday'] < 0
+                    or h['seconds'] < 0 or index != index0 + i):
+                bad += 1
+    return (torch.from_numpy(fields) if want_fields else None,
+            torch.from_numpy(uo))
+
+
+def _mark4_time_words(mjd0, ticks):
+    """Time-code words 3 and 4 (CRC bits zero) at ``ticks`` quarter
+    milliseconds after 00:00 of MJD mjd0: restates mark4_time_words of
+    csrc/bb_scan.cu with the datetime module."""
+    import datetime
+    day, tick = divmod(int(ticks), 86400 * 4000)
+    date = datetime.date(1858, 11, 17) + datetime.timedelta(int(mjd0) + day)
+    yday = date.timetuple().tm_yday
+    sec, qms = divmod(tick, 4000)
+
+    def bcd(v):
+        return ((v // 100) << 8) | ((v // 10 % 10) << 4) | (v % 10)
+
+    w3 = ((date.year % 10) << 28) | (bcd(yday) << 16) \
+        | (bcd(sec // 3600) << 8) | bcd(sec // 60 % 60)
+    w4 = (bcd(sec % 60) << 24) | (bcd(qms // 4) << 12)
+    return w3, w4
 
 
 def _mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
-                frame_offset=None):
+                frame_offset=None, check=None, bad=None, want_words=True):
     buf = src.numpy()
     dtype = {16: '<u2', 32: '<u4', 64: '<u8'}[ntrack]
     if frame_stride is None:
@@ -124,7 +161,14 @@ def _mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
         h = oheaders.mark4_parse(stream)
         words5[i] = oheaders.mark4_stream2words(stream)[:, track]
         uo[i] = off + ntrack * 20 if h['valid'] else -1
-    return torch.from_numpy(words5.view(np.int32)), torch.from_numpy(uo)
+        if check is not None and check[3] > 0:
+            index0, mjd0, tick0, tick_step = check
+            w3, w4 = _mark4_time_words(mjd0, tick0 + tick_step * (index0 + i))
+            if int(words5[i, 3]) != w3 \
+                    or (int(words5[i, 4]) & 0xfffff000) != w4:
+                bad += 1
+    return (torch.from_numpy(words5.view(np.int32)) if want_words else None,
+            torch.from_numpy(uo))
 
 
 def install(monkeypatch):
@@ -161,6 +205,9 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'vdif_scan', _vdif_scan)
     monkeypatch.setattr(kernels, 'mark5b_scan', _mark5b_scan)
     monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
+    monkeypatch.setattr(
+        kernels, 'new_counter',
+        lambda dev: torch.zeros(1, dtype=torch.int32))
     monkeypatch.setattr(kernels, '_on', lambda d: contextlib.nullcontext())
     monkeypatch.setattr(device, 'is_device_tensor',
                         lambda t: isinstance(t, torch.Tensor))

@@ -406,6 +406,43 @@ def mark4_synthetic_and_write():
     assert got.size == 2 * 160000
 
 
+def mark4_time_code_rollover():
+    """Streams written across a year end and across 29 February are read
+    back with verify: the time code the scan kernel computes for every frame
+    position (year digit, day of year, h:m:s.ms) must be the one the writer
+    generated (mark4/header.py:223-262)."""
+    rng = np.random.default_rng(5)
+    for start, decade, stop in (
+            ('2020-12-31T23:59:59.9900', 2020, '2021-01-01T00:00:00.01'),
+            ('2020-02-28T23:59:59.9875', 2020, '2020-02-29T00:00:00.0075'),
+            ('2019-02-28T23:59:59.9950', 2010, '2019-03-01T00:00:00.0150'),
+            ('2099-12-31T23:59:59.9900', 2090, '2100-01-01T00:00:00.01')):
+        h0 = bb.mark4.Mark4Header.fromvalues(
+            32, time=start, bps=2, fanout=4, nsb=1, system_id=108)
+        data = rng.choice(np.array([-3.316505, -1., 1., 3.316505],
+                                   np.float32), size=(8 * 80000, 4))
+        buf = io.BytesIO()
+        fw = bb.mark4.open(buf, 'ws', header0=h0, sample_rate=32e6)
+        fw.write(data)
+        raw = np.frombuffer(buf.getvalue(), np.uint8)
+        want = ostream.mark4_read(raw, 32)
+        with bb.mark4.open(io.BytesIO(raw.tobytes()), 'rs', ntrack=32,
+                           decade=decade, chunk_nbytes=3 * 80000) as fh:
+            assert fh.stop_time.isot.startswith(stop), fh.stop_time.isot
+            _same(fh.read(), want)
+        # a frame out of place is caught by the same check
+        frames = raw.reshape(8, -1).copy()
+        frames[[5, 6]] = frames[[6, 5]]
+        try:
+            with bb.mark4.open(io.BytesIO(frames.tobytes()), 'rs', ntrack=32,
+                               decade=decade) as fh:
+                fh.read()
+        except OSError:
+            pass
+        else:
+            raise AssertionError('swapped frames not detected')
+
+
 # ------------------------------------------------------------------ GUPPI
 def _guppi_expected(frames, overlap, start, count):
     """Reference read loop on per-frame decoded arrays (full length incl.

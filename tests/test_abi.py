@@ -24,7 +24,7 @@ def test_library_exports_everything():
     lib = _lib.load()          # raises ImportError listing missing symbols
     for name in declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.bb_abi_version() == 1
+    assert lib.bb_abi_version() == 2
     assert lib.bb_device_count() >= 0
     assert isinstance(lib.bb_last_error(), bytes)
 

@@ -73,8 +73,9 @@ def test_shard_bounds():
 
 
 @pytest.mark.timeout(300)
-def test_world_size_2_gloo():
-    world = 2
+@pytest.mark.parametrize('world', [2, 3])
+def test_world_size_n_gloo(world):
+    # world 3 over 7 frame sets: gathered blocks of 3, 3 and 1 sets
     port = _free_port()
     ctx = mp.get_context('spawn')
     with ctx.Manager() as manager:
@@ -88,5 +89,6 @@ def test_world_size_2_gloo():
         assert all(p.exitcode == 0 for p in procs), [p.exitcode
                                                      for p in procs]
         out = dict(results)
-    assert out[0][0] and out[1][0]
-    assert out[0][2] == out[1][1]              # contiguous shards
+    assert all(out[r][0] for r in range(world))
+    assert all(out[r][2] == out[r + 1][1]      # contiguous shards
+               for r in range(world - 1))

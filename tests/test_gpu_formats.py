@@ -223,6 +223,70 @@ def test_mark5b_scan_sample(sample_outputs):
                           stream.mark5b_read(raw, 8, fill_value=-999.))
 
 
+def test_scan_index_checks(sample_outputs):
+    """Frame-index checks folded into the scan kernels == the reference's
+    `_get_index` arithmetic (vdif/base.py:386-390, mark5b/base.py:206-213)
+    applied by the oracle to every header."""
+    # VDIF: sample.vdif has 2 frame sets of 8 threads, frame_nr 0 and 1
+    raw = sample_bytes('sample.vdif')
+    f = sample_outputs['sample_vdif_fields']
+    sec0, fnr0 = int(f[0, 2]), int(f[0, 4])
+    slot = torch.full((1024,), -1, dtype=torch.int32, device=DEV)
+    slot[:8] = torch.arange(8, dtype=torch.int32)
+    bad = kernels.new_counter(DEV)
+    fields, _, _ = kernels.vdif_scan(_t(raw), 16, 5032, 32, 8, slot, 8,
+                                     check=(0, sec0, fnr0, 1600), bad=bad,
+                                     want_fields=False)
+    assert fields is None and int(bad.item()) == 0
+    # the counter accumulates: a wrong expected position flags both sets
+    kernels.vdif_scan(_t(raw), 16, 5032, 32, 8, slot, 8,
+                      check=(5, sec0, fnr0, 1600), bad=bad)
+    assert int(bad.item()) == 2
+    # second set one second later but same frame_nr: index = fps + 0, not 1
+    raw2 = raw.copy()
+    w = raw2[8 * 5032:].view('<u4')
+    for k in range(8):
+        w[k * 1258] += 1                        # seconds of set 1
+        w[k * 1258 + 1] -= 1                    # frame_nr 1 -> 0
+    bad2 = kernels.new_counter(DEV)
+    kernels.vdif_scan(_t(raw2), 16, 5032, 32, 8, slot, 8,
+                      check=(0, sec0, fnr0, 1600), bad=bad2)
+    assert int(bad2.item()) == 1
+    kernels.vdif_scan(_t(raw2), 16, 5032, 32, 8, slot, 8,
+                      check=(0, sec0, fnr0, 1), bad=bad2)   # 1 frame / s: ok
+    assert int(bad2.item()) == 1
+    # Mark 5B: sample.m5b, frames in sequence
+    raw = sample_bytes('sample.m5b')
+    hd = headers.mark5b_parse_batch(raw, 4)
+    jd0, s0, n0 = int(hd['jday'][0]), int(hd['seconds'][0]), \
+        int(hd['frame_nr'][0])
+    bad = kernels.new_counter(DEV)
+    kernels.mark5b_scan(_t(raw), 4, check=(0, jd0, s0, n0, 6400), bad=bad,
+                        want_fields=False)
+    assert int(bad.item()) == 0
+    raw2 = raw.copy()
+    raw2[2 * 10016:2 * 10016 + 4] = 0            # sync word of frame 2 gone
+    raw2[3 * 10016 + 4] ^= 2                     # frame_nr of frame 3 differs
+    kernels.mark5b_scan(_t(raw2), 4, check=(0, jd0, s0, n0, 6400), bad=bad)
+    assert int(bad.item()) == 2
+    # jday wraps modulo 1000: header0 at day 999, frames at day 0
+    kernels.mark5b_scan(_t(raw), 4, check=(
+        -86400 * 6400, (jd0 - 1) % 1000, s0, n0, 6400), bad=bad)
+    assert int(bad.item()) == 2
+    # Mark 4: sample.m4 (2014-06-16T07:38:12.47500, 2.5 ms per frame)
+    raw = sample_bytes('sample.m4')[0xa88:][:2 * 160000]
+    tick0 = ((7 * 60 + 38) * 60 + 12) * 4000 + 1900
+    bad = kernels.new_counter(DEV)
+    words5, uo = kernels.mark4_scan(_t(raw), 2, 64, check=(0, 56824, tick0, 10),
+                                    bad=bad, want_words=False)
+    assert words5 is None and int(bad.item()) == 0
+    kernels.mark4_scan(_t(raw), 2, 64, check=(1, 56824, tick0, 10), bad=bad)
+    assert int(bad.item()) == 2
+    kernels.mark4_scan(_t(raw), 2, 64, check=(0, 56824 - 365, tick0, 10),
+                       bad=bad)                  # a year earlier: year digit
+    assert int(bad.item()) == 4
+
+
 def test_fuzz_int8_transposed():
     for case in int8_cases.fuzz_cases(150, seed=78):
         test_int8_transposed(case)

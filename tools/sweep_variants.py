@@ -59,6 +59,7 @@ def report(name, nbytes, fn, seconds):
 def main():
     gib = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     seconds = float(sys.argv[2]) if len(sys.argv) > 2 else 1.5
+    quick = len(sys.argv) > 3 and sys.argv[3] == 'knock' 
     print(torch.cuda.get_device_name(0), 'chunk %.2f GiB packed' % gib)
     n = int(16 * gib * 2**30)
     a = torch.empty(n, dtype=torch.uint8, device=DEV)
@@ -91,7 +92,7 @@ def main():
         lv = levels.offset_binary(2)
         nbytes = nunit * frame + out.numel() * 4
         ref = None
-        for c2 in (0, 1, 2, 3, 4, 5):
+        for c2 in ((0, 1) if quick else (0, 1, 2, 3, 4, 5)):
             for tu in ((1,) if c2 < 2 else (1, 2)):
                 os.environ['BB_TUNE_C2'] = str(c2)
                 os.environ['BB_TUNE_TILE_U'] = str(tu)
@@ -125,11 +126,28 @@ def main():
                                         lv, out=out)
             report('%s DEC input aliased to %d sets (L2 hits)'
                    % (name, alias), nbytes, fn_alias, seconds)
+        # knock-outs: which part of the kernel costs the gap to the fill rate
+        for c2 in (0, 1):
+            for knock in (1, 2):
+                os.environ['BB_TUNE_C2'] = str(c2)
+                os.environ['BB_TUNE_KNOCK'] = str(knock)
+
+                def fn_k():
+                    kernels.decode_bitfield(raw, off, nset, nthread, payload,
+                                            2, nelem, cplx,
+                                            kernels.CODEC_LEVELS, lv, out=out)
+                report('%s DEC C2=%d knock-out %d (%s)' % (
+                    name, c2, knock, 'no payload loads' if knock == 1
+                    else 'no loads at all'), nbytes, fn_k, seconds)
+        os.environ['BB_TUNE_C2'] = '0'
+        os.environ['BB_TUNE_KNOCK'] = '0'
         del raw, out, ref
         torch.cuda.empty_cache()
 
     # ---- Mark 4: 64 tracks (C3) and 32 tracks, fan-out 4
     lv4 = levels.sign_magnitude()
+    if quick:
+        return
     for name, nchan in (('C3 mark4 64 trk', 8), ('mark4 32 trk', 4)):
         fbytes = nchan * 20000
         nframe = max(1, int(gib * 2**30) // fbytes)
