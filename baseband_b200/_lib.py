@@ -77,8 +77,13 @@ SIGNATURES = {
     'bb_mark4_scan': (c_int, [
         _pv, _pi64, c_int64, c_int64, c_int32, c_int32, _pv, _pi64, _pv,
         c_int64, c_int32, c_int64, c_int64, c_void_p]),
+    'bb_frames_assemble': (c_int, [
+        _pv, c_int64, c_int64, c_int32, _pv, _pv, c_uint32, c_int64, c_int32,
+        c_int64, _pi64, c_void_p]),
     'bb_probe_fill': (c_int, [_pv, c_int64, c_int32, c_void_p]),
     'bb_probe_copy': (c_int, [_pv, _pv, c_int64, c_void_p]),
+    'bb_probe_expand': (c_int, [_pv, c_int64, _pv, c_int32, c_void_p]),
+    'bb_probe_prefetch': (c_int, [_pv, c_int64, c_void_p]),
 }
 
 # every symbol include/baseband_b200.h declares

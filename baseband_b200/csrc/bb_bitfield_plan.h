@@ -101,7 +101,12 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     int mode = pick_mode(nelem, nthread, aligned_rows, true);
     // rows of four float4 (the C2 shape): BB_TUNE_C2 = 0 ROWGROUP + table,
     // 1 ROWGROUP + select, 2/3 TILE (8 positions) table/select, 4/5 TILE (4)
-    const int c2 = tune("BB_TUNE_C2", 0);
+    // Per-mode default (profiles/r2_sweep_variants.txt): four real threads
+    // per float4 (ROWGROUP4) select the levels in registers -- 32 registers,
+    // 8 CTAs per SM, no shared-memory lookups; same burst rate as the table
+    // but it holds it in long runs (6.75 vs 6.57 TB/s sustained); the complex
+    // pairs of ROWGROUP2 stay with the pair table (6.78 vs 6.74).
+    const int c2 = tune("BB_TUNE_C2", mode == MODE_ROWGROUP4 ? 1 : 0);
     int sel = 0, tile_p = 8;
     const int tile_u = tune("BB_TUNE_TILE_U", 1) >= 2 ? 2 : 1;
     if (bps == 2 && (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2)) {

@@ -53,9 +53,110 @@ k_probe_copy(float4 *dst, const float4 *src, unsigned long long n4) {
     }
 }
 
+// 1:16 expansion (2 bit -> float32) with ideal access patterns and no
+// arithmetic to speak of: the ceiling for a stream that reads one byte for
+// every sixteen it writes.  A warp reads 256 contiguous bytes (pattern 0) or
+// -- pattern 1, the shape of 16 interleaved VDIF threads -- 16 pieces of 16
+// bytes from 16 streams `stream_stride` bytes apart, and writes 4 KiB
+// contiguous, 512 bytes per store instruction.  Pattern 2 = pattern 0 with
+// the input wrapped to one MiB (always an L2 hit: no DRAM reads at all).
+template <int PATTERN>
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_expand(float4 *dst, const uint32_t *src, unsigned long long n4,
+               unsigned long long stream_stride_words) {
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned long long chunk =
+        (unsigned long long)blockIdx.x * (kProbeBlock / 32) + warp;
+    const unsigned long long base = chunk * (32 * kProbeF4);
+    if (base >= n4) return;
+    uint32_t w0, w1;
+    if (PATTERN == 0 || PATTERN == 2) {
+        // pattern 2: the input wraps every MiB, i.e. it stays in L2
+        const unsigned long long at = chunk * 32 + lane;
+        const uint2 v = reinterpret_cast<const uint2 *>(src)[
+            PATTERN == 2 ? (at & 0x1ffffull) : at];
+        w0 = v.x;
+        w1 = v.y;
+    } else {
+        // chunk = 4 word positions x 16 streams; lane -> (stream pair, word)
+        const unsigned long long k = chunk * 4 + (lane & 3u);
+        const unsigned st = (lane >> 2) * 2;
+        w0 = src[st * stream_stride_words + k];
+        w1 = src[(st + 1) * stream_stride_words + k];
+    }
+#pragma unroll
+    for (int j = 0; j < kProbeF4; ++j) {
+        const unsigned long long i = base + j * 32 + lane;
+        const uint32_t a = (j & 1 ? w1 : w0) >> (8 * (j >> 1));
+        const float4 v = make_float4(__uint_as_float(0x3f800000u | (a & 3u)),
+                                     __uint_as_float(0x3f800000u | (a & 12u)),
+                                     __uint_as_float(0x3f800000u | (a & 48u)),
+                                     __uint_as_float(0x3f800000u | (a & 192u)));
+        if (i < n4) dst[i] = v;
+    }
+}
+
+// Pull `nbytes` of src into L2 with evict_last priority (a pure-read phase
+// ahead of a kernel that then finds its input in L2).
+__global__ void __launch_bounds__(256)
+k_probe_prefetch(const uint8_t *src, unsigned long long nbytes) {
+    const unsigned long long stride = (unsigned long long)gridDim.x * 256 * 128;
+    for (unsigned long long at = ((unsigned long long)blockIdx.x * 256
+                                  + threadIdx.x) * 128;
+         at < nbytes; at += stride)
+        asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(src + at));
+}
+
 }  // namespace bb
 
 using namespace bb;
+
+extern "C" int bb_probe_prefetch(const void *src, int64_t nbytes,
+                                 void *stream) {
+    if (!src || nbytes < 0) return set_error(BB_ERR_ARGUMENT, "bad arguments");
+    if (nbytes == 0) return BB_OK;
+    const unsigned long long lines = ((unsigned long long)nbytes + 127) / 128;
+    unsigned long long grid = (lines + 255) / 256;
+    const unsigned long long cap = (unsigned long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    k_probe_prefetch<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(
+        (const uint8_t *)src, (unsigned long long)nbytes);
+    BB_CHECK_LAUNCH("bb_probe_prefetch");
+    return BB_OK;
+}
+
+
+extern "C" int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
+                               int32_t pattern, void *stream) {
+    if (!dst || !src || nbytes < 0 || (nbytes & 4095) || !aligned(dst, 16)
+        || !aligned(src, 8))
+        return set_error(BB_ERR_ARGUMENT,
+                         "dst 16-byte, src 8-byte aligned, nbytes a multiple "
+                         "of 4096");
+    if (nbytes == 0) return BB_OK;
+    const unsigned long long n4 = (unsigned long long)nbytes / 16;
+    const unsigned long long per = kProbeBlock * kProbeF4;
+    const unsigned long long grid = (n4 + per - 1) / per;
+    if (grid > 0x7fffffffull)
+        return set_error(BB_ERR_ARGUMENT, "buffer too large for one launch");
+    // pattern 1: 16 streams of nbytes / 16 / 16 bytes each
+    const unsigned long long stride_words = (unsigned long long)nbytes / 1024;
+    if (pattern == 1)
+        k_probe_expand<1><<<(unsigned)grid, kProbeBlock, 0,
+                            as_stream(stream)>>>(
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+    else if (pattern == 2)
+        k_probe_expand<2><<<(unsigned)grid, kProbeBlock, 0,
+                            as_stream(stream)>>>(
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+    else
+        k_probe_expand<0><<<(unsigned)grid, kProbeBlock, 0,
+                            as_stream(stream)>>>(
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+    BB_CHECK_LAUNCH("bb_probe_expand");
+    return BB_OK;
+}
+
 
 extern "C" int bb_probe_fill(void *dst, int64_t nbytes, int32_t pattern,
                              void *stream) {

@@ -260,6 +260,46 @@ k_mark4_scan(const uint8_t *src, const long long *frame_offset,
         unit_offset[i] = bad ? -1 : off + (long long)sizeof(W) * 160;
 }
 
+
+// ---------------------------------------------------------------- writers
+// Frame assembly for the stream writers: one warp per frame copies the
+// frame's header (built on the host, a few bytes per frame) to the head of
+// the frame, writes the unit-offset entries the encode kernel takes, and --
+// where the format marks invalid frames by a payload pattern (Mark 5B,
+// baseband/mark5b/frame.py:126-133) -- fills the payload of those frames and
+// takes them out of the encode (-1).
+__global__ void __launch_bounds__(kScanBlock)
+k_frames_assemble(uint8_t *dst, long long nframe, long long frame_stride,
+                  int header_nbytes, const uint8_t *headers,
+                  const uint8_t *valid, uint32_t fill_word,
+                  long long payload_nbytes, int units_per_frame,
+                  long long unit_stride, long long *unit_offset) {
+    const int lane = threadIdx.x & 31;
+    const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nframe) return;                     // warp-uniform
+    uint8_t *frame = dst + i * frame_stride;
+    const uint8_t *h = headers + i * (long long)header_nbytes;
+    if ((header_nbytes & 3) == 0
+        && ((reinterpret_cast<uintptr_t>(frame)
+             | reinterpret_cast<uintptr_t>(h)) & 3) == 0) {
+        const uint32_t *hs = reinterpret_cast<const uint32_t *>(h);
+        uint32_t *hd = reinterpret_cast<uint32_t *>(frame);
+        for (int k = lane; k < header_nbytes / 4; k += 32) hd[k] = hs[k];
+    } else {
+        for (int k = lane; k < header_nbytes; k += 32) frame[k] = h[k];
+    }
+    const bool ok = !valid || valid[i];
+    if (unit_offset)
+        for (int u = lane; u < units_per_frame; u += 32)
+            unit_offset[i * units_per_frame + u] = ok
+                ? i * frame_stride + header_nbytes + u * unit_stride : -1;
+    if (!ok) {
+        uint32_t *pl = reinterpret_cast<uint32_t *>(frame + header_nbytes);
+        for (long long k = lane; k < payload_nbytes / 4; k += 32)
+            pl[k] = fill_word;
+    }
+}
+
 }  // namespace bb
 
 using namespace bb;
@@ -352,5 +392,30 @@ extern "C" int bb_mark4_scan(
             p, fo, frame_stride, nframe, track, words5, (long long *)unit_offset,
             n_inconsistent, index0, mjd0, tick0, tick_step);
     BB_CHECK_LAUNCH("bb_mark4_scan");
+    return BB_OK;
+}
+
+extern "C" int bb_frames_assemble(
+    void *dst, int64_t nframe, int64_t frame_stride, int32_t header_nbytes,
+    const void *headers, const uint8_t *valid, uint32_t fill_word,
+    int64_t payload_nbytes, int32_t units_per_frame, int64_t unit_stride,
+    int64_t *unit_offset, void *stream) {
+    if (!dst || (!headers && header_nbytes > 0))
+        return set_error(BB_ERR_ARGUMENT, "null dst or headers");
+    if (nframe < 0 || header_nbytes < 0 || units_per_frame < 1
+        || frame_stride < header_nbytes)
+        return set_error(BB_ERR_ARGUMENT, "bad frame geometry");
+    if (valid && (!aligned(dst, 4) || (frame_stride & 3) || (header_nbytes & 3)
+                  || (payload_nbytes & 3)))
+        return set_error(BB_ERR_ALIGNMENT,
+                         "payload fill needs 4-byte aligned payloads");
+    if (nframe == 0) return BB_OK;
+    const long long nthr = (long long)nframe * 32;
+    k_frames_assemble<<<(unsigned)((nthr + kScanBlock - 1) / kScanBlock),
+                        kScanBlock, 0, as_stream(stream)>>>(
+        (uint8_t *)dst, nframe, frame_stride, header_nbytes,
+        (const uint8_t *)headers, valid, fill_word, payload_nbytes,
+        units_per_frame, unit_stride, (long long *)unit_offset);
+    BB_CHECK_LAUNCH("bb_frames_assemble");
     return BB_OK;
 }

@@ -183,8 +183,6 @@ class DADAStreamWriter(_DADAStreamBase, StreamWriterBase):
         if h0.bps != 8:
             raise ValueError('DADAPayload cannot encode data with {} bits'
                              .format(h0.bps))
-        frames = torch.empty((nframe, h0.frame_nbytes), dtype=torch.uint8,
-                             device=dev)
         texts = []
         for i in range(nframe):
             header = h0.copy()
@@ -193,22 +191,20 @@ class DADAStreamWriter(_DADAStreamBase, StreamWriterBase):
             with io.BytesIO() as s:
                 header.tofile(s)
                 texts.append(np.frombuffer(s.getvalue(), np.uint8))
-        frames[:, :h0.nbytes] = torch.from_numpy(np.stack(texts)).to(dev)
+        headers = torch.from_numpy(np.stack(texts)).to(dev)
         ib = 2 if h0.complex_data else 1
         nelem = h0['NPOL'] * h0['NCHAN'] * ib
         if h0.get('INSTRUMENT') == 'MKBF':
             heap_nbytes = nelem * HEAP
             per = h0.payload_nbytes // heap_nbytes
-            uo = ((torch.arange(nframe, dtype=torch.int64, device=dev)
-                   * h0.frame_nbytes + h0.nbytes)[:, None]
-                  + torch.arange(per, dtype=torch.int64, device=dev)
-                  * heap_nbytes).reshape(-1)
+            frames, uo = kernels.frames_assemble(
+                headers, h0.frame_nbytes, units_per_frame=per,
+                unit_stride=heap_nbytes)
             kernels.encode_int8_transposed(flat, frames.view(-1), uo,
                                            nframe * per,
                                            h0['NPOL'] * h0['NCHAN'], HEAP, ib)
         else:
-            uo = (torch.arange(nframe, dtype=torch.int64, device=dev)
-                  * h0.frame_nbytes + h0.nbytes)
+            frames, uo = kernels.frames_assemble(headers, h0.frame_nbytes)
             kernels.encode_bitfield(flat, frames.view(-1), uo, nframe, 1,
                                     h0.payload_nbytes, 8, nelem,
                                     kernels.QUANT_SINT)

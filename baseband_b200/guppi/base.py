@@ -155,8 +155,6 @@ class GUPPIStreamWriter(_GUPPIStreamBase, StreamWriterBase):
         h0 = self.header0
         dev = flat.device
         hdr_nbytes, frame_nbytes = h0.nbytes, h0.frame_nbytes
-        frames = torch.empty((nframe, frame_nbytes), dtype=torch.uint8,
-                             device=dev)
         texts = []
         for i in range(nframe):
             header = h0.copy()
@@ -165,9 +163,8 @@ class GUPPIStreamWriter(_GUPPIStreamBase, StreamWriterBase):
             raw = header.tostring().encode('ascii')
             texts.append(np.frombuffer(
                 raw + b'\0' * (hdr_nbytes - len(raw)), np.uint8))
-        frames[:, :hdr_nbytes] = torch.from_numpy(np.stack(texts)).to(dev)
-        uo = (torch.arange(nframe, dtype=torch.int64, device=dev)
-              * frame_nbytes + hdr_nbytes)
+        frames, uo = kernels.frames_assemble(
+            torch.from_numpy(np.stack(texts)).to(dev), frame_nbytes)
         spf, ib = self._samples_per_frame, 2 if h0.complex_data else 1
         if h0.bps != 8:
             raise ValueError('GUPPIPayload cannot encode data with {} bits'

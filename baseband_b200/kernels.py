@@ -375,6 +375,34 @@ def mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
     return words5, unit_offset
 
 
+def frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
+                    fill_word=0, units_per_frame=1, unit_stride=0):
+    """bb_frames_assemble -> (frames uint8 (nframe, frame_nbytes),
+    unit_offset int64 (nframe * units_per_frame,)).
+
+    ``headers``: uint8 CUDA tensor (nframe, header_nbytes), one header per
+    frame; ``valid``: optional uint8 CUDA tensor (nframe,), frames with 0 get
+    their payload filled with ``fill_word`` and unit offsets -1."""
+    lib = _lib.load()
+    dev = headers.device
+    nframe, header_nbytes = headers.shape
+    frames = torch.empty((nframe, frame_nbytes), dtype=torch.uint8,
+                         device=dev)
+    unit_offset = torch.empty((nframe * units_per_frame,), dtype=torch.int64,
+                              device=dev)
+    with _on(dev):
+        rc = lib.bb_frames_assemble(
+            _dev(frames, 'frames'), nframe, frame_nbytes, header_nbytes,
+            _dev(headers, 'headers', torch.uint8),
+            None if valid is None else _dev(valid, 'valid', torch.uint8),
+            int(fill_word), int(payload_nbytes), int(units_per_frame),
+            int(unit_stride), _dev(unit_offset, 'unit_offset'),
+            _stream_ptr(dev))
+    _lib.check(rc, lib)
+    _count()
+    return frames, unit_offset
+
+
 def probe_fill(dst, pattern=0):
     """bb_probe_fill: write the whole tensor ``dst`` with the decode kernels'
     launch shape (pure-write bandwidth probe)."""
@@ -400,3 +428,18 @@ def probe_copy(dst, src):
     _lib.check(rc, lib)
     _count()
     return dst
+
+
+def probe_expand(dst, src, pattern=0):
+    """bb_probe_expand: write all of ``dst`` from 1/16 as many bytes of
+    ``src`` (the ceiling for a 2 bit -> float32 stream)."""
+    lib = _lib.load()
+    nbytes = dst.numel() * dst.element_size() // 4096 * 4096
+    if src.numel() * src.element_size() < nbytes // 16:
+        raise ValueError('src too small')
+    with _on(dst.device):
+        rc = lib.bb_probe_expand(_dev(dst, 'dst'), nbytes, _dev(src, 'src'),
+                                 pattern, _stream_ptr(dst.device))
+    _lib.check(rc, lib)
+    _count()
+    return nbytes + nbytes // 16

@@ -264,12 +264,9 @@ class Mark4StreamWriter(StreamWriterBase):
         stream = words2stream(words)                     # (nframe, 160)
         crc = crc_of_bits(np.ascontiguousarray(stream[:, :-12].T), CRC12)
         stream[:, -12:] = crc.T
-        frames = torch.empty((nframe, h0.frame_nbytes), dtype=torch.uint8,
-                             device=dev)
-        frames[:, :h0.nbytes] = torch.from_numpy(
-            stream.view(np.uint8).reshape(nframe, h0.nbytes)).to(dev)
-        uo = (torch.arange(nframe, dtype=torch.int64, device=dev)
-              * h0.frame_nbytes + h0.nbytes)
+        frames, uo = kernels.frames_assemble(
+            torch.from_numpy(stream.view(np.uint8).reshape(
+                nframe, h0.nbytes)).to(dev), h0.frame_nbytes)
         kernels.mark4_encode(flat, frames.view(-1), uo, nframe, nchan, fanout,
                              ft)
         return frames.view(-1)

@@ -297,19 +297,16 @@ class Mark5BStreamWriter(_Mark5BStreamBase, StreamWriterBase):
         stream = (((bj << 20) | bs) << 16) | bf
         crc = crc_array(stream, 48, CRC16)
         words[:, 3] = ((bf << 16) | crc).astype(np.uint32)
-        frames = torch.empty((nframe, 10016), dtype=torch.uint8, device=dev)
-        frames[:, :16] = torch.from_numpy(words.view(np.uint8)).to(dev)
-        uo_host = np.arange(nframe, dtype=np.int64) * 10016 + 16
-        uo_host[~valid] = -1
-        kernels.encode_bitfield(flat, frames.view(-1),
-                                torch.from_numpy(uo_host).to(dev), nframe, 1,
+        # headers into place, unit offsets, and -- for invalid frames -- the
+        # fill pattern instead of an encoded payload (mark5b/frame.py:126-133)
+        # in one launch; the encode skips units at -1
+        frames, uo = kernels.frames_assemble(
+            torch.from_numpy(words.view(np.uint8)).to(dev), 10016, 10000,
+            valid=None if valid.all() else torch.from_numpy(
+                valid.astype(np.uint8)).to(dev), fill_word=FILL_PATTERN)
+        kernels.encode_bitfield(flat, frames.view(-1), uo, nframe, 1,
                                 10000, self._bps, self._sample_shape[0],
                                 kernels.QUANT_MARK5B)
-        if not valid.all():
-            # invalid frames carry the fill pattern (mark5b/frame.py:126-133)
-            fill = torch.from_numpy(np.full(2500, FILL_PATTERN, '<u4')
-                                    .view(np.uint8)).to(dev)
-            frames[torch.from_numpy(~valid).to(dev), 16:] = fill
         return frames.view(-1)
 
 

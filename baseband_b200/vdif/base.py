@@ -412,12 +412,10 @@ class VDIFStreamWriter(_VDIFStreamBase, StreamWriterBase):
                                                      & 0xffffffff))
                           | (tids[None, :] << np.uint32(16)))
         n = nframe * nthread
-        frames = torch.empty((n, h0.frame_nbytes), dtype=torch.uint8,
-                             device=dev)
-        frames[:, :h0.nbytes] = torch.from_numpy(
-            words.reshape(n, nw).view(np.uint8)).to(dev)
-        uo = (torch.arange(n, dtype=torch.int64, device=dev)
-              * h0.frame_nbytes + h0.nbytes)
+        # headers into place + unit offsets: one launch (bb_frames_assemble)
+        frames, uo = kernels.frames_assemble(
+            torch.from_numpy(words.reshape(n, nw)
+                             .view(np.uint8)).to(dev), h0.frame_nbytes)
         nelem = self._sample_shape[1] * (2 if self._complex_data else 1)
         kernels.encode_bitfield(flat, frames.view(-1), uo, nframe, nthread,
                                 h0.payload_nbytes, h0.bps, nelem,

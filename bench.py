@@ -251,10 +251,15 @@ def run_b200(args):
     back = torch.empty_like(raw)
     back.view(nframe, FRAME)[:, :32] = raw.view(nframe, FRAME)[:, :32]
     dec_events = []
+    passes = max(1, args.passes)
+    # frame-index check of the scan: the synthetic headers count 2000 frame
+    # sets per second from second 100 (synthetic.vdif_headers)
+    check = (first_set, 100, 0, 2000)
 
-    def step(record=False):
+    def one_pass(record=False):
         _, uo, bad = kernels.vdif_scan(raw, nframe, FRAME, 32, NTHREAD, slot,
-                                       NTHREAD)
+                                       NTHREAD, check=check, bad=counter,
+                                       want_fields=False)
         if record:
             e0 = torch.cuda.Event(enable_timing=True)
             e1 = torch.cuda.Event(enable_timing=True)
@@ -266,19 +271,27 @@ def run_b200(args):
             dec_events.append((e0, e1))
         kernels.encode_bitfield(out, back, uo, nset, NTHREAD, PAYLOAD, 2, 1,
                                 kernels.QUANT_OFFSET_BINARY)
-        return bad
+
+    def step(record=False):
+        # record one decode launch in four: 640 event pairs would do no harm,
+        # but the sustained figure needs no more
+        for k in range(passes):
+            one_pass(record and (k % 4 == 0))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        bad = step()
+    counter = kernels.new_counter(dev)
+    one_pass()
     torch.cuda.synchronize()
-    assert int(bad.item()) == 0
+    assert int(counter.item()) == 0
     if not torch.equal(back, raw):
         raise SystemExit('round trip mismatch: decode->encode must be exact')
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -295,43 +308,67 @@ def run_b200(args):
     elapsed_ms = t0.elapsed_time(t1)
     launches = kernels.launch_count - launches0
     clocks = sampler.stop() if rank == 0 else None
+    assert int(counter.item()) == 0
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
-    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+    dec_all = [a.elapsed_time(b) for a, b in dec_events]
+    dec_ms = sum(dec_all) / len(dec_all)          # sustained: mean over the run
+    dec_best_ms = min(dec_all)                    # burst: best single launch
+
+    # ------------------------------------------------ ceilings, same run
+    ceilings = measure_ceilings(dev, out, kernels)
 
     # ------------------------------------------------ end-to-end (host bufs)
     e2e = measure_e2e(args, dev, rank, world, lv, slot)
     del out, back, raw
     torch.cuda.empty_cache()
     named = measure_named_configs(args, dev, rank, world)
+    sharded = measure_sharded_read(args, dev, rank, world)
+    consumer = measure_consumer(args, dev, rank, world)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    samples_per_step = nset * SET_SAMPLES * world
+    samples_per_step = nset * SET_SAMPLES * world * passes
     value = samples_per_step * args.steps / (elapsed_ms * 1e-3) / 1e9
     peak, which = peaks()
     algo_bytes = nset * (SET_BYTES + SET_SAMPLES * 4)
     achieved = algo_bytes / (dec_ms * 1e-3) / 1e9
+    burst = algo_bytes / (dec_best_ms * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(DECODE_KERNEL, nset * SET_SAMPLES)
+    wp = ceilings['write_peak_sustained_gbs']
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': config_dict(chunk_bytes, world),
+        'data': 'synthetic',
+        'config': config_dict(chunk_bytes, world, passes),
+        'timed_region_s': elapsed_ms * 1e-3,
         'decode_only_gsamples_s': nset * SET_SAMPLES / (dec_ms * 1e-3) / 1e9,
         'roofline': {
-            'bound': 'hbm', 'kernel': 'k_decode_bitfield<2,LEVELS,ROWGROUP4>',
+            'bound': 'hbm', 'kernel': DECODE_KERNEL,
             'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-            'frac': achieved / peak, 'peak_source': which + ' copy bandwidth',
+            'frac': achieved / peak, 'peak_source': which + ' copy bandwidth '
+            '(MEASURED_PEAKS.json)',
+            'what': 'sustained: mean of {} decode launches spread over the '
+                    '{:.1f} s timed region'.format(len(dec_all),
+                                                   elapsed_ms * 1e-3),
+            'burst': {'achieved': burst, 'frac': burst / peak,
+                      'what': 'best single decode launch of the same run'},
+            'write_peak': wp, 'frac_of_write_peak': achieved / wp,
+            'frac_of_expand_ceiling': achieved
+            / ceilings['expand_1to16_sustained_gbs'],
+            'ceilings_in_run': ceilings,
             'algorithmic_bytes_per_sample': ALGO_BYTES_PER_SAMPLE,
-            'traffic': NCU_TRAFFIC_BYTES_PER_SAMPLE * nset * SET_SAMPLES
-            if NCU_TRAFFIC_BYTES_PER_SAMPLE else None},
+            'algorithmic_bytes_per_launch': algo_bytes,
+            'traffic': traffic, 'traffic_source': traffic_src},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-        'named_configs': named,
+        'named_configs': named, 'sharded_read': sharded,
+        'consumer': consumer,
         'host_binding': ('rank pinned to the {} CPUs local to its GPU'
                          .format(len(numa_cpus)) if numa_cpus else 'none'),
     }
@@ -342,10 +379,92 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-# dram bytes per decoded sample from the ncu --set full capture of the decode
-# kernel (profiles/r1_decode_c2_summary.txt: 537.5 MB read + 8.499 GB written
-# for 4177 frame sets): (read + write) / samples.
-NCU_TRAFFIC_BYTES_PER_SAMPLE = 4.2256
+DECODE_KERNEL = 'k_decode_bitfield<2,LEVELS,ROWGROUP4>'
+
+
+def measure_ceilings(dev, scratch, kernels, seconds=0.4):
+    """Pure-write and copy rates of this GPU, measured in this run with the
+    library's own probe kernels (full-grid st.global.v4 fill; ld/st.v4 copy)
+    on the decode output buffer: the ceilings the decode rate is quoted
+    against next to MEASURED_PEAKS.json's torch copy figure."""
+    import torch
+    flat = scratch.view(-1)
+    half = flat.numel() // 2
+    a, b = flat[:half], flat[half:2 * half]
+
+    def rate(fn, nbytes):
+        fn()
+        torch.cuda.synchronize(dev)
+        ev, t_end = [], time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            ev.append((e0, e1))
+            e1.synchronize()
+        ms = [x.elapsed_time(y) for x, y in ev]
+        return (nbytes / (sum(ms) / len(ms) * 1e-3) / 1e9,
+                nbytes / (min(ms) * 1e-3) / 1e9)
+
+    fill_s, fill_b = rate(lambda: kernels.probe_fill(flat, 1),
+                          flat.numel() * 4)
+    copy_s, copy_b = rate(lambda: kernels.probe_copy(a, b), 2 * half * 4)
+    # 1:16 expansion with ideal access patterns: the first 15/16 of the
+    # buffer written from the last 1/16 read (16 interleaved input streams,
+    # the shape of this workload)
+    n16 = flat.numel() * 4 // 17 // 4096 * 4096
+    src = flat[flat.numel() - n16 // 64:]
+    dst = flat[:n16 // 4]
+    exp_s, exp_b = rate(lambda: kernels.probe_expand(dst, src, 1),
+                        n16 + n16 // 16)
+    return {'write_peak_sustained_gbs': fill_s, 'write_peak_burst_gbs': fill_b,
+            'copy_sustained_gbs': copy_s, 'copy_burst_gbs': copy_b,
+            'expand_1to16_sustained_gbs': exp_s,
+            'expand_1to16_burst_gbs': exp_b,
+            'how': 'bb_probe_fill (decode store pattern) over the {:.0f} GiB '
+                   'decode output buffer, bb_probe_copy half -> half, '
+                   'bb_probe_expand (reads 1 byte per 16 written from 16 '
+                   'interleaved streams, no arithmetic: the ceiling of a '
+                   '2 bit -> float32 stream); mean and best launch over {} s '
+                   'each'.format(flat.numel() * 4 / 2**30, seconds)}
+
+
+def _source_hash():
+    """Hash of the kernel sources: ncu figures are only quoted for the code
+    they were captured from."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(glob.glob(os.path.join(ROOT, 'baseband_b200', 'csrc',
+                                              '*.cu*'))
+                       + glob.glob(os.path.join(ROOT, 'baseband_b200',
+                                                'csrc', '*.h'))):
+        with open(path, 'rb') as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, nsample):
+    """dram bytes per launch of ``kernel`` from the committed ncu capture
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from an
+    `ncu --set full` report), scaled to this launch's sample count -- or
+    None when no capture exists for the kernel sources as they are now."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    try:
+        with open(path) as fh:
+            table = json.load(fh)
+        entry = table[kernel]
+    except (OSError, KeyError, ValueError):
+        return None, 'no ncu capture committed for this kernel'
+    if entry.get('csrc_sha16') != _source_hash():
+        return None, ('stale: {} was captured from other kernel sources ({})'
+                      .format(entry.get('report'), entry.get('csrc_sha16')))
+    per_sample = (entry['dram_bytes_read'] + entry['dram_bytes_write']) \
+        / entry['samples_per_launch']
+    return per_sample * nsample, '{} ({} B/sample measured x {} samples)' \
+        .format(entry.get('report'), round(per_sample, 4), nsample)
 
 
 def measure_e2e(args, dev, rank, world, lv, slot):
@@ -451,6 +570,94 @@ def measure_e2e(args, dev, rank, world, lv, slot):
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '
                     'float32 array returned to the host is 16x the packed '
                     'input'.format(args.e2e_mib)}
+
+
+def measure_sharded_read(args, dev, rank, world):
+    """`parallel.read_sharded` on ONE logical stream held in pinned host
+    memory: every rank opens the same frames (same seed) and decodes its
+    contiguous share of frame sets to a device tensor -- H2D of the packed
+    frames inside the timed region, no collective; then the optional
+    gather (`gather=True`): each rank decodes into its place in the full
+    result and one in-place all_gather_into_tensor over NVLink fills in the
+    rest.  Rates: Gsamples/s over all ranks (max-over-ranks time) and the
+    collective alone in GB/s received per GPU (CUDA events)."""
+    import torch
+    import torch.distributed as dist
+    import baseband_b200 as bb
+    from baseband_b200 import parallel, synthetic
+    from baseband_b200.base.memory import HostBuffer
+    nbytes = int(args.sharded_mib * 2**20)
+    if nbytes <= 0:
+        return None
+    nset = max(world, nbytes // SET_BYTES)
+    src = HostBuffer(synthetic.vdif_stream(
+        nset, NTHREAD, PAYLOAD, seed=99, thread_order=np.arange(NTHREAD)))
+    fh = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+                      chunk_nbytes=int(args.e2e_chunk_mib * 2**20))
+    reps = 3
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            out = fn()
+        torch.cuda.synchronize(dev)
+        dt = (time.perf_counter() - t0) / reps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return dt, out
+
+    dt, (data, (a, b)) = timed(lambda: parallel.read_sharded(fh, rank, world))
+    result = {'logical_stream_bytes': int(src.size),
+              'gsamples_s': nset * SET_SAMPLES / dt / 1e9,
+              'shard_rows': int(b - a),
+              'api': "parallel.read_sharded(vdif.open(HostBuffer, 'rs', "
+                     "device=...))"}
+    del data
+    if world > 1:
+        dt, (whole, _) = timed(
+            lambda: parallel.read_sharded(fh, rank, world, gather=True))
+        result['gather_gsamples_s'] = nset * SET_SAMPLES / dt / 1e9
+        # the collective alone, in place on the gathered result
+        block = parallel.gather_block(fh, world)
+        shape = tuple(whole.shape[1:])
+        del whole
+        full = torch.empty((world * block,) + shape, dtype=torch.float32,
+                           device=dev)
+        mine = full[rank * block:(rank + 1) * block]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        dist.all_gather_into_tensor(full, mine)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ev[0].record()
+        for _ in range(reps):
+            dist.all_gather_into_tensor(full, mine)
+        ev[1].record()
+        torch.cuda.synchronize(dev)
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        recv = (world - 1) * block * NTHREAD * 4
+        result['all_gather'] = {
+            'ms': float(t.item()),
+            'received_gbs_per_gpu': recv / (float(t.item()) * 1e-3) / 1e9,
+            'bytes_received_per_gpu': int(recv),
+            'how': 'one in-place all_gather_into_tensor of equal frame-'
+                   'aligned blocks (NCCL over NVLink), CUDA events, max '
+                   'over ranks'}
+        del full, mine
+    fh.close()
+    torch.cuda.empty_cache()
+    return result
+
+
+def measure_consumer(args, dev, rank, world):
+    return None
 
 
 def measure_named_configs(args, dev, rank, world):
@@ -571,16 +778,22 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--chunk-gib', type=float, default=1.0,
-                    help='packed bytes resident per GPU per step')
+                    help='packed bytes of one resident chunk per GPU')
+    ap.add_argument('--passes', type=int, default=32,
+                    help='chunks per step (32 x 1 GiB: 20 steps keep the GPU '
+                         'busy for ~3.5 s, a sustained figure)')
     ap.add_argument('--e2e-mib', type=float, default=128.0)
     ap.add_argument('--e2e-chunk-mib', type=float, default=32.0,
                     help='packed MiB per pipeline stage of the e2e reader')
     ap.add_argument('--named-mib', type=float, default=1024.0,
                     help='packed MiB per GPU for the C3-C5 shapes (0 = skip)')
+    ap.add_argument('--sharded-mib', type=float, default=256.0,
+                    help='packed MiB of the ONE logical stream read_sharded '
+                         'splits over the ranks (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -280,6 +280,25 @@ int bb_mark4_scan(const void *src, const int64_t *frame_offset,
                   int32_t *n_inconsistent, int64_t index0, int32_t mjd0,
                   int64_t tick0, int64_t tick_step, void *stream);
 
+/* Writer-side frame assembly (the per-frame loop of StreamWriterBase.write,
+ * baseband/base/base.py:1190-1262, which writes header + payload frame by
+ * frame): header i (`headers + i * header_nbytes`, device memory, built by
+ * the host from header0 and the frame index) is copied to
+ * `dst + i * frame_stride`, and
+ *   unit_offset[i * units_per_frame + u]
+ *       = i * frame_stride + header_nbytes + u * unit_stride
+ * is written for the encode call that follows.  With `valid` (device uint8
+ * per frame) non-NULL, the payload of a frame with valid[i] == 0 is filled
+ * with `fill_word` and its units are set to -1 so that the encode skips it
+ * (Mark 5B: fill pattern 0x11223344, baseband/mark5b/frame.py:126-133).
+ * `unit_offset` may be NULL. */
+int bb_frames_assemble(void *dst, int64_t nframe, int64_t frame_stride,
+                       int32_t header_nbytes, const void *headers,
+                       const uint8_t *valid, uint32_t fill_word,
+                       int64_t payload_nbytes, int32_t units_per_frame,
+                       int64_t unit_stride, int64_t *unit_offset,
+                       void *stream);
+
 /* ------------------------------------------------------ bandwidth probes
  * Not part of the reference's path: the ceilings bench.py quotes next to the
  * decode kernels, measured in the same run with the kernels' own launch shape
@@ -289,6 +308,16 @@ int bb_mark4_scan(const void *src, const int64_t *frame_offset,
  * a 16-byte-vector copy (read + write). */
 int bb_probe_fill(void *dst, int64_t nbytes, int32_t pattern, void *stream);
 int bb_probe_copy(void *dst, const void *src, int64_t nbytes, void *stream);
+/* bb_probe_expand: the ceiling for a 1:16 expanding stream (2 bit -> float32)
+ * with ideal access patterns: reads nbytes / 16 bytes of src and writes nbytes
+ * of dst (pattern 0: contiguous input; 1: input in 16 interleaved streams, the
+ * shape of a 16-thread VDIF frame set; 2: contiguous input wrapped to one MiB,
+ * i.e. always an L2 hit).  nbytes a multiple of 4096. */
+int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
+                    int32_t pattern, void *stream);
+/* bb_probe_prefetch: a pure-read phase that pulls nbytes of src into L2
+ * (prefetch.global.L2::evict_last), for phased read-then-write experiments. */
+int bb_probe_prefetch(const void *src, int64_t nbytes, void *stream);
 
 #ifdef __cplusplus
 }

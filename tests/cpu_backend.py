@@ -171,6 +171,23 @@ def _mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
             torch.from_numpy(uo))
 
 
+def _frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
+                     fill_word=0, units_per_frame=1, unit_stride=0):
+    """numpy restatement of k_frames_assemble (csrc/bb_scan.cu)."""
+    nframe, hn = headers.shape
+    frames = torch.zeros((nframe, frame_nbytes), dtype=torch.uint8)
+    f = frames.numpy()
+    f[:, :hn] = headers.numpy()
+    uo = (np.arange(nframe, dtype=np.int64)[:, None] * frame_nbytes + hn
+          + np.arange(units_per_frame, dtype=np.int64) * unit_stride)
+    if valid is not None:
+        bad = valid.numpy() == 0
+        uo[bad] = -1
+        f[bad, hn:hn + payload_nbytes] = np.full(
+            payload_nbytes // 4, fill_word, '<u4').view(np.uint8)
+    return frames, torch.from_numpy(uo.reshape(-1))
+
+
 def install(monkeypatch):
     from baseband_b200 import _lib, device, kernels
     emu = emu_build.load()
@@ -205,6 +222,7 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'vdif_scan', _vdif_scan)
     monkeypatch.setattr(kernels, 'mark5b_scan', _mark5b_scan)
     monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
+    monkeypatch.setattr(kernels, 'frames_assemble', _frames_assemble)
     monkeypatch.setattr(
         kernels, 'new_counter',
         lambda dev: torch.zeros(1, dtype=torch.int32))

@@ -271,7 +271,7 @@ def test_scan_index_checks(sample_outputs):
     assert int(bad.item()) == 2
     # jday wraps modulo 1000: header0 at day 999, frames at day 0
     kernels.mark5b_scan(_t(raw), 4, check=(
-        -86400 * 6400, (jd0 - 1) % 1000, s0, n0, 6400), bad=bad)
+        86400 * 6400, (jd0 - 1) % 1000, s0, n0, 6400), bad=bad)
     assert int(bad.item()) == 2
     # Mark 4: sample.m4 (2014-06-16T07:38:12.47500, 2.5 ms per frame)
     raw = sample_bytes('sample.m4')[0xa88:][:2 * 160000]
@@ -290,3 +290,33 @@ def test_scan_index_checks(sample_outputs):
 def test_fuzz_int8_transposed():
     for case in int8_cases.fuzz_cases(150, seed=78):
         test_int8_transposed(case)
+
+
+def test_frames_assemble():
+    """bb_frames_assemble == the numpy restatement used by the CPU backend:
+    headers in place, unit offsets, Mark 5B-style payload fill of invalid
+    frames (mark5b/frame.py:126-133) and several units per frame (MKBF)."""
+    import cpu_backend
+    rng = np.random.default_rng(5)
+    for nframe, hn, frame, payload, per, ustride, use_valid in (
+            (7, 16, 10016, 10000, 1, 0, True),
+            (5, 32, 8032, 8000, 1, 0, False),
+            (3, 4096, 4096 + 8192, 8192, 4, 2048, False),
+            (2, 1280, 160000, 0, 1, 0, False),
+            (4, 6, 6 + 40, 40, 1, 0, False)):          # unaligned header
+        hdr = rng.integers(0, 256, (nframe, hn), dtype=np.uint8)
+        valid = (rng.random(nframe) > 0.4).astype(np.uint8) \
+            if use_valid else None
+        want_f, want_uo = cpu_backend._frames_assemble(
+            torch.from_numpy(hdr), frame, payload,
+            None if valid is None else torch.from_numpy(valid),
+            0x11223344, per, ustride)
+        got_f, got_uo = kernels.frames_assemble(
+            _t(hdr).view(nframe, hn), frame, payload,
+            None if valid is None else _t(valid), 0x11223344, per, ustride)
+        assert torch.equal(got_uo.cpu(), want_uo)
+        got, want = got_f.cpu().numpy(), want_f.numpy()
+        assert np.array_equal(got[:, :hn], want[:, :hn])
+        if valid is not None:
+            bad = valid == 0
+            assert np.array_equal(got[bad], want[bad])

@@ -1,6 +1,6 @@
 """Run one kernel case a few times (for ncu captures).
 usage: python tools/run_case.py {guppi|guppitf|mark5b|mark4enc|vdif48|vdif44|
-vdif22c|vdif84|c2} [gib]   (REPS=n launches per kernel, default 3)"""
+vdif22c|vdif84|c2|mark4} [gib]   (REPS=n launches per kernel, default 3)"""
 import os
 import sys
 
@@ -70,6 +70,16 @@ elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84',
                                 nelem, kernels.QUANT_MARK5B if case == 'mark5b'
                                 else kernels.QUANT_SINT if case == 'gsb'
                                 else kernels.QUANT_OFFSET_BINARY)
+elif case == 'mark4':
+    # C3: 64 tracks, fan-out 4, 8 channels: header scan + decode
+    nframe = int(gib * 2**30) // 160000
+    from baseband_b200 import synthetic
+    raw = synthetic.mark4_stream_device(nframe, torch.device(DEV))
+    out = None
+    for _ in range(reps):
+        _, off = kernels.mark4_scan(raw, nframe, 64)
+        out = kernels.mark4_decode(raw, off, nframe, 8, 4, False,
+                                   levels.sign_magnitude(), out=out)
 elif case == 'mark4enc':
     nframe = int(gib * 2**30) // 160000
     raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,

@@ -72,6 +72,13 @@ def main():
            seconds)
     report('bb_probe_fill rowgroup pattern', n,
            lambda: kernels.probe_fill(b, 1), seconds)
+    # 1:16 expansion with ideal access patterns: what a 2 bit -> float32
+    # stream can reach at all (bytes = read + written)
+    for pat, what in ((0, 'contiguous input'), (1, '16 input streams')):
+        report('bb_probe_expand 1:16, %s' % what, n + n // 16,
+               lambda pat=pat: kernels.probe_expand(b, a, pat), seconds)
+    report('bb_probe_expand 1:16, input wrapped to 1 MiB (L2 hits)',
+           n + n // 16, lambda: kernels.probe_expand(b, a, 2), seconds)
     del a, b
     torch.cuda.empty_cache()
 
@@ -112,7 +119,7 @@ def main():
                 report('%s DEC C2=%d U=%d %s' % (name, c2, tu,
                                                   'ok' if same else 'MISMATCH'),
                        nbytes, fn, seconds)
-        os.environ['BB_TUNE_C2'] = '0'
+        os.environ.pop('BB_TUNE_C2', None)
         # where does the gap to the pure-write rate come from?  Same launch,
         # but every set reads the frames of the first `alias` sets, so the
         # packed input stays in L2 and DRAM sees writes only.
@@ -139,7 +146,7 @@ def main():
                 report('%s DEC C2=%d knock-out %d (%s)' % (
                     name, c2, knock, 'no payload loads' if knock == 1
                     else 'no loads at all'), nbytes, fn_k, seconds)
-        os.environ['BB_TUNE_C2'] = '0'
+        os.environ.pop('BB_TUNE_C2', None)
         os.environ['BB_TUNE_KNOCK'] = '0'
         del raw, out, ref
         torch.cuda.empty_cache()
