@@ -688,6 +688,45 @@ class StreamReaderBase(StreamBase):
             self._streams = _device.Streams(dev)
         return self._stages, self._streams
 
+    # -- packed consumers ------------------------------------------------
+    def _packed_units(self, raw, frame0, nframe):
+        """Unit table of a chunk for consumers that work on the packed
+        payloads: ``(unit_offset, nthread, payload_nbytes, bps, nelem)`` as
+        the bit-field kernels take them.  Formats whose payloads are not
+        plain bit fields do not provide it."""
+        raise NotImplementedError('{} has no packed bit-field payloads'
+                                  .format(type(self).__name__))
+
+    def _for_each_packed_chunk(self, frame0, nframe, fn):
+        """Stream the raw bytes of frames [frame0, frame0 + nframe) through
+        the device -- the reader's own ingest pipeline: pinned (or zero-copy)
+        host chunk -> H2D on the copy stream, double buffered -- and call
+        ``fn(raw, first_frame, nframe_in_chunk)`` for every chunk on the
+        compute stream.  Nothing is decoded."""
+        dev = self.device
+        stages, ss = self._pipeline(dev)
+        spf = self._samples_per_frame
+        per = self._frames_per_chunk()
+        ss.after_caller(1)
+        for k, c0 in enumerate(range(frame0, frame0 + nframe, per)):
+            nf = min(per, frame0 + nframe - c0)
+            st = stages[k % 2]
+            nbytes = self._chunk_nbytes_of(c0, nf, 0, nf * spf)
+            if st.done is not None:
+                st.done.synchronize()
+            pin, raw = st.buffers(nbytes, 0, dev, False)
+            got = self._read_raw(c0, nf, pin, 0, nf * spf)
+            pin = pin if got is None else got
+            with ss.use(0):
+                ss.wait_event(0, st.free)
+                raw.copy_(pin, non_blocking=True)
+                st.done = ss.event(0)
+            with ss.use(1):
+                ss.wait_event(1, st.done)
+                fn(raw, c0, nf)
+                st.free = ss.event(1)
+        ss.caller_after(1)
+
     # -- device output ---------------------------------------------------
     def _read_to_device(self, start, count, out):
         dev = out.device if out is not None else self.device

@@ -1,0 +1,297 @@
+// State counts of packed bit-field payloads (sm_100a): a consumer that works
+// on the packed words and never materialises float32 samples in HBM.
+//
+// counts[bin][thread][elem][code] = number of samples of `elem` (channel, or
+// re/im component of a channel) of VDIF thread `thread` whose code is `code`,
+// over the valid frames of integration bin `bin`.  Codes are the bit fields of
+// the payload in the reference's layout (baseband/vdif/payload.py:53-63,
+// baseband/mark5b/payload.py:20-59: sample i of a word occupies bits
+// [i*bps, (i+1)*bps), element index fastest), i.e. exactly what the decode
+// kernels look up in the level table, so that
+//     sum(decoded**2) over a bin  ==  sum_c counts[..., c] * levels[c]**2.
+// Integer counts are order-independent: the result is bit-exact whatever the
+// launch shape.  HBM-read bound: one pass over the packed bytes.
+#include "bb_runtime.cuh"
+
+namespace bb {
+
+struct CountGeom {
+    const uint8_t *src;
+    const long long *unit_offset;     // [nset][nthread], < 0: invalid frame
+    unsigned long long *counts;       // [nbin][nthread][nelem][ncode]
+    long long nset;                   // frame sets in this call
+    long long set_origin;             // set 0 of this call, counted from bin 0
+    long long sets_per_bin;
+    long long bin_first;              // first bin this launch covers
+    int nthread, nelem, split;
+    uint32_t nword;                   // 32-bit words per unit payload
+};
+
+__device__ __forceinline__ bool count_range(const CountGeom &p, long long &lo,
+                                            long long &hi, long long &bin) {
+    bin = p.bin_first + blockIdx.z;
+    lo = bin * p.sets_per_bin - p.set_origin;
+    hi = lo + p.sets_per_bin;
+    if (lo < 0) lo = 0;
+    if (hi > p.nset) hi = p.nset;
+    return lo < hi;
+}
+
+template <int BPS, int NE>
+struct ElemMask {
+    // sample slots of element e within a word, one bit (the lowest of the
+    // field) per slot
+    static __host__ __device__ constexpr uint32_t of(int e) {
+        uint32_t m = 0u;
+        for (int s = e; s < 32 / BPS; s += NE) m |= 1u << (s * BPS);
+        return m;
+    }
+};
+
+// Register path: NE elements per word (NE * ncode <= 16 counters), counted
+// with popcounts of per-code indicator words; code 0 follows from the number
+// of words seen.
+template <int BPS, int NE>
+__device__ __forceinline__ void count_word(uint32_t w, uint32_t (&c)[NE][3]) {
+    if (BPS == 1) {
+#pragma unroll
+        for (int e = 0; e < NE; ++e)
+            c[e][0] += __popc(w & ElemMask<1, NE>::of(e));
+    } else {
+        const uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+        const uint32_t i3 = lo & hi, i2 = hi ^ i3, i1 = lo ^ i3;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+            const uint32_t m = ElemMask<2, NE>::of(e);
+            c[e][0] += __popc(i1 & m);
+            c[e][1] += __popc(i2 & m);
+            c[e][2] += __popc(i3 & m);
+        }
+    }
+}
+
+constexpr int kCountBlock = 256;
+
+template <int BPS, int NE>
+__global__ void __launch_bounds__(kCountBlock)
+k_state_counts_reg(const CountGeom p) {
+    constexpr int NCODE = 1 << BPS;
+    __shared__ unsigned long long tot[NE * NCODE];
+    long long lo, hi, bin;
+    if (!count_range(p, lo, hi, bin)) return;
+    const int t = blockIdx.y;
+    if (threadIdx.x < NE * NCODE) tot[threadIdx.x] = 0ull;
+    __syncthreads();
+    uint32_t c[NE][3];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) c[e][0] = c[e][1] = c[e][2] = 0u;
+    uint32_t nw = 0u;
+    const uint32_t nquad = p.nword / 4u;
+    for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
+        const long long off = p.unit_offset[s * p.nthread + t];
+        if (off < 0) continue;                        // invalid frame
+        const uint8_t *base = p.src + off;
+        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(base);
+#pragma unroll 2
+            for (uint32_t i = threadIdx.x; i < nquad; i += kCountBlock) {
+                const uint4 v = q[i];
+                count_word<BPS, NE>(v.x, c);
+                count_word<BPS, NE>(v.y, c);
+                count_word<BPS, NE>(v.z, c);
+                count_word<BPS, NE>(v.w, c);
+                nw += 4u;
+            }
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+            for (uint32_t i = nquad * 4u + threadIdx.x; i < p.nword;
+                 i += kCountBlock) {
+                count_word<BPS, NE>(w[i], c);
+                nw += 1u;
+            }
+        } else {
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+            for (uint32_t i = threadIdx.x; i < p.nword; i += kCountBlock) {
+                count_word<BPS, NE>(w[i], c);
+                nw += 1u;
+            }
+        }
+    }
+    // warp sums -> shared 64-bit totals -> one global atomic per counter
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t nw_warp = __reduce_add_sync(0xffffffffu, nw);
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+        uint32_t rest = nw_warp * (32 / BPS / NE);
+#pragma unroll
+        for (int k = 0; k < NCODE - 1; ++k) {
+            const uint32_t v = __reduce_add_sync(0xffffffffu, c[e][k]);
+            rest -= v;
+            if (lane == 0 && v)
+                atomicAdd(&tot[e * NCODE + k + 1], (unsigned long long)v);
+        }
+        if (lane == 0 && rest)
+            atomicAdd(&tot[e * NCODE], (unsigned long long)rest);
+    }
+    __syncthreads();
+    if (threadIdx.x < NE * NCODE && tot[threadIdx.x])
+        atomicAdd(p.counts + ((size_t)(bin * p.nthread + t) * NE) * NCODE
+                  + threadIdx.x, tot[threadIdx.x]);
+}
+
+// General path (any power-of-two nelem, bps 1, 2 or 4): every thread keeps a
+// private histogram over (slot in word, code) in shared memory -- laid out
+// [counter][thread], so bank = thread and no two threads ever touch the same
+// word -- and always sees words of the same class (word index mod P, P =
+// words per complete sample), so that a slot is one fixed element.
+constexpr int kHistBlock = 128;
+
+template <int BPS>
+__global__ void __launch_bounds__(kHistBlock)
+k_state_counts_hist(const CountGeom p, int words_per_sample) {
+    constexpr int NCODE = 1 << BPS, SPW = 32 / BPS, NCNT = SPW * NCODE;
+    extern __shared__ uint32_t hist[];            // [NCNT][kHistBlock]
+    long long lo, hi, bin;
+    if (!count_range(p, lo, hi, bin)) return;
+    const int t = blockIdx.y;
+    for (int i = threadIdx.x; i < NCNT * kHistBlock; i += kHistBlock)
+        hist[i] = 0u;
+    // (only this thread touches column threadIdx.x: no barrier needed)
+    for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
+        const long long off = p.unit_offset[s * p.nthread + t];
+        if (off < 0) continue;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(p.src + off);
+        for (uint32_t i = threadIdx.x; i < p.nword; i += kHistBlock) {
+            const uint32_t v = w[i];
+#pragma unroll
+            for (int j = 0; j < SPW; ++j) {
+                const uint32_t code = (v >> (j * BPS)) & (NCODE - 1);
+                hist[(j * NCODE + code) * kHistBlock + threadIdx.x] += 1u;
+            }
+        }
+    }
+    // lanes of a warp that share a class add up by shuffles, then one global
+    // atomic per (class, slot, code) and warp
+    const int P = words_per_sample;               // power of two <= kHistBlock
+    const int cls = threadIdx.x % P;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long *out = p.counts
+        + (size_t)(bin * p.nthread + t) * p.nelem * NCODE;
+    for (int j = 0; j < SPW; ++j) {
+        const int e = p.nelem >= SPW ? cls * SPW + j : j % p.nelem;
+#pragma unroll
+        for (int code = 0; code < NCODE; ++code) {
+            uint32_t v = hist[(j * NCODE + code) * kHistBlock + threadIdx.x];
+            for (int o = 16; o >= P && o >= 1; o >>= 1)
+                v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((P >= 32 || lane < (uint32_t)P) && v)
+                atomicAdd(out + (size_t)e * NCODE + code,
+                          (unsigned long long)v);
+        }
+    }
+}
+
+template <int BPS, int NE>
+static void launch_reg(const CountGeom &g, dim3 grid, cudaStream_t s) {
+    k_state_counts_reg<BPS, NE><<<grid, kCountBlock, 0, s>>>(g);
+}
+
+template <int BPS>
+static int launch_hist(const CountGeom &g, dim3 grid, int P, cudaStream_t s) {
+    constexpr int NCNT = (32 / BPS) * (1 << BPS);
+    const size_t smem = (size_t)NCNT * kHistBlock * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(
+            k_state_counts_hist<BPS>,
+            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return check_cuda(e, "bb_state_counts (smem)");
+        attr_set = true;
+    }
+    k_state_counts_hist<BPS><<<grid, kHistBlock, smem, s>>>(g, P);
+    return BB_OK;
+}
+
+}  // namespace bb
+
+using namespace bb;
+
+extern "C" int bb_state_counts(
+    const void *src, const int64_t *unit_offset, int64_t nset, int32_t nthread,
+    int64_t payload_nbytes, int32_t bps, int32_t nelem, int64_t set_origin,
+    int64_t sets_per_bin, uint64_t *counts, int64_t nbin, void *stream) {
+    if (!src || !unit_offset || !counts)
+        return set_error(BB_ERR_ARGUMENT, "null pointer");
+    if (!(bps == 1 || bps == 2 || bps == 4))
+        return set_error(BB_ERR_UNSUPPORTED,
+                         "state counts exist for 1, 2 and 4 bits per sample");
+    if (nset < 0 || nthread < 1 || nthread > 65535 || nelem < 1
+        || (nelem & (nelem - 1)) || payload_nbytes <= 0 || (payload_nbytes & 3)
+        || set_origin < 0 || sets_per_bin < 1 || nbin < 1)
+        return set_error(BB_ERR_ARGUMENT, "bad geometry (nelem must be a "
+                         "power of two, payload a multiple of 4 bytes)");
+    if (!aligned(src, 4))
+        return set_error(BB_ERR_ALIGNMENT, "src must be 4-byte aligned");
+    if (payload_nbytes / 4 > 0x7fffffff)
+        return set_error(BB_ERR_ARGUMENT, "payload too large");
+    if ((payload_nbytes * 8) % ((int64_t)bps * nelem))
+        return set_error(BB_ERR_ARGUMENT,
+                         "payload does not hold whole samples");
+    if (nset == 0) return BB_OK;
+    const int64_t b0 = set_origin / sets_per_bin;
+    const int64_t b1 = (set_origin + nset - 1) / sets_per_bin;     // inclusive
+    if (b1 >= nbin)
+        return set_error(BB_ERR_ARGUMENT, "sets run past the last bin");
+    const int spw = 32 / bps, ncode = 1 << bps;
+    const bool reg = bps <= 2 && nelem <= spw && nelem * ncode <= 16;
+    const int P = nelem > spw ? nelem / spw : 1;
+    if (!reg && P > kHistBlock)
+        return set_error(BB_ERR_UNSUPPORTED,
+                         "too many elements per sample for state counts");
+    CountGeom g;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.counts = (unsigned long long *)counts;
+    g.nset = nset;
+    g.set_origin = set_origin;
+    g.sets_per_bin = sets_per_bin;
+    g.nthread = nthread;
+    g.nelem = nelem;
+    g.nword = (uint32_t)(payload_nbytes / 4);
+    // CTAs per (bin, thread): enough to fill the GPU four deep, at most one
+    // per set of a bin, and few enough words each that 32-bit counters hold
+    const int64_t nb = b1 - b0 + 1;
+    const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
+    int64_t split = (4ll * sm_count() + nb * nthread - 1) / (nb * nthread);
+    const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
+        / (1ll << 26);
+    if (split < need) split = need;
+    if (split > per_bin) split = per_bin;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
+    g.split = (int)split;
+    cudaStream_t s = as_stream(stream);
+    for (int64_t z0 = 0; z0 < nb; z0 += 65535) {
+        const int64_t nz = nb - z0 < 65535 ? nb - z0 : 65535;
+        g.bin_first = b0 + z0;
+        dim3 grid((unsigned)split, (unsigned)nthread, (unsigned)nz);
+        if (reg) {
+            if (bps == 1) {
+                if (nelem == 1) launch_reg<1, 1>(g, grid, s);
+                else if (nelem == 2) launch_reg<1, 2>(g, grid, s);
+                else if (nelem == 4) launch_reg<1, 4>(g, grid, s);
+                else launch_reg<1, 8>(g, grid, s);
+            } else {
+                if (nelem == 1) launch_reg<2, 1>(g, grid, s);
+                else if (nelem == 2) launch_reg<2, 2>(g, grid, s);
+                else launch_reg<2, 4>(g, grid, s);
+            }
+        } else {
+            int rc = bps == 1 ? launch_hist<1>(g, grid, P, s)
+                : bps == 2 ? launch_hist<2>(g, grid, P, s)
+                : launch_hist<4>(g, grid, P, s);
+            if (rc != BB_OK) return rc;
+        }
+        BB_CHECK_LAUNCH("bb_state_counts");
+    }
+    return BB_OK;
+}

@@ -403,6 +403,30 @@ def frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
     return frames, unit_offset
 
 
+def state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
+                 counts, set_origin=0, sets_per_bin=None):
+    """bb_state_counts: add the state counts of ``nset`` frame sets to
+    ``counts`` (int64 CUDA tensor (nbin, nthread, nelem, 2**bps))."""
+    lib = _lib.load()
+    _require_cuda(src, unit_offset, counts)
+    nbin = counts.shape[0]
+    if tuple(counts.shape[1:]) != (nthread, nelem, 1 << bps):
+        raise ValueError('counts must have shape (nbin, nthread, nelem, '
+                         '2**bps)')
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nset)
+    with _on(src.device):
+        rc = lib.bb_state_counts(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nset, nthread,
+            payload_nbytes, bps, nelem, int(set_origin), int(sets_per_bin),
+            _dev(counts, 'counts', torch.int64), nbin,
+            _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return counts
+
+
 def probe_fill(dst, pattern=0):
     """bb_probe_fill: write the whole tensor ``dst`` with the decode kernels'
     launch shape (pure-write bandwidth probe)."""

@@ -160,6 +160,14 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
     _frame_nbytes = 10016
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
+        uo, nthread, payload_nbytes, bps, nelem = self._packed_units(
+            raw, frame0, nframe)
+        kernels.decode_bitfield(
+            raw, uo, nframe, nthread, payload_nbytes, bps, nelem, False,
+            kernels.CODEC_LEVELS, self._levels, self._fill_value,
+            sample_start, nsample, out)
+
+    def _packed_units(self, raw, frame0, nframe):
         if self._index is not None:
             # lossy stream: scan the physical frames of the chunk (payload
             # validity), then pick each stream frame's entry from the index
@@ -182,10 +190,7 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
                 raw, nframe, check=check,
                 bad=self._bad_counter(raw.device) if self.verify else None,
                 want_fields=False)
-        kernels.decode_bitfield(
-            raw, uo, nframe, 1, 10000, self._bps, self._sample_shape[0],
-            False, kernels.CODEC_LEVELS, self._levels, self._fill_value,
-            sample_start, nsample, out)
+        return uo, 1, 10000, self._bps, self._sample_shape[0]
 
     def _frame_index(self, jday, seconds, frame_nr):
         """mark5b/base.py:206-213 on arrays (torch or numpy); jday wraps

@@ -1,0 +1,122 @@
+"""Consumers that run on the GPU behind the stream readers.
+
+The reference hands decoded samples to analysis code through the
+``baseband.tasks`` plug-in point (baseband/tasks/__init__.py:25-62; the
+baseband-tasks package: ``Square``, ``Integrate``, ...).  With the decode on
+the GPU the end-to-end rate of ``fh.read()`` into host memory is set by the
+device-to-host link (4 bytes per sample); a consumer that stays on the device
+is not.  The ones here go one step further and never decode at all: they run
+on the packed payloads as they arrive in HBM, through the reader's own ingest
+pipeline (file / pinned host -> H2D -> header scan), and return a few numbers.
+
+``state_counts(fh, samples_per_bin)``
+    how often each code (state) occurs per integration bin, VDIF thread and
+    channel -- the digitiser statistics -- as exact integers;
+``integrated_power(fh, samples_per_bin)``
+    mean (or summed) power per bin, thread and channel, the result of
+    ``Integrate(Square(fh), samples_per_bin)``, from the same counts:
+    ``sum(x**2) = sum_c counts[c] * level[c]**2``.  Invalid frames do not
+    contribute (and do not count in the mean).
+
+Both take any reader with packed bit-field payloads of 1, 2 or 4 bits (VDIF,
+Mark 5B).
+"""
+import numpy as np
+import torch
+
+from . import kernels
+
+__all__ = ['state_counts', 'integrated_power', 'state_levels']
+
+
+def _frame_range(fh, count, samples_per_bin):
+    spf = fh.samples_per_frame
+    start = fh.tell()
+    if count is None:
+        count = fh.shape[0] - start
+    if start % spf or count % spf:
+        raise ValueError('state counts work on whole frames: the sample '
+                         'pointer and count must be multiples of '
+                         'samples_per_frame ({})'.format(spf))
+    if count <= 0:
+        raise ValueError('nothing to count')
+    if samples_per_bin is None:
+        samples_per_bin = count
+    if samples_per_bin % spf:
+        raise ValueError('samples_per_bin must be a multiple of '
+                         'samples_per_frame ({})'.format(spf))
+    return start // spf, count // spf, samples_per_bin // spf
+
+
+def state_levels(fh):
+    """float32 level of every code of ``fh``'s payloads (the decode table)."""
+    codec = getattr(fh, '_codec', None)
+    lv = codec[1] if codec is not None else getattr(fh, '_levels', None)
+    if lv is None:
+        raise TypeError('{} has no level table'.format(type(fh).__name__))
+    return np.asarray(lv, np.float32)
+
+
+def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
+    """Occurrences of every code in the next ``count`` samples of ``fh``.
+
+    Returns an int64 array ``(nbin,) + sample shape [+ (2,) for complex
+    data] + (2**bps,)``; for VDIF the sample shape is ``(nthread, nchan)``
+    with the threads the reader decodes (its thread subset; unit dimensions
+    dropped if the reader squeezes), for Mark 5B ``(nchan,)``.  Bin ``b`` covers samples ``[b, b + 1) *
+    samples_per_bin`` from the current sample pointer (default: one bin);
+    frames marked invalid are skipped.  The sample pointer advances by
+    ``count``.  The packed frames go host -> HBM once; nothing else moves but
+    the counts (``device_output=True`` leaves even those on the GPU).
+    """
+    frame0, nframe, frames_per_bin = _frame_range(fh, count, samples_per_bin)
+    nbin = -(-nframe // frames_per_bin)
+    state = {}
+
+    def consume(raw, f0, nf):
+        uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
+        if 'counts' not in state:
+            state['geom'] = (nthread, nelem, bps)
+            state['counts'] = torch.zeros(
+                (nbin, nthread, nelem, 1 << bps), dtype=torch.int64,
+                device=raw.device)
+        kernels.state_counts(raw, uo, nf, nthread, payload_nbytes, bps, nelem,
+                             state['counts'], set_origin=f0 - frame0,
+                             sets_per_bin=frames_per_bin)
+
+    fh._for_each_packed_chunk(frame0, nframe, consume)
+    check = getattr(fh, '_new_inconsistencies', None)
+    if check is not None and getattr(fh, '_index', None) is None and check():
+        raise OSError('stream is not a regular sequence of frames; read() '
+                      'it once (which indexes it) before counting states.')
+    fh.seek(fh.tell() + nframe * fh.samples_per_frame)
+    counts = state['counts']
+    nthread, nelem, bps = state['geom']
+    shape = tuple(fh._unsliced_shape)
+    if getattr(fh, '_decode_ids', None) is not None and len(shape) == 2:
+        shape = (nthread, shape[1])
+    if getattr(fh, 'squeeze', False):
+        shape = tuple(d for d in shape if d > 1)
+    if fh.complex_data:
+        shape = shape + (2,)
+    counts = counts.view((nbin,) + shape + (1 << bps,))
+    return counts if device_output else counts.cpu().numpy()
+
+
+def integrated_power(fh, samples_per_bin=None, count=None, average=True):
+    """Power per integration bin: ``Integrate(Square(fh), samples_per_bin)``
+    of the baseband-tasks vocabulary, computed from `state_counts` (float64:
+    ``sum_c counts[c] * level[c]**2``; for complex data re**2 + im**2).
+    With ``average`` the mean over the valid samples of the bin (NaN for a
+    bin without valid samples), else the sum."""
+    lv = state_levels(fh).astype(np.float64)
+    counts = state_counts(fh, samples_per_bin, count)
+    total = (counts * lv ** 2).sum(-1)
+    nvalid = counts.sum(-1)
+    if fh.complex_data:
+        total = total.sum(-1)
+        nvalid = nvalid[..., 0]
+    if not average:
+        return total
+    with np.errstate(invalid='ignore', divide='ignore'):
+        return total / nvalid

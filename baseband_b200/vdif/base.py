@@ -264,6 +264,14 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         return data
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
+        uo, nthread, payload_nbytes, bps, nelem = self._packed_units(
+            raw, frame0, nframe)
+        kernels.decode_bitfield(
+            raw, uo, nframe, nthread, payload_nbytes, bps, nelem,
+            self._complex_data, self._codec[0], self._codec[1],
+            self._fill_value, sample_start, nsample, out)
+
+    def _packed_units(self, raw, frame0, nframe):
         h0 = self.header0
         dev = raw.device
         nelem = self._sample_shape[1] * (2 if self._complex_data else 1)
@@ -286,10 +294,7 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
                 raw, nframe * nthread_file, h0.frame_nbytes, h0.nbytes,
                 nthread_file, self._slots_dev, len(self._decode_ids),
                 check=check, bad=self._bad_counter(dev), want_fields=False)
-        kernels.decode_bitfield(
-            raw, uo, nframe, len(self._decode_ids), h0.payload_nbytes,
-            h0.bps, nelem, self._complex_data, self._codec[0],
-            self._codec[1], self._fill_value, sample_start, nsample, out)
+        return uo, len(self._decode_ids), h0.payload_nbytes, h0.bps, nelem
 
     # ------------------------------------------- irregular (lossy) streams
     def _build_index(self):

@@ -657,7 +657,88 @@ def measure_sharded_read(args, dev, rank, world):
 
 
 def measure_consumer(args, dev, rank, world):
-    return None
+    """Second end-to-end line: a consumer that stays on the GPU.  Pinned host
+    frames -> `tasks.state_counts(fh, samples_per_bin)` (the reader's ingest
+    pipeline: H2D of the packed frames, header scan with frame-index check,
+    bb_state_counts on the packed words) -> the counts (a few KB) back on the
+    host as a numpy array, from which integrated power follows.  No float32
+    sample ever exists, so the rate is set by the H2D link at 2 bits per
+    sample instead of the D2H link at 32.  Also the kernel alone on a
+    resident chunk, in GB/s of packed bytes read."""
+    import torch
+    import torch.distributed as dist
+    import baseband_b200 as bb
+    from baseband_b200 import kernels, synthetic, tasks
+    from baseband_b200.base.memory import HostBuffer
+    nbytes = int(args.consumer_mib * 2**20)
+    if nbytes <= 0:
+        return None
+    nset = max(1, nbytes // SET_BYTES)
+    src = HostBuffer(synthetic.vdif_stream(
+        nset, NTHREAD, PAYLOAD, seed=31 + rank,
+        thread_order=np.arange(NTHREAD)))
+    fh = bb.vdif.open(src, 'rs', sample_rate=64e6, device=dev,
+                      chunk_nbytes=int(args.e2e_chunk_mib * 2**20))
+    sets_per_bin = 200                     # 0.1 s of this stream per bin
+
+    def step():
+        fh.seek(0)
+        return tasks.state_counts(fh, sets_per_bin * SPF)
+
+    counts = step()
+    assert int(counts.sum()) == nset * SET_SAMPLES
+    if world > 1:
+        dist.barrier()
+    steps = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        counts = step()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    fh.close()
+    # the kernel alone, chunk resident in HBM
+    kset = int(args.chunk_gib * 2**30) // SET_BYTES
+    raw = synthetic.vdif_stream_device(kset, NTHREAD, PAYLOAD, dev,
+                                       seed=synthetic.VDIF_SEED + rank)
+    uo = (torch.arange(kset * NTHREAD, dtype=torch.int64, device=dev)
+          * FRAME + 32)
+    acc = torch.zeros((-(-kset // sets_per_bin), NTHREAD, 1, 4),
+                      dtype=torch.int64, device=dev)
+    ev = []
+    for k in range(8):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        kernels.state_counts(raw, uo, kset, NTHREAD, PAYLOAD, 2, 1, acc,
+                             sets_per_bin=sets_per_bin)
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    ms = sorted(a.elapsed_time(b) for a, b in ev[2:])
+    kms = ms[len(ms) // 2]
+    del raw, uo, acc
+    torch.cuda.empty_cache()
+    return {'value': nset * SET_SAMPLES * world * steps / dt / 1e9,
+            'unit': UNIT, 'h2d_bytes_per_step': int(src.size),
+            'd2h_bytes_per_step': int(counts.nbytes), 'steps': steps,
+            'ingest_h2d_gbs_per_gpu': src.size * steps / dt / 1e9,
+            'api': "tasks.state_counts(vdif.open(HostBuffer, 'rs', "
+                   "device=...), samples_per_bin) -> numpy int64 "
+                   "(nbin, 16, 4); tasks.integrated_power from the same",
+            'kernel': {
+                'name': 'k_state_counts_reg<2,1>',
+                'packed_gbs': kset * NTHREAD * PAYLOAD / (kms * 1e-3) / 1e9,
+                'gsamples_s': kset * SET_SAMPLES / (kms * 1e-3) / 1e9,
+                'ms': kms, 'bound': 'hbm read',
+                'what': 'bb_state_counts alone on a resident {:.1f} GiB '
+                        'chunk (median of 6 launches, CUDA events); bytes = '
+                        'payload bytes read'.format(args.chunk_gib)},
+            'note': 'packed frames in, state counts out: what '
+                    'Integrate(Square(fh)) needs, without the 16x expansion '
+                    'to float32 ever touching HBM or PCIe'}
 
 
 def measure_named_configs(args, dev, rank, world):
@@ -794,6 +875,9 @@ def main():
     ap.add_argument('--sharded-mib', type=float, default=256.0,
                     help='packed MiB of the ONE logical stream read_sharded '
                          'splits over the ranks (0 = skip)')
+    ap.add_argument('--consumer-mib', type=float, default=512.0,
+                    help='packed MiB per GPU and step of the state-count '
+                         'consumer leg (0 = skip)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

@@ -299,6 +299,29 @@ int bb_frames_assemble(void *dst, int64_t nframe, int64_t frame_stride,
                        int64_t unit_stride, int64_t *unit_offset,
                        void *stream);
 
+/* ------------------------------------------------- consumers on the device
+ * The plug-in point for analysis that follows the decode is
+ * baseband/tasks/__init__.py:25-62 (entry-point group 'baseband.tasks', the
+ * baseband-tasks package: Square, Integrate, ...).  A consumer that runs on
+ * the GPU need not see float32 samples at all:
+ *
+ * bb_state_counts accumulates, straight from the packed payloads,
+ *   counts[bin][thread][elem][code] += number of samples with that code
+ * (uint64, device memory, nbin x nthread x nelem x 2**bps, caller-zeroed) for
+ * the frame sets of this call.  Set s of the call belongs to integration bin
+ * (set_origin + s) / sets_per_bin; units at offset < 0 (invalid frames) are
+ * left out, so sum_c counts = valid samples.  `code` is the bit field the
+ * decoders look up in the level table (sample i of a word in bits
+ * [i*bps, (i+1)*bps), element fastest: baseband/vdif/payload.py:53-63), hence
+ *   sum over a bin of decoded**2 == sum_c counts[..., c] * levels[c]**2,
+ * i.e. integrated power (Integrate(Square(fh))) and the digitiser statistics
+ * follow from one pass over the packed bytes.  bps 1, 2, 4; nelem a power of
+ * two; exact integer arithmetic (bit-identical for any launch shape). */
+int bb_state_counts(const void *src, const int64_t *unit_offset, int64_t nset,
+                    int32_t nthread, int64_t payload_nbytes, int32_t bps,
+                    int32_t nelem, int64_t set_origin, int64_t sets_per_bin,
+                    uint64_t *counts, int64_t nbin, void *stream);
+
 /* ------------------------------------------------------ bandwidth probes
  * Not part of the reference's path: the ceilings bench.py quotes next to the
  * decode kernels, measured in the same run with the kernels' own launch shape

@@ -188,6 +188,28 @@ def _frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
     return frames, torch.from_numpy(uo.reshape(-1))
 
 
+def _state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
+                  counts, set_origin=0, sets_per_bin=None):
+    """numpy restatement of bb_state_counts (csrc/bb_counts.cu)."""
+    buf = src.numpy()
+    uo = unit_offset.numpy().reshape(nset, nthread)
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nset)
+    out = counts.numpy()
+    shifts = np.arange(0, 32, bps, dtype=np.uint32)
+    for s in range(nset):
+        b = (set_origin + s) // sets_per_bin
+        for t in range(nthread):
+            if uo[s, t] < 0:
+                continue
+            w = buf[uo[s, t]:uo[s, t] + payload_nbytes].view('<u4')
+            codes = ((w[:, None] >> shifts) & ((1 << bps) - 1)).reshape(-1)
+            for e in range(nelem):
+                out[b, t, e] += np.bincount(codes[e::nelem],
+                                            minlength=1 << bps)
+    return counts
+
+
 def install(monkeypatch):
     from baseband_b200 import _lib, device, kernels
     emu = emu_build.load()
@@ -223,6 +245,7 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'mark5b_scan', _mark5b_scan)
     monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
     monkeypatch.setattr(kernels, 'frames_assemble', _frames_assemble)
+    monkeypatch.setattr(kernels, 'state_counts', _state_counts)
     monkeypatch.setattr(
         kernels, 'new_counter',
         lambda dev: torch.zeros(1, dtype=torch.int32))

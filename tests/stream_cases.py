@@ -1347,3 +1347,116 @@ def vdif_mark5b_payload_edv_ab():
     _same(frame.data, want[:5000])
     pl = bb.vdif.VDIFPayload.fromdata(want[:5000], frame.header)
     assert np.array_equal(pl.words, frame.payload.words)
+
+
+# ------------------------------------------------------- consumers (tasks)
+def _counts_from_decoded(data, lv, rows_per_bin):
+    """Oracle for the state counts: how often each level occurs in the
+    reference's decoded samples, per bin (data: (nsample, ...) float32 with
+    NaN where frames are invalid)."""
+    nbin = -(-data.shape[0] // rows_per_bin)
+    out = np.zeros((nbin,) + data.shape[1:] + (len(lv),), np.int64)
+    for b in range(nbin):
+        block = data[b * rows_per_bin:(b + 1) * rows_per_bin]
+        for c, level in enumerate(lv):
+            out[b, ..., c] = (block == level).sum(0)
+    return out
+
+
+def vdif_task_state_counts():
+    """tasks.state_counts / integrated_power == counting the levels in what
+    the reference decodes (oracle), for the C2 geometry (register path, one
+    real channel per thread), with invalid frames, bins that do not line up
+    with the chunks, and a thread subset."""
+    from baseband_b200 import levels, tasks
+    raw = synthetic.vdif_stream(11, 16, 8000, seed=8, invalid=[5, 40, 41])
+    lv = levels.offset_binary(2)
+    decoded = ostream.vdif_read(raw, fill_value=np.nan)[:, :, 0]
+    for chunk, sets_per_bin in ((16 * 8032 * 3, 2), (1 << 30, 4), (16 * 8032,
+                                                                    11)):
+        with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=64e6,
+                          chunk_nbytes=chunk) as fh:
+            got = tasks.state_counts(fh, sets_per_bin * 32000)
+            assert fh.tell() == 11 * 32000
+            want = _counts_from_decoded(decoded, lv, sets_per_bin * 32000)
+            assert got.dtype == np.int64 and got.shape == want.shape
+            assert np.array_equal(got, want)
+            fh.seek(2 * 32000)
+            part = tasks.state_counts(fh, 3 * 32000, count=6 * 32000)
+            assert np.array_equal(part, _counts_from_decoded(
+                decoded[2 * 32000:8 * 32000], lv, 3 * 32000))
+            fh.seek(0)
+            power = tasks.integrated_power(fh, sets_per_bin * 32000)
+            x = decoded.astype(np.float64) ** 2
+            nb = want.shape[0]
+            ref = np.stack([np.nanmean(x[b * sets_per_bin * 32000:
+                                         (b + 1) * sets_per_bin * 32000], 0)
+                            for b in range(nb)])
+            assert np.allclose(power, ref, rtol=1e-10, atol=0)   # float64 summation order
+            try:
+                fh.seek(5)
+                tasks.state_counts(fh, 32000)
+            except ValueError:
+                pass
+            else:
+                raise AssertionError('partial frames must be refused')
+    with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=64e6,
+                      subset=[3, 12]) as fh:
+        got = tasks.state_counts(fh)
+        assert np.array_equal(got, _counts_from_decoded(
+            decoded[:, [3, 12]], lv, 11 * 32000))
+
+
+def vdif_task_state_counts_shapes():
+    """Other payload shapes: complex, several channels per thread (register
+    path with 2 and 4 elements per word; histogram path for 8 and 16
+    channels, 4-bit), 1 bit."""
+    from baseband_b200 import levels, tasks
+    for bps, nthread, nchan, cplx, payload in (
+            (2, 8, 1, True, 8000), (2, 2, 4, False, 4000),
+            (2, 2, 8, False, 4000), (2, 1, 16, True, 8000),
+            (1, 4, 1, False, 2000), (1, 2, 8, False, 2000),
+            (1, 1, 64, False, 4000), (4, 2, 1, False, 2000),
+            (4, 1, 4, True, 4000), (2, 1, 64, False, 8000)):
+        nset = 5
+        raw = synthetic.vdif_stream(nset, nthread, payload, bps=bps,
+                                    nchan=nchan, complex_data=cplx,
+                                    seed=100 + bps + nchan, invalid=[3])
+        lv = levels.offset_binary(bps)
+        with bb.vdif.open(io.BytesIO(raw.tobytes()), 'rs', sample_rate=1e6,
+                          squeeze=False, fill_value=np.nan,
+                          chunk_nbytes=2 * nthread * (payload + 32)) as fh:
+            decoded = fh.read()
+            spf = fh.samples_per_frame
+            fh.seek(0)
+            got = tasks.state_counts(fh, 2 * spf)
+            fh.seek(0)
+            power = tasks.integrated_power(fh, 2 * spf, average=False)
+        if cplx:
+            # an invalid complex frame reads as fill + 0j: blank both parts
+            decoded = np.stack([decoded.real, np.where(
+                np.isnan(decoded.real), np.nan, decoded.imag)], -1)
+        want = _counts_from_decoded(decoded, lv, 2 * spf)
+        assert got.shape == want.shape, (got.shape, want.shape)
+        assert np.array_equal(got, want), (bps, nthread, nchan, cplx)
+        x = np.nan_to_num(decoded.astype(np.float64)) ** 2
+        if cplx:
+            x = x.sum(-1)
+        ref = np.stack([x[b * 2 * spf:(b + 1) * 2 * spf].sum(0)
+                        for b in range(3)])
+        assert np.allclose(power, ref, rtol=1e-10, atol=0)   # float64 summation order
+
+
+def mark5b_task_state_counts():
+    from baseband_b200 import levels, tasks
+    raw, valid = synthetic.mark5b_stream(12, invalid_fraction=0.25, seed=9)
+    lv = levels.mark5b(2)
+    decoded = ostream.mark5b_read(raw, 16, fill_value=np.nan)
+    with bb.mark5b.open(io.BytesIO(raw.tobytes()), 'rs', nchan=16,
+                        sample_rate=16e6, kday=56000,
+                        chunk_nbytes=5 * 10016) as fh:
+        got = tasks.state_counts(fh, 4 * 2500)
+    want = _counts_from_decoded(decoded, lv, 4 * 2500)
+    assert got.shape == want.shape == (3, 16, 4)
+    assert np.array_equal(got, want)
+    assert got.sum() == valid.sum() * 2500 * 16

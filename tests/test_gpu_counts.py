@@ -1,0 +1,77 @@
+"""bb_state_counts (csrc/bb_counts.cu) against its numpy restatement
+(tests/cpu_backend.py:_state_counts), through the C ABI: every template
+instance, shuffled / invalid / unaligned units, bins that cut the call at
+arbitrary sets, accumulation over calls."""
+import numpy as np
+import pytest
+import torch
+
+import cpu_backend
+from baseband_b200 import kernels
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+CASES = [(bps, nelem) for bps in (1, 2, 4)
+         for nelem in (1, 2, 4, 8, 16, 32, 64, 256)]
+
+
+@pytest.mark.parametrize('bps,nelem', CASES)
+def test_state_counts_fuzz(bps, nelem):
+    rng = np.random.default_rng(1000 * bps + nelem)
+    for trial in range(4):
+        nthread = int(rng.choice([1, 2, 3, 16]))
+        words_per_sample = max(1, nelem * bps // 32)
+        nword = words_per_sample * int(rng.integers(1, 700))
+        payload = nword * 4
+        nset = int(rng.integers(1, 9))
+        hdr = int(rng.choice([0, 4, 16, 32]))        # 4: unaligned for uint4
+        frame = payload + hdr
+        nunit = nset * nthread
+        raw = rng.integers(0, 256, nunit * frame + 64, dtype=np.uint8)
+        uo = (rng.permutation(nunit).astype(np.int64) * frame + hdr)
+        uo[rng.random(nunit) < 0.15] = -1
+        sets_per_bin = int(rng.integers(1, nset + 2))
+        origin = int(rng.integers(0, 5))
+        nbin = (origin + nset - 1) // sets_per_bin + 1
+        shape = (nbin, nthread, nelem, 1 << bps)
+        want = torch.zeros(shape, dtype=torch.int64)
+        cpu_backend._state_counts(torch.from_numpy(raw), torch.from_numpy(uo),
+                                  nset, nthread, payload, bps, nelem, want,
+                                  origin, sets_per_bin)
+        got = torch.zeros(shape, dtype=torch.int64, device=DEV)
+        d_raw, d_uo = torch.from_numpy(raw).to(DEV), torch.from_numpy(uo).to(DEV)
+        kernels.state_counts(d_raw, d_uo, nset, nthread, payload, bps, nelem,
+                             got, origin, sets_per_bin)
+        assert torch.equal(got.cpu(), want), (bps, nelem, trial)
+        # accumulates
+        kernels.state_counts(d_raw, d_uo, nset, nthread, payload, bps, nelem,
+                             got, origin, sets_per_bin)
+        assert torch.equal(got.cpu(), 2 * want)
+
+
+def test_state_counts_large_and_errors():
+    # C2 geometry, enough sets that the split over CTAs matters
+    nset, nthread, payload = 300, 16, 8000
+    g = torch.Generator(device=DEV).manual_seed(3)
+    raw = torch.randint(0, 256, (nset * nthread * 8032,), dtype=torch.uint8,
+                        device=DEV, generator=g)
+    uo = torch.arange(nset * nthread, dtype=torch.int64, device=DEV) * 8032 + 32
+    got = torch.zeros((3, nthread, 1, 4), dtype=torch.int64, device=DEV)
+    kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1, got, 0, 128)
+    codes = raw.view(nset, nthread, 8032)[:, :, 32:]
+    for c in range(4):
+        per_set = sum(((codes >> (2 * k)) & 3) == c for k in range(4)).sum(-1)
+        want = torch.stack([per_set[b * 128:(b + 1) * 128].sum(0)
+                            for b in range(3)])
+        assert torch.equal(got[:, :, 0, c], want)
+    with pytest.raises(KeyError):                        # 8 bit: unsupported
+        kernels.state_counts(raw, uo, 1, 1, 8000, 8, 1, torch.zeros(
+            (1, 1, 1, 256), dtype=torch.int64, device=DEV))
+    with pytest.raises(ValueError):                      # bins too few
+        kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1,
+                             got[:1], 0, 128)
+    with pytest.raises(ValueError):                      # nelem not 2**k
+        kernels.state_counts(raw, uo, 1, 1, 8000 - 8000 % 12, 2, 3,
+                             torch.zeros((1, 1, 3, 4), dtype=torch.int64,
+                                         device=DEV))
