@@ -279,14 +279,19 @@ BB_HD void rowgroup_emit(const DecGeom &p, const float *lut,
         if (row0 + ii < 0 || row0 + ii >= p.nsample) continue;
         const uint32_t i = c0 + ii;
         F4 v;
+        // (with SEL there is no table in shared memory: same select here)
         if (E == 1) {
-            v.x = ok0 ? decode_one<BPS, CODEC>(w[0], i, lut) : p.fill;
-            v.y = ok1 ? decode_one<BPS, CODEC>(w[1 % G], i, lut) : p.fill;
-            v.z = ok2 ? decode_one<BPS, CODEC>(w[2 % G], i, lut) : p.fill;
-            v.w = ok3 ? decode_one<BPS, CODEC>(w[3 % G], i, lut) : p.fill;
+            v.x = ok0 ? decode_one_v<BPS, CODEC, SEL>(w[0], i, lut, lv)
+                : p.fill;
+            v.y = ok1 ? decode_one_v<BPS, CODEC, SEL>(w[1 % G], i, lut, lv)
+                : p.fill;
+            v.z = ok2 ? decode_one_v<BPS, CODEC, SEL>(w[2 % G], i, lut, lv)
+                : p.fill;
+            v.w = ok3 ? decode_one_v<BPS, CODEC, SEL>(w[3 % G], i, lut, lv)
+                : p.fill;
         } else {
-            F2 a = decode_pair<BPS, CODEC>(w[0], i, lut);
-            F2 b = decode_pair<BPS, CODEC>(w[1 % G], i, lut);
+            F2 a = decode_pair_v<BPS, CODEC, SEL>(w[0], i, lut, lv);
+            F2 b = decode_pair_v<BPS, CODEC, SEL>(w[1 % G], i, lut, lv);
             v.x = ok0 ? a.x : p.fill;
             v.y = ok0 ? a.y : fill_im;
             v.z = ok1 ? b.x : p.fill;

@@ -87,30 +87,47 @@ k_state_counts_reg(const CountGeom p) {
     for (int e = 0; e < NE; ++e) c[e][0] = c[e][1] = c[e][2] = 0u;
     uint32_t nw = 0u;
     const uint32_t nquad = p.nword / 4u;
-    for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
-        const long long off = p.unit_offset[s * p.nthread + t];
-        if (off < 0) continue;                        // invalid frame
-        const uint8_t *base = p.src + off;
-        if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
-            const uint4 *q = reinterpret_cast<const uint4 *>(base);
-#pragma unroll 2
+    // kSets units per round: their offsets first, then one 16-byte load of
+    // each per thread in flight before any counting (memory-level
+    // parallelism; a unit is only a few KB)
+    constexpr int kSets = 4;
+    for (long long s0 = lo + blockIdx.x; s0 < hi;
+         s0 += (long long)p.split * kSets) {
+        const uint8_t *base[kSets];
+        bool vec = true;
+#pragma unroll
+        for (int u = 0; u < kSets; ++u) {
+            const long long s = s0 + (long long)u * p.split;
+            const long long off = s < hi ? p.unit_offset[s * p.nthread + t]
+                : -1;
+            base[u] = off >= 0 ? p.src + off : nullptr;   // < 0: invalid
+            vec = vec && (reinterpret_cast<uintptr_t>(base[u]) & 15u) == 0;
+        }
+        if (vec) {                                   // CTA-uniform
             for (uint32_t i = threadIdx.x; i < nquad; i += kCountBlock) {
-                const uint4 v = q[i];
-                count_word<BPS, NE>(v.x, c);
-                count_word<BPS, NE>(v.y, c);
-                count_word<BPS, NE>(v.z, c);
-                count_word<BPS, NE>(v.w, c);
-                nw += 4u;
+                uint4 v[kSets];
+#pragma unroll
+                for (int u = 0; u < kSets; ++u)
+                    if (base[u])
+                        v[u] = reinterpret_cast<const uint4 *>(base[u])[i];
+#pragma unroll
+                for (int u = 0; u < kSets; ++u)
+                    if (base[u]) {
+                        count_word<BPS, NE>(v[u].x, c);
+                        count_word<BPS, NE>(v[u].y, c);
+                        count_word<BPS, NE>(v[u].z, c);
+                        count_word<BPS, NE>(v[u].w, c);
+                        nw += 4u;
+                    }
             }
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
-            for (uint32_t i = nquad * 4u + threadIdx.x; i < p.nword;
-                 i += kCountBlock) {
-                count_word<BPS, NE>(w[i], c);
-                nw += 1u;
-            }
-        } else {
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
-            for (uint32_t i = threadIdx.x; i < p.nword; i += kCountBlock) {
+        }
+#pragma unroll
+        for (int u = 0; u < kSets; ++u) {
+            if (!base[u]) continue;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base[u]);
+            // tail words of a vector pass, or everything when unaligned
+            for (uint32_t i = (vec ? nquad * 4u : 0u) + threadIdx.x;
+                 i < p.nword; i += kCountBlock) {
                 count_word<BPS, NE>(w[i], c);
                 nw += 1u;
             }
@@ -257,11 +274,11 @@ extern "C" int bb_state_counts(
     g.nthread = nthread;
     g.nelem = nelem;
     g.nword = (uint32_t)(payload_nbytes / 4);
-    // CTAs per (bin, thread): enough to fill the GPU four deep, at most one
+    // CTAs per (bin, thread): enough to fill the GPU sixteen deep, at most one
     // per set of a bin, and few enough words each that 32-bit counters hold
     const int64_t nb = b1 - b0 + 1;
     const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
-    int64_t split = (4ll * sm_count() + nb * nthread - 1) / (nb * nthread);
+    int64_t split = (16ll * sm_count() + nb * nthread - 1) / (nb * nthread);
     const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
         / (1ll << 26);
     if (split < need) split = need;
