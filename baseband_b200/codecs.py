@@ -29,7 +29,7 @@ _zero_offset = {}
 def _offset0(dev):
     key = str(dev)
     if key not in _zero_offset:
-        _zero_offset[key] = torch.zeros(1, dtype=torch.int64, device=dev)
+        _zero_offset[key] = kernels.zeros(1, torch.int64, dev)
     return _zero_offset[key]
 
 

@@ -174,6 +174,32 @@ def pinned_empty(shape, dtype):
     return torch.empty(shape, dtype=dtype, pin_memory=True)
 
 
+class _UseStream:
+    """``with`` block that makes ``stream`` the current one: what
+    ``torch.cuda.stream`` does, minus its per-entry Python overhead (an
+    uncached small read enters three of these; they were a quarter of its
+    cost)."""
+    __slots__ = ('ident', 'index', 'prev')
+
+    def __init__(self, stream):
+        self.ident = (stream.stream_id, stream.device_index,
+                      stream.device_type)
+        self.index = stream.device_index
+        self.prev = None
+
+    def __enter__(self):
+        self.prev = torch._C._cuda_getCurrentStream(self.index)
+        torch._C._cuda_setStream(stream_id=self.ident[0],
+                                 device_index=self.ident[1],
+                                 device_type=self.ident[2])
+
+    def __exit__(self, *exc):
+        prev = self.prev
+        torch._C._cuda_setStream(stream_id=prev[0], device_index=prev[1],
+                                 device_type=prev[2])
+        return False
+
+
 class Streams:
     """The three CUDA streams of the read pipeline: 0 = H2D copies,
     1 = kernels, 2 = D2H copies.  All CUDA stream/event plumbing of the host
@@ -182,9 +208,10 @@ class Streams:
     def __init__(self, dev):
         self.dev = dev
         self.streams = [torch.cuda.Stream(dev) for _ in range(3)]
+        self._use = [_UseStream(s) for s in self.streams]
 
     def use(self, i):
-        return torch.cuda.stream(self.streams[i])
+        return self._use[i]
 
     def wait(self, i, j):
         """Stream i waits for everything queued so far on stream j."""

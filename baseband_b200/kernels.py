@@ -25,12 +25,32 @@ def _count(n=1):
     launch_count += n
 
 
+class _Here:
+    """No-op guard: the device is already current."""
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_HERE = _Here()
+
+
 def _on(device):
+    """Device guard for a C call; free when ``device`` is already current
+    (the per-call cost of ``torch.cuda.device`` showed in small reads)."""
+    index = device.index
+    if index is None or torch._C._cuda_getDevice() == index:
+        return _HERE
     return torch.cuda.device(device)
 
 
 def _stream_ptr(device):
-    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    index = device.index
+    if index is None:
+        index = torch._C._cuda_getDevice()
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(index))
 
 
 def _dev(t, name, dtype=None):
@@ -267,10 +287,23 @@ VDIF_NFIELD = 17
 M5B_NFIELD = 12
 
 
+def zeros(shape, dtype, device):
+    """Zeroed device tensor by ``bb_memset`` (a memset on the current stream,
+    not a fill kernel)."""
+    lib = _lib.load()
+    t = torch.empty(shape, dtype=dtype, device=device)
+    if t.numel():
+        with _on(t.device):
+            _lib.check(lib.bb_memset(ctypes.c_void_p(t.data_ptr()), 0,
+                                     t.numel() * t.element_size(),
+                                     _stream_ptr(t.device)), lib)
+    return t
+
+
 def new_counter(device):
     """Zeroed device int32[1]: the accumulating inconsistency counter the scan
     kernels add to (one per reader, looked at once per ``read``)."""
-    return torch.zeros(1, dtype=torch.int32, device=device)
+    return zeros(1, torch.int32, device)
 
 
 def vdif_scan(src, nframe, frame_stride, header_nbytes, frames_per_set,

@@ -77,9 +77,8 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
         uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
         if 'counts' not in state:
             state['geom'] = (nthread, nelem, bps)
-            state['counts'] = torch.zeros(
-                (nbin, nthread, nelem, 1 << bps), dtype=torch.int64,
-                device=raw.device)
+            state['counts'] = kernels.zeros(
+                (nbin, nthread, nelem, 1 << bps), torch.int64, raw.device)
         kernels.state_counts(raw, uo, nf, nthread, payload_nbytes, bps, nelem,
                              state['counts'], set_origin=f0 - frame0,
                              sets_per_bin=frames_per_bin)

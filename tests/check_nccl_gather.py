@@ -30,15 +30,29 @@ ok = np.array_equal(data.cpu().numpy(), want[a:b])
 whole, span = parallel.read_sharded(fh, gather=True)
 ok = ok and span == (0, want.shape[0]) and np.array_equal(
     whole.cpu().numpy(), want)
-# timing of the gather of a larger decoded shard (NVLink)
-big = torch.empty((1 << 28,), dtype=torch.float32, device=dev)   # 1 GiB
-pieces = [torch.empty_like(big) for _ in range(world)]
-dist.all_gather(pieces, big)
+# host-output readers gather through the same call (NCCL needs device
+# tensors: the shard is read to the device first by the caller's choice of
+# reader; here: a second, uneven stream whose last block is short)
+raw2 = synthetic.vdif_stream(5, 8, 5000, seed=6)
+want2 = ostream.vdif_read(raw2)[:, :, 0]
+fh2 = bb.vdif.open(io.BytesIO(raw2.tobytes()), 'rs', sample_rate=32e6,
+                   device=dev)
+whole2, span2 = parallel.read_sharded(fh2, gather=True)
+ok = ok and span2 == (0, want2.shape[0]) and np.array_equal(
+    whole2.cpu().numpy(), want2)
+# timing of the in-place gather of larger decoded shards (NVLink)
+block = 1 << 28                                                  # 1 GiB f32
+full = torch.empty((world * block,), dtype=torch.float32, device=dev)
+mine = full[rank * block:(rank + 1) * block]
+dist.all_gather_into_tensor(full, mine)
 torch.cuda.synchronize()
+dist.barrier()
 t0 = time.perf_counter()
-dist.all_gather(pieces, big)
+for _ in range(3):
+    dist.all_gather_into_tensor(full, mine)
 torch.cuda.synchronize()
-dt = time.perf_counter() - t0
+dt = (time.perf_counter() - t0) / 3
+big = mine
 flag = torch.tensor([int(ok)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

@@ -15,6 +15,8 @@ SAMPLES = os.path.join(GOLDEN, 'samples')
 def pytest_configure(config):
     config.addinivalue_line(
         'markers', 'gpu: needs a CUDA device (run on the B200 box)')
+    config.addinivalue_line(
+        'markers', 'gpu2: needs two CUDA devices (NCCL; gpurun --gpus 2)')
 
 
 def pytest_collection_modifyitems(config, items):

@@ -249,6 +249,9 @@ def install(monkeypatch):
     monkeypatch.setattr(
         kernels, 'new_counter',
         lambda dev: torch.zeros(1, dtype=torch.int32))
+    monkeypatch.setattr(
+        kernels, 'zeros',
+        lambda shape, dtype, device: torch.zeros(shape, dtype=dtype))
     monkeypatch.setattr(kernels, '_on', lambda d: contextlib.nullcontext())
     monkeypatch.setattr(device, 'is_device_tensor',
                         lambda t: isinstance(t, torch.Tensor))
