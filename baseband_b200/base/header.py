@@ -109,6 +109,33 @@ class BitFieldHeader:
 
     __copy__ = copy
 
+    # -- what does not change within a stream -----------------------------
+    def invariants(self):
+        """Keys of the header parts shared by all headers of a stream
+        (baseband/base/header.py:564-586): the sync pattern unless a class
+        says more."""
+        return {'sync_pattern'} if 'sync_pattern' in self._fields else set()
+
+    def invariant_pattern(self, invariants=None):
+        """``(pattern, mask)``: the header words and, for each, the bits that
+        belong to invariant fields -- what a sync search can match on
+        (baseband/base/header.py:588-647, instance form)."""
+        if invariants is None:
+            invariants = self.invariants()
+        if not invariants:
+            raise ValueError('cannot create an invariant_mask without some '
+                             'invariants')
+        nword = len(self.words)
+        mask = [0] * nword
+        for key in invariants:
+            word, bit, nbits = self._fields[key][:3]
+            if nbits == 64:
+                mask[word] = mask[word + 1] = 0xffffffff
+            else:
+                mask[word] |= (((1 << nbits) - 1) << bit) & 0xffffffff
+        pattern = [int(w) & 0xffffffff for w in self.words]
+        return pattern, mask
+
     # -- dict-like ------------------------------------------------------------
     def keys(self):
         return self._fields.keys()

@@ -563,10 +563,11 @@ class StreamReaderBase(StreamBase):
     def _frames_per_chunk(self):
         return max(1, self._chunk_nbytes // self._frame_nbytes)
 
-    # Streams with frame-level losses (missing / duplicated / re-ordered
-    # frames): a reader may install ``_index``, an int64 table (nframe, nslot)
-    # of PHYSICAL frame numbers in the file (-1 = absent).  Chunks are then
-    # read as the span of physical frames they touch.
+    # Irregular streams (missing / duplicated / re-ordered frames, bytes
+    # lost or inserted between frames): a reader may install ``_index``, an
+    # int64 table (nframe, nslot) of the BYTE OFFSETS of the frames in the
+    # file (-1 = absent), built on the device by `_build_index_on_device`.
+    # Chunks are then read as the byte span of the frames they touch.
     _index = None
 
     def _set_index_table(self, table, phys_frame_nbytes):
@@ -577,25 +578,148 @@ class StreamReaderBase(StreamBase):
         self._phys_frame_nbytes = phys_frame_nbytes
         self._nframe = table.shape[0]
 
-    def _chunk_first_frame(self, frame0, nframe):
+    def _chunk_first_byte(self, frame0, nframe):
+        """File offset of the first frame a chunk touches."""
         lo = self._index_lo[frame0:frame0 + nframe].min()
         return 0 if lo == np.iinfo(np.int64).max else int(lo)
 
     def _chunk_nbytes_of(self, frame0, nframe, sample_start, nsample):
-        """Raw bytes a chunk needs on the device."""
+        """Raw bytes a chunk needs on the device (and in pinned memory)."""
         if self._index is None:
             return nframe * self._frame_nbytes
+        _, span, dev_nbytes, _, _ = self._chunk_layout(frame0, nframe)
+        return max(span, dev_nbytes)
+
+    _layout_cache = None
+
+    def _chunk_layout(self, frame0, nframe):
+        """How the frames of an indexed chunk get to the device:
+        ``(first_byte, span, dev_nbytes, runs, rel)``.  The file bytes
+        [first_byte, first_byte + span) hold every frame of the chunk.  Where
+        all frames sit a multiple of 16 bytes from the first (whole frames
+        missing or re-ordered), that span goes up in one copy.  Bytes lost or
+        inserted between frames shift the later ones off the kernels' word
+        alignment: the span is then copied as ``runs`` of equally aligned
+        frames ``(source offset, device offset, length)``, each to a 16-byte
+        boundary.  ``rel`` (nframe, nslot) = device offset of each frame in
+        the chunk buffer, -1 where absent."""
+        key = (frame0, nframe)
+        if self._layout_cache is not None and self._layout_cache[0] == key:
+            return self._layout_cache[1]
+        fb = self._phys_frame_nbytes
         table = self._index[frame0:frame0 + nframe]
-        first = self._chunk_first_frame(frame0, nframe)
-        last = int(table.max()) + 1 if (table >= 0).any() else first + 1
-        return (last - first) * self._phys_frame_nbytes
+        valid = table >= 0
+        first = self._chunk_first_byte(frame0, nframe)
+        rel = np.full(table.shape, -1, np.int64)
+        if not valid.any():
+            layout = (first, fb, fb, [(0, 0, fb)], rel)
+        else:
+            offs = np.unique(table[valid])               # file order
+            span = int(offs[-1]) + fb - first
+            phase = (offs - first) % 16
+            if not phase.any():
+                rel[valid] = table[valid] - first
+                layout = (first, span, span, [(0, 0, span)], rel)
+            else:
+                breaks = np.flatnonzero(np.diff(phase)) + 1
+                starts = np.concatenate([[0], breaks])
+                stops = np.concatenate([breaks, [offs.size]])
+                shift = np.empty(offs.size, np.int64)
+                runs, dst = [], 0
+                for a, b in zip(starts, stops):
+                    src = int(offs[a]) - first
+                    length = int(offs[b - 1]) + fb - int(offs[a])
+                    runs.append((src, dst, length))
+                    shift[a:b] = dst - src
+                    dst += -(-length // 16) * 16
+                at = np.searchsorted(offs, table[valid])
+                rel[valid] = table[valid] - first + shift[at]
+                layout = (first, span, dst, runs, rel)
+        self._layout_cache = (key, layout)
+        return layout
+
+    def _upload(self, raw, pin, frame0, nframe):
+        """Queue the host-to-device copy of a chunk on the current stream."""
+        if self._index is None:
+            raw.copy_(pin, non_blocking=True)
+            return
+        _, _, _, runs, _ = self._chunk_layout(frame0, nframe)
+        for src, dst, length in runs:
+            raw[dst:dst + length].copy_(pin[src:src + length],
+                                        non_blocking=True)
+
+    def _build_index_on_device(self, pattern, mask, frame_nbytes,
+                               index_chunk, nslot, nset_max):
+        """Frame table of an irregular stream, built on the GPU: the file is
+        streamed through the device in overlapping chunks; in each,
+        bb_locate_frames finds every place the stream's (masked) sync pattern
+        starts a frame that is followed by another one (or the end of the
+        file) -- the reference's `locate_frames` (base/base.py:181-335) over
+        the whole file -- and ``index_chunk(raw, base, locations, count,
+        table, stats)`` scatters the frames found into the table by their
+        header time (bb_vdif_index / bb_mark5b_index).  Returns the table
+        (nset, nslot) of byte offsets on the host and the kernels' stats."""
+        from .. import kernels
+        dev = self.device
+        fh = self.fh_raw
+        size = fh.seek(0, 2)
+        fh.seek(0)
+        pat = np.asarray(pattern, '<u4').view(np.uint8)
+        msk = np.asarray(mask, '<u4').view(np.uint8)
+        overlap = frame_nbytes + pat.size
+        step = max(4 * frame_nbytes, self._chunk_nbytes // frame_nbytes
+                   * frame_nbytes)
+        table = kernels.index_table(nset_max * nslot, dev)
+        stats = kernels.zeros(3, torch.int32, dev)
+        stages, ss = self._pipeline(dev)
+        zero_copy = getattr(fh, 'pinned_view', None)
+        ss.after_caller(1)
+        pos, k = self._file_offset0, 0
+        while pos < size:
+            n = min(step + overlap, size - pos)
+            at_eof = pos + n >= size
+            st = stages[k % 2]
+            if st.done is not None:
+                st.done.synchronize()
+            pin, raw = st.buffers(n, 0, dev, False)
+            view = zero_copy(pos, n) if zero_copy is not None else None
+            if view is None:
+                got = read_file_into(fh, pos, pin.numpy())
+                if got != n:
+                    raise EOFError('could not read the file for indexing.')
+                view = pin
+            with ss.use(0):
+                ss.wait_event(0, st.free)
+                raw.copy_(view, non_blocking=True)
+                st.done = ss.event(0)
+            with ss.use(1):
+                ss.wait_event(1, st.done)
+                locations, count = kernels.locate_frames(
+                    raw, pat, msk, frame_nbytes, 0,
+                    own_stop=n if at_eof else step, check=1, at_eof=at_eof,
+                    base=pos)
+                index_chunk(raw, pos, locations, count, table, stats)
+                st.free = ss.event(1)
+            if at_eof:
+                break
+            pos += step
+            k += 1
+        with ss.use(1):
+            offsets = kernels.index_table_finish(table)
+        ss.caller_after(1)
+        stats = stats.cpu().numpy()
+        nset = int(stats[0]) + 1
+        host = offsets[:nset * nslot].cpu().numpy().reshape(nset, nslot)
+        if not (host >= 0).any():
+            host = host[:0]
+        return host, stats
 
     def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):
         """Fill ``pinned`` (uint8 tensor) with the bytes of frames
         [frame0, frame0 + nframe)."""
         if self._index is not None:
-            offset = self._file_offset0 + self._chunk_first_frame(
-                frame0, nframe) * self._phys_frame_nbytes
+            offset, span = self._chunk_layout(frame0, nframe)[:2]
+            pinned = pinned[:span]
         else:
             offset = self._file_offset0 + frame0 * self._frame_nbytes
         zero_copy = getattr(self.fh_raw, 'pinned_view', None)
@@ -665,19 +789,23 @@ class StreamReaderBase(StreamBase):
     # one device counter per reader; a read looks at it once, at its end.
     _bad_dev = None
     _bad_seen = 0
+    _bad_dirty = False
 
     def _bad_counter(self, dev):
+        """The counter, for a scan that is about to be launched."""
         if self._bad_dev is None or self._bad_dev.device != dev:
             from .. import kernels
             self._bad_dev = kernels.new_counter(dev)
             self._bad_seen = 0
+        self._bad_dirty = True
         return self._bad_dev
 
     def _new_inconsistencies(self):
         """Frames the scan kernels found out of place since the last call
-        (synchronises with the device)."""
-        if self._bad_dev is None:
+        (synchronises with the device, but only if a scan ran since)."""
+        if self._bad_dev is None or not self._bad_dirty:
             return 0
+        self._bad_dirty = False
         now = int(self._bad_dev.item())
         new, self._bad_seen = now - self._bad_seen, now
         return new
@@ -719,7 +847,7 @@ class StreamReaderBase(StreamBase):
             pin = pin if got is None else got
             with ss.use(0):
                 ss.wait_event(0, st.free)
-                raw.copy_(pin, non_blocking=True)
+                self._upload(raw, pin, c0, nf)
                 st.done = ss.event(0)
             with ss.use(1):
                 ss.wait_event(1, st.done)
@@ -753,7 +881,7 @@ class StreamReaderBase(StreamBase):
                 # raw[k%2] must no longer be read by the decode of chunk k-2
                 # (only that: the copy overlaps the decode of chunk k-1)
                 ss.wait_event(0, st.free)
-                raw.copy_(pin, non_blocking=True)
+                self._upload(raw, pin, f0, nf)
                 st.done = ss.event(0)
             with ss.use(1):
                 ss.wait_event(1, st.done)
@@ -815,7 +943,7 @@ class StreamReaderBase(StreamBase):
                 got = self._read_raw(f0, nf, pin, s0, ns)
                 pin = pin if got is None else got
                 with ss.use(0):
-                    raw.copy_(pin, non_blocking=True)
+                    self._upload(raw, pin, f0, nf)
                 with ss.use(1):
                     ss.wait(1, 0)
                     self._decode_chunk(raw, f0, nf, s0, ns, st.dec[:ns * fps])
@@ -866,6 +994,7 @@ class StreamReaderBase(StreamBase):
         state.pop('_slots_dev', None)
         state.pop('_bad_dev', None)
         state.pop('_bad_seen', None)
+        state.pop('_bad_dirty', None)
         state.pop('_sample_shape_cache', None)    # namedtuple made on the fly
         wrapper = state['fh_raw']
         fh = getattr(wrapper, 'fh_raw', wrapper)

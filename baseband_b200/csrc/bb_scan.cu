@@ -119,12 +119,22 @@ k_mark5b_scan(const uint8_t *src, const long long *frame_offset,
     const uint32_t kFill = 0x11223344u;
     const int lane = threadIdx.x & 31;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < nframe;
+    bool live = i < nframe;
     long long off = 0;
     bool candidate = false;
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
     if (live) {
         off = frame_offset ? frame_offset[i] : i * frame_stride;
+        if (off < 0) {
+            // a frame the stream's index knows to be absent
+            if (unit_offset) unit_offset[i] = -1;
+            if (fields)
+                for (int k = 0; k < BB_M5B_NFIELD; ++k)
+                    fields[k * nframe + i] = 0;
+            live = false;
+        }
+    }
+    if (live) {
         const uint8_t *h = src + off;
         w0 = ldw(h); w1 = ldw(h + 4); w2 = ldw(h + 8); w3 = ldw(h + 12);
         candidate = ldw(h + 16) == kFill && ldw(h + 20) == kFill

@@ -436,6 +436,103 @@ def frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
     return frames, unit_offset
 
 
+def _host_bytes(values):
+    arr = np.ascontiguousarray(values).view(np.uint8).reshape(-1)
+    return arr, arr.ctypes.data_as(ctypes.c_void_p)
+
+
+def locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
+                  own_stop=None, check=1, at_eof=True, base=0,
+                  max_locations=None):
+    """bb_locate_frames -> (locations int64 (max_locations,), count int32[1]),
+    both on the device; ``locations[:count]`` are the (unordered) byte
+    positions ``base + loc`` at which the masked pattern starts a frame."""
+    lib = _lib.load()
+    dev = src.device
+    nbytes = src.numel()
+    if own_stop is None:
+        own_stop = nbytes
+    pat, pat_p = _host_bytes(pattern)
+    if mask is not None:
+        msk, msk_p = _host_bytes(mask)
+        if msk.size != pat.size:
+            raise ValueError('mask and pattern must have the same size')
+    else:
+        msk_p = None
+    if max_locations is None:
+        max_locations = (nbytes // frame_nbytes + 2) if frame_nbytes else 4096
+    locations = torch.empty((max(int(max_locations), 1),), dtype=torch.int64,
+                            device=dev)
+    count = zeros(1, torch.int32, dev)
+    with _on(dev):
+        rc = lib.bb_locate_frames(
+            _dev(src, 'src', torch.uint8), nbytes, int(own_stop), pat_p,
+            msk_p, pat.size, int(pattern_offset), int(frame_nbytes),
+            int(check), int(bool(at_eof)), int(base),
+            _dev(locations, 'locations'), int(max_locations),
+            _dev(count, 'count'), _stream_ptr(dev))
+    _lib.check(rc, lib)
+    _count()
+    return locations, count
+
+
+def index_table(nentry, device):
+    """Empty frame table (bb_index_table_init): int64 storage of the uint64
+    entries."""
+    lib = _lib.load()
+    table = torch.empty((int(nentry),), dtype=torch.int64, device=device)
+    with _on(table.device):
+        rc = lib.bb_index_table_init(_dev(table, 'table'), int(nentry),
+                                     _stream_ptr(table.device))
+    _lib.check(rc, lib)
+    _count()
+    return table
+
+
+def vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
+               frame_nr0, fps, nset_max, table, stats):
+    lib = _lib.load()
+    with _on(src.device):
+        rc = lib.bb_vdif_index(
+            _dev(src, 'src', torch.uint8), int(base),
+            _dev(locations, 'locations', torch.int64),
+            _dev(count, 'count', torch.int32), locations.numel(),
+            _dev(thread_slot, 'thread_slot', torch.int32), nthread,
+            int(seconds0), int(frame_nr0), int(fps), int(nset_max),
+            _dev(table, 'table', torch.int64),
+            _dev(stats, 'stats', torch.int32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+
+
+def mark5b_index(src, base, locations, count, jday0, seconds0, frame_nr0,
+                 fps, nset_max, table, stats):
+    lib = _lib.load()
+    with _on(src.device):
+        rc = lib.bb_mark5b_index(
+            _dev(src, 'src', torch.uint8), int(base),
+            _dev(locations, 'locations', torch.int64),
+            _dev(count, 'count', torch.int32), locations.numel(), int(jday0),
+            int(seconds0), int(frame_nr0), int(fps), int(nset_max),
+            _dev(table, 'table', torch.int64),
+            _dev(stats, 'stats', torch.int32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+
+
+def index_table_finish(table):
+    """bb_index_table_finish -> int64 byte offsets, -1 = missing/invalid."""
+    lib = _lib.load()
+    offsets = torch.empty_like(table)
+    with _on(table.device):
+        rc = lib.bb_index_table_finish(
+            _dev(table, 'table', torch.int64), table.numel(),
+            _dev(offsets, 'offsets'), _stream_ptr(table.device))
+    _lib.check(rc, lib)
+    _count()
+    return offsets
+
+
 def state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
                  counts, set_origin=0, sets_per_bin=None):
     """bb_state_counts: add the state counts of ``nset`` frame sets to

@@ -169,17 +169,13 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
 
     def _packed_units(self, raw, frame0, nframe):
         if self._index is not None:
-            # lossy stream: scan the physical frames of the chunk (payload
-            # validity), then pick each stream frame's entry from the index
-            nphys = raw.numel() // 10016
-            fields, uo_phys = kernels.mark5b_scan(raw, nphys)
-            table = self._index[frame0:frame0 + nframe, 0]
-            rel = torch.from_numpy(np.where(
-                table >= 0, table - self._chunk_first_frame(frame0, nframe),
-                0)).to(raw.device)
-            present = torch.from_numpy(table >= 0).to(raw.device)
-            uo = torch.where(present, uo_phys[rel],
-                             torch.full_like(rel, -1))
+            # irregular stream: the frames of the chunk sit where the index
+            # says (`_chunk_layout`); the scan still decides payload validity
+            rel = self._chunk_layout(frame0, nframe)[4][:, 0]
+            _, uo = kernels.mark5b_scan(
+                raw, nframe, frame_offset=torch.from_numpy(
+                    np.ascontiguousarray(rel)).to(raw.device),
+                want_fields=False)
         else:
             # with verify, the frame index the header time implies
             # (mark5b/base.py:206-213) is checked inside the scan kernel
@@ -202,36 +198,26 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
                 + frame_nr - h0['frame_nr'])
 
     def _build_index(self):
-        """Index of a stream with missing / duplicated / re-ordered frames
-        from one strided pass over all headers (cf. VDIFStreamReader)."""
-        from ..base.utils import bcd_decode
-        fh = self.fh_raw
-        size = fh.seek(0, 2)
+        """Frame table of a stream with missing / duplicated / re-ordered
+        frames or bytes lost between frames, built on the GPU from every sync
+        word 0xABADDEED that is followed by another one a frame later (cf.
+        VDIFStreamReader._build_index)."""
+        h0 = self.header0
+        size = self.fh_raw.seek(0, 2)
+        self.fh_raw.seek(0)
         nphys = (size - self._file_offset0) // 10016
-        words = np.empty((nphys, 4), '<u4')
-        step = 4096
-        for first in range(0, nphys, step):
-            n = min(step, nphys - first)
-            fh.seek(self._file_offset0 + first * 10016)
-            block = np.frombuffer(fh.read(n * 10016), np.uint8)
-            words[first:first + n] = block.reshape(n, 10016)[
-                :, :16].copy().view('<u4')
-        ok = words[:, 0] == 0xABADDEED
-        jday = np.zeros(nphys, np.int64)
-        seconds = np.zeros(nphys, np.int64)
-        try:
-            jday[ok] = bcd_decode((words[ok, 2] >> 20).astype(np.uint32))
-            seconds[ok] = bcd_decode((words[ok, 2] & 0xfffff).astype(
-                np.uint32))
-        except ValueError:
+        fps = int(round(self._frame_rate))
+        nset_max = 2 * nphys + fps + 2
+
+        def index_chunk(raw, base, locations, count, table, stats):
+            kernels.mark5b_index(raw, base, locations, count, h0.jday,
+                                 h0.seconds, h0['frame_nr'], fps, nset_max,
+                                 table, stats)
+
+        table, stats = self._build_index_on_device(
+            [0xABADDEED], [0xffffffff], 10016, index_chunk, 1, nset_max)
+        if stats[2]:
             raise OSError('Mark 5B headers with invalid BCD time codes.')
-        frame_nr = (words[:, 1] & 0x7fff).astype(np.int64)
-        index = self._frame_index(jday, seconds, frame_nr)
-        ok &= (index >= 0) & (index < 2 * nphys + int(self._frame_rate))
-        nset = int(index[ok].max()) + 1 if ok.any() else 0
-        table = np.full((nset, 1), -1, np.int64)
-        sel = np.flatnonzero(ok)[::-1]               # first occurrence wins
-        table[index[sel], 0] = sel
         self._set_index_table(table, 10016)
 
     def read(self, count=None, out=None, **kwargs):

@@ -276,11 +276,10 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         dev = raw.device
         nelem = self._sample_shape[1] * (2 if self._complex_data else 1)
         if self._index is not None:
-            # irregular stream: unit table from the host-built frame index
-            table = self._index[frame0:frame0 + nframe]
-            base = self._chunk_first_frame(frame0, nframe)
-            uo = np.where(table >= 0,
-                          (table - base) * h0.frame_nbytes + h0.nbytes, -1)
+            # irregular stream: unit table from the frame index (where each
+            # frame of the chunk was put on the device: `_chunk_layout`)
+            rel = self._chunk_layout(frame0, nframe)[4]
+            uo = np.where(rel >= 0, rel + h0.nbytes, -1)
             uo = torch.from_numpy(np.ascontiguousarray(uo.reshape(-1))).to(dev)
         else:
             if self._slots_dev is None or self._slots_dev.device != dev:
@@ -298,46 +297,38 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
 
     # ------------------------------------------- irregular (lossy) streams
     def _build_index(self):
-        """Host-side index for streams with missing, duplicated or
-        re-ordered frames (the frame-level losses of network recorders; the
-        reference repairs these one frame at a time in ``_bad_frame``,
-        vdif/base.py:536-755).  All frame headers are read with one strided
-        numpy pass; every frame is assigned to (set index, thread slot) from
-        its seconds / frame_nr / thread_id.  Returns an int64 table
-        ``(nset, nthread)`` of physical frame numbers, -1 where a frame is
-        missing or flagged invalid.  Byte-level corruption (frames of the
-        wrong length) is out of scope."""
+        """Frame table for streams with missing, duplicated or re-ordered
+        frames, or with bytes lost or inserted between frames (the losses of
+        network recorders; the reference repairs these one frame at a time in
+        ``_bad_frame``, vdif/base.py:536-755, on top of `locate_frames`,
+        base/base.py:181-335).  Built on the GPU (`_build_index_on_device`):
+        every header that matches the stream's invariant header bits
+        (vdif/header.py:109-115) and is followed by another such header one
+        frame on is assigned to (set index, thread slot) from its seconds /
+        frame_nr / thread_id; the first such frame in the file wins, frames
+        flagged invalid count as missing.  Installs an int64 table
+        ``(nset, nthread)`` of frame byte offsets, -1 where there is none."""
         h0 = self.header0
-        fh = self.fh_raw
-        size = fh.seek(0, 2)
+        dev = self.device
+        size = self.fh_raw.seek(0, 2)
+        self.fh_raw.seek(0)
         nphys = size // h0.frame_nbytes
-        words = np.empty((nphys, 4), '<u4')
-        step = max(1, (64 << 20) // h0.frame_nbytes)
-        for first in range(0, nphys, step):
-            n = min(step, nphys - first)
-            fh.seek(first * h0.frame_nbytes)
-            block = np.frombuffer(fh.read(n * h0.frame_nbytes), np.uint8)
-            words[first:first + n] = block.reshape(n, h0.frame_nbytes)[
-                :, :16].copy().view('<u4')
-        fh.seek(0)
-        seconds = (words[:, 0] & 0x3fffffff).astype(np.int64)
-        invalid = (words[:, 0] >> 31).astype(bool)
-        frame_nr = (words[:, 1] & 0xffffff).astype(np.int64)
-        tid = ((words[:, 3] >> 16) & 0x3ff).astype(np.int64)
         fps = int(round(self._frame_rate))
-        index = (seconds - h0['seconds']) * fps + frame_nr - h0['frame_nr']
-        slot = self._slots_host[tid].astype(np.int64)
-        ok = (index >= 0) & (slot >= 0) & (index < 2 * nphys + fps)
-        nset = int(index[ok].max()) + 1 if ok.any() else 0
-        table = np.full((nset, len(self._decode_ids)), -1, np.int64)
-        phys = np.arange(nphys, dtype=np.int64)
-        # first occurrence wins: assign in reverse order
-        sel = np.flatnonzero(ok)[::-1]
-        table[index[sel], slot[sel]] = phys[sel]
-        # frames flagged invalid decode to fill: drop them from the table
-        bad = np.flatnonzero(ok & invalid)
-        hit = table[index[bad], slot[bad]] == phys[bad]
-        table[index[bad][hit], slot[bad][hit]] = -1
+        nthread_file = max(1, len(self._file_thread_ids))
+        nslot = len(self._decode_ids)
+        nset_max = 2 * (nphys // nthread_file) + fps + 2
+        pattern, mask = h0.invariant_pattern()
+        if self._slots_dev is None or self._slots_dev.device != dev:
+            self._slots_dev = torch.from_numpy(self._slots_host).to(dev)
+
+        def index_chunk(raw, base, locations, count, table, stats):
+            kernels.vdif_index(raw, base, locations, count, self._slots_dev,
+                               nslot, h0['seconds'], h0['frame_nr'], fps,
+                               nset_max, table, stats)
+
+        table, stats = self._build_index_on_device(
+            pattern, mask, h0.frame_nbytes, index_chunk, nslot, nset_max)
+        self._index_stats = {'frames_outside_table': int(stats[1])}
         self._set_index_table(table, h0.frame_nbytes)
 
     def read(self, count=None, out=None, **kwargs):

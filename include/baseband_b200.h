@@ -249,7 +249,9 @@ int bb_vdif_scan(const void *src, const int64_t *frame_offset,
  * device int32) unless its sync word is 0xABADDEED, its BCD time is valid and
  *   (seconds - seconds0 + 86400 * dday) * frames_per_second
  *       + frame_nr - frame_nr0 == index0 + i,
- * dday = jday - jday0 wrapped into [-500, 500).  `fields` may be NULL. */
+ * dday = jday - jday0 wrapped into [-500, 500).  `fields` may be NULL.
+ * A negative frame_offset[i] marks a frame the stream's index knows to be
+ * absent: unit_offset[i] = -1, fields 0, nothing is read. */
 typedef enum bb_mark5b_field {
     BB_M5B_SYNC = 0, BB_M5B_USER, BB_M5B_INTERNAL_TVG, BB_M5B_FRAME_NR,
     BB_M5B_BCD_JDAY, BB_M5B_BCD_SECONDS, BB_M5B_BCD_FRACTION, BB_M5B_CRC,
@@ -298,6 +300,62 @@ int bb_frames_assemble(void *dst, int64_t nframe, int64_t frame_stride,
                        int64_t payload_nbytes, int32_t units_per_frame,
                        int64_t unit_stride, int64_t *unit_offset,
                        void *stream);
+
+/* ------------------------------------------ frame location and frame index
+ * The device-side replacement for the reference's sync search and frame
+ * bookkeeping of irregular streams (`locate_frames`,
+ * baseband/base/base.py:181-335; `RawOffsets`, baseband/base/offsets.py:6-126;
+ * the per-frame repair of baseband/vdif/base.py:536-755 and the read-ahead
+ * verification of baseband/base/base.py:1083-1219).
+ *
+ * bb_locate_frames: every byte position loc in [0, own_stop) of the device
+ * region src[0, nbytes) where the masked pattern (host arrays of
+ * pattern_nbytes <= 256 bytes; mask NULL = all ones) occurs at
+ * loc + pattern_offset AND -- with frame_nbytes > 0 and check != 0 -- again
+ * at loc + pattern_offset + check * frame_nbytes if that position lies inside
+ * the region (the reference's `check=1`).  With at_eof != 0 the region ends
+ * the file: frames must fit in it and a check position beyond it is not
+ * required; otherwise a position whose check cannot be seen is left to the
+ * next (overlapping) region.  base + loc is appended (atomically, unordered)
+ * to locations[0, max_locations); *count (device int32, caller-zeroed)
+ * receives the number found, which may exceed max_locations.
+ *
+ * Frame table: uint64 entries, bb_index_table_init sets them to "empty".
+ * bb_vdif_index / bb_mark5b_index read the header at every location found
+ * (src = device copy of the file bytes from offset `base` on), compute its
+ * frame index relative to the stream's first header
+ *   VDIF    (seconds - seconds0) * fps + frame_nr - frame_nr0, slot from
+ *           thread_slot[thread_id]        (baseband/vdif/base.py:386-390)
+ *   Mark 5B (seconds - seconds0 + 86400 * dday) * fps + frame_nr - frame_nr0,
+ *           BCD jday / seconds, dday = jday - jday0 wrapped to [-500, 500)
+ *                                        (baseband/mark5b/base.py:206-213)
+ * and keep, per (index, slot), the frame that comes first in the file
+ * (atomicMin of 2 * offset + invalid flag).  stats (device int32[3],
+ * caller-zeroed): [0] largest index seen, [1] frames outside
+ * [0, nset_max), [2] headers with an invalid BCD time.
+ * bb_index_table_finish turns the table into int64 byte offsets of the
+ * frames, -1 where a frame is missing or flagged invalid: the
+ * `frame_offset` / unit tables the scan and decode kernels take. */
+int bb_locate_frames(const void *src, int64_t nbytes, int64_t own_stop,
+                     const uint8_t *pattern, const uint8_t *mask,
+                     int32_t pattern_nbytes, int64_t pattern_offset,
+                     int64_t frame_nbytes, int32_t check, int32_t at_eof,
+                     int64_t base, int64_t *locations, int32_t max_locations,
+                     int32_t *count, void *stream);
+int bb_index_table_init(uint64_t *table, int64_t nentry, void *stream);
+int bb_vdif_index(const void *src, int64_t base, const int64_t *locations,
+                  const int32_t *count, int32_t max_locations,
+                  const int32_t *thread_slot, int32_t nthread,
+                  int32_t seconds0, int32_t frame_nr0,
+                  int32_t frames_per_second, int64_t nset_max,
+                  uint64_t *table, int32_t *stats, void *stream);
+int bb_mark5b_index(const void *src, int64_t base, const int64_t *locations,
+                    const int32_t *count, int32_t max_locations,
+                    int32_t jday0, int32_t seconds0, int32_t frame_nr0,
+                    int32_t frames_per_second, int64_t nset_max,
+                    uint64_t *table, int32_t *stats, void *stream);
+int bb_index_table_finish(const uint64_t *table, int64_t nentry,
+                          int64_t *offsets, void *stream);
 
 /* ------------------------------------------------- consumers on the device
  * The plug-in point for analysis that follows the decode is

@@ -107,6 +107,9 @@ def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None,
     for i in range(nframe):
         off = int(frame_offset[i]) if frame_offset is not None \
             else i * frame_stride
+        if off < 0:                       # absent according to the index
+            uo[i] = -1
+            continue
         h = oheaders.mark5b_parse(buf[off:off + 16].view('<u4'))
         pl = buf[off + 16:off + 10016].view('<u4')
         valid = not bool((pl == 0x11223344).all())
@@ -188,6 +191,110 @@ def _frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
     return frames, torch.from_numpy(uo.reshape(-1))
 
 
+_EMPTY = -1            # 0xffff...ff as int64
+
+
+def _locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
+                   own_stop=None, check=1, at_eof=True, base=0,
+                   max_locations=None):
+    """k_locate_frames restated with numpy (csrc/bb_index.cu)."""
+    buf = src.numpy()
+    nbytes = buf.size
+    own_stop = nbytes if own_stop is None else min(own_stop, nbytes)
+    pat = np.ascontiguousarray(pattern).view(np.uint8).reshape(-1)
+    msk = (np.ascontiguousarray(mask).view(np.uint8).reshape(-1)
+           if mask is not None else np.full(pat.size, 0xff, np.uint8))
+    n = pat.size
+    if nbytes < n:
+        hits = np.zeros(0, bool)
+    else:
+        win = np.lib.stride_tricks.sliding_window_view(buf, n)
+        hits = (((win ^ pat) & msk) == 0).all(-1)       # index = pattern pos
+    found = []
+    for loc in range(own_stop):
+        at = loc + pattern_offset
+        if at + n > nbytes or not hits[at]:
+            continue
+        if frame_nbytes > 0:
+            if at_eof and loc + frame_nbytes > nbytes:
+                continue
+            if check:
+                c = at + check * frame_nbytes
+                if c >= 0 and c + n <= nbytes:
+                    if not hits[c]:
+                        continue
+                elif not at_eof and c + n > nbytes:
+                    continue
+        found.append(base + loc)
+    if max_locations is None:
+        max_locations = (nbytes // frame_nbytes + 2) if frame_nbytes else 4096
+    out = np.zeros(max(int(max_locations), 1), np.int64)
+    keep = found[:max_locations]
+    out[:len(keep)] = keep
+    return torch.from_numpy(out), torch.tensor([len(found)], dtype=torch.int32)
+
+
+def _index_table(nentry, device):
+    return torch.full((int(nentry),), _EMPTY, dtype=torch.int64)
+
+
+def _scatter(table, at, off, invalid):
+    t = table.numpy().view(np.uint64)
+    t[at] = min(int(t[at]), 2 * int(off) + int(invalid))
+
+
+def _vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
+                frame_nr0, fps, nset_max, table, stats):
+    buf, slots, st = src.numpy(), thread_slot.numpy(), stats.numpy()
+    for off in locations.numpy()[:min(int(count), locations.numel())]:
+        w = buf[off - base:off - base + 16].copy().view('<u4')
+        index = ((int(w[0]) & 0x3fffffff) - seconds0) * fps \
+            + (int(w[1]) & 0xffffff) - frame_nr0
+        slot = slots[(int(w[3]) >> 16) & 0x3ff]
+        if not 0 <= slot < nthread:
+            continue
+        if not 0 <= index < nset_max:
+            st[1] += 1
+            continue
+        _scatter(table, index * nthread + slot, off, int(w[0]) >> 31)
+        st[0] = max(st[0], index)
+
+
+def _mark5b_index(src, base, locations, count, jday0, seconds0, frame_nr0,
+                  fps, nset_max, table, stats):
+    buf, st = src.numpy(), stats.numpy()
+
+    def bcd(v, nd):
+        out = 0
+        for d in range(nd):
+            nib = (v >> (4 * d)) & 0xf
+            if nib > 9:
+                return -1
+            out += nib * 10 ** d
+        return out
+    for off in locations.numpy()[:min(int(count), locations.numel())]:
+        w = buf[off - base:off - base + 16].copy().view('<u4')
+        jday, seconds = bcd(int(w[2]) >> 20, 3), bcd(int(w[2]), 5)
+        if jday < 0 or seconds < 0:
+            st[2] += 1
+            continue
+        dday = (jday - jday0 + 1500) % 1000 - 500
+        index = (seconds - seconds0 + 86400 * dday) * fps \
+            + (int(w[1]) & 0x7fff) - frame_nr0
+        if not 0 <= index < nset_max:
+            st[1] += 1
+            continue
+        _scatter(table, index, off, 0)
+        st[0] = max(st[0], index)
+
+
+def _index_table_finish(table):
+    t = table.numpy().view(np.uint64)
+    out = np.where((t == np.uint64(0xffffffffffffffff)) | (t & np.uint64(1)).astype(bool),
+                   np.int64(-1), (t >> np.uint64(1)).astype(np.int64))
+    return torch.from_numpy(out.astype(np.int64))
+
+
 def _state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
                   counts, set_origin=0, sets_per_bin=None):
     """numpy restatement of bb_state_counts (csrc/bb_counts.cu)."""
@@ -246,6 +353,11 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
     monkeypatch.setattr(kernels, 'frames_assemble', _frames_assemble)
     monkeypatch.setattr(kernels, 'state_counts', _state_counts)
+    monkeypatch.setattr(kernels, 'locate_frames', _locate_frames)
+    monkeypatch.setattr(kernels, 'index_table', _index_table)
+    monkeypatch.setattr(kernels, 'vdif_index', _vdif_index)
+    monkeypatch.setattr(kernels, 'mark5b_index', _mark5b_index)
+    monkeypatch.setattr(kernels, 'index_table_finish', _index_table_finish)
     monkeypatch.setattr(
         kernels, 'new_counter',
         lambda dev: torch.zeros(1, dtype=torch.int32))

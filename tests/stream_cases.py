@@ -1460,3 +1460,68 @@ def mark5b_task_state_counts():
     assert got.shape == want.shape == (3, 16, 4)
     assert np.array_equal(got, want)
     assert got.sum() == valid.sum() * 2500 * 16
+
+
+# -------------------------------------------- byte-level damage (GPU index)
+def vdif_byte_slip():
+    """Bytes lost inside a frame and bytes inserted between frames: the GPU
+    frame index (sync search on the stream's invariant header bits + check
+    one frame on, `locate_frames` of base/base.py:181-335, then placement by
+    header time) recovers every frame that is followed by a header where it
+    should be; the others read as fill_value."""
+    import warnings
+    nset, nthread = 9, 4
+    raw = synthetic.vdif_stream(nset, nthread, 5000, seed=43,
+                                thread_order=np.arange(nthread))
+    full = ostream.vdif_read(raw)[:, :, 0]
+    rng = np.random.default_rng(2)
+    for cut, extra in (((13, 700, 1234), None),       # cut inside frame 13
+                       (None, (22, 7)),               # 7 bytes after frame 21
+                       ((17, 100, 2), (30, 10001))):  # both; odd alignments
+        pieces, lost = raw.copy(), []
+        if extra is not None:
+            at, n = extra
+            pieces = np.concatenate([
+                pieces[:at * 5032], rng.integers(0, 256, n, dtype=np.uint8),
+                pieces[at * 5032:]])
+            lost.append(at - 1)          # its check lands in the garbage
+        if cut is not None:
+            i, a, n = cut
+            pieces = np.concatenate([pieces[:i * 5032 + a],
+                                     pieces[i * 5032 + a + n:]])
+            lost.append(i)               # truncated
+        want = full.copy()
+        for i in lost:
+            s, t = divmod(i, nthread)
+            want[s * 20000:(s + 1) * 20000, t] = -7.
+        for chunk in (None, 3 * nthread * 5032):
+            with warnings.catch_warnings(record=True):
+                warnings.simplefilter('always')
+                with bb.vdif.open(io.BytesIO(pieces.tobytes()), 'rs',
+                                  sample_rate=32e6, fill_value=-7.,
+                                  chunk_nbytes=chunk) as fh:
+                    data = fh.read()
+                    assert fh._index is not None
+                    assert data.shape == want.shape, (data.shape, want.shape)
+                    _same(data, want)
+                    fh.seek(39990)
+                    _same(fh.read(20020), want[39990:60010])
+
+
+def mark5b_byte_slip():
+    """The reference's own corrupted Mark 5B file (mark5b/tests/
+    test_mark5b.py:508-524: bytes [10040, 20000) of sample.m5b cut out):
+    frame 1 is gone, frames 2 and 3 sit 9960 bytes early."""
+    import warnings
+    m5 = np.fromfile(sample_path('sample.m5b'), np.uint8)
+    bad = np.concatenate([m5[:10040], m5[20000:]])
+    want = OUT['sample_m5b_data'].copy()
+    want[5000:10000] = -3.
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        with bb.mark5b.open(io.BytesIO(bad.tobytes()), 'rs', nchan=8,
+                            sample_rate=32e6, kday=56000,
+                            fill_value=-3.) as fh:
+            assert fh._index is not None
+            assert fh._index[:, 0].tolist() == [0, -1, 10072, 20088]
+            _same(fh.read(), want)

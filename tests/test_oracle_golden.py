@@ -317,3 +317,66 @@ def test_encode_round_trips(sample_outputs):
     words = raw[0xa88 + 1280:0xa88 + 160000].view('<u8')
     d = codec.mark4_decode(words, 8, 4)
     assert np.array_equal(codec.mark4_encode(d, 8, 4), words)
+
+
+def test_locate_frames_oracle_known_answers():
+    """oracle.locate.locate_frames against the answers the reference's own
+    tests assert (vdif/tests/test_vdif.py:695-760, mark5b/tests/
+    test_mark5b.py:489-506)."""
+    from oracle import locate
+    from conftest import sample_bytes
+    data = sample_bytes('sample.vdif')
+    size = data.size
+    words = data[:32].view('<u4')
+    sync = int(words[5])
+    every = [x * 5032 for x in range(16)]
+    assert sync == 0xACABFEED
+    assert locate.locate_frames(data, 0, sync, offset=20) == every
+    assert locate.locate_frames(data, size, sync, offset=20,
+                                forward=False) == every[::-1]
+    mask = [0, 0, 0xffffffff, 0xfc00ffff, 0xffffffff, 0, 0, 0]
+    assert locate.locate_frames(data, 10, words, mask=mask,
+                                frame_nbytes=5032) == [5032, 10064]
+    # the header's invariants (what passing header0 means)
+    inv = [0x40000000, 0, 0xffffffff, 0xfc00ffff, 0xffffffff, 0xffffffff,
+           0, 0]
+    for pos, fwd, want in ((5000, True, [5032, 10064]),
+                           (15000, True, [15096, 20128]),
+                           (20128, True, [20128, 25160]),
+                           (16, False, [0]),
+                           (size - 10000, False, [14 * 5032, 13 * 5032]),
+                           (size - 5000, False, [15 * 5032, 14 * 5032]),
+                           (size - 20, True, []),
+                           (40254, True, [8 * 5032, 9 * 5032]),
+                           (40254, False, [7 * 5032, 6 * 5032])):
+        assert locate.locate_frames(data, pos, words, mask=inv,
+                                    frame_nbytes=5032, forward=fwd) == want
+    m5 = sample_bytes('sample.m5b')
+    s5 = 0xABADDEED
+    assert locate.locate_frames(m5, 0, s5, frame_nbytes=10016) == [0, 10016]
+    assert locate.locate_frames(m5, 0, s5, frame_nbytes=10016,
+                                forward=False) == [0]
+    assert locate.locate_frames(m5, 10000, s5, frame_nbytes=10016) \
+        == [10016, 20032]
+    assert locate.locate_frames(m5, 16, s5, frame_nbytes=10016,
+                                forward=False) == [0]
+    assert locate.locate_frames(m5, m5.size - 20, s5, frame_nbytes=10016) == []
+    assert locate.locate_frames(m5, m5.size - 10000, s5, frame_nbytes=10016,
+                                forward=False) == [3 * 10016, 2 * 10016]
+    assert locate.locate_frames(m5, m5.size - 30, s5, frame_nbytes=10016) == []
+    # the reference's corrupted file (test_mark5b.py:508-524): bytes
+    # [10040, 20000) cut out
+    bad = np.concatenate([m5[:10040], m5[20000:]])
+    shifted = 2 * 10016 - 9960
+    assert locate.locate_frames(bad, 0, s5, frame_nbytes=10016) == [0, shifted]
+    assert locate.locate_frames(bad, 0, s5, frame_nbytes=10016,
+                                check=None) == [0, 10016, shifted]
+    assert locate.locate_frames(bad, 10000, s5, frame_nbytes=10016) \
+        == [shifted, shifted + 10016]
+    assert locate.locate_frames(bad, 10000, s5, frame_nbytes=10016,
+                                check=None) == [10016, shifted,
+                                                shifted + 10016]
+    short = m5[:10018]
+    assert locate.locate_frames(short, 10, s5, frame_nbytes=10016) == []
+    assert locate.locate_frames(short, 10, s5, frame_nbytes=10016,
+                                forward=False) == [0]
