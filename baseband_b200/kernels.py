@@ -437,7 +437,12 @@ def frames_assemble(headers, frame_nbytes, payload_nbytes=0, valid=None,
 
 
 def _host_bytes(values):
-    arr = np.ascontiguousarray(values).view(np.uint8).reshape(-1)
+    """Byte view of a pattern: bytes stay bytes, integers are unsigned 32-bit
+    little-endian words (`byte_array`, baseband/base/utils.py:251-270)."""
+    arr = np.asarray(values)
+    if arr.dtype.kind in 'iu' and arr.dtype.itemsize != 1:
+        arr = arr.astype('<u4')
+    arr = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
     return arr, arr.ctypes.data_as(ctypes.c_void_p)
 
 

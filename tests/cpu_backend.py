@@ -201,9 +201,10 @@ def _locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
     buf = src.numpy()
     nbytes = buf.size
     own_stop = nbytes if own_stop is None else min(own_stop, nbytes)
-    pat = np.ascontiguousarray(pattern).view(np.uint8).reshape(-1)
-    msk = (np.ascontiguousarray(mask).view(np.uint8).reshape(-1)
-           if mask is not None else np.full(pat.size, 0xff, np.uint8))
+    from baseband_b200.kernels import _host_bytes
+    pat = _host_bytes(pattern)[0]
+    msk = (_host_bytes(mask)[0] if mask is not None
+           else np.full(pat.size, 0xff, np.uint8))
     n = pat.size
     if nbytes < n:
         hits = np.zeros(0, bool)

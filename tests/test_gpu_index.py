@@ -117,8 +117,8 @@ def test_vdif_and_mark5b_index_tables():
     want = locate.frame_table(blob, locs, index_of, nthread,
                               lambda loc: blob[loc + 3] >> 7)
     d = torch.from_numpy(blob).to(DEV)
-    loc, cnt = kernels.locate_frames(d, words, [0x40000000, 0, 0xffffffff,
-                                                0xfc00ffff], 1032)
+    loc, cnt = kernels.locate_frames(d, words[:4], [0x40000000, 0, 0xffffffff,
+                                                    0xfc00ffff], 1032)
     slot = torch.from_numpy(np.arange(1024, dtype=np.int32)).to(DEV)
     table = kernels.index_table(20 * nthread, DEV)
     stats = kernels.zeros(3, torch.int32, DEV)
