@@ -96,6 +96,29 @@ k_probe_expand(float4 *dst, const uint32_t *src, unsigned long long n4,
     }
 }
 
+// 1:4 expansion (8 bit -> float32), ideal patterns: a warp reads 1 KiB
+// contiguous (two 16-byte loads per lane) and writes 4 KiB contiguous.
+__global__ void __launch_bounds__(kProbeBlock)
+k_probe_expand4(float4 *dst, const uint4 *src, unsigned long long n4) {
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const unsigned long long chunk =
+        (unsigned long long)blockIdx.x * (kProbeBlock / 32) + warp;
+    const unsigned long long base = chunk * (32 * kProbeF4);
+    if (base >= n4) return;
+    const uint4 a = src[chunk * 64 + lane], b = src[chunk * 64 + 32 + lane];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < kProbeF4; ++j) {
+        const unsigned long long i = base + j * 32 + lane;
+        const float4 v = make_float4(
+            __uint_as_float(0x3f800000u | (w[j] & 0xffu)),
+            __uint_as_float(0x3f800000u | ((w[j] >> 8) & 0xffu)),
+            __uint_as_float(0x3f800000u | ((w[j] >> 16) & 0xffu)),
+            __uint_as_float(0x3f800000u | (w[j] >> 24)));
+        if (i < n4) dst[i] = v;
+    }
+}
+
 // Pull `nbytes` of src into L2 with evict_last priority (a pure-read phase
 // ahead of a kernel that then finds its input in L2).
 __global__ void __launch_bounds__(256)
@@ -141,7 +164,12 @@ extern "C" int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
         return set_error(BB_ERR_ARGUMENT, "buffer too large for one launch");
     // pattern 1: 16 streams of nbytes / 16 / 16 bytes each
     const unsigned long long stride_words = (unsigned long long)nbytes / 1024;
-    if (pattern == 1)
+    if (pattern == 3) {
+        if (!aligned(src, 16))
+            return set_error(BB_ERR_ALIGNMENT, "src must be 16-byte aligned");
+        k_probe_expand4<<<(unsigned)grid, kProbeBlock, 0, as_stream(stream)>>>(
+            (float4 *)dst, (const uint4 *)src, n4);
+    } else if (pattern == 1)
         k_probe_expand<1><<<(unsigned)grid, kProbeBlock, 0,
                             as_stream(stream)>>>(
             (float4 *)dst, (const uint32_t *)src, n4, stride_words);

@@ -118,6 +118,8 @@ def decode_bitfield(src, unit_offset, nset, nthread, payload_nbytes, bps,
                           device=src.device)
     elif out.numel() != nsample * nthread * nelem:
         raise ValueError('out has the wrong number of elements')
+    if out.numel() == 0:
+        return out                       # an empty tensor has no storage
     keep, lv = _levels_arg(levels)
     with _on(src.device):
         rc = lib.bb_decode_bitfield(
@@ -139,6 +141,8 @@ def encode_bitfield(data, dst, unit_offset, nset, nthread, payload_nbytes,
     lib = _lib.load()
     _require_cuda(data, dst, unit_offset)
     code = _float_code(data)
+    if data.numel() == 0:
+        return dst                      # nothing to encode
     with _on(dst.device):
         rc = lib.bb_encode_bitfield(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -159,6 +163,8 @@ def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
     if out is None:
         out = torch.empty((nsample, nchan), dtype=torch.float32,
                           device=src.device)
+    if out.numel() == 0:
+        return out
     keep, lv = _levels_arg(levels)
     with _on(src.device):
         rc = lib.bb_mark4_decode(
@@ -175,6 +181,8 @@ def mark4_decode(src, unit_offset, nframe, nchan, fanout, ft=False,
 def mark4_encode(data, dst, unit_offset, nframe, nchan, fanout, ft=False):
     lib = _lib.load()
     code = _float_code(data)
+    if data.numel() == 0:
+        return dst                      # nothing to encode
     with _on(dst.device):
         rc = lib.bb_mark4_encode(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -204,6 +212,8 @@ def mark4_decode_words(words, nword, nchan, fanout, ft=False, levels=None,
 def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
     lib = _lib.load()
     code = _float_code(data)
+    if data.numel() == 0:
+        return words                      # nothing to encode
     with _on(words.device):
         rc = lib.bb_mark4_encode_words(
             _dev(data, 'data'), code, _dev(words, 'words'), nword, nchan,
@@ -216,6 +226,8 @@ def mark4_encode_words(data, words, nword, nchan, fanout, ft=False):
 def decode_int8_transposed(src, unit_offset, nunit, nrow, ncol, item_nbytes,
                            col_begin, col_end, out_col0, out):
     lib = _lib.load()
+    if out.numel() == 0:
+        return out
     with _on(src.device):
         rc = lib.bb_decode_int8_transposed(
             _dev(src, 'src', torch.uint8),
@@ -233,6 +245,8 @@ def encode_int8_transposed(data, dst, unit_offset, nunit, nrow, ncol,
                            item_nbytes):
     lib = _lib.load()
     code = _float_code(data)
+    if data.numel() == 0:
+        return dst                      # nothing to encode
     with _on(dst.device):
         rc = lib.bb_encode_int8_transposed(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -248,6 +262,8 @@ def decode_int8_timefirst(src, unit_offset, nunit, nsample, nchan, npol,
     """bb_decode_int8_timefirst: [time][chan][pol] int8 -> (time, pol, chan)
     float32 rows of ``out``."""
     lib = _lib.load()
+    if out.numel() == 0:
+        return out
     with _on(src.device):
         rc = lib.bb_decode_int8_timefirst(
             _dev(src, 'src', torch.uint8),
@@ -265,6 +281,8 @@ def encode_int8_timefirst(data, dst, unit_offset, nunit, nsample, nchan, npol,
                           item_nbytes):
     lib = _lib.load()
     code = _float_code(data)
+    if data.numel() == 0:
+        return dst                      # nothing to encode
     with _on(dst.device):
         rc = lib.bb_encode_int8_timefirst(
             _dev(data, 'data'), code, _dev(dst, 'dst', torch.uint8),
@@ -594,11 +612,12 @@ def probe_expand(dst, src, pattern=0):
     ``src`` (the ceiling for a 2 bit -> float32 stream)."""
     lib = _lib.load()
     nbytes = dst.numel() * dst.element_size() // 4096 * 4096
-    if src.numel() * src.element_size() < nbytes // 16:
+    ratio = 4 if pattern == 3 else 16
+    if src.numel() * src.element_size() < nbytes // ratio:
         raise ValueError('src too small')
     with _on(dst.device):
         rc = lib.bb_probe_expand(_dev(dst, 'dst'), nbytes, _dev(src, 'src'),
                                  pattern, _stream_ptr(dst.device))
     _lib.check(rc, lib)
     _count()
-    return nbytes + nbytes // 16
+    return nbytes + nbytes // ratio

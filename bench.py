@@ -531,16 +531,26 @@ def measure_e2e(args, dev, rank, world, lv, slot):
     # Link rates for context: plain pinned <-> device copies of the same
     # buffers (what PCIe delivers on this box).
     def copy_rate(dst, srcbuf):
+        # all ranks copy at the same time (barrier first), slowest rank's rate:
+        # the link as the e2e pipeline finds it, not an idle one
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         dst.copy_(srcbuf, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
         e0.record()
         for _ in range(3):
             dst.copy_(srcbuf, non_blocking=True)
         e1.record()
         torch.cuda.synchronize(dev)
-        return 3 * srcbuf.numel() * srcbuf.element_size() / (
+        rate = 3 * srcbuf.numel() * srcbuf.element_size() / (
             e0.elapsed_time(e1) * 1e-3) / 1e9
+        if world > 1:
+            t = torch.tensor([rate], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            rate = float(t.item())
+        return rate
 
     probe = torch.empty_like(host_out, device=dev)
     d2h_gbs = copy_rate(host_out, probe)
@@ -561,10 +571,14 @@ def measure_e2e(args, dev, rank, world, lv, slot):
                 'e2e_d2h_gbs': (host_out.numel() * 4 + src.size) * steps
                 / dt / 1e9,
                 'ingest_h2d_gbs': src.size * steps / dt_dev / 1e9,
-                'note': 'e2e moves 4 B/sample device->host: e2e_d2h_gbs vs '
-                        'd2h_copy_gbs is the fraction of the link it '
-                        'reaches; ingest_h2d_gbs is the packed-frame ingest '
-                        'rate of the device-output path'},
+                'e2e_fraction_of_d2h_link': (host_out.numel() * 4 + src.size)
+                * steps / dt / 1e9 / d2h_gbs,
+                'note': 'link rates: plain pinned copies of the same buffers '
+                        'with all ranks copying at once (barrier, slowest '
+                        'rank).  e2e moves 4 B/sample device->host: '
+                        'e2e_d2h_gbs vs d2h_copy_gbs is the fraction of the '
+                        'link it reaches; ingest_h2d_gbs is the packed-frame '
+                        'ingest rate of the device-output path'},
             'api': "vdif.open(HostBuffer,'rs').read(out=pinned numpy, "
                    "on_device=vdif.open(HostBuffer,'ws').write)",
             'note': 'per GPU {} MiB packed per step; PCIe bound: the decoded '

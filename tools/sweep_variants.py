@@ -77,6 +77,8 @@ def main():
     for pat, what in ((0, 'contiguous input'), (1, '16 input streams')):
         report('bb_probe_expand 1:16, %s' % what, n + n // 16,
                lambda pat=pat: kernels.probe_expand(b, a, pat), seconds)
+    report('bb_probe_expand 1:4 (8 bit -> float32), contiguous input',
+           n + n // 4, lambda: kernels.probe_expand(b, a, 3), seconds)
     report('bb_probe_expand 1:16, input wrapped to 1 MiB (L2 hits)',
            n + n // 16, lambda: kernels.probe_expand(b, a, 2), seconds)
     del a, b
