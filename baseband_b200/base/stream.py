@@ -18,6 +18,7 @@ CUDA ``torch.Tensor`` as ``out`` keeps the decoded samples on the GPU.
 
 There is no CPU decode path: without the CUDA library every read raises.
 """
+import mmap
 import operator
 import os
 from collections import namedtuple
@@ -37,9 +38,16 @@ DEFAULT_CHUNK_NBYTES = 64 << 20
 
 # File -> pinned staging buffer: one readinto() copies out of the page cache on
 # a single core (a few GB/s), far below the PCIe link.  Large chunks of plain
-# files are therefore read as several slices with os.preadv on a small thread
-# pool (the system call releases the GIL), which keeps the H2D copy fed.
+# files are therefore copied as several slices on a small thread pool, from a
+# read-only mmap of the file: a user-space memcpy out of the mapped page cache
+# moves ~15 GB/s per core where the kernel's copy in read()/preadv() manages
+# ~6 (profiles/r2_host_copy.txt: 4 threads 43 vs 22 GB/s, 8 threads 66 vs
+# 36), which keeps the H2D copy fed with half the cores.  The page tables of
+# each slice are filled in one go (MADV_POPULATE_READ) instead of one fault
+# per page.  os.preadv slices remain as the fallback where mmap is refused.
 PARALLEL_READ_MIN_NBYTES = 8 << 20
+PARALLEL_READ_MMAP = True
+_MADV_POPULATE_READ = 22            # linux/mman.h (Linux >= 5.14)
 # read(out=<pageable numpy array>) at least this large: staged D2H (see
 # StreamReaderBase._read_to_host).
 STAGED_HOST_OUT_MIN_NBYTES = 4 << 20
@@ -81,6 +89,22 @@ def _parallel_readinto(fh, offset, view):
     n = view.size
     step = -(-n // PARALLEL_READ_THREADS)
     step = (step + 4095) // 4096 * 4096
+    mapped = _mapped_file(raw, fd, offset + n) if PARALLEL_READ_MMAP else None
+    if mapped is not None:
+        mm, arr = mapped
+        n = max(0, min(n, arr.size - offset))
+
+        def piece_mapped(lo):
+            hi = min(lo + step, n)
+            a = (offset + lo) // mmap.PAGESIZE * mmap.PAGESIZE
+            try:
+                mm.madvise(_MADV_POPULATE_READ, a, offset + hi - a)
+            except (OSError, ValueError, OverflowError):
+                pass                           # older kernel: plain faults
+            np.copyto(view[lo:hi], arr[offset + lo:offset + hi])
+            return hi - lo
+
+        return sum(_read_pool.map(piece_mapped, range(0, n, step)))
 
     def piece(lo):
         hi = min(lo + step, n)
@@ -94,6 +118,31 @@ def _parallel_readinto(fh, offset, view):
         return got
 
     return sum(_read_pool.map(piece, range(0, n, step)))
+
+
+_file_maps = None
+
+
+def _mapped_file(raw, fd, need):
+    """Read-only mmap of the plain file behind ``raw`` (kept per file object,
+    re-made when the file has grown past it) as ``(mmap, uint8 array)``, or
+    None if it cannot be mapped."""
+    global _file_maps
+    if _file_maps is None:
+        import weakref
+        _file_maps = weakref.WeakKeyDictionary()
+    try:
+        entry = _file_maps.get(raw)
+        if entry is None or entry[1].size < need:
+            size = os.fstat(fd).st_size
+            if size <= 0:
+                return None
+            mm = mmap.mmap(fd, size, prot=mmap.PROT_READ)
+            entry = (mm, np.frombuffer(mm, np.uint8))
+            _file_maps[raw] = entry
+        return entry
+    except (OSError, ValueError, TypeError):
+        return None
 
 
 def read_file_into(fh, offset, view):

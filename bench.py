@@ -881,7 +881,8 @@ def main():
     ap.add_argument('--passes', type=int, default=32,
                     help='chunks per step (32 x 1 GiB: 20 steps keep the GPU '
                          'busy for ~3.5 s, a sustained figure)')
-    ap.add_argument('--e2e-mib', type=float, default=128.0)
+    ap.add_argument('--e2e-mib', type=float, default=256.0,
+                    help='packed MiB per GPU and step of the e2e leg')
     ap.add_argument('--e2e-chunk-mib', type=float, default=32.0,
                     help='packed MiB per pipeline stage of the e2e reader')
     ap.add_argument('--named-mib', type=float, default=1024.0,

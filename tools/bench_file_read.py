@@ -20,8 +20,10 @@ nbytes = raw.size
 del raw
 print('host CPUs available:', len(os.sched_getaffinity(0)))
 try:
-    for threads in (1, 2, 4, 8, 12, 16):
+    for threads, use_mmap in [(t, m) for m in (False, True)
+                              for t in (1, 2, 4, 8, 12, 16)]:
         stream.PARALLEL_READ_THREADS = threads
+        stream.PARALLEL_READ_MMAP = use_mmap
         stream._read_pool = None
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
         best = 1e9
@@ -32,13 +34,15 @@ try:
             data = fh.read()
             torch.cuda.synchronize()
             best = min(best, time.perf_counter() - t0)
-        print('file -> device, %d read thread(s): %5.1f GB/s packed ingest, '
-              '%6.1f Gsamp/s' % (threads, nbytes / best / 1e9,
+        print('file -> device, %2d %s thread(s): %5.1f GB/s packed ingest, '
+              '%6.1f Gsamp/s' % (threads, 'mmap copy' if use_mmap else
+                                 'preadv   ', nbytes / best / 1e9,
                                  data.numel() / best / 1e9))
         fh.close()
         del data
     out = torch.empty((nset * 32000, 16), dtype=torch.float32,
                       pin_memory=True)
+    stream.PARALLEL_READ_MMAP = True
     for threads in (1, 8):
         stream.PARALLEL_READ_THREADS = threads
         stream._read_pool = None
