@@ -80,6 +80,9 @@ SIGNATURES = {
     'bb_frames_assemble': (c_int, [
         _pv, c_int64, c_int64, c_int32, _pv, _pv, c_uint32, c_int64, c_int32,
         c_int64, _pi64, c_void_p]),
+    'bb_host_copy': (c_int, [c_void_p, c_void_p, c_int64, c_int32]),
+    'bb_host_pread': (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32,
+                              POINTER(c_int64)]),
     'bb_locate_frames': (c_int, [
         _pv, c_int64, c_int64, _pv, _pv, c_int32, c_int64, c_int64, c_int32,
         c_int32, c_int64, _pi64, c_int32, _pv, c_void_p]),
@@ -140,6 +143,22 @@ def load():
         if _lib.bb_abi_version() != 2:
             raise ImportError('baseband_b200: ABI version mismatch')
     return _lib
+
+
+_host = None
+
+
+def host_io():
+    """The library's host-side entry points (bb_host_copy, bb_host_pread):
+    plain C++ threads, usable without a GPU."""
+    global _host
+    if _host is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError('baseband_b200: library not built ({})'
+                              .format(LIB_PATH))
+        _host = bind(ctypes.CDLL(LIB_PATH),
+                     required=('bb_host_copy', 'bb_host_pread'))
+    return _host
 
 
 class BasebandCudaError(RuntimeError):

@@ -42,28 +42,24 @@ DEFAULT_CHUNK_NBYTES = 64 << 20
 # read-only mmap of the file: a user-space memcpy out of the mapped page cache
 # moves ~15 GB/s per core where the kernel's copy in read()/preadv() manages
 # ~6 (profiles/r2_host_copy.txt: 4 threads 43 vs 22 GB/s, 8 threads 66 vs
-# 36), which keeps the H2D copy fed with half the cores.  The page tables of
-# each slice are filled in one go (MADV_POPULATE_READ) instead of one fault
-# per page.  os.preadv slices remain as the fallback where mmap is refused.
+# 36), which keeps the H2D copy fed with half the cores.  The slices run on the
+# library's pool of native threads (bb_host_copy; bb_host_pread where mmap is
+# refused): a Python thread pool costs ~50 us per slice, as much as the copy
+# of a small chunk.
 PARALLEL_READ_MIN_NBYTES = 8 << 20
 PARALLEL_READ_MMAP = True
-_MADV_POPULATE_READ = 22            # linux/mman.h (Linux >= 5.14)
 # read(out=<pageable numpy array>) at least this large: staged D2H (see
 # StreamReaderBase._read_to_host).
 STAGED_HOST_OUT_MIN_NBYTES = 4 << 20
 PARALLEL_READ_THREADS = max(1, min(8, len(os.sched_getaffinity(0))
                                    if hasattr(os, 'sched_getaffinity')
                                    else (os.cpu_count() or 1)))
-_read_pool = None
-
-
 def _parallel_readinto(fh, offset, view):
     """Fill the writable uint8 numpy array ``view`` from absolute byte
     ``offset`` of the plain file behind ``fh``.  Returns the bytes read, or
     None if ``fh`` is not a plain file (the caller falls back to
     ``readinto``)."""
-    global _read_pool
-    if PARALLEL_READ_THREADS < 2 or not hasattr(os, 'preadv'):
+    if PARALLEL_READ_THREADS < 1:
         return None
     # only genuine binary files: anything else with a fileno() (gzip, ...)
     # would hand out the bytes of the file underneath it
@@ -82,42 +78,23 @@ def _parallel_readinto(fh, offset, view):
             return None
     except (OSError, ValueError):
         return None
-    if _read_pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _read_pool = ThreadPoolExecutor(PARALLEL_READ_THREADS,
-                                        thread_name_prefix='bb-read')
+    import ctypes
+    from .._lib import host_io
+    lib = host_io()
     n = view.size
-    step = -(-n // PARALLEL_READ_THREADS)
-    step = (step + 4095) // 4096 * 4096
+    dst = ctypes.c_void_p(view.ctypes.data)
     mapped = _mapped_file(raw, fd, offset + n) if PARALLEL_READ_MMAP else None
     if mapped is not None:
-        mm, arr = mapped
+        # user-space memcpy out of the mapped page cache, native threads
+        arr = mapped[1]
         n = max(0, min(n, arr.size - offset))
-
-        def piece_mapped(lo):
-            hi = min(lo + step, n)
-            a = (offset + lo) // mmap.PAGESIZE * mmap.PAGESIZE
-            try:
-                mm.madvise(_MADV_POPULATE_READ, a, offset + hi - a)
-            except (OSError, ValueError, OverflowError):
-                pass                           # older kernel: plain faults
-            np.copyto(view[lo:hi], arr[offset + lo:offset + hi])
-            return hi - lo
-
-        return sum(_read_pool.map(piece_mapped, range(0, n, step)))
-
-    def piece(lo):
-        hi = min(lo + step, n)
-        mv = memoryview(view[lo:hi])
-        got = 0
-        while got < hi - lo:
-            k = os.preadv(fd, [mv[got:]], offset + lo + got)
-            if k <= 0:
-                break
-            got += k
-        return got
-
-    return sum(_read_pool.map(piece, range(0, n, step)))
+        rc = lib.bb_host_copy(dst, ctypes.c_void_p(arr.ctypes.data + offset),
+                              n, PARALLEL_READ_THREADS)
+        return n if rc == 0 else None
+    nread = ctypes.c_int64(0)
+    rc = lib.bb_host_pread(fd, dst, n, offset, PARALLEL_READ_THREADS,
+                           ctypes.byref(nread))
+    return int(nread.value) if rc == 0 else None
 
 
 _file_maps = None

@@ -301,6 +301,17 @@ int bb_frames_assemble(void *dst, int64_t nframe, int64_t frame_stride,
                        int64_t unit_stride, int64_t *unit_offset,
                        void *stream);
 
+/* ---------------------------------------------------------- host ingest
+ * File -> pinned staging on a persistent pool of native threads (the
+ * reference reads each payload with one fh.readinto,
+ * baseband/base/payload.py:83-143).  bb_host_copy: memcpy in up to `nthreads`
+ * slices (e.g. out of a read-only mmap of the file: the page cache itself);
+ * bb_host_pread: the same with pread(2) from a file descriptor, *nread =
+ * bytes read before the first short slice.  No CUDA involved. */
+int bb_host_copy(void *dst, const void *src, int64_t nbytes, int32_t nthreads);
+int bb_host_pread(int32_t fd, void *dst, int64_t nbytes, int64_t offset,
+                  int32_t nthreads, int64_t *nread);
+
 /* ------------------------------------------ frame location and frame index
  * The device-side replacement for the reference's sync search and frame
  * bookkeeping of irregular streams (`locate_frames`,

@@ -552,7 +552,8 @@ def guppi_synthetic_and_write():
 
 
 def vdif_parallel_file_read():
-    """Large chunks of plain files are read with os.preadv on a thread pool
+    """Large chunks of plain files are copied out of the page cache by a pool
+    of native threads
     (base/stream.py:_parallel_readinto): same bytes, same samples; other
     file-like objects fall back to readinto."""
     import tempfile

@@ -24,7 +24,6 @@ try:
                               for t in (1, 2, 4, 8, 12, 16)]:
         stream.PARALLEL_READ_THREADS = threads
         stream.PARALLEL_READ_MMAP = use_mmap
-        stream._read_pool = None
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
         best = 1e9
         for rep in range(4):
@@ -45,7 +44,6 @@ try:
     stream.PARALLEL_READ_MMAP = True
     for threads in (1, 8):
         stream.PARALLEL_READ_THREADS = threads
-        stream._read_pool = None
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6)
         best = 1e9
         for rep in range(3):
