@@ -431,17 +431,19 @@ def measure_ceilings(dev, scratch, kernels, seconds=0.4):
                    'each'.format(flat.numel() * 4 / 2**30, seconds)}
 
 
-def _source_hash():
-    """Hash of the kernel sources: ncu figures are only quoted for the code
+# the sources the bit-field decode kernel is compiled from
+DECODE_SOURCES = ('bb_bitfield.cu', 'bb_bitfield.cuh', 'bb_bitfield_plan.h',
+                  'bb_common.cuh', 'bb_quant.cuh', 'bb_runtime.cuh')
+
+
+def _source_hash(names=DECODE_SOURCES):
+    """Hash of a kernel's sources: ncu figures are only quoted for the code
     they were captured from."""
-    import glob
     import hashlib
     h = hashlib.sha256()
-    for path in sorted(glob.glob(os.path.join(ROOT, 'baseband_b200', 'csrc',
-                                              '*.cu*'))
-                       + glob.glob(os.path.join(ROOT, 'baseband_b200',
-                                                'csrc', '*.h'))):
-        with open(path, 'rb') as fh:
+    for name in sorted(names):
+        with open(os.path.join(ROOT, 'baseband_b200', 'csrc', name),
+                  'rb') as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
 
@@ -458,7 +460,8 @@ def ncu_traffic(kernel, nsample):
         entry = table[kernel]
     except (OSError, KeyError, ValueError):
         return None, 'no ncu capture committed for this kernel'
-    if entry.get('csrc_sha16') != _source_hash():
+    if entry.get('csrc_sha16') != _source_hash(
+            entry.get('sources', DECODE_SOURCES)):
         return None, ('stale: {} was captured from other kernel sources ({})'
                       .format(entry.get('report'), entry.get('csrc_sha16')))
     per_sample = (entry['dram_bytes_read'] + entry['dram_bytes_write']) \

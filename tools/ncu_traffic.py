@@ -34,7 +34,7 @@ def main():
     def nbytes(key):
         return float(d[key]) * UNIT[units[key]]
 
-    from bench import _source_hash
+    from bench import DECODE_SOURCES, _source_hash
     path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
     table = json.load(open(path)) if os.path.exists(path) else {}
     git = subprocess.run(['git', 'rev-parse', '--short', 'HEAD'], cwd=ROOT,
@@ -42,7 +42,8 @@ def main():
     table[name] = {
         'ncu_kernel_name': d['Kernel Name'], 'grid': d['Grid Size'],
         'report': os.path.basename(rep), 'git': git,
-        'csrc_sha16': _source_hash(),
+        'sources': list(DECODE_SOURCES),
+        'csrc_sha16': _source_hash(DECODE_SOURCES),
         'dram_bytes_read': nbytes('dram__bytes_read.sum'),
         'dram_bytes_write': nbytes('dram__bytes_write.sum'),
         'gpu_time_us_under_ncu': float(d['gpu__time_duration.sum'])

@@ -80,6 +80,18 @@ elif case == 'mark4':
         _, off = kernels.mark4_scan(raw, nframe, 64)
         out = kernels.mark4_decode(raw, off, nframe, 8, 4, False,
                                    levels.sign_magnitude(), out=out)
+elif case == 'counts':
+    # the state-count consumer on the C2 geometry
+    payload, frame, nthread = 8000, 8032, 16
+    nset = int(gib * 2**30) // frame // nthread
+    raw = torch.randint(0, 256, (nset * nthread * frame,), dtype=torch.uint8,
+                        device=DEV)
+    uo = torch.arange(nset * nthread, dtype=torch.int64, device=DEV) * frame + 32
+    acc = kernels.zeros((-(-nset // 200), nthread, 1, 4), torch.int64,
+                        torch.device(DEV))
+    for _ in range(reps):
+        kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1, acc,
+                             sets_per_bin=200)
 elif case == 'mark4enc':
     nframe = int(gib * 2**30) // 160000
     raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,
