@@ -143,13 +143,20 @@ def run_reference(args):
         'ms_per_step': dt / args.steps * 1e3, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': config_dict(cores * nset * SET_BYTES, args.gpus),
+        # the same workload description as the B200 arm prints; what one
+        # step of THIS arm covers of it is stated in cpu_baseline.sample
+        'config': config_dict(
+            int(args.chunk_gib * 2**30) // SET_BYTES * SET_BYTES, args.gpus,
+            max(1, args.passes)),
         'cpu_baseline': {
             'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '{} processes x {} frame sets per step, numpy oracle '
-                      '(port of the reference CPU path; the reference '
-                      'package needs astropy, absent here)'.format(cores,
-                                                                   nset)},
+            'sample': 'a step of this arm is a bounded sample of the '
+                      'workload: {} processes x {} frame sets ({:.0f} MB '
+                      'packed) of the same synthetic stream, decode + encode '
+                      'round trip, numpy oracle (port of the reference CPU '
+                      'path; the reference package needs astropy, absent '
+                      'here)'.format(cores, nset,
+                                     cores * nset * SET_BYTES / 1e6)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0,
                 'd2h_bytes_per_step': 0},
     }

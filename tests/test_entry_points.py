@@ -119,3 +119,48 @@ def _entry_point_protocol():
     assert 'baseband.io' in text
     for fmt in FORMATS:
         assert 'baseband_b200.' + fmt in text
+
+
+REF_TASKS = '/root/reference/baseband/tasks/__init__.py'
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TASKS),
+                    reason='reference tree only exists in the build container')
+def test_reference_tasks_loader_finds_b200_consumers(tmp_path, monkeypatch):
+    """The analysis plug-in point (baseband/tasks/__init__.py:25-62): the
+    reference's own loader, given the entry points pyproject.toml declares
+    (written to a dist-info as baseband/tests/test_entry_points.py:103-110
+    does), exposes the GPU consumers, and they run."""
+    import cpu_backend
+    cpu_backend.install(monkeypatch)
+    import baseband_b200 as bb
+    from baseband_b200 import tasks as b200_tasks
+    info = tmp_path / 'b200_tasks-0.1.dist-info'
+    info.mkdir()
+    (info / 'entry_points.txt').write_text(
+        '[baseband.tasks]\n'
+        'state_counts = baseband_b200.tasks:state_counts\n'
+        'integrated_power = baseband_b200.tasks:integrated_power\n'
+        '_ = baseband_b200.tasks:__all__\n')
+    monkeypatch.syspath_prepend(str(tmp_path))
+    spec = importlib.util.spec_from_file_location('ref_baseband_tasks',
+                                                  REF_TASKS)
+    tasks = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tasks)
+    assert tasks._bad_entries == []
+    assert tasks.state_counts is b200_tasks.state_counts
+    assert tasks.integrated_power is b200_tasks.integrated_power
+    assert tasks.state_levels is b200_tasks.state_levels     # via __all__
+    with bb.vdif.open(sample_path('sample.vdif'), 'rs') as fh:
+        counts = tasks.state_counts(fh, 20000)
+        data = OUT['sample_vdif_data'][:, :, 0]
+        lv = tasks.state_levels(fh)
+        want = np.stack([np.stack([(data[b * 20000:(b + 1) * 20000] == v
+                                    ).sum(0) for v in lv], -1)
+                         for b in range(2)])
+        assert np.array_equal(counts, want)
+        fh.seek(0)
+        power = tasks.integrated_power(fh, 20000)
+        ref = np.stack([(data[b * 20000:(b + 1) * 20000].astype(np.float64)
+                         ** 2).mean(0) for b in range(2)])
+        assert np.allclose(power, ref, rtol=1e-10, atol=0)
