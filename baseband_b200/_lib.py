@@ -93,6 +93,10 @@ SIGNATURES = {
     'bb_mark5b_index': (c_int, [
         _pv, c_int64, _pi64, _pv, c_int32, c_int32, c_int32, c_int32,
         c_int32, c_int64, _pv, _pv, c_void_p]),
+    'bb_mark4_index': (c_int, [
+        _pv, c_int64, _pi64, _pv, c_int32, c_int32, c_int32, c_int32,
+        c_int32, c_int32, c_int32, c_int64, c_int64, c_int32, c_int64, _pv,
+        _pv, c_void_p]),
     'bb_index_table_finish': (c_int, [_pv, c_int64, _pi64, c_void_p]),
     'bb_state_counts': (c_int, [
         _pv, _pi64, c_int64, c_int32, c_int64, c_int32, c_int32, c_int64,

@@ -675,7 +675,8 @@ class StreamReaderBase(StreamBase):
                                         non_blocking=True)
 
     def _build_index_on_device(self, pattern, mask, frame_nbytes,
-                               index_chunk, nslot, nset_max):
+                               index_chunk, nslot, nset_max,
+                               pattern_offset=0):
         """Frame table of an irregular stream, built on the GPU: the file is
         streamed through the device in overlapping chunks; in each,
         bb_locate_frames finds every place the stream's (masked) sync pattern
@@ -690,13 +691,14 @@ class StreamReaderBase(StreamBase):
         fh = self.fh_raw
         size = fh.seek(0, 2)
         fh.seek(0)
-        pat = np.asarray(pattern, '<u4').view(np.uint8)
-        msk = np.asarray(mask, '<u4').view(np.uint8)
-        overlap = frame_nbytes + pat.size
+        pat = kernels._host_bytes(pattern)[0]
+        msk = kernels._host_bytes(mask)[0]
+        overlap = frame_nbytes + pattern_offset + pat.size
         step = max(4 * frame_nbytes, self._chunk_nbytes // frame_nbytes
                    * frame_nbytes)
         table = kernels.index_table(nset_max * nslot, dev)
         stats = kernels.zeros(3, torch.int32, dev)
+        counts = []
         stages, ss = self._pipeline(dev)
         zero_copy = getattr(fh, 'pinned_view', None)
         ss.after_caller(1)
@@ -721,11 +723,12 @@ class StreamReaderBase(StreamBase):
             with ss.use(1):
                 ss.wait_event(1, st.done)
                 locations, count = kernels.locate_frames(
-                    raw, pat, msk, frame_nbytes, 0,
+                    raw, pat, msk, frame_nbytes, pattern_offset,
                     own_stop=n if at_eof else step, check=1, at_eof=at_eof,
                     base=pos)
                 index_chunk(raw, pos, locations, count, table, stats)
                 st.free = ss.event(1)
+            counts.append((count, locations.numel()))
             if at_eof:
                 break
             pos += step
@@ -733,6 +736,9 @@ class StreamReaderBase(StreamBase):
         with ss.use(1):
             offsets = kernels.index_table_finish(table)
         ss.caller_after(1)
+        if any(int(count.item()) > room for count, room in counts):
+            raise OSError('too many sync-pattern candidates to index this '
+                          'file: is it in this format at all?')
         stats = stats.cpu().numpy()
         nset = int(stats[0]) + 1
         host = offsets[:nset * nslot].cpu().numpy().reshape(nset, nslot)

@@ -138,6 +138,83 @@ k_mark5b_index(const uint8_t *src, long long base, const long long *locations,
     atomicMax(stats, (int)(index < 0x7fffffff ? index : 0x7fffffff));
 }
 
+// Mark 4: one warp per header found.  The time code of one track is gathered
+// bit by bit (a header word of a track is spread over 32 steps of the
+// ntrack-bit stream words, baseband/mark4/header.py:47-63): step
+// 32 * w + lane, bit `track`, ballot, bit reversal.  Unit year, day of year,
+// h, m, s and ms (baseband/mark4/header.py:223-262; the ms digit stands for
+// quarters: + (ms % 5) / 4 ms) give the time in 0.25 ms ticks relative to the
+// first header, which must be a whole number of frame periods.
+__global__ void __launch_bounds__(kIndexBlock)
+k_mark4_index(const uint8_t *src, long long base, const long long *locations,
+              const int *count, int max_loc, int wordbytes, int track,
+              int year0, int yday0, int days_year0, int days_prev_year,
+              long long tick0, long long tick_step, int check_crc,
+              long long nset_max, unsigned long long *table, int *stats) {
+    const int lane = threadIdx.x & 31;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n = *count < max_loc ? *count : max_loc;
+    if (i >= n) return;                               // warp-uniform
+    const long long off = locations[i];
+    const uint8_t *h = src + (off - base);
+    uint32_t w5[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const uint8_t b = h[(size_t)(32 * k + lane) * wordbytes
+                            + (track >> 3)];
+        w5[k] = __brev(__ballot_sync(0xffffffffu, (b >> (track & 7)) & 1));
+    }
+    if (lane) return;
+    if (check_crc) {
+        // CRC-12 (x^12 + x^11 + x^3 + x^2 + x + 1, baseband/mark4/header.py:
+        // 25-27) over the 160 header bits of the track, first step first: a
+        // header that ends in its CRC leaves no remainder.  The all-ones sync
+        // also matches a few bytes either side of the true frame start when
+        // the neighbouring header bits are ones; those candidates fail here.
+        uint32_t rem = 0u;
+#pragma unroll 1
+        for (int k = 0; k < 5; ++k)
+            for (int b = 31; b >= 0; --b) {
+                const uint32_t top = (rem >> 11) & 1u;
+                rem = ((rem << 1) | ((w5[k] >> b) & 1u)) & 0xfffu;
+                if (top) rem ^= 0x80fu;
+            }
+        if (rem) {
+            atomicAdd(stats + 2, 1);
+            return;
+        }
+    }
+    const uint32_t w[2] = {w5[3], w5[4]};
+    const int y = bcd_digits(w[0] >> 28, 1), doy = bcd_digits(w[0] >> 16, 3),
+        hh = bcd_digits(w[0] >> 8, 2), mm = bcd_digits(w[0], 2),
+        ss = bcd_digits(w[1] >> 24, 2), ms = bcd_digits(w[1] >> 12, 3);
+    if (y < 0 || doy < 1 || doy > 366 || hh < 0 || hh > 23 || mm < 0
+        || mm > 59 || ss < 0 || ss > 60 || ms < 0 || ms % 5 == 4) {
+        atomicAdd(stats + 2, 1);                      // not a time code
+        return;
+    }
+    const int dy = ((y - year0 % 10 + 15) % 10) - 5;
+    long long ddays;
+    if (dy == 0) ddays = doy - yday0;
+    else if (dy == 1) ddays = doy + days_year0 - yday0;
+    else if (dy == -1) ddays = doy - days_prev_year - yday0;
+    else { atomicAdd(stats + 1, 1); return; }
+    const long long ticks = ddays * (86400ll * 4000ll)
+        + ((long long)hh * 3600 + mm * 60 + ss) * 4000ll + ms * 4 + ms % 5
+        - tick0;
+    if (ticks % tick_step) {
+        atomicAdd(stats + 2, 1);                      // off the frame grid
+        return;
+    }
+    const long long index = ticks / tick_step;
+    if (index < 0 || index >= nset_max) {
+        atomicAdd(stats + 1, 1);
+        return;
+    }
+    atomicMin(table + index, 2ull * (unsigned long long)off);
+    atomicMax(stats, (int)(index < 0x7fffffff ? index : 0x7fffffff));
+}
+
 __global__ void __launch_bounds__(kIndexBlock)
 k_index_fill(unsigned long long *table, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -241,6 +318,29 @@ extern "C" int bb_mark5b_index(
         max_locations, jday0, seconds0, frame_nr0, frames_per_second,
         nset_max, (unsigned long long *)table, stats);
     BB_CHECK_LAUNCH("bb_mark5b_index");
+    return BB_OK;
+}
+
+extern "C" int bb_mark4_index(
+    const void *src, int64_t base, const int64_t *locations,
+    const int32_t *count, int32_t max_locations, int32_t ntrack,
+    int32_t track, int32_t year0, int32_t yday0, int32_t days_year0,
+    int32_t days_prev_year, int64_t tick0, int64_t tick_step,
+    int32_t check_crc, int64_t nset_max, uint64_t *table, int32_t *stats,
+    void *stream) {
+    if (!src || !locations || !count || !table || !stats)
+        return set_error(BB_ERR_ARGUMENT, "null pointer");
+    if ((ntrack != 16 && ntrack != 32 && ntrack != 64) || track < 0
+        || track >= ntrack || tick_step < 1 || nset_max < 0)
+        return set_error(BB_ERR_ARGUMENT, "bad geometry");
+    if (max_locations == 0) return BB_OK;
+    k_mark4_index<<<blocks_for((long long)max_locations * 32), kIndexBlock, 0,
+                    as_stream(stream)>>>(
+        (const uint8_t *)src, base, (const long long *)locations, count,
+        max_locations, ntrack / 8, track, year0, yday0, days_year0,
+        days_prev_year, tick0, tick_step, check_crc, nset_max,
+        (unsigned long long *)table, stats);
+    BB_CHECK_LAUNCH("bb_mark4_index");
     return BB_OK;
 }
 

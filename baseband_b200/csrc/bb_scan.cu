@@ -246,6 +246,14 @@ k_mark4_scan(const uint8_t *src, const long long *frame_offset,
     long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= nframe) return;                     // warp-uniform
     long long off = frame_offset ? frame_offset[i] : i * frame_stride;
+    if (off < 0) {                 // absent according to the stream's index
+        if (lane == 0) {
+            if (unit_offset) unit_offset[i] = -1;
+            if (words5)
+                for (int w = 0; w < 5; ++w) words5[i * 5 + w] = 0u;
+        }
+        return;                                   // warp-uniform
+    }
     const W *st = reinterpret_cast<const W *>(src + off);
     bool bad = false;
     uint32_t got3 = 0u, got4 = 0u;

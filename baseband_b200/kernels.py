@@ -483,7 +483,10 @@ def locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
     else:
         msk_p = None
     if max_locations is None:
-        max_locations = (nbytes // frame_nbytes + 2) if frame_nbytes else 4096
+        # a sync pattern can match a few bytes either side of a frame start
+        # as well: room for several candidates per frame
+        max_locations = (8 * (nbytes // frame_nbytes + 2) if frame_nbytes
+                         else 4096)
     locations = torch.empty((max(int(max_locations), 1),), dtype=torch.int64,
                             device=dev)
     count = zeros(1, torch.int32, dev)
@@ -537,6 +540,24 @@ def mark5b_index(src, base, locations, count, jday0, seconds0, frame_nr0,
             _dev(locations, 'locations', torch.int64),
             _dev(count, 'count', torch.int32), locations.numel(), int(jday0),
             int(seconds0), int(frame_nr0), int(fps), int(nset_max),
+            _dev(table, 'table', torch.int64),
+            _dev(stats, 'stats', torch.int32), _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+
+
+def mark4_index(src, base, locations, count, ntrack, track, year0, yday0,
+                days_year0, days_prev_year, tick0, tick_step, nset_max, table,
+                stats, check_crc=True):
+    lib = _lib.load()
+    with _on(src.device):
+        rc = lib.bb_mark4_index(
+            _dev(src, 'src', torch.uint8), int(base),
+            _dev(locations, 'locations', torch.int64),
+            _dev(count, 'count', torch.int32), locations.numel(), int(ntrack),
+            int(track), int(year0), int(yday0), int(days_year0),
+            int(days_prev_year), int(tick0), int(tick_step),
+            int(bool(check_crc)), int(nset_max),
             _dev(table, 'table', torch.int64),
             _dev(stats, 'stats', torch.int32), _stream_ptr(src.device))
     _lib.check(rc, lib)

@@ -156,6 +156,18 @@ class Mark4StreamReader(StreamReaderBase):
                            '{}'.format(coder))
         self._levels = levels.sign_magnitude()
         self._tick = None
+        if self.verify and self._nframe > 1:
+            # the time of the last frame must match its position, else frames
+            # were lost (or bytes slipped): index the file
+            fh_raw.seek(offset0 + (self._nframe - 1) * header0.frame_nbytes)
+            try:
+                last = fh_raw.read_header()
+                lossy = int(round((last.time - header0.time)
+                                  * self._frame_rate)) != self._nframe - 1
+            except Exception:
+                lossy = True
+            if lossy:
+                self._build_index()
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
         h0 = self.header0
@@ -164,24 +176,75 @@ class Mark4StreamReader(StreamReaderBase):
         # frame: the scan kernel compares the BCD words with those the writer
         # would generate for the frame's position
         check = None
-        if self.verify:
-            if self._tick is None:
-                self._tick = _tick_grid(h0, self._frame_rate)
-            check = (frame0,) + self._tick
-        _, uo = kernels.mark4_scan(
-            raw, nframe, h0.ntrack, check=check,
-            bad=self._bad_counter(raw.device) if self.verify else None,
-            want_words=False)
+        if self._index is not None:
+            # irregular stream: frames sit where the index says
+            rel = self._chunk_layout(frame0, nframe)[4][:, 0]
+            _, uo = kernels.mark4_scan(
+                raw, nframe, h0.ntrack, frame_offset=torch.from_numpy(
+                    np.ascontiguousarray(rel)).to(raw.device),
+                want_words=False)
+        else:
+            if self.verify:
+                if self._tick is None:
+                    self._tick = _tick_grid(h0, self._frame_rate)
+                check = (frame0,) + self._tick
+            _, uo = kernels.mark4_scan(
+                raw, nframe, h0.ntrack, check=check,
+                bad=self._bad_counter(raw.device) if self.verify else None,
+                want_words=False)
         kernels.mark4_decode(raw, uo, nframe, nchan, fanout, ft,
                              self._levels, self._fill_value, sample_start,
                              nsample, out)
 
+    def _build_index(self):
+        """Frame table of an irregular stream, built on the GPU: every place
+        where all tracks carry the 32-step all-ones sync word at steps 64..95
+        (baseband/mark4/header.py:125-131), with another one a frame later, is
+        placed by the BCD time code of track 0 (cf.
+        VDIFStreamReader._build_index)."""
+        h0 = self.header0
+        wordbytes = h0.ntrack // 8
+        size = self.fh_raw.seek(0, 2)
+        self.fh_raw.seek(0)
+        nphys = (size - self._file_offset0) // h0.frame_nbytes
+        mjd0, tick0, tick_step = _tick_grid(h0, self._frame_rate)
+        nset_max = 2 * nphys + int(round(self._frame_rate)) + 2
+        import datetime
+        date = datetime.date(1858, 11, 17) + datetime.timedelta(mjd0)
+        yday0 = date.timetuple().tm_yday
+
+        def ndays(year):
+            return 366 if (year % 4 == 0 and year % 100 != 0) \
+                or year % 400 == 0 else 365
+
+        def index_chunk(raw, base, locations, count, table, stats):
+            kernels.mark4_index(raw, base, locations, count, h0.ntrack, 0,
+                                date.year, yday0, ndays(date.year),
+                                ndays(date.year - 1), tick0, tick_step,
+                                nset_max, table, stats)
+
+        pattern = np.full(32 * wordbytes, 0xff, np.uint8)
+        table, stats = self._build_index_on_device(
+            pattern, pattern, h0.frame_nbytes, index_chunk, 1, nset_max,
+            pattern_offset=64 * wordbytes)
+        self._set_index_table(table, h0.frame_nbytes)
+
     def read(self, count=None, out=None, **kwargs):
+        offset = self.offset
         result = super().read(count, out, **kwargs)
-        if self._new_inconsistencies():
-            raise OSError('Mark 4 stream is not a regular sequence of '
-                          'frames; recovery of corrupt files is not part of '
-                          'the GPU path.')
+        if self._index is None and self._new_inconsistencies():
+            if not self.verify:
+                raise OSError('Mark 4 stream is not a regular sequence of '
+                              'frames and verify is off.')
+            import warnings
+            warnings.warn('Mark 4 stream has missing or out-of-order '
+                          'frames; indexing all headers and filling the '
+                          'gaps with fill_value.')
+            self._build_index()
+            self.offset = offset
+            # "everything" means everything the index knows of
+            return super().read(None if count is None and out is None
+                                else result.shape[0], out, **kwargs)
         return result
 
 

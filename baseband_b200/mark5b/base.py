@@ -233,7 +233,8 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
                           'gaps with fill_value.')
             self._build_index()
             self.offset = offset
-            return super().read(result.shape[0], out, **kwargs)
+            return super().read(None if count is None and out is None
+                                else result.shape[0], out, **kwargs)
         return result
 
 

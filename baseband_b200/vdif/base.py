@@ -347,7 +347,8 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
                           'gaps with fill_value.')
             self._build_index()
             self.offset = offset
-            n = result.shape[0]
+            # "everything" means everything the index knows of
+            n = None if count is None and out is None else result.shape[0]
             return super().read(n, out if out is not None else None, **kwargs)
         return result
 

@@ -275,7 +275,8 @@ int bb_mark5b_scan(const void *src, const int64_t *frame_offset,
  * non-NULL, frame i is counted in *n_inconsistent (accumulating) unless the
  * time code of `track` (unit year, day of year, h, m, s, ms) is that of
  * tick0 + tick_step * (index0 + i) quarter-milliseconds after 00:00 of MJD
- * mjd0.  `words5` may be NULL. */
+ * mjd0.  `words5` may be NULL.  A negative frame_offset[i] marks an absent
+ * frame (unit_offset[i] = -1, nothing read). */
 int bb_mark4_scan(const void *src, const int64_t *frame_offset,
                   int64_t frame_stride, int64_t nframe, int32_t ntrack,
                   int32_t track, uint32_t *words5, int64_t *unit_offset,
@@ -340,10 +341,18 @@ int bb_host_pread(int32_t fd, void *dst, int64_t nbytes, int64_t offset,
  *   Mark 5B (seconds - seconds0 + 86400 * dday) * fps + frame_nr - frame_nr0,
  *           BCD jday / seconds, dday = jday - jday0 wrapped to [-500, 500)
  *                                        (baseband/mark5b/base.py:206-213)
+ *   Mark 4  time code of one track (unit year, day of year, h, m, s, ms:
+ *           baseband/mark4/header.py:223-262) in 0.25 ms ticks relative to the
+ *           first header (year0, yday0, tick0 = its tick within its day),
+ *           divided by tick_step; year digit within +-1 year of year0; with
+ *           check_crc the track's CRC-12 must hold (the all-ones sync also
+ *           matches next to the true frame start when neighbouring header
+ *           bits are set; the CRC tells them apart)
  * and keep, per (index, slot), the frame that comes first in the file
  * (atomicMin of 2 * offset + invalid flag).  stats (device int32[3],
  * caller-zeroed): [0] largest index seen, [1] frames outside
- * [0, nset_max), [2] headers with an invalid BCD time.
+ * [0, nset_max), [2] headers with an invalid BCD time (Mark 4: or a time off
+ * the frame grid).
  * bb_index_table_finish turns the table into int64 byte offsets of the
  * frames, -1 where a frame is missing or flagged invalid: the
  * `frame_offset` / unit tables the scan and decode kernels take. */
@@ -365,6 +374,13 @@ int bb_mark5b_index(const void *src, int64_t base, const int64_t *locations,
                     int32_t jday0, int32_t seconds0, int32_t frame_nr0,
                     int32_t frames_per_second, int64_t nset_max,
                     uint64_t *table, int32_t *stats, void *stream);
+int bb_mark4_index(const void *src, int64_t base, const int64_t *locations,
+                   const int32_t *count, int32_t max_locations,
+                   int32_t ntrack, int32_t track, int32_t year0,
+                   int32_t yday0, int32_t days_year0, int32_t days_prev_year,
+                   int64_t tick0, int64_t tick_step, int32_t check_crc,
+                   int64_t nset_max, uint64_t *table, int32_t *stats,
+                   void *stream);
 int bb_index_table_finish(const uint64_t *table, int64_t nentry,
                           int64_t *offsets, void *stream);
 

@@ -160,7 +160,10 @@ def _mark4_scan(src, nframe, ntrack, frame_stride=None, track=0,
     for i in range(nframe):
         off = int(frame_offset[i]) if frame_offset is not None \
             else i * frame_stride
-        stream = buf[off:off + ntrack * 20].view(dtype)
+        if off < 0:                       # absent according to the index
+            uo[i] = -1
+            continue
+        stream = buf[off:off + ntrack * 20].copy().view(dtype)
         h = oheaders.mark4_parse(stream)
         words5[i] = oheaders.mark4_stream2words(stream)[:, track]
         uo[i] = off + ntrack * 20 if h['valid'] else -1
@@ -228,7 +231,8 @@ def _locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
                     continue
         found.append(base + loc)
     if max_locations is None:
-        max_locations = (nbytes // frame_nbytes + 2) if frame_nbytes else 4096
+        max_locations = (8 * (nbytes // frame_nbytes + 2) if frame_nbytes
+                         else 4096)
     out = np.zeros(max(int(max_locations), 1), np.int64)
     keep = found[:max_locations]
     out[:len(keep)] = keep
@@ -282,6 +286,64 @@ def _mark5b_index(src, base, locations, count, jday0, seconds0, frame_nr0,
         dday = (jday - jday0 + 1500) % 1000 - 500
         index = (seconds - seconds0 + 86400 * dday) * fps \
             + (int(w[1]) & 0x7fff) - frame_nr0
+        if not 0 <= index < nset_max:
+            st[1] += 1
+            continue
+        _scatter(table, index, off, 0)
+        st[0] = max(st[0], index)
+
+
+def _mark4_index(src, base, locations, count, ntrack, track, year0, yday0,
+                 days_year0, days_prev_year, tick0, tick_step, nset_max,
+                 table, stats, check_crc=True):
+    """k_mark4_index restated with the oracle's bit transpose."""
+    buf, st = src.numpy(), stats.numpy()
+    dtype = {16: '<u2', 32: '<u4', 64: '<u8'}[ntrack]
+
+    def bcd(v, nd):
+        out = 0
+        for d in range(nd):
+            nib = (v >> (4 * d)) & 0xf
+            if nib > 9:
+                return -1
+            out += nib * 10 ** d
+        return out
+    for off in locations.numpy()[:min(int(count), locations.numel())]:
+        stream = buf[off - base:off - base + ntrack * 20].copy().view(dtype)
+        words = oheaders.mark4_stream2words(stream)[:, track]
+        if check_crc:
+            from baseband_b200.base.utils import crc_remainder
+            message = 0
+            for word in words:
+                message = (message << 32) | int(word)
+            if crc_remainder(message, 0x180f, extend=False):
+                st[2] += 1
+                continue
+        w3, w4 = int(words[3]), int(words[4])
+        y, doy, hh, mm = bcd(w3 >> 28, 1), bcd(w3 >> 16, 3), \
+            bcd(w3 >> 8, 2), bcd(w3, 2)
+        ss, ms = bcd(w4 >> 24, 2), bcd(w4 >> 12, 3)
+        if (y < 0 or not 1 <= doy <= 366 or not 0 <= hh <= 23
+                or not 0 <= mm <= 59 or not 0 <= ss <= 60 or ms < 0
+                or ms % 5 == 4):
+            st[2] += 1
+            continue
+        dy = (y - year0 % 10 + 15) % 10 - 5
+        if dy == 0:
+            ddays = doy - yday0
+        elif dy == 1:
+            ddays = doy + days_year0 - yday0
+        elif dy == -1:
+            ddays = doy - days_prev_year - yday0
+        else:
+            st[1] += 1
+            continue
+        ticks = ddays * 86400 * 4000 + (hh * 3600 + mm * 60 + ss) * 4000 \
+            + ms * 4 + ms % 5 - tick0
+        if ticks % tick_step:
+            st[2] += 1
+            continue
+        index = ticks // tick_step
         if not 0 <= index < nset_max:
             st[1] += 1
             continue
@@ -358,6 +420,7 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'index_table', _index_table)
     monkeypatch.setattr(kernels, 'vdif_index', _vdif_index)
     monkeypatch.setattr(kernels, 'mark5b_index', _mark5b_index)
+    monkeypatch.setattr(kernels, 'mark4_index', _mark4_index)
     monkeypatch.setattr(kernels, 'index_table_finish', _index_table_finish)
     monkeypatch.setattr(
         kernels, 'new_counter',

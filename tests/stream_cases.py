@@ -430,17 +430,18 @@ def mark4_time_code_rollover():
                            decade=decade, chunk_nbytes=3 * 80000) as fh:
             assert fh.stop_time.isot.startswith(stop), fh.stop_time.isot
             _same(fh.read(), want)
-        # a frame out of place is caught by the same check
+        # a frame out of place is caught by the same check, and the stream
+        # is then read through the GPU frame index (time codes across the
+        # year end / leap day included)
+        import warnings
         frames = raw.reshape(8, -1).copy()
         frames[[5, 6]] = frames[[6, 5]]
-        try:
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter('always')
             with bb.mark4.open(io.BytesIO(frames.tobytes()), 'rs', ntrack=32,
                                decade=decade) as fh:
-                fh.read()
-        except OSError:
-            pass
-        else:
-            raise AssertionError('swapped frames not detected')
+                _same(fh.read(), want)
+                assert fh._index is not None
 
 
 # ------------------------------------------------------------------ GUPPI
@@ -1526,3 +1527,50 @@ def mark5b_byte_slip():
             assert fh._index is not None
             assert fh._index[:, 0].tolist() == [0, -1, 10072, 20088]
             _same(fh.read(), want)
+
+
+def mark4_missing_frames_and_byte_slip():
+    """Irregular Mark 4 streams: frames dropped, swapped, a junk prefix and
+    bytes cut out of a frame -- the GPU index (all-ones sync search with check
+    one frame on, placement by the BCD time code of track 0) fills what is
+    gone with fill_value.  Also across a year end (unit-year digit wraps)."""
+    import warnings
+    for start in ('2014-06-16T07:38:12.475', '2019-12-31T23:59:59.990'):
+        h0 = bb.mark4.Mark4Header.fromvalues(
+            32, time=start, bps=2, fanout=4, nsb=1, system_id=108)
+        nframe, spf, fb = 11, 80000, 80000
+        rng = np.random.default_rng(17)
+        data = rng.choice(np.array([-3.316505, -1., 1., 3.316505],
+                                   np.float32), size=(nframe * spf, 4))
+        buf = io.BytesIO()
+        fw = bb.mark4.open(buf, 'ws', header0=h0, sample_rate=32e6)
+        fw.write(data)
+        raw = np.frombuffer(buf.getvalue(), np.uint8)
+        assert raw.size == nframe * fb
+        full = ostream.mark4_read(raw, 32, fill_value=-2.)
+        frames = raw.reshape(nframe, fb)
+
+        def check(blob, lost, **kwargs):
+            want = full.copy()
+            for i in lost:
+                want[i * spf:(i + 1) * spf] = -2.
+            with warnings.catch_warnings(record=True):
+                warnings.simplefilter('always')
+                with bb.mark4.open(io.BytesIO(blob.tobytes()), 'rs',
+                                   ntrack=32, decade=2010, sample_rate=32e6,
+                                   fill_value=-2., **kwargs) as fh:
+                    got = fh.read()
+                    assert fh._index is not None
+                    n = min(got.shape[0], want.shape[0])
+                    assert n >= (max(set(range(nframe)) - set(lost)) + 1) * spf
+                    _same(got[:n], want[:n])
+        # frames 3 and 7 dropped, 5 and 6 swapped
+        order = [0, 1, 2, 4, 6, 5, 8, 9, 10]
+        check(frames[order].reshape(-1), [3, 7])
+        check(frames[order].reshape(-1), [3, 7], chunk_nbytes=3 * fb)
+        # 1001 bytes cut out of frame 4 (its successor's sync is not where it
+        # should be: frame 4 reads as fill), junk before the first frame
+        junk = rng.integers(0, 255, 77, dtype=np.uint8)
+        blob = np.concatenate([junk, raw[:4 * fb + 30000],
+                               raw[4 * fb + 31001:]])
+        check(blob, [4])

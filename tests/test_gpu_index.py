@@ -146,3 +146,50 @@ def test_vdif_and_mark5b_index_tables():
         want[f] = pos * 10016
     assert np.array_equal(got, want)
     assert stats.cpu().numpy().tolist() == [11, 0, 0]
+
+
+def test_mark4_index_table():
+    """bb_mark4_index == its numpy restatement (tests/cpu_backend.py, built
+    on the oracle's stream2words) on a written stream with frames shuffled
+    and dropped, across a year end; sync candidates next to the true frame
+    starts are rejected by the CRC-12."""
+    import io
+    import cpu_backend
+    import baseband_b200 as bb
+    h0 = bb.mark4.Mark4Header.fromvalues(
+        64, time='2019-12-31T23:59:59.990', bps=2, fanout=4, nsb=1,
+        system_id=108)
+    rng = np.random.default_rng(3)
+    data = rng.choice(np.array([-3.316505, -1., 1., 3.316505], np.float32),
+                      size=(9 * 80000, 8))
+    buf = io.BytesIO()
+    fw = bb.mark4.open(buf, 'ws', header0=h0, sample_rate=32e6)
+    fw.write(data)
+    frames = np.frombuffer(buf.getvalue(), np.uint8).reshape(9, 160000)
+    order = [0, 2, 1, 3, 5, 6, 8, 7]
+    blob = np.concatenate([rng.integers(0, 255, 13, dtype=np.uint8),
+                           frames[order].reshape(-1)])
+    pat = np.full(256, 0xff, np.uint8)
+    d = torch.from_numpy(blob).to(DEV)
+    loc, cnt = kernels.locate_frames(d, pat, pat, 160000, 512)
+    want_loc, want_cnt = cpu_backend._locate_frames(
+        torch.from_numpy(blob), pat, pat, 160000, 512)
+    n = int(cnt.item())
+    assert n == int(want_cnt.item()) and n >= len(order)
+    assert sorted(loc[:n].cpu().tolist()) == sorted(want_loc[:n].tolist())
+    args = (64, 0, 2019, 365, 365, 365, 345599960, 10, 40)
+    table = kernels.index_table(40, DEV)
+    stats = kernels.zeros(3, torch.int32, DEV)
+    kernels.mark4_index(d, 0, loc, cnt, *args, table, stats)
+    got = kernels.index_table_finish(table).cpu().numpy()
+    ref_table = cpu_backend._index_table(40, None)
+    ref_stats = torch.zeros(3, dtype=torch.int32)
+    cpu_backend._mark4_index(torch.from_numpy(blob), 0, want_loc, want_cnt,
+                             *args, ref_table, ref_stats)
+    want = cpu_backend._index_table_finish(ref_table).numpy()
+    assert np.array_equal(got, want)
+    expect = np.full(40, -1, np.int64)
+    for pos, f in enumerate(order):
+        expect[f] = 13 + pos * 160000
+    assert np.array_equal(got, expect)
+    assert stats.cpu().tolist() == ref_stats.tolist()
