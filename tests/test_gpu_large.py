@@ -160,6 +160,11 @@ def test_c2_full_64gib_stream():
                       device=DEV)
     nchunk = (64 << 30) // (nset * nthread * frame)
     total = 0
+    # the consumer alongside: state counts of the whole stream in bins of
+    # 10 000 frame sets that do not line up with the chunks
+    per_bin = 10000
+    counts = kernels.zeros((-(-nchunk * nset // per_bin), nthread, 1, 4),
+                           torch.int64, torch.device(DEV))
     for k in range(nchunk):
         raw = synthetic.vdif_stream_device(nset, nthread, payload, DEV,
                                            seed=1000 + k, first_set=k * nset)
@@ -173,13 +178,27 @@ def test_c2_full_64gib_stream():
                                 kernels.QUANT_OFFSET_BINARY)
         assert int(bad.item()) == 0
         assert torch.equal(back, raw), 'chunk %d' % k
+        kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1, counts,
+                             set_origin=k * nset, sets_per_bin=per_bin)
         if k % 8 == 0:          # histogram check on every 8th chunk
             want = _code_counts_2bit(raw.view(nframe, frame)[:, 32:])
             got = [int((out == float(v)).sum().item()) for v in lv]
             assert got == want, 'chunk %d' % k
+            one = kernels.zeros((1, nthread, 1, 4), torch.int64,
+                                torch.device(DEV))
+            kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1, one)
+            assert one.sum((0, 1, 2)).tolist() == want, 'chunk %d' % k
+            per_thread = torch.stack([(out[:, :, 0] == float(v)).sum(0)
+                                      for v in lv], -1)
+            assert torch.equal(one[0, :, 0], per_thread), 'chunk %d' % k
         total += out.numel()
         del raw, back
     assert total >= 2.7e11          # the 64 GiB stream: 2.74e11 samples
+    # every sample of the stream was counted exactly once, bin by bin
+    assert int(counts.sum().item()) == total
+    per = counts.sum((1, 2, 3)).cpu().numpy()
+    assert (per[:-1] == per_bin * 32000 * nthread).all()
+    assert per[-1] == total - per[:-1].sum()
 
 
 def test_c3_full_16gib_mark4_stream():
@@ -273,3 +292,69 @@ def test_c5_full_16gib_mark5b_stream():
         assert torch.equal(back.view(nframe, 10016)[ok],
                            raw.view(nframe, 10016)[ok]), 'chunk %d' % k
         del raw, back
+
+
+def test_large_irregular_stream_index():
+    """The GPU frame index at size: 256 MiB of VDIF frame sets in pinned host
+    memory with 1 % of the frames dropped, some swapped and a few bytes cut
+    out of one frame.  The table must be exactly what the damage implies, and
+    a read through it must give fill_value for the lost frames and the
+    reference decode (oracle) for sampled intact ones."""
+    import time
+    import warnings
+    nthread, payload, frame = 8, 5000, 5032
+    nset = (256 << 20) // (nthread * frame)
+    raw = synthetic.vdif_stream(nset, nthread, payload, seed=12,
+                                thread_order=np.arange(nthread))
+    frames = raw.reshape(nset * nthread, frame)
+    rng = np.random.default_rng(4)
+    nframe = nset * nthread
+    keep = np.ones(nframe, bool)
+    keep[rng.choice(np.arange(nthread * 4, nframe - nthread * 4),
+                    nframe // 100, replace=False)] = False
+    order = np.flatnonzero(keep)
+    for a in rng.choice(order.size - 2, 50, replace=False):
+        order[[a, a + 1]] = order[[a + 1, a]]               # swapped pairs
+    blob = frames[order].reshape(-1)
+    cut_at = int(order.size // 2)                 # cut 3 bytes out of a frame
+    cut = cut_at * frame + 1000
+    blob = np.concatenate([blob[:cut], blob[cut + 3:]])
+    lost_by_cut = int(order[cut_at])
+    expect = np.full((nset, nthread), -1, np.int64)
+    for pos, f in enumerate(order):
+        if f == lost_by_cut:
+            continue
+        off = pos * frame - (3 if pos > cut_at else 0)
+        s, t = divmod(int(f), nthread)
+        expect[s, t] = off
+    src = HostBuffer(blob)
+    with warnings.catch_warnings(record=True):
+        warnings.simplefilter('always')
+        fh = bb.vdif.open(src, 'rs', sample_rate=40e6, fill_value=-5.,
+                          device=DEV)
+        if fh._index is None:
+            fh.read(1)                            # detection during a read
+        t0 = time.perf_counter()
+        fh._build_index()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        print('index of %.0f MiB built in %.1f ms (%.1f GB/s)' % (
+            blob.size / 2**20, dt * 1e3, blob.size / dt / 1e9))
+        table = fh._index
+        assert table.shape == expect.shape
+        assert np.array_equal(table, expect)
+        fh.seek(0)
+        data = fh.read()
+    assert tuple(data.shape) == (nset * 20000, nthread)
+    gone = np.argwhere(expect < 0)
+    assert len(gone) == nframe // 100 + 1
+    for s, t in gone[:40]:
+        assert bool((data[s * 20000:(s + 1) * 20000, t] == -5.).all())
+    for s, t in rng.integers(0, [nset, nthread], (12, 2)):
+        if expect[s, t] < 0:
+            continue
+        words = frames[s * nthread + t, 32:].view('<u4')
+        want = codec.vdif_payload_decode(words, 2, (1,), False)[:, 0]
+        got = data[s * 20000:(s + 1) * 20000, t].cpu().numpy()
+        assert np.array_equal(got.view('u4'), want.view('u4'))
+    fh.close()
