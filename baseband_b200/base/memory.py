@@ -41,6 +41,7 @@ class HostBuffer:
         self.pos = 0
         self.name = name
         self.closed = False
+        self._pending = []           # events of device copies still landing
 
     # ------------------------------------------------------------ file API
     def seek(self, offset, whence=0):
@@ -51,7 +52,22 @@ class HostBuffer:
     def tell(self):
         return self.pos
 
+    # Writers let their device-to-host copies land here without blocking the
+    # host (`defer`); whoever looks at the bytes waits for them first.
+    def defer(self, event):
+        """Register an event after which the bytes reserved so far are in
+        place."""
+        self._pending.append(event)
+        if len(self._pending) > 64:
+            self._pending.pop(0).synchronize()
+
+    def wait(self):
+        """Block until every deferred copy into this buffer has landed."""
+        while self._pending:
+            self._pending.pop().synchronize()
+
     def readinto(self, target):
+        self.wait()
         view = np.frombuffer(target, np.uint8)
         n = max(0, min(view.size, self.size - self.pos))
         view[:n] = self.tensor.numpy()[self.pos:self.pos + n]
@@ -62,6 +78,7 @@ class HostBuffer:
         if n is None or n < 0:
             n = self.size - self.pos
         n = max(0, min(n, self.size - self.pos))
+        self.wait()
         out = self.tensor.numpy()[self.pos:self.pos + n].tobytes()
         self.pos += n
         return out
@@ -72,9 +89,11 @@ class HostBuffer:
         return view.size
 
     def close(self):
+        self.wait()
         self.closed = True
 
     def getvalue(self):
+        self.wait()
         return self.tensor.numpy()[:self.size]
 
     # ------------------------------------------------- zero-copy extensions
@@ -82,6 +101,7 @@ class HostBuffer:
         """Pinned tensor over [offset, offset + nbytes) or None past EOF."""
         if offset + nbytes > self.size:
             return None
+        self.wait()
         return self.tensor[offset:offset + nbytes]
 
     def reserve(self, nbytes):

@@ -1216,7 +1216,14 @@ class StreamWriterBase(StreamBase):
         if reserve is not None:
             # sink is pinned host memory: let the D2H copy land in it
             reserve(frames.numel()).copy_(frames.view(-1), non_blocking=True)
-            _device.current_stream_synchronize(frames.device)
+            defer = getattr(self.fh_raw, 'defer', None)
+            if defer is not None and frames.is_cuda:
+                # the sink waits for the copy when its bytes are looked at;
+                # the host goes on (inside read(on_device=writer.write) this
+                # keeps the device-to-host link busy with the decoded chunk)
+                defer(_device.record_event(frames.device))
+            else:
+                _device.current_stream_synchronize(frames.device)
             return
         host = _device.pinned_empty(frames.shape, torch.uint8)
         host.copy_(frames, non_blocking=True)

@@ -244,6 +244,13 @@ class Streams:
             s.synchronize()
 
 
+def record_event(dev):
+    """Event recorded on the current stream of ``dev``."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return ev
+
+
 def current_stream_synchronize(dev):
     torch.cuda.current_stream(dev).synchronize()
 
