@@ -598,6 +598,7 @@ class StreamReaderBase(StreamBase):
 
     def _set_index_table(self, table, phys_frame_nbytes):
         self._small_cache = None     # decoded without the index: stale
+        self._layout_cache = None
         self._index = table
         self._index_lo = np.where(table >= 0, table,
                                   np.iinfo(np.int64).max)
