@@ -14,9 +14,11 @@ __global__ void __launch_bounds__(kI8Threads) k_int8_decode_t(const I8Geom p) {
 
 __global__ void __launch_bounds__(kF8Threads) k_int8_decode_t64(const I8Geom p) {
     __shared__ __align__(16) uint32_t tile[kF8SmemWords];
-    f8_dec_load(p, tile, blockIdx.x, threadIdx.x);
+    // knock-outs (BB_TUNE_KNOCK_I8, tools/sweep_guppi.py): which half of the
+    // kernel costs what
+    if (!(p.knock & 1u)) f8_dec_load(p, tile, blockIdx.x, threadIdx.x);
     __syncthreads();
-    f8_dec_store(p, tile, blockIdx.x, threadIdx.x);
+    if (!(p.knock & 2u)) f8_dec_store(p, tile, blockIdx.x, threadIdx.x);
 }
 
 // Min-blocks hint of 4: lets ptxas keep eight float4 loads in flight (64
@@ -73,6 +75,8 @@ static int fill_geom(I8Geom &g, int64_t nunit, int64_t nrow, int64_t ncol,
     g.tiles_c = (uint32_t)((ncol + tc - 1) / tc);
     g.group = 16;
     if (const char *e = getenv("BB_I8_GROUP")) g.group = (uint32_t)atoi(e);
+    g.knock = 0;
+    if (const char *e = getenv("BB_TUNE_KNOCK_I8")) g.knock = (uint32_t)atoi(e);
     if (g.group < 1) g.group = 1;
     if (g.group > g.tiles_c) g.group = g.tiles_c;
     nblocks = (uint64_t)nunit * g.tiles_r * g.tiles_c;

@@ -34,6 +34,7 @@ struct I8Geom {
     uint32_t nunit, nrow, ncol, ib;  // ib = item bytes (1 or 2)
     uint32_t tiles_r, tiles_c;       // tiles per unit
     uint32_t group;                  // fast path: column tiles per group
+    uint32_t knock;                  // experiments: 1 no loads, 2 no stores
 };
 
 struct I8Tile { uint32_t unit, r0, j0; };

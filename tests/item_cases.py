@@ -111,6 +111,22 @@ def _guppi_payload():
                                  header=frame.header)
 
 
+def _gsb_payload_4bit():
+    # rawdump: real 4-bit samples, two per byte
+    rng = np.random.default_rng(8)
+    words = rng.integers(-128, 128, 256, dtype=np.int8)
+    return bb.gsb.GSBPayload(words, sample_shape=(1,), bps=4,
+                             complex_data=False)
+
+
+def _gsb_payload_8bit():
+    # phased: complex 8-bit, 2 polarisations x 8 channels
+    rng = np.random.default_rng(9)
+    words = rng.integers(-128, 128, 40 * 2 * 8 * 2, dtype=np.int8)
+    return bb.gsb.GSBPayload(words, sample_shape=(2, 8), bps=8,
+                             complex_data=True)
+
+
 def _vdif_frameset():
     with bb.vdif.open(sample_path('sample.vdif'), 'rb') as fh:
         return fh.read_frameset()
@@ -123,6 +139,8 @@ MAKERS = {
     'vdif_payload_1bit': _vdif_payload_1bit,
     'mark5b_payload': _mark5b_payload, 'mark4_payload': _mark4_payload,
     'dada_payload': _dada_payload, 'guppi_payload': _guppi_payload,
+    'gsb_payload_4bit': _gsb_payload_4bit,
+    'gsb_payload_8bit': _gsb_payload_8bit,
     'vdif_frame': _vdif_frame, 'mark5b_frame': _mark5b_frame,
     'mark4_frame': _mark4_frame, 'dada_frame': _dada_frame,
     'guppi_frame': _guppi_frame, 'vdif_frameset': _vdif_frameset,
@@ -140,6 +158,7 @@ ITEMS_3 = ITEMS_2 + [(15,), (slice(10, 20), slice(None), 0), (10, 1, 0),
 NAXES = {'vdif_payload': 2, 'vdif_payload_c4': 2, 'vdif_payload_8bit': 2,
          'vdif_payload_4bit': 2, 'vdif_payload_1bit': 2, 'mark5b_payload': 2,
          'mark4_payload': 2, 'dada_payload': 3, 'guppi_payload': 3,
+         'gsb_payload_4bit': 2, 'gsb_payload_8bit': 3,
          'vdif_frame': 2, 'mark5b_frame': 2, 'mark4_frame': 2,
          'dada_frame': 3, 'guppi_frame': 3, 'vdif_frameset': 3}
 

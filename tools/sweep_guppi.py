@@ -5,7 +5,8 @@ sys.path.insert(0, '.')
 from baseband_b200 import kernels
 from tools.sweep_decode import timeit
 DEV = 'cuda:0'
-for spf in (65536, 60000):
+for spf, knock in ((65536, '0'), (65536, '1'), (65536, '2'), (60000, '0')):
+    os.environ['BB_TUNE_KNOCK_I8'] = knock
     nchan, npol, ov = 512, 2, 512
     fbytes = nchan * spf * npol * 2
     nfr = 8
@@ -19,5 +20,8 @@ for spf in (65536, 60000):
     best, med = timeit(lambda: kernels.decode_int8_transposed(
         raw, off, nfr, nchan, spf * npol, 2, cb, ce, oc0, out))
     nbytes = out.numel() * 5
-    print('group %s spf %d: %7.1f GB/s best %7.1f med' % (
-        os.environ.get('BB_I8_GROUP'), spf, nbytes / best / 1e6, nbytes / med / 1e6))
+    print('group %s spf %d knock %s (1 = no loads, 2 = no stores; algorithmic '
+          'bytes): %7.1f GB/s best %7.1f med' % (
+              os.environ.get('BB_I8_GROUP'), spf, knock, nbytes / best / 1e6,
+              nbytes / med / 1e6))
+os.environ['BB_TUNE_KNOCK_I8'] = '0'
