@@ -85,11 +85,12 @@ SIGNATURES = {
                               POINTER(c_int64)]),
     'bb_locate_frames': (c_int, [
         _pv, c_int64, c_int64, _pv, _pv, c_int32, c_int64, c_int64, c_int32,
-        c_int32, c_int64, _pi64, c_int32, _pv, c_void_p]),
+        c_int32, c_int64, _pi64, c_int32, _pv, _pi64, c_int32, _pv,
+        c_void_p]),
     'bb_index_table_init': (c_int, [_pv, c_int64, c_void_p]),
     'bb_vdif_index': (c_int, [
         _pv, c_int64, _pi64, _pv, c_int32, _pv, c_int32, c_int32, c_int32,
-        c_int32, c_int64, _pv, _pv, c_void_p]),
+        c_int32, c_int32, c_int64, _pv, _pv, c_void_p]),
     'bb_mark5b_index': (c_int, [
         _pv, c_int64, _pi64, _pv, c_int32, c_int32, c_int32, c_int32,
         c_int32, c_int64, _pv, _pv, c_void_p]),

@@ -698,8 +698,11 @@ class StreamReaderBase(StreamBase):
         step = max(4 * frame_nbytes, self._chunk_nbytes // frame_nbytes
                    * frame_nbytes)
         table = kernels.index_table(nset_max * nslot, dev)
-        stats = kernels.zeros(3, torch.int32, dev)
+        stats = kernels.zeros(4, torch.int32, dev)
         counts = []
+        # headers not followed by another one (kept aside, see below)
+        loose = (torch.empty(4096, dtype=torch.int64, device=dev),
+                 kernels.zeros(1, torch.int32, dev))
         stages, ss = self._pipeline(dev)
         zero_copy = getattr(fh, 'pinned_view', None)
         ss.after_caller(1)
@@ -726,7 +729,7 @@ class StreamReaderBase(StreamBase):
                 locations, count = kernels.locate_frames(
                     raw, pat, msk, frame_nbytes, pattern_offset,
                     own_stop=n if at_eof else step, check=1, at_eof=at_eof,
-                    base=pos)
+                    base=pos, unverified=loose)
                 index_chunk(raw, pos, locations, count, table, stats)
                 st.free = ss.event(1)
             counts.append((count, locations.numel()))
@@ -745,6 +748,8 @@ class StreamReaderBase(StreamBase):
         host = offsets[:nset * nslot].cpu().numpy().reshape(nset, nslot)
         if not (host >= 0).any():
             host = host[:0]
+        nloose = min(int(loose[1].item()), loose[0].numel())
+        self._index_loose = np.sort(loose[0][:nloose].cpu().numpy())
         return host, stats
 
     def _read_raw(self, frame0, nframe, pinned, sample_start=0, nsample=0):

@@ -36,7 +36,8 @@ k_locate_frames(const uint8_t *src, long long nbytes, long long own_stop,
                 const Pattern p, int first, long long pattern_offset,
                 long long frame_nbytes, int check, int at_eof,
                 long long base, long long *locations, int max_out,
-                int *count) {
+                int *count, long long *unverified, int max_unverified,
+                int *count_unverified) {
     const long long loc = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (loc >= own_stop) return;
     const long long at = loc + pattern_offset;
@@ -51,7 +52,16 @@ k_locate_frames(const uint8_t *src, long long nbytes, long long own_stop,
             const long long c = at + (long long)check * frame_nbytes;
             // a check position inside the data must hold the pattern too
             if (c >= 0 && c + p.n <= nbytes) {
-                if (!match_at(src, nbytes, c, p)) return;
+                if (!match_at(src, nbytes, c, p)) {
+                    // a header that is not followed by another one: kept
+                    // aside, the caller may still want it (the last frame
+                    // before trailing damage)
+                    if (unverified) {
+                        const int u = atomicAdd(count_unverified, 1);
+                        if (u < max_unverified) unverified[u] = base + loc;
+                    }
+                    return;
+                }
             } else if (!at_eof && c + p.n > nbytes) {
                 return;                   // cannot be verified in this chunk
             }
@@ -75,7 +85,7 @@ constexpr unsigned long long kEmpty = ~0ull;
 __global__ void __launch_bounds__(kIndexBlock)
 k_vdif_index(const uint8_t *src, long long base, const long long *locations,
              const int *count, int max_loc, const int *thread_slot,
-             int nthread, int seconds0, int frame_nr0, int fps,
+             int nthread, int seconds0, int frame_nr0, int fps, int thread0,
              long long nset_max, unsigned long long *table, int *stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = *count < max_loc ? *count : max_loc;
@@ -96,7 +106,11 @@ k_vdif_index(const uint8_t *src, long long base, const long long *locations,
     }
     atomicMin(table + index * nthread + slot,
               2ull * (unsigned long long)off + invalid);
-    atomicMax(stats, (int)(index < 0x7fffffff ? index : 0x7fffffff));
+    const int capped = (int)(index < 0x7fffffff ? index : 0x7fffffff);
+    atomicMax(stats, capped);
+    // the stream ends with the last good frame of the first header's thread
+    // (`_last_header`, baseband/vdif/base.py:493-519)
+    if (tid == thread0) atomicMax(stats + 3, capped);
 }
 
 __device__ __forceinline__ int bcd_digits(uint32_t v, int ndigit) {
@@ -243,8 +257,11 @@ extern "C" int bb_locate_frames(
     const void *src, int64_t nbytes, int64_t own_stop, const uint8_t *pattern,
     const uint8_t *mask, int32_t pattern_nbytes, int64_t pattern_offset,
     int64_t frame_nbytes, int32_t check, int32_t at_eof, int64_t base,
-    int64_t *locations, int32_t max_locations, int32_t *count, void *stream) {
-    if (!src || !pattern || !locations || !count)
+    int64_t *locations, int32_t max_locations, int32_t *count,
+    int64_t *unverified, int32_t max_unverified, int32_t *count_unverified,
+    void *stream) {
+    if (!src || !pattern || !locations || !count
+        || (unverified && !count_unverified))
         return set_error(BB_ERR_ARGUMENT, "null pointer");
     if (pattern_nbytes < 1 || pattern_nbytes > kMaxPattern)
         return set_error(BB_ERR_ARGUMENT, "pattern must be 1..%d bytes",
@@ -267,7 +284,8 @@ extern "C" int bb_locate_frames(
                       as_stream(stream)>>>(
         (const uint8_t *)src, nbytes, own_stop, p, first, pattern_offset,
         frame_nbytes, check, at_eof, base, (long long *)locations,
-        max_locations, count);
+        max_locations, count, (long long *)unverified, max_unverified,
+        count_unverified);
     BB_CHECK_LAUNCH("bb_locate_frames");
     return BB_OK;
 }
@@ -286,8 +304,8 @@ extern "C" int bb_vdif_index(
     const void *src, int64_t base, const int64_t *locations,
     const int32_t *count, int32_t max_locations, const int32_t *thread_slot,
     int32_t nthread, int32_t seconds0, int32_t frame_nr0,
-    int32_t frames_per_second, int64_t nset_max, uint64_t *table,
-    int32_t *stats, void *stream) {
+    int32_t frames_per_second, int32_t thread0, int64_t nset_max,
+    uint64_t *table, int32_t *stats, void *stream) {
     if (!src || !locations || !count || !thread_slot || !table || !stats)
         return set_error(BB_ERR_ARGUMENT, "null pointer");
     if (nthread < 1 || frames_per_second < 1 || nset_max < 0)
@@ -297,7 +315,8 @@ extern "C" int bb_vdif_index(
                    as_stream(stream)>>>(
         (const uint8_t *)src, base, (const long long *)locations, count,
         max_locations, thread_slot, nthread, seconds0, frame_nr0,
-        frames_per_second, nset_max, (unsigned long long *)table, stats);
+        frames_per_second, thread0, nset_max, (unsigned long long *)table,
+        stats);
     BB_CHECK_LAUNCH("bb_vdif_index");
     return BB_OK;
 }

@@ -466,10 +466,12 @@ def _host_bytes(values):
 
 def locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
                   own_stop=None, check=1, at_eof=True, base=0,
-                  max_locations=None):
+                  max_locations=None, unverified=None):
     """bb_locate_frames -> (locations int64 (max_locations,), count int32[1]),
     both on the device; ``locations[:count]`` are the (unordered) byte
-    positions ``base + loc`` at which the masked pattern starts a frame."""
+    positions ``base + loc`` at which the masked pattern starts a frame.
+    ``unverified = (locations, count)`` (device tensors, count accumulating)
+    collects the positions that hold the pattern but fail the check."""
     lib = _lib.load()
     dev = src.device
     nbytes = src.numel()
@@ -496,7 +498,13 @@ def locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
             msk_p, pat.size, int(pattern_offset), int(frame_nbytes),
             int(check), int(bool(at_eof)), int(base),
             _dev(locations, 'locations'), int(max_locations),
-            _dev(count, 'count'), _stream_ptr(dev))
+            _dev(count, 'count'),
+            None if unverified is None else _dev(unverified[0], 'unverified',
+                                                 torch.int64),
+            0 if unverified is None else unverified[0].numel(),
+            None if unverified is None else _dev(unverified[1], 'count',
+                                                 torch.int32),
+            _stream_ptr(dev))
     _lib.check(rc, lib)
     _count()
     return locations, count
@@ -516,7 +524,7 @@ def index_table(nentry, device):
 
 
 def vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
-               frame_nr0, fps, nset_max, table, stats):
+               frame_nr0, fps, nset_max, table, stats, thread0=-1):
     lib = _lib.load()
     with _on(src.device):
         rc = lib.bb_vdif_index(
@@ -524,8 +532,8 @@ def vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
             _dev(locations, 'locations', torch.int64),
             _dev(count, 'count', torch.int32), locations.numel(),
             _dev(thread_slot, 'thread_slot', torch.int32), nthread,
-            int(seconds0), int(frame_nr0), int(fps), int(nset_max),
-            _dev(table, 'table', torch.int64),
+            int(seconds0), int(frame_nr0), int(fps), int(thread0),
+            int(nset_max), _dev(table, 'table', torch.int64),
             _dev(stats, 'stats', torch.int32), _stream_ptr(src.device))
     _lib.check(rc, lib)
     _count()

@@ -216,8 +216,8 @@ class Mark5BStreamReader(_Mark5BStreamBase, StreamReaderBase):
 
         table, stats = self._build_index_on_device(
             [0xABADDEED], [0xffffffff], 10016, index_chunk, 1, nset_max)
-        if stats[2]:
-            raise OSError('Mark 5B headers with invalid BCD time codes.')
+        # (headers whose BCD time code cannot be read are not placed: their
+        # frames read as fill_value, as in the reference's repair)
         self._set_index_table(table, 10016)
 
     def read(self, count=None, out=None, **kwargs):

@@ -324,10 +324,37 @@ class VDIFStreamReader(_VDIFStreamBase, StreamReaderBase):
         def index_chunk(raw, base, locations, count, table, stats):
             kernels.vdif_index(raw, base, locations, count, self._slots_dev,
                                nslot, h0['seconds'], h0['frame_nr'], fps,
-                               nset_max, table, stats)
+                               nset_max, table, stats,
+                               thread0=h0['thread_id'])
 
         table, stats = self._build_index_on_device(
             pattern, mask, h0.frame_nbytes, index_chunk, nslot, nset_max)
+        # the stream ends with the last good frame of the first header's
+        # thread, as in the reference (vdif/base.py:493-519)
+        table = table[:int(stats[3]) + 1]
+        # A header not followed by another one is normally the frame before
+        # a break (its payload may be short).  The last such frame of the
+        # stream is different: what follows it is beyond the end of the
+        # stream, and the reference, which stops at its last good header,
+        # reads it as it stands.
+        last = int(table.max()) if table.size else -1
+        for loc in self._index_loose:
+            if loc <= last or loc + h0.frame_nbytes > size:
+                continue
+            self.fh_raw.seek(int(loc))
+            try:
+                header = self.fh_raw.read_header(edv=h0.edv)
+            except Exception:
+                continue
+            finally:
+                self.fh_raw.seek(0)
+            index = ((header['seconds'] - h0['seconds']) * fps
+                     + header['frame_nr'] - h0['frame_nr'])
+            slot = int(self._slots_host[header['thread_id']])
+            if (0 <= index < table.shape[0] and 0 <= slot < nslot
+                    and table[index, slot] < 0
+                    and not header['invalid_data']):
+                table[index, slot] = loc
         self._index_stats = {'frames_outside_table': int(stats[1])}
         self._set_index_table(table, h0.frame_nbytes)
 

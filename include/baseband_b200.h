@@ -330,7 +330,11 @@ int bb_host_pread(int32_t fd, void *dst, int64_t nbytes, int64_t offset,
  * required; otherwise a position whose check cannot be seen is left to the
  * next (overlapping) region.  base + loc is appended (atomically, unordered)
  * to locations[0, max_locations); *count (device int32, caller-zeroed)
- * receives the number found, which may exceed max_locations.
+ * receives the number found, which may exceed max_locations.  Positions that
+ * hold the pattern and fit but FAIL the check go to `unverified` (same
+ * conventions; may be NULL): the caller may still accept the last frame
+ * before trailing damage, as the reference does by ending a stream at its
+ * last good header (baseband/vdif/base.py:493-519).
  *
  * Frame table: uint64 entries, bb_index_table_init sets them to "empty".
  * bb_vdif_index / bb_mark5b_index read the header at every location found
@@ -349,8 +353,10 @@ int bb_host_pread(int32_t fd, void *dst, int64_t nbytes, int64_t offset,
  *           matches next to the true frame start when neighbouring header
  *           bits are set; the CRC tells them apart)
  * and keep, per (index, slot), the frame that comes first in the file
- * (atomicMin of 2 * offset + invalid flag).  stats (device int32[3],
- * caller-zeroed): [0] largest index seen, [1] frames outside
+ * (atomicMin of 2 * offset + invalid flag).  stats (device int32[4],
+ * caller-zeroed): [3] (VDIF) largest index among the frames of thread
+ * `thread0`, the first header's: where the reference ends the stream
+ * (`_last_header`, baseband/vdif/base.py:493-519); [0] largest index seen, [1] frames outside
  * [0, nset_max), [2] headers with an invalid BCD time (Mark 4: or a time off
  * the frame grid).
  * bb_index_table_finish turns the table into int64 byte offsets of the
@@ -361,14 +367,17 @@ int bb_locate_frames(const void *src, int64_t nbytes, int64_t own_stop,
                      int32_t pattern_nbytes, int64_t pattern_offset,
                      int64_t frame_nbytes, int32_t check, int32_t at_eof,
                      int64_t base, int64_t *locations, int32_t max_locations,
-                     int32_t *count, void *stream);
+                     int32_t *count, int64_t *unverified,
+                     int32_t max_unverified, int32_t *count_unverified,
+                     void *stream);
 int bb_index_table_init(uint64_t *table, int64_t nentry, void *stream);
 int bb_vdif_index(const void *src, int64_t base, const int64_t *locations,
                   const int32_t *count, int32_t max_locations,
                   const int32_t *thread_slot, int32_t nthread,
                   int32_t seconds0, int32_t frame_nr0,
-                  int32_t frames_per_second, int64_t nset_max,
-                  uint64_t *table, int32_t *stats, void *stream);
+                  int32_t frames_per_second, int32_t thread0,
+                  int64_t nset_max, uint64_t *table, int32_t *stats,
+                  void *stream);
 int bb_mark5b_index(const void *src, int64_t base, const int64_t *locations,
                     const int32_t *count, int32_t max_locations,
                     int32_t jday0, int32_t seconds0, int32_t frame_nr0,

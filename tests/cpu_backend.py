@@ -110,8 +110,18 @@ def _mark5b_scan(src, nframe, frame_stride=10016, frame_offset=None,
         if off < 0:                       # absent according to the index
             uo[i] = -1
             continue
-        h = oheaders.mark5b_parse(buf[off:off + 16].view('<u4'))
-        pl = buf[off + 16:off + 10016].view('<u4')
+        try:
+            h = oheaders.mark5b_parse(buf[off:off + 16].copy().view('<u4'))
+        except ValueError:
+            # a time code that is not BCD: the kernel's bcd() gives -1
+            w = buf[off:off + 16].copy().view('<u4')
+            h = {'sync_pattern': int(w[0]), 'user': int(w[1]) >> 16,
+                 'internal_tvg': (int(w[1]) >> 15) & 1,
+                 'frame_nr': int(w[1]) & 0x7fff, 'bcd_jday': int(w[2]) >> 20,
+                 'bcd_seconds': int(w[2]) & 0xfffff,
+                 'bcd_fraction': int(w[3]) >> 16, 'crc': int(w[3]) & 0xffff,
+                 'jday': -1, 'seconds': -1, 'fraction_ns': -1}
+        pl = buf[off + 16:off + 10016].copy().view('<u4')
         valid = not bool((pl == 0x11223344).all())
         row = [h['sync_pattern'], h['user'], h['internal_tvg'], h['frame_nr'],
                h['bcd_jday'], h['bcd_seconds'], h['bcd_fraction'], h['crc'],
@@ -199,7 +209,7 @@ _EMPTY = -1            # 0xffff...ff as int64
 
 def _locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
                    own_stop=None, check=1, at_eof=True, base=0,
-                   max_locations=None):
+                   max_locations=None, unverified=None):
     """k_locate_frames restated with numpy (csrc/bb_index.cu)."""
     buf = src.numpy()
     nbytes = buf.size
@@ -226,6 +236,11 @@ def _locate_frames(src, pattern, mask=None, frame_nbytes=0, pattern_offset=0,
                 c = at + check * frame_nbytes
                 if c >= 0 and c + n <= nbytes:
                     if not hits[c]:
+                        if unverified is not None:
+                            u = int(unverified[1])
+                            if u < unverified[0].numel():
+                                unverified[0][u] = base + loc
+                            unverified[1].add_(1)
                         continue
                 elif not at_eof and c + n > nbytes:
                     continue
@@ -249,7 +264,7 @@ def _scatter(table, at, off, invalid):
 
 
 def _vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
-                frame_nr0, fps, nset_max, table, stats):
+                frame_nr0, fps, nset_max, table, stats, thread0=-1):
     buf, slots, st = src.numpy(), thread_slot.numpy(), stats.numpy()
     for off in locations.numpy()[:min(int(count), locations.numel())]:
         w = buf[off - base:off - base + 16].copy().view('<u4')
@@ -263,6 +278,8 @@ def _vdif_index(src, base, locations, count, thread_slot, nthread, seconds0,
             continue
         _scatter(table, index * nthread + slot, off, int(w[0]) >> 31)
         st[0] = max(st[0], index)
+        if (int(w[3]) >> 16) & 0x3ff == thread0 and st.size > 3:
+            st[3] = max(st[3], index)
 
 
 def _mark5b_index(src, base, locations, count, jday0, seconds0, frame_nr0,

@@ -121,7 +121,7 @@ def test_vdif_and_mark5b_index_tables():
                                                     0xfc00ffff], 1032)
     slot = torch.from_numpy(np.arange(1024, dtype=np.int32)).to(DEV)
     table = kernels.index_table(20 * nthread, DEV)
-    stats = kernels.zeros(3, torch.int32, DEV)
+    stats = kernels.zeros(4, torch.int32, DEV)
     kernels.vdif_index(d, 0, loc, cnt, slot, nthread, 100, 0, 5, 20, table,
                        stats)
     got = kernels.index_table_finish(table).cpu().numpy().reshape(20, nthread)
@@ -138,14 +138,14 @@ def test_vdif_and_mark5b_index_tables():
     d = torch.from_numpy(blob).to(DEV)
     loc, cnt = kernels.locate_frames(d, [0xABADDEED], None, 10016)
     table = kernels.index_table(40, DEV)
-    stats = kernels.zeros(3, torch.int32, DEV)
+    stats = kernels.zeros(4, torch.int32, DEV)
     kernels.mark5b_index(d, 0, loc, cnt, 999, 86399, 0, 4, 40, table, stats)
     got = kernels.index_table_finish(table).cpu().numpy()
     want = np.full(40, -1, np.int64)
     for pos, f in enumerate([0, 1, 3, 2, 4, 6, 7, 8, 9, 11, 10]):
         want[f] = pos * 10016
     assert np.array_equal(got, want)
-    assert stats.cpu().numpy().tolist() == [11, 0, 0]
+    assert stats.cpu().numpy().tolist() == [11, 0, 0, 0]
 
 
 def test_mark4_index_table():
@@ -179,11 +179,11 @@ def test_mark4_index_table():
     assert sorted(loc[:n].cpu().tolist()) == sorted(want_loc[:n].tolist())
     args = (64, 0, 2019, 365, 365, 365, 345599960, 10, 40)
     table = kernels.index_table(40, DEV)
-    stats = kernels.zeros(3, torch.int32, DEV)
+    stats = kernels.zeros(4, torch.int32, DEV)
     kernels.mark4_index(d, 0, loc, cnt, *args, table, stats)
     got = kernels.index_table_finish(table).cpu().numpy()
     ref_table = cpu_backend._index_table(40, None)
-    ref_stats = torch.zeros(3, dtype=torch.int32)
+    ref_stats = torch.zeros(4, dtype=torch.int32)
     cpu_backend._mark4_index(torch.from_numpy(blob), 0, want_loc, want_cnt,
                              *args, ref_table, ref_stats)
     want = cpu_backend._index_table_finish(ref_table).numpy()
