@@ -6,6 +6,7 @@
 // and no per-slice interpreter overhead, hence native threads instead of a
 // Python thread pool (profiles/r2_file_ingest.txt).
 #include <errno.h>
+#include <pthread.h>
 #include <string.h>
 #include <unistd.h>
 #include <atomic>
@@ -28,9 +29,18 @@ struct CopyJob {
 
 class HostPool {
   public:
+    // One pool per process, made on first use and never destroyed (its
+    // threads are detached).  A forked child starts without threads: it
+    // drops the parent's pool object (whose workers do not exist there, and
+    // whose locks may be held) and makes its own on first use.
     static HostPool &get() {
-        static HostPool pool;
-        return pool;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            pthread_atfork(nullptr, nullptr, [] { instance() = nullptr; });
+        });
+        HostPool *&pool = instance();
+        if (!pool) pool = new HostPool();
+        return *pool;
     }
 
     // Run jobs[0..n) on the pool (job 0 on the calling thread); returns when
@@ -59,13 +69,9 @@ class HostPool {
 
   private:
     HostPool() = default;
-    ~HostPool() {
-        {
-            std::lock_guard<std::mutex> lock(mutex_);
-            stop_ = true;
-        }
-        wake_.notify_all();
-        for (auto &t : workers_) t.join();
+    static HostPool *&instance() {
+        static HostPool *pool = nullptr;
+        return pool;
     }
 
     static void execute(CopyJob &job) {
@@ -86,8 +92,10 @@ class HostPool {
     }
 
     void ensure_workers(int n) {
-        while ((int)workers_.size() < n)
-            workers_.emplace_back([this] { loop(); });
+        while (nworkers_ < n) {
+            std::thread([this] { loop(); }).detach();
+            ++nworkers_;
+        }
     }
 
     void loop() {
@@ -114,7 +122,7 @@ class HostPool {
 
     std::mutex batch_mutex_, mutex_;
     std::condition_variable wake_, finished_;
-    std::vector<std::thread> workers_;
+    int nworkers_ = 0;
     CopyJob *jobs_ = nullptr;
     int next_ = 0, njobs_ = 0, pending_ = 0;
     unsigned long long generation_ = 0;
