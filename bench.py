@@ -334,6 +334,7 @@ def run_b200(args):
     named = measure_named_configs(args, dev, rank, world)
     sharded = measure_sharded_read(args, dev, rank, world)
     consumer = measure_consumer(args, dev, rank, world)
+    file_ingest = measure_file_ingest(args, dev, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -375,7 +376,7 @@ def run_b200(args):
             'traffic': traffic, 'traffic_source': traffic_src},
         'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
         'named_configs': named, 'sharded_read': sharded,
-        'consumer': consumer,
+        'consumer': consumer, 'file_ingest': file_ingest,
         'host_binding': ('rank pinned to the {} CPUs local to its GPU'
                          .format(len(numa_cpus)) if numa_cpus else 'none'),
     }
@@ -680,6 +681,57 @@ def measure_sharded_read(args, dev, rank, world):
     return result
 
 
+def measure_file_ingest(args, dev, rank, world):
+    """Users open files: the same frames from a FILE in the page cache
+    (/dev/shm) through `vdif.open(path, 'rs', device=...).read()`: native
+    thread pool copying out of an mmap of the file into pinned staging, H2D,
+    scan + decode, samples left in HBM.  Packed GB/s per GPU (slowest rank)
+    and Gsamples/s over all ranks."""
+    import torch
+    import torch.distributed as dist
+    import baseband_b200 as bb
+    from baseband_b200 import synthetic
+    nbytes = int(args.file_mib * 2**20)
+    if nbytes <= 0:
+        return None
+    nset = max(1, nbytes // SET_BYTES)
+    folder = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
+    path = os.path.join(folder, 'bb_bench_{}_{}.vdif'.format(os.getpid(),
+                                                             rank))
+    synthetic.vdif_stream(nset, NTHREAD, PAYLOAD, seed=41 + rank,
+                          thread_order=np.arange(NTHREAD)).tofile(path)
+    try:
+        fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
+        best = None
+        for rep in range(4):
+            fh.seek(0)
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            data = fh.read()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            best = dt if best is None or rep and dt < best else best
+            del data
+        fh.close()
+    finally:
+        os.remove(path)
+    torch.cuda.empty_cache()
+    return {'packed_gbs_per_gpu': nset * SET_BYTES / best / 1e9,
+            'gsamples_s': nset * SET_SAMPLES * world / best / 1e9,
+            'file_bytes': int(nset * SET_BYTES),
+            'api': "vdif.open(path, 'rs', device=...).read() of a file in "
+                   "the page cache (" + folder + ")",
+            'how': 'best of 3 passes after a warm-up, all ranks at once, '
+                   'slowest rank; bb_host_copy out of an mmap of the file '
+                   '-> pinned staging -> H2D -> scan + decode'}
+
+
 def measure_consumer(args, dev, rank, world):
     """Second end-to-end line: a consumer that stays on the GPU.  Pinned host
     frames -> `tasks.state_counts(fh, samples_per_bin)` (the reader's ingest
@@ -900,6 +952,9 @@ def main():
     ap.add_argument('--sharded-mib', type=float, default=256.0,
                     help='packed MiB of the ONE logical stream read_sharded '
                          'splits over the ranks (0 = skip)')
+    ap.add_argument('--file-mib', type=float, default=512.0,
+                    help='packed MiB per GPU of the file-ingest leg (0 = '
+                         'skip)')
     ap.add_argument('--consumer-mib', type=float, default=512.0,
                     help='packed MiB per GPU and step of the state-count '
                          'consumer leg (0 = skip)')

@@ -5,7 +5,7 @@ tail -3 gpurun_out/r2_bench_b.err
 python - <<'PY'
 import json
 d = json.load(open('gpurun_out/r2_bench_b.json'))
-for k in ('value', 'ms_per_step', 'timed_region_s', 'decode_only_gsamples_s', 'gpu_launches', 'clocks', 'sharded_read', 'consumer'):
+for k in ("value", "ms_per_step", "timed_region_s", "decode_only_gsamples_s", "gpu_launches", "clocks", "sharded_read", "file_ingest"):
     print(k, d.get(k))
 r = d['roofline']
 print({k: r[k] for k in ('achieved', 'frac', 'burst', 'write_peak', 'frac_of_write_peak', 'frac_of_expand_ceiling')})
