@@ -81,6 +81,8 @@ SIGNATURES = {
         _pv, c_int64, c_int64, c_int32, _pv, _pv, c_uint32, c_int64, c_int32,
         c_int64, _pi64, c_void_p]),
     'bb_host_copy': (c_int, [c_void_p, c_void_p, c_int64, c_int32]),
+    'bb_host_copy_begin': (c_int, [c_void_p, c_void_p, c_int64, c_int32]),
+    'bb_host_copy_wait': (c_int, [POINTER(c_int64)]),
     'bb_host_pread': (c_int, [c_int32, c_void_p, c_int64, c_int64, c_int32,
                               POINTER(c_int64)]),
     'bb_locate_frames': (c_int, [

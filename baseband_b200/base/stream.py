@@ -54,15 +54,10 @@ STAGED_HOST_OUT_MIN_NBYTES = 4 << 20
 PARALLEL_READ_THREADS = max(1, min(8, len(os.sched_getaffinity(0))
                                    if hasattr(os, 'sched_getaffinity')
                                    else (os.cpu_count() or 1)))
-def _parallel_readinto(fh, offset, view):
-    """Fill the writable uint8 numpy array ``view`` from absolute byte
-    ``offset`` of the plain file behind ``fh``.  Returns the bytes read, or
-    None if ``fh`` is not a plain file (the caller falls back to
-    ``readinto``)."""
-    if PARALLEL_READ_THREADS < 1:
-        return None
-    # only genuine binary files: anything else with a fileno() (gzip, ...)
-    # would hand out the bytes of the file underneath it
+def _plain_file(fh):
+    """``(io.FileIO, fd)`` of the plain binary file behind ``fh``, or None:
+    anything else with a fileno() (gzip, ...) would hand out the bytes of the
+    file underneath it."""
     import io
     import stat
     plain = fh
@@ -78,6 +73,20 @@ def _parallel_readinto(fh, offset, view):
             return None
     except (OSError, ValueError):
         return None
+    return raw, fd
+
+
+def _parallel_readinto(fh, offset, view):
+    """Fill the writable uint8 numpy array ``view`` from absolute byte
+    ``offset`` of the plain file behind ``fh``.  Returns the bytes read, or
+    None if ``fh`` is not a plain file (the caller falls back to
+    ``readinto``)."""
+    if PARALLEL_READ_THREADS < 1:
+        return None
+    plain = _plain_file(fh)
+    if plain is None:
+        return None
+    raw, fd = plain
     import ctypes
     from .._lib import host_io
     lib = host_io()
@@ -95,6 +104,32 @@ def _parallel_readinto(fh, offset, view):
     rc = lib.bb_host_pread(fd, dst, n, offset, PARALLEL_READ_THREADS,
                            ctypes.byref(nread))
     return int(nread.value) if rc == 0 else None
+
+
+class _Ready:
+    """A chunk read that is already complete."""
+    def __init__(self, value):
+        self.value = value
+
+    def wait(self):
+        return self.value
+
+
+class _PendingCopy:
+    """A chunk being copied into pinned staging by the library's thread pool
+    (bb_host_copy_begin); `wait` returns the staging tensor."""
+    def __init__(self, lib, tensor, nbytes):
+        self.lib, self.tensor, self.nbytes = lib, tensor, nbytes
+
+    def wait(self):
+        import ctypes
+        lib, self.lib = self.lib, None
+        if lib is not None:
+            moved = ctypes.c_int64(0)
+            lib.bb_host_copy_wait(ctypes.byref(moved))
+            if moved.value != self.nbytes:
+                raise EOFError('could not read a whole chunk of frames.')
+        return self.tensor
 
 
 _file_maps = None
@@ -773,6 +808,39 @@ class StreamReaderBase(StreamBase):
                 nframe, frame0))
         return pinned
 
+    def _read_raw_begin(self, frame0, nframe, pinned, sample_start=0,
+                        nsample=0):
+        """Start filling ``pinned`` with the bytes of a chunk and return a
+        handle whose ``wait()`` gives the tensor to upload.  For plain files
+        the copy out of the page cache runs on the library's thread pool
+        while the caller queues the previous chunk's GPU work (one chunk of
+        read-ahead); everything else is read on the spot."""
+        if (type(self)._read_raw is StreamReaderBase._read_raw
+                and PARALLEL_READ_MMAP and PARALLEL_READ_THREADS >= 1
+                and getattr(self.fh_raw, 'pinned_view', None) is None):
+            if self._index is not None:
+                offset, span = self._chunk_layout(frame0, nframe)[:2]
+                target = pinned[:span]
+            else:
+                offset = self._file_offset0 + frame0 * self._frame_nbytes
+                target = pinned
+            n = target.numel()
+            plain = _plain_file(self.fh_raw)
+            if plain is not None and n >= PARALLEL_READ_MIN_NBYTES:
+                mapped = _mapped_file(plain[0], plain[1], offset + n)
+                if mapped is not None and mapped[1].size >= offset + n:
+                    import ctypes
+                    from .._lib import host_io
+                    lib = host_io()
+                    rc = lib.bb_host_copy_begin(
+                        ctypes.c_void_p(target.data_ptr()),
+                        ctypes.c_void_p(mapped[1].ctypes.data + offset), n,
+                        PARALLEL_READ_THREADS)
+                    if rc == 0:
+                        return _PendingCopy(lib, target, n)
+        got = self._read_raw(frame0, nframe, pinned, sample_start, nsample)
+        return _Ready(pinned if got is None else got)
+
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
         """Decode ``nsample`` samples starting ``sample_start`` samples into
         the first frame of ``raw`` (device bytes of ``nframe`` frames) into
@@ -874,23 +942,38 @@ class StreamReaderBase(StreamBase):
         spf = self._samples_per_frame
         per = self._frames_per_chunk()
         ss.after_caller(1)
-        for k, c0 in enumerate(range(frame0, frame0 + nframe, per)):
+        starts = list(range(frame0, frame0 + nframe, per))
+
+        def begin(k):
+            c0 = starts[k]
             nf = min(per, frame0 + nframe - c0)
             st = stages[k % 2]
-            nbytes = self._chunk_nbytes_of(c0, nf, 0, nf * spf)
             if st.done is not None:
                 st.done.synchronize()
-            pin, raw = st.buffers(nbytes, 0, dev, False)
-            got = self._read_raw(c0, nf, pin, 0, nf * spf)
-            pin = pin if got is None else got
-            with ss.use(0):
-                ss.wait_event(0, st.free)
-                self._upload(raw, pin, c0, nf)
-                st.done = ss.event(0)
-            with ss.use(1):
-                ss.wait_event(1, st.done)
-                fn(raw, c0, nf)
-                st.free = ss.event(1)
+            pin, _ = st.buffers(self._chunk_nbytes_of(c0, nf, 0, nf * spf),
+                                0, dev, False)
+            return self._read_raw_begin(c0, nf, pin, 0, nf * spf)
+
+        ahead = begin(0) if starts else None
+        for k, c0 in enumerate(starts):
+            nf = min(per, frame0 + nframe - c0)
+            st = stages[k % 2]
+            raw = st.raw[:self._chunk_nbytes_of(c0, nf, 0, nf * spf)]
+            pin = ahead.wait()
+            ahead = begin(k + 1) if k + 1 < len(starts) else None
+            try:
+                with ss.use(0):
+                    ss.wait_event(0, st.free)
+                    self._upload(raw, pin, c0, nf)
+                    st.done = ss.event(0)
+                with ss.use(1):
+                    ss.wait_event(1, st.done)
+                    fn(raw, c0, nf)
+                    st.free = ss.event(1)
+            except BaseException:
+                if ahead is not None:
+                    ahead.wait()
+                raise
         ss.caller_after(1)
 
     # -- device output ---------------------------------------------------
@@ -907,39 +990,61 @@ class StreamReaderBase(StreamBase):
             flat = torch.empty(count * fps, dtype=torch.float32, device=dev)
         stages, ss = self._pipeline(dev)
         ss.after_caller(1)
-        for k, (f0, nf, s0, ns, row) in enumerate(self._chunks(start, count)):
+        chunks = list(self._chunks(start, count))
+
+        def begin(k):
+            """Start reading chunk k into its stage's pinned buffer."""
+            f0, nf, s0, ns, _ = chunks[k]
             st = stages[k % 2]
-            nbytes = self._chunk_nbytes_of(f0, nf, s0, ns)
             if st.done is not None:
                 st.done.synchronize()        # pinned buffer free again
-            pin, raw = st.buffers(nbytes, 0, dev, False)
-            got = self._read_raw(f0, nf, pin, s0, ns)
-            pin = pin if got is None else got
-            with ss.use(0):
-                # raw[k%2] must no longer be read by the decode of chunk k-2
-                # (only that: the copy overlaps the decode of chunk k-1)
-                ss.wait_event(0, st.free)
-                self._upload(raw, pin, f0, nf)
-                st.done = ss.event(0)
-            with ss.use(1):
-                ss.wait_event(1, st.done)
-                piece = flat[row * fps:(row + ns) * fps]
-                if piece.data_ptr() % 16:
-                    tmp = torch.empty(ns * fps, dtype=torch.float32,
-                                      device=dev)
-                    self._decode_chunk(raw, f0, nf, s0, ns, tmp)
-                    piece.copy_(tmp)
-                else:
-                    self._decode_chunk(raw, f0, nf, s0, ns, piece)
-                if self._on_device is not None:
-                    self._on_device(self._finish(piece, ns))
-                st.free = ss.event(1)
+            pin, _ = st.buffers(self._chunk_nbytes_of(f0, nf, s0, ns), 0,
+                                dev, False)
+            return self._read_raw_begin(f0, nf, pin, s0, ns)
+
+        ahead = begin(0) if chunks else None
+        for k, (f0, nf, s0, ns, row) in enumerate(chunks):
+            st = stages[k % 2]
+            raw = st.raw[:self._chunk_nbytes_of(f0, nf, s0, ns)]
+            pin = ahead.wait()
+            # the next chunk leaves the page cache while this one's copy and
+            # kernels are queued
+            ahead = begin(k + 1) if k + 1 < len(chunks) else None
+            try:
+                self._queue_chunk(ss, st, raw, pin, flat, fps, dev,
+                                  f0, nf, s0, ns, row)
+            except BaseException:
+                if ahead is not None:
+                    ahead.wait()
+                raise
         ss.caller_after(1)
         result = self._finish(flat, count)
         if out is not None and not direct:
             out.copy_(result)
             return out
         return out if direct else result
+
+    def _queue_chunk(self, ss, st, raw, pin, flat, fps, dev, f0, nf, s0, ns,
+                     row):
+        """H2D copy and decode of one chunk of a device-output read."""
+        with ss.use(0):
+            # raw[k%2] must no longer be read by the decode of chunk k-2
+            # (only that: the copy overlaps the decode of chunk k-1)
+            ss.wait_event(0, st.free)
+            self._upload(raw, pin, f0, nf)
+            st.done = ss.event(0)
+        with ss.use(1):
+            ss.wait_event(1, st.done)
+            piece = flat[row * fps:(row + ns) * fps]
+            if piece.data_ptr() % 16:
+                tmp = torch.empty(ns * fps, dtype=torch.float32, device=dev)
+                self._decode_chunk(raw, f0, nf, s0, ns, tmp)
+                piece.copy_(tmp)
+            else:
+                self._decode_chunk(raw, f0, nf, s0, ns, piece)
+            if self._on_device is not None:
+                self._on_device(self._finish(piece, ns))
+            st.free = ss.event(1)
 
     # -- host output -----------------------------------------------------
     def _read_to_host(self, start, count, out):

@@ -46,25 +46,36 @@ class HostPool {
     // Run jobs[0..n) on the pool (job 0 on the calling thread); returns when
     // all are finished.  One batch at a time.
     void run(CopyJob *jobs, int n) {
-        std::lock_guard<std::mutex> batch(batch_mutex_);
+        acquire();
         if (n > 1) {
             ensure_workers(n - 1);
-            {
-                std::lock_guard<std::mutex> lock(mutex_);
-                jobs_ = jobs;
-                next_ = 1;
-                njobs_ = n;
-                pending_ = n - 1;
-                ++generation_;
-            }
-            wake_.notify_all();
+            post(jobs, 1, n);
         }
         execute(jobs[0]);
-        if (n > 1) {
-            std::unique_lock<std::mutex> lock(mutex_);
-            finished_.wait(lock, [this] { return pending_ == 0; });
-            jobs_ = nullptr;
+        if (n > 1) finish();
+        release();
+    }
+
+    // The same without the caller: the jobs (copied) run on the workers only
+    // and `wait` collects them.  begin/wait pairs must not be nested.
+    void begin(const CopyJob *jobs, int n) {
+        acquire();
+        for (int i = 0; i < n; ++i) held_[i] = jobs[i];
+        nheld_ = n;
+        ensure_workers(n < 1 ? 1 : n);
+        post(held_, 0, n);
+    }
+
+    long long wait() {
+        finish();
+        long long total = 0;
+        for (int i = 0; i < nheld_; ++i) {
+            total += held_[i].done;
+            if (held_[i].done < held_[i].nbytes) break;
         }
+        nheld_ = 0;
+        release();
+        return total;
     }
 
   private:
@@ -89,6 +100,38 @@ class HostPool {
             got += k;
         }
         job.done = got;
+    }
+
+    void acquire() {
+        std::unique_lock<std::mutex> lock(mutex_);
+        idle_.wait(lock, [this] { return !busy_; });
+        busy_ = true;
+    }
+
+    void release() {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            busy_ = false;
+        }
+        idle_.notify_one();
+    }
+
+    void post(CopyJob *jobs, int first, int n) {
+        {
+            std::lock_guard<std::mutex> lock(mutex_);
+            jobs_ = jobs;
+            next_ = first;
+            njobs_ = n;
+            pending_ = n - first;
+            ++generation_;
+        }
+        wake_.notify_all();
+    }
+
+    void finish() {
+        std::unique_lock<std::mutex> lock(mutex_);
+        finished_.wait(lock, [this] { return pending_ == 0; });
+        jobs_ = nullptr;
     }
 
     void ensure_workers(int n) {
@@ -120,8 +163,11 @@ class HostPool {
         }
     }
 
-    std::mutex batch_mutex_, mutex_;
-    std::condition_variable wake_, finished_;
+    std::mutex mutex_;
+    std::condition_variable wake_, finished_, idle_;
+    bool busy_ = false;
+    CopyJob held_[64];
+    int nheld_ = 0;
     int nworkers_ = 0;
     CopyJob *jobs_ = nullptr;
     int next_ = 0, njobs_ = 0, pending_ = 0;
@@ -129,16 +175,13 @@ class HostPool {
     bool stop_ = false;
 };
 
-static int run_split(uint8_t *dst, const uint8_t *src, int fd,
-                     long long offset, long long nbytes, int nthreads,
-                     long long *moved) {
+static int split_jobs(CopyJob *jobs, uint8_t *dst, const uint8_t *src, int fd,
+                      long long offset, long long nbytes, int nthreads) {
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
-    // slices on 4 KiB boundaries of the destination, at least 1 MiB each
     long long step = (nbytes + nthreads - 1) / nthreads;
     if (step < (1ll << 20)) step = 1ll << 20;
     step = (step + 4095) / 4096 * 4096;
-    CopyJob jobs[64];
     int n = 0;
     for (long long lo = 0; lo < nbytes && n < 64; lo += step, ++n) {
         jobs[n].dst = dst + lo;
@@ -146,7 +189,17 @@ static int run_split(uint8_t *dst, const uint8_t *src, int fd,
         jobs[n].fd = fd;
         jobs[n].offset = offset + lo;
         jobs[n].nbytes = lo + step < nbytes ? step : nbytes - lo;
+        jobs[n].done = 0;
     }
+    return n;
+}
+
+static int run_split(uint8_t *dst, const uint8_t *src, int fd,
+                     long long offset, long long nbytes, int nthreads,
+                     long long *moved) {
+    // slices on 4 KiB boundaries of the destination, at least 1 MiB each
+    CopyJob jobs[64];
+    const int n = split_jobs(jobs, dst, src, fd, offset, nbytes, nthreads);
     if (n) HostPool::get().run(jobs, n);
     long long total = 0;
     for (int i = 0; i < n; ++i) {
@@ -180,4 +233,21 @@ extern "C" int bb_host_pread(int32_t fd, void *dst, int64_t nbytes,
                        &moved);
     *nread = moved;
     return rc;
+}
+
+extern "C" int bb_host_copy_begin(void *dst, const void *src, int64_t nbytes,
+                                  int32_t nthreads) {
+    if (nbytes < 0 || (nbytes > 0 && (!dst || !src)))
+        return set_error(BB_ERR_ARGUMENT, "bad host copy arguments");
+    CopyJob jobs[64];
+    const int n = split_jobs(jobs, (uint8_t *)dst, (const uint8_t *)src, -1,
+                             0, nbytes, nthreads);
+    HostPool::get().begin(jobs, n);
+    return BB_OK;
+}
+
+extern "C" int bb_host_copy_wait(int64_t *nbytes) {
+    const long long moved = HostPool::get().wait();
+    if (nbytes) *nbytes = moved;
+    return BB_OK;
 }

@@ -310,6 +310,14 @@ int bb_frames_assemble(void *dst, int64_t nframe, int64_t frame_stride,
  * bb_host_pread: the same with pread(2) from a file descriptor, *nread =
  * bytes read before the first short slice.  No CUDA involved. */
 int bb_host_copy(void *dst, const void *src, int64_t nbytes, int32_t nthreads);
+/* The same without blocking the caller: bb_host_copy_begin hands the slices
+ * to the pool and returns; bb_host_copy_wait blocks until they are done
+ * (*nbytes = bytes copied; may be NULL).  One copy in flight at a time, begun
+ * and waited for by the same thread: the readers use it to fill the next
+ * chunk's staging buffer while they queue the current chunk's GPU work. */
+int bb_host_copy_begin(void *dst, const void *src, int64_t nbytes,
+                       int32_t nthreads);
+int bb_host_copy_wait(int64_t *nbytes);
 int bb_host_pread(int32_t fd, void *dst, int64_t nbytes, int64_t offset,
                   int32_t nthreads, int64_t *nread);
 
