@@ -32,9 +32,13 @@ from ..timeutil import Time, as_time
 __all__ = ['StreamBase', 'StreamReaderBase', 'StreamWriterBase',
            'as_hertz', 'DEFAULT_CHUNK_NBYTES']
 
-# Packed bytes per pipeline stage.  A 2-bit stream expands 16x, so 64 MiB of
-# frames become 1 GiB of float32 per stage (two stages in flight).
-DEFAULT_CHUNK_NBYTES = 64 << 20
+# Packed bytes per pipeline stage.  A 2-bit stream expands 16x, so 16 MiB of
+# frames become 256 MiB of float32 per stage (two stages in flight).  With
+# one chunk of read-ahead the per-chunk host work is hidden, and staging
+# buffers of this size stay in the host's last-level cache between the copy
+# out of the page cache and the DMA read: file ingest peaks at 8-16 MiB
+# (profiles/r2_file_chunks.txt: 38-43 GB/s, against 30 at 64 MiB).
+DEFAULT_CHUNK_NBYTES = 16 << 20
 
 # File -> pinned staging buffer: one readinto() copies out of the page cache on
 # a single core (a few GB/s), far below the PCIe link.  Large chunks of plain
