@@ -51,6 +51,16 @@ class Mark4FileReader(_FileBase):
         dt = h1.time - h0.time
         return float(1 / dt)
 
+    def _default_pattern(self):
+        # every track carries the all-ones sync word at steps 64..95
+        # (mark4/header.py:125-131)
+        if self.ntrack is None:
+            raise ValueError('ntrack is needed to locate frames; use '
+                             'determine_ntrack() first.')
+        nb = self.ntrack // 8
+        return np.full(32 * nb, 0xff, np.uint8), {
+            'frame_nbytes': self.ntrack * 2500, 'offset': 64 * nb}
+
     def locate_frame(self, forward=True, maximum=None):
         """Move to the first frame: the byte position where every track has
         the 32-step all-ones sync word at steps 64..95 and again one frame

@@ -55,6 +55,10 @@ class Mark5BFileReader(_FileBase):
                 header = self.read_header()
         return float(highest + 1)
 
+    def _default_pattern(self):
+        # the sync word starts every frame (mark5b/header.py:60-63)
+        return [0xABADDEED], {'frame_nbytes': 10016}
+
     def locate_frame(self, maximum=None):
         """Offset of the first sync pattern that is followed by another one a
         frame ahead (or the end of file) and has a correct CRC

@@ -39,6 +39,27 @@ class _FileBase:
     def temporary_offset(self, offset=None, whence=0):
         return _TemporaryOffset(self.fh_raw, offset, whence)
 
+    # sync search around the file pointer (base/base.py:181-376)
+    def locate_frames(self, pattern=None, **kwargs):
+        """Positions of frames near the current one, nearest first; see
+        `baseband_b200.base.locate.locate_frames`.  Without ``pattern`` the
+        format's own invariant header bits are used."""
+        from ..base import locate
+        if pattern is None:
+            pattern, extra = self._default_pattern()
+            for key, value in extra.items():
+                kwargs.setdefault(key, value)
+        return locate.locate_frames(self.fh_raw, pattern, **kwargs)
+
+    def find_header(self, *args, **kwargs):
+        """Nearest readable header; the file pointer is left at its start."""
+        from ..base import locate
+        return locate.find_header(self, *args, **kwargs)
+
+    def _default_pattern(self):
+        raise TypeError('a pattern (or a header) is needed to locate {} '
+                        'frames.'.format(type(self).__name__))
+
 
 class _TemporaryOffset:
     def __init__(self, fh, offset, whence):
