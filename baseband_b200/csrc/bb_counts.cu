@@ -207,6 +207,70 @@ k_state_counts_hist(const CountGeom p, int words_per_sample) {
     }
 }
 
+// 8-bit two's-complement samples (GUPPI, DADA): count, sum and sum of squares
+// per element instead of a 256-bin histogram -- what power, mean and variance
+// need, still exact integers.  A word holds four samples; dp4a against
+// constant byte masks gives the per-byte-lane sum (x . 1) and sum of squares
+// (x . x) in one instruction each.  As in the histogram path a thread only
+// ever sees words of one class (word index mod P, P = words per complete
+// sample), so a byte lane is one fixed element.
+__global__ void __launch_bounds__(kCountBlock)
+k_int8_moments(const CountGeom p, int words_per_sample) {
+    long long lo, hi, bin;
+    if (!count_range(p, lo, hi, bin)) return;
+    const int t = blockIdx.y;
+    long long sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, nw = 0;
+    for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
+        const long long off = p.unit_offset[s * p.nthread + t];
+        if (off < 0) continue;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(p.src + off);
+        // partial sums of up to 32 words stay in 32 bits (32 * 16384 * ...)
+        for (uint32_t i0 = threadIdx.x; i0 < p.nword;
+             i0 += 32u * kCountBlock) {
+            int ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0}, n = 0;
+#pragma unroll 4
+            for (uint32_t i = i0; i < p.nword && n < 32;
+                 i += kCountBlock, ++n) {
+                const int v = (int)w[i];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    ps[b] = __dp4a(v, 1 << (8 * b), ps[b]);
+                    pq[b] = __dp4a(v, (int)((uint32_t)v & (0xffu << (8 * b))),
+                                   pq[b]);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                sum[b] += ps[b];
+                sq[b] += pq[b];
+            }
+            nw += n;
+        }
+    }
+    const int P = words_per_sample;               // power of two <= block
+    const int cls = threadIdx.x % P;
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long *out = p.counts
+        + (size_t)(bin * p.nthread + t) * p.nelem * 3;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        long long v[3] = {nw, sum[b], sq[b]};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            for (int o = 16; o >= P && o >= 1; o >>= 1)
+                v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        }
+        if (P >= 32 || lane < (uint32_t)P) {
+            const int e = p.nelem >= 4 ? cls * 4 + b : b % p.nelem;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (v[k])
+                    atomicAdd(out + (size_t)e * 3 + k,
+                              (unsigned long long)v[k]);
+        }
+    }
+}
+
 template <int BPS, int NE>
 static void launch_reg(const CountGeom &g, dim3 grid, cudaStream_t s) {
     k_state_counts_reg<BPS, NE><<<grid, kCountBlock, 0, s>>>(g);
@@ -309,6 +373,58 @@ extern "C" int bb_state_counts(
             if (rc != BB_OK) return rc;
         }
         BB_CHECK_LAUNCH("bb_state_counts");
+    }
+    return BB_OK;
+}
+
+extern "C" int bb_int8_moments(
+    const void *src, const int64_t *unit_offset, int64_t nset, int32_t nthread,
+    int64_t payload_nbytes, int32_t nelem, int64_t set_origin,
+    int64_t sets_per_bin, int64_t *moments, int64_t nbin, void *stream) {
+    if (!src || !unit_offset || !moments)
+        return set_error(BB_ERR_ARGUMENT, "null pointer");
+    if (nset < 0 || nthread < 1 || nthread > 65535 || nelem < 1
+        || (nelem & (nelem - 1)) || payload_nbytes <= 0 || (payload_nbytes & 3)
+        || payload_nbytes % nelem || set_origin < 0 || sets_per_bin < 1
+        || nbin < 1)
+        return set_error(BB_ERR_ARGUMENT, "bad geometry (nelem must be a "
+                         "power of two, payload whole samples and words)");
+    if (!aligned(src, 4))
+        return set_error(BB_ERR_ALIGNMENT, "src must be 4-byte aligned");
+    if (payload_nbytes / 4 > 0x7fffffff)
+        return set_error(BB_ERR_ARGUMENT, "payload too large");
+    const int P = nelem > 4 ? nelem / 4 : 1;
+    if (P > kCountBlock)
+        return set_error(BB_ERR_UNSUPPORTED,
+                         "too many elements per sample for moments");
+    if (nset == 0) return BB_OK;
+    const int64_t b0 = set_origin / sets_per_bin;
+    const int64_t b1 = (set_origin + nset - 1) / sets_per_bin;
+    if (b1 >= nbin)
+        return set_error(BB_ERR_ARGUMENT, "sets run past the last bin");
+    CountGeom g;
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.counts = (unsigned long long *)moments;
+    g.nset = nset;
+    g.set_origin = set_origin;
+    g.sets_per_bin = sets_per_bin;
+    g.nthread = nthread;
+    g.nelem = nelem;
+    g.nword = (uint32_t)(payload_nbytes / 4);
+    const int64_t nb = b1 - b0 + 1;
+    const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
+    int64_t split = (16ll * sm_count() + nb * nthread - 1) / (nb * nthread);
+    if (split > per_bin) split = per_bin;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
+    g.split = (int)split;
+    for (int64_t z0 = 0; z0 < nb; z0 += 65535) {
+        const int64_t nz = nb - z0 < 65535 ? nb - z0 : 65535;
+        g.bin_first = b0 + z0;
+        dim3 grid((unsigned)split, (unsigned)nthread, (unsigned)nz);
+        k_int8_moments<<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
+        BB_CHECK_LAUNCH("bb_int8_moments");
     }
     return BB_OK;
 }

@@ -122,6 +122,33 @@ class GUPPIStreamReader(_GUPPIStreamBase, StreamReaderBase):
             frame += nframe
             row += n
 
+    def _packed_units(self, raw, frame0, nframe):
+        """Units for consumers that work on the packed int8 samples
+        (`tasks.moments`): the non-overlap part of every frame.  Channels
+        first: one unit per channel row (`thread` = channel, elements = pol x
+        (re, im)); time first: one unit per frame (elements = chan x pol x
+        (re, im))."""
+        import torch
+        h0 = self.header0
+        if h0.bps != 8:
+            raise KeyError(h0.bps)
+        ib = 2 if h0.complex_data else 1
+        spf = self._samples_per_frame                  # without the overlap
+        start = np.arange(nframe, dtype=np.int64) * self._frame_nbytes \
+            + h0.nbytes
+        if h0.channels_first:
+            rowbytes = self._full_spf * h0.npol * ib
+            uo = start[:, None] + np.arange(h0.nchan, dtype=np.int64) \
+                * rowbytes
+            geom = (h0.nchan, spf * h0.npol * ib, 8, h0.npol * ib)
+        else:
+            uo = start
+            geom = (1, spf * h0.nchan * h0.npol * ib, 8,
+                    h0.nchan * h0.npol * ib)
+        uo = torch.from_numpy(np.ascontiguousarray(uo.reshape(-1))).to(
+            raw.device)
+        return (uo,) + geom
+
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
         h0 = self.header0
         offsets = np.arange(nframe) * self._frame_nbytes + h0.nbytes

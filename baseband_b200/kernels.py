@@ -609,6 +609,29 @@ def state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
     return counts
 
 
+def int8_moments(src, unit_offset, nset, nthread, payload_nbytes, nelem,
+                 moments, set_origin=0, sets_per_bin=None):
+    """bb_int8_moments: add (n, sum, sum of squares) of ``nset`` sets of
+    8-bit units to ``moments`` (int64 CUDA tensor (nbin, nthread, nelem, 3))."""
+    lib = _lib.load()
+    _require_cuda(src, unit_offset, moments)
+    nbin = moments.shape[0]
+    if tuple(moments.shape[1:]) != (nthread, nelem, 3):
+        raise ValueError('moments must have shape (nbin, nthread, nelem, 3)')
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nset)
+    with _on(src.device):
+        rc = lib.bb_int8_moments(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nset, nthread,
+            payload_nbytes, nelem, int(set_origin), int(sets_per_bin),
+            _dev(moments, 'moments', torch.int64), nbin,
+            _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return moments
+
+
 def probe_fill(dst, pattern=0):
     """bb_probe_fill: write the whole tensor ``dst`` with the decode kernels'
     launch shape (pure-write bandwidth probe)."""

@@ -18,15 +18,19 @@ pipeline (file / pinned host -> H2D -> header scan), and return a few numbers.
     ``sum(x**2) = sum_c counts[c] * level[c]**2``.  Invalid frames do not
     contribute (and do not count in the mean).
 
-Both take any reader with packed bit-field payloads of 1, 2 or 4 bits (VDIF,
-Mark 5B).
+``moments(fh, samples_per_bin)``
+    count, sum and sum of squares for 8-bit two's-complement streams (GUPPI),
+    which `integrated_power` uses for those.
+
+`state_counts` takes any reader with packed bit-field payloads of 1, 2 or 4
+bits (VDIF, Mark 5B).
 """
 import numpy as np
 import torch
 
 from . import kernels
 
-__all__ = ['state_counts', 'integrated_power', 'state_levels']
+__all__ = ['state_counts', 'moments', 'integrated_power', 'state_levels']
 
 
 def _frame_range(fh, count, samples_per_bin):
@@ -102,12 +106,76 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
     return counts if device_output else counts.cpu().numpy()
 
 
+def moments(fh, samples_per_bin=None, count=None):
+    """Count, sum and sum of squares of the next ``count`` samples of a
+    reader of 8-bit two's-complement data (GUPPI), per integration bin and
+    sample element, straight from the packed bytes (exact integers).
+
+    Returns three int64 arrays ``(n, total, total_of_squares)`` of shape
+    ``(nbin,) + sample shape [+ (2,) for complex data]``.  Bins cover whole
+    frames from the current sample pointer; GUPPI's overlap samples, which
+    repeat in the next frame, are left out, and so is the overlap that ends
+    the file.  The sample pointer advances by ``count``."""
+    frame0, nframe, frames_per_bin = _frame_range(fh, _whole_frames(fh, count),
+                                                  samples_per_bin)
+    nbin = -(-nframe // frames_per_bin)
+    state = {}
+
+    def consume(raw, f0, nf):
+        uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
+        if bps != 8:
+            raise TypeError('moments are for 8-bit data; use state_counts')
+        if 'm' not in state:
+            state['geom'] = (nthread, nelem)
+            state['m'] = kernels.zeros((nbin, nthread, nelem, 3), torch.int64,
+                                       raw.device)
+        kernels.int8_moments(raw, uo, nf, nthread, payload_nbytes, nelem,
+                             state['m'], set_origin=f0 - frame0,
+                             sets_per_bin=frames_per_bin)
+
+    fh._for_each_packed_chunk(frame0, nframe, consume)
+    fh.seek(fh.tell() + nframe * fh.samples_per_frame)
+    m = state['m'].cpu().numpy()
+    nthread, nelem = state['geom']
+    h0 = fh.header0
+    ib = 2 if fh.complex_data else 1
+    # (thread = channel, elem = (pol, part)) or (elem = (chan, pol, part))
+    m = m.reshape(nbin, h0.nchan, h0.npol, ib, 3)
+    m = m.transpose(0, 2, 1, 3, 4)                 # -> (nbin, npol, nchan, ..)
+    if ib == 1:
+        m = m[:, :, :, 0]
+    if getattr(fh, 'squeeze', False):
+        m = m.reshape((nbin,) + tuple(d for d in m.shape[1:3] if d > 1)
+                      + m.shape[3:])
+    return m[..., 0], m[..., 1], m[..., 2]
+
+
+def _whole_frames(fh, count):
+    """Default count for formats whose stream ends in an overlap: all whole
+    frames from the sample pointer."""
+    if count is not None:
+        return count
+    spf = fh.samples_per_frame
+    return (fh._nframe * spf) - fh.tell()
+
+
 def integrated_power(fh, samples_per_bin=None, count=None, average=True):
     """Power per integration bin: ``Integrate(Square(fh), samples_per_bin)``
     of the baseband-tasks vocabulary, computed from `state_counts` (float64:
     ``sum_c counts[c] * level[c]**2``; for complex data re**2 + im**2).
     With ``average`` the mean over the valid samples of the bin (NaN for a
     bin without valid samples), else the sum."""
+    if fh.bps == 8 and getattr(fh, '_codec', None) is None \
+            and getattr(fh, '_levels', None) is None:
+        # 8-bit two's complement: from the moments
+        n, _, sq = moments(fh, samples_per_bin, count)
+        total = sq.astype(np.float64)
+        if fh.complex_data:
+            total, n = total.sum(-1), n[..., 0]
+        if not average:
+            return total
+        with np.errstate(invalid='ignore', divide='ignore'):
+            return total / n
     lv = state_levels(fh).astype(np.float64)
     counts = state_counts(fh, samples_per_bin, count)
     total = (counts * lv ** 2).sum(-1)

@@ -424,6 +424,19 @@ int bb_state_counts(const void *src, const int64_t *unit_offset, int64_t nset,
                     int32_t nelem, int64_t set_origin, int64_t sets_per_bin,
                     uint64_t *counts, int64_t nbin, void *stream);
 
+/* The same for 8-bit two's-complement payloads (GUPPI, DADA;
+ * baseband/guppi/payload.py:25-48): instead of a histogram,
+ *   moments[bin][thread][elem][0..2] += (number of samples, sum, sum of
+ *   squares)
+ * as int64 (caller-zeroed): power (sum of squares / n), mean and variance per
+ * integration bin, exact.  elem = byte index within a sample (nelem a power of
+ * two, <= 1024); for channels-first GUPPI a unit is one channel row of a
+ * frame, so `thread` is the channel and elem = (pol, re/im). */
+int bb_int8_moments(const void *src, const int64_t *unit_offset, int64_t nset,
+                    int32_t nthread, int64_t payload_nbytes, int32_t nelem,
+                    int64_t set_origin, int64_t sets_per_bin,
+                    int64_t *moments, int64_t nbin, void *stream);
+
 /* ------------------------------------------------------ bandwidth probes
  * Not part of the reference's path: the ceilings bench.py quotes next to the
  * decode kernels, measured in the same run with the kernels' own launch shape

@@ -397,6 +397,27 @@ def _state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
     return counts
 
 
+def _int8_moments(src, unit_offset, nset, nthread, payload_nbytes, nelem,
+                  moments, set_origin=0, sets_per_bin=None):
+    """numpy restatement of bb_int8_moments (csrc/bb_counts.cu)."""
+    buf = src.numpy()
+    uo = unit_offset.numpy().reshape(nset, nthread)
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nset)
+    out = moments.numpy()
+    for s in range(nset):
+        b = (set_origin + s) // sets_per_bin
+        for t in range(nthread):
+            if uo[s, t] < 0:
+                continue
+            x = buf[uo[s, t]:uo[s, t] + payload_nbytes].view(np.int8) \
+                .astype(np.int64).reshape(-1, nelem)
+            out[b, t, :, 0] += x.shape[0]
+            out[b, t, :, 1] += x.sum(0)
+            out[b, t, :, 2] += (x * x).sum(0)
+    return moments
+
+
 def install(monkeypatch):
     from baseband_b200 import _lib, device, kernels
     emu = emu_build.load()
@@ -433,6 +454,7 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'mark4_scan', _mark4_scan)
     monkeypatch.setattr(kernels, 'frames_assemble', _frames_assemble)
     monkeypatch.setattr(kernels, 'state_counts', _state_counts)
+    monkeypatch.setattr(kernels, 'int8_moments', _int8_moments)
     monkeypatch.setattr(kernels, 'locate_frames', _locate_frames)
     monkeypatch.setattr(kernels, 'index_table', _index_table)
     monkeypatch.setattr(kernels, 'vdif_index', _vdif_index)

@@ -1574,3 +1574,39 @@ def mark4_missing_frames_and_byte_slip():
         blob = np.concatenate([junk, raw[:4 * fb + 30000],
                                raw[4 * fb + 31001:]])
         check(blob, [4])
+
+
+def guppi_task_moments():
+    """tasks.moments / integrated_power for 8-bit GUPPI streams, channels
+    first (with overlap) and time first, against sums over the decoded
+    samples (oracle), with bins that do not line up with the chunks."""
+    from baseband_b200 import tasks
+    for kwargs, fmt in ((dict(nchan=8, npol=2, samples_per_frame=64,
+                              overlap=8), {}),
+                        (dict(nchan=4, npol=2, samples_per_frame=96,
+                              overlap=0), {}),
+                        (dict(nchan=16, npol=1, samples_per_frame=32,
+                              overlap=0), {})):
+        for nframe, per_bin, chunk in ((7, 2, None), (5, 5, 1)):
+            raw, _ = synthetic.guppi_stream(nframe, **kwargs)
+            decoded = ostream.guppi_read(raw)          # (nsample, npol, nchan)
+            with bb.guppi.open(io.BytesIO(raw.tobytes()), 'rs',
+                               squeeze=False) as fh:
+                spf = fh.samples_per_frame
+                if chunk:
+                    fh._chunk_nbytes = chunk * fh._frame_nbytes
+                n, total, sq = tasks.moments(fh, per_bin * spf)
+                assert fh.tell() == nframe * spf
+                fh.seek(0)
+                power = tasks.integrated_power(fh, per_bin * spf)
+            body = decoded[:nframe * spf]
+            parts = np.stack([body.real, body.imag], -1).astype(np.int64)
+            nbin = -(-nframe // per_bin)
+            for b in range(nbin):
+                blk = parts[b * per_bin * spf:(b + 1) * per_bin * spf]
+                assert np.array_equal(n[b], np.full(blk.shape[1:],
+                                                    blk.shape[0]))
+                assert np.array_equal(total[b], blk.sum(0))
+                assert np.array_equal(sq[b], (blk * blk).sum(0))
+                want = (blk.astype(np.float64) ** 2).sum(-1).mean(0)
+                assert np.allclose(power[b], want, rtol=1e-12, atol=0)

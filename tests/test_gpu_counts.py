@@ -75,3 +75,44 @@ def test_state_counts_large_and_errors():
         kernels.state_counts(raw, uo, 1, 1, 8000 - 8000 % 12, 2, 3,
                              torch.zeros((1, 1, 3, 4), dtype=torch.int64,
                                          device=DEV))
+
+
+@pytest.mark.parametrize('nelem', (1, 2, 4, 8, 16, 64, 256, 1024))
+def test_int8_moments_fuzz(nelem):
+    """bb_int8_moments against its numpy restatement: every element class,
+    shuffled / invalid units, bins cutting the call, accumulation, values at
+    the extremes (-128 squared must not overflow the dp4a partial sums)."""
+    rng = np.random.default_rng(50 + nelem)
+    for trial in range(4):
+        nthread = int(rng.choice([1, 2, 5]))
+        nsamp = int(rng.integers(1, 3000)) * max(1, 4 // nelem)
+        payload = nsamp * nelem
+        payload += (-payload) % 4
+        if payload % nelem:
+            payload = -(-payload // (4 * nelem)) * 4 * nelem
+        nset = int(rng.integers(1, 7))
+        hdr = int(rng.choice([0, 4, 16]))
+        frame = payload + hdr
+        nunit = nset * nthread
+        raw = rng.integers(0, 256, nunit * frame + 16, dtype=np.uint8)
+        if trial == 0:
+            raw[:] = 0x80                                # all -128
+        uo = rng.permutation(nunit).astype(np.int64) * frame + hdr
+        uo[rng.random(nunit) < 0.2] = -1
+        per_bin = int(rng.integers(1, nset + 2))
+        origin = int(rng.integers(0, 4))
+        nbin = (origin + nset - 1) // per_bin + 1
+        shape = (nbin, nthread, nelem, 3)
+        want = torch.zeros(shape, dtype=torch.int64)
+        cpu_backend._int8_moments(torch.from_numpy(raw), torch.from_numpy(uo),
+                                  nset, nthread, payload, nelem, want, origin,
+                                  per_bin)
+        got = torch.zeros(shape, dtype=torch.int64, device=DEV)
+        d_raw, d_uo = torch.from_numpy(raw).to(DEV), torch.from_numpy(uo).to(DEV)
+        for _ in range(2):
+            kernels.int8_moments(d_raw, d_uo, nset, nthread, payload, nelem,
+                                 got, origin, per_bin)
+        assert torch.equal(got.cpu(), 2 * want), (nelem, trial)
+    with pytest.raises(ValueError):
+        kernels.int8_moments(d_raw, d_uo, 1, 1, 12, 3, torch.zeros(
+            (1, 1, 3, 3), dtype=torch.int64, device=DEV))
