@@ -46,12 +46,13 @@ elif case == 'guppitf':
     for _ in range(reps):
         kernels.encode_int8_timefirst(out, back, off, nfr, nt, nchan, npol, 2)
 elif case in ('mark5b', 'c2', 'vdif48', 'vdif44', 'vdif22c', 'vdif84',
-              'vdif18', 'gsb'):
+              'vdif18', 'gsb', 'vdif82c'):
     bps, nthread, nelem, payload, hdr = {
         'mark5b': (2, 1, 16, 10000, 16), 'c2': (2, 16, 1, 8000, 32),
         'vdif48': (2, 4, 8, 8000, 32), 'vdif44': (4, 4, 1, 8000, 32),
         'vdif22c': (2, 2, 2, 8000, 32), 'vdif84': (8, 4, 1, 8000, 32),
-        'vdif18': (1, 8, 1, 8000, 32), 'gsb': (8, 2, 1024, 1 << 22, 0)}[case]
+        'vdif18': (1, 8, 1, 8000, 32), 'gsb': (8, 2, 1024, 1 << 22, 0),
+        'vdif82c': (8, 2, 2, 8000, 32)}[case]
     frame = payload + hdr
     nset = int(gib * 2**30) // frame // nthread
     nunit = nset * nthread
