@@ -85,6 +85,11 @@ def read_sharded(fh, rank=None, world=None, gather=False, group=None):
     block = gather_block(fh, world)
     start, stop = min(total, rank * block), min(total, (rank + 1) * block)
     on_device = getattr(fh, '_device_output', False)
+    backend = dist.get_backend(group)
+    if not on_device and backend == 'nccl':
+        raise TypeError('gather=True over NCCL needs a reader with device '
+                        'output (open(..., device=...)): NCCL moves device '
+                        'tensors only.')
     t_dtype = torch.complex64 if fh.complex_data else torch.float32
     shape = (world * block,) + tuple(fh.sample_shape)
     if on_device:
@@ -97,7 +102,6 @@ def read_sharded(fh, rank=None, world=None, gather=False, group=None):
         fh.read(out=mine[:stop - start] if on_device
                 else mine[:stop - start].numpy())
     # rows past the end of the stream (short last blocks) are never looked at
-    backend = dist.get_backend(group)
     if on_device or backend != 'gloo':
         dist.all_gather_into_tensor(whole, mine, group=group)
     else:
