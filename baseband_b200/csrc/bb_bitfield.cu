@@ -23,7 +23,8 @@ struct Unroll {
         : MODE == MODE_WORDROW4 ? 32 / BPS
         : MODE == MODE_WORDROW2 ? 16 / BPS
         : MODE == MODE_WORDROW4X2 ? 64 / BPS
-        : MODE == MODE_WORDROW2X2 ? 32 / BPS : 1;
+        : MODE == MODE_WORDROW2X2 ? 32 / BPS
+        : MODE == MODE_RUNS ? 4 : 1;
     // float4 stores per thread.  Measured (profiles/README.md, per-thread
     // work sweep): the warp-cooperative modes are 2-3 % faster with 8 than
     // with 16 (WORDRUN 6.44 -> 6.63 TB/s, above the copy rate) and slower
@@ -200,6 +201,21 @@ k_decode_bitfield(const DecGeom p, const LevelTable<BPS> lv) {
 #pragma unroll
             for (int b = 0; b < RB; ++b)
                 rowgroup_emit<BPS, CODEC, G, SEL>(p, lut, it[b], lv);
+        }
+        return;
+    }
+    if (MODE == MODE_RUNS) {
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            RunsItem it[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].gidx = -1;
+                if (item < p.nitems) runs_fetch<BPS>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) runs_emit<BPS, CODEC>(p, lut, it[b]);
         }
         return;
     }
@@ -433,6 +449,11 @@ static int launch_decode(const std::vector<DecLaunch> &launches,
         case MODE_RUN:
             k_decode_bitfield<BPS, CODEC, MODE_RUN>
                 <<<tile_grid(n, Unroll<BPS, MODE_RUN>::value), kBlock, 0,
+                   stream>>>(l.g, lv);
+            break;
+        case MODE_RUNS:
+            k_decode_bitfield<BPS, CODEC, MODE_RUNS>
+                <<<tile_grid(n, Unroll<BPS, MODE_RUNS>::value), kBlock, 0,
                    stream>>>(l.g, lv);
             break;
         case MODE_WORDRUN:

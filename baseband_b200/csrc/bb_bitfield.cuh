@@ -76,6 +76,7 @@ struct DecGeom {
     uint32_t debug;                 // knock-out experiments (BB_TUNE_KNOCK)
     float fill;
     FastDiv div_nword, div_ngroup, div_rowlen, div_spf, div_nelem, div_unitlen;
+    FastDiv div_f4row;              // RUNS: float4 per row
 };
 
 // 8-bit offset-binary levels without a table: (code - 127.5) / 35.5 in float32
@@ -369,6 +370,75 @@ BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
     RunItem it;
     run_fetch<BPS>(p, item, it);
     run_emit<BPS, CODEC>(p, lut, it);
+}
+
+// RUNS: RUN for words that hold S = tpw >= 2 complete samples of a thread slot
+// (nelem * BPS * S == 32; several threads of several channels).  In RUN every
+// float4 redoes two divisions, the unit-offset load and the load of a word it
+// shares with S - 1 other float4 -- 93 instructions per float4, issue bound
+// (profiles/r2_ncu_issue_bound_modes.txt).  Here an item is one float4
+// position f of a group of S consecutive rows: the S float4 (one per row) all
+// come out of ONE word, so that work is done once per S stores.  Consecutive
+// lanes take consecutive f: a warp store covers whole rows (rowlen * 4 bytes
+// each) S rows apart.  The planner only picks it when the read starts and ends
+// on multiples of S rows.
+struct RunsItem {
+    uint32_t w, e;                  // word; first element of the float4
+    long long gidx;                 // output float index of row 0, < 0: none
+    bool valid;
+};
+
+template <int BPS>
+BB_HD void runs_fetch(const DecGeom &p, uint32_t item, RunsItem &it) {
+    const uint32_t S = p.tpw;
+    const uint32_t rowlen = p.nthread * p.nelem;
+    uint32_t rg, f;
+    p.div_f4row.divmod(item, rg, f);
+    const uint32_t row = rg * S;                  // within the launch
+    const long long row_abs = p.row_base + row;
+    it.w = 0u;
+    it.valid = false;
+    it.gidx = -1;
+    if (row_abs < 0 || row_abs >= p.nsample) return;
+    it.gidx = row_abs * (long long)rowlen + 4ll * f;
+    const uint32_t slot = (4u * f) >> p.log2_nelem;
+    it.e = (4u * f) & (p.nelem - 1u);
+    uint32_t set, t;
+    p.div_spf.divmod(row, set, t);
+    const long long off = p.unit_offset[(size_t)set * p.nthread + slot];
+    if (off >= 0) {
+        it.valid = true;
+        it.w = load_u32(p.src + off + 4ull * (t / S));
+    }
+}
+
+template <int BPS, int CODEC>
+BB_HD void runs_emit(const DecGeom &p, const float *lut, const RunsItem &it) {
+    if (it.gidx < 0) return;
+    const uint32_t S = p.tpw;
+    const size_t rowlen = (size_t)p.nthread * p.nelem;
+    float *dst = p.out + it.gidx;
+    const float fill_im = p.complex_fill ? 0.f : p.fill;
+#pragma unroll 2
+    for (uint32_t s = 0; s < S; ++s, dst += rowlen) {
+        F4 v;
+        if (it.valid) {
+            const uint32_t pair = ((s << p.log2_nelem) + it.e) >> 1;
+            F2 a = decode_pair<BPS, CODEC>(it.w, pair, lut);
+            F2 b = decode_pair<BPS, CODEC>(it.w, pair + 1, lut);
+            v = F4{a.x, a.y, b.x, b.y};
+        } else {
+            v = F4{p.fill, fill_im, p.fill, fill_im};
+        }
+        *reinterpret_cast<F4 *>(dst) = v;
+    }
+}
+
+template <int BPS, int CODEC>
+BB_HD void dec_runs(const DecGeom &p, const float *lut, uint32_t item) {
+    RunsItem it;
+    runs_fetch<BPS>(p, item, it);
+    runs_emit<BPS, CODEC>(p, lut, it);
 }
 
 // WORDRUN: a warp owns chunk = 32 consecutive words of the launch (nthread

@@ -13,7 +13,8 @@ enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
        MODE_WORDRUN = 4, MODE_WORDROW4 = 7, MODE_ROWWORD4 = 8,
        MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10,
        MODE_WORDROW4X2 = 11, MODE_WORDROW2X2 = 12,     // rows of two float4
-       MODE_TILE4 = 13, MODE_TILE2 = 14 };             // rows of four float4
+       MODE_TILE4 = 13, MODE_TILE2 = 14,               // rows of four float4
+       MODE_RUNS = 15 };        // RUN, one word -> its S samples as S rows
 
 // Development tunables (BB_TUNE_<NAME> environment variables), read at every
 // call so that a sweep can change them inside one process.
@@ -119,6 +120,13 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         }
     }
     const int cpw = 32 / bps;
+    // several threads of several channels, S = cpw / nelem >= 2 samples per
+    // word, read aligned to S rows: one item per word position and float4
+    const int runs_s = (mode == MODE_RUN && nthread > 1 && nelem >= 4
+                        && cpw / nelem >= 2) ? cpw / nelem : 0;
+    if (runs_s && sample_start % runs_s == 0 && nsample % runs_s == 0
+        && tune("BB_TUNE_RUNS", 1))
+        mode = MODE_RUNS;
     int64_t first = sample_start / spf;
     int64_t last = (sample_start + nsample + spf - 1) / spf;
     // items per set and the 32-bit budget for one launch
@@ -131,12 +139,15 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup * (tpw > 8 ? tpw / 8 : 1);
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
+    } else if (mode == MODE_RUNS) {
+        per_set = (uint64_t)spf / runs_s * rowlen / 4;
     } else if (mode == MODE_WORDRUN || is_wordrow(mode) || is_tile(mode)) {
         per_set = nword;                  // items are lanes = words
     } else {
         per_set = (uint64_t)spf * rowlen;
     }
-    const uint64_t budget = mode == MODE_RUN ? 0x3fffffffull
+    const uint64_t budget = (mode == MODE_RUN || mode == MODE_RUNS)
+        ? 0x3fffffffull
         : (mode == MODE_WORDRUN || is_wordrow(mode) || is_tile(mode))
         ? 0x03ffffffull : 0x7fffffffull;
     if (per_set > budget) {
@@ -175,6 +186,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.div_spf = make_fastdiv(spf);
         g.div_nelem = make_fastdiv(nelem);
         g.div_unitlen = make_fastdiv((uint32_t)((uint64_t)spf * nelem));
+        g.div_f4row = make_fastdiv((uint32_t)(rowlen / 4 ? rowlen / 4 : 1));
         DecLaunch l;
         l.mode = mode;
         l.g = g;

@@ -139,6 +139,7 @@ static void run_decode(const std::vector<DecLaunch> &launches,
             if (l.mode == MODE_ROWGROUP4) dec_rowgroup<BPS, CODEC, 4>(l.g, lut, item);
             else if (l.mode == MODE_ROWGROUP2) dec_rowgroup<BPS, CODEC, 2>(l.g, lut, item);
             else if (l.mode == MODE_RUN) dec_run<BPS, CODEC>(l.g, lut, item);
+            else if (l.mode == MODE_RUNS) dec_runs<BPS, CODEC>(l.g, lut, item);
             else dec_scalar<BPS, CODEC>(l.g, lut, item);
         }
     }
