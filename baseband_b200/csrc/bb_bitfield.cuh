@@ -77,6 +77,7 @@ struct DecGeom {
     float fill;
     FastDiv div_nword, div_ngroup, div_rowlen, div_spf, div_nelem, div_unitlen;
     FastDiv div_f4row;              // RUNS: float4 per row
+    uint32_t runs_rows;             // RUNS: rows per item (a multiple of tpw)
 };
 
 // 8-bit offset-binary levels without a table: (code - 127.5) / 35.5 in float32
@@ -372,31 +373,31 @@ BB_HD void dec_run(const DecGeom &p, const float *lut, uint32_t item) {
     run_emit<BPS, CODEC>(p, lut, it);
 }
 
-// RUNS: RUN for words that hold S = tpw >= 2 complete samples of a thread slot
+// RUNS: RUN for words that hold S = tpw >= 1 complete samples of a thread slot
 // (nelem * BPS * S == 32; several threads of several channels).  In RUN every
 // float4 redoes two divisions, the unit-offset load and the load of a word it
 // shares with S - 1 other float4 -- 93 instructions per float4, issue bound
 // (profiles/r2_ncu_issue_bound_modes.txt).  Here an item is one float4
-// position f of a group of S consecutive rows: the S float4 (one per row) all
-// come out of ONE word, so that work is done once per S stores.  Consecutive
-// lanes take consecutive f: a warp store covers whole rows (rowlen * 4 bytes
-// each) S rows apart.  The planner only picks it when the read starts and ends
-// on multiples of S rows.
+// position f of a group of R = runs_rows consecutive rows (R = max(S, 4)): the
+// R float4, one per row, come out of R / S consecutive words of one slot, so
+// that work is done once per R stores.  Consecutive lanes take consecutive f:
+// a warp store covers whole rows (rowlen * 4 bytes each) R rows apart.  The
+// planner only picks it when the read starts and ends on multiples of R rows.
 struct RunsItem {
-    uint32_t w, e;                  // word; first element of the float4
+    uint32_t w[4];                  // the R / S words
+    uint32_t e;                     // first element of the float4
     long long gidx;                 // output float index of row 0, < 0: none
     bool valid;
 };
 
 template <int BPS>
 BB_HD void runs_fetch(const DecGeom &p, uint32_t item, RunsItem &it) {
-    const uint32_t S = p.tpw;
+    const uint32_t S = p.tpw, R = p.runs_rows;
     const uint32_t rowlen = p.nthread * p.nelem;
     uint32_t rg, f;
     p.div_f4row.divmod(item, rg, f);
-    const uint32_t row = rg * S;                  // within the launch
+    const uint32_t row = rg * R;                  // within the launch
     const long long row_abs = p.row_base + row;
-    it.w = 0u;
     it.valid = false;
     it.gidx = -1;
     if (row_abs < 0 || row_abs >= p.nsample) return;
@@ -408,29 +409,36 @@ BB_HD void runs_fetch(const DecGeom &p, uint32_t item, RunsItem &it) {
     const long long off = p.unit_offset[(size_t)set * p.nthread + slot];
     if (off >= 0) {
         it.valid = true;
-        it.w = load_u32(p.src + off + 4ull * (t / S));
+        const uint8_t *q = p.src + off + 4ull * (t / S);
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j)
+            if (j * S < R) it.w[j] = load_u32(q + 4u * j);
     }
 }
 
 template <int BPS, int CODEC>
 BB_HD void runs_emit(const DecGeom &p, const float *lut, const RunsItem &it) {
     if (it.gidx < 0) return;
-    const uint32_t S = p.tpw;
+    const uint32_t S = p.tpw, R = p.runs_rows;
     const size_t rowlen = (size_t)p.nthread * p.nelem;
     float *dst = p.out + it.gidx;
     const float fill_im = p.complex_fill ? 0.f : p.fill;
-#pragma unroll 2
-    for (uint32_t s = 0; s < S; ++s, dst += rowlen) {
-        F4 v;
-        if (it.valid) {
+    if (!it.valid) {
+        for (uint32_t r = 0; r < R; ++r, dst += rowlen)
+            *reinterpret_cast<F4 *>(dst) = F4{p.fill, fill_im, p.fill,
+                                              fill_im};
+        return;
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) {
+        if (j * S >= R) break;
+        const uint32_t w = it.w[j];
+        for (uint32_t s = 0; s < S && j * S + s < R; ++s, dst += rowlen) {
             const uint32_t pair = ((s << p.log2_nelem) + it.e) >> 1;
-            F2 a = decode_pair<BPS, CODEC>(it.w, pair, lut);
-            F2 b = decode_pair<BPS, CODEC>(it.w, pair + 1, lut);
-            v = F4{a.x, a.y, b.x, b.y};
-        } else {
-            v = F4{p.fill, fill_im, p.fill, fill_im};
+            F2 a = decode_pair<BPS, CODEC>(w, pair, lut);
+            F2 b = decode_pair<BPS, CODEC>(w, pair + 1, lut);
+            *reinterpret_cast<F4 *>(dst) = F4{a.x, a.y, b.x, b.y};
         }
-        *reinterpret_cast<F4 *>(dst) = v;
     }
 }
 

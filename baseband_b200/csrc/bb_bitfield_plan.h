@@ -120,13 +120,23 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         }
     }
     const int cpw = 32 / bps;
-    // several threads of several channels, S = cpw / nelem >= 2 samples per
-    // word, read aligned to S rows: one item per word position and float4
+    // several threads of several channels, S = cpw / nelem >= 1 samples per
+    // word: one item per float4 position and group of R = max(S, 4) rows
+    // (R / S words), if the read is aligned to R rows (else to S, S >= 2)
     const int runs_s = (mode == MODE_RUN && nthread > 1 && nelem >= 4
-                        && cpw / nelem >= 2) ? cpw / nelem : 0;
-    if (runs_s && sample_start % runs_s == 0 && nsample % runs_s == 0
-        && tune("BB_TUNE_RUNS", 1))
-        mode = MODE_RUNS;
+                        && cpw / nelem >= 1 && tune("BB_TUNE_RUNS", 1))
+        ? cpw / nelem : 0;
+    int runs_rows = 0;
+    if (runs_s) {
+        const int wide = runs_s > 4 ? runs_s : 4;
+        if (sample_start % wide == 0 && nsample % wide == 0
+            && spf % wide == 0)
+            runs_rows = wide;
+        else if (runs_s >= 2 && sample_start % runs_s == 0
+                 && nsample % runs_s == 0)
+            runs_rows = runs_s;
+    }
+    if (runs_rows) mode = MODE_RUNS;
     int64_t first = sample_start / spf;
     int64_t last = (sample_start + nsample + spf - 1) / spf;
     // items per set and the 32-bit budget for one launch
@@ -140,7 +150,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
     } else if (mode == MODE_RUN) {
         per_set = (uint64_t)spf * rowlen / 4;
     } else if (mode == MODE_RUNS) {
-        per_set = (uint64_t)spf / runs_s * rowlen / 4;
+        per_set = (uint64_t)spf / runs_rows * rowlen / 4;
     } else if (mode == MODE_WORDRUN || is_wordrow(mode) || is_tile(mode)) {
         per_set = nword;                  // items are lanes = words
     } else {
@@ -187,6 +197,7 @@ inline bool plan_decode(const void *src, const int64_t *unit_offset,
         g.div_nelem = make_fastdiv(nelem);
         g.div_unitlen = make_fastdiv((uint32_t)((uint64_t)spf * nelem));
         g.div_f4row = make_fastdiv((uint32_t)(rowlen / 4 ? rowlen / 4 : 1));
+        g.runs_rows = (uint32_t)runs_rows;
         DecLaunch l;
         l.mode = mode;
         l.g = g;

@@ -72,14 +72,21 @@ DECODE_CASES = [
     # with an odd start, which must fall back to RUN
     _case('runs_2bit_4thr_8ch_full', 2, 8, 4, 3, 640, invalid=(5, 6)),
     _case('runs_2bit_8thr_4ch_partial', 2, 4, 8, 3, 404, start=4 * 33,
-          count=4 * 901, invalid=(11,), fill=-3.0),
+          count=4 * 201, invalid=(11,), fill=-3.0),
     _case('runs_1bit_2thr_4ch', 1, 4, 2, 2, 68, start=8, count=8 * 30),
     _case('runs_4bit_5thr_4ch', 4, 4, 5, 2, 240, start=2, count=2 * 77,
           invalid=(0, 9)),
     _case('runs_2bit_2thr_cplx_2ch', 2, 4, 2, 2, 320, cplx=True, start=12,
           count=4 * 50, invalid=(1,), fill=5.0),
+    _case('runs_2bit_4thr_8ch_s2_only', 2, 8, 4, 3, 640, start=2 * 15,
+          count=2 * 401, invalid=(2,)),            # aligned to 2, not to 4
+    _case('runs_8bit_3thr_4ch', 8, 4, 3, 2, 400, start=8, count=4 * 40,
+          invalid=(4,), fill=1.5),                 # S = 1: four words an item
+    _case('runs_2bit_2thr_16ch', 2, 16, 2, 2, 320, invalid=(3,)),
+    _case('runs_4bit_2thr_8ch_cplx', 4, 8, 2, 2, 256, cplx=True, start=4,
+          count=4 * 13),
     _case('run_2bit_8thr_4ch_odd_start', 2, 4, 8, 3, 404, start=4 * 33 + 1,
-          count=4 * 901),
+          count=4 * 201),
     # SCALAR: odd geometries / unaligned row ranges
     _case('2bit_3thr_1ch', 2, 1, 3, 3, 100, invalid=(4,), fill=9.0),
     _case('2bit_1thr_1ch_unaligned', 2, 1, 1, 2, 500, start=3, count=1001),
