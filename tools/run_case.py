@@ -93,6 +93,17 @@ elif case == 'counts':
     for _ in range(reps):
         kernels.state_counts(raw, uo, nset, nthread, payload, 2, 1, acc,
                              sets_per_bin=200)
+elif case == 'mark4ftenc':
+    # 64 tracks, fan-out 2, 16 channels, Fortaleza layout: encode
+    nframe = int(gib * 2**30) // 160000
+    raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,
+                        device=DEV)
+    off = torch.arange(nframe, dtype=torch.int64, device=DEV) * 160000 + 1280
+    out = kernels.mark4_decode(raw, off, nframe, 16, 2, True,
+                               levels.sign_magnitude())
+    back = raw.clone()
+    for _ in range(reps):
+        kernels.mark4_encode(out, back, off, nframe, 16, 2, True)
 elif case == 'mark4enc':
     nframe = int(gib * 2**30) // 160000
     raw = torch.randint(0, 256, (nframe * 160000,), dtype=torch.uint8,
