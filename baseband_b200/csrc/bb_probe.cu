@@ -3,6 +3,7 @@
 // kernels themselves (one-shot grid, 256 threads, 8 float4 per thread, every
 // warp store 512 contiguous bytes).  A write-dominated decoder is bounded by
 // the pure-write rate, not by the 50/50 copy rate.
+#include <stdlib.h>
 #include "bb_runtime.cuh"
 
 namespace bb {
@@ -63,14 +64,34 @@ k_probe_copy(float4 *dst, const float4 *src, unsigned long long n4) {
 template <int PATTERN>
 __global__ void __launch_bounds__(kProbeBlock)
 k_probe_expand(float4 *dst, const uint32_t *src, unsigned long long n4,
-               unsigned long long stream_stride_words) {
+               unsigned long long stream_stride_words, unsigned lead,
+               unsigned ahead) {
     const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (PATTERN == 4 && threadIdx.x == 0 && blockIdx.x % lead == 0) {
+        // pattern 4 = pattern 0 with the reads clustered in time: one thread
+        // in `lead` CTAs asks L2 for the input of `lead` CTAs, `ahead` CTAs
+        // before they run (a CTA reads 2 KiB), so that DRAM sees read bursts
+        // of lead * 2 KiB instead of a trickle mixed into the writes
+        const unsigned long long first =
+            ((unsigned long long)blockIdx.x + ahead) * (kProbeBlock / 32) * 256;
+        const unsigned long long total = n4 * 16 / 16;      // input bytes
+        if (first < total) {
+            unsigned long long nb = (unsigned long long)lead
+                * (kProbeBlock / 32) * 256;
+            if (first + nb > total) nb = (total - first) & ~15ull;
+            if (nb)
+                asm volatile(
+                    "cp.async.bulk.prefetch.L2.global [%0], %1;"
+                    :: "l"(reinterpret_cast<const char *>(src) + first),
+                       "r"((unsigned)nb) : "memory");
+        }
+    }
     const unsigned long long chunk =
         (unsigned long long)blockIdx.x * (kProbeBlock / 32) + warp;
     const unsigned long long base = chunk * (32 * kProbeF4);
     if (base >= n4) return;
     uint32_t w0, w1;
-    if (PATTERN == 0 || PATTERN == 2) {
+    if (PATTERN == 0 || PATTERN == 2 || PATTERN == 4) {
         // pattern 2: the input wraps every MiB, i.e. it stays in L2
         const unsigned long long at = chunk * 32 + lane;
         const uint2 v = reinterpret_cast<const uint2 *>(src)[
@@ -164,7 +185,16 @@ extern "C" int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
         return set_error(BB_ERR_ARGUMENT, "buffer too large for one launch");
     // pattern 1: 16 streams of nbytes / 16 / 16 bytes each
     const unsigned long long stride_words = (unsigned long long)nbytes / 1024;
-    if (pattern == 3) {
+    unsigned lead = 512, ahead = 2048;
+    if (const char *e = getenv("BB_PROBE_LEAD")) lead = (unsigned)atoi(e);
+    if (const char *e = getenv("BB_PROBE_AHEAD")) ahead = (unsigned)atoi(e);
+    if (lead < 1) lead = 1;
+    if (pattern == 4) {
+        k_probe_expand<4><<<(unsigned)grid, kProbeBlock, 0,
+                            as_stream(stream)>>>(
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words, lead,
+            ahead);
+    } else if (pattern == 3) {
         if (!aligned(src, 16))
             return set_error(BB_ERR_ALIGNMENT, "src must be 16-byte aligned");
         k_probe_expand4<<<(unsigned)grid, kProbeBlock, 0, as_stream(stream)>>>(
@@ -172,15 +202,15 @@ extern "C" int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
     } else if (pattern == 1)
         k_probe_expand<1><<<(unsigned)grid, kProbeBlock, 0,
                             as_stream(stream)>>>(
-            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words, lead, ahead);
     else if (pattern == 2)
         k_probe_expand<2><<<(unsigned)grid, kProbeBlock, 0,
                             as_stream(stream)>>>(
-            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words, lead, ahead);
     else
         k_probe_expand<0><<<(unsigned)grid, kProbeBlock, 0,
                             as_stream(stream)>>>(
-            (float4 *)dst, (const uint32_t *)src, n4, stride_words);
+            (float4 *)dst, (const uint32_t *)src, n4, stride_words, lead, ahead);
     BB_CHECK_LAUNCH("bb_probe_expand");
     return BB_OK;
 }

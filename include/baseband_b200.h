@@ -451,7 +451,9 @@ int bb_probe_copy(void *dst, const void *src, int64_t nbytes, void *stream);
  * of dst (pattern 0: contiguous input; 1: input in 16 interleaved streams, the
  * shape of a 16-thread VDIF frame set; 2: contiguous input wrapped to one MiB,
  * i.e. always an L2 hit; 3: a 1:4 stream instead, 8 bit -> float32, reading
- * nbytes / 4 bytes of contiguous input).  nbytes a multiple of 4096. */
+ * nbytes / 4 bytes of contiguous input; 4: pattern 0 with leader threads
+ * prefetching the next wave's input into L2 in bursts, BB_PROBE_LEAD /
+ * BB_PROBE_AHEAD CTAs).  nbytes a multiple of 4096. */
 int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
                     int32_t pattern, void *stream);
 /* bb_probe_prefetch: a pure-read phase that pulls nbytes of src into L2
