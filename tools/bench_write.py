@@ -27,7 +27,6 @@ for label, min_nbytes, threads in (('torch pageable copy', 1 << 60, 1),
                                    ('staged upload, 8 threads', 32 << 20, 8)):
     bbdev.STAGED_UPLOAD_MIN_NBYTES = min_nbytes
     bbdev.STAGED_UPLOAD_THREADS = threads
-    bbdev._copy_pool = None
     best = 1e9
     for rep in range(3):
         sink = HostBuffer(nset * nthread * 8032)
