@@ -83,17 +83,19 @@ struct DecGeom {
 // 8-bit offset-binary levels without a table: (code - 127.5) / 35.5 in float32
 // as numpy computes it (baseband/base/encoding.py:131-144).  A 256-entry table
 // in shared memory suffers ~3-way bank conflicts under random codes (the LSU
-// data pipe was 73 % busy); this is seven ALU operations instead.
-// code - 127.5: the byte is planted in the mantissa of 2^22 (ulp 0.5), so one
-// exact subtraction yields it; the division is a multiplication by the
-// rounded reciprocal corrected with two FMAs (Markstein) -- `affine8_matches`
-// checks on the host, for all 256 codes, that this equals the table given.
+// data pipe was 73 % busy); this is four ALU operations instead.
+// One byte permute plants the code in the second mantissa byte of 2^23 (ulp 1:
+// 2^23 + 256 code), one exact subtraction leaves x = 256 (code - 127.5), and
+// the quotient is x times the reciprocal of 256 * 35.5 carried in two terms,
+// hi + lo, summed in one FMA: a single rounding of a product that is exact to
+// ~2^-48, which for these 256 inputs lands on the correctly rounded quotient.
+// `affine8_matches` checks on the host, for all 256 codes, that this equals
+// the table given (else the table path is used).
 BB_HD float affine8(uint32_t w, uint32_t c) {
-    const uint32_t u = (((w >> (8u * c)) & 0xffu) << 1) | 0x4A800000u;
-    const float x = add_rn(uint_as_float(u), -4194431.5f);
-    constexpr float r = 1.0f / 35.5f;
-    const float q = mul_rn(x, r);
-    return fma_rn(fma_rn(-q, 35.5f, x), r, q);
+    const uint32_t u = byte_perm(w, 0x4B000000u, 0x7404u | (c << 4));
+    const float x = add_rn(uint_as_float(u), -8421248.0f);   // 2^23 + 32640
+    constexpr float r_hi = 0x1.cd8568p-14f, r_lo = 0x1.207362p-39f;
+    return fma_rn(x, r_hi, mul_rn(x, r_lo));
 }
 
 inline bool affine8_matches(const float *levels) {

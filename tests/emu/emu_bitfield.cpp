@@ -285,3 +285,14 @@ extern "C" long long emu_quant2_check(int is_double, int nulp) {
     }
     return bad;
 }
+
+// Number of 8-bit codes for which the table-free decode differs (bitwise)
+// from the level table given.
+extern "C" int emu_affine8_mismatches(const float *levels) {
+    int bad = 0;
+    for (uint32_t code = 0; code < 256; ++code) {
+        const float v = affine8(code << 16, 2);
+        bad += __builtin_memcmp(&v, &levels[code], 4) != 0;
+    }
+    return bad + (affine8_matches(levels) ? 0 : 1000);
+}

@@ -332,6 +332,19 @@ def test_quant2_folded_thresholds(emu):
     assert emu.emu_quant2_check(1, 200000) == 0
 
 
+def test_affine8_is_the_8bit_table(emu):
+    """The table-free 8-bit decode (byte permute, subtract, two-term
+    reciprocal) reproduces the reference's 256 levels bit for bit, so the
+    planner takes it for the standard table -- and not for another one."""
+    emu.emu_affine8_mismatches.restype = ctypes.c_int
+    emu.emu_affine8_mismatches.argtypes = [ctypes.c_void_p]
+    table = np.ascontiguousarray(levels.offset_binary(8))
+    assert emu.emu_affine8_mismatches(_ptr(table)) == 0
+    other = table.copy()
+    other[17] = np.nextafter(other[17], np.float32(1))
+    assert emu.emu_affine8_mismatches(_ptr(other)) == 1001
+
+
 def test_fuzz_bitfield(emu):
     """Random geometries through the planner + kernel bodies vs the oracle."""
     from bitfield_cases import fuzz_cases
