@@ -111,6 +111,7 @@ SIGNATURES = {
     'bb_probe_copy': (c_int, [_pv, _pv, c_int64, c_void_p]),
     'bb_probe_expand': (c_int, [_pv, c_int64, _pv, c_int32, c_void_p]),
     'bb_probe_prefetch': (c_int, [_pv, c_int64, c_void_p]),
+    'bb_probe_read': (c_int, [_pv, c_int64, c_void_p]),
 }
 
 # every symbol include/baseband_b200.h declares

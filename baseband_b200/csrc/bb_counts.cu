@@ -25,6 +25,7 @@ struct CountGeom {
     long long bin_first;              // first bin this launch covers
     int nthread, nelem, split;
     uint32_t nword;                   // 32-bit words per unit payload
+    uint32_t nseg;                    // register path: work items per unit
 };
 
 __device__ __forceinline__ bool count_range(const CountGeom &p, long long &lo,
@@ -103,6 +104,7 @@ __device__ __forceinline__ void count_quad(const uint4 &v,
 }
 
 constexpr int kCountBlock = 256;
+constexpr uint32_t kCountSeg = 128;     // 16-byte quads per work item (4 per lane)
 
 template <int BPS, int NE>
 __global__ void __launch_bounds__(kCountBlock)
@@ -119,51 +121,65 @@ k_state_counts_reg(const CountGeom p) {
     for (int e = 0; e < NE; ++e) c[e][0] = c[e][1] = c[e][2] = 0u;
     uint32_t nw = 0u;
     const uint32_t nquad = p.nword / 4u;
-    // kSets units per round: their offsets first, then one 16-byte load of
-    // each per thread in flight before any counting (memory-level
-    // parallelism; a unit is only a few KB)
-    constexpr int kSets = 4;
-    for (long long s0 = lo + blockIdx.x; s0 < hi;
-         s0 += (long long)p.split * kSets) {
-        const uint8_t *base[kSets];
-        bool vec = true;
-#pragma unroll
-        for (int u = 0; u < kSets; ++u) {
-            const long long s = s0 + (long long)u * p.split;
-            const long long off = s < hi ? p.unit_offset[s * p.nthread + t]
-                : -1;
-            base[u] = off >= 0 ? p.src + off : nullptr;   // < 0: invalid
-            vec = vec && (reinterpret_cast<uintptr_t>(base[u]) & 15u) == 0;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    // The CTA owns the units of sets lo + blockIdx.x + k * split; a work item
+    // is one segment (kCountSeg 16-byte quads) of one of them, taken by one
+    // warp: four 16-byte loads per lane in flight before any counting, and
+    // the unit offset of the warp's next item is fetched before the current
+    // one is counted (the offset -> payload dependency is off the critical
+    // path).  Per item the bookkeeping is one small division and one 8-byte
+    // load, against 4 x ~25 counting instructions.
+    const long long first = lo + blockIdx.x;
+    const uint32_t nitem = first >= hi ? 0u
+        : (uint32_t)((hi - first + p.split - 1) / p.split) * p.nseg;
+    const long long *uo = p.unit_offset + t;
+    uint32_t item = warp, g = 0u;
+    long long off = -1;
+    if (item < nitem) {
+        const uint32_t k = item / p.nseg;
+        g = item - k * p.nseg;
+        off = uo[(first + (long long)k * p.split) * p.nthread];
+    }
+    while (item < nitem) {
+        const uint32_t next = item + kCountBlock / 32;
+        uint32_t g_next = 0u;
+        long long off_next = -1;
+        if (next < nitem) {
+            const uint32_t k = next / p.nseg;
+            g_next = next - k * p.nseg;
+            off_next = uo[(first + (long long)k * p.split) * p.nthread];
         }
-        if (vec) {                                   // CTA-uniform
-            for (uint32_t i = threadIdx.x; i < nquad; i += kCountBlock) {
-                uint4 v[kSets];
+        if (off >= 0) {                              // < 0: invalid frame
+            const uint8_t *base = p.src + off;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+            const bool last = g + 1u == p.nseg;
+            uint32_t w0 = g * (kCountSeg * 4u);      // words left to do singly
+            uint32_t w1 = last ? p.nword : w0 + kCountSeg * 4u;
+            if ((reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(base);
+                const uint32_t i0 = g * kCountSeg + lane;
+                uint4 v[kCountSeg / 32];
 #pragma unroll
-                for (int u = 0; u < kSets; ++u)
-                    if (base[u])
-                        v[u] = reinterpret_cast<const uint4 *>(base[u])[i];
+                for (int u = 0; u < kCountSeg / 32; ++u)
+                    if (i0 + 32u * u < nquad) v[u] = q[i0 + 32u * u];
 #pragma unroll
-                for (int u = 0; u < kSets; ++u)
-                    if (base[u]) {
+                for (int u = 0; u < kCountSeg / 32; ++u)
+                    if (i0 + 32u * u < nquad) {
                         count_quad<BPS, NE>(v[u], c);
                         nw += 4u;
                     }
+                w0 = last ? nquad * 4u : w1;         // the 0-3 tail words
             }
-        }
-#pragma unroll
-        for (int u = 0; u < kSets; ++u) {
-            if (!base[u]) continue;
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(base[u]);
-            // tail words of a vector pass, or everything when unaligned
-            for (uint32_t i = (vec ? nquad * 4u : 0u) + threadIdx.x;
-                 i < p.nword; i += kCountBlock) {
+            for (uint32_t i = w0 + lane; i < w1; i += 32u) {
                 count_word<BPS, NE>(w[i], c);
                 nw += 1u;
             }
         }
+        item = next;
+        g = g_next;
+        off = off_next;
     }
     // warp sums -> shared 64-bit totals -> one global atomic per counter
-    const uint32_t lane = threadIdx.x & 31u;
     const uint32_t nw_warp = __reduce_add_sync(0xffffffffu, nw);
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
@@ -247,44 +263,119 @@ k_state_counts_hist(const CountGeom p, int words_per_sample) {
 
 // 8-bit two's-complement samples (GUPPI, DADA): count, sum and sum of squares
 // per element instead of a 256-bin histogram -- what power, mean and variance
-// need, still exact integers.  A word holds four samples; dp4a against
-// constant byte masks gives the per-byte-lane sum (x . 1) and sum of squares
-// (x . x) in one instruction each.  As in the histogram path a thread only
-// ever sees words of one class (word index mod P, P = words per complete
-// sample), so a byte lane is one fixed element.
+// need, still exact integers.  A word holds four samples: each byte is
+// sign-extended with one permute, added to a 32-bit sum (two words per
+// three-input add) and squared into a 32-bit sum with one multiply-add; the
+// partial sums are folded into 64-bit totals long before they can overflow.
+// Ten integer operations per word.  (A first version used dp4a against byte
+// masks -- eight dp4a per word -- and stopped at 1.5 TB/s: dp4a issues at a
+// fraction of the integer rate.)  As in
+// the histogram path a thread only ever sees words of one class (word index
+// mod P, P = words per complete sample), so a byte lane is one fixed element.
+struct MomAcc {
+    // a 32-bit partial sum of squares holds 2^32 / 2^14 words
+    static constexpr uint32_t kFold = (1u << 18) - 64u;
+    int s[4] = {0, 0, 0, 0};
+    uint32_t q[4] = {0u, 0u, 0u, 0u}, pend = 0u;
+    long long sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, nw = 0;
+
+    __device__ __forceinline__ void word(uint32_t v) {
+        // byte b sign-extended: one permute with sign replication (or shift)
+        const int x0 = sext<0x8880u>(v), x1 = sext<0x9991u>(v);
+        const int x2 = sext<0xaaa2u>(v), x3 = (int)v >> 24;
+        s[0] += x0;
+        s[1] += x1;
+        s[2] += x2;
+        s[3] += x3;
+        square_add(q[0], (uint32_t)x0);
+        square_add(q[1], (uint32_t)x1);
+        square_add(q[2], (uint32_t)x2);
+        square_add(q[3], (uint32_t)x3);
+        pend += 1u;
+    }
+    // prmt with bit 3 of a selector nibble set replicates the sign of the
+    // chosen byte (the __byte_perm intrinsic only passes three bits)
+    template <uint32_t SEL>
+    static __device__ __forceinline__ int sext(uint32_t v) {
+        int x;
+        asm("prmt.b32 %0, %1, 0, %2;" : "=r"(x) : "r"(v), "n"(SEL));
+        return x;
+    }
+    // q += x * x as one IMAD, spelled out: left to itself the compiler gathers
+    // the bytes of four words with shifts and permutes to feed a dp4a, which
+    // is the slow instruction this formulation avoids.
+    static __device__ __forceinline__ void square_add(uint32_t &q, uint32_t x) {
+        asm("mad.lo.u32 %0, %1, %1, %0;" : "+r"(q) : "r"(x));
+    }
+    __device__ __forceinline__ void fold() {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            sum[b] += s[b];
+            sq[b] += q[b];
+            s[b] = 0;
+            q[b] = 0u;
+        }
+        nw += pend;
+        pend = 0u;
+    }
+    __device__ __forceinline__ void finish() { fold(); }
+};
+
+template <int U>                        // loads in flight per thread
 __global__ void __launch_bounds__(kCountBlock)
 k_int8_moments(const CountGeom p, int words_per_sample) {
     long long lo, hi, bin;
     if (!count_range(p, lo, hi, bin)) return;
     const int t = blockIdx.y;
-    long long sum[4] = {0, 0, 0, 0}, sq[4] = {0, 0, 0, 0}, nw = 0;
+    MomAcc a;
     for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
         const long long off = p.unit_offset[s * p.nthread + t];
         if (off < 0) continue;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(p.src + off);
-        // partial sums of up to 32 words stay in 32 bits (32 * 16384 * ...)
-        for (uint32_t i0 = threadIdx.x; i0 < p.nword;
-             i0 += 32u * kCountBlock) {
-            int ps[4] = {0, 0, 0, 0}, pq[4] = {0, 0, 0, 0}, n = 0;
-#pragma unroll 4
-            for (uint32_t i = i0; i < p.nword && n < 32;
-                 i += kCountBlock, ++n) {
-                const int v = (int)w[i];
+        const uint8_t *base = p.src + off;
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+        uint32_t first = 0u;             // words not taken by the vector pass
+        if (words_per_sample == 1
+            && (reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+            // every word is of the same class: 16-byte loads
+            const uint4 *q4 = reinterpret_cast<const uint4 *>(base);
+            const uint32_t nquad = p.nword / 4u;
+            for (uint32_t i0 = threadIdx.x; i0 < nquad;
+                 i0 += U * kCountBlock) {
+                uint4 v[U];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    ps[b] = __dp4a(v, 1 << (8 * b), ps[b]);
-                    pq[b] = __dp4a(v, (int)((uint32_t)v & (0xffu << (8 * b))),
-                                   pq[b]);
-                }
-            }
+                for (int u = 0; u < U; ++u)
+                    if (i0 + u * kCountBlock < nquad)
+                        v[u] = q4[i0 + u * kCountBlock];
+                if (a.pend > MomAcc::kFold) a.fold();
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                sum[b] += ps[b];
-                sq[b] += pq[b];
+                for (int u = 0; u < U; ++u)
+                    if (i0 + u * kCountBlock < nquad) {
+                        a.word(v[u].x);
+                        a.word(v[u].y);
+                        a.word(v[u].z);
+                        a.word(v[u].w);
+                    }
             }
-            nw += n;
+            first = nquad * 4u;
+        }
+        // a thread's words are kCountBlock apart: the class (index mod P,
+        // P a power of two <= kCountBlock) stays the same
+        for (uint32_t i0 = first + threadIdx.x; i0 < p.nword;
+             i0 += U * kCountBlock) {
+            uint32_t v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * kCountBlock < p.nword)
+                    v[u] = w[i0 + u * kCountBlock];
+            if (a.pend > MomAcc::kFold) a.fold();
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i0 + u * kCountBlock < p.nword) a.word(v[u]);
         }
     }
+    a.finish();
+    const long long nw = a.nw;
+    long long (&sum)[4] = a.sum, (&sq)[4] = a.sq;
     const int P = words_per_sample;               // power of two <= block
     const int cls = threadIdx.x % P;
     const uint32_t lane = threadIdx.x & 31u;
@@ -334,6 +425,12 @@ static int launch_hist(const CountGeom &g, dim3 grid, int P, cudaStream_t s) {
 
 using namespace bb;
 
+// CTAs per SM a launch aims at (development tunable BB_TUNE_COUNT_DEPTH).
+static int count_depth() {
+    const char *e = getenv("BB_TUNE_COUNT_DEPTH");
+    return (e && *e && atoi(e) > 0) ? atoi(e) : 24;     // swept: tools/sweep_counts.py
+}
+
 extern "C" int bb_state_counts(
     const void *src, const int64_t *unit_offset, int64_t nset, int32_t nthread,
     int64_t payload_nbytes, int32_t bps, int32_t nelem, int64_t set_origin,
@@ -376,15 +473,24 @@ extern "C" int bb_state_counts(
     g.nthread = nthread;
     g.nelem = nelem;
     g.nword = (uint32_t)(payload_nbytes / 4);
-    // CTAs per (bin, thread): enough to fill the GPU sixteen deep, at most one
+    // CTAs per (bin, thread): enough to fill the GPU 24 deep, at most one
     // per set of a bin, and few enough words each that 32-bit counters hold
     const int64_t nb = b1 - b0 + 1;
     const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
-    int64_t split = (16ll * sm_count() + nb * nthread - 1) / (nb * nthread);
+    const int64_t want = (int64_t)count_depth() * sm_count();
+    int64_t split = (want + nb * nthread - 1) / (nb * nthread);
     const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
         / (1ll << 26);
     if (split < need) split = need;
     if (split > per_bin) split = per_bin;
+    // register path: a warp takes a segment of a unit, so a CTA wants at
+    // least one segment per warp
+    g.nseg = (g.nword / 4u + kCountSeg - 1u) / kCountSeg;
+    if (g.nseg < 1u) g.nseg = 1u;
+    if (reg) {
+        const int64_t full = per_bin * g.nseg / (kCountBlock / 32);
+        if (split > full && full >= need) split = full;
+    }
     if (split < 1) split = 1;
     if (split > 65535) split = 65535;
     g.split = (int)split;
@@ -452,7 +558,8 @@ extern "C" int bb_int8_moments(
     g.nword = (uint32_t)(payload_nbytes / 4);
     const int64_t nb = b1 - b0 + 1;
     const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
-    int64_t split = (16ll * sm_count() + nb * nthread - 1) / (nb * nthread);
+    const int64_t want = (int64_t)count_depth() * sm_count();
+    int64_t split = (want + nb * nthread - 1) / (nb * nthread);
     if (split > per_bin) split = per_bin;
     if (split < 1) split = 1;
     if (split > 65535) split = 65535;
@@ -461,7 +568,14 @@ extern "C" int bb_int8_moments(
         const int64_t nz = nb - z0 < 65535 ? nb - z0 : 65535;
         g.bin_first = b0 + z0;
         dim3 grid((unsigned)split, (unsigned)nthread, (unsigned)nz);
-        k_int8_moments<<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
+        const char *e_u = getenv("BB_TUNE_MOM_U");
+        const int u = (e_u && *e_u) ? atoi(e_u) : 4;
+        if (u == 8)
+            k_int8_moments<8><<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
+        else if (u == 2)
+            k_int8_moments<2><<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
+        else
+            k_int8_moments<4><<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
         BB_CHECK_LAUNCH("bb_int8_moments");
     }
     return BB_OK;

@@ -659,6 +659,18 @@ def probe_copy(dst, src):
     return dst
 
 
+def probe_read(src):
+    """bb_probe_read: read all of ``src`` and store nothing (pure-read
+    bandwidth probe: the ceiling of the packed-byte consumers)."""
+    lib = _lib.load()
+    nbytes = src.numel() * src.element_size()
+    with _on(src.device):
+        rc = lib.bb_probe_read(_dev(src, 'src'), nbytes,
+                               _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+
+
 def probe_expand(dst, src, pattern=0):
     """bb_probe_expand: write all of ``dst`` from 1/16 as many bytes of
     ``src`` (the ceiling for a 2 bit -> float32 stream)."""

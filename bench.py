@@ -795,7 +795,21 @@ def measure_consumer(args, dev, rank, world):
     torch.cuda.synchronize(dev)
     ms = sorted(a.elapsed_time(b) for a, b in ev[2:])
     kms = ms[len(ms) // 2]
-    del raw, uo, acc
+    # its ceiling, in the same run: the pure-read probe over the same bytes
+    ev = []
+    whole = raw[:raw.numel() // 16 * 16]
+    for k in range(8):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        kernels.probe_read(whole)
+        e1.record()
+        ev.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    ms = sorted(a.elapsed_time(b) for a, b in ev[2:])
+    read_peak = whole.numel() / (ms[len(ms) // 2] * 1e-3) / 1e9
+    frame_gbs = kset * NTHREAD * FRAME / (kms * 1e-3) / 1e9
+    del raw, uo, acc, whole
     torch.cuda.empty_cache()
     return {'value': nset * SET_SAMPLES * world * steps / dt / 1e9,
             'unit': UNIT, 'h2d_bytes_per_step': int(src.size),
@@ -809,9 +823,15 @@ def measure_consumer(args, dev, rank, world):
                 'packed_gbs': kset * NTHREAD * PAYLOAD / (kms * 1e-3) / 1e9,
                 'gsamples_s': kset * SET_SAMPLES / (kms * 1e-3) / 1e9,
                 'ms': kms, 'bound': 'hbm read',
+                'read_peak_gbs': read_peak,
+                'frac_of_read_peak': frame_gbs / read_peak,
                 'what': 'bb_state_counts alone on a resident {:.1f} GiB '
                         'chunk (median of 6 launches, CUDA events); bytes = '
-                        'payload bytes read'.format(args.chunk_gib)},
+                        'payload bytes read; read_peak = bb_probe_read over '
+                        'the same buffer (a kernel that loads and stores '
+                        'nothing), the fraction counts whole frames, as the '
+                        'headers share sectors with the payloads'.format(
+                            args.chunk_gib)},
             'note': 'packed frames in, state counts out: what '
                     'Integrate(Square(fh)) needs, without the 16x expansion '
                     'to float32 ever touching HBM or PCIe'}

@@ -459,6 +459,10 @@ int bb_probe_expand(void *dst, int64_t nbytes, const void *src,
 /* bb_probe_prefetch: a pure-read phase that pulls nbytes of src into L2
  * (prefetch.global.L2::evict_last), for phased read-then-write experiments. */
 int bb_probe_prefetch(const void *src, int64_t nbytes, void *stream);
+/* bb_probe_read: read nbytes of src with the same launch shape and store
+ * nothing: the pure-read rate, the ceiling of the consumers that only read
+ * packed bytes (bb_state_counts, bb_int8_moments). */
+int bb_probe_read(const void *src, int64_t nbytes, void *stream);
 
 #ifdef __cplusplus
 }

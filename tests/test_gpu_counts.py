@@ -81,7 +81,8 @@ def test_state_counts_large_and_errors():
 def test_int8_moments_fuzz(nelem):
     """bb_int8_moments against its numpy restatement: every element class,
     shuffled / invalid units, bins cutting the call, accumulation, values at
-    the extremes (-128 squared must not overflow the dp4a partial sums)."""
+    the extremes (all -128; the overflow point of the 32-bit partial sums is
+    covered by test_gpu_large.test_int8_moments_one_huge_unit)."""
     rng = np.random.default_rng(50 + nelem)
     for trial in range(4):
         nthread = int(rng.choice([1, 2, 5]))

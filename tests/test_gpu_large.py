@@ -358,3 +358,29 @@ def test_large_irregular_stream_index():
         got = data[s * 20000:(s + 1) * 20000, t].cpu().numpy()
         assert np.array_equal(got.view('u4'), want.view('u4'))
     fh.close()
+
+
+def test_int8_moments_one_huge_unit():
+    """bb_int8_moments over one 1.25 GiB unit: a single CTA-thread then sees
+    more than 2^18 words, the point at which its 32-bit partial sums of
+    squares must have been folded into the 64-bit totals.  Worst case first
+    (every sample -128), then a period-4 pattern with known per-lane sums."""
+    n = 5 << 28                                       # bytes, multiple of 16
+    nword = n // 4
+    uo = torch.zeros(1, dtype=torch.int64, device=DEV)
+    raw = torch.full((n,), 0x80, dtype=torch.uint8, device=DEV)
+    got = torch.zeros((1, 1, 4, 3), dtype=torch.int64, device=DEV)
+    kernels.int8_moments(raw, uo, 1, 1, n, 4, got)
+    want = np.array([[nword, -128 * nword, 16384 * nword]] * 4)
+    assert np.array_equal(got.cpu().numpy()[0, 0], want)
+    pattern = np.array([-128, 127, -1, 3], np.int8)
+    raw.view(torch.int32).fill_(int(pattern.view(np.int32)[0]))
+    got.zero_()
+    kernels.int8_moments(raw, uo, 1, 1, n, 4, got)
+    want = np.stack([np.full(4, nword), pattern.astype(np.int64) * nword,
+                     pattern.astype(np.int64) ** 2 * nword], axis=1)
+    assert np.array_equal(got.cpu().numpy()[0, 0], want)
+    # one element (real, single polarisation): the four lanes are summed
+    got1 = torch.zeros((1, 1, 1, 3), dtype=torch.int64, device=DEV)
+    kernels.int8_moments(raw, uo, 1, 1, n, 1, got1)
+    assert np.array_equal(got1.cpu().numpy()[0, 0, 0], want.sum(axis=0))
