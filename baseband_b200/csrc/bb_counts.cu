@@ -224,39 +224,213 @@ k_state_counts_hist(const CountGeom p, int words_per_sample) {
     long long lo, hi, bin;
     if (!count_range(p, lo, hi, bin)) return;
     const int t = blockIdx.y;
-    for (int i = threadIdx.x; i < NCNT * kHistBlock; i += kHistBlock)
-        hist[i] = 0u;
-    // (only this thread touches column threadIdx.x: no barrier needed)
-    for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
-        const long long off = p.unit_offset[s * p.nthread + t];
-        if (off < 0) continue;
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(p.src + off);
-        for (uint32_t i = threadIdx.x; i < p.nword; i += kHistBlock) {
-            const uint32_t v = w[i];
-#pragma unroll
-            for (int j = 0; j < SPW; ++j) {
-                const uint32_t code = (v >> (j * BPS)) & (NCODE - 1);
-                hist[(j * NCODE + code) * kHistBlock + threadIdx.x] += 1u;
-            }
-        }
-    }
-    // lanes of a warp that share a class add up by shuffles, then one global
-    // atomic per (class, slot, code) and warp
-    const int P = words_per_sample;               // power of two <= kHistBlock
-    const int cls = threadIdx.x % P;
+    // a thread's words are `stride` apart, so their class (index mod P) is
+    // fixed; more classes than threads: one pass per kHistBlock classes
+    const uint32_t P = (uint32_t)words_per_sample;      // a power of two
+    const uint32_t stride = P > kHistBlock ? P : kHistBlock;
+    const uint32_t npass = P > kHistBlock ? P / kHistBlock : 1u;
     const uint32_t lane = threadIdx.x & 31u;
     unsigned long long *out = p.counts
         + (size_t)(bin * p.nthread + t) * p.nelem * NCODE;
-    for (int j = 0; j < SPW; ++j) {
-        const int e = p.nelem >= SPW ? cls * SPW + j : j % p.nelem;
+    for (uint32_t m = 0; m < npass; ++m) {
+        const uint32_t start = threadIdx.x + kHistBlock * m;
+        // (only this thread touches column threadIdx.x: no barrier needed)
+        for (int c = 0; c < NCNT; ++c)
+            hist[c * kHistBlock + threadIdx.x] = 0u;
+        for (long long s = lo + blockIdx.x; s < hi; s += p.split) {
+            const long long off = p.unit_offset[s * p.nthread + t];
+            if (off < 0) continue;
+            const uint32_t *w =
+                reinterpret_cast<const uint32_t *>(p.src + off);
+            for (uint32_t i = start; i < p.nword; i += stride) {
+                const uint32_t v = w[i];
 #pragma unroll
-        for (int code = 0; code < NCODE; ++code) {
-            uint32_t v = hist[(j * NCODE + code) * kHistBlock + threadIdx.x];
-            for (int o = 16; o >= P && o >= 1; o >>= 1)
-                v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((P >= 32 || lane < (uint32_t)P) && v)
-                atomicAdd(out + (size_t)e * NCODE + code,
-                          (unsigned long long)v);
+                for (int j = 0; j < SPW; ++j) {
+                    const uint32_t code = (v >> (j * BPS)) & (NCODE - 1);
+                    // fire-and-forget shared atomic (the column is private:
+                    // atomicity is not needed, but a plain += makes every
+                    // sample wait for the previous one's load-add-store)
+                    atomicAdd(&hist[(j * NCODE + code) * kHistBlock
+                                    + threadIdx.x], 1u);
+                }
+            }
+        }
+        // lanes of a warp that share a class add up by shuffles, then one
+        // global atomic per (class, slot, code) and warp
+        const uint32_t cls = start % P;
+        for (int j = 0; j < SPW; ++j) {
+            const uint32_t e = p.nelem >= SPW ? cls * SPW + j : j % p.nelem;
+#pragma unroll
+            for (int code = 0; code < NCODE; ++code) {
+                uint32_t v =
+                    hist[(j * NCODE + code) * kHistBlock + threadIdx.x];
+                for (uint32_t o = 16; o >= P && o >= 1; o >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+                if ((P >= 32 || lane < P) && v)
+                    atomicAdd(out + (size_t)e * NCODE + code,
+                              (unsigned long long)v);
+            }
+        }
+    }
+}
+
+// 1 and 2 bits with more elements than the register path holds: vertical
+// counters.  The low bits of the 16 two-bit fields of a word (and the high
+// bits, and the fields with both set; 1 bit: the even and the odd bits) are
+// 16 one-bit indicators spaced two bits apart -- words of them can simply be
+// ADDED, three at a time, into 16 two-bit fields; those are spilled into
+// four-bit fields (every 3 words), those into bytes (every 15; the bytes
+// live in shared memory, registers are what limits this kernel), those into
+// the thread's private 32-bit counters in shared memory (every 255).  About
+// 17 integer operations per word whatever the number of channels, against a
+// shared-memory read-modify-write per SAMPLE in the histogram path (0.5
+// TB/s).  A thread's words are `stride` apart, so a field is one fixed
+// element; the codes are separated at the end as in the register path.
+#ifndef BB_VERT_WORDS
+#define BB_VERT_WORDS 15
+#endif
+#ifndef BB_VERT_MINB
+#define BB_VERT_MINB 5
+#endif
+constexpr int kVertBlock = 128;
+constexpr int kVertWords = BB_VERT_WORDS;   // loads in flight per thread (3 n)
+
+template <int BPS>
+__global__ void __launch_bounds__(kVertBlock, BB_VERT_MINB)
+k_state_counts_vert(const CountGeom p, int words_per_sample) {
+    constexpr int NI = BPS == 2 ? 3 : 2;    // indicator words per data word
+    constexpr int NCODE = 1 << BPS, SPW = 32 / BPS;
+    constexpr uint32_t M1 = 0x55555555u, M2 = 0x33333333u, M4 = 0x0f0f0f0fu;
+    constexpr uint32_t kWarps = kVertBlock / 32;
+    // private columns: 32-bit counters [NI * 16] and byte fields [NI * 4]
+    extern __shared__ uint32_t cnt[];       // [NI * 20][kVertBlock]
+    long long lo, hi, bin;
+    if (!count_range(p, lo, hi, bin)) return;
+    const int t = blockIdx.y;
+    // a warp takes whole units (frames are small: a CTA-wide stride would
+    // leave a thread a handful of words of each); a lane's words are
+    // `stride` apart, so their class (index mod P) is fixed; more classes
+    // than lanes: one pass per 32 classes
+    const uint32_t P = (uint32_t)words_per_sample;      // a power of two
+    const uint32_t stride = P > 32u ? P : 32u;
+    const uint32_t npass = P > 32u ? P / 32u : 1u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long *out = p.counts
+        + (size_t)(bin * p.nthread + t) * p.nelem * NCODE;
+    for (uint32_t m = 0; m < npass; ++m) {
+        const uint32_t start = lane + 32u * m;
+        for (int c = 0; c < NI * 16; ++c)
+            cnt[c * kVertBlock + threadIdx.x] = 0u;
+        uint32_t *a8 = cnt + NI * 16 * kVertBlock + threadIdx.x;   // [NI * 4]
+        for (int c = 0; c < NI * 4; ++c) a8[c * kVertBlock] = 0u;
+        uint32_t nblock = 0u, nw = 0u;
+        // field f of a2 -> field f / 2 of a4[f % 2]; field h of a4[q] ->
+        // byte h / 2 of a8[2 q + h % 2]: byte g of a8[2 q + r] counts field
+        // 4 g + 2 r + q.  (Rolled loops: this runs once per 255 words.)
+        auto flush = [&]() {
+#pragma unroll 1
+            for (int c = 0; c < NI * 4; ++c) {
+                const int n = c >> 2, k = c & 3;
+                const uint32_t b = a8[c * kVertBlock];
+                a8[c * kVertBlock] = 0u;
+                uint32_t *c0 = cnt + (n * 16 + 2 * (k & 1) + (k >> 1))
+                    * kVertBlock + threadIdx.x;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)               // field 4 g + ...
+                    c0[4 * g * kVertBlock] += (b >> (8 * g)) & 0xffu;
+            }
+            nblock = 0u;
+        };
+        for (long long s = lo + (long long)blockIdx.x * kWarps + warp; s < hi;
+             s += (long long)p.split * kWarps) {
+            const long long off = p.unit_offset[s * p.nthread + t];
+            if (off < 0 || start >= p.nword) continue;
+            const uint32_t *w =
+                reinterpret_cast<const uint32_t *>(p.src + off);
+            nw += (p.nword - start + stride - 1u) / stride;
+            for (uint32_t i0 = start; i0 < p.nword;
+                 i0 += kVertWords * stride) {
+                uint32_t v[kVertWords];
+#pragma unroll
+                for (int j = 0; j < kVertWords; ++j) {
+                    const uint32_t i = i0 + j * stride;
+                    v[j] = i < p.nword ? w[i] : 0u;   // 0: adds nothing
+                }
+                uint32_t a4[NI][2];
+#pragma unroll
+                for (int n = 0; n < NI; ++n) a4[n][0] = a4[n][1] = 0u;
+#pragma unroll
+                for (int g = 0; g < kVertWords / 3; ++g) {
+                    if (i0 + 3u * g * stride >= p.nword) break;
+                    // three words: indicators add up in two-bit fields
+                    const uint32_t v0 = v[3 * g], v1 = v[3 * g + 1],
+                                   v2 = v[3 * g + 2];
+                    const uint32_t x0 = v0 & M1, y0 = (v0 >> 1) & M1;
+                    const uint32_t x1 = v1 & M1, y1 = (v1 >> 1) & M1;
+                    const uint32_t x2 = v2 & M1, y2 = (v2 >> 1) & M1;
+                    uint32_t a2[NI];
+                    a2[0] = x0 + x1 + x2;
+                    a2[1] = y0 + y1 + y2;
+                    if (BPS == 2)
+                        a2[NI - 1] = (x0 & y0) + (x1 & y1) + (x2 & y2);
+#pragma unroll
+                    for (int n = 0; n < NI; ++n) {
+                        a4[n][0] += a2[n] & M2;
+                        a4[n][1] += (a2[n] >> 2) & M2;
+                    }
+                }
+                // at most 5 groups in the four-bit fields: into the bytes
+#pragma unroll
+                for (int n = 0; n < NI; ++n)
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        a8[(n * 4 + 2 * q) * kVertBlock] += a4[n][q] & M4;
+                        a8[(n * 4 + 2 * q + 1) * kVertBlock] +=
+                            (a4[n][q] >> 4) & M4;
+                    }
+                if (++nblock == 255u / kVertWords) flush();    // bytes full
+            }
+        }
+        flush();
+        // field f of indicator n -> sample slot; lanes that share a class
+        // add up by shuffles, then global atomics (one set per warp)
+        const uint32_t cls = start % P;
+        uint32_t all = nw;
+        for (uint32_t o = 16; o >= P && o >= 1; o >>= 1)
+            all += __shfl_xor_sync(0xffffffffu, all, o);
+        for (int f = 0; f < 16; ++f) {
+            uint32_t c[NI];
+#pragma unroll
+            for (int n = 0; n < NI; ++n) {
+                c[n] = cnt[(n * 16 + f) * kVertBlock + threadIdx.x];
+                for (uint32_t o = 16; o >= P && o >= 1; o >>= 1)
+                    c[n] += __shfl_xor_sync(0xffffffffu, c[n], o);
+            }
+            if (!(P >= 32u || lane < P)) continue;
+            if (BPS == 2) {
+                const uint32_t e = p.nelem >= SPW ? cls * SPW + f
+                    : f % p.nelem;
+                const uint32_t n3 = c[NI - 1], n1 = c[0] - n3, n2 = c[1] - n3;
+                const uint32_t nk[4] = {all - n1 - n2 - n3, n1, n2, n3};
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (nk[k])
+                        atomicAdd(out + (size_t)e * NCODE + k % NCODE,
+                                  (unsigned long long)nk[k]);
+            } else {
+#pragma unroll
+                for (int n = 0; n < 2; ++n) {
+                    const uint32_t slot = 2u * f + n;
+                    const uint32_t e = p.nelem >= SPW ? cls * SPW + slot
+                        : slot % p.nelem;
+                    if (all - c[n])
+                        atomicAdd(out + (size_t)e * NCODE,
+                                  (unsigned long long)(all - c[n]));
+                    if (c[n])
+                        atomicAdd(out + (size_t)e * NCODE + 1 % NCODE,
+                                  (unsigned long long)c[n]);
+                }
+            }
         }
     }
 }
@@ -425,10 +599,13 @@ static int launch_hist(const CountGeom &g, dim3 grid, int P, cudaStream_t s) {
 
 using namespace bb;
 
-// CTAs per SM a launch aims at (development tunable BB_TUNE_COUNT_DEPTH).
-static int count_depth() {
-    const char *e = getenv("BB_TUNE_COUNT_DEPTH");
-    return (e && *e && atoi(e) > 0) ? atoi(e) : 24;     // swept: tools/sweep_counts.py
+// CTAs per SM a launch aims at (development tunables BB_TUNE_COUNT_DEPTH,
+// BB_TUNE_VERT_DEPTH; defaults swept with tools/sweep_counts.py).  The
+// vertical-counter kernel has a fixed cost per CTA (zeroing and reading out 60
+// shared-memory words per thread); 16 measured best (4 -> 16: +15 %).
+static int count_depth(bool vert = false) {
+    const char *e = getenv(vert ? "BB_TUNE_VERT_DEPTH" : "BB_TUNE_COUNT_DEPTH");
+    return (e && *e && atoi(e) > 0) ? atoi(e) : vert ? 16 : 24;
 }
 
 extern "C" int bb_state_counts(
@@ -460,9 +637,6 @@ extern "C" int bb_state_counts(
     const int spw = 32 / bps, ncode = 1 << bps;
     const bool reg = bps <= 2 && nelem <= spw && nelem * ncode <= 16;
     const int P = nelem > spw ? nelem / spw : 1;
-    if (!reg && P > kHistBlock)
-        return set_error(BB_ERR_UNSUPPORTED,
-                         "too many elements per sample for state counts");
     CountGeom g;
     g.src = (const uint8_t *)src;
     g.unit_offset = (const long long *)unit_offset;
@@ -477,7 +651,7 @@ extern "C" int bb_state_counts(
     // per set of a bin, and few enough words each that 32-bit counters hold
     const int64_t nb = b1 - b0 + 1;
     const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
-    const int64_t want = (int64_t)count_depth() * sm_count();
+    const int64_t want = (int64_t)count_depth(!reg && bps <= 2) * sm_count();
     int64_t split = (want + nb * nthread - 1) / (nb * nthread);
     const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
         / (1ll << 26);
@@ -489,6 +663,9 @@ extern "C" int bb_state_counts(
     if (g.nseg < 1u) g.nseg = 1u;
     if (reg) {
         const int64_t full = per_bin * g.nseg / (kCountBlock / 32);
+        if (split > full && full >= need) split = full;
+    } else if (bps <= 2) {                 // vertical counters: a unit per warp
+        const int64_t full = per_bin / (kVertBlock / 32);
         if (split > full && full >= need) split = full;
     }
     if (split < 1) split = 1;
@@ -511,9 +688,17 @@ extern "C" int bb_state_counts(
                 else launch_reg<2, 4>(g, grid, s);
             }
         } else {
-            int rc = bps == 1 ? launch_hist<1>(g, grid, P, s)
-                : bps == 2 ? launch_hist<2>(g, grid, P, s)
-                : launch_hist<4>(g, grid, P, s);
+            int rc = BB_OK;
+            if (bps == 4) {
+                rc = launch_hist<4>(g, grid, P, s);
+            } else {
+                const size_t smem = (size_t)(bps == 2 ? 3 : 2) * 20
+                    * kVertBlock * sizeof(uint32_t);
+                if (bps == 2)
+                    k_state_counts_vert<2><<<grid, kVertBlock, smem, s>>>(g, P);
+                else
+                    k_state_counts_vert<1><<<grid, kVertBlock, smem, s>>>(g, P);
+            }
             if (rc != BB_OK) return rc;
         }
         BB_CHECK_LAUNCH("bb_state_counts");

@@ -12,8 +12,10 @@ from baseband_b200 import kernels
 pytestmark = pytest.mark.gpu
 DEV = 'cuda:0'
 
+# up to more word classes than a CTA has threads (several passes): 4 bit x
+# 2048 elements (1024 complex channels) is 256 words per sample
 CASES = [(bps, nelem) for bps in (1, 2, 4)
-         for nelem in (1, 2, 4, 8, 16, 32, 64, 256)]
+         for nelem in (1, 2, 4, 8, 16, 32, 64, 256, 2048, 8192)]
 
 
 @pytest.mark.parametrize('bps,nelem', CASES)
@@ -23,6 +25,9 @@ def test_state_counts_fuzz(bps, nelem):
         nthread = int(rng.choice([1, 2, 3, 16]))
         words_per_sample = max(1, nelem * bps // 32)
         nword = words_per_sample * int(rng.integers(1, 700))
+        if trial == 3 and words_per_sample <= 4:
+            # > 255 words per thread: the vertical counters flush in between
+            nword = words_per_sample * int(rng.integers(40000, 50000))
         payload = nword * 4
         nset = int(rng.integers(1, 9))
         hdr = int(rng.choice([0, 4, 16, 32]))        # 4: unaligned for uint4

@@ -70,3 +70,33 @@ for depth, mu in ((24, 2), (24, 4), (24, 8), (8, 8), (48, 4), (48, 8)):
     ts = sorted(ts[2:])
     print('int8 moments depth %3d U %d: %.1f GB/s median, %.1f best' % (
         depth, mu, raw.numel() / ts[len(ts) // 2] / 1e6, raw.numel() / ts[0] / 1e6))
+
+# the other paths: vertical counters (1 / 2 bit, many elements), shared-memory
+# histogram (4 bit)
+del raw, uo
+os.environ['BB_TUNE_COUNT_DEPTH'] = '24'
+payload, frame = 8192, 8224
+for bps, nthread, nelem in ((4, 4, 1), (4, 1, 1024), (2, 1, 64), (2, 4, 8),
+                            (2, 1, 16), (1, 1, 64), (1, 8, 1)):
+    nset = int(gib * 2**30) // frame // nthread
+    raw = torch.randint(0, 256, (nset * nthread * frame,), dtype=torch.uint8,
+                        device=DEV)
+    uo = torch.arange(nset * nthread, dtype=torch.int64, device=DEV) * frame + 32
+    acc = kernels.zeros((-(-nset // 500), nthread, nelem, 1 << bps),
+                        torch.int64, torch.device(DEV))
+    for vd in ((4, 7, 8, 12, 16) if bps < 4 and nelem > 8 // bps else (7,)):
+        os.environ['BB_TUNE_VERT_DEPTH'] = str(vd)
+        ts = []
+        for i in range(8):
+            a, b = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+            a.record()
+            kernels.state_counts(raw, uo, nset, nthread, payload, bps, nelem,
+                                 acc, sets_per_bin=500)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[2:])
+        print('counts %d bit, %d threads x %d elements, depth %d: %.1f GB/s '
+              'median' % (bps, nthread, nelem, vd,
+                          nset * nthread * payload / ts[len(ts) // 2] / 1e6))
+    del raw, uo, acc
