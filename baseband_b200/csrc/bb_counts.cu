@@ -435,6 +435,126 @@ k_state_counts_vert(const CountGeom p, int words_per_sample) {
     }
 }
 
+// 4 bits: the same idea with one indicator per code.  The four bit planes of
+// the eight nibbles (and their complements) give the eight minterms of the
+// low three bits with one LOP3 each and from those the 15 codes above zero
+// with one more; an indicator is 8 one-bit flags four bits apart, so 15
+// words of them add up in nibble fields, which are spilled into byte fields
+// (shared memory) and those, every 255 words, into the private counters.
+// ~55 integer operations per word against eight shared-memory atomics.
+constexpr int kVert4Block = 128;
+
+__global__ void __launch_bounds__(kVert4Block, 5)
+k_state_counts_vert4(const CountGeom p, int words_per_sample) {
+    constexpr int NI = 15, NCODE = 16, SPW = 8, NW = 15;
+    constexpr uint32_t M = 0x11111111u, M4 = 0x0f0f0f0fu;
+    constexpr uint32_t kWarps = kVert4Block / 32;
+    // private columns: pairs of 16-bit counters [NI * 4] (the launcher keeps
+    // a lane below 2^16 words: shared memory is what limits the number of
+    // resident warps here), byte fields [NI * 2]
+    extern __shared__ uint32_t cnt[];       // [NI * 6][kVert4Block]
+    long long lo, hi, bin;
+    if (!count_range(p, lo, hi, bin)) return;
+    const int t = blockIdx.y;
+    const uint32_t P = (uint32_t)words_per_sample;      // a power of two
+    const uint32_t stride = P > 32u ? P : 32u;
+    const uint32_t npass = P > 32u ? P / 32u : 1u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned long long *out = p.counts
+        + (size_t)(bin * p.nthread + t) * p.nelem * NCODE;
+    uint32_t *a8 = cnt + NI * 4 * kVert4Block + threadIdx.x;       // [NI * 2]
+    for (uint32_t m = 0; m < npass; ++m) {
+        const uint32_t start = lane + 32u * m;
+        for (int c = 0; c < NI * 6; ++c)
+            cnt[c * kVert4Block + threadIdx.x] = 0u;
+        uint32_t nblock = 0u, nw = 0u;
+        // byte g of a8[2 c + r] counts nibble field 2 g + r of indicator c;
+        // cnt[4 c + g] holds fields 2 g (low half) and 2 g + 1 (high half)
+        auto flush = [&]() {
+#pragma unroll 1
+            for (int c = 0; c < NI; ++c) {
+                const uint32_t b0 = a8[(2 * c) * kVert4Block];
+                const uint32_t b1 = a8[(2 * c + 1) * kVert4Block];
+                a8[(2 * c) * kVert4Block] = 0u;
+                a8[(2 * c + 1) * kVert4Block] = 0u;
+                uint32_t *c0 = cnt + 4 * c * kVert4Block + threadIdx.x;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    c0[g * kVert4Block] += ((b0 >> (8 * g)) & 0xffu)
+                        | (((b1 >> (8 * g)) & 0xffu) << 16);
+            }
+            nblock = 0u;
+        };
+        for (long long s = lo + (long long)blockIdx.x * kWarps + warp; s < hi;
+             s += (long long)p.split * kWarps) {
+            const long long off = p.unit_offset[s * p.nthread + t];
+            if (off < 0 || start >= p.nword) continue;
+            const uint32_t *w =
+                reinterpret_cast<const uint32_t *>(p.src + off);
+            nw += (p.nword - start + stride - 1u) / stride;
+            for (uint32_t i0 = start; i0 < p.nword; i0 += NW * stride) {
+                uint32_t v[NW];
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    const uint32_t i = i0 + j * stride;
+                    // past the end: code 0 everywhere, which is not counted
+                    v[j] = i < p.nword ? w[i] : 0u;
+                }
+                uint32_t a4[NI];
+#pragma unroll
+                for (int c = 0; c < NI; ++c) a4[c] = 0u;
+#pragma unroll
+                for (int j = 0; j < NW; ++j) {
+                    if (i0 + (uint32_t)j * stride >= p.nword) break;
+                    const uint32_t x = v[j];
+                    const uint32_t p0 = x & M, p1 = (x >> 1) & M;
+                    const uint32_t p2 = (x >> 2) & M, p3 = (x >> 3) & M;
+                    const uint32_t n0 = p0 ^ M, n1 = p1 ^ M, n2 = p2 ^ M,
+                                   n3 = p3 ^ M;
+                    uint32_t mt[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        mt[k] = ((k & 1) ? p0 : n0) & ((k & 2) ? p1 : n1)
+                            & ((k & 4) ? p2 : n2);
+#pragma unroll
+                    for (int c = 1; c < 16; ++c)
+                        a4[c - 1] += mt[c & 7] & ((c & 8) ? p3 : n3);
+                }
+                // at most 15 in the nibble fields: into the bytes
+#pragma unroll
+                for (int c = 0; c < NI; ++c) {
+                    a8[(2 * c) * kVert4Block] += a4[c] & M4;
+                    a8[(2 * c + 1) * kVert4Block] += (a4[c] >> 4) & M4;
+                }
+                if (++nblock == 255u / NW) flush();           // bytes full
+            }
+        }
+        flush();
+        // nibble field h of indicator c - 1 -> (sample slot h, code c); lanes
+        // that share a class add up by shuffles, then global atomics
+        const uint32_t cls = start % P;
+        uint32_t all = nw;
+        for (uint32_t o = 16; o >= P && o >= 1; o >>= 1)
+            all += __shfl_xor_sync(0xffffffffu, all, o);
+        for (int h = 0; h < SPW; ++h) {
+            const uint32_t e = p.nelem >= SPW ? cls * SPW + h : h % p.nelem;
+            uint32_t rest = all;
+            for (int c = 1; c < NCODE; ++c) {
+                uint32_t n = (cnt[((c - 1) * 4 + h / 2) * kVert4Block
+                                  + threadIdx.x] >> (16 * (h & 1))) & 0xffffu;
+                for (uint32_t o = 16; o >= P && o >= 1; o >>= 1)
+                    n += __shfl_xor_sync(0xffffffffu, n, o);
+                rest -= n;
+                if ((P >= 32u || lane < P) && n)
+                    atomicAdd(out + (size_t)e * NCODE + c,
+                              (unsigned long long)n);
+            }
+            if ((P >= 32u || lane < P) && rest)
+                atomicAdd(out + (size_t)e * NCODE, (unsigned long long)rest);
+        }
+    }
+}
+
 // 8-bit two's-complement samples (GUPPI, DADA): count, sum and sum of squares
 // per element instead of a 256-bin histogram -- what power, mean and variance
 // need, still exact integers.  A word holds four samples: each byte is
@@ -602,10 +722,11 @@ using namespace bb;
 // CTAs per SM a launch aims at (development tunables BB_TUNE_COUNT_DEPTH,
 // BB_TUNE_VERT_DEPTH; defaults swept with tools/sweep_counts.py).  The
 // vertical-counter kernel has a fixed cost per CTA (zeroing and reading out 60
-// shared-memory words per thread); 16 measured best (4 -> 16: +15 %).
-static int count_depth(bool vert = false) {
+// shared-memory words per thread, 90 at 4 bit, and its read-out is ~50
+// atomics per thread, 120 at 4 bit): 16 measured best at 1/2 bit, 8 at 4 bit.
+static int count_depth(bool vert = false, int bps = 2) {
     const char *e = getenv(vert ? "BB_TUNE_VERT_DEPTH" : "BB_TUNE_COUNT_DEPTH");
-    return (e && *e && atoi(e) > 0) ? atoi(e) : vert ? 16 : 24;
+    return (e && *e && atoi(e) > 0) ? atoi(e) : !vert ? 24 : bps == 4 ? 8 : 16;
 }
 
 extern "C" int bb_state_counts(
@@ -651,10 +772,11 @@ extern "C" int bb_state_counts(
     // per set of a bin, and few enough words each that 32-bit counters hold
     const int64_t nb = b1 - b0 + 1;
     const int64_t per_bin = sets_per_bin < nset ? sets_per_bin : nset;
-    const int64_t want = (int64_t)count_depth(!reg && bps <= 2) * sm_count();
+    const int64_t want = (int64_t)count_depth(!reg, bps) * sm_count();
     int64_t split = (want + nb * nthread - 1) / (nb * nthread);
-    const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
+    int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
         / (1ll << 26);
+    bool hist4 = false;
     if (split < need) split = need;
     if (split > per_bin) split = per_bin;
     // register path: a warp takes a segment of a unit, so a CTA wants at
@@ -664,8 +786,22 @@ extern "C" int bb_state_counts(
     if (reg) {
         const int64_t full = per_bin * g.nseg / (kCountBlock / 32);
         if (split > full && full >= need) split = full;
-    } else if (bps <= 2) {                 // vertical counters: a unit per warp
-        const int64_t full = per_bin / (kVertBlock / 32);
+    } else {                               // vertical counters: a unit per warp
+        if (bps == 4) {
+            // 16-bit counters: a lane must stay below 2^16 words
+            const int64_t lane_words = ((int64_t)g.nword + 31) / 32;
+            const int64_t units = 60000 / lane_words;     // per warp
+            if (units < 1) {
+                hist4 = true;              // huge units: histogram kernel
+            } else {
+                const int64_t need4 = (per_bin + units * (kVert4Block / 32) - 1)
+                    / (units * (kVert4Block / 32));
+                if (need4 > 65535) hist4 = true;
+                else if (need4 > need) need = need4;
+                if (split < need) split = need;
+            }
+        }
+        const int64_t full = per_bin / ((bps == 4 ? kVert4Block : kVertBlock) / 32);
         if (split > full && full >= need) split = full;
     }
     if (split < 1) split = 1;
@@ -689,8 +825,21 @@ extern "C" int bb_state_counts(
             }
         } else {
             int rc = BB_OK;
-            if (bps == 4) {
-                rc = launch_hist<4>(g, grid, P, s);
+            if (bps == 4 && (hist4 || getenv("BB_TUNE_COUNT_HIST4"))) {
+                rc = launch_hist<4>(g, grid, P, s);       // the first version
+            } else if (bps == 4) {
+                const size_t smem = (size_t)15 * 6 * kVert4Block
+                    * sizeof(uint32_t);
+                static bool attr_set = false;
+                if (!attr_set) {
+                    rc = check_cuda(cudaFuncSetAttribute(
+                        k_state_counts_vert4,
+                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                        (int)smem), "bb_state_counts (smem)");
+                    attr_set = rc == BB_OK;
+                }
+                if (rc == BB_OK)
+                    k_state_counts_vert4<<<grid, kVert4Block, smem, s>>>(g, P);
             } else {
                 const size_t smem = (size_t)(bps == 2 ? 3 : 2) * 20
                     * kVertBlock * sizeof(uint32_t);

@@ -384,3 +384,29 @@ def test_int8_moments_one_huge_unit():
     got1 = torch.zeros((1, 1, 1, 3), dtype=torch.int64, device=DEV)
     kernels.int8_moments(raw, uo, 1, 1, n, 1, got1)
     assert np.array_equal(got1.cpu().numpy()[0, 0, 0], want.sum(axis=0))
+
+
+@pytest.mark.parametrize('payload,nset', [(128 << 10, 512), (8 << 20, 3)])
+def test_state_counts_4bit_counter_limits(payload, nset):
+    """4-bit state counts keep pairs of 16-bit counters per lane: one bin of
+    512 units of 128 KiB makes the launcher split the bin so that no lane
+    passes 2^16 words; 8 MiB units are beyond what one lane may take and go
+    to the histogram kernel.  All nibbles are one element here, so numpy's
+    bincount is the answer."""
+    g = torch.Generator(device=DEV).manual_seed(payload % 1000 + nset)
+    raw = torch.randint(0, 256, (nset * payload,), dtype=torch.uint8,
+                        device=DEV, generator=g)
+    uo = torch.arange(nset, dtype=torch.int64, device=DEV) * payload
+    got = torch.zeros((1, 1, 1, 16), dtype=torch.int64, device=DEV)
+    kernels.state_counts(raw, uo, nset, 1, payload, 4, 1, got)
+    host = raw.cpu().numpy()
+    want = np.bincount(host & 15, minlength=16) \
+        + np.bincount(host >> 4, minlength=16)
+    assert np.array_equal(got.cpu().numpy()[0, 0, 0], want)
+    # two elements (a complex channel): low nibbles are re, high nibbles im
+    got2 = torch.zeros((1, 1, 2, 16), dtype=torch.int64, device=DEV)
+    kernels.state_counts(raw, uo, nset, 1, payload, 4, 2, got2)
+    assert np.array_equal(got2.cpu().numpy()[0, 0, 0],
+                          np.bincount(host & 15, minlength=16))
+    assert np.array_equal(got2.cpu().numpy()[0, 0, 1],
+                          np.bincount(host >> 4, minlength=16))

@@ -84,7 +84,7 @@ for bps, nthread, nelem in ((4, 4, 1), (4, 1, 1024), (2, 1, 64), (2, 4, 8),
     uo = torch.arange(nset * nthread, dtype=torch.int64, device=DEV) * frame + 32
     acc = kernels.zeros((-(-nset // 500), nthread, nelem, 1 << bps),
                         torch.int64, torch.device(DEV))
-    for vd in ((4, 7, 8, 12, 16) if bps < 4 and nelem > 8 // bps else (7,)):
+    for vd in ((8, 16, 24, 32, 48) if bps == 4 or nelem > 8 // bps else (16,)):
         os.environ['BB_TUNE_VERT_DEPTH'] = str(vd)
         ts = []
         for i in range(8):
