@@ -3,7 +3,9 @@ staging, by page-locking its mapping (cudaHostRegister, read-only) piece by
 piece?  Prints the rate of registering / unregistering pieces on 1..T
 threads and of the H2D copy out of the registered mapping.
 
-    python tools/probe_register.py [MiB] [piece MiB]
+    python tools/probe_register.py [MiB] [piece MiB] [rw]
+
+(rw: map the file shared and writable instead of read-only)
 """
 import ctypes
 import glob
@@ -39,8 +41,10 @@ rt.cudaMemcpyAsync.argtypes = [ctypes.c_void_p, ctypes.c_void_p,
                                ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
 READ_ONLY = 0x08
 
-fd = os.open(path, os.O_RDONLY)
-mm = mmap.mmap(fd, n, access=mmap.ACCESS_READ)
+writable = len(sys.argv) > 3 and sys.argv[3] == 'rw'
+fd = os.open(path, os.O_RDWR if writable else os.O_RDONLY)
+mm = mmap.mmap(fd, n, access=mmap.ACCESS_WRITE if writable
+               else mmap.ACCESS_READ)
 base = ctypes.addressof(ctypes.c_char.from_buffer_copy(b'x'))  # placeholder
 arr = np.frombuffer(mm, np.uint8)
 base = arr.ctypes.data
