@@ -39,6 +39,8 @@ __all__ = ['StreamBase', 'StreamReaderBase', 'StreamWriterBase',
 # out of the page cache and the DMA read: file ingest peaks at 8-16 MiB
 # (profiles/r2_file_chunks.txt: 38-43 GB/s, against 30 at 64 MiB).
 DEFAULT_CHUNK_NBYTES = 16 << 20
+# stages a device-output read rotates over (see `_pipeline`; 2 or 3)
+DEVICE_READ_STAGES = 3
 
 # File -> pinned staging buffer: one readinto() copies out of the page cache on
 # a single core (a few GB/s), far below the PCIe link.  Large chunks of plain
@@ -50,7 +52,9 @@ DEFAULT_CHUNK_NBYTES = 16 << 20
 # library's pool of native threads (bb_host_copy; bb_host_pread where mmap is
 # refused): a Python thread pool costs ~50 us per slice, as much as the copy
 # of a small chunk.
-PARALLEL_READ_MIN_NBYTES = 8 << 20
+# (from 2 MiB on: a `chunk_nbytes` of 8 MiB is a little less than 8 MiB of whole
+# frames, and fell back to the single readinto -- 7 instead of 40 GB/s)
+PARALLEL_READ_MIN_NBYTES = 2 << 20
 PARALLEL_READ_MMAP = True
 # read(out=<pageable numpy array>) at least this large: staged D2H (see
 # StreamReaderBase._read_to_host).
@@ -921,8 +925,15 @@ class StreamReaderBase(StreamBase):
         return new
 
     def _pipeline(self, dev):
+        """The pipeline stages and streams.  Host-output reads and the index
+        build alternate between the first two stages; reads that leave their
+        result on the device (and the packed consumers) rotate over all
+        three, so that starting the read-ahead of chunk k + 1 never has to
+        wait for the upload of chunk k - 1 to release its pinned buffer --
+        with two, the next upload was only queued after that wait, and the
+        copy engine idled for a host wake-up between chunks."""
         if self._stages is None:
-            self._stages = [_Stage(), _Stage()]
+            self._stages = [_Stage() for _ in range(3)]
             self._streams = _device.Streams(dev)
         return self._stages, self._streams
 
@@ -951,7 +962,7 @@ class StreamReaderBase(StreamBase):
         def begin(k):
             c0 = starts[k]
             nf = min(per, frame0 + nframe - c0)
-            st = stages[k % 2]
+            st = stages[k % DEVICE_READ_STAGES]
             if st.done is not None:
                 st.done.synchronize()
             pin, _ = st.buffers(self._chunk_nbytes_of(c0, nf, 0, nf * spf),
@@ -961,7 +972,7 @@ class StreamReaderBase(StreamBase):
         ahead = begin(0) if starts else None
         for k, c0 in enumerate(starts):
             nf = min(per, frame0 + nframe - c0)
-            st = stages[k % 2]
+            st = stages[k % DEVICE_READ_STAGES]
             raw = st.raw[:self._chunk_nbytes_of(c0, nf, 0, nf * spf)]
             pin = ahead.wait()
             ahead = begin(k + 1) if k + 1 < len(starts) else None
@@ -999,7 +1010,7 @@ class StreamReaderBase(StreamBase):
         def begin(k):
             """Start reading chunk k into its stage's pinned buffer."""
             f0, nf, s0, ns, _ = chunks[k]
-            st = stages[k % 2]
+            st = stages[k % DEVICE_READ_STAGES]
             if st.done is not None:
                 st.done.synchronize()        # pinned buffer free again
             pin, _ = st.buffers(self._chunk_nbytes_of(f0, nf, s0, ns), 0,
@@ -1008,7 +1019,7 @@ class StreamReaderBase(StreamBase):
 
         ahead = begin(0) if chunks else None
         for k, (f0, nf, s0, ns, row) in enumerate(chunks):
-            st = stages[k % 2]
+            st = stages[k % DEVICE_READ_STAGES]
             raw = st.raw[:self._chunk_nbytes_of(f0, nf, s0, ns)]
             pin = ahead.wait()
             # the next chunk leaves the page cache while this one's copy and

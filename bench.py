@@ -715,7 +715,7 @@ def measure_file_ingest(args, dev, rank, world):
     try:
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
         best = None
-        for rep in range(4):
+        for rep in range(9):
             fh.seek(0)
             torch.cuda.synchronize(dev)
             if world > 1:
@@ -739,7 +739,7 @@ def measure_file_ingest(args, dev, rank, world):
             'file_bytes': int(nset * SET_BYTES),
             'api': "vdif.open(path, 'rs', device=...).read() of a file in "
                    "the page cache (" + folder + ")",
-            'how': 'best of 3 passes after a warm-up, all ranks at once, '
+            'how': 'best of 8 passes after a warm-up, all ranks at once, '
                    'slowest rank; bb_host_copy out of an mmap of the file '
                    '-> pinned staging -> H2D -> scan + decode'}
 
