@@ -104,6 +104,9 @@ SIGNATURES = {
     'bb_state_counts': (c_int, [
         _pv, _pi64, c_int64, c_int32, c_int64, c_int32, c_int32, c_int64,
         c_int64, _pv, c_int64, c_void_p]),
+    'bb_mark4_state_counts': (c_int, [
+        _pv, _pi64, c_int64, c_int32, c_int32, c_int32, c_int64, c_int64,
+        _pv, c_int64, c_void_p]),
     'bb_int8_moments': (c_int, [
         _pv, _pi64, c_int64, c_int32, c_int64, c_int32, c_int64, c_int64,
         _pv, c_int64, c_void_p]),

@@ -12,6 +12,7 @@
 // Integer counts are order-independent: the result is bit-exact whatever the
 // launch shape.  HBM-read bound: one pass over the packed bytes.
 #include "bb_runtime.cuh"
+#include "bb_mark4_plan.h"
 
 namespace bb {
 
@@ -26,6 +27,9 @@ struct CountGeom {
     int nthread, nelem, split;
     uint32_t nword;                   // 32-bit words per unit payload
     uint32_t nseg;                    // register path: work items per unit
+    // Mark 4 (vertical counters with a word transform): channel of every
+    // two-bit field of a transformed word, per word class
+    uint8_t field_elem[2][16];
 };
 
 __device__ __forceinline__ bool count_range(const CountGeom &p, long long &lo,
@@ -286,6 +290,35 @@ k_state_counts_hist(const CountGeom p, int words_per_sample) {
 // shared-memory read-modify-write per SAMPLE in the histogram path (0.5
 // TB/s).  A thread's words are `stride` apart, so a field is one fixed
 // element; the codes are separated at the end as in the register path.
+// Mark 4 track words -> words of sixteen two-bit codes (sign | magnitude <<
+// 1), so that the vertical counters apply unchanged.  Standard fan-out 4
+// layouts (32 / 64 tracks): the reference's reorder32 bit swap
+// (baseband/mark4/payload.py:48-69) does exactly that.  The other layouts
+// keep, per byte, four sign bits below four magnitude bits
+// (mark4/payload.py:122-288): both nibbles are spread to every other bit and
+// interleaved; Fortaleza first swaps track bits 4 <-> 8 and 6 <-> 10.
+enum { XF_NONE = 0, XF_M4_REORDER = 1, XF_M4_NIBBLES = 2, XF_M4_FT = 3 };
+
+__host__ __device__ __forceinline__ uint32_t m4_spread4(uint32_t x) {
+    x = (x | (x << 2)) & 0x33333333u;     // nibble bits 0..3 -> 0, 1, 4, 5
+    return (x | (x << 1)) & 0x55555555u;  //                   -> 0, 2, 4, 6
+}
+
+template <int XF>
+__host__ __device__ __forceinline__ uint32_t m4_to_codes(uint32_t w) {
+    if (XF == XF_M4_REORDER)
+        return (w & 0xAA55AA55u) | ((w & 0x55005500u) >> 7)
+            | ((w & 0x00AA00AAu) << 7);
+    if (XF == XF_M4_FT) {
+        const uint32_t t = ((w >> 4) ^ w) & 0x00000050u;
+        w ^= t | (t << 4);
+    }
+    if (XF == XF_M4_NIBBLES || XF == XF_M4_FT)
+        return m4_spread4(w & 0x0f0f0f0fu)
+            | (m4_spread4((w >> 4) & 0x0f0f0f0fu) << 1);
+    return w;
+}
+
 #ifndef BB_VERT_WORDS
 #define BB_VERT_WORDS 15
 #endif
@@ -295,7 +328,7 @@ k_state_counts_hist(const CountGeom p, int words_per_sample) {
 constexpr int kVertBlock = 128;
 constexpr int kVertWords = BB_VERT_WORDS;   // loads in flight per thread (3 n)
 
-template <int BPS>
+template <int BPS, int XF = XF_NONE>
 __global__ void __launch_bounds__(kVertBlock, BB_VERT_MINB)
 k_state_counts_vert(const CountGeom p, int words_per_sample) {
     constexpr int NI = BPS == 2 ? 3 : 2;    // indicator words per data word
@@ -356,6 +389,11 @@ k_state_counts_vert(const CountGeom p, int words_per_sample) {
                     const uint32_t i = i0 + j * stride;
                     v[j] = i < p.nword ? w[i] : 0u;   // 0: adds nothing
                 }
+                if (XF != XF_NONE) {
+#pragma unroll
+                    for (int j = 0; j < kVertWords; ++j)
+                        v[j] = m4_to_codes<XF>(v[j]);
+                }
                 uint32_t a4[NI][2];
 #pragma unroll
                 for (int n = 0; n < NI; ++n) a4[n][0] = a4[n][1] = 0u;
@@ -408,10 +446,14 @@ k_state_counts_vert(const CountGeom p, int words_per_sample) {
             }
             if (!(P >= 32u || lane < P)) continue;
             if (BPS == 2) {
-                const uint32_t e = p.nelem >= SPW ? cls * SPW + f
-                    : f % p.nelem;
+                const uint32_t e = XF != XF_NONE ? p.field_elem[cls & 1u][f]
+                    : p.nelem >= SPW ? cls * SPW + f : f % p.nelem;
                 const uint32_t n3 = c[NI - 1], n1 = c[0] - n3, n2 = c[1] - n3;
-                const uint32_t nk[4] = {all - n1 - n2 - n3, n1, n2, n3};
+                // Mark 4 counts are indexed 2 * sign + magnitude, as its level
+                // table is: fields are sign | magnitude << 1, so 1 <-> 2
+                const uint32_t nk[4] = {all - n1 - n2 - n3,
+                                        XF != XF_NONE ? n2 : n1,
+                                        XF != XF_NONE ? n1 : n2, n3};
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (nk[k])
@@ -911,6 +953,121 @@ extern "C" int bb_int8_moments(
         else
             k_int8_moments<4><<<grid, kCountBlock, 0, as_stream(stream)>>>(g, P);
         BB_CHECK_LAUNCH("bb_int8_moments");
+    }
+    return BB_OK;
+}
+
+
+// Mark 4: the (sign, magnitude) states of every channel straight from the
+// track words.  Frames are the units (`unit_offset[i]` = offset of frame i's
+// payload, i.e. past the 160 header steps, < 0: invalid frame; as written by
+// bb_mark4_scan); counts[bin][chan][2 * sign + magnitude].
+template <int XF>
+static bool m4_field_table(int nchan, int fanout, int ft, int wordbytes,
+                           uint8_t (&table)[2][16], std::string &err) {
+    uint16_t pos[32];
+    int ntrack = 0;
+    if (!m4_build_pos(nchan, fanout, ft, pos, ntrack, err)) return false;
+    int chan_of[64], mag_of[64];
+    for (int b = 0; b < 64; ++b) chan_of[b] = mag_of[b] = -1;
+    for (int i = 0; i < nchan * fanout; ++i) {
+        chan_of[pos[i] & 0xff] = i % nchan;
+        mag_of[pos[i] & 0xff] = 0;
+        chan_of[pos[i] >> 8] = i % nchan;
+        mag_of[pos[i] >> 8] = 1;
+    }
+    for (int cls = 0; cls < 2; ++cls)
+        for (int f = 0; f < 16; ++f) table[cls][f] = 0xff;
+    for (int cls = 0; cls < (wordbytes == 8 ? 2 : 1); ++cls)
+        for (int b32 = 0; b32 < 32; ++b32) {
+            // a 32-bit load holds half an 8-byte word, one 4-byte word or two
+            // 2-byte words of the track stream
+            const int b = wordbytes == 8 ? 32 * cls + b32 : b32 % ntrack;
+            const uint32_t codes = m4_to_codes<XF>(1u << b32);
+            int q = 0;
+            while (q < 32 && !((codes >> q) & 1u)) ++q;
+            if (q == 32 || (codes & (codes - 1u)) || chan_of[b] < 0
+                || (q & 1) != mag_of[b]) {
+                err = "internal error: Mark 4 code transform";
+                return false;
+            }
+            const int f = q >> 1;
+            if (table[cls][f] != 0xff && table[cls][f] != chan_of[b]) {
+                err = "internal error: Mark 4 field table";
+                return false;
+            }
+            table[cls][f] = (uint8_t)chan_of[b];
+        }
+    return true;
+}
+
+extern "C" int bb_mark4_state_counts(
+    const void *src, const int64_t *unit_offset, int64_t nframe, int32_t nchan,
+    int32_t fanout, int32_t ft, int64_t set_origin, int64_t sets_per_bin,
+    uint64_t *counts, int64_t nbin, void *stream) {
+    if (!src || !unit_offset || !counts)
+        return set_error(BB_ERR_ARGUMENT, "null pointer");
+    if (nframe < 0 || set_origin < 0 || sets_per_bin < 1 || nbin < 1)
+        return set_error(BB_ERR_ARGUMENT, "bad geometry");
+    if (!aligned(src, 4))
+        return set_error(BB_ERR_ALIGNMENT, "src must be 4-byte aligned");
+    CountGeom g;
+    std::string err;
+    const int ntrack = nchan * 2 * fanout, wordbytes = ntrack / 8;
+    const int xf = ft ? XF_M4_FT : (fanout == 4 && nchan >= 4) ? XF_M4_REORDER
+        : XF_M4_NIBBLES;
+    const bool ok = xf == XF_M4_FT
+        ? m4_field_table<XF_M4_FT>(nchan, fanout, ft, wordbytes, g.field_elem,
+                                   err)
+        : xf == XF_M4_REORDER
+        ? m4_field_table<XF_M4_REORDER>(nchan, fanout, ft, wordbytes,
+                                        g.field_elem, err)
+        : m4_field_table<XF_M4_NIBBLES>(nchan, fanout, ft, wordbytes,
+                                        g.field_elem, err);
+    if (!ok) return set_error(BB_ERR_UNSUPPORTED, "%s", err.c_str());
+    if (nframe == 0) return BB_OK;
+    const int64_t b0 = set_origin / sets_per_bin;
+    const int64_t b1 = (set_origin + nframe - 1) / sets_per_bin;
+    if (b1 >= nbin)
+        return set_error(BB_ERR_ARGUMENT, "frames run past the last bin");
+    g.src = (const uint8_t *)src;
+    g.unit_offset = (const long long *)unit_offset;
+    g.counts = (unsigned long long *)counts;
+    g.nset = nframe;
+    g.set_origin = set_origin;
+    g.sets_per_bin = sets_per_bin;
+    g.nthread = 1;
+    g.nelem = nchan;
+    g.nword = (uint32_t)((20000 - 160) * wordbytes / 4);
+    g.nseg = 1u;
+    const int P = wordbytes == 8 ? 2 : 1;
+    const int64_t nb = b1 - b0 + 1;
+    const int64_t per_bin = sets_per_bin < nframe ? sets_per_bin : nframe;
+    int64_t split = ((int64_t)count_depth(true) * sm_count() + nb - 1) / nb;
+    const int64_t need = (per_bin * (int64_t)g.nword + (1ll << 26) - 1)
+        / (1ll << 26);
+    const int64_t full = per_bin / (kVertBlock / 32);
+    if (split > full) split = full;
+    if (split < need) split = need;
+    if (split > per_bin) split = per_bin;
+    if (split < 1) split = 1;
+    if (split > 65535) split = 65535;
+    g.split = (int)split;
+    const size_t smem = (size_t)3 * 20 * kVertBlock * sizeof(uint32_t);
+    cudaStream_t s = as_stream(stream);
+    for (int64_t z0 = 0; z0 < nb; z0 += 65535) {
+        const int64_t nz = nb - z0 < 65535 ? nb - z0 : 65535;
+        g.bin_first = b0 + z0;
+        dim3 grid((unsigned)split, 1u, (unsigned)nz);
+        if (xf == XF_M4_FT)
+            k_state_counts_vert<2, XF_M4_FT><<<grid, kVertBlock, smem, s>>>(g, P);
+        else if (xf == XF_M4_REORDER)
+            k_state_counts_vert<2, XF_M4_REORDER>
+                <<<grid, kVertBlock, smem, s>>>(g, P);
+        else
+            k_state_counts_vert<2, XF_M4_NIBBLES>
+                <<<grid, kVertBlock, smem, s>>>(g, P);
+        BB_CHECK_LAUNCH("bb_mark4_state_counts");
     }
     return BB_OK;
 }

@@ -609,6 +609,31 @@ def state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
     return counts
 
 
+def mark4_state_counts(src, unit_offset, nframe, nchan, fanout, ft, counts,
+                       set_origin=0, sets_per_bin=None):
+    """bb_mark4_state_counts: add the (sign, magnitude) state counts of
+    ``nframe`` Mark 4 frames (``unit_offset``: payload offsets as written by
+    `mark4_scan`) to ``counts`` (int64 CUDA tensor (nbin, nchan, 4), indexed
+    2 * sign + magnitude like `levels.sign_magnitude`)."""
+    lib = _lib.load()
+    _require_cuda(src, unit_offset, counts)
+    nbin = counts.shape[0]
+    if tuple(counts.shape[1:]) != (nchan, 4):
+        raise ValueError('counts must have shape (nbin, nchan, 4)')
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nframe)
+    with _on(src.device):
+        rc = lib.bb_mark4_state_counts(
+            _dev(src, 'src', torch.uint8),
+            _dev(unit_offset, 'unit_offset', torch.int64), nframe, nchan,
+            fanout, int(bool(ft)), int(set_origin), int(sets_per_bin),
+            _dev(counts, 'counts', torch.int64), nbin,
+            _stream_ptr(src.device))
+    _lib.check(rc, lib)
+    _count()
+    return counts
+
+
 def int8_moments(src, unit_offset, nset, nthread, payload_nbytes, nelem,
                  moments, set_origin=0, sets_per_bin=None):
     """bb_int8_moments: add (n, sum, sum of squares) of ``nset`` sets of

@@ -180,8 +180,25 @@ class Mark4StreamReader(StreamReaderBase):
                 self._build_index()
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
-        h0 = self.header0
         nchan, fanout, ft = self._mode
+        uo = self._payload_offsets(raw, frame0, nframe)
+        kernels.mark4_decode(raw, uo, nframe, nchan, fanout, ft,
+                             self._levels, self._fill_value, sample_start,
+                             nsample, out)
+
+    def _count_states(self, raw, frame0, nframe, counts, origin, per_bin):
+        """Consumer hook of `tasks.state_counts`: (sign, magnitude) states
+        per channel straight from the track words of a chunk; the 160 header
+        steps of every frame and invalid frames are not counted."""
+        nchan, fanout, ft = self._mode
+        uo = self._payload_offsets(raw, frame0, nframe)
+        kernels.mark4_state_counts(raw, uo, nframe, nchan, fanout, ft, counts,
+                                   set_origin=origin, sets_per_bin=per_bin)
+
+    def _payload_offsets(self, raw, frame0, nframe):
+        """Header scan of a chunk: payload offset of every frame (< 0:
+        invalid)."""
+        h0 = self.header0
         # with verify, the time code of track 0 must advance by one frame per
         # frame: the scan kernel compares the BCD words with those the writer
         # would generate for the frame's position
@@ -202,9 +219,7 @@ class Mark4StreamReader(StreamReaderBase):
                 raw, nframe, h0.ntrack, check=check,
                 bad=self._bad_counter(raw.device) if self.verify else None,
                 want_words=False)
-        kernels.mark4_decode(raw, uo, nframe, nchan, fanout, ft,
-                             self._levels, self._fill_value, sample_start,
-                             nsample, out)
+        return uo
 
     def _build_index(self):
         """Frame table of an irregular stream, built on the GPU: every place

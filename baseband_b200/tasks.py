@@ -67,7 +67,10 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
     Returns an int64 array ``(nbin,) + sample shape [+ (2,) for complex
     data] + (2**bps,)``; for VDIF the sample shape is ``(nthread, nchan)``
     with the threads the reader decodes (its thread subset; unit dimensions
-    dropped if the reader squeezes), for Mark 5B ``(nchan,)``.  Bin ``b`` covers samples ``[b, b + 1) *
+    dropped if the reader squeezes), for Mark 5B and Mark 4 ``(nchan,)``
+    (Mark 4: codes indexed ``2 * sign + magnitude`` like its level table,
+    counted from the track words; the header steps that open every frame are
+    not samples and are left out).  Bin ``b`` covers samples ``[b, b + 1) *
     samples_per_bin`` from the current sample pointer (default: one bin);
     frames marked invalid are skipped.  The sample pointer advances by
     ``count``.  The packed frames go host -> HBM once; nothing else moves but
@@ -77,7 +80,17 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
     nbin = -(-nframe // frames_per_bin)
     state = {}
 
+    own = getattr(fh, '_count_states', None)     # Mark 4: track words
+
     def consume(raw, f0, nf):
+        if own is not None:
+            if 'counts' not in state:
+                nchan = fh._unsliced_shape[-1]
+                state['geom'] = (1, nchan, 2)
+                state['counts'] = kernels.zeros((nbin, nchan, 4), torch.int64,
+                                                raw.device)
+            own(raw, f0, nf, state['counts'], f0 - frame0, frames_per_bin)
+            return
         uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
         if 'counts' not in state:
             state['geom'] = (nthread, nelem, bps)

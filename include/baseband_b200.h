@@ -437,6 +437,19 @@ int bb_int8_moments(const void *src, const int64_t *unit_offset, int64_t nset,
                     int64_t set_origin, int64_t sets_per_bin,
                     int64_t *moments, int64_t nbin, void *stream);
 
+/* bb_mark4_state_counts: the same for Mark 4 track words.  Frames are the
+ * units: unit_offset[i] is the offset of frame i's payload (past the 160
+ * header steps, as bb_mark4_scan writes it; < 0: invalid frame, left out);
+ * frame i belongs to bin (set_origin + i) / sets_per_bin.
+ *   counts[bin][chan][2 * sign + magnitude]   (nbin x nchan x 4, caller-zeroed)
+ * indexed like the level table of bb_mark4_decode (baseband/mark4/payload.py:
+ * 88-115), so integrated power = sum_c counts[..., c] * levels[c]**2.  The
+ * five track layouts of bb_mark4_decode (nchan, fanout, ft). */
+int bb_mark4_state_counts(const void *src, const int64_t *unit_offset,
+                          int64_t nframe, int32_t nchan, int32_t fanout,
+                          int32_t ft, int64_t set_origin, int64_t sets_per_bin,
+                          uint64_t *counts, int64_t nbin, void *stream);
+
 /* ------------------------------------------------------ bandwidth probes
  * Not part of the reference's path: the ceilings bench.py quotes next to the
  * decode kernels, measured in the same run with the kernels' own launch shape

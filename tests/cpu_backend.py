@@ -397,6 +397,30 @@ def _state_counts(src, unit_offset, nset, nthread, payload_nbytes, bps, nelem,
     return counts
 
 
+def _mark4_state_counts(src, unit_offset, nframe, nchan, fanout, ft, counts,
+                        set_origin=0, sets_per_bin=None):
+    """bb_mark4_state_counts restated with the (emulated) decoder: decoding
+    with the level table (0, 1, 2, 3) yields the index 2 * sign + magnitude
+    of every sample; header steps and invalid frames decode to the fill."""
+    from baseband_b200 import kernels
+    if sets_per_bin is None:
+        sets_per_bin = max(1, set_origin + nframe)
+    out = counts.numpy()
+    if nframe == 0:
+        return counts
+    codes = kernels.mark4_decode(
+        src, unit_offset, nframe, nchan, fanout, ft,
+        levels=np.arange(4, dtype=np.float32), fill_value=-1.0).numpy()
+    codes = codes.reshape(nframe, -1, nchan)
+    for i in range(nframe):
+        b = (set_origin + i) // sets_per_bin
+        for c in range(nchan):
+            col = codes[i, :, c]
+            out[b, c] += np.bincount(col[col >= 0].astype(np.int64),
+                                     minlength=4)
+    return counts
+
+
 def _int8_moments(src, unit_offset, nset, nthread, payload_nbytes, nelem,
                   moments, set_origin=0, sets_per_bin=None):
     """numpy restatement of bb_int8_moments (csrc/bb_counts.cu)."""
@@ -455,6 +479,7 @@ def install(monkeypatch):
     monkeypatch.setattr(kernels, 'frames_assemble', _frames_assemble)
     monkeypatch.setattr(kernels, 'state_counts', _state_counts)
     monkeypatch.setattr(kernels, 'int8_moments', _int8_moments)
+    monkeypatch.setattr(kernels, 'mark4_state_counts', _mark4_state_counts)
     monkeypatch.setattr(kernels, 'locate_frames', _locate_frames)
     monkeypatch.setattr(kernels, 'index_table', _index_table)
     monkeypatch.setattr(kernels, 'vdif_index', _vdif_index)

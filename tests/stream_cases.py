@@ -1464,6 +1464,54 @@ def mark5b_task_state_counts():
     assert got.sum() == valid.sum() * 2500 * 16
 
 
+def mark4_task_state_counts():
+    """tasks.state_counts on Mark 4 track words == counting the levels in what
+    the reference decoded from its own sample files (golden vectors), for all
+    five track layouts; header steps (fill) are not counted.  Plus the
+    synthetic C3 stream with an invalid frame, in two bins."""
+    from baseband_b200 import levels, tasks
+    lv = levels.sign_magnitude()
+    for name, ntrack in M4_SAMPLES:
+        want_data = OUT[name.replace('.', '_') + '_data']
+        with bb.mark4.open(sample_path(name), 'rs', ntrack=ntrack,
+                           decade=2010, fill_value=-7.) as fh:
+            spf = fh.samples_per_frame
+            nframe = fh.shape[0] // spf
+            got = tasks.state_counts(fh, spf, count=nframe * spf)
+            assert fh.tell() == nframe * spf
+            assert np.array_equal(tasks.state_levels(fh), lv)
+        want = _counts_from_decoded(want_data[:nframe * spf], lv, spf)
+        assert got.shape == want.shape == (nframe, want_data.shape[1], 4)
+        assert np.array_equal(got, want), name
+        fanout = spf // 20000
+        assert np.all(got.sum(-1) == (20000 - 160) * fanout)
+    h0 = bb.mark4.Mark4Header.fromvalues(
+        64, time='2014-06-16T07:38:12.475', bps=2, fanout=4, nsb=1,
+        system_id=108)
+    rng = np.random.default_rng(77)
+    data = rng.choice(lv, size=(6 * 80000, 8), p=[.1, .4, .3, .2])
+    buf = io.BytesIO()
+    fw = bb.mark4.open(buf, 'ws', header0=h0, sample_rate=32e6)
+    fw.write(data[:2 * 80000])
+    fw.write(data[2 * 80000:3 * 80000], valid=False)
+    fw.write(data[3 * 80000:])
+    decoded = ostream.mark4_read(np.frombuffer(buf.getvalue(), np.uint8), 64,
+                                 fill_value=np.nan)
+    with bb.mark4.open(io.BytesIO(buf.getvalue()), 'rs', ntrack=64,
+                       decade=2010, chunk_nbytes=2 * 160000) as fh:
+        fh.seek(80000)
+        got = tasks.state_counts(fh, 3 * 80000, count=5 * 80000)
+        fh.seek(80000)
+        power = tasks.integrated_power(fh, 3 * 80000, count=5 * 80000,
+                                       average=False)
+    want = _counts_from_decoded(decoded[80000:], lv, 3 * 80000)
+    assert got.shape == want.shape == (2, 8, 4)
+    assert np.array_equal(got, want)
+    assert got[0].sum() == 2 * 8 * (80000 - 640)      # one frame invalid
+    assert np.allclose(power, (want * lv.astype(np.float64) ** 2).sum(-1),
+                       rtol=1e-12)
+
+
 # -------------------------------------------- byte-level damage (GPU index)
 def vdif_byte_slip():
     """Bytes lost inside a frame and bytes inserted between frames: the GPU

@@ -122,3 +122,51 @@ def test_int8_moments_fuzz(nelem):
     with pytest.raises(ValueError):
         kernels.int8_moments(d_raw, d_uo, 1, 1, 12, 3, torch.zeros(
             (1, 1, 3, 3), dtype=torch.int64, device=DEV))
+
+
+M4_LAYOUTS = [(8, 4, False), (4, 4, False), (8, 2, False), (2, 4, False),
+              (16, 2, True)]
+
+
+@pytest.mark.parametrize('nchan,fanout,ft', M4_LAYOUTS)
+def test_mark4_state_counts(nchan, fanout, ft):
+    """bb_mark4_state_counts (track words -> two-bit code words -> vertical
+    counters) against the decoder: decoding with the level table (0, 1, 2, 3)
+    gives the index 2 * sign + magnitude of every sample (that decode is
+    itself parity-tested against the oracle and the reference's golden
+    vectors).  Random track words, shuffled / invalid frames, several bins,
+    accumulation."""
+    rng = np.random.default_rng(nchan * 10 + fanout)
+    wordbytes = nchan * 2 * fanout // 8
+    frame = 20000 * wordbytes
+    for trial in range(3):
+        nframe = int(rng.integers(1, 12))
+        raw = rng.integers(0, 256, nframe * frame, dtype=np.uint8)
+        uo = rng.permutation(nframe).astype(np.int64) * frame \
+            + 160 * wordbytes
+        if nframe > 2:
+            uo[rng.random(nframe) < 0.25] = -1
+        per_bin = int(rng.integers(1, nframe + 2))
+        origin = int(rng.integers(0, 4))
+        nbin = (origin + nframe - 1) // per_bin + 1
+        d_raw, d_uo = torch.from_numpy(raw).to(DEV), torch.from_numpy(uo).to(DEV)
+        codes = kernels.mark4_decode(d_raw, d_uo, nframe, nchan, fanout, ft,
+                                     levels=np.arange(4, dtype=np.float32),
+                                     fill_value=-1.0)
+        codes = codes.cpu().numpy().reshape(nframe, -1, nchan)
+        want = np.zeros((nbin, nchan, 4), np.int64)
+        for i in range(nframe):
+            for c in range(nchan):
+                col = codes[i, :, c]
+                want[(origin + i) // per_bin, c] += np.bincount(
+                    col[col >= 0].astype(np.int64), minlength=4)
+        got = torch.zeros((nbin, nchan, 4), dtype=torch.int64, device=DEV)
+        for _ in range(2):
+            kernels.mark4_state_counts(d_raw, d_uo, nframe, nchan, fanout, ft,
+                                       got, origin, per_bin)
+        assert np.array_equal(got.cpu().numpy(), 2 * want), (trial, nframe)
+        valid = int((uo >= 0).sum())
+        assert got.sum().item() == 2 * valid * (20000 - 160) * fanout * nchan
+    with pytest.raises(KeyError):
+        kernels.mark4_state_counts(d_raw, d_uo, 1, 3, 4, False, torch.zeros(
+            (1, 3, 4), dtype=torch.int64, device=DEV))

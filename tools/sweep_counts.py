@@ -100,3 +100,31 @@ for bps, nthread, nelem in ((4, 4, 1), (4, 1, 1024), (2, 1, 64), (2, 4, 8),
               'median' % (bps, nthread, nelem, vd,
                           nset * nthread * payload / ts[len(ts) // 2] / 1e6))
     del raw, uo, acc
+
+# Mark 4 track words (C3: 64 tracks, fan-out 4; and the 16-track layout)
+from baseband_b200 import synthetic  # noqa: E402
+for nchan, fanout, ft in ((8, 4, False), (16, 2, True), (2, 4, False)):
+    wordbytes = nchan * 2 * fanout // 8
+    frame = 20000 * wordbytes
+    nframe = int(gib * 2**30) // frame
+    raw = torch.randint(0, 256, (nframe * frame,), dtype=torch.uint8,
+                        device=DEV)
+    uo = torch.arange(nframe, dtype=torch.int64, device=DEV) * frame \
+        + 160 * wordbytes
+    acc = kernels.zeros((-(-nframe // 50), nchan, 4), torch.int64,
+                        torch.device(DEV))
+    os.environ.pop('BB_TUNE_VERT_DEPTH', None)
+    ts = []
+    for i in range(8):
+        a, b = (torch.cuda.Event(enable_timing=True) for _ in range(2))
+        a.record()
+        kernels.mark4_state_counts(raw, uo, nframe, nchan, fanout, ft, acc,
+                                   sets_per_bin=50)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ts = sorted(ts[2:])
+    print('mark4 counts %d ch fan-out %d%s: %.1f GB/s median (frame bytes)' % (
+        nchan, fanout, ' ft' if ft else '',
+        nframe * frame / ts[len(ts) // 2] / 1e6))
+    del raw, uo, acc
