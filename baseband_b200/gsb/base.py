@@ -183,6 +183,18 @@ class GSBStreamReader(_GSBStreamBase, StreamReaderBase):
                 k += 1
 
     def _decode_chunk(self, raw, frame0, nframe, sample_start, nsample, out):
+        uo, npol, pn, bps, nelem, npart = self._packed_units(raw, frame0,
+                                                             nframe)
+        kernels.decode_bitfield(
+            raw, uo, nframe * npart, npol, pn, bps, nelem, self._complex_data,
+            kernels.CODEC_SINT, None, self._fill_value, sample_start, nsample,
+            out)
+
+    def _packed_units(self, raw, frame0, nframe):
+        """Unit table of a chunk (the raw files' pieces sit one after the
+        other in ``raw``, `_read_raw`): a frame is ``npart`` sets of ``npol``
+        units (`tasks.state_counts` for the 4-bit modes, `tasks.moments` for
+        8 bit)."""
         files = self._files()
         npol, npart = len(files), len(files[0])
         pn = self._payload_nbytes
@@ -193,10 +205,24 @@ class GSBStreamReader(_GSBStreamBase, StreamReaderBase):
         uo = ((pol * npart + part) * span + frame * pn).reshape(-1)
         nchan = self._sample_shape[-1]
         nelem = nchan * (2 if self._complex_data else 1)
-        kernels.decode_bitfield(
-            raw, torch.from_numpy(uo).to(raw.device), nframe * npart, npol,
-            pn, self._bps, nelem, self._complex_data, kernels.CODEC_SINT,
-            None, self._fill_value, sample_start, nsample, out)
+        return (torch.from_numpy(uo).to(raw.device), npol, pn, self._bps,
+                nelem, npart)
+
+    @property
+    def _levels(self):
+        """Value of every 4-bit code (two's complement nibbles,
+        gsb/payload.py:19-42), for `tasks.state_levels`; 8-bit streams are
+        summarised by their moments instead."""
+        if self._bps != 4:
+            return None
+        code = np.arange(16)
+        return np.where(code < 8, code, code - 16).astype(np.float32)
+
+    def _moments_view(self, m):
+        """(nbin, npol, nchan * parts, 3) -> (nbin,) + sample shape + parts."""
+        ib = 2 if self._complex_data else 1
+        m = m.reshape((m.shape[0],) + tuple(self._sample_shape) + (ib, 3))
+        return m if ib == 2 else m[..., 0, :]
 
 
 class GSBStreamWriter(_GSBStreamBase, StreamWriterBase):

@@ -52,6 +52,13 @@ def _frame_range(fh, count, samples_per_bin):
     return start // spf, count // spf, samples_per_bin // spf
 
 
+def _units(fh, raw, f0, nf):
+    """`fh._packed_units` with the number of unit sets per frame (1 unless
+    the reader says otherwise: GSB frames are several sets)."""
+    units = fh._packed_units(raw, f0, nf)
+    return units if len(units) == 6 else tuple(units) + (1,)
+
+
 def state_levels(fh):
     """float32 level of every code of ``fh``'s payloads (the decode table)."""
     codec = getattr(fh, '_codec', None)
@@ -91,14 +98,15 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
                                                 raw.device)
             own(raw, f0, nf, state['counts'], f0 - frame0, frames_per_bin)
             return
-        uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
+        uo, nthread, payload_nbytes, bps, nelem, per = _units(fh, raw, f0, nf)
         if 'counts' not in state:
             state['geom'] = (nthread, nelem, bps)
             state['counts'] = kernels.zeros(
                 (nbin, nthread, nelem, 1 << bps), torch.int64, raw.device)
-        kernels.state_counts(raw, uo, nf, nthread, payload_nbytes, bps, nelem,
-                             state['counts'], set_origin=f0 - frame0,
-                             sets_per_bin=frames_per_bin)
+        kernels.state_counts(raw, uo, nf * per, nthread, payload_nbytes, bps,
+                             nelem, state['counts'],
+                             set_origin=(f0 - frame0) * per,
+                             sets_per_bin=frames_per_bin * per)
 
     fh._for_each_packed_chunk(frame0, nframe, consume)
     check = getattr(fh, '_new_inconsistencies', None)
@@ -121,7 +129,7 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
 
 def moments(fh, samples_per_bin=None, count=None):
     """Count, sum and sum of squares of the next ``count`` samples of a
-    reader of 8-bit two's-complement data (GUPPI), per integration bin and
+    reader of 8-bit two's-complement data (GUPPI, GSB), per integration bin and
     sample element, straight from the packed bytes (exact integers).
 
     Returns three int64 arrays ``(n, total, total_of_squares)`` of shape
@@ -135,21 +143,31 @@ def moments(fh, samples_per_bin=None, count=None):
     state = {}
 
     def consume(raw, f0, nf):
-        uo, nthread, payload_nbytes, bps, nelem = fh._packed_units(raw, f0, nf)
+        uo, nthread, payload_nbytes, bps, nelem, per = _units(fh, raw, f0, nf)
         if bps != 8:
             raise TypeError('moments are for 8-bit data; use state_counts')
         if 'm' not in state:
             state['geom'] = (nthread, nelem)
             state['m'] = kernels.zeros((nbin, nthread, nelem, 3), torch.int64,
                                        raw.device)
-        kernels.int8_moments(raw, uo, nf, nthread, payload_nbytes, nelem,
-                             state['m'], set_origin=f0 - frame0,
-                             sets_per_bin=frames_per_bin)
+        kernels.int8_moments(raw, uo, nf * per, nthread, payload_nbytes,
+                             nelem, state['m'],
+                             set_origin=(f0 - frame0) * per,
+                             sets_per_bin=frames_per_bin * per)
 
     fh._for_each_packed_chunk(frame0, nframe, consume)
     fh.seek(fh.tell() + nframe * fh.samples_per_frame)
     m = state['m'].cpu().numpy()
     nthread, nelem = state['geom']
+    view = getattr(fh, '_moments_view', None)
+    if view is not None:                           # GSB: (pol, chan, parts)
+        m = view(m)
+        if getattr(fh, 'squeeze', False):
+            keep = tuple(d for d in m.shape[1:1 + len(fh._unsliced_shape)]
+                         if d > 1)
+            m = m.reshape((nbin,) + keep
+                          + m.shape[1 + len(fh._unsliced_shape):])
+        return m[..., 0], m[..., 1], m[..., 2]
     h0 = fh.header0
     ib = 2 if fh.complex_data else 1
     # (thread = channel, elem = (pol, part)) or (elem = (chan, pol, part))

@@ -1512,6 +1512,55 @@ def mark4_task_state_counts():
                        rtol=1e-12)
 
 
+def gsb_task_counts_and_moments():
+    """Consumers on GSB streams: state counts of the 4-bit raw-voltage dump
+    and moments / power of the 8-bit phased-array mode (two polarisations in
+    two files each), against the reference's decoded sample files (golden
+    vectors), in bins that cut across the chunks."""
+    from baseband_b200 import tasks
+    with bb.gsb.open(os.path.join(GSB, 'sample_gsb_rawdump.timestamp'), 'rs',
+                     raw=os.path.join(GSB, 'sample_gsb_rawdump.dat'),
+                     sample_rate=1e8 / 3 / 2 ** 10, payload_nbytes=4096,
+                     squeeze=False, chunk_nbytes=3 * 4096) as fh:
+        lv = tasks.state_levels(fh)
+        assert np.array_equal(lv, np.r_[0:8, -8:0].astype(np.float32))
+        fh.seek(8192)
+        got = tasks.state_counts(fh, 4 * 8192, count=9 * 8192)
+        fh.seek(8192)
+        power = tasks.integrated_power(fh, 4 * 8192, count=9 * 8192)
+    decoded = ostream.gsb_rawdump_read(
+        np.fromfile(os.path.join(GSB, 'sample_gsb_rawdump.dat'), np.uint8),
+        payload_nbytes=4096, nframe=10)[8192:]
+    _same(decoded[:8192], OUT['gsb_rawdump_8192_data'][8192:])
+    want = _counts_from_decoded(decoded, lv, 4 * 8192)
+    assert got.shape == want.shape == (3, 1, 16)
+    assert np.array_equal(got, want)
+    for b in range(3):
+        blk = decoded[b * 4 * 8192:(b + 1) * 4 * 8192].astype(np.float64)
+        assert np.allclose(power[b], (blk ** 2).mean(0), rtol=1e-12)
+    frames = OUT['gsb_phased_8192_frames']            # (5, 16, 2, 512)
+    want = frames.reshape(-1, 2, 512)
+    raw = [[os.path.join(GSB, 'sample_gsb_phased.Pol-%s%d.dat' % (p, k))
+            for k in (1, 2)] for p in 'LR']
+    ts = os.path.join(GSB, 'sample_gsb_phased.timestamp')
+    with bb.gsb.open(ts, 'rs', raw=raw, sample_rate=1e8 / 3 / 2 ** 19,
+                     payload_nbytes=8192, chunk_nbytes=2 * 4 * 8192) as fh:
+        fh.seek(16)
+        n, total, sq = tasks.moments(fh, 3 * 16, count=4 * 16)
+        assert fh.tell() == 5 * 16
+        fh.seek(16)
+        power = tasks.integrated_power(fh, 3 * 16, count=4 * 16)
+    parts = np.stack([want.real, want.imag], -1).astype(np.int64)[16:]
+    assert n.shape == total.shape == sq.shape == (2, 2, 512, 2)
+    for b in range(2):
+        blk = parts[b * 48:(b + 1) * 48]
+        assert np.all(n[b] == blk.shape[0])
+        assert np.array_equal(total[b], blk.sum(0))
+        assert np.array_equal(sq[b], (blk * blk).sum(0))
+        assert np.allclose(power[b], (blk.astype(np.float64) ** 2)
+                           .sum(-1).mean(0), rtol=1e-12)
+
+
 # -------------------------------------------- byte-level damage (GPU index)
 def vdif_byte_slip():
     """Bytes lost inside a frame and bytes inserted between frames: the GPU
