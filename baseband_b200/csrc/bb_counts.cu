@@ -11,6 +11,13 @@
 //     sum(decoded**2) over a bin  ==  sum_c counts[..., c] * levels[c]**2.
 // Integer counts are order-independent: the result is bit-exact whatever the
 // launch shape.  HBM-read bound: one pass over the packed bytes.
+//
+// Kernels: k_state_counts_reg (1/2 bit, <= 16 counters per word: popcounts in
+// registers), k_state_counts_vert / _vert4 (more elements, 4 bit: vertical
+// counters; with a word transform also Mark 4 track words,
+// bb_mark4_state_counts), k_state_counts_hist (4-bit units too large for the
+// 16-bit counters of _vert4), k_int8_moments (8-bit two's complement: n, sum,
+// sum of squares).
 #include "bb_runtime.cuh"
 #include "bb_mark4_plan.h"
 
