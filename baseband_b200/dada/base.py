@@ -161,6 +161,75 @@ class DADAStreamReader(_DADAStreamBase, StreamReaderBase):
                       h0.complex_data, self._mkbf, sample_start - s0,
                       nsample, out)
 
+    # -- packed consumers (tasks.moments) -----------------------------------
+    def _for_each_packed_chunk(self, frame0, nframe, fn):
+        """The base loop works on whole frames; DADA frames can be far larger
+        than a chunk, so the pieces of `_chunks` (never spanning frames) go
+        through the same three-stage pipeline and ``fn`` sees each as part of
+        its frame (``fn(raw, frame, 1)``, the piece being the one unit)."""
+        if self._mkbf:
+            raise NotImplementedError('packed consumers do not know the MKBF '
+                                      'heap layout')
+        from ..base.stream import DEVICE_READ_STAGES
+        dev = self.device
+        stages, ss = self._pipeline(dev)
+        spf = self._samples_per_frame
+        word = lcm(4, self._sample_nbytes)
+        chunks = list(self._chunks(frame0 * spf, nframe * spf))
+        for f0, nf, s0, ns, _ in chunks:
+            if (s0 * self._sample_nbytes) % 4 or (ns * self._sample_nbytes) % 4:
+                raise ValueError('chunk_nbytes must hold whole words of whole '
+                                 'samples ({} bytes) for a packed consumer'
+                                 .format(word))
+        ss.after_caller(1)
+
+        def begin(k):
+            f0, nf, s0, ns, _ = chunks[k]
+            st = stages[k % DEVICE_READ_STAGES]
+            if st.done is not None:
+                st.done.synchronize()
+            pin, _ = st.buffers(self._chunk_nbytes_of(f0, nf, s0, ns), 0, dev,
+                                False)
+            return self._read_raw_begin(f0, nf, pin, s0, ns)
+
+        ahead = begin(0) if chunks else None
+        for k, (f0, nf, s0, ns, _) in enumerate(chunks):
+            st = stages[k % DEVICE_READ_STAGES]
+            raw = st.raw[:self._chunk_nbytes_of(f0, nf, s0, ns)]
+            pin = ahead.wait()
+            ahead = begin(k + 1) if k + 1 < len(chunks) else None
+            try:
+                with ss.use(0):
+                    ss.wait_event(0, st.free)
+                    self._upload(raw, pin, f0, nf)
+                    st.done = ss.event(0)
+                with ss.use(1):
+                    ss.wait_event(1, st.done)
+                    fn(raw[:ns * self._sample_nbytes], f0, 1)
+                    st.free = ss.event(1)
+            except BaseException:
+                if ahead is not None:
+                    ahead.wait()
+                raise
+        ss.caller_after(1)
+
+    def _packed_units(self, raw, frame0, nframe):
+        """``raw`` is one piece of one frame's payload: a single unit."""
+        import torch
+        h0 = self.header0
+        if h0.bps != 8:
+            raise KeyError(h0.bps)
+        ib = 2 if h0.complex_data else 1
+        uo = torch.zeros(1, dtype=torch.int64).to(raw.device)
+        return uo, 1, raw.numel(), 8, h0['NPOL'] * h0['NCHAN'] * ib
+
+    def _moments_view(self, m):
+        """(nbin, 1, npol * nchan * parts, 3) -> (nbin, npol, nchan, parts)."""
+        h0 = self.header0
+        ib = 2 if h0.complex_data else 1
+        m = m.reshape(m.shape[0], h0['NPOL'], h0['NCHAN'], ib, 3)
+        return m if ib == 2 else m[..., 0, :]
+
     @property
     def stop_time(self):
         return self.start_time + self._offset_seconds(self._nsample)

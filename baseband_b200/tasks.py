@@ -129,7 +129,7 @@ def state_counts(fh, samples_per_bin=None, count=None, device_output=False):
 
 def moments(fh, samples_per_bin=None, count=None):
     """Count, sum and sum of squares of the next ``count`` samples of a
-    reader of 8-bit two's-complement data (GUPPI, GSB), per integration bin and
+    reader of 8-bit two's-complement data (GUPPI, GSB, DADA), per integration bin and
     sample element, straight from the packed bytes (exact integers).
 
     Returns three int64 arrays ``(n, total, total_of_squares)`` of shape
@@ -187,7 +187,8 @@ def _whole_frames(fh, count):
     if count is not None:
         return count
     spf = fh.samples_per_frame
-    return (fh._nframe * spf) - fh.tell()
+    whole = min(fh._nframe * spf, fh.shape[0] // spf * spf)   # DADA: the last
+    return whole - fh.tell()                                  # may be short
 
 
 def integrated_power(fh, samples_per_bin=None, count=None, average=True):

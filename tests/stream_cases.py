@@ -5,6 +5,7 @@ import io
 import os
 
 import numpy as np
+import pytest
 import torch
 
 import baseband_b200 as bb
@@ -1559,6 +1560,42 @@ def gsb_task_counts_and_moments():
         assert np.array_equal(sq[b], (blk * blk).sum(0))
         assert np.allclose(power[b], (blk.astype(np.float64) ** 2)
                            .sum(-1).mean(0), rtol=1e-12)
+
+
+def dada_task_moments():
+    """tasks.moments / integrated_power on DADA streams, whose frames are cut
+    into pieces by the chunk size, against the reference's decoded sample
+    files (golden vectors)."""
+    from baseband_b200 import tasks
+    for name in ('sample.dada', 'sample_meerkat.dada'):
+        want = OUT[name.replace('.', '_') + '_data']      # (n, npol, nchan)
+        for chunk in (None, 4096, 10000):
+            with bb.dada.open(sample_path(name), 'rs', squeeze=False,
+                              chunk_nbytes=chunk) as fh:
+                spf = fh.samples_per_frame
+                n, total, sq = tasks.moments(fh)
+                assert fh.tell() == fh.shape[0] // spf * spf
+                fh.seek(0)
+                power = tasks.integrated_power(fh)
+            body = want[:want.shape[0] // spf * spf]
+            if np.iscomplexobj(body):
+                parts = np.stack([body.real, body.imag], -1).astype(np.int64)
+                mean_power = (parts.astype(np.float64) ** 2).sum(-1).mean(0)
+            else:
+                parts = body.astype(np.int64)
+                mean_power = (parts.astype(np.float64) ** 2).mean(0)
+            assert n.shape == (1,) + parts.shape[1:], (n.shape, parts.shape)
+            assert np.all(n[0] == parts.shape[0])
+            assert np.array_equal(total[0], parts.sum(0))
+            assert np.array_equal(sq[0], (parts * parts).sum(0))
+            assert np.allclose(power[0], mean_power, rtol=1e-12)
+    with bb.dada.open(sample_path('sample_meerkat.dada'), 'rs',
+                      chunk_nbytes=4098) as fh:     # 2049 two-byte samples
+        with pytest.raises(ValueError):       # pieces must be whole words
+            tasks.moments(fh)
+    with bb.dada.open(sample_path('sample_mkbf.dada'), 'rs') as fh:
+        with pytest.raises(NotImplementedError):
+            tasks.moments(fh)
 
 
 # -------------------------------------------- byte-level damage (GPU index)
