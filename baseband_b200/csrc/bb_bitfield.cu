@@ -346,6 +346,23 @@ __global__ void __launch_bounds__(kBlock)
 k_encode_bitfield(const EncGeom p, const QuantConsts<T> c) {
     constexpr int U = EncUnroll<BPS, MODE>::value;
     const uint32_t item0 = blockIdx.x * (kBlock * U) + threadIdx.x;
+    if (MODE == MODE_RUNQ) {
+        // four words per item: two items' (eight) loads in flight
+        constexpr int B = sizeof(T) == 4 ? 2 : 1;
+#pragma unroll 1
+        for (int u0 = 0; u0 < U; u0 += B) {
+            EncQuadItem<T> it[B];
+#pragma unroll
+            for (int b = 0; b < B; ++b) {
+                const uint32_t item = item0 + (u0 + b) * kBlock;
+                it[b].dst = nullptr;
+                if (item < p.nitems) enc_quad_fetch<T>(p, item, it[b]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; ++b) enc_quad_emit<T, QUANT>(c, it[b]);
+        }
+        return;
+    }
     if (MODE == MODE_RUN && BPS >= 4) {
         // few float4 per word: keep the loads of several words in flight
         constexpr int B = BPS == 8 ? 4 : 2;
@@ -521,6 +538,11 @@ static int launch_encode(const std::vector<EncLaunch> &launches,
         case MODE_RUN:
             k_encode_bitfield<T, BPS, QUANT, MODE_RUN>
                 <<<tile_grid(n, 4), kBlock, 0, stream>>>(l.g, consts);
+            break;
+        case MODE_RUNQ:
+            if constexpr (BPS == 8)
+                k_encode_bitfield<T, 8, QUANT, MODE_RUNQ>
+                    <<<tile_grid(n, 4), kBlock, 0, stream>>>(l.g, consts);
             break;
         default:
             k_encode_bitfield<T, BPS, QUANT, MODE_SCALAR>

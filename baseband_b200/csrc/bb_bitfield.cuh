@@ -968,6 +968,55 @@ BB_HD void enc_word_emit(const QuantConsts<T> &c,
     store_u32(it.dst, w);
 }
 
+// RUNQ (8 bit): item = four consecutive words of one unit = 16 codes of one
+// row segment; `div_nword` divides by the number of such quads per unit.
+template <typename T>
+struct EncQuadItem {
+    Vec4<T> v[4];
+    uint8_t *dst;                   // null: nothing to do
+};
+
+template <typename T>
+BB_HD void enc_quad_fetch(const EncGeom &p, uint32_t item, EncQuadItem<T> &it) {
+    uint32_t rest, kq, set, slot;
+    p.div_nthread.divmod(item, rest, slot);
+    p.div_nword.divmod(rest, set, kq);
+    const long long off = p.unit_offset[set * p.nthread + slot];
+    it.dst = nullptr;
+    if (off < 0) return;
+    it.dst = p.dst + off + 16ull * kq;
+    const T *in = reinterpret_cast<const T *>(p.in) + p.in_elem_offset;
+    const size_t rowlen = (size_t)p.nthread * p.nelem;
+    const uint32_t pc = kq * 16u;
+    size_t idx = (size_t)set * p.spf * rowlen;
+    if (p.nthread == 1) {
+        idx += pc;
+    } else {
+        const uint32_t t = pc >> p.log2_nelem, e = pc & (p.nelem - 1u);
+        idx += ((size_t)t * p.nthread + slot) * p.nelem + e;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) it.v[m] = Vec4<T>::load(in + idx + 4 * m);
+}
+
+template <typename T, int QUANT>
+BB_HD void enc_quad_emit(const QuantConsts<T> &c, const EncQuadItem<T> &it) {
+    if (it.dst == nullptr) return;
+    uint32_t w[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+        w[m] = quantise<T, 8, QUANT>(it.v[m].x, c)
+            | (quantise<T, 8, QUANT>(it.v[m].y, c) << 8)
+            | (quantise<T, 8, QUANT>(it.v[m].z, c) << 16)
+            | (quantise<T, 8, QUANT>(it.v[m].w, c) << 24);
+    if ((reinterpret_cast<uintptr_t>(it.dst) & 15u) == 0) {
+        *reinterpret_cast<U4 *>(it.dst) = U4{w[0], w[1], w[2], w[3]};
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) store_u32(it.dst + 4 * m, w[m]);
+    }
+}
+
 // RUN / SCALAR: item = output word index over all units of the launch.
 template <typename T, int BPS, int QUANT, bool VEC>
 BB_HD void enc_word(const EncGeom &p, const QuantConsts<T> &c,

@@ -14,7 +14,8 @@ enum { MODE_ROWGROUP4 = 0, MODE_ROWGROUP2 = 1, MODE_RUN = 2, MODE_SCALAR = 3,
        MODE_ROWWORD2 = 9, MODE_WORDROW2 = 10,
        MODE_WORDROW4X2 = 11, MODE_WORDROW2X2 = 12,     // rows of two float4
        MODE_TILE4 = 13, MODE_TILE2 = 14,               // rows of four float4
-       MODE_RUNS = 15 };        // RUN, one word -> its S samples as S rows
+       MODE_RUNS = 15,          // RUN, one word -> its S samples as S rows
+       MODE_RUNQ = 16 };        // 8-bit encode: four words per item
 
 // Development tunables (BB_TUNE_<NAME> environment variables), read at every
 // call so that a sweep can change them inside one process.
@@ -231,6 +232,12 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
     if (mode == MODE_ROWGROUP2 && nthread == 2 && nword <= rw_budget
         && bps <= 2)
         mode = MODE_ROWWORD2;
+    // 8 bit, whole words of one row segment in fours (one thread, or >= 16
+    // elements per thread row): an item is four words -- the divisions and
+    // the unit-offset load once per 64 input bytes, one 16-byte store
+    if (mode == MODE_RUN && bps == 8 && nword % 4 == 0
+        && (nthread == 1 || nelem % 16 == 0) && tune("BB_TUNE_RUNQ", 1))
+        mode = MODE_RUNQ;
     uint64_t per_set;
     uint32_t ngroup = 1;
     if (mode == MODE_ROWGROUP4 || mode == MODE_ROWGROUP2) {
@@ -238,6 +245,8 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
         per_set = (uint64_t)nword * ngroup;
     } else if (mode == MODE_ROWWORD4 || mode == MODE_ROWWORD2) {
         per_set = nword;                  // items are lanes = word positions
+    } else if (mode == MODE_RUNQ) {
+        per_set = (uint64_t)(nword / 4) * nthread;
     } else {
         per_set = (uint64_t)nword * nthread;
     }
@@ -266,7 +275,7 @@ inline bool plan_encode(const void *in, void *dst, const int64_t *unit_offset,
             g.nitems = (g.nwords_total + 31u) / 32u * 32u;
         g.ngroup = ngroup;
         g.log2_nelem = ilog2_exact(nelem);
-        g.div_nword = make_fastdiv(nword);
+        g.div_nword = make_fastdiv(mode == MODE_RUNQ ? nword / 4 : nword);
         g.div_ngroup = make_fastdiv(ngroup);
         g.div_nthread = make_fastdiv(nthread);
         launches.push_back({mode, g});

@@ -19,6 +19,7 @@ namespace bb {
 struct alignas(16) F4 { float x, y, z, w; };
 struct alignas(16) D2 { double x, y; };
 struct alignas(8) F2 { float x, y; };
+struct alignas(16) U4 { uint32_t x, y, z, w; };
 
 BB_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)

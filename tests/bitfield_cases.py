@@ -185,10 +185,10 @@ def oracle_decode(c):
 
 
 def _ecase(id, bps, nelem, nthread, nset, payload_nbytes, quant='vdif',
-           dtype='f4', invalid=()):
+           dtype='f4', invalid=(), offset0=32):
     return dict(id=id, bps=bps, nelem=nelem, nthread=nthread, nset=nset,
                 payload_nbytes=payload_nbytes, quant=quant, dtype=dtype,
-                invalid=invalid)
+                invalid=invalid, offset0=offset0)
 
 
 ENCODE_CASES = [
@@ -225,6 +225,18 @@ ENCODE_CASES = [
     _ecase('dada_8bit_cplx', 8, 4, 1, 2, 6400, quant='sint'),
     _ecase('gsb_8bit_2thr_f64', 8, 1024, 2, 2, 4096, quant='sint',
            dtype='f8'),
+    # 8 bit in items of four words (RUNQ): one thread, or >= 16 elements per
+    # thread row; payloads not at 16-byte offsets (four 4-byte stores); and
+    # the shapes that must stay with one word per item
+    _ecase('gsb_8bit_2thr', 8, 1024, 2, 3, 8192, quant='sint', invalid=(3,)),
+    _ecase('vdif_8bit_1thr', 8, 1, 1, 3, 8000),
+    _ecase('vdif_8bit_1thr_16ch_off8', 8, 16, 1, 3, 8000, offset0=40),
+    _ecase('vdif_8bit_3thr_32ch_off4', 8, 32, 3, 2, 4096, offset0=36,
+           invalid=(4,)),
+    _ecase('dada_8bit_cplx_f64_off8', 8, 4, 1, 2, 6400, quant='sint',
+           dtype='f8', offset0=8),
+    _ecase('8bit_1thr_odd_words', 8, 2, 1, 2, 8008),
+    _ecase('8bit_2thr_8ch', 8, 8, 2, 2, 4096),
 ]
 
 _QUANT = {'vdif': 0, 'mark5b': 1, 'sint': 2}
@@ -247,7 +259,7 @@ def make_encode_case(case):
     nunit = nset * nthread
     stride = nbytes + 32
     order = rng.permutation(nunit)
-    unit_offset = (order * stride + 32).astype(np.int64)
+    unit_offset = (order * stride + case.get('offset0', 32)).astype(np.int64)
     truth = unit_offset.copy()
     for u in case['invalid']:
         unit_offset[u] = -1

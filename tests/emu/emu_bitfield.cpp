@@ -172,7 +172,11 @@ static void run_encode(const std::vector<EncLaunch> &launches) {
             if (l.mode == MODE_ROWGROUP4) enc_rowgroup<T, BPS, QUANT, 4>(l.g, c, item);
             else if (l.mode == MODE_ROWGROUP2) enc_rowgroup<T, BPS, QUANT, 2>(l.g, c, item);
             else if (l.mode == MODE_RUN) enc_word<T, BPS, QUANT, true>(l.g, c, item);
-            else enc_word<T, BPS, QUANT, false>(l.g, c, item);
+            else if (l.mode == MODE_RUNQ) {
+                EncQuadItem<T> it;
+                enc_quad_fetch<T>(l.g, item, it);
+                enc_quad_emit<T, QUANT>(c, it);
+            } else enc_word<T, BPS, QUANT, false>(l.g, c, item);
         }
     }
 }
