@@ -8,13 +8,19 @@ a collective used: one NCCL all-gather of the decoded shards over NVLink
 (``gather=True``).  Gathering *decoded* float32 moves 16x the packed bytes for
 2-bit data; prefer leaving the shards where they are.
 
+The packed-byte consumer shards the same way, and its collective is tiny:
+`state_counts_sharded` counts whole integration bins per rank and sums the
+int64 count tables with one all-reduce (a few KB), so every rank ends up with
+the counts of the whole stream.
+
 One process per GPU (``torchrun``); ``torch.distributed`` is plumbing only.
 """
 import os
 
 import torch
 
-__all__ = ['shard_bounds', 'shard_samples', 'gather_block', 'read_sharded']
+__all__ = ['shard_bounds', 'shard_samples', 'gather_block', 'read_sharded',
+           'state_counts_sharded']
 
 
 def shard_bounds(nitem, rank, world):
@@ -113,3 +119,49 @@ def read_sharded(fh, rank=None, world=None, gather=False, group=None):
     if not on_device:
         whole = whole.numpy()
     return whole, (0, total)
+
+
+def state_counts_sharded(fh, samples_per_bin, rank=None, world=None,
+                         reduce=True, group=None):
+    """`tasks.state_counts` of ONE stream over all ranks: the integration
+    bins are dealt out in contiguous ranges (`shard_bounds`), every rank
+    ingests and counts only its own frames, and -- with ``reduce`` -- one
+    all-reduce of the int64 count table (zeros outside the rank's bins)
+    leaves the counts of the whole stream on every rank.
+
+    Returns ``(counts, (bin0, bin1))``: the table (numpy; all bins with
+    ``reduce``, else this rank's bins only) and the range of bins this rank
+    counted.  The stream must hold whole bins from the current sample
+    pointer on (a last partial bin is left out)."""
+    from . import tasks
+    rank, world = _dist_env(rank, world)
+    start = fh.tell()
+    nbin = (fh.shape[0] - start) // samples_per_bin
+    if nbin <= 0:
+        raise ValueError('the stream does not hold one whole bin')
+    b0, b1 = shard_bounds(nbin, rank, world)
+    mine = None
+    if b1 > b0:
+        fh.seek(start + b0 * samples_per_bin)
+        mine = tasks.state_counts(fh, samples_per_bin,
+                                  count=(b1 - b0) * samples_per_bin,
+                                  device_output=reduce and world > 1)
+    if not reduce or world == 1:
+        return mine, (b0, b1)
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = fh.device if backend == 'nccl' else torch.device('cpu')
+    # every rank needs the shape of a bin's table, also one without bins
+    shape = [None]
+    if mine is not None:
+        shape[0] = tuple(mine.shape[1:])
+    shapes = [None] * world
+    dist.all_gather_object(shapes, shape[0], group=group)
+    bin_shape = next(s for s in shapes if s is not None)
+    whole = torch.zeros((nbin,) + tuple(bin_shape), dtype=torch.int64,
+                        device=dev)
+    if mine is not None:
+        whole[b0:b1] = mine.to(dev)
+    dist.all_reduce(whole, op=dist.ReduceOp.SUM, group=group)
+    fh.seek(start + nbin * samples_per_bin)
+    return whole.cpu().numpy(), (b0, b1)

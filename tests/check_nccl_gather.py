@@ -40,6 +40,20 @@ fh2 = bb.vdif.open(io.BytesIO(raw2.tobytes()), 'rs', sample_rate=32e6,
 whole2, span2 = parallel.read_sharded(fh2, gather=True)
 ok = ok and span2 == (0, want2.shape[0]) and np.array_equal(
     whole2.cpu().numpy(), want2)
+# the packed-byte consumer over the ranks: bins dealt out, one all-reduce of
+# the int64 count tables
+from baseband_b200 import levels, tasks  # noqa: E402
+lv = levels.offset_binary(2)
+want = ostream.vdif_read(raw, fill_value=np.nan)[:, :, 0]   # fill: no level
+for sets_per_bin in (1, 5, 37):
+    fh.seek(0)
+    counts, (b0, b1) = parallel.state_counts_sharded(fh, sets_per_bin * 32000)
+    nbin = 37 // sets_per_bin
+    rows = want[:nbin * sets_per_bin * 32000].reshape(nbin, -1, 16)
+    ok = ok and counts.shape == (nbin, 16, 4) and all(
+        np.array_equal(counts[..., c], (rows == lv[c]).sum(1))
+        for c in range(4))
+    ok = ok and (b0, b1) == parallel.shard_bounds(nbin, rank, world)
 # timing of the in-place gather of larger decoded shards (NVLink)
 block = 1 << 28                                                  # 1 GiB f32
 full = torch.empty((world * block,), dtype=torch.float32, device=dev)

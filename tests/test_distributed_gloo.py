@@ -53,6 +53,25 @@ def _worker(rank, world, port, results):
         gfh = bb.guppi.open(io.BytesIO(graw.tobytes()), 'rs', device='cpu')
         gdata, (ga, gb) = parallel.read_sharded(gfh, gather=True)
         ok = ok and np.array_equal(gdata.numpy(), gwant)
+        # the packed-byte consumer: bins dealt out over the ranks, one
+        # all-reduce of the count tables (7 bins; with 5-set bins a single
+        # bin, so that ranks without bins take part too)
+        from baseband_b200 import levels, tasks
+        fh.seek(0)
+        single = tasks.state_counts(fh, 32000)
+        for per_bin in (32000, 5 * 32000):
+            fh.seek(0)
+            counts, (b0, b1) = parallel.state_counts_sharded(fh, per_bin)
+            nbin = 7 * 32000 // per_bin
+            ok = ok and (b0, b1) == parallel.shard_bounds(nbin, rank, world)
+            ok = ok and counts.shape == (nbin, 16, 4)
+            ok = ok and np.array_equal(
+                counts, single[:nbin * (per_bin // 32000)].reshape(
+                    nbin, -1, 16, 4).sum(1))
+            ok = ok and fh.tell() == nbin * per_bin
+        lv = levels.offset_binary(2)
+        ok = ok and all(np.array_equal(single[..., c], (want.reshape(
+            7, 32000, 16) == lv[c]).sum(1)) for c in range(4))
         results[rank] = (bool(ok), a, b)
     finally:
         dist.destroy_process_group()
