@@ -710,9 +710,9 @@ def measure_file_ingest(args, dev, rank, world):
     folder = '/dev/shm' if os.path.isdir('/dev/shm') else '/tmp'
     path = os.path.join(folder, 'bb_bench_{}_{}.vdif'.format(os.getpid(),
                                                              rank))
-    synthetic.vdif_stream(nset, NTHREAD, PAYLOAD, seed=41 + rank,
-                          thread_order=np.arange(NTHREAD)).tofile(path)
     try:
+        synthetic.vdif_stream(nset, NTHREAD, PAYLOAD, seed=41 + rank,
+                              thread_order=np.arange(NTHREAD)).tofile(path)
         fh = bb.vdif.open(path, 'rs', sample_rate=64e6, device=dev)
         best = None
         for rep in range(9):
@@ -732,7 +732,8 @@ def measure_file_ingest(args, dev, rank, world):
             del data
         fh.close()
     finally:
-        os.remove(path)
+        if os.path.exists(path):
+            os.remove(path)
     torch.cuda.empty_cache()
     return {'packed_gbs_per_gpu': nset * SET_BYTES / best / 1e9,
             'gsamples_s': nset * SET_SAMPLES * world / best / 1e9,
